@@ -1,0 +1,78 @@
+// Shared device/host helpers for the diffsheg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace dsheg {
+
+typedef __nv_bfloat16 bf16;
+
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+
+// ---- activation-type traits: float (fp32 mode) or bf16 (bf16 mode) -------------------------
+template <typename T> struct AT;
+template <> struct AT<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct AT<bf16> {
+  static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// exact-erf GELU (nn.GELU() default, reference transformer.py:174,440)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_SILU) return silu_f(v);
+  if (act == ACT_GELU) return gelu_f(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- virtual-concat GEMM operand description ------------------------------------------------
+// A is the column-wise concatenation of up to 4 row-major segments; segment s covers K columns
+// [kpad_off[s], kpad_off[s] + k[s]) of W, whose K axis lays every segment out padded to 64.
+struct Seg {
+  const void* ptr;
+  int ld;  // elements
+  int k;   // true width
+};
+
+struct GemmDesc {
+  Seg a[4];
+  int nseg = 0;
+  int M = 0, N = 0;
+  const void* w = nullptr;  // [N, Kp] row-major, Kp = sum over segments of round_up(k, 64)
+  int Kp = 0;
+  const float* bias = nullptr;   // [N]
+  const float* csum = nullptr;   // [N]  LayerNorm fold: out = rstd*(acc - mu*csum) + bias
+  const float* mu = nullptr;     // [M]
+  const float* rstd = nullptr;   // [M]
+  int act = ACT_NONE;
+  const void* res = nullptr;  // residual, activation type (or fp32 when res_f32), added after act
+  int ldr = 0;
+  int res_mod = 0;   // residual row = m % res_mod when > 0 (positional-encoding add)
+  int res_f32 = 0;
+  void* out = nullptr;
+  int ldo = 0;
+  int out_f32 = 0;   // store fp32 instead of the activation type
+  void* out2 = nullptr;  // optional duplicate store (same ld / type as out)
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace dsheg

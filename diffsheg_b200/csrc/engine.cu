@@ -1,0 +1,744 @@
+// diffsheg_b200 engine: handle, packed weights, workspace and the per-step launch graph of the
+// UniDiffuser denoiser (reference models/transformer.py:728-770) behind the C ABI of
+// include/diffsheg_b200.h.  All device work is enqueued on the caller's stream; no host syncs.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/diffsheg_b200.h"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "sampler.cuh"
+
+using namespace dsheg;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevTensor {
+  void* ptr = nullptr;
+  int dtype = 0;
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+};
+
+struct LinW {
+  const void* w = nullptr;
+  const float* b = nullptr;
+  const float* csum = nullptr;
+  int N = 0, Kp = 0;
+};
+struct LayerW {
+  LinW feat1, feat2, qkv, sa_out, ffn1, ffn2, ffn_out;
+  const float* nullc = nullptr;
+  const float *sa_g = nullptr, *sa_b = nullptr, *ffn_g = nullptr, *ffn_b = nullptr;
+  bool has_feat = false;
+};
+struct MlpW { const float *w0, *b0, *w2, *b2; };
+struct NetW {
+  MlpW te{}, pid{};
+  const float *hub_w0 = nullptr, *hub_b0 = nullptr, *hub_w3 = nullptr;
+  const float* pe = nullptr;
+  LinW ss, joint, audproj, out;
+  std::vector<LayerW> layers;
+  int feats = 0, x_off = 0, kin = 0;
+};
+
+}  // namespace
+
+struct dsheg_handle {
+  dsheg_config cfg{};
+  int device = 0, num_sms = 148;
+  std::string err;
+  std::unordered_map<std::string, DevTensor> tensors;
+  bool finalized = false;
+  int gemm_engine = 1;  // 1 = tcgen05 (bf16 mode default), 0 = SIMT
+  int64_t launches = 0;
+  // resolved weights
+  const float* freqs = nullptr;
+  MlpW te_aud{};
+  const float *ssa_w = nullptr, *ssa_b = nullptr;
+  LayerW aud;
+  NetW net[2];  // 0 = expression, 1 = gesture
+  // workspace
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  void *H, *QKV, *Z, *Y, *F1, *XF, *HUB[2], *EXPR, *AUD256, *A0, *A1, *XIN, *EMBS[2];
+  float *Y32, *O, *MID, *MU, *RSTD, *MU2, *RSTD2, *SIN, *TEH, *TEMB, *SSA, *PIDH, *PIDE[2], *SS[2];
+  int ldE = 0, ldXin = 0, ldO = 0;
+  // window state
+  int B = 0, T = 0;
+  bool window_ready = false;
+  // optional per-kernel-class timing (bench.py's roofline pass): CUDA events around each launch
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t e0, e1; int cat; double work; };
+  std::vector<ProfRec> prof;
+};
+
+namespace {
+
+inline int esz(const dsheg_handle* h) { return h->cfg.precision == DSHEG_PREC_BF16 ? 2 : 4; }
+
+#define CK(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      h->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                            \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                    \
+  do {                                                                                        \
+    h->launches++;                                                                            \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      h->err = std::string("launch ") + name + ": " + cudaGetErrorString(_e);                 \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+int fail(dsheg_handle* h, const std::string& msg) {
+  h->err = msg;
+  return 1;
+}
+
+// categories: 0 = GEMM (work = FLOPs), 1 = attention (work = algorithmic bytes), 2 = row-wise LN/stat kernels (bytes)
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROW = 2, PROF_NCAT = 3 };
+inline void prof_begin(dsheg_handle* h, cudaStream_t st, int cat, double work) {
+  if (!h->profiling) return;
+  dsheg_handle::ProfRec r;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  r.cat = cat;
+  r.work = work;
+  cudaEventRecord(r.e0, st);
+  h->prof.push_back(r);
+}
+inline void prof_end(dsheg_handle* h, cudaStream_t st) {
+  if (!h->profiling) return;
+  cudaEventRecord(h->prof.back().e1, st);
+}
+
+// ---- weight resolution ---------------------------------------------------------------------
+struct Resolver {
+  dsheg_handle* h;
+  bool ok = true;
+  const DevTensor* get(const std::string& key, int dtype, std::vector<int64_t> shape) {
+    auto it = h->tensors.find(key);
+    if (it == h->tensors.end()) {
+      if (ok) h->err = "missing packed tensor '" + key + "'";
+      ok = false;
+      return nullptr;
+    }
+    const DevTensor& t = it->second;
+    if (t.dtype != dtype || t.shape != shape) {
+      if (ok) {
+        std::string s = "packed tensor '" + key + "' has wrong dtype/shape: got dtype " + std::to_string(t.dtype) + " [";
+        for (auto d : t.shape) s += std::to_string(d) + ",";
+        s += "] expected dtype " + std::to_string(dtype) + " [";
+        for (auto d : shape) s += std::to_string(d) + ",";
+        h->err = s + "]";
+      }
+      ok = false;
+      return nullptr;
+    }
+    return &t;
+  }
+  const float* f32(const std::string& key, std::vector<int64_t> shape) {
+    const DevTensor* t = get(key, DSHEG_DTYPE_F32, shape);
+    return t ? reinterpret_cast<const float*>(t->ptr) : nullptr;
+  }
+  LinW lin(const std::string& name, int N, int Kp, bool csum) {
+    LinW l;
+    const int wdt = h->cfg.precision == DSHEG_PREC_BF16 ? DSHEG_DTYPE_BF16 : DSHEG_DTYPE_F32;
+    const DevTensor* t = get(name + ".w", wdt, {N, Kp});
+    l.w = t ? t->ptr : nullptr;
+    l.b = f32(name + ".b", {N});
+    if (csum) l.csum = f32(name + ".csum", {N});
+    l.N = N;
+    l.Kp = Kp;
+    return l;
+  }
+  MlpW mlp(const std::string& name, int E, int Kin) {
+    MlpW m;
+    m.w0 = f32(name + ".w0", {E, Kin});
+    m.b0 = f32(name + ".b0", {E});
+    m.w2 = f32(name + ".w2", {E, E});
+    m.b2 = f32(name + ".b2", {E});
+    return m;
+  }
+  LayerW layer(const std::string& p, int D, int F, int featKp, bool has_null) {
+    LayerW L;
+    L.has_feat = featKp > 0;
+    if (L.has_feat) {
+      L.feat1 = lin(p + ".feat1", 2 * D, featKp, true);
+      L.feat2 = lin(p + ".feat2", D, 2 * D, false);
+      if (has_null) L.nullc = f32(p + ".nullc", {D});
+    }
+    L.qkv = lin(p + ".qkv", 3 * D, round_up(D, 64), true);
+    L.sa_g = f32(p + ".sa.g", {D});
+    L.sa_b = f32(p + ".sa.b", {D});
+    L.sa_out = lin(p + ".sa_out", D, round_up(D, 64), false);
+    L.ffn1 = lin(p + ".ffn1", F, round_up(D, 64), false);
+    L.ffn2 = lin(p + ".ffn2", D, round_up(F, 64), false);
+    L.ffn_g = f32(p + ".ffn.g", {D});
+    L.ffn_b = f32(p + ".ffn.b", {D});
+    L.ffn_out = lin(p + ".ffn_out", D, round_up(D, 64), false);
+    return L;
+  }
+};
+
+// ---- the per-step graph, templated on the activation / weight element type -------------------
+template <typename TA, typename TW>
+struct Runner {
+  dsheg_handle* h;
+  cudaStream_t st;
+
+  int gemm(GemmDesc& d, const LinW& l, const char* name) {
+    d.w = l.w; d.N = l.N; d.Kp = l.Kp; d.bias = l.b;
+    cudaError_t e;
+    double ktrue = 0;
+    for (int s = 0; s < d.nseg; ++s) ktrue += d.a[s].k;
+    prof_begin(h, st, PROF_GEMM, 2.0 * d.M * (double)d.N * ktrue);
+    if (std::is_same<TA, bf16>::value && h->gemm_engine == 1) {
+      std::string terr;
+      e = tc::launch_gemm_tc(d, h->num_sms, st, &terr);
+      if (e != cudaSuccess && !terr.empty()) return fail(h, std::string("gemm ") + name + ": " + terr);
+    } else {
+      e = launch_gemm_simt<TA, TW>(d, st);
+    }
+    prof_end(h, st);
+    h->launches++;
+    if (e != cudaSuccess) return fail(h, std::string("gemm ") + name + ": " + cudaGetErrorString(e));
+    return 0;
+  }
+
+  static Seg seg(const void* p, int ld, int k) { Seg s; s.ptr = p; s.ld = ld; s.k = k; return s; }
+
+  // One LinearTemporalDiffusionTransformerLayer (tr:300-346) on `rows` hidden rows of width D.
+  //   hin/hout: residual stream in / out (may alias);  n_uncond: leading CFG-null rows
+  int layer(const LayerW& L, TA* hin, int ld_hin, TA* hmid, TA* hout, int ld_hout, int rows, int n_uncond, int D, int F,
+            int H, const Seg* extra, int n_extra, const float* ss, int ss_ld, int ssB, int T) {
+    const int warps_per_block = 8;
+    TA* hcur = hin;
+    int ldc = ld_hin;
+    if (L.has_feat) {
+      // K7: LayerNorm(P) stats over the virtual concat + null-row constant for the uncond half
+      const int n_cond = rows - n_uncond;
+      Seg e3[3] = {seg(nullptr, 0, 0), seg(nullptr, 0, 0), seg(nullptr, 0, 0)};
+      for (int i = 0; i < n_extra; ++i) e3[i] = extra[i];
+      feat_prep_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+          hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
+      LAUNCH_CHECK("feat_prep");
+      TA* hc = hin + (size_t)n_uncond * ld_hin;
+      GemmDesc g1;
+      g1.a[0] = seg(hc, ld_hin, D);
+      for (int i = 0; i < n_extra; ++i) g1.a[1 + i] = extra[i];
+      g1.nseg = 1 + n_extra; g1.M = n_cond;
+      g1.csum = L.feat1.csum; g1.mu = h->MU; g1.rstd = h->RSTD; g1.act = ACT_SILU;
+      g1.out = h->F1; g1.ldo = 2 * D;
+      if (gemm(g1, L.feat1, "feat1")) return 1;
+      GemmDesc g2;
+      g2.a[0] = seg(h->F1, 2 * D, 2 * D); g2.nseg = 1; g2.M = n_cond;
+      g2.res = hc; g2.ldr = ld_hin; g2.out = hc; g2.ldo = ld_hin;  // cond_residual (tr:337-338), in place
+      if (gemm(g2, L.feat2, "feat2")) return 1;
+    }
+    // K8: LayerNorm(D) folded into the fused QKV projection
+    prof_begin(h, st, PROF_ROW, (double)rows * D * sizeof(TA));
+    rowstats_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(hcur, ldc, D, rows, h->MU2, h->RSTD2);
+    prof_end(h, st);
+    LAUNCH_CHECK("rowstats");
+    GemmDesc gq;
+    gq.a[0] = seg(hcur, ldc, D); gq.nseg = 1; gq.M = rows;
+    gq.csum = L.qkv.csum; gq.mu = h->MU2; gq.rstd = h->RSTD2;
+    gq.out = h->QKV; gq.ldo = 3 * D;
+    if (gemm(gq, L.qkv, "qkv")) return 1;
+    // K9 + K10 prologue: linear attention, then LN * (1+scale) + shift, SiLU
+    const int n_samples = rows / T;
+    const int HD = D / H;
+    // algorithmic traffic: read q,k,v + write z, all in the activation type (4*rows*D*sizeof)
+    prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
+    if (HD == 64) {
+      attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
+                                                                          L.sa_g, L.sa_b, ss, ss_ld);
+    } else if (HD == 16) {
+      attn_kernel<TA, 16><<<n_samples, 256, attn_smem_bytes<16>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
+                                                                          L.sa_g, L.sa_b, ss, ss_ld);
+    } else {
+      return fail(h, "unsupported head dim");
+    }
+    prof_end(h, st);
+    LAUNCH_CHECK("attn");
+    GemmDesc go;
+    go.a[0] = seg(h->Z, D, D); go.nseg = 1; go.M = rows;
+    go.res = hcur; go.ldr = ldc; go.out = hmid; go.ldo = D;
+    if (gemm(go, L.sa_out, "sa_out")) return 1;
+    // K11: FFN
+    GemmDesc f1;
+    f1.a[0] = seg(hmid, D, D); f1.nseg = 1; f1.M = rows; f1.act = ACT_GELU; f1.out = h->F1; f1.ldo = F;
+    if (gemm(f1, L.ffn1, "ffn1")) return 1;
+    GemmDesc f2;
+    f2.a[0] = seg(h->F1, F, F); f2.nseg = 1; f2.M = rows; f2.out = h->Y; f2.ldo = D;
+    if (gemm(f2, L.ffn2, "ffn2")) return 1;
+    prof_begin(h, st, PROF_ROW, 2.0 * rows * D * sizeof(TA));
+    ln_mod_silu_kernel<TA, TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+        (const TA*)h->Y, D, (TA*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
+    prof_end(h, st);
+    LAUNCH_CHECK("ln_mod_silu");
+    GemmDesc fo;
+    fo.a[0] = seg(h->Z, D, D); fo.nseg = 1; fo.M = rows;
+    fo.res = hmid; fo.ldr = D; fo.out = hout; fo.ldo = ld_hout;
+    if (gemm(fo, L.ffn_out, "ffn_out")) return 1;
+    return 0;
+  }
+
+  int prepare_window(const float* mel, const float* hubert, const float* pid, int B, int T) {
+    const dsheg_config& c = h->cfg;
+    const int R1 = B * T, E = 4 * c.latent_dim, A = c.audio_dim;
+    {
+      const size_t n = (size_t)R1 * A;
+      mel_stage_kernel<TA><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mel, A, (TA*)h->AUD256, 2 * A, (TA*)h->A0, R1);
+      LAUNCH_CHECK("mel_stage");
+    }
+    const int tiles = (T + HC_TR - 1) / HC_TR;
+    for (int n = 0; n < 2; ++n) {
+      const NetW& nw = h->net[n];
+      // K4: hubert_encoder (BN folded into conv 0)
+      hubconv_kernel<float><<<B * tiles, HC_CO, (HC_TR + 2) * c.hubert_dim * sizeof(float), st>>>(
+          hubert, c.hubert_dim, nw.hub_w0, nw.hub_b0, ACT_GELU, h->MID, HC_CO, T, tiles);
+      LAUNCH_CHECK("hubconv0");
+      hubconv_kernel<TA><<<B * tiles, HC_CO, (HC_TR + 2) * HC_CO * sizeof(float), st>>>(
+          h->MID, HC_CO, nw.hub_w3, nullptr, ACT_NONE, (TA*)h->HUB[n], HC_CO, T, tiles);
+      LAUNCH_CHECK("hubconv3");
+      // K2: pid_embed MLP (fp32 SIMT GEMMs, once per window)
+      GemmDesc p0;
+      p0.a[0] = seg(pid, c.style_dim, c.style_dim); p0.nseg = 1; p0.M = B; p0.N = E; p0.Kp = round_up(c.style_dim, 64);
+      p0.w = nw.pid.w0; p0.bias = nw.pid.b0; p0.act = ACT_SILU; p0.out = h->PIDH; p0.ldo = E; p0.out_f32 = 1;
+      if (launch_gemm_simt<float, float>(p0, st) != cudaSuccess) return fail(h, "pid_embed.0 launch failed");
+      h->launches++;
+      GemmDesc p2;
+      p2.a[0] = seg(h->PIDH, E, E); p2.nseg = 1; p2.M = B; p2.N = E; p2.Kp = E;
+      p2.w = nw.pid.w2; p2.bias = nw.pid.b2; p2.out = h->PIDE[n]; p2.ldo = E; p2.out_f32 = 1;
+      if (launch_gemm_simt<float, float>(p2, st) != cudaSuccess) return fail(h, "pid_embed.2 launch failed");
+      h->launches++;
+    }
+    return 0;
+  }
+
+  int denoise(const float* x, int t_orig, float a, float b, float cond_scale, float* eps_out) {
+    const dsheg_config& c = h->cfg;
+    const int B = h->B, T = h->T, R1 = B * T, D = c.latent_dim, E = 4 * D, F = c.ff_size, A = c.audio_dim;
+    const int L = c.num_layers, Dtot = c.dim_pose + c.expression_dim;
+    const bool two = c.classifier_free && cond_scale != 1.0f;  // tr:537
+    const int G = two ? 2 : 1, R = G * R1;
+    // ---- K1: timestep embeddings of the three nets (rows are identical: t = [i]*B, gd:1196)
+    sinus_kernel<<<1, 256, 0, st>>>((float)t_orig, h->freqs, D / 2, h->SIN);
+    LAUNCH_CHECK("sinus");
+    {
+      GemvBatch g0, g2;
+      const MlpW* tes[3] = {&h->te_aud, &h->net[0].te, &h->net[1].te};
+      for (int i = 0; i < 3; ++i) {
+        g0.p[i] = {h->SIN, tes[i]->w0, tes[i]->b0, h->TEH + i * E};
+        g2.p[i] = {h->TEH + i * E, tes[i]->w2, tes[i]->b2, h->TEMB + i * E};
+      }
+      gemv_kernel<<<dim3((E + 7) / 8, 3), 256, 0, st>>>(g0, E, D, ACT_SILU, 0);
+      LAUNCH_CHECK("time_embed.0");
+      gemv_kernel<<<dim3((E + 7) / 8, 3), 256, 0, st>>>(g2, E, E, ACT_NONE, 0);
+      LAUNCH_CHECK("time_embed.2");
+      // K3 (audio layer): both StylizationBlocks' emb_layers, one row
+      GemvBatch ga;
+      ga.p[0] = {h->TEMB, h->ssa_w, h->ssa_b, h->SSA};
+      ga.p[1] = ga.p[0]; ga.p[2] = ga.p[0];
+      gemv_kernel<<<dim3((4 * A + 7) / 8, 1), 256, 0, st>>>(ga, 4 * A, E, ACT_NONE, 1);
+      LAUNCH_CHECK("aud_ss");
+    }
+    // ---- K3: scale/shift of all 2L StylizationBlocks per net, one GEMM [B,2048] x [2048, 2L*2D]
+    for (int n = 0; n < 2; ++n) {
+      const size_t ne = (size_t)B * E;
+      embs_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->TEMB + (1 + n) * E, h->PIDE[n], (TA*)h->EMBS[n], B, E);
+      LAUNCH_CHECK("embs");
+      GemmDesc g;
+      g.a[0] = seg(h->EMBS[n], E, E); g.nseg = 1; g.M = B; g.out = h->SS[n]; g.ldo = L * 4 * D; g.out_f32 = 1;
+      if (gemm(g, h->net[n].ss, "ss")) return 1;
+    }
+    // ---- K5: encoder_aud (D=128, 8 heads of 16) on 2*mel, result into AUD256[:, A:2A]
+    if (layer(h->aud, (TA*)h->A0, A, (TA*)h->A1, (TA*)h->AUD256 + A, 2 * A, R1, 0, A, F, c.num_heads, nullptr, 0, h->SSA, 4 * A, 1, T))
+      return 1;
+    // ---- the two MotionTransformers, expression first (tr:741-763)
+    for (int n = 0; n < 2; ++n) {
+      const NetW& nw = h->net[n];
+      GemmDesc gx;  // K6: audio_proj
+      gx.a[0] = seg(h->AUD256, 2 * A, 2 * A); gx.nseg = 1; gx.M = R1; gx.out = h->XF; gx.ldo = c.aud_latent_dim;
+      if (gemm(gx, nw.audproj, "audio_proj")) return 1;
+      {
+        const size_t ne = (size_t)R1 * h->ldXin;
+        cast_pad_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(x, Dtot, nw.x_off, nw.feats, (TA*)h->XIN, h->ldXin, R1);
+        LAUNCH_CHECK("cast_pad");
+      }
+      TA* Hu = (TA*)h->H;
+      TA* Hc = Hu + (size_t)(two ? R1 : 0) * D;
+      GemmDesc gj;  // K6: joint_embed + PE, written to both CFG halves (they start identical, tr:538)
+      gj.a[0] = seg(h->XIN, h->ldXin, nw.feats); gj.nseg = 1; gj.M = R1;
+      gj.res = nw.pe; gj.ldr = D; gj.res_mod = T; gj.res_f32 = 1;
+      gj.out = Hc; gj.ldo = D; gj.out2 = two ? Hu : nullptr;
+      if (gemm(gj, nw.joint, "joint_embed")) return 1;
+      Seg extra[3];
+      int n_extra = 0;
+      extra[n_extra++] = seg(h->XF, c.aud_latent_dim, c.aud_latent_dim);
+      extra[n_extra++] = seg(h->HUB[n], HC_CO, HC_CO);
+      if (n == 1) extra[n_extra++] = seg(h->EXPR, h->ldE, c.expression_dim);  // tr:506-507,533-535
+      for (int l = 0; l < L; ++l) {
+        if (layer(nw.layers[l], Hu, D, Hu, Hu, D, R, two ? R1 : 0, D, F, c.num_heads, extra, n_extra,
+                  h->SS[n] + (size_t)l * 4 * D, L * 4 * D, B, T))
+          return 1;
+      }
+      GemmDesc go;  // K12: out projection (fp32 result)
+      go.a[0] = seg(Hu, D, D); go.nseg = 1; go.M = R; go.out = h->O; go.ldo = h->ldO; go.out_f32 = 1;
+      if (gemm(go, nw.out, "out")) return 1;
+      {
+        const int wcols = (n == 0) ? h->ldE : nw.feats;
+        const size_t ne = (size_t)R1 * wcols;
+        cfg_mix_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->O, h->ldO, R1, nw.feats, two ? 1 : 0, cond_scale, eps_out,
+                                                                          x, Dtot, nw.x_off, a, b, n == 0 ? (TA*)h->EXPR : nullptr,
+                                                                          h->ldE);
+        LAUNCH_CHECK("cfg_mix");
+      }
+    }
+    return 0;
+  }
+};
+
+template <typename F>
+int with_runner(dsheg_handle* h, cudaStream_t st, F&& f) {
+  if (h->cfg.precision == DSHEG_PREC_BF16) {
+    Runner<bf16, bf16> r{h, st};
+    return f(r);
+  }
+  Runner<float, float> r{h, st};
+  return f(r);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* dsheg_last_error(const dsheg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+  if (cfg->abi_version != DSHEG_ABI_VERSION) { g_create_error = "ABI version mismatch"; return 1; }
+  if (cfg->latent_dim % 64 || cfg->audio_dim % 64 || cfg->latent_dim / cfg->num_heads != 64 ||
+      cfg->audio_dim / cfg->num_heads != 16 || cfg->latent_dim > 32 * LMS_MAXV || cfg->ff_size % 64 ||
+      cfg->aud_latent_dim != 2 * cfg->audio_dim || cfg->max_batch < 1 || cfg->max_frames < 2) {
+    g_create_error = "unsupported configuration (need latent 512 / 8 heads of 64, audio 128 / 8 heads of 16)";
+    return 1;
+  }
+  if (cfg->precision != DSHEG_PREC_FP32 && cfg->precision != DSHEG_PREC_BF16) { g_create_error = "bad precision"; return 1; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return 1; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); return 1; }
+  if (prop.major != 10) {
+    g_create_error = "diffsheg_b200 requires an sm_100a (B200) device, found sm_" + std::to_string(prop.major * 10 + prop.minor);
+    return 1;
+  }
+  dsheg_handle* h = new dsheg_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->gemm_engine = 1;
+  const char* eng = getenv("DSHEG_GEMM_ENGINE");
+  if (eng && !strcmp(eng, "simt")) h->gemm_engine = 0;
+
+  const dsheg_config& c = h->cfg;
+  const size_t G = c.classifier_free ? 2 : 1;
+  const size_t R1 = (size_t)c.max_batch * c.max_frames, R = G * R1;
+  const size_t D = c.latent_dim, E = 4 * D, F = c.ff_size, A = c.audio_dim, L = c.num_layers;
+  const size_t es = esz(h);
+  h->ldE = round_up(c.expression_dim, 64);
+  h->ldXin = round_up(c.dim_pose > c.expression_dim ? c.dim_pose : c.expression_dim, 64);
+  h->ldO = round_up(c.dim_pose > c.expression_dim ? c.dim_pose : c.expression_dim, 4);
+  struct Req { void** p; size_t bytes; };
+  std::vector<Req> reqs = {
+      {&h->H, R * D * es}, {&h->QKV, R * 3 * D * es}, {&h->Z, R * D * es}, {&h->Y, R * D * es}, {&h->F1, R * (F > 2 * D ? F : 2 * D) * es},
+      {&h->XF, R1 * c.aud_latent_dim * es}, {&h->HUB[0], R1 * HC_CO * es}, {&h->HUB[1], R1 * HC_CO * es},
+      {&h->EXPR, R1 * h->ldE * es}, {&h->AUD256, R1 * 2 * A * es}, {&h->A0, R1 * A * es}, {&h->A1, R1 * A * es},
+      {&h->XIN, R1 * h->ldXin * es}, {&h->EMBS[0], (size_t)c.max_batch * E * es}, {&h->EMBS[1], (size_t)c.max_batch * E * es},
+      {(void**)&h->Y32, R * D * 4}, {(void**)&h->O, R * h->ldO * 4}, {(void**)&h->MID, R1 * HC_CO * 4},
+      {(void**)&h->MU, R * 4}, {(void**)&h->RSTD, R * 4}, {(void**)&h->MU2, R * 4}, {(void**)&h->RSTD2, R * 4},
+      {(void**)&h->SIN, D * 4}, {(void**)&h->TEH, 3 * E * 4}, {(void**)&h->TEMB, 3 * E * 4}, {(void**)&h->SSA, 4 * A * 4},
+      {(void**)&h->PIDH, (size_t)c.max_batch * E * 4}, {(void**)&h->PIDE[0], (size_t)c.max_batch * E * 4},
+      {(void**)&h->PIDE[1], (size_t)c.max_batch * E * 4}, {(void**)&h->SS[0], (size_t)c.max_batch * L * 4 * D * 4},
+      {(void**)&h->SS[1], (size_t)c.max_batch * L * 4 * D * 4},
+  };
+  size_t total = 0;
+  for (auto& r : reqs) total += (r.bytes + 1023) / 1024 * 1024;
+  e = cudaMalloc(&h->arena, total);
+  if (e != cudaSuccess) {
+    g_create_error = "workspace cudaMalloc of " + std::to_string(total >> 20) + " MiB failed: " + cudaGetErrorString(e);
+    delete h;
+    return 1;
+  }
+  h->arena_bytes = total;
+  cudaMemset(h->arena, 0, total);
+  size_t off = 0;
+  for (auto& r : reqs) { *r.p = (char*)h->arena + off; off += (r.bytes + 1023) / 1024 * 1024; }
+  // kernels that need > 48 KB dynamic shared memory
+  const int attn64 = (int)attn_smem_bytes<64>(c.max_frames), attn16 = (int)attn_smem_bytes<16>(c.max_frames);
+  if (attn64 > 227 * 1024) { g_create_error = "max_frames too large for the attention kernel"; cudaFree(h->arena); delete h; return 1; }
+  cudaFuncSetAttribute(attn_kernel<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn64);
+  cudaFuncSetAttribute(attn_kernel<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn64);
+  cudaFuncSetAttribute(attn_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
+  cudaFuncSetAttribute(attn_kernel<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
+  cudaFuncSetAttribute(hubconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
+  cudaFuncSetAttribute(hubconv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaFree(h->arena); delete h; return 1; }
+  *out = h;
+  return 0;
+}
+
+void dsheg_destroy(dsheg_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->tensors) cudaFree(kv.second.ptr);
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+}
+
+int dsheg_load_tensor(dsheg_handle* h, const char* key, const void* host_data, int32_t dtype, const int64_t* shape, int32_t ndim) {
+  if (!h || !key || !host_data) return 1;
+  if (dtype != DSHEG_DTYPE_F32 && dtype != DSHEG_DTYPE_BF16) return fail(h, "bad dtype");
+  CK(cudaSetDevice(h->device));
+  DevTensor t;
+  t.dtype = dtype;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
+  const size_t bytes = t.numel * (dtype == DSHEG_DTYPE_F32 ? 4 : 2);
+  CK(cudaMalloc(&t.ptr, bytes ? bytes : 16));
+  CK(cudaMemcpy(t.ptr, host_data, bytes, cudaMemcpyHostToDevice));
+  auto it = h->tensors.find(key);
+  if (it != h->tensors.end()) { cudaFree(it->second.ptr); h->tensors.erase(it); }
+  h->tensors[key] = t;
+  h->finalized = false;
+  return 0;
+}
+
+int dsheg_finalize_weights(dsheg_handle* h) {
+  if (!h) return 1;
+  const dsheg_config& c = h->cfg;
+  const int D = c.latent_dim, E = 4 * D, F = c.ff_size, A = c.audio_dim, L = c.num_layers;
+  Resolver r{h};
+  h->freqs = r.f32("freqs", {D / 2});
+  h->te_aud = r.mlp("aud.te", E, D);
+  h->ssa_w = r.f32("aud.ss.w", {4 * A, E});
+  h->ssa_b = r.f32("aud.ss.b", {4 * A});
+  h->aud = r.layer("aud.l0", A, F, 0, false);
+  const char* names[2] = {"exp", "ges"};
+  for (int n = 0; n < 2; ++n) {
+    NetW& nw = h->net[n];
+    const std::string p = names[n];
+    nw.feats = n == 0 ? c.expression_dim : c.dim_pose;
+    nw.x_off = n == 0 ? c.dim_pose : 0;  // x = cat(gesture, expression), tr:741
+    nw.te = r.mlp(p + ".te", E, D);
+    nw.pid = r.mlp(p + ".pid", E, round_up(c.style_dim, 64));
+    nw.hub_w0 = r.f32(p + ".hub.w0", {3, c.hubert_dim, HC_CO});
+    nw.hub_b0 = r.f32(p + ".hub.b0", {HC_CO});
+    nw.hub_w3 = r.f32(p + ".hub.w3", {3, HC_CO, HC_CO});
+    nw.pe = r.f32(p + ".pe", {c.max_frames, D});
+    nw.ss = r.lin(p + ".ss", L * 4 * D, E, false);
+    nw.joint = r.lin(p + ".joint", D, round_up(nw.feats, 64), false);
+    nw.audproj = r.lin(p + ".audproj", c.aud_latent_dim, 2 * A, false);
+    nw.out = r.lin(p + ".out", nw.feats, D, false);
+    const int featKp = D + c.aud_latent_dim + HC_CO + (n == 1 ? round_up(c.expression_dim, 64) : 0);
+    nw.layers.clear();
+    for (int l = 0; l < L; ++l) nw.layers.push_back(r.layer(p + ".l" + std::to_string(l), D, F, featKp, c.classifier_free != 0));
+  }
+  if (!r.ok) return 1;
+  h->finalized = true;
+  return 0;
+}
+
+int dsheg_prepare_window(dsheg_handle* h, const float* mel, const float* hubert, const float* person_id, int32_t B, int32_t T,
+                         void* stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "weights not finalized");
+  if (B < 1 || B > h->cfg.max_batch || T < 2 || T > h->cfg.max_frames) return fail(h, "window shape exceeds the workspace (max_batch/max_frames)");
+  CK(cudaSetDevice(h->device));
+  h->B = B; h->T = T;
+  int rc = with_runner(h, (cudaStream_t)stream, [&](auto& r) { return r.prepare_window(mel, hubert, person_id, B, T); });
+  h->window_ready = rc == 0;
+  return rc;
+}
+
+int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, float b, float cond_scale, float* eps_out, void* stream) {
+  if (!h) return 1;
+  if (!h->window_ready) return fail(h, "dsheg_prepare_window has not been called");
+  return with_runner(h, (cudaStream_t)stream, [&](auto& r) { return r.denoise(x, t_orig, a, b, cond_scale, eps_out); });
+}
+
+int64_t dsheg_launch_count(const dsheg_handle* h) { return h ? h->launches : 0; }
+
+int dsheg_profile_begin(dsheg_handle* h) {
+  if (!h) return 1;
+  h->prof.clear();
+  h->profiling = true;
+  return 0;
+}
+
+int dsheg_profile_end(dsheg_handle* h, double* ms, double* work, int64_t* count) {
+  if (!h || !ms || !work || !count) return 1;
+  h->profiling = false;
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; work[c] = 0; count[c] = 0; }
+  for (auto& r : h->prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms[r.cat] += t; work[r.cat] += r.work; count[r.cat] += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  h->prof.clear();
+  return 0;
+}
+
+// ---- stateless sampler steps ---------------------------------------------------------------
+static std::string g_step_error;
+static int step_done(const char* name) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string(name) + ": " + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, int32_t T, int32_t D, float sqrt_recip_ac,
+                    float sqrt_recipm1_ac, float sqrt_ac_prev, float sqrt_one_minus_ac_prev, const float* gt,
+                    const uint8_t* mask, const float* noise2, int32_t blend, int32_t overlap_len, float* pred_xstart_out,
+                    void* stream) {
+  if (!x || !eps || !x_out || n <= 0 || (mask && (!gt || !noise2))) { g_create_error = "dsheg_ddim_step: bad arguments"; return 1; }
+  DdimArgs p;
+  p.x = x; p.eps = eps; p.x_out = x_out; p.pred_out = pred_xstart_out; p.n = n; p.T = T; p.D = D;
+  p.a = sqrt_recip_ac; p.b = sqrt_recipm1_ac; p.sqrt_acp = sqrt_ac_prev; p.sqrt_1m_acp = sqrt_one_minus_ac_prev;
+  p.gt = gt; p.mask = mask; p.noise2 = noise2; p.blend = blend; p.overlap_len = overlap_len;
+  ddim_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p);
+  return step_done("dsheg_ddim_step");
+}
+
+int dsheg_undo_step(const float* x, const float* noise, float* x_out, int64_t n, float sqrt_one_minus_beta, float sqrt_beta,
+                    void* stream) {
+  if (!x || !noise || !x_out || n <= 0) { g_create_error = "dsheg_undo_step: bad arguments"; return 1; }
+  undo_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, noise, x_out, n, sqrt_one_minus_beta, sqrt_beta);
+  return step_done("dsheg_undo_step");
+}
+
+int dsheg_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, int64_t n, float sqrt_recip_ac,
+                    float sqrt_recipm1_ac, float coef1, float coef2, float sigma, float* pred_xstart_out, void* stream) {
+  if (!x || !eps || !noise || !x_out || n <= 0) { g_create_error = "dsheg_ddpm_step: bad arguments"; return 1; }
+  ddpm_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, x_out, pred_xstart_out, n, sqrt_recip_ac,
+                                                                 sqrt_recipm1_ac, coef1, coef2, sigma);
+  return step_done("dsheg_ddpm_step");
+}
+
+int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, const float* noise, float* x_out, int64_t n,
+                        float sqrt_ac, float sqrt_one_minus_ac, void* stream) {
+  if (!x || !gt || !mask || !noise || !x_out || n <= 0) { g_create_error = "dsheg_repaint_merge: bad arguments"; return 1; }
+  repaint_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, gt, mask, noise, x_out, n, sqrt_ac, sqrt_one_minus_ac);
+  return step_done("dsheg_repaint_merge");
+}
+
+// ---- op-level test entry points --------------------------------------------------------------
+namespace {
+__global__ void f32_to_bf16_pad_kernel(const float* in, int rows, int cols, bf16* out, int ld) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * ld) return;
+  const int r = (int)(i / ld), c = (int)(i % ld);
+  out[i] = __float2bfloat16_rn(c < cols ? in[(size_t)r * cols + c] : 0.f);
+}
+}  // namespace
+
+int dsheg_op_linear(int32_t precision, const float* A, const float* W, const float* bias, const float* residual, float* out,
+                    int32_t M, int32_t N, int32_t K, int32_t act, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmDesc d;
+  d.nseg = 1; d.M = M; d.N = N; d.bias = bias; d.act = act; d.out = out; d.ldo = N; d.out_f32 = 1;
+  const int Kp = round_up(K, 64);
+  if (precision == DSHEG_PREC_FP32) {
+    // the SIMT kernel reads W with row stride Kp: repack when K is not a multiple of 64
+    float* Wp = nullptr;
+    if (Kp != K) {
+      if (cudaMalloc(&Wp, (size_t)N * Kp * 4) != cudaSuccess) { g_create_error = "op_linear: cudaMalloc"; return 1; }
+      cudaMemsetAsync(Wp, 0, (size_t)N * Kp * 4, st);
+      cudaMemcpy2DAsync(Wp, (size_t)Kp * 4, W, (size_t)K * 4, (size_t)K * 4, N, cudaMemcpyDeviceToDevice, st);
+    }
+    d.a[0].ptr = A; d.a[0].ld = K; d.a[0].k = K; d.w = Wp ? Wp : W; d.Kp = Kp;
+    d.res = residual; d.ldr = N; d.res_f32 = 1;
+    cudaError_t e = launch_gemm_simt<float, float>(d, st);
+    cudaStreamSynchronize(st);
+    if (Wp) cudaFree(Wp);
+    if (e != cudaSuccess) { g_create_error = std::string("op_linear simt: ") + cudaGetErrorString(e); return 1; }
+    return step_done("dsheg_op_linear");
+  }
+  bf16 *Ab = nullptr, *Wb = nullptr;
+  if (cudaMalloc(&Ab, (size_t)M * Kp * 2) != cudaSuccess || cudaMalloc(&Wb, (size_t)N * Kp * 2) != cudaSuccess) {
+    g_create_error = "op_linear: cudaMalloc";
+    return 1;
+  }
+  f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)M * Kp + 255) / 256), 256, 0, st>>>(A, M, K, Ab, Kp);
+  f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)N * Kp + 255) / 256), 256, 0, st>>>(W, N, K, Wb, Kp);
+  d.a[0].ptr = Ab; d.a[0].ld = Kp; d.a[0].k = K; d.w = Wb; d.Kp = Kp;
+  d.res = residual; d.ldr = N; d.res_f32 = 1;
+  std::string terr;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* eng = getenv("DSHEG_GEMM_ENGINE");
+  cudaError_t e;
+  if (eng && !strcmp(eng, "simt")) e = launch_gemm_simt<bf16, bf16>(d, st);
+  else e = tc::launch_gemm_tc(d, sms, st, &terr);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(Ab);
+  cudaFree(Wb);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    g_create_error = "op_linear tc: " + terr + " " + cudaGetErrorString(e != cudaSuccess ? e : e2);
+    return 1;
+  }
+  return 0;
+}
+
+int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift, float* z, int32_t Bn,
+                       int32_t T, int32_t D, int32_t H, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* y32 = nullptr;
+  if (cudaMalloc(&y32, (size_t)Bn * T * D * 4) != cudaSuccess) { g_create_error = "op_attention: cudaMalloc"; return 1; }
+  const int HD = D / H;
+  if (HD == 64) {
+    cudaFuncSetAttribute(attn_kernel<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<64>(T));
+    attn_kernel<float, 64><<<Bn, 256, attn_smem_bytes<64>(T), st>>>(qkv, y32, z, T, D, H, Bn, ln_g, ln_b, scale_shift, 2 * D);
+  } else if (HD == 16) {
+    cudaFuncSetAttribute(attn_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>(T));
+    attn_kernel<float, 16><<<Bn, 256, attn_smem_bytes<16>(T), st>>>(qkv, y32, z, T, D, H, Bn, ln_g, ln_b, scale_shift, 2 * D);
+  } else {
+    cudaFree(y32);
+    g_create_error = "op_attention: head dim must be 16 or 64";
+    return 1;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(y32);
+  if (e != cudaSuccess) { g_create_error = std::string("op_attention: ") + cudaGetErrorString(e); return 1; }
+  return step_done("dsheg_op_attention");
+}
+
+}  // extern "C"

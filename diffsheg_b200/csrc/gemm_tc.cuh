@@ -1,0 +1,378 @@
+// tcgen05 (UMMA) bf16 GEMM for sm_100a:  out[M,N] = epilogue( A[M,K] . W[N,K]^T ), fp32 accumulate.
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a 6-stage smem ring
+//   * one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction), accumulators
+//     live in TMEM (2 x 128 columns, double-buffered so the epilogue of tile i overlaps the
+//     mainloop of tile i+1)
+//   * 4 epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
+//     fused epilogue: LayerNorm fold, bias, SiLU / GELU(erf), residual / positional add, bf16 or
+//     fp32 store (optionally duplicated for the two CFG halves)
+//   * persistent: one CTA per SM walks tiles n-fastest so concurrently running CTAs share the
+//     A row-panel through L2; W panels (<= 2 MB) stay L2-resident
+//   * A is a VIRTUAL CONCAT of up to 4 row-major segments (one tensor map each): the feat_proj
+//     input cat(h, audio, hubert, expr) (transformer.py:304-310) is never materialised.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (TMEM lane
+// quadrants 2,3,0,1).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dsheg {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_ACC = 2, TMEM_COLS = NUM_ACC * BN;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int UMMA_K = 16;
+
+struct Params {
+  int M, N, num_kb, nseg;
+  int seg_kb_start[5];
+  int tiles_m, tiles_n;
+  const float* bias; const float* csum; const float* mu; const float* rstd;
+  int act;
+  const void* res; int ldr, res_mod, res_f32;
+  void* out; int ldo, out_f32; void* out2;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    // watchdog: a lost arrive / wrong descriptor becomes a launch error after 4 s, not a hung GPU
+    if ((++spins & 0x3FFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile [rows][64 bf16] (8-row groups of 1024 B): SBO = 1024 B,
+// LBO unused, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                           // version = 1
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+               const __grid_constant__ CUtensorMap tmW, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: one full warp, which also owns the dealloc
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        int seg = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          while (kb >= p.seg_kb_start[seg + 1]) ++seg;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
+          tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
+          tma_load_2d(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);        // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (= UMMA_K bf16) inside the 128B swizzle atom: +2 in 16-byte units
+            tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
+          }
+          tc_commit(empty_bar(stage));              // frees the smem slot when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));                  // accumulator complete -> epilogue
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp % 4;  // TMEM lane quadrant this warp may touch
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      float mu = 0.f, rstd = 1.f;
+      if (p.csum && row_ok) { mu = p.mu[m]; rstd = p.rstd[m]; }
+      const int mr = p.res_mod > 0 ? m % p.res_mod : m;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        const int n0 = n_blk * BN + c * 32;
+        if (!row_ok || n0 >= p.N) continue;
+        const bool full = (n0 + 32 <= p.N);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + j;
+          float t = __uint_as_float(r[j]);
+          if (full || n < p.N) {
+            if (p.csum) t = rstd * (t - mu * __ldg(p.csum + n));
+            if (p.bias) t += __ldg(p.bias + n);
+            t = apply_act(t, p.act);
+          }
+          v[j] = t;
+        }
+        if (p.res) {
+          if (p.res_f32) {
+            const float* rp = reinterpret_cast<const float*>(p.res) + (size_t)mr * p.ldr + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) v[j] += rp[j];
+          } else if (full) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (size_t)mr * p.ldr + n0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 w = rp[u];
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
+                v[u * 8 + e * 2] += __bfloat162float(h2.x);
+                v[u * 8 + e * 2 + 1] += __bfloat162float(h2.y);
+              }
+            }
+          } else {
+            const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (size_t)mr * p.ldr + n0;
+            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        const size_t o = (size_t)m * p.ldo + n0;
+        if (p.out_f32) {
+          float* op = reinterpret_cast<float*>(p.out) + o;
+          float* op2 = p.out2 ? reinterpret_cast<float*>(p.out2) + o : nullptr;
+          if (full && (p.ldo % 4 == 0)) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 f = make_float4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
+              reinterpret_cast<float4*>(op)[u] = f;
+              if (op2) reinterpret_cast<float4*>(op2)[u] = f;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) { op[j] = v[j]; if (op2) op2[j] = v[j]; }
+          }
+        } else {
+          bf16* op = reinterpret_cast<bf16*>(p.out) + o;
+          bf16* op2 = p.out2 ? reinterpret_cast<bf16*>(p.out2) + o : nullptr;
+          if (full && (p.ldo % 8 == 0)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 w;
+              w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
+              w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
+              w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
+              w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
+              reinterpret_cast<uint4*>(op)[u] = w;
+              if (op2) reinterpret_cast<uint4*>(op2)[u] = w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) { op[j] = __float2bfloat16_rn(v[j]); if (op2) op2[j] = __float2bfloat16_rn(v[j]); }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle,
+// out-of-bounds elements read as zero (ragged M / N / K tails need no padding in memory).
+inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) { *err = "TMA operand not 16-byte aligned"; return false; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r); return false; }
+  return true;
+}
+
+inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  Params p{};
+  CUtensorMap maps[5];
+  p.M = d.M; p.N = d.N; p.nseg = d.nseg;
+  int kb = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    p.seg_kb_start[s] = kb;
+    if (!make_tmap(&maps[s], d.a[s].ptr, d.M, d.a[s].k, d.a[s].ld, BM, err)) return cudaErrorInvalidValue;
+    kb += (d.a[s].k + BK - 1) / BK;
+  }
+  for (int s = d.nseg; s < 5; ++s) p.seg_kb_start[s] = kb;
+  for (int s = d.nseg; s < 4; ++s) maps[s] = maps[0];
+  p.num_kb = kb;
+  if (kb * BK != d.Kp) { *err = "GEMM weight K padding does not match the A segments"; return cudaErrorInvalidValue; }
+  if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, BN, err)) return cudaErrorInvalidValue;
+  p.tiles_m = (d.M + BM - 1) / BM; p.tiles_n = (d.N + BN - 1) / BN;
+  p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd; p.act = d.act;
+  p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod; p.res_f32 = d.res_f32;
+  p.out = d.out; p.ldo = d.ldo; p.out_f32 = d.out_f32; p.out2 = d.out2;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace dsheg

@@ -1,0 +1,163 @@
+"""Pack a reference ``checkpoint['encoder']`` state_dict into the tensors the CUDA engine loads.
+
+Input contract: the UniDiffuser state_dict of the reference (keys as produced by
+models/transformer.py:590-699; DDP ``module.`` prefixes are stripped like
+trainers/ddpm_show_trainer.py:271-274).  All folds are done in float64 on the host and are
+exact up to floating-point reassociation:
+
+* ``*.feat1`` / ``*.qkv``: the LayerNorm in front of the Linear (tr:285-286, tr:119-125) is folded
+  into it: W' = W * gamma, b' = b + W beta, csum[n] = sum_k W'[n,k]; the kernel applies
+  rstd * (x W'^T - mu * csum) + b' with per-row (mu, rstd).  csum is taken over W' AS STORED
+  (after bf16 rounding) so the subtraction cancels exactly.
+* ``*.nullc``: under classifier-free guidance the whole feat_proj input row of the uncond half is the
+  learned ``null_cond_emb`` (tr:326-332), so feat_proj(null) is one constant vector per layer.
+* ``*.hub``: BatchNorm1d (eval) folded into the first Conv1d of hubert_encoder (tr:436-442).
+* K axes of GEMM weights are laid out per A-segment, each padded to a multiple of 64
+  (h | audio_proj | hubert | expr for feat1).
+
+Packed names (n in aud/exp/ges, i = layer): see ``pack_state_dict``; shapes are validated by
+``dsheg_finalize_weights``.
+"""
+import math
+
+import numpy as np
+import torch
+
+F32, BF16 = 0, 1
+
+
+def _r64(k):
+    return (k + 63) // 64 * 64
+
+
+def _pad_segments(W, widths):
+    """[N, sum(widths)] -> [N, sum(round_up(w, 64))], zero padded per segment."""
+    cols, off = [], 0
+    for w in widths:
+        seg = W[:, off:off + w]
+        pad = _r64(w) - w
+        if pad:
+            seg = torch.cat([seg, torch.zeros(W.shape[0], pad, dtype=W.dtype)], dim=1)
+        cols.append(seg)
+        off += w
+    assert off == W.shape[1], (off, W.shape)
+    return torch.cat(cols, dim=1)
+
+
+class Packer:
+    def __init__(self, sd, cfg, precision):
+        self.sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
+        self.cfg, self.bf16 = cfg, precision == "bf16"
+        self.out = {}
+
+    def g(self, key):
+        return self.sd[key].detach().to("cpu", torch.float64)
+
+    def put_f32(self, name, t):
+        self.out[name] = (t.to(torch.float32).contiguous(), F32)
+
+    def put_w(self, name, W, widths=None):
+        """GEMM weight [N, K] -> stored [N, Kp] in the GEMM element type; returns the stored values (f64)."""
+        W = _pad_segments(W, widths or [W.shape[1]])
+        if self.bf16:
+            st = W.to(torch.bfloat16).contiguous()
+            self.out[name] = (st, BF16)
+            return st.to(torch.float64)
+        st = W.to(torch.float32).contiguous()
+        self.out[name] = (st, F32)
+        return st.to(torch.float64)
+
+    def lin(self, name, key, widths=None):
+        self.put_w(name + ".w", self.g(key + ".weight"), widths)
+        self.put_f32(name + ".b", self.g(key + ".bias"))
+
+    def lin_ln_fold(self, name, W, b, gamma, beta, widths=None):
+        Wp = W * gamma[None, :]
+        stored = self.put_w(name + ".w", Wp, widths)
+        self.put_f32(name + ".b", b + W @ beta)
+        self.put_f32(name + ".csum", stored.sum(dim=1))
+
+    def mlp(self, name, key0, key2, pad_k=False):
+        w0 = self.g(key0 + ".weight")
+        if pad_k:
+            w0 = _pad_segments(w0, [w0.shape[1]])
+        self.put_f32(name + ".w0", w0)
+        self.put_f32(name + ".b0", self.g(key0 + ".bias"))
+        self.put_f32(name + ".w2", self.g(key2 + ".weight"))
+        self.put_f32(name + ".b2", self.g(key2 + ".bias"))
+
+    def layer(self, name, key, seg_widths, null_row):
+        g = self.g
+        if seg_widths:
+            fp = key + ".feat_proj"
+            gam, bet = g(fp + ".0.weight"), g(fp + ".0.bias")
+            W1, b1 = g(fp + ".1.weight"), g(fp + ".1.bias")
+            W2, b2 = g(fp + ".3.weight"), g(fp + ".3.bias")
+            self.lin_ln_fold(name + ".feat1", W1, b1, gam, bet, seg_widths)
+            self.put_w(name + ".feat2.w", W2)
+            self.put_f32(name + ".feat2.b", b2)
+            if null_row is not None:
+                mu = null_row.mean()
+                var = ((null_row - mu) ** 2).mean()
+                z = (null_row - mu) / torch.sqrt(var + 1e-5) * gam + bet
+                hid = W1 @ z + b1
+                hid = hid * torch.sigmoid(hid)
+                self.put_f32(name + ".nullc", W2 @ hid + b2)
+        sa = key + ".sa_block"
+        Wqkv = torch.cat([g(sa + ".query.weight"), g(sa + ".key.weight"), g(sa + ".value.weight")], 0)
+        bqkv = torch.cat([g(sa + ".query.bias"), g(sa + ".key.bias"), g(sa + ".value.bias")], 0)
+        self.lin_ln_fold(name + ".qkv", Wqkv, bqkv, g(sa + ".norm.weight"), g(sa + ".norm.bias"))
+        self.put_f32(name + ".sa.g", g(sa + ".proj_out.norm.weight"))
+        self.put_f32(name + ".sa.b", g(sa + ".proj_out.norm.bias"))
+        self.lin(name + ".sa_out", sa + ".proj_out.out_layers.2")
+        ff = key + ".ffn"
+        self.lin(name + ".ffn1", ff + ".linear1")
+        self.lin(name + ".ffn2", ff + ".linear2")
+        self.put_f32(name + ".ffn.g", g(ff + ".proj_out.norm.weight"))
+        self.put_f32(name + ".ffn.b", g(ff + ".proj_out.norm.bias"))
+        self.lin(name + ".ffn_out", ff + ".proj_out.out_layers.2")
+
+    def run(self, max_frames):
+        cfg, g = self.cfg, self.g
+        D, L = cfg["latent_dim"], cfg["num_layers"]
+        half = D // 2
+        # tr:52-54, computed with torch exactly as the reference does
+        freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+        self.put_f32("freqs", freqs)
+        self.mlp("aud.te", "time_embed.0", "time_embed.2")
+        a = "encoder_aud"
+        self.put_f32("aud.ss.w", torch.cat([g(a + ".sa_block.proj_out.emb_layers.1.weight"),
+                                            g(a + ".ffn.proj_out.emb_layers.1.weight")], 0))
+        self.put_f32("aud.ss.b", torch.cat([g(a + ".sa_block.proj_out.emb_layers.1.bias"),
+                                            g(a + ".ffn.proj_out.emb_layers.1.bias")], 0))
+        self.layer("aud.l0", a, None, None)
+        for name, key, extra in (("exp", "encoder_exp", 0), ("ges", "encoder_ges", cfg["expression_dim"])):
+            self.mlp(name + ".te", key + ".time_embed.0", key + ".time_embed.2")
+            self.mlp(name + ".pid", key + ".pid_embed.0", key + ".pid_embed.2", pad_k=True)
+            he = key + ".hubert_encoder"
+            s = g(he + ".1.weight") / torch.sqrt(g(he + ".1.running_var") + 1e-5)
+            w0 = g(he + ".0.weight") * s[:, None, None]           # [128, 1024, 3]
+            self.put_f32(name + ".hub.w0", w0.permute(2, 1, 0))   # [3][Cin][Cout]
+            self.put_f32(name + ".hub.b0", g(he + ".1.bias") - g(he + ".1.running_mean") * s)
+            self.put_f32(name + ".hub.w3", g(he + ".3.weight").permute(2, 1, 0))
+            pe = g(key + ".PE.pe")[0]
+            assert max_frames <= pe.shape[0]
+            self.put_f32(name + ".pe", pe[:max_frames])
+            blocks = [key + f".temporal_decoder_blocks.{i}" for i in range(L)]
+            self.put_w(name + ".ss.w", torch.cat(
+                [g(b + m + ".proj_out.emb_layers.1.weight") for b in blocks for m in (".sa_block", ".ffn")], 0))
+            self.put_f32(name + ".ss.b", torch.cat(
+                [g(b + m + ".proj_out.emb_layers.1.bias") for b in blocks for m in (".sa_block", ".ffn")], 0))
+            self.lin(name + ".joint", key + ".joint_embed")
+            self.lin(name + ".audproj", key + ".audio_proj")
+            self.lin(name + ".out", key + ".out")
+            widths = [D, cfg["aud_latent_dim"], cfg["hubert_enc_dim"]] + ([extra] if extra else [])
+            null = g(key + ".null_cond_emb")[0] if cfg["classifier_free"] else None
+            for i, b in enumerate(blocks):
+                self.layer(f"{name}.l{i}", b, widths, null)
+        return self.out
+
+
+def pack_state_dict(sd, cfg, precision, max_frames):
+    """-> {packed_name: (cpu tensor, dtype_code)}"""
+    return Packer(sd, cfg, precision).run(max_frames)

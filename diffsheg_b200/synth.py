@@ -136,3 +136,20 @@ def make_inputs(cfg, B, T=None, seed=2):
     g3 = torch.Generator().manual_seed(seed + 1)
     x_T = torch.randn(B, T, cfg["net_dim_pose"], generator=g3)
     return dict(mel=mel, hubert=hubert, person_id=pid, x_T=x_T)
+
+
+def make_opt(cfg, **over):
+    """The sampler-relevant subset of the reference's ``opt`` Namespace (options/base_options.py:16-128,
+    runner.py:124-222) for synthetic runs: what FusedGaussianDiffusion / generate_batch read."""
+    import argparse
+
+    opt = argparse.Namespace(
+        dataset_name=cfg["dataset_name"], dim_pose=cfg["dim_pose"], expression_dim=cfg["expression_dim"],
+        split_pos=cfg["dim_pose"], net_dim_pose=cfg["net_dim_pose"], n_poses=cfg["n_poses"],
+        style_dim=cfg["style_dim"], classifier_free=cfg["classifier_free"], cond_scale=cfg["cond_scale"],
+        ddim=True, timestep_respacing="ddim25", diffusion_steps=1000, overlap_len=0, addBlend=True,
+        jump_length=3, jump_n_sample=5, no_resample=False, no_repaint=False, same_overlap_noisy=False,
+        fix_head_var=False, PE="pe_sinu", model_mean_type="epsilon", unidiffuser=True)
+    for k, v in over.items():
+        setattr(opt, k, v)
+    return opt

@@ -1,0 +1,133 @@
+/*
+ * diffsheg_b200 -- C ABI of the B200-native DiffSHEG sampling hot path.
+ *
+ * One shared library (libdiffsheg_b200.so, sm_100a only).  Plain pointers and sizes: no
+ * torch / C++ types cross this boundary.  All data pointers are DEVICE pointers unless the
+ * argument name starts with `host_`; `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success and a non-zero status otherwise; the message is
+ * available from dsheg_last_error().  Nothing here throws, aborts or synchronises the
+ * device (except dsheg_load_tensor / dsheg_finalize_weights, which are set-up calls).
+ *
+ * The reference (JeremyCJM/DiffSHEG, pure Python) has no FFI; each entry point replaces
+ * the Python code cited beside it (paths relative to the reference repository).
+ */
+#ifndef DIFFSHEG_B200_H_
+#define DIFFSHEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSHEG_ABI_VERSION 1
+
+enum { DSHEG_PREC_FP32 = 0, DSHEG_PREC_BF16 = 1 };
+enum { DSHEG_DTYPE_F32 = 0, DSHEG_DTYPE_BF16 = 1 };
+
+/* Frozen subset of the reference `opt` Namespace + build_models() arguments
+ * (runner.py:32-45, runner.py:124-222, options/base_options.py:16-128). */
+typedef struct dsheg_config {
+  int32_t abi_version;     /* DSHEG_ABI_VERSION */
+  int32_t dim_pose;        /* gesture channels: 129 (SHOW) / 141 (BEAT); opt.split_pos */
+  int32_t expression_dim;  /* 103 / 51 */
+  int32_t audio_dim;       /* mel channels, 128 */
+  int32_t hubert_dim;      /* 1024 */
+  int32_t aud_latent_dim;  /* 256 */
+  int32_t latent_dim;      /* 512 */
+  int32_t num_layers;      /* 8 */
+  int32_t num_heads;       /* 8 */
+  int32_t ff_size;         /* 1024 */
+  int32_t style_dim;       /* 4 / 30 */
+  int32_t classifier_free; /* opt.classifier_free */
+  int32_t precision;       /* DSHEG_PREC_* : arithmetic of the per-step GEMMs/activations */
+  int32_t max_batch;       /* workspace is sized for max_batch x max_frames (x2 under CFG) */
+  int32_t max_frames;
+} dsheg_config;
+
+typedef struct dsheg_handle dsheg_handle;
+
+/* Last error message of `h` (or of the last failed dsheg_create when h == NULL). */
+const char* dsheg_last_error(const dsheg_handle* h);
+
+/* Replaces UniDiffuser.__init__ (models/transformer.py:590-699) + .to(device).  */
+int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out);
+void dsheg_destroy(dsheg_handle* h);
+
+/* Weight upload: packed tensors by name (the packed contract is documented in
+ * diffsheg_b200/pack.py, built from checkpoint['encoder'], trainers/ddpm_show_trainer.py:
+ * 278-292).  host_data is HOST memory, copied synchronously. */
+int dsheg_load_tensor(dsheg_handle* h, const char* key, const void* host_data, int32_t dtype,
+                      const int64_t* shape, int32_t ndim);
+/* Resolve every tensor the configured network needs; fails listing the first missing key. */
+int dsheg_finalize_weights(dsheg_handle* h);
+
+/* Per-window, step-invariant work: person-id MLP (transformer.py:453-457,559),
+ * hubert_encoder conv stack for both nets (transformer.py:436-442,512-515), mel staging.
+ * mel [B,T,audio_dim], hubert [B,T,hubert_dim], person_id [B,style_dim], fp32 contiguous. */
+int dsheg_prepare_window(dsheg_handle* h, const float* mel, const float* hubert, const float* person_id,
+                         int32_t B, int32_t T, void* stream);
+
+/* One denoiser call: UniDiffuser.forward (transformer.py:728-770) for a batch-uniform
+ * ORIGINAL timestep t_orig (gaussian_diffusion.py:1196 builds t = [i]*B; respace.py:119-124
+ * maps it), a = sqrt_recip_alphas_cumprod[t], b = sqrt_recipm1_alphas_cumprod[t]
+ * (gaussian_diffusion.py:527-532).  x, eps_out: [B,T,dim_pose+expression_dim] fp32. */
+int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, float b, float cond_scale,
+                  float* eps_out, void* stream);
+
+/* Kernel launches issued by this handle since creation (bench.py reports the delta). */
+int64_t dsheg_launch_count(const dsheg_handle* h);
+
+/* Per-kernel-class device timing for bench.py's roofline pass: between begin and end every GEMM,
+ * attention and row-wise (LayerNorm/statistics) launch is bracketed by CUDA events on the launching
+ * stream.  end() synchronises and returns, for class c in {0 GEMM, 1 attention, 2 row-wise}:
+ * ms[c] summed kernel time, work[c] algorithmic FLOPs (c = 0) or bytes (c = 1, 2), count[c] launches. */
+int dsheg_profile_begin(dsheg_handle* h);
+int dsheg_profile_end(dsheg_handle* h, double* ms, double* work, int64_t* count);
+
+/* ---- stateless sampler-step kernels (fp32, elementwise, HBM-bound) ---------------------- */
+
+/* ddim_sample, eta = 0 (gaussian_diffusion.py:976-1066): x_out = DDIM update of (x, eps),
+ * then, when gt/mask are given, the RePaint merge :1034-1056 with noise2 and the linear
+ * overlap blend (blend != 0, first overlap_len frames).  n = B*T*D elements, frame stride
+ * D, T frames per sample.  gt/mask/noise2 may be NULL (no repaint).  mask: 1 byte/element. */
+int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, int32_t T, int32_t D,
+                    float sqrt_recip_ac, float sqrt_recipm1_ac, float sqrt_ac_prev,
+                    float sqrt_one_minus_ac_prev, const float* gt, const uint8_t* mask,
+                    const float* noise2, int32_t blend, int32_t overlap_len, float* pred_xstart_out,
+                    void* stream);
+
+/* _undo (gaussian_diffusion.py:467-473): x_out = sqrt(1-beta) x + sqrt(beta) noise. */
+int dsheg_undo_step(const float* x, const float* noise, float* x_out, int64_t n, float sqrt_one_minus_beta,
+                    float sqrt_beta, void* stream);
+
+/* p_sample (gaussian_diffusion.py:747-774 with q_posterior :475-497): posterior mean from
+ * (x, eps) + nonzero * exp(0.5 logvar) * noise. */
+int dsheg_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, int64_t n,
+                    float sqrt_recip_ac, float sqrt_recipm1_ac, float coef1, float coef2,
+                    float sigma /* exp(0.5*logvar) or 0 at t == 0 */, float* pred_xstart_out, void* stream);
+
+/* p_sample's harmonize pre-merge (gaussian_diffusion.py:727-745):
+ * x_out = mask ? sqrt_ac*gt + sqrt_one_minus_ac*noise : x. */
+int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, const float* noise,
+                        float* x_out, int64_t n, float sqrt_ac, float sqrt_one_minus_ac, void* stream);
+
+/* ---- op-level entry points used by the parity tests -------------------------------------- */
+
+/* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32 or the
+ * tcgen05 bf16 engine.  A/W/out/residual are fp32 device arrays; the bf16 engine converts
+ * internally (test path only).  act: 0 none, 1 SiLU, 2 GELU(erf). */
+int dsheg_op_linear(int32_t precision, const float* A, const float* W, const float* bias,
+                    const float* residual, float* out, int32_t M, int32_t N, int32_t K, int32_t act,
+                    void* stream);
+
+/* Linear self-attention core + Stylization prologue on one [Bn,T,3D] qkv tensor
+ * (transformer.py:122-128 then :92-96 up to the SiLU): z = SiLU(LN(y)*(1+scale)+shift). */
+int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
+                       float* z, int32_t Bn, int32_t T, int32_t D, int32_t H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSHEG_B200_H_ */
