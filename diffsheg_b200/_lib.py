@@ -75,6 +75,7 @@ SIGNATURES = {
     "dsheg_repaint_merge": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _P]),
     "dsheg_op_linear": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "dsheg_op_attention": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "dsheg_op_attention_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P]),
 }
 
 

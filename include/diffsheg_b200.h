@@ -127,6 +127,10 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
 int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
                        float* z, int32_t Bn, int32_t T, int32_t D, int32_t H, void* stream);
 
+/* Same op on the bf16 fast path (tensor-core kernel, D = 512, 8 heads, T <= 96): qkv and z are bf16 arrays. */
+int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
+                            void* z, int32_t Bn, int32_t T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

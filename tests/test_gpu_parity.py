@@ -137,6 +137,29 @@ def test_op_attention(L, Bn, T, D, H):
     assert relmax(z, want) < 2e-5
 
 
+@pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (2, 84), (1, 30), (5, 96), (2, 16), (1, 7)])
+def test_op_attention_bf16_tensor_core(L, Bn, T):
+    """mma.sync attention kernel vs an fp64 evaluation of the same bf16 inputs (bf16 output rounding: 2^-8)."""
+    torch.manual_seed(T)
+    D, H = 512, 8
+    qkv = (1.5 * torch.randn(Bn, T, 3 * D, device="cuda")).bfloat16()
+    g, b = 1 + 0.1 * torch.randn(D, device="cuda"), 0.1 * torch.randn(D, device="cuda")
+    ss = 0.5 * torch.randn(Bn, 2 * D, device="cuda")
+    z = torch.zeros(Bn, T, D, device="cuda", dtype=torch.bfloat16)
+    assert L.dsheg_op_attention_bf16(P(qkv), P(g), P(b), P(ss), P(z), Bn, T, S()) == 0, L.dsheg_last_error(None)
+    q, k, v = qkv.double().split(D, dim=-1)
+    q = torch.softmax(q.view(Bn, T, H, -1), dim=-1)
+    k = torch.softmax(k.view(Bn, T, H, -1), dim=1)
+    att = torch.einsum("bnhd,bnhl->bhdl", k, v.view(Bn, T, H, -1))
+    y = torch.einsum("bnhd,bhdl->bnhl", q, att).reshape(Bn, T, D)
+    yn = torch.nn.functional.layer_norm(y, (D,), g.double(), b.double(), 1e-5)
+    want = torch.nn.functional.silu(yn * (1 + ss[:, None, :D].double()) + ss[:, None, D:].double())
+    torch.cuda.synchronize()
+    err = relmax(z.float(), want)
+    print(f"\n[parity] attention bf16 tensor-core Bn{Bn} T{T}: relmax={err:.3e}")
+    assert err < 3e-2
+
+
 # ------------------------------------------------------------------------------------------------
 # single denoiser call vs the committed reference outputs (tests/golden, made by the REAL reference)
 # ------------------------------------------------------------------------------------------------
