@@ -668,6 +668,10 @@ int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, co
 
 // ---- op-level test entry points --------------------------------------------------------------
 namespace {
+__global__ void bf16_to_f32_kernel(const bf16* in, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
 __global__ void f32_to_bf16_pad_kernel(const float* in, int rows, int cols, bf16* out, int ld) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * ld) return;
@@ -680,7 +684,7 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
                     int32_t M, int32_t N, int32_t K, int32_t act, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   GemmDesc d;
-  d.nseg = 1; d.M = M; d.N = N; d.bias = bias; d.act = act; d.out = out; d.ldo = N; d.out_f32 = 1;
+  d.nseg = 1; d.M = M; d.N = N; d.bias = bias; d.act = act;
   const int Kp = round_up(K, 64);
   if (precision == DSHEG_PREC_FP32) {
     // the SIMT kernel reads W with row stride Kp: repack when K is not a multiple of 64
@@ -691,22 +695,27 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
       cudaMemcpy2DAsync(Wp, (size_t)Kp * 4, W, (size_t)K * 4, (size_t)K * 4, N, cudaMemcpyDeviceToDevice, st);
     }
     d.a[0].ptr = A; d.a[0].ld = K; d.a[0].k = K; d.w = Wp ? Wp : W; d.Kp = Kp;
-    d.res = residual; d.ldr = N; d.res_f32 = 1;
+    d.res = residual; d.ldr = N; d.res_f32 = 1; d.out = out; d.ldo = N; d.out_f32 = 1;
     cudaError_t e = launch_gemm_simt<float, float>(d, st);
     cudaStreamSynchronize(st);
     if (Wp) cudaFree(Wp);
     if (e != cudaSuccess) { g_create_error = std::string("op_linear simt: ") + cudaGetErrorString(e); return 1; }
     return step_done("dsheg_op_linear");
   }
-  bf16 *Ab = nullptr, *Wb = nullptr;
-  if (cudaMalloc(&Ab, (size_t)M * Kp * 2) != cudaSuccess || cudaMalloc(&Wb, (size_t)N * Kp * 2) != cudaSuccess) {
-    g_create_error = "op_linear: cudaMalloc";
-    return 1;
-  }
+  // bf16 engine: bf16 operands; bf16 output + bf16 residual when N % 32 == 0 (the engine's layout), else fp32 output
+  const bool bf_out = (N % 32) == 0;
+  if (!bf_out && (act != ACT_NONE || residual)) { g_create_error = "op_linear bf16: N % 32 != 0 supports no act / residual"; return 1; }
+  bf16 *Ab = nullptr, *Wb = nullptr, *Rb = nullptr, *Ob = nullptr;
+  bool ok = cudaMalloc(&Ab, (size_t)M * Kp * 2) == cudaSuccess && cudaMalloc(&Wb, (size_t)N * Kp * 2) == cudaSuccess;
+  if (ok && bf_out) ok = cudaMalloc(&Ob, (size_t)M * N * 2) == cudaSuccess;
+  if (ok && residual) ok = cudaMalloc(&Rb, (size_t)M * N * 2) == cudaSuccess;
+  if (!ok) { g_create_error = "op_linear: cudaMalloc"; return 1; }
   f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)M * Kp + 255) / 256), 256, 0, st>>>(A, M, K, Ab, Kp);
   f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)N * Kp + 255) / 256), 256, 0, st>>>(W, N, K, Wb, Kp);
+  if (residual) f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(residual, M, N, Rb, N);
   d.a[0].ptr = Ab; d.a[0].ld = Kp; d.a[0].k = K; d.w = Wb; d.Kp = Kp;
-  d.res = residual; d.ldr = N; d.res_f32 = 1;
+  d.res = Rb; d.ldr = N; d.res_f32 = 0;
+  d.out = bf_out ? (void*)Ob : (void*)out; d.ldo = N; d.out_f32 = bf_out ? 0 : 1;
   std::string terr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -715,13 +724,58 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
   cudaError_t e;
   if (eng && !strcmp(eng, "simt")) e = launch_gemm_simt<bf16, bf16>(d, st);
   else e = tc::launch_gemm_tc(d, sms, st, &terr);
+  if (e == cudaSuccess && bf_out) bf16_to_f32_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(Ob, out, (size_t)M * N);
   cudaError_t e2 = cudaStreamSynchronize(st);
-  cudaFree(Ab);
-  cudaFree(Wb);
+  cudaFree(Ab); cudaFree(Wb);
+  if (Ob) cudaFree(Ob);
+  if (Rb) cudaFree(Rb);
   if (e != cudaSuccess || e2 != cudaSuccess) {
     g_create_error = "op_linear tc: " + terr + " " + cudaGetErrorString(e != cudaSuccess ? e : e2);
     return 1;
   }
+  return 0;
+}
+
+// Times one tcgen05 GEMM shape (bf16, device-resident random-ish data): mode 0 bias, 1 LN+bias, 2 LN+bias+SiLU,
+// 3 bias+bf16 residual (in place), 4 bias+GELU; bn = 0 (auto) / 128 / 256.  Returns the mean ms over `iters`.
+int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out) {
+  if (K % 64 || N % 32 || !ms_out) { g_create_error = "bench_gemm: need K % 64 == 0, N % 32 == 0"; return 1; }
+  bf16 *Ab = nullptr, *Wb = nullptr, *Ob = nullptr;
+  float *vec = nullptr;
+  if (cudaMalloc(&Ab, (size_t)M * K * 2) != cudaSuccess || cudaMalloc(&Wb, (size_t)N * K * 2) != cudaSuccess ||
+      cudaMalloc(&Ob, (size_t)M * N * 2) != cudaSuccess || cudaMalloc(&vec, ((size_t)2 * N + 2 * M) * 4) != cudaSuccess) {
+    g_create_error = "bench_gemm: cudaMalloc";
+    return 1;
+  }
+  cudaMemset(Ab, 0x3c, (size_t)M * K * 2);   // bf16 0x3c3c ~ 0.0115
+  cudaMemset(Wb, 0x3c, (size_t)N * K * 2);
+  cudaMemset(Ob, 0, (size_t)M * N * 2);
+  cudaMemset(vec, 0, ((size_t)2 * N + 2 * M) * 4);
+  GemmDesc d;
+  d.nseg = 1; d.M = M; d.N = N; d.Kp = K; d.a[0].ptr = Ab; d.a[0].ld = K; d.a[0].k = K; d.w = Wb;
+  d.bias = vec; d.out = Ob; d.ldo = N;
+  if (mode == 1 || mode == 2) { d.csum = vec + N; d.mu = vec + 2 * N; d.rstd = vec + 2 * N + M; }
+  if (mode == 2) d.act = ACT_SILU;
+  if (mode == 3) { d.res = Ob; d.ldr = N; }
+  if (mode == 4) d.act = ACT_GELU;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  std::string terr;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = tc::launch_gemm_tc(d, sms, 0, &terr, bn);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters && e == cudaSuccess; ++i) e = tc::launch_gemm_tc(d, sms, 0, &terr, bn);
+  cudaEventRecord(e1, 0);
+  cudaError_t e2 = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / (iters > 0 ? iters : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(Ab); cudaFree(Wb); cudaFree(Ob); cudaFree(vec);
+  if (e != cudaSuccess || e2 != cudaSuccess) { g_create_error = "bench_gemm: " + terr + " " + cudaGetErrorString(e != cudaSuccess ? e : e2); return 1; }
   return 0;
 }
 

@@ -1,19 +1,21 @@
 // tcgen05 (UMMA) bf16 GEMM for sm_100a:  out[M,N] = epilogue( A[M,K] . W[N,K]^T ), fp32 accumulate.
 //
-//   * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a 6-stage smem ring
-//   * one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction), accumulators
-//     live in TMEM (2 x 128 columns, double-buffered so the epilogue of tile i overlaps the
-//     mainloop of tile i+1)
-//   * 4 epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
-//     fused epilogue: LayerNorm fold, bias, SiLU / GELU(erf), residual / positional add, bf16 or
-//     fp32 store (optionally duplicated for the two CFG halves)
-//   * persistent: one CTA per SM walks tiles n-fastest so concurrently running CTAs share the
-//     A row-panel through L2; W panels (<= 2 MB) stay L2-resident
-//   * A is a VIRTUAL CONCAT of up to 4 row-major segments (one tensor map each): the feat_proj
-//     input cat(h, audio, hubert, expr) (transformer.py:304-310) is never materialised.
+//   * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a multi-stage smem ring
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16 per instruction), accumulators live in
+//     TMEM (2 x BN columns, double-buffered: the epilogue of tile i overlaps the mainloop of tile i+1)
+//   * 16 epilogue warps (4 TMEM lane quadrants x 4 column groups) read TMEM with tcgen05.ld (one accumulator
+//     row per thread) and apply the fused epilogue -- LayerNorm fold, bias, SiLU / GELU, residual or
+//     positional add, bf16 / fp32 store, optional duplicate store for the two CFG halves.  The epilogue is
+//     specialised at compile time (no per-element branches), bias / column sums are staged in smem once per
+//     tile, row statistics and the residual row segment are fetched BEFORE waiting on the accumulator, so
+//     their latency hides behind the mainloop.  (v0 of this kernel had 4 epilogue warps and a generic
+//     per-element epilogue: ncu showed IPC 0.12 and 5-11 % tensor-pipe activity -- profiles/r01.)
+//   * persistent: one CTA per SM walks tiles n-fastest so concurrently running CTAs share the A row-panel
+//     through L2; W panels (<= 2 MB) stay L2-resident
+//   * A is a VIRTUAL CONCAT of up to 4 row-major segments (one tensor map each): the feat_proj input
+//     cat(h, audio, hubert, expr) (transformer.py:304-310) is never materialised.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (TMEM lane
-// quadrants 2,3,0,1).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-3 idle, 4..19 = epilogue.
 #pragma once
 #include <cuda.h>
 
@@ -22,22 +24,34 @@
 namespace dsheg {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 6;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_ACC = 2, TMEM_COLS = NUM_ACC * BN;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NUM_ACC = 2;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int UMMA_K = 16;
+
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = NUM_ACC * BN;
+  static constexpr int VEC_BYTES = NUM_ACC * 2 * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + VEC_BYTES;
+  static constexpr int CPW = BN / 4;  // accumulator columns per epilogue warp
+  // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+enum { RES_NONE = 0, RES_BF16 = 1, RES_F32_MOD = 2 };
 
 struct Params {
   int M, N, num_kb, nseg;
   int seg_kb_start[5];
   int tiles_m, tiles_n;
   const float* bias; const float* csum; const float* mu; const float* rstd;
-  int act;
-  const void* res; int ldr, res_mod, res_f32;
-  void* out; int ldo, out_f32; void* out2;
+  const void* res; int ldr, res_mod;
+  void* out; int ldo; void* out2;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -105,6 +119,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 
 // K-major, 128B-swizzled operand tile [rows][64 bf16] (8-row groups of 1024 B): SBO = 1024 B,
 // LBO unused, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
@@ -116,18 +131,36 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Epilogue activations for bf16 outputs (MUFU.TANH, |abs err| <= 2^-10.99 on tanh, i.e. below the bf16
+// output resolution):  silu(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2 (exact identity);
+// gelu(x) ~= h + h*tanh(0.79788456 x + 0.03567741 x^3)  (tanh form, |gelu_tanh - gelu_erf| < 5e-4).
+template <int ACT> __device__ __forceinline__ float act_fast(float x) {
+  if (ACT == ACT_SILU) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
+  if (ACT == ACT_GELU) {
+    const float h = 0.5f * x;
+    const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+    return fmaf(h, tanh_fast(u), h);
+  }
+  return x;
+}
 
+template <int BN, bool LN, int ACT, int RES, bool OUTF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmW, const Params p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, CPW = C::CPW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -136,20 +169,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
+  float* vecs = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + 256);  // [NUM_ACC][2][BN]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
   }
   if (warp == 1) {  // TMEM allocation: one full warp, which also owns the dealloc
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -195,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (= UMMA_K bf16) inside the 128B swizzle atom: +2 in 16-byte units
-            tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
+            tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
           }
           tc_commit(empty_bar(stage));              // frees the smem slot when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -205,79 +240,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     __syncwarp();
-  } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp % 4;  // TMEM lane quadrant this warp may touch
+  } else if (warp >= 4) {
+    // ================= epilogue (16 warps) =================
+    const int q = warp & 3;           // TMEM lane quadrant this warp may touch (warp id % 4)
+    const int cg = (warp - 4) >> 2;   // column group
+    const int etid = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+      const int n_tile0 = n_blk * BN;
+      // ---- stage per-column vectors for this tile (double-buffered with the accumulator stage)
+      float* vb = vecs + acc * 2 * BN;
+      for (int i = etid; i < BN; i += NUM_EPI_WARPS * 32) {
+        const int n = n_tile0 + i;
+        vb[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        if (LN) vb[BN + i] = n < p.N ? __ldg(p.csum + n) : 0.f;
+      }
+      epi_bar_sync();
+      // ---- per-row operands, fetched before the accumulator is ready
       const int m = m_blk * BM + q * 32 + lane;
       const bool row_ok = m < p.M;
-      float mu = 0.f, rstd = 1.f;
-      if (p.csum && row_ok) { mu = p.mu[m]; rstd = p.rstd[m]; }
-      const int mr = p.res_mod > 0 ? m % p.res_mod : m;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      float rs = 1.f, rm = 0.f;  // v = rs * acc + rm * csum[n] + bias[n]
+      if (LN && row_ok) { rs = __ldg(p.rstd + m); rm = -rs * __ldg(p.mu + m); }
+      const int nc0 = n_tile0 + cg * CPW;  // first global column of this warp
+      uint4 rres[RES == RES_BF16 ? CPW / 8 : 1];
+      if (RES == RES_BF16) {
+        if (row_ok) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (size_t)m * p.ldr + nc0);
+#pragma unroll
+          for (int u = 0; u < CPW / 8; ++u) rres[u] = rp[u];
+        }
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < CPW / 32; ++ch) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        const int n0 = n_blk * BN + c * 32;
-        if (!row_ok || n0 >= p.N) continue;
-        const bool full = (n0 + 32 <= p.N);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
+        const int n0 = nc0 + ch * 32;
+        const float* bvec = vb + cg * CPW + ch * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + j;
-          float t = __uint_as_float(r[j]);
-          if (full || n < p.N) {
-            if (p.csum) t = rstd * (t - mu * __ldg(p.csum + n));
-            if (p.bias) t += __ldg(p.bias + n);
-            t = apply_act(t, p.act);
-          }
-          v[j] = t;
-        }
-        if (p.res) {
-          if (p.res_f32) {
-            const float* rp = reinterpret_cast<const float*>(p.res) + (size_t)mr * p.ldr + n0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (full || n0 + j < p.N) v[j] += rp[j];
-          } else if (full) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (size_t)mr * p.ldr + n0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 w = rp[u];
-              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
-                v[u * 8 + e * 2] += __bfloat162float(h2.x);
-                v[u * 8 + e * 2 + 1] += __bfloat162float(h2.y);
-              }
-            }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bvec + j);
+          float t0 = __uint_as_float(r[j]), t1 = __uint_as_float(r[j + 1]), t2 = __uint_as_float(r[j + 2]), t3 = __uint_as_float(r[j + 3]);
+          if (LN) {
+            const float4 c4 = *reinterpret_cast<const float4*>(bvec + BN + j);
+            t0 = fmaf(rs, t0, fmaf(rm, c4.x, b4.x)); t1 = fmaf(rs, t1, fmaf(rm, c4.y, b4.y));
+            t2 = fmaf(rs, t2, fmaf(rm, c4.z, b4.z)); t3 = fmaf(rs, t3, fmaf(rm, c4.w, b4.w));
           } else {
-            const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (size_t)mr * p.ldr + n0;
-            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+            t0 += b4.x; t1 += b4.y; t2 += b4.z; t3 += b4.w;
+          }
+          v[j] = act_fast<ACT>(t0); v[j + 1] = act_fast<ACT>(t1); v[j + 2] = act_fast<ACT>(t2); v[j + 3] = act_fast<ACT>(t3);
+        }
+        if (RES == RES_BF16) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 w = rres[ch * 4 + u];
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
+              v[u * 8 + e * 2] += __bfloat162float(h2.x);
+              v[u * 8 + e * 2 + 1] += __bfloat162float(h2.y);
+            }
           }
         }
-        const size_t o = (size_t)m * p.ldo + n0;
-        if (p.out_f32) {
-          float* op = reinterpret_cast<float*>(p.out) + o;
-          float* op2 = p.out2 ? reinterpret_cast<float*>(p.out2) + o : nullptr;
-          if (full && (p.ldo % 4 == 0)) {
+        if (RES == RES_F32_MOD) {
+          if (row_ok) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + (size_t)(m % p.res_mod) * p.ldr + n0);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const float4 f = make_float4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
-              reinterpret_cast<float4*>(op)[u] = f;
-              if (op2) reinterpret_cast<float4*>(op2)[u] = f;
+              const float4 f = __ldg(rp + u);
+              v[u * 4] += f.x; v[u * 4 + 1] += f.y; v[u * 4 + 2] += f.z; v[u * 4 + 3] += f.w;
+            }
+          }
+        }
+        if (row_ok) {
+          const size_t o = (size_t)m * p.ldo + n0;
+          if (OUTF32) {
+            float* op = reinterpret_cast<float*>(p.out) + o;
+            if (n0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n0 + j < p.N) op[j] = v[j];
             }
           } else {
-            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) { op[j] = v[j]; if (op2) op2[j] = v[j]; }
-          }
-        } else {
-          bf16* op = reinterpret_cast<bf16*>(p.out) + o;
-          bf16* op2 = p.out2 ? reinterpret_cast<bf16*>(p.out2) + o : nullptr;
-          if (full && (p.ldo % 8 == 0)) {
+            bf16* op = reinterpret_cast<bf16*>(p.out) + o;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               uint4 w;
@@ -286,11 +337,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
               w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
               reinterpret_cast<uint4*>(op)[u] = w;
-              if (op2) reinterpret_cast<uint4*>(op2)[u] = w;
+              if (p.out2) reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + o)[u] = w;
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) { op[j] = __float2bfloat16_rn(v[j]); if (op2) op2[j] = __float2bfloat16_rn(v[j]); }
           }
         }
       }
@@ -305,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -343,13 +391,53 @@ inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int
   return true;
 }
 
-inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err) {
+template <int BN, bool LN, int ACT, int RES, bool OUTF32>
+inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  return cudaGetLastError();
+}
+
+template <int BN>
+inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st,
+                            std::string* err) {
+  const bool ln = d.csum != nullptr;
+  const int res = !d.res ? RES_NONE : (d.res_f32 ? RES_F32_MOD : RES_BF16);
+  if (d.out_f32) {
+    if (!ln && d.act == ACT_NONE && res == RES_NONE && !d.out2) return launch_variant<BN, false, ACT_NONE, RES_NONE, true>(maps, p, grid, st);
+  } else if (ln) {
+    if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false>(maps, p, grid, st);
+    if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false>(maps, p, grid, st);
+  } else {
+    if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, false, ACT_NONE, RES_NONE, false>(maps, p, grid, st);
+    if (d.act == ACT_NONE && res == RES_BF16) return launch_variant<BN, false, ACT_NONE, RES_BF16, false>(maps, p, grid, st);
+    if (d.act == ACT_NONE && res == RES_F32_MOD) return launch_variant<BN, false, ACT_NONE, RES_F32_MOD, false>(maps, p, grid, st);
+    if (d.act == ACT_GELU && res == RES_NONE) return launch_variant<BN, false, ACT_GELU, RES_NONE, false>(maps, p, grid, st);
+    if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, false, ACT_SILU, RES_NONE, false>(maps, p, grid, st);
+  }
+  *err = "no tcgen05 GEMM variant for this epilogue combination";
+  return cudaErrorInvalidValue;
+}
+
+inline int g_bn_override() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DSHEG_TC_BN"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err, int bn_force = 0) {
+  // vector paths need 16-byte aligned rows; every engine buffer satisfies this
+  if (!d.out_f32 && ((d.ldo % 8) || (d.N % 32))) { *err = "bf16-output GEMM needs N % 32 == 0 and ldo % 8 == 0"; return cudaErrorInvalidValue; }
+  if (d.res && !d.res_f32 && (d.ldr % 8)) { *err = "bf16 residual needs ldr % 8 == 0"; return cudaErrorInvalidValue; }
+  if (d.res && d.res_f32 && ((d.ldr % 4) || d.res_mod <= 0)) { *err = "fp32 residual needs ldr % 4 == 0 and res_mod > 0"; return cudaErrorInvalidValue; }
+  int bn = bn_force ? bn_force : g_bn_override();
+  if (bn != 128 && bn != 256) bn = (d.N % 256 == 0) ? 256 : 128;
   Params p{};
   CUtensorMap maps[5];
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
@@ -363,15 +451,14 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   for (int s = d.nseg; s < 4; ++s) maps[s] = maps[0];
   p.num_kb = kb;
   if (kb * BK != d.Kp) { *err = "GEMM weight K padding does not match the A segments"; return cudaErrorInvalidValue; }
-  if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, BN, err)) return cudaErrorInvalidValue;
-  p.tiles_m = (d.M + BM - 1) / BM; p.tiles_n = (d.N + BN - 1) / BN;
-  p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd; p.act = d.act;
-  p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod; p.res_f32 = d.res_f32;
-  p.out = d.out; p.ldo = d.ldo; p.out_f32 = d.out_f32; p.out2 = d.out2;
+  if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, bn, err)) return cudaErrorInvalidValue;
+  p.tiles_m = (d.M + BM - 1) / BM; p.tiles_n = (d.N + bn - 1) / bn;
+  p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd;
+  p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod;
+  p.out = d.out; p.ldo = d.ldo; p.out2 = d.out2;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
-  return cudaGetLastError();
+  return bn == 256 ? dispatch<256>(d, maps, p, grid, st, err) : dispatch<128>(d, maps, p, grid, st, err);
 }
 
 }  // namespace tc

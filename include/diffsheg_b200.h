@@ -117,10 +117,15 @@ int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, co
 
 /* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32 or the
  * tcgen05 bf16 engine.  A/W/out/residual are fp32 device arrays; the bf16 engine converts
- * internally (test path only).  act: 0 none, 1 SiLU, 2 GELU(erf). */
+ * operands, residual and (when N % 32 == 0) the output to bf16 internally, exactly the layout the
+ * denoiser uses (test path only).  act: 0 none, 1 SiLU, 2 GELU. */
 int dsheg_op_linear(int32_t precision, const float* A, const float* W, const float* bias,
                     const float* residual, float* out, int32_t M, int32_t N, int32_t K, int32_t act,
                     void* stream);
+
+/* Device timing of one tcgen05 GEMM shape (tuning / roofline aid): mode 0 bias, 1 LN-fold+bias,
+ * 2 LN-fold+bias+SiLU, 3 bias+bf16 residual, 4 bias+GELU; bn 0 = auto, 128 or 256. */
+int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out);
 
 /* Linear self-attention core + Stylization prologue on one [Bn,T,3D] qkv tensor
  * (transformer.py:122-128 then :92-96 up to the SiLU): z = SiLU(LN(y)*(1+scale)+shift). */

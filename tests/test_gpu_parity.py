@@ -97,26 +97,37 @@ def test_undo_ddpm_merge(L):
 # op level
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("M,N,K,act", [(256, 512, 512, 0), (77, 103, 129, 1), (1000, 1536, 512, 2),
-                                       (1, 384, 128, 0), (300, 1024, 1024, 1), (129, 128, 64, 0)])
-def test_op_linear(L, prec, M, N, K, act):
+@pytest.mark.parametrize("M,N,K,act,use_res", [(256, 512, 512, 0, True), (77, 103, 129, 0, False), (1000, 1536, 512, 2, False),
+                                               (1, 384, 128, 0, False), (300, 1024, 1024, 1, False), (129, 128, 64, 0, True),
+                                               (2000, 256, 256, 0, False), (517, 512, 1024, 0, True), (130, 16384, 2048, 0, False)])
+def test_op_linear(L, prec, M, N, K, act, use_res):
+    """fp32: SIMT engine vs fp64.  bf16: tcgen05 engine on bf16-rounded operands / residual, bf16 output when
+    N % 32 == 0 (the denoiser's layout); tolerance = bf16 output rounding (2^-8) + the tanh-based activations."""
     torch.manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda")
     W = torch.randn(N, K, device="cuda") / K ** 0.5
     bias = torch.randn(N, device="cuda")
-    res = torch.randn(M, N, device="cuda")
+    res = torch.randn(M, N, device="cuda") if use_res else None
     out = torch.full((M, N), float("nan"), device="cuda")
     rc = L.dsheg_op_linear(0 if prec == "fp32" else 1, P(A), P(W), P(bias), P(res), P(out), M, N, K, act, S())
     assert rc == 0, L.dsheg_last_error(None)
     if prec == "bf16":
         A, W = A.bfloat16().float(), W.bfloat16().float()
+        res = res.bfloat16().float() if use_res else None
     want = A.double() @ W.double().T + bias.double()
     if act == 1:
         want = torch.nn.functional.silu(want)
     elif act == 2:
         want = torch.nn.functional.gelu(want)
-    want = want + res.double()
-    assert relmax(out, want) < (1e-5 if prec == "fp32" else 2e-5)  # bf16 inputs pre-rounded: fp32-accumulate exact
+    if use_res:
+        want = want + res.double()
+    err = relmax(out, want)
+    print(f"\n[parity] linear {prec} M{M} N{N} K{K} act{act} res{int(use_res)}: relmax={err:.3e}")
+    assert torch.isfinite(out).all()
+    if prec == "fp32":
+        assert err < 1e-5
+    else:
+        assert err < (2e-5 if N % 32 else 6e-3)
 
 
 @pytest.mark.parametrize("Bn,T,D,H", [(3, 88, 512, 8), (2, 34, 512, 8), (2, 30, 128, 8), (1, 84, 512, 8)])
