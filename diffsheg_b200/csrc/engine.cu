@@ -239,8 +239,18 @@ struct Runner {
       const int n_cond = rows - n_uncond;
       Seg e3[3] = {seg(nullptr, 0, 0), seg(nullptr, 0, 0), seg(nullptr, 0, 0)};
       for (int i = 0; i < n_extra; ++i) e3[i] = extra[i];
-      feat_prep_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
-          hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
+      {
+        double fb = (double)n_uncond * D * 2 + (double)n_cond * D;  // uncond rows: read+write h; cond rows: read the concat
+        for (int i = 0; i < n_extra; ++i) fb += (double)n_cond * extra[i].k;
+        prof_begin(h, st, PROF_ROW, fb * sizeof(TA));
+      }
+      if (std::is_same<TA, bf16>::value)
+        feat_prep_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+            (bf16*)hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
+      else
+        feat_prep_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+            hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
+      prof_end(h, st);
       LAUNCH_CHECK("feat_prep");
       TA* hc = hin + (size_t)n_uncond * ld_hin;
       GemmDesc g1;
@@ -257,7 +267,10 @@ struct Runner {
     }
     // K8: LayerNorm(D) folded into the fused QKV projection
     prof_begin(h, st, PROF_ROW, (double)rows * D * sizeof(TA));
-    rowstats_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(hcur, ldc, D, rows, h->MU2, h->RSTD2);
+    if (std::is_same<TA, bf16>::value)
+      rowstats_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>((const bf16*)hcur, ldc, D, rows, h->MU2, h->RSTD2);
+    else
+      rowstats_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(hcur, ldc, D, rows, h->MU2, h->RSTD2);
     prof_end(h, st);
     LAUNCH_CHECK("rowstats");
     GemmDesc gq;
@@ -295,8 +308,12 @@ struct Runner {
     f2.a[0] = seg(h->F1, F, F); f2.nseg = 1; f2.M = rows; f2.out = h->Y; f2.ldo = D;
     if (gemm(f2, L.ffn2, "ffn2")) return 1;
     prof_begin(h, st, PROF_ROW, 2.0 * rows * D * sizeof(TA));
-    ln_mod_silu_kernel<TA, TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
-        (const TA*)h->Y, D, (TA*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
+    if (std::is_same<TA, bf16>::value)
+      ln_mod_silu_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+          (const bf16*)h->Y, D, (bf16*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
+    else
+      ln_mod_silu_kernel<TA, TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+          (const TA*)h->Y, D, (TA*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
     prof_end(h, st);
     LAUNCH_CHECK("ln_mod_silu");
     GemmDesc fo;

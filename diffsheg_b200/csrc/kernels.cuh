@@ -115,6 +115,175 @@ __global__ void ln_mod_silu_kernel(const TIN* y, int ldy, TA* z, int ldz, int D,
 }
 
 // ---------------------------------------------------------------------------------------------
+// bf16 fast paths of the row-wise kernels: one warp per row, 16-byte (8 x bf16) accesses, the row is read
+// ONCE and kept in registers for the second (variance / normalise) pass.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __bfloat162float(h2.x);
+    f[2 * e + 1] = __bfloat162float(h2.y);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
+}
+
+constexpr int FP_MAXCH = 5;  // 16-byte chunks per lane: covers concat rows up to 1280 elements
+
+// feat_prep for bf16 (same contract as feat_prep_kernel).  D % 8 == 0, every segment row 16-byte aligned.
+__global__ void feat_prep_bf16_kernel(bf16* h, int ldh, int D, int n_uncond, int n_rows, const float* nullc, Seg s1, Seg s2,
+                                      Seg s3, int nseg_extra, float* mu, float* rstd) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= n_rows) return;
+  bf16* hr = h + (size_t)row * ldh;
+  if (row < n_uncond) {
+    for (int c = lane; c < D / 8; c += 32) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(hr + c * 8), f);
+      const float4 n0 = __ldg(reinterpret_cast<const float4*>(nullc + c * 8)), n1 = __ldg(reinterpret_cast<const float4*>(nullc + c * 8 + 4));
+      f[0] += n0.x; f[1] += n0.y; f[2] += n0.z; f[3] += n0.w; f[4] += n1.x; f[5] += n1.y; f[6] += n1.z; f[7] += n1.w;
+      *reinterpret_cast<uint4*>(hr + c * 8) = pack8(f);
+    }
+    return;
+  }
+  const int cr = row - n_uncond;
+  const bf16* base[4] = {hr, nullptr, nullptr, nullptr};
+  int kk[4] = {D, 0, 0, 0}, cstart[5];
+  const Seg segs[3] = {s1, s2, s3};
+  for (int s = 0; s < nseg_extra; ++s) {
+    base[1 + s] = reinterpret_cast<const bf16*>(segs[s].ptr) + (size_t)cr * segs[s].ld;
+    kk[1 + s] = segs[s].k;
+  }
+  cstart[0] = 0;
+  int P = 0;
+  for (int s = 0; s < 4; ++s) { cstart[s + 1] = cstart[s] + (kk[s] + 7) / 8; P += kk[s]; }
+  float v[FP_MAXCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < FP_MAXCH; ++i) {
+    const int ch = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    if (ch < cstart[4]) {
+      int s = 0;
+      while (ch >= cstart[s + 1]) ++s;
+      const int c0 = (ch - cstart[s]) * 8;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base[s] + c0), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[i][e] = (c0 + e < kk[s]) ? f[e] : 0.f; sum += v[i][e]; }
+    }
+  }
+  const float mean = warp_sum(sum) / (float)P;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < FP_MAXCH; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < cstart[4]) {
+      int s = 0;
+      while (ch >= cstart[s + 1]) ++s;
+      const int c0 = (ch - cstart[s]) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = (c0 + e < kk[s]) ? v[i][e] - mean : 0.f; var += dlt * dlt; }
+    }
+  }
+  var = warp_sum(var) / (float)P;
+  if (lane == 0) { mu[cr] = mean; rstd[cr] = rsqrtf(var + LN_EPS); }
+}
+
+// rowstats for bf16, D % 8 == 0, D <= 1024
+__global__ void rowstats_bf16_kernel(const bf16* x, int ld, int D, int n_rows, float* mu, float* rstd) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= n_rows) return;
+  const bf16* xr = x + (size_t)row * ld;
+  float v[4][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    if (c < D) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + c), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if ((lane + 32 * i) * 8 < D) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = v[i][e] - mean; var += dlt * dlt; }
+    }
+  }
+  var = warp_sum(var) / (float)D;
+  if (lane == 0) { mu[row] = mean; rstd[row] = rsqrtf(var + LN_EPS); }
+}
+
+// ln_mod_silu for bf16 in / bf16 out, D % 8 == 0, D <= 512
+__global__ void ln_mod_silu_bf16_kernel(const bf16* y, int ldy, bf16* z, int ldz, int D, int n_rows, int T, int B, const float* g,
+                                        const float* b, const float* ss, int ss_ld) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= n_rows) return;
+  const bf16* yr = y + (size_t)row * ldy;
+  bf16* zr = z + (size_t)row * ldz;
+  const float* sc = ss + (size_t)((row / T) % B) * ss_ld;
+  float v[2][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    if (c < D) {
+      unpack8(*reinterpret_cast<const uint4*>(yr + c), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if ((lane + 32 * i) * 8 < D) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = v[i][e] - mean; var += dlt * dlt; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)D + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < D) {
+      float gg[8], bb[8], s1[8], s2[8], o[8];
+      *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(g + c)); *reinterpret_cast<float4*>(gg + 4) = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+      *reinterpret_cast<float4*>(bb) = __ldg(reinterpret_cast<const float4*>(b + c)); *reinterpret_cast<float4*>(bb + 4) = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+      *reinterpret_cast<float4*>(s1) = __ldg(reinterpret_cast<const float4*>(sc + c)); *reinterpret_cast<float4*>(s1 + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+      *reinterpret_cast<float4*>(s2) = __ldg(reinterpret_cast<const float4*>(sc + D + c)); *reinterpret_cast<float4*>(s2 + 4) = __ldg(reinterpret_cast<const float4*>(sc + D + c + 4));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float t = ((v[i][e] - mean) * rstd * gg[e] + bb[e]) * (1.f + s1[e]) + s2[e];
+        o[e] = silu_f(t);
+      }
+      *reinterpret_cast<uint4*>(zr + c) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Linear ("efficient") self-attention core (tr:122-128), one CTA per sample, heads in sequence:
 //   Q' = softmax_d(Q)   K' = softmax_t(K)   A = K'^T V  [HD x HD]   Y = Q' A
 // followed, in the same CTA, by the StylizationBlock prologue over the full D-wide row (needs all
