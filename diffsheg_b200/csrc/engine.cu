@@ -720,7 +720,7 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
     return step_done("dsheg_op_linear");
   }
   // bf16 engine: bf16 operands; bf16 output + bf16 residual when N % 32 == 0 (the engine's layout), else fp32 output
-  const bool bf_out = (N % 32) == 0;
+  const bool bf_out = (N % 64) == 0;
   if (!bf_out && (act != ACT_NONE || residual)) { g_create_error = "op_linear bf16: N % 32 != 0 supports no act / residual"; return 1; }
   bf16 *Ab = nullptr, *Wb = nullptr, *Rb = nullptr, *Ob = nullptr;
   bool ok = cudaMalloc(&Ab, (size_t)M * Kp * 2) == cudaSuccess && cudaMalloc(&Wb, (size_t)N * Kp * 2) == cudaSuccess;
@@ -756,7 +756,7 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
 // Times one tcgen05 GEMM shape (bf16, device-resident random-ish data): mode 0 bias, 1 LN+bias, 2 LN+bias+SiLU,
 // 3 bias+bf16 residual (in place), 4 bias+GELU; bn = 0 (auto) / 128 / 256.  Returns the mean ms over `iters`.
 int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out) {
-  if (K % 64 || N % 32 || !ms_out) { g_create_error = "bench_gemm: need K % 64 == 0, N % 32 == 0"; return 1; }
+  if (K % 64 || N % 64 || !ms_out) { g_create_error = "bench_gemm: need K % 64 == 0, N % 64 == 0"; return 1; }
   bf16 *Ab = nullptr, *Wb = nullptr, *Ob = nullptr;
   float *vec = nullptr;
   if (cudaMalloc(&Ab, (size_t)M * K * 2) != cudaSuccess || cudaMalloc(&Wb, (size_t)N * K * 2) != cudaSuccess ||

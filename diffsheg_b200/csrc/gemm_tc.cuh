@@ -3,19 +3,21 @@
 //   * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a multi-stage smem ring
 //   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16 per instruction), accumulators live in
 //     TMEM (2 x BN columns, double-buffered: the epilogue of tile i overlaps the mainloop of tile i+1)
-//   * 16 epilogue warps (4 TMEM lane quadrants x 4 column groups) read TMEM with tcgen05.ld (one accumulator
-//     row per thread) and apply the fused epilogue -- LayerNorm fold, bias, SiLU / GELU, residual or
-//     positional add, bf16 / fp32 store, optional duplicate store for the two CFG halves.  The epilogue is
-//     specialised at compile time (no per-element branches), bias / column sums are staged in smem once per
-//     tile, row statistics and the residual row segment are fetched BEFORE waiting on the accumulator, so
-//     their latency hides behind the mainloop.  (v0 of this kernel had 4 epilogue warps and a generic
-//     per-element epilogue: ncu showed IPC 0.12 and 5-11 % tensor-pipe activity -- profiles/r01.)
+//   * BN/16 epilogue warps (4 TMEM lane quadrants x BN/64 column groups) read TMEM with tcgen05.ld (one
+//     accumulator row per thread, 64 columns per warp) and apply the fused epilogue -- LayerNorm fold, bias,
+//     SiLU / GELU, residual or positional add, optional duplicate store for the two CFG halves.  The epilogue
+//     is specialised at compile time (no per-element branches); bias / column sums are staged in smem once
+//     per tile; every warp owns a 4 KB swizzled staging box: the bf16 residual box arrives by TMA LOAD (issued
+//     before the accumulator is ready), results leave by TMA STORE (cp.async.bulk.tensor, bulk groups), so all
+//     global traffic of the epilogue is full-line and asynchronous and warps never synchronise with each other.
+//     (History in profiles/r01: v0 = 4 generic epilogue warps, IPC 0.12, 5-11 % tensor pipe; v2 = 16
+//     specialised warps with direct 16-byte global accesses, lg_throttle / long_scoreboard bound.)
 //   * persistent: one CTA per SM walks tiles n-fastest so concurrently running CTAs share the A row-panel
 //     through L2; W panels (<= 2 MB) stay L2-resident
 //   * A is a VIRTUAL CONCAT of up to 4 row-major segments (one tensor map each): the feat_proj input
 //     cat(h, audio, hubert, expr) (transformer.py:304-310) is never materialised.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-3 idle, 4..19 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-3 idle, 4.. = epilogue.
 #pragma once
 #include <cuda.h>
 
@@ -27,18 +29,21 @@ namespace tc {
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_ACC = 2;
-constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int UMMA_K = 16;
+constexpr int CPW = 64;            // accumulator columns per epilogue warp (= one 128-byte bf16 row segment)
+constexpr int STG_BYTES = 32 * CPW * 2;  // per-warp staging box: 32 rows x 64 bf16, 128B-swizzled
+constexpr int BAR_BYTES = 512;
 
 template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int NE = BN / 16;  // epilogue warps
+  static constexpr int NUM_THREADS = 128 + NE * 32;
+  static constexpr int STAGES = BN == 128 ? 5 : 3;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
   static constexpr int VEC_BYTES = NUM_ACC * 2 * BN * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + VEC_BYTES;
-  static constexpr int CPW = BN / 4;  // accumulator columns per epilogue warp
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + NE * STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + VEC_BYTES;
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
@@ -119,7 +124,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
+template <int NTHREADS> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile [rows][64 bf16] (8-row groups of 1024 B): SBO = 1024 B,
 // LBO unused, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
@@ -155,33 +168,38 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
 }
 
 template <int BN, bool LN, int ACT, int RES, bool OUTF32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<BN>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-               const __grid_constant__ CUtensorMap tmW, const Params p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
   using C = Cfg<BN>;
-  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, CPW = C::CPW;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stg_base = smem_base + C::PIPE_BYTES;
+  const uint32_t bar_base = stg_base + NE * STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
-  float* vecs = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + 256);  // [NUM_ACC][2][BN]
+  auto res_bar = [&](int e) { return bar_base + 8u * (2 * STAGES + 2 * NUM_ACC + e); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC + NE);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - smem_base));
+  float* vecs = reinterpret_cast<float*>(gen_base + (bar_base - smem_base) + BAR_BYTES);  // [NUM_ACC][2][BN]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NE); }
+    for (int e = 0; e < NE; ++e) mbar_init(res_bar(e), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (!OUTF32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
   if (warp == 1) {  // TMEM allocation: one full warp, which also owns the dealloc
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS)
@@ -241,38 +259,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ================= epilogue (16 warps) =================
-    const int q = warp & 3;           // TMEM lane quadrant this warp may touch (warp id % 4)
-    const int cg = (warp - 4) >> 2;   // column group
+    // ================= epilogue (NE warps, each 32 rows x 64 columns) =================
+    const int e = warp - 4;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may touch (warp id % 4)
+    const int cg = e >> 2;    // column group
     const int etid = threadIdx.x - 128;
-    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t stg = stg_base + e * STG_BYTES;
+    uint8_t* stg_gen = gen_base + (stg - smem_base);
+    int acc = 0; uint32_t acc_phase = 0, res_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       const int n_tile0 = n_blk * BN;
       // ---- stage per-column vectors for this tile (double-buffered with the accumulator stage)
       float* vb = vecs + acc * 2 * BN;
-      for (int i = etid; i < BN; i += NUM_EPI_WARPS * 32) {
+      for (int i = etid; i < BN; i += NE * 32) {
         const int n = n_tile0 + i;
         vb[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
         if (LN) vb[BN + i] = n < p.N ? __ldg(p.csum + n) : 0.f;
       }
-      epi_bar_sync();
+      epi_bar_sync<NE * 32>();
+      const int m0 = m_blk * BM + q * 32;     // first row of this warp's box
+      const int nc0 = n_tile0 + cg * CPW;     // first column of this warp's box
+      if (!OUTF32) {
+        if (lane == 0) bulk_wait_read0();     // the previous tile's TMA store has finished reading the box
+        __syncwarp();
+        if (RES == RES_BF16 && lane == 0) {   // residual box by TMA, in flight while the mainloop runs
+          mbar_arrive_expect_tx(res_bar(e), STG_BYTES);
+          tma_load_2d(&tmRes, res_bar(e), stg, nc0, m0);
+        }
+      }
       // ---- per-row operands, fetched before the accumulator is ready
-      const int m = m_blk * BM + q * 32 + lane;
+      const int m = m0 + lane;
       const bool row_ok = m < p.M;
       float rs = 1.f, rm = 0.f;  // v = rs * acc + rm * csum[n] + bias[n]
       if (LN && row_ok) { rs = __ldg(p.rstd + m); rm = -rs * __ldg(p.mu + m); }
-      const int nc0 = n_tile0 + cg * CPW;  // first global column of this warp
-      uint4 rres[RES == RES_BF16 ? CPW / 8 : 1];
-      if (RES == RES_BF16) {
-        if (row_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (size_t)m * p.ldr + nc0);
-#pragma unroll
-          for (int u = 0; u < CPW / 8; ++u) rres[u] = rp[u];
-        }
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (RES == RES_BF16) { mbar_wait(res_bar(e), res_phase); res_phase ^= 1; }
 #pragma unroll
       for (int ch = 0; ch < CPW / 32; ++ch) {
         uint32_t r[32];
@@ -293,19 +316,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           v[j] = act_fast<ACT>(t0); v[j + 1] = act_fast<ACT>(t1); v[j + 2] = act_fast<ACT>(t2); v[j + 3] = act_fast<ACT>(t3);
         }
-        if (RES == RES_BF16) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 w = rres[ch * 4 + u];
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
-              v[u * 8 + e * 2] += __bfloat162float(h2.x);
-              v[u * 8 + e * 2 + 1] += __bfloat162float(h2.y);
-            }
-          }
-        }
         if (RES == RES_F32_MOD) {
           if (row_ok) {
             const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + (size_t)(m % p.res_mod) * p.ldr + n0);
@@ -316,10 +326,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
-        if (row_ok) {
-          const size_t o = (size_t)m * p.ldo + n0;
-          if (OUTF32) {
-            float* op = reinterpret_cast<float*>(p.out) + o;
+        if (OUTF32) {
+          if (row_ok) {
+            float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n0;
             if (n0 + 32 <= p.N && (p.ldo & 3) == 0) {
 #pragma unroll
               for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
@@ -327,26 +336,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (n0 + j < p.N) op[j] = v[j];
             }
-          } else {
-            bf16* op = reinterpret_cast<bf16*>(p.out) + o;
+          }
+        } else {
+          // this thread's row of the box: 16-byte chunk c of row `lane` lives at chunk position c ^ (lane & 7)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 w;
-              w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
-              w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
-              w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
-              w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
-              reinterpret_cast<uint4*>(op)[u] = w;
-              if (p.out2) reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + o)[u] = w;
+          for (int u = 0; u < 4; ++u) {
+            uint4* sp = reinterpret_cast<uint4*>(stg_gen + lane * 128 + (((ch * 4 + u) ^ (lane & 7)) << 4));
+            if (RES == RES_BF16) {
+              const uint4 w = *sp;
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k2]);
+                v[u * 8 + k2 * 2] += __bfloat162float(h2.x);
+                v[u * 8 + k2 * 2 + 1] += __bfloat162float(h2.y);
+              }
             }
+            uint4 w;
+            w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
+            w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
+            w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
+            w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
+            *sp = w;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));   // TMEM stage is free for the MMA warp
+      if (!OUTF32) {
+        fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, stg, nc0, m0);         // rows >= M / columns >= N are clipped by the tensor map
+          if (p.out2) tma_store_2d(&tmOut2, stg, nc0, m0);
+          bulk_commit();
+        }
+      }
       if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
     }
+    if (!OUTF32 && lane == 0) bulk_wait0();           // all stores complete before the CTA exits
   }
 
   tc_fence_before();
@@ -377,6 +406,7 @@ inline EncodeTiledFn get_encode_fn() {
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle,
 // out-of-bounds elements read as zero (ragged M / N / K tails need no padding in memory).
 inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
+  // box = [box_rows x 64 columns] = 128-byte rows: operand tiles (K-major) and epilogue boxes share this geometry
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) { *err = "TMA operand not 16-byte aligned"; return false; }
@@ -400,7 +430,7 @@ inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  kern<<<grid, Cfg<BN>::NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
   return cudaGetLastError();
 }
 
@@ -433,13 +463,13 @@ inline int g_bn_override() {
 
 inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err, int bn_force = 0) {
   // vector paths need 16-byte aligned rows; every engine buffer satisfies this
-  if (!d.out_f32 && ((d.ldo % 8) || (d.N % 32))) { *err = "bf16-output GEMM needs N % 32 == 0 and ldo % 8 == 0"; return cudaErrorInvalidValue; }
+  if (!d.out_f32 && ((d.ldo % 8) || (d.N % 64))) { *err = "bf16-output GEMM needs N % 64 == 0 and ldo % 8 == 0"; return cudaErrorInvalidValue; }
   if (d.res && !d.res_f32 && (d.ldr % 8)) { *err = "bf16 residual needs ldr % 8 == 0"; return cudaErrorInvalidValue; }
   if (d.res && d.res_f32 && ((d.ldr % 4) || d.res_mod <= 0)) { *err = "fp32 residual needs ldr % 4 == 0 and res_mod > 0"; return cudaErrorInvalidValue; }
   int bn = bn_force ? bn_force : g_bn_override();
   if (bn != 128 && bn != 256) bn = (d.N % 256 == 0) ? 256 : 128;
   Params p{};
-  CUtensorMap maps[5];
+  CUtensorMap maps[8];
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
   int kb = 0;
   for (int s = 0; s < d.nseg; ++s) {
@@ -452,6 +482,12 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   p.num_kb = kb;
   if (kb * BK != d.Kp) { *err = "GEMM weight K padding does not match the A segments"; return cudaErrorInvalidValue; }
   if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, bn, err)) return cudaErrorInvalidValue;
+  maps[5] = maps[6] = maps[7] = maps[4];
+  if (!d.out_f32) {  // epilogue boxes: 32 rows x 64 columns of the bf16 output / residual
+    if (!make_tmap(&maps[5], d.out, d.M, d.N, d.ldo, 32, err)) return cudaErrorInvalidValue;
+    if (d.out2 && !make_tmap(&maps[6], d.out2, d.M, d.N, d.ldo, 32, err)) return cudaErrorInvalidValue;
+    if (d.res && !d.res_f32 && !make_tmap(&maps[7], d.res, d.M, d.N, d.ldr, 32, err)) return cudaErrorInvalidValue;
+  }
   p.tiles_m = (d.M + BM - 1) / BM; p.tiles_n = (d.N + bn - 1) / bn;
   p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd;
   p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod;
