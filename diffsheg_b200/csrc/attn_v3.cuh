@@ -1,0 +1,302 @@
+// Linear-attention core + StylizationBlock prologue, bf16 fast path (D = 512, 8 heads of 64, T <= 96).
+//
+// One CTA (512 threads) per sample, TWO warps per head.  Per head (reference transformer.py:122-128):
+//   K' = softmax_t(K)   Q' = softmax_d(Q)   A = K'^T V  [64x64]   Y = Q' A  [T x 64]
+// * K and V head tiles land in shared memory with cp.async (16-B chunks, XOR-swizzled so that ldmatrix is
+//   conflict-free without padding); Q goes global -> registers directly as mma A fragments.
+// * both contractions run on tensor cores with warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate): the
+//   64x64 per-head products are far too small for a tcgen05/TMEM pipeline and the kernel only has to keep up
+//   with HBM (32 FLOP per byte).  The two warps of a head split the time rows for the column softmax and for
+//   Y = Q'A, and the l-halves for A^T = V^T K'; A^T (bf16, normalised by 1/sum_t exp K) replaces the dead K
+//   tile in smem and is read back as ldmatrix B fragments.  Named barriers (64 threads) synchronise a pair.
+// * softmax denominators are applied after the products (per column of A, per row of Y) in fp32.
+// * Y (bf16) replaces the dead V tile; after a CTA barrier each warp normalises full 512-wide rows (LayerNorm
+//   over all heads), applies (1+scale), shift and SiLU (transformer.py:92-96) and writes z with 1 KB coalesced
+//   row stores.  The attention output never round-trips through HBM before the out-proj GEMM.
+// Algorithmic HBM traffic: read q,k,v + write z = 4 * T * 512 * 2 bytes per sample.
+// (v2 of this kernel -- one warp per head, A^T in registers, profiles/r01 -- was latency bound: IPC 0.35 with
+//  two warps per scheduler and 19 % of the HBM roofline.)
+#pragma once
+#include "common.cuh"
+
+namespace dsheg {
+namespace av3 {
+
+constexpr int TP = 96;                  // padded time rows (6 m-tiles of 16)
+constexpr int HD = 64, NH = 8, D = 512;
+constexpr int NTHREADS = 512;
+constexpr int TILE_BYTES = TP * HD * 2;  // 12288
+constexpr int RED_FLOATS = NH * 2 * HD;  // per-(head, half) column partials
+constexpr int SMEM_BYTES = NH * 2 * TILE_BYTES + 2 * RED_FLOATS * 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pair_sync(int head) { asm volatile("bar.sync %0, 64;" ::"r"(head + 1) : "memory"); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w);
+  return make_float2(__bfloat162float(v.x), __bfloat162float(v.y));
+}
+// byte offset of 16-B chunk `c` (0..7) of row `r` inside a swizzled [rows][64] bf16 tile
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// Q fragments of one 16-row m-tile straight from global memory (rows >= T read as zero)
+__device__ __forceinline__ void load_q_tile(const bf16* qhead, int row0, int T, int g, int q, uint32_t (&qa)[4][4]) {
+  const int r0 = row0 + g, r1 = row0 + g + 8;
+  const uint32_t* p0 = reinterpret_cast<const uint32_t*>(qhead + (size_t)r0 * (3 * D));
+  const uint32_t* p1 = reinterpret_cast<const uint32_t*>(qhead + (size_t)r1 * (3 * D));
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    qa[ks][0] = r0 < T ? __ldg(p0 + ks * 8 + q) : 0u;
+    qa[ks][1] = r1 < T ? __ldg(p1 + ks * 8 + q) : 0u;
+    qa[ks][2] = r0 < T ? __ldg(p0 + ks * 8 + 4 + q) : 0u;
+    qa[ks][3] = r1 < T ? __ldg(p1 + ks * 8 + 4 + q) : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
+               const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = warp >> 1, half = warp & 1;
+  const int g = lane >> 2, q = lane & 3;
+  const int smp = blockIdx.x;
+  const size_t row0 = (size_t)smp * T;
+  uint8_t* Ks = sm + head * 2 * TILE_BYTES;
+  uint8_t* Vs = Ks + TILE_BYTES;
+  float* red = reinterpret_cast<float*>(sm + NH * 2 * TILE_BYTES);  // [NH][2][HD] column max partials
+  float* red2 = red + RED_FLOATS;                                    // [NH][2][HD] column sum partials
+  const uint32_t ks_addr = smem_addr(Ks), vs_addr = smem_addr(Vs);
+  const bf16* qhead = qkv + row0 * (3 * D) + head * HD;
+  const int n_mt = (T + 15) >> 4;  // 16-row tiles that contain valid frames
+  const int Tpad = n_mt * 16;
+
+  // ---- 1. K and V head tiles -> smem (cp.async); the pair splits the rows by parity
+  for (int i = lane; i < ((T - half + 1) >> 1) * 8; i += 32) {
+    const int r = 2 * (i >> 3) + half, c = i & 7;
+    const bf16* src = qhead + (size_t)r * (3 * D) + c * 8;
+    cp_async16(ks_addr + swz(r, c), src + D);
+    cp_async16(vs_addr + swz(r, c), src + 2 * D);
+  }
+  if (half == 0) {
+    for (int i = lane; i < (Tpad - T) * 8; i += 32) {
+      const int r = T + (i >> 3), c = i & 7;
+      *reinterpret_cast<uint4*>(Vs + swz(r, c)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // ---- 2. this warp's first Q m-tile (global -> registers) overlaps the cp.async latency
+  uint32_t qa[4][4];
+  if (half < n_mt) load_q_tile(qhead, half * 16, T, g, q, qa);
+  cp_async_wait_all();
+  pair_sync(head);
+
+  // ---- 3. softmax over time per K column: lane owns columns 2*lane, 2*lane+1; the pair splits the rows
+  {
+    const int c = lane >> 2, w = lane & 3;
+    const int rsplit = (T + 1) >> 1;
+    const int r_lo = half ? rsplit : 0, r_hi = half ? T : rsplit;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 8
+    for (int r = r_lo; r < r_hi; ++r) {
+      const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(Ks + swz(r, c) + w * 4));
+      m0 = fmaxf(m0, v.x);
+      m1 = fmaxf(m1, v.y);
+    }
+    float* myred = red + (head * 2 + half) * HD;
+    const float* otred = red + (head * 2 + (half ^ 1)) * HD;
+    myred[2 * lane] = m0;
+    myred[2 * lane + 1] = m1;
+    pair_sync(head);
+    m0 = fmaxf(m0, otred[2 * lane]);
+    m1 = fmaxf(m1, otred[2 * lane + 1]);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int r = r_lo; r < r_hi; ++r) {
+      uint32_t* p = reinterpret_cast<uint32_t*>(Ks + swz(r, c) + w * 4);
+      const float2 v = unpack2(*p);
+      // round first so that the normaliser is the sum of exactly what the tensor core multiplies
+      const __nv_bfloat162 ex = __floats2bfloat162_rn(__expf(v.x - m0), __expf(v.y - m1));
+      s0 += __bfloat162float(ex.x);
+      s1 += __bfloat162float(ex.y);
+      *p = *reinterpret_cast<const uint32_t*>(&ex);
+    }
+    float* myred2 = red2 + (head * 2 + half) * HD;
+    myred2[2 * lane] = s0;
+    myred2[2 * lane + 1] = s1;
+    if (half == 1) {
+      for (int i = lane; i < (Tpad - T) * 8; i += 32) {
+        const int r = T + (i >> 3), cc = i & 7;
+        *reinterpret_cast<uint4*>(Ks + swz(r, cc)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    pair_sync(head);
+  }
+
+  // ---- 4. A^T[l][d] = sum_t V[t][l] K'[t][d] for this warp's l-half (two 16-row m-tiles)
+  float acc[2][8][4];
+  {
+    const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
+    for (int kt = 0; kt < n_mt; ++kt) {  // 16 frames per k-step
+      uint32_t a0[4], a1[4];
+      {
+        const int r = kt * 16 + rr + ((mat >> 1) << 3);
+        ldsm_x4_trans(vs_addr + swz(r, 4 * half + (mat & 1)), a0[0], a0[1], a0[2], a0[3]);
+        ldsm_x4_trans(vs_addr + swz(r, 4 * half + 2 + (mat & 1)), a1[0], a1[1], a1[2], a1[3]);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // two d n-tiles per ldmatrix.x4
+        uint32_t b0, b1, b2, b3;
+        const int r = kt * 16 + rr + ((mat & 1) << 3), c = 2 * np + (mat >> 1);
+        ldsm_x4_trans(ks_addr + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(acc[0][2 * np], a0, b0, b1);
+        mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
+        mma_bf16(acc[1][2 * np], a1, b0, b1);
+        mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
+      }
+    }
+  }
+  pair_sync(head);  // both warps are done reading K' and V: K's tile now receives A^T, V's tile Y
+  {
+    const float* sa = red2 + (head * 2) * HD;
+    const float* sb = sa + HD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int d0 = 8 * nt + 2 * q;
+      const float i0 = 1.f / (sa[d0] + sb[d0]), i1 = 1.f / (sa[d0 + 1] + sb[d0 + 1]);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int l = 32 * half + 16 * mi + g;
+        *reinterpret_cast<uint32_t*>(Ks + swz(l, nt) + q * 4) = pack2(acc[mi][nt][0] * i0, acc[mi][nt][1] * i1);
+        *reinterpret_cast<uint32_t*>(Ks + swz(l + 8, nt) + q * 4) = pack2(acc[mi][nt][2] * i0, acc[mi][nt][3] * i1);
+      }
+    }
+  }
+  pair_sync(head);  // A^T[l][d] (bf16, 64 x 64) complete
+
+  // ---- 5. Y[t][l] = softmax_d(Q)[t][:] . A for this warp's m-tiles (mt = half, half+2, ...); bf16 Y -> V tile
+  {
+    const int mat = lane >> 3, rr = lane & 7;
+    for (int mt = half; mt < n_mt; mt += 2) {
+      // row softmax numerators in registers: this lane holds 16 of the 64 d's of rows g and g+8; the quad holds all
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 a0 = unpack2(qa[ks][0]), a1 = unpack2(qa[ks][1]), a2 = unpack2(qa[ks][2]), a3 = unpack2(qa[ks][3]);
+        mx0 = fmaxf(mx0, fmaxf(fmaxf(a0.x, a0.y), fmaxf(a2.x, a2.y)));
+        mx1 = fmaxf(mx1, fmaxf(fmaxf(a1.x, a1.y), fmaxf(a3.x, a3.y)));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sm0 = 0.f, sm1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 a0 = unpack2(qa[ks][0]), a1 = unpack2(qa[ks][1]), a2 = unpack2(qa[ks][2]), a3 = unpack2(qa[ks][3]);
+        const __nv_bfloat162 e0 = __floats2bfloat162_rn(__expf(a0.x - mx0), __expf(a0.y - mx0));
+        const __nv_bfloat162 e2 = __floats2bfloat162_rn(__expf(a2.x - mx0), __expf(a2.y - mx0));
+        const __nv_bfloat162 e1 = __floats2bfloat162_rn(__expf(a1.x - mx1), __expf(a1.y - mx1));
+        const __nv_bfloat162 e3 = __floats2bfloat162_rn(__expf(a3.x - mx1), __expf(a3.y - mx1));
+        sm0 += __bfloat162float(e0.x) + __bfloat162float(e0.y) + __bfloat162float(e2.x) + __bfloat162float(e2.y);
+        sm1 += __bfloat162float(e1.x) + __bfloat162float(e1.y) + __bfloat162float(e3.x) + __bfloat162float(e3.y);
+        pa[ks][0] = *reinterpret_cast<const uint32_t*>(&e0);
+        pa[ks][1] = *reinterpret_cast<const uint32_t*>(&e1);
+        pa[ks][2] = *reinterpret_cast<const uint32_t*>(&e2);
+        pa[ks][3] = *reinterpret_cast<const uint32_t*>(&e3);
+      }
+      sm0 += __shfl_xor_sync(0xffffffffu, sm0, 1); sm0 += __shfl_xor_sync(0xffffffffu, sm0, 2);
+      sm1 += __shfl_xor_sync(0xffffffffu, sm1, 1); sm1 += __shfl_xor_sync(0xffffffffu, sm1, 2);
+      if (mt + 2 < n_mt) load_q_tile(qhead, (mt + 2) * 16, T, g, q, qa);  // prefetch under the MMAs
+      float y[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f; }
+#pragma unroll
+      for (int kd = 0; kd < 4; ++kd) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // B fragments of two l n-tiles per ldmatrix.x4 from A^T[l][d]
+          uint32_t b0, b1, b2, b3;
+          const int r = 16 * np + rr + ((mat >> 1) << 3), c = 2 * kd + (mat & 1);
+          ldsm_x4(ks_addr + swz(r, c), b0, b1, b2, b3);
+          mma_bf16(y[2 * np], pa[kd], b0, b1);
+          mma_bf16(y[2 * np + 1], pa[kd], b2, b3);
+        }
+      }
+      const float r0 = 1.f / sm0, r1 = 1.f / sm1;
+      const int ra = mt * 16 + g, rb = ra + 8;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(Vs + swz(ra, nt) + q * 4) = pack2(y[nt][0] * r0, y[nt][1] * r0);
+        *reinterpret_cast<uint32_t*>(Vs + swz(rb, nt) + q * 4) = pack2(y[nt][2] * r1, y[nt][3] * r1);
+      }
+    }
+  }
+  __syncthreads();  // all 8 heads of the sample are in smem
+
+  // ---- 6. StylizationBlock prologue over full rows: LN(512) * (1 + scale) + shift, SiLU; one warp per row
+  {
+    const int hh = lane >> 2, c0 = (lane & 3) * 2;  // this lane covers head hh, 16-B chunks c0 and c0+1
+    const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
+    const int col0 = hh * HD + c0 * 8;
+    const float* sc = ss + (size_t)(smp % B) * ss_ld;
+    float gg[16], bb[16], s1[16], s2[16];
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + col0 + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + e));
+      gg[e] = a.x; gg[e + 1] = a.y; gg[e + 2] = a.z; gg[e + 3] = a.w;
+      bb[e] = b4.x; bb[e + 1] = b4.y; bb[e + 2] = b4.z; bb[e + 3] = b4.w;
+      s1[e] = 1.f + c4.x; s1[e + 1] = 1.f + c4.y; s1[e + 2] = 1.f + c4.z; s1[e + 3] = 1.f + c4.w;
+      s2[e] = d4.x; s2[e + 1] = d4.y; s2[e + 2] = d4.z; s2[e + 3] = d4.w;
+    }
+    for (int t = warp; t < T; t += NTHREADS / 32) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
+      const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
+      const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      float v[16];
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float2 p2 = unpack2(w[e]); v[2 * e] = p2.x; v[2 * e + 1] = p2.y; s += p2.x + p2.y; }
+      const float mean = warp_sum(s) * (1.f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { const float dlt = v[e] - mean; var += dlt * dlt; }
+      const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + 1e-5f);
+      uint32_t o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float a0 = ((v[2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e]) * s1[2 * e] + s2[2 * e];
+        const float a1 = ((v[2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]) * s1[2 * e + 1] + s2[2 * e + 1];
+        o[e] = pack2(silu_f(a0), silu_f(a1));
+      }
+      uint4* dst = reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+}  // namespace av3
+}  // namespace dsheg

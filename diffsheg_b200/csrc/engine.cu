@@ -13,6 +13,7 @@
 
 #include "../../include/diffsheg_b200.h"
 #include "attn_v2.cuh"
+#include "attn_v3.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -63,7 +64,8 @@ struct dsheg_handle {
   std::unordered_map<std::string, DevTensor> tensors;
   bool finalized = false;
   int gemm_engine = 1;  // 1 = tcgen05 (bf16 mode default), 0 = SIMT
-  int attn_v2 = 1;      // bf16 mode: tensor-core attention kernel (0 = generic SIMT kernel, DSHEG_ATTN=v1)
+  int attn_v2 = 1;      // bf16 mode: 1 = tensor-core attention (attn_v3), 2 = previous one-warp-per-head kernel
+                        // (DSHEG_ATTN=v2), 0 = generic SIMT kernel (DSHEG_ATTN=v1)
   int64_t launches = 0;
   // resolved weights
   const float* freqs = nullptr;
@@ -283,7 +285,9 @@ struct Runner {
     const int HD = D / H;
     // algorithmic traffic: read q,k,v + write z, all in the activation type (4*rows*D*sizeof)
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
-    if (std::is_same<TA, bf16>::value && HD == 64 && D == av2::D && H == av2::NH && T <= av2::TP && h->attn_v2) {
+    if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 1) {
+      av3::attn_v3_kernel<<<n_samples, av3::NTHREADS, av3::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
+    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av2::D && H == av2::NH && T <= av2::TP && h->attn_v2 == 2) {
       av2::attn_v2_kernel<<<n_samples, 256, av2::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 64) {
       attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
@@ -486,6 +490,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (eng && !strcmp(eng, "simt")) h->gemm_engine = 0;
   const char* att = getenv("DSHEG_ATTN");
   if (att && !strcmp(att, "v1")) h->attn_v2 = 0;
+  if (att && !strcmp(att, "v2")) h->attn_v2 = 2;
 
   const dsheg_config& c = h->cfg;
   const size_t G = c.classifier_free ? 2 : 1;
@@ -528,6 +533,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   cudaFuncSetAttribute(attn_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(attn_kernel<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
+  cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
   cudaFuncSetAttribute(hubconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
   cudaFuncSetAttribute(hubconv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
   e = cudaGetLastError();
@@ -821,10 +827,17 @@ int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, c
 
 int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_b, const float* scale_shift, void* z, int32_t Bn,
                             int32_t T, void* stream) {
-  if (T > av2::TP || T < 1) { g_create_error = "op_attention_bf16: T must be <= 96"; return 1; }
-  cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
-  av2::attn_v2_kernel<<<Bn, 256, av2::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b, scale_shift,
-                                                                          2 * av2::D);
+  if (T > av3::TP || T < 1) { g_create_error = "op_attention_bf16: T must be <= 96"; return 1; }
+  const char* att = getenv("DSHEG_ATTN");
+  if (att && !strcmp(att, "v2")) {
+    cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
+    av2::attn_v2_kernel<<<Bn, 256, av2::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b, scale_shift,
+                                                                            2 * av2::D);
+  } else {
+    cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
+    av3::attn_v3_kernel<<<Bn, av3::NTHREADS, av3::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
+                                                                                      scale_shift, 2 * av3::D);
+  }
   return step_done("dsheg_op_attention_bf16");
 }
 

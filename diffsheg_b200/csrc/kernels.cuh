@@ -136,9 +136,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
-constexpr int FP_MAXCH = 5;  // 16-byte chunks per lane: covers concat rows up to 1280 elements
-
-// feat_prep for bf16 (same contract as feat_prep_kernel).  D % 8 == 0, every segment row 16-byte aligned.
+// feat_prep for bf16 (same contract as feat_prep_kernel).  D % 8 == 0, D <= 512, extra segments <= 256 wide,
+// every segment row 16-byte aligned.
 __global__ void feat_prep_bf16_kernel(bf16* h, int ldh, int D, int n_uncond, int n_rows, const float* nullc, Seg s1, Seg s2,
                                       Seg s3, int nseg_extra, float* mu, float* rstd) {
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -156,44 +155,52 @@ __global__ void feat_prep_bf16_kernel(bf16* h, int ldh, int D, int n_uncond, int
     return;
   }
   const int cr = row - n_uncond;
-  const bf16* base[4] = {hr, nullptr, nullptr, nullptr};
-  int kk[4] = {D, 0, 0, 0}, cstart[5];
-  const Seg segs[3] = {s1, s2, s3};
-  for (int s = 0; s < nseg_extra; ++s) {
-    base[1 + s] = reinterpret_cast<const bf16*>(segs[s].ptr) + (size_t)cr * segs[s].ld;
-    kk[1 + s] = segs[s].k;
-  }
-  cstart[0] = 0;
-  int P = 0;
-  for (int s = 0; s < 4; ++s) { cstart[s + 1] = cstart[s] + (kk[s] + 7) / 8; P += kk[s]; }
-  float v[FP_MAXCH][8];
+  // h: up to 2 chunks per lane (D <= 512); each extra segment: 1 chunk per lane (k <= 256)
+  float vh[2][8], vx[3][8];
   float sum = 0.f;
+  int P = D;
 #pragma unroll
-  for (int i = 0; i < FP_MAXCH; ++i) {
-    const int ch = lane + 32 * i;
+  for (int i = 0; i < 2; ++i) {
+    const int c = (lane + 32 * i) * 8;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
-    if (ch < cstart[4]) {
-      int s = 0;
-      while (ch >= cstart[s + 1]) ++s;
-      const int c0 = (ch - cstart[s]) * 8;
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(base[s] + c0), f);
+    for (int e = 0; e < 8; ++e) vh[i][e] = 0.f;
+    if (c < D) {
+      unpack8(*reinterpret_cast<const uint4*>(hr + c), vh[i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { v[i][e] = (c0 + e < kk[s]) ? f[e] : 0.f; sum += v[i][e]; }
+      for (int e = 0; e < 8; ++e) sum += vh[i][e];
+    }
+  }
+  const Seg segs[3] = {s1, s2, s3};
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vx[s][e] = 0.f;
+    if (s < nseg_extra) {
+      const int c = lane * 8, k = segs[s].k;
+      P += k;
+      if (c < k) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(segs[s].ptr) + (size_t)cr * segs[s].ld + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { vx[s][e] = (c + e < k) ? f[e] : 0.f; sum += vx[s][e]; }
+      }
     }
   }
   const float mean = warp_sum(sum) / (float)P;
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < FP_MAXCH; ++i) {
-    const int ch = lane + 32 * i;
-    if (ch < cstart[4]) {
-      int s = 0;
-      while (ch >= cstart[s + 1]) ++s;
-      const int c0 = (ch - cstart[s]) * 8;
+  for (int i = 0; i < 2; ++i) {
+    if ((lane + 32 * i) * 8 < D) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float dlt = (c0 + e < kk[s]) ? v[i][e] - mean : 0.f; var += dlt * dlt; }
+      for (int e = 0; e < 8; ++e) { const float dlt = vh[i][e] - mean; var += dlt * dlt; }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s < nseg_extra) {
+      const int c = lane * 8, k = segs[s].k;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = (c + e < k) ? vx[s][e] - mean : 0.f; var += dlt * dlt; }
     }
   }
   var = warp_sum(var) / (float)P;
@@ -268,11 +275,15 @@ __global__ void ln_mod_silu_bf16_kernel(const bf16* y, int ldy, bf16* z, int ldz
   for (int i = 0; i < 2; ++i) {
     const int c = (lane + 32 * i) * 8;
     if (c < D) {
-      float gg[8], bb[8], s1[8], s2[8], o[8];
-      *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(g + c)); *reinterpret_cast<float4*>(gg + 4) = __ldg(reinterpret_cast<const float4*>(g + c + 4));
-      *reinterpret_cast<float4*>(bb) = __ldg(reinterpret_cast<const float4*>(b + c)); *reinterpret_cast<float4*>(bb + 4) = __ldg(reinterpret_cast<const float4*>(b + c + 4));
-      *reinterpret_cast<float4*>(s1) = __ldg(reinterpret_cast<const float4*>(sc + c)); *reinterpret_cast<float4*>(s1 + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
-      *reinterpret_cast<float4*>(s2) = __ldg(reinterpret_cast<const float4*>(sc + D + c)); *reinterpret_cast<float4*>(s2 + 4) = __ldg(reinterpret_cast<const float4*>(sc + D + c + 4));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c)), g1 = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(sc + c)), p1 = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(sc + D + c)), q1 = __ldg(reinterpret_cast<const float4*>(sc + D + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float s1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      const float s2[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float t = ((v[i][e] - mean) * rstd * gg[e] + bb[e]) * (1.f + s1[e]) + s2[e];
