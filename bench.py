@@ -137,6 +137,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_ref_cuda(args):
+    """R-cuda row of BASELINE.md: the reference's eager torch op stream (oracle port) on the SAME GPU, fp32, torch default
+    matmul precision (TF32 off) and with TF32 on -- the denominator of north_star's >= 10x target.  Informational."""
+    from diffsheg_b200 import synth
+    from oracle import diffusion as odiff
+    cfg = synth.make_cfg("show")
+    B, T = args.ref_cuda, cfg["n_poses"]
+    sd = {k: v.cuda() for k, v in synth.make_state_dict(cfg, seed=1).items()}
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=2).items()}
+    d = odiff.OracleDiffusion(1000, "ddim25")
+    den = odiff.make_denoise(sd, cfg, inp["mel"], inp["person_id"], inp["hubert"])
+    rows = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            d.ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"], device="cuda")  # warm-up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            d.ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"], device="cuda")
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rows[name] = {"ms_per_step": ms, "frames_per_s": B * T / (ms / 1e3)}
+    print(json.dumps({"impl": "reference-op-stream torch-cuda eager (oracle port)", "metric": METRIC, "unit": UNIT, "batch": B,
+                      "note": "no generate_src_mask host syncs (SURVEY F8): an upper bound on the real reference", "rows": rows}))
+
+
 def run_ours(args):
     from diffsheg_b200 import FusedSpacedDiffusion, FusedUniDiffuser, generate_batch, get_named_beta_schedule, space_timesteps, synth
     from diffsheg_b200.dist import gather_motion
@@ -258,9 +287,12 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=4, help="bounded CPU sample of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cuda", type=int, default=0, help="time the reference op stream (oracle port) eagerly on the GPU at this batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.ref_cuda:
+        run_ref_cuda(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

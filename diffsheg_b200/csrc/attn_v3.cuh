@@ -261,15 +261,15 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
     const int col0 = hh * HD + c0 * 8;
     const float* sc = ss + (size_t)(smp % B) * ss_ld;
-    float gg[16], bb[16], s1[16], s2[16];
+    // per-column constants folded once:  t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*G + Bc
+    float G[16], Bc[16];
 #pragma unroll
     for (int e = 0; e < 16; e += 4) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
       const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + col0 + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + e));
-      gg[e] = a.x; gg[e + 1] = a.y; gg[e + 2] = a.z; gg[e + 3] = a.w;
-      bb[e] = b4.x; bb[e + 1] = b4.y; bb[e + 2] = b4.z; bb[e + 3] = b4.w;
-      s1[e] = 1.f + c4.x; s1[e + 1] = 1.f + c4.y; s1[e + 2] = 1.f + c4.z; s1[e + 3] = 1.f + c4.w;
-      s2[e] = d4.x; s2[e + 1] = d4.y; s2[e + 2] = d4.z; s2[e + 3] = d4.w;
+      G[e] = a.x * (1.f + c4.x); G[e + 1] = a.y * (1.f + c4.y); G[e + 2] = a.z * (1.f + c4.z); G[e + 3] = a.w * (1.f + c4.w);
+      Bc[e] = fmaf(b4.x, 1.f + c4.x, d4.x); Bc[e + 1] = fmaf(b4.y, 1.f + c4.y, d4.y);
+      Bc[e + 2] = fmaf(b4.z, 1.f + c4.z, d4.z); Bc[e + 3] = fmaf(b4.w, 1.f + c4.w, d4.w);
     }
     for (int t = warp; t < T; t += NTHREADS / 32) {
       const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
@@ -282,14 +282,18 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
       const float mean = warp_sum(s) * (1.f / D);
       float var = 0.f;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) { const float dlt = v[e] - mean; var += dlt * dlt; }
+      for (int e = 0; e < 16; ++e) { v[e] -= mean; var = fmaf(v[e], v[e], var); }
       const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + 1e-5f);
       uint32_t o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float a0 = ((v[2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e]) * s1[2 * e] + s2[2 * e];
-        const float a1 = ((v[2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]) * s1[2 * e + 1] + s2[2 * e + 1];
-        o[e] = pack2(silu_f(a0), silu_f(a1));
+        // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
+        const float h0 = 0.5f * fmaf(v[2 * e] * rstd, G[2 * e], Bc[2 * e]);
+        const float h1 = 0.5f * fmaf(v[2 * e + 1] * rstd, G[2 * e + 1], Bc[2 * e + 1]);
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        o[e] = pack2(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
       }
       uint4* dst = reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0);
       dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
