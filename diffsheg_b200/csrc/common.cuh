@@ -71,6 +71,16 @@ struct GemmDesc {
   int ldo = 0;
   int out_f32 = 0;   // store fp32 instead of the activation type
   void* out2 = nullptr;  // optional duplicate store (same ld / type as out)
+  // ---- fused LayerNorm statistics (tcgen05 engine only; N == 512 residual-stream GEMMs) -------------------
+  // producer side (residual variants): per row and 64-column group, (sum, sum of squares) of the stored output
+  float2* ps_out = nullptr;      // [M][N/64]
+  const float* nullc = nullptr;  // [N] added to rows m < n_uncond (next layer's feat_proj(null_cond_emb) constant)
+  int n_uncond = 0;
+  // consumer side (LN-fold variants): mu / rstd rebuilt from the partials (+ optional per-row extra partial)
+  const float2* ps_in = nullptr;  // [M][ps_slots]
+  const float2* cs_in = nullptr;  // [M] (sum, sumsq) of the conditioning part of the virtual concat, or null
+  int ps_slots = 0;
+  int ps_P = 0;                   // number of elements the LayerNorm runs over
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -78,6 +78,8 @@ struct dsheg_handle {
   size_t arena_bytes = 0;
   void *H, *QKV, *Z, *Y, *F1, *XF, *HUB[2], *EXPR, *AUD256, *A0, *A1, *XIN, *EMBS[2];
   float *Y32, *O, *MID, *MU, *RSTD, *MU2, *RSTD2, *SIN, *TEH, *TEMB, *SSA, *PIDH, *PIDE[2], *SS[2];
+  float2 *PS, *CS;      // fused LayerNorm statistics: per-row / per-64-column partials, conditioning partials
+  int fuse_stats = 1;   // bf16 + tcgen05 engine: LN statistics come from the producer GEMM epilogues (DSHEG_FUSE_STATS=0 disables)
   int ldE = 0, ldXin = 0, ldO = 0;
   // window state
   int B = 0, T = 0;
@@ -231,12 +233,36 @@ struct Runner {
 
   // One LinearTemporalDiffusionTransformerLayer (tr:300-346) on `rows` hidden rows of width D.
   //   hin/hout: residual stream in / out (may alias);  n_uncond: leading CFG-null rows
+  //   stats_in:   the LayerNorm partials PS of hin are valid (written by the previous layer's ffn_out epilogue,
+  //               which also added this layer's null-row constant to the CFG-null rows)
+  //   next_nullc: when non-null, ffn_out emits PS for the next layer and adds next_nullc to the CFG-null rows
   int layer(const LayerW& L, TA* hin, int ld_hin, TA* hmid, TA* hout, int ld_hout, int rows, int n_uncond, int D, int F,
-            int H, const Seg* extra, int n_extra, const float* ss, int ss_ld, int ssB, int T) {
+            int H, const Seg* extra, int n_extra, const float* ss, int ss_ld, int ssB, int T, bool stats_in = false,
+            bool emit_stats = false, const float* next_nullc = nullptr) {
     const int warps_per_block = 8;
     TA* hcur = hin;
     int ldc = ld_hin;
-    if (L.has_feat) {
+    const int slots = D / 64;
+    if (L.has_feat && stats_in) {
+      // K7, fused: statistics of the virtual concat = residual-stream partials (PS) + conditioning partials (CS)
+      const int n_cond = rows - n_uncond;
+      TA* hc = hin + (size_t)n_uncond * ld_hin;
+      int P = D;
+      for (int i = 0; i < n_extra; ++i) P += extra[i].k;
+      GemmDesc g1;
+      g1.a[0] = seg(hc, ld_hin, D);
+      for (int i = 0; i < n_extra; ++i) g1.a[1 + i] = extra[i];
+      g1.nseg = 1 + n_extra; g1.M = n_cond;
+      g1.csum = L.feat1.csum; g1.act = ACT_SILU;
+      g1.ps_in = h->PS + (size_t)n_uncond * slots; g1.cs_in = h->CS; g1.ps_slots = slots; g1.ps_P = P;
+      g1.out = h->F1; g1.ldo = 2 * D;
+      if (gemm(g1, L.feat1, "feat1")) return 1;
+      GemmDesc g2;
+      g2.a[0] = seg(h->F1, 2 * D, 2 * D); g2.nseg = 1; g2.M = n_cond;
+      g2.res = hc; g2.ldr = ld_hin; g2.out = hc; g2.ldo = ld_hin;
+      g2.ps_out = h->PS + (size_t)n_uncond * slots;  // refreshed partials of the cond rows for the QKV LayerNorm
+      if (gemm(g2, L.feat2, "feat2")) return 1;
+    } else if (L.has_feat) {
       // K7: LayerNorm(P) stats over the virtual concat + null-row constant for the uncond half
       const int n_cond = rows - n_uncond;
       Seg e3[3] = {seg(nullptr, 0, 0), seg(nullptr, 0, 0), seg(nullptr, 0, 0)};
@@ -268,6 +294,10 @@ struct Runner {
       if (gemm(g2, L.feat2, "feat2")) return 1;
     }
     // K8: LayerNorm(D) folded into the fused QKV projection
+    GemmDesc gq;
+    if (L.has_feat && stats_in) {
+      gq.ps_in = h->PS; gq.ps_slots = slots; gq.ps_P = D;
+    } else {
     prof_begin(h, st, PROF_ROW, (double)rows * D * sizeof(TA));
     if (std::is_same<TA, bf16>::value)
       rowstats_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>((const bf16*)hcur, ldc, D, rows, h->MU2, h->RSTD2);
@@ -275,9 +305,10 @@ struct Runner {
       rowstats_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(hcur, ldc, D, rows, h->MU2, h->RSTD2);
     prof_end(h, st);
     LAUNCH_CHECK("rowstats");
-    GemmDesc gq;
+    gq.mu = h->MU2; gq.rstd = h->RSTD2;
+    }
     gq.a[0] = seg(hcur, ldc, D); gq.nseg = 1; gq.M = rows;
-    gq.csum = L.qkv.csum; gq.mu = h->MU2; gq.rstd = h->RSTD2;
+    gq.csum = L.qkv.csum;
     gq.out = h->QKV; gq.ldo = 3 * D;
     if (gemm(gq, L.qkv, "qkv")) return 1;
     // K9 + K10 prologue: linear attention, then LN * (1+scale) + shift, SiLU
@@ -323,6 +354,7 @@ struct Runner {
     GemmDesc fo;
     fo.a[0] = seg(h->Z, D, D); fo.nseg = 1; fo.M = rows;
     fo.res = hmid; fo.ldr = D; fo.out = hout; fo.ldo = ld_hout;
+    if (emit_stats) { fo.ps_out = h->PS; fo.nullc = next_nullc; fo.n_uncond = n_uncond; }
     if (gemm(fo, L.ffn_out, "ffn_out")) return 1;
     return 0;
   }
@@ -422,9 +454,16 @@ struct Runner {
       extra[n_extra++] = seg(h->XF, c.aud_latent_dim, c.aud_latent_dim);
       extra[n_extra++] = seg(h->HUB[n], HC_CO, HC_CO);
       if (n == 1) extra[n_extra++] = seg(h->EXPR, h->ldE, c.expression_dim);  // tr:506-507,533-535
+      const bool fused = std::is_same<TA, bf16>::value && h->gemm_engine == 1 && h->fuse_stats && D == 512;
+      if (fused) {
+        cond_stats_bf16_kernel<<<(R1 + 7) / 8, 256, 0, st>>>(extra[0], extra[1], n_extra > 2 ? extra[2] : extra[0], n_extra, R1, h->CS);
+        LAUNCH_CHECK("cond_stats");
+      }
       for (int l = 0; l < L; ++l) {
+        const bool last = (l + 1 == L);
         if (layer(nw.layers[l], Hu, D, Hu, Hu, D, R, two ? R1 : 0, D, F, c.num_heads, extra, n_extra,
-                  h->SS[n] + (size_t)l * 4 * D, L * 4 * D, B, T))
+                  h->SS[n] + (size_t)l * 4 * D, L * 4 * D, B, T, fused && l > 0, fused && !last,
+                  (fused && !last && two) ? nw.layers[l + 1].nullc : nullptr))
           return 1;
       }
       GemmDesc go;  // K12: out projection (fp32 result)
@@ -491,6 +530,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   const char* att = getenv("DSHEG_ATTN");
   if (att && !strcmp(att, "v1")) h->attn_v2 = 0;
   if (att && !strcmp(att, "v2")) h->attn_v2 = 2;
+  const char* fs = getenv("DSHEG_FUSE_STATS");
+  if (fs && !strcmp(fs, "0")) h->fuse_stats = 0;
 
   const dsheg_config& c = h->cfg;
   const size_t G = c.classifier_free ? 2 : 1;
@@ -512,6 +553,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
       {(void**)&h->PIDH, (size_t)c.max_batch * E * 4}, {(void**)&h->PIDE[0], (size_t)c.max_batch * E * 4},
       {(void**)&h->PIDE[1], (size_t)c.max_batch * E * 4}, {(void**)&h->SS[0], (size_t)c.max_batch * L * 4 * D * 4},
       {(void**)&h->SS[1], (size_t)c.max_batch * L * 4 * D * 4},
+      {(void**)&h->PS, R * (D / 64) * sizeof(float2)}, {(void**)&h->CS, R1 * sizeof(float2)},
   };
   size_t total = 0;
   for (auto& r : reqs) total += (r.bytes + 1023) / 1024 * 1024;

@@ -57,6 +57,8 @@ struct Params {
   const float* bias; const float* csum; const float* mu; const float* rstd;
   const void* res; int ldr, res_mod;
   void* out; int ldo; void* out2;
+  float2* ps_out; const float* nullc; int n_uncond;
+  const float2* ps_in; const float2* cs_in; int ps_slots; float ps_invP;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -274,8 +276,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       float* vb = vecs + acc * 2 * BN;
       for (int i = etid; i < BN; i += NE * 32) {
         const int n = n_tile0 + i;
-        vb[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        const float bv = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        vb[i] = bv;
         if (LN) vb[BN + i] = n < p.N ? __ldg(p.csum + n) : 0.f;
+        else if (RES != RES_NONE && p.nullc) vb[BN + i] = bv + (n < p.N ? __ldg(p.nullc + n) : 0.f);
       }
       epi_bar_sync<NE * 32>();
       const int m0 = m_blk * BM + q * 32;     // first row of this warp's box
@@ -292,7 +296,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int m = m0 + lane;
       const bool row_ok = m < p.M;
       float rs = 1.f, rm = 0.f;  // v = rs * acc + rm * csum[n] + bias[n]
-      if (LN && row_ok) { rs = __ldg(p.rstd + m); rm = -rs * __ldg(p.mu + m); }
+      if (LN && row_ok) {
+        if (p.ps_in) {  // statistics from the producer epilogue's per-64-column partials (fixed summation order)
+          float sx = 0.f, sq = 0.f;
+          const float4* pp = reinterpret_cast<const float4*>(p.ps_in + (size_t)m * p.ps_slots);
+          for (int u = 0; u < p.ps_slots / 2; ++u) { const float4 f = __ldg(pp + u); sx += f.x + f.z; sq += f.y + f.w; }
+          if (p.cs_in) { const float2 c = __ldg(p.cs_in + m); sx += c.x; sq += c.y; }
+          const float mean = sx * p.ps_invP;
+          rs = rsqrtf(fmaxf(sq * p.ps_invP - mean * mean, 0.f) + 1e-5f);
+          rm = -rs * mean;
+        } else {
+          rs = __ldg(p.rstd + m); rm = -rs * __ldg(p.mu + m);
+        }
+      }
+      // rows of the CFG-null half take bias + nullc (slot 1) instead of bias (slot 0)
+      const int bsel = (!LN && RES != RES_NONE && p.nullc && m < p.n_uncond) ? BN : 0;
+      float psum = 0.f, psq = 0.f;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (RES == RES_BF16) { mbar_wait(res_bar(e), res_phase); res_phase ^= 1; }
@@ -301,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
         const int n0 = nc0 + ch * 32;
-        const float* bvec = vb + cg * CPW + ch * 32;
+        const float* bvec = vb + cg * CPW + ch * 32 + (LN ? 0 : bsel);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -352,6 +371,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 v[u * 8 + k2 * 2 + 1] += __bfloat162float(h2.y);
               }
             }
+            if (RES != RES_NONE) {
+#pragma unroll
+              for (int k2 = 0; k2 < 8; ++k2) { psum += v[u * 8 + k2]; psq = fmaf(v[u * 8 + k2], v[u * 8 + k2], psq); }
+            }
             uint4 w;
             w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
             w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
@@ -361,6 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
+      if (RES != RES_NONE && !OUTF32 && p.ps_out && row_ok) p.ps_out[(size_t)m * (p.N / CPW) + (nc0 / CPW)] = make_float2(psum, psq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));   // TMEM stage is free for the MMA warp
@@ -492,6 +516,10 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd;
   p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod;
   p.out = d.out; p.ldo = d.ldo; p.out2 = d.out2;
+  p.ps_out = d.ps_out; p.nullc = d.nullc; p.n_uncond = d.n_uncond;
+  p.ps_in = d.ps_in; p.cs_in = d.cs_in; p.ps_slots = d.ps_slots; p.ps_invP = d.ps_P > 0 ? 1.0f / (float)d.ps_P : 0.f;
+  if ((d.ps_out || d.nullc) && (d.out_f32 || !d.res)) { *err = "fused LN statistics need a bf16-output residual GEMM"; return cudaErrorInvalidValue; }
+  if (d.ps_in && (!d.csum || (d.ps_slots & 1))) { *err = "ps_in needs an LN-fold GEMM and an even slot count"; return cudaErrorInvalidValue; }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
   return bn == 256 ? dispatch<256>(d, maps, p, grid, st, err) : dispatch<128>(d, maps, p, grid, st, err);

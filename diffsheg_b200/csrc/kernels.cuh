@@ -207,6 +207,31 @@ __global__ void feat_prep_bf16_kernel(bf16* h, int ldh, int D, int n_uncond, int
   if (lane == 0) { mu[cr] = mean; rstd[cr] = rsqrtf(var + LN_EPS); }
 }
 
+// (sum, sum of squares) of the conditioning part (xf | hubert [| expr]) of the feat_proj input row: step-wide
+// constant across the 8 layers of a net, combined with the residual-stream partials in the feat1 epilogue.
+__global__ void cond_stats_bf16_kernel(Seg s1, Seg s2, Seg s3, int nseg, int n_rows, float2* cs) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= n_rows) return;
+  const Seg segs[3] = {s1, s2, s3};
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s < nseg) {
+      const int c = lane * 8, k = segs[s].k;
+      if (c < k) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(segs[s].ptr) + (size_t)row * segs[s].ld + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (c + e < k) { sum += f[e]; sq = fmaf(f[e], f[e], sq); }
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  if (lane == 0) cs[row] = make_float2(sum, sq);
+}
+
 // rowstats for bf16, D % 8 == 0, D <= 1024
 __global__ void rowstats_bf16_kernel(const bf16* x, int ld, int D, int n_rows, float* mu, float* rstd) {
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
