@@ -343,7 +343,9 @@ struct Runner {
     f2.a[0] = seg(h->F1, F, F); f2.nseg = 1; f2.M = rows; f2.out = h->Y; f2.ldo = D;
     if (gemm(f2, L.ffn2, "ffn2")) return 1;
     prof_begin(h, st, PROF_ROW, 2.0 * rows * D * sizeof(TA));
-    if (std::is_same<TA, bf16>::value)
+    if (std::is_same<TA, bf16>::value && D == 512)
+      ln_mod_silu_sample_bf16_kernel<<<rows / T, 256, 0, st>>>((const bf16*)h->Y, (bf16*)h->Z, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
+    else if (std::is_same<TA, bf16>::value)
       ln_mod_silu_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
           (const bf16*)h->Y, D, (bf16*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
     else

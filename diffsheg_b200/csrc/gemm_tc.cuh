@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace dsheg {
@@ -429,7 +431,34 @@ inline EncodeTiledFn get_encode_fn() {
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle,
 // out-of-bounds elements read as zero (ragged M / N / K tails need no padding in memory).
+inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err);
+
+// Encoding a tensor map costs ~1 us of host time and a GEMM needs up to 8: cache them (workspace pointers are
+// stable for the life of a handle), which matters for the launch-bound small-batch configurations.
 inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
+  struct Key {
+    const void* p; int r, c, l, b;
+    bool operator==(const Key& o) const { return p == o.p && r == o.r && c == o.c && l == o.l && b == o.b; }
+  };
+  struct Hash {
+    size_t operator()(const Key& k) const {
+      size_t h = reinterpret_cast<size_t>(k.p);
+      h ^= (size_t)k.r * 0x9E3779B97F4A7C15ull; h ^= (size_t)k.c * 0xC2B2AE3D27D4EB4Full;
+      h ^= ((size_t)k.l << 20) ^ ((size_t)k.b << 7);
+      return h;
+    }
+  };
+  static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+  const Key k{ptr, rows, cols, ld, box_rows};
+  auto it = cache.find(k);
+  if (it != cache.end()) { *map = it->second; return true; }
+  if (!make_tmap_uncached(map, ptr, rows, cols, ld, box_rows, err)) return false;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(k, *map);
+  return true;
+}
+
+inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
   // box = [box_rows x 64 columns] = 128-byte rows: operand tiles (K-major) and epilogue boxes share this geometry
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }

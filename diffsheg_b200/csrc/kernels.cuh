@@ -319,6 +319,57 @@ __global__ void ln_mod_silu_bf16_kernel(const bf16* y, int ldy, bf16* z, int ldz
   }
 }
 
+// ln_mod_silu, D == 512, bf16: one CTA (8 warps) per SAMPLE so that the per-column coefficients
+//   t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*G + Bc
+// are folded once per lane and reused for the sample's T rows (the per-row variant spends 8x more load
+// instructions on g/b/scale/shift than on data).  SiLU(x) = h + h*tanh(h), h = x/2 (MUFU.TANH).
+__global__ void __launch_bounds__(256) ln_mod_silu_sample_bf16_kernel(const bf16* y, bf16* z, int T, int B, const float* g,
+                                                                      const float* b, const float* ss, int ss_ld) {
+  constexpr int D = 512;
+  const int smp = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const float* sc = ss + (size_t)(smp % B) * ss_ld;
+  float G[16], Bc[16];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(g + c + e)), b4 = __ldg(reinterpret_cast<const float4*>(b + c + e));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + c + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + c + e));
+      G[i * 8 + e] = a.x * (1.f + c4.x); G[i * 8 + e + 1] = a.y * (1.f + c4.y);
+      G[i * 8 + e + 2] = a.z * (1.f + c4.z); G[i * 8 + e + 3] = a.w * (1.f + c4.w);
+      Bc[i * 8 + e] = fmaf(b4.x, 1.f + c4.x, d4.x); Bc[i * 8 + e + 1] = fmaf(b4.y, 1.f + c4.y, d4.y);
+      Bc[i * 8 + e + 2] = fmaf(b4.z, 1.f + c4.z, d4.z); Bc[i * 8 + e + 3] = fmaf(b4.w, 1.f + c4.w, d4.w);
+    }
+  }
+  const size_t row0 = (size_t)smp * T;
+  for (int t = warp; t < T; t += 8) {
+    const bf16* yr = y + (row0 + t) * D;
+    float v[16];
+    unpack8(*reinterpret_cast<const uint4*>(yr + lane * 8), *reinterpret_cast<float(*)[8]>(&v[0]));
+    unpack8(*reinterpret_cast<const uint4*>(yr + 256 + lane * 8), *reinterpret_cast<float(*)[8]>(&v[8]));
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s += v[e];
+    const float mean = warp_sum(s) * (1.f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { v[e] -= mean; var = fmaf(v[e], v[e], var); }
+    const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + LN_EPS);
+    float o[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float hh = 0.5f * fmaf(v[e] * rstd, G[e], Bc[e]);
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+      o[e] = fmaf(hh, th, hh);
+    }
+    bf16* zr = z + (row0 + t) * D;
+    *reinterpret_cast<uint4*>(zr + lane * 8) = pack8(*reinterpret_cast<float(*)[8]>(&o[0]));
+    *reinterpret_cast<uint4*>(zr + 256 + lane * 8) = pack8(*reinterpret_cast<float(*)[8]>(&o[8]));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Linear ("efficient") self-attention core (tr:122-128), one CTA per sample, heads in sequence:
 //   Q' = softmax_d(Q)   K' = softmax_t(K)   A = K'^T V  [HD x HD]   Y = Q' A
