@@ -61,6 +61,7 @@ struct Params {
   void* out; int ldo; void* out2;
   float2* ps_out; const float* nullc; int n_uncond;
   const float2* ps_in; const float2* cs_in; int ps_slots; float ps_invP;
+  int prefetch;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -102,6 +103,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// L2 prefetch of a tensor tile (no smem destination): used by the producer to pull the NEXT tile's A row-panel from
+// HBM into L2 one tile ahead, so the 3-stage smem ring only has to cover L2 latency, not HBM latency.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -221,9 +227,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        // prefetch the next tile's A panel into L2 (only when it is a new M-tile: the n-fastest order makes the
+        // CTAs of one wave share a panel, so each panel is prefetched by the tiles_n CTAs that will read it)
+        const int next = tile + gridDim.x;
+        const bool pf = p.prefetch && next < num_tiles && (next / p.tiles_n) != m_blk;
+        const int pf_m = pf ? (next / p.tiles_n) * BM : 0;
         int seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           while (kb >= p.seg_kb_start[seg + 1]) ++seg;
+          if (pf && (kb % p.tiles_n) == n_blk) {   // the tiles_n CTAs sharing the next panel split its k-blocks
+            const CUtensorMap* mp = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
+            tma_prefetch_l2_2d(mp, (kb - p.seg_kb_start[seg]) * BK, pf_m);
+          }
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
@@ -551,6 +566,11 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.ps_in && (!d.csum || (d.ps_slots & 1))) { *err = "ps_in needs an LN-fold GEMM and an even slot count"; return cudaErrorInvalidValue; }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("DSHEG_TC_PREFETCH"); pf = e ? atoi(e) : 1; }
+    p.prefetch = pf;
+  }
   return bn == 256 ? dispatch<256>(d, maps, p, grid, st, err) : dispatch<128>(d, maps, p, grid, st, err);
 }
 

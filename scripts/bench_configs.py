@@ -27,6 +27,7 @@ def timed(fn, reps=1):
 def setup(name, B, T, ddim=True, steps=1000, **opt_over):
     cfg = synth.make_cfg(name)
     sd = synth.make_state_dict(cfg, seed=1)
+    T = T or cfg["n_poses"]
     eng = FusedUniDiffuser(sd, cfg, precision="bf16", max_batch=B, max_frames=min(T, cfg["n_poses"]))
     opt = synth.make_opt(cfg, ddim=ddim, diffusion_steps=steps, **opt_over)
     betas = get_named_beta_schedule("linear", steps)
