@@ -806,6 +806,8 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
 // Times one tcgen05 GEMM shape (bf16, device-resident random-ish data): mode 0 bias, 1 LN+bias, 2 LN+bias+SiLU,
 // 3 bias+bf16 residual (in place), 4 bias+GELU; bn = 0 (auto) / 128 / 256.  Returns the mean ms over `iters`.
 int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out) {
+  const int cg = bn >= 1000 ? 2 : (bn >= 100 ? 1 : 0);   // bn = 2256 selects the CTA-pair kernel explicitly, 128/256 the single-CTA one
+  if (bn >= 1000) bn -= 2000;
   if (K % 64 || N % 64 || !ms_out) { g_create_error = "bench_gemm: need K % 64 == 0, N % 64 == 0"; return 1; }
   bf16 *Ab = nullptr, *Wb = nullptr, *Ob = nullptr;
   float *vec = nullptr;
@@ -832,9 +834,9 @@ int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = tc::launch_gemm_tc(d, sms, 0, &terr, bn);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = tc::launch_gemm_tc(d, sms, 0, &terr, bn, cg);
   cudaEventRecord(e0, 0);
-  for (int i = 0; i < iters && e == cudaSuccess; ++i) e = tc::launch_gemm_tc(d, sms, 0, &terr, bn);
+  for (int i = 0; i < iters && e == cudaSuccess; ++i) e = tc::launch_gemm_tc(d, sms, 0, &terr, bn, cg);
   cudaEventRecord(e1, 0);
   cudaError_t e2 = cudaDeviceSynchronize();
   float ms = 0.f;

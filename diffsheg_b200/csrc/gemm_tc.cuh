@@ -36,18 +36,23 @@ constexpr int CPW = 64;            // accumulator columns per epilogue warp (= o
 constexpr int STG_BYTES = 32 * CPW * 2;  // per-warp staging box: 32 rows x 64 bf16, 128B-swizzled
 constexpr int BAR_BYTES = 512;
 
-template <int BN> struct Cfg {
+// CG = 1: one CTA per tile (128 x BN).  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile:
+// each CTA stages its 128 A rows and HALF of the W tile (128 of the 256 N rows); the pair's tensor cores read both
+// halves, so the smem fill + operand-read traffic per MMA drops by a third.  ncu on the CG = 1 kernel showed it
+// bound by shared-memory bandwidth (TMA fill 96 B/clk + UMMA operand reads 96 B/clk against ~128 B/clk).
+template <int BN, int CG = 1> struct Cfg {
+  static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
-  static constexpr int STAGES = BN == 128 ? 5 : 3;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGES = CG == 2 ? 4 : (BN == 128 ? 5 : 3);
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
   static constexpr int VEC_BYTES = NUM_ACC * 2 * BN * 4;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = PIPE_BYTES + NE * STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + VEC_BYTES;
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 };
 
 enum { RES_NONE = 0, RES_BF16 = 1, RES_F32_MOD = 2 };
@@ -134,6 +139,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// ---- CTA-pair (cta_group::2) primitives ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's smem whose completion bytes are credited to the LEADER CTA's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(0x1000000000000000ull) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 template <int NTHREADS> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -177,14 +215,16 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
   return x;
 }
 
-template <int BN, bool LN, int ACT, int RES, bool OUTF32>
-__global__ void __launch_bounds__(Cfg<BN>::NUM_THREADS, 1)
+template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG>
+__global__ void __launch_bounds__(Cfg<BN, CG>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
+  const int cta_stride = gridDim.x / CG, cta_first = blockIdx.x / CG;   // tiles are walked per CTA (pair)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -204,20 +244,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NE); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NE * CG); }
     for (int e = 0; e < NE; ++e) mbar_init(res_bar(e), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     if (!OUTF32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
-  if (warp == 1) {  // TMEM allocation: one full warp, which also owns the dealloc
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // TMEM allocation: one full warp (the same warp id in both CTAs of a pair), which also owns the dealloc
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -225,12 +270,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const uint32_t leader_full0 = CG == 2 ? mapa_rank(full_bar(0), 0) : 0u;
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+        const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
         // prefetch the next tile's A panel into L2 (only when it is a new M-tile: the n-fastest order makes the
         // CTAs of one wave share a panel, so each panel is prefetched by the tiles_n CTAs that will read it)
-        const int next = tile + gridDim.x;
-        const bool pf = p.prefetch && next < num_tiles && (next / p.tiles_n) != m_blk;
+        const int next = tile + cta_stride;
+        const bool pf = p.prefetch && CG == 1 && next < num_tiles && (next / p.tiles_n) != m_blk;
         const int pf_m = pf ? (next / p.tiles_n) * BM : 0;
         int seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -240,11 +286,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tma_prefetch_l2_2d(mp, (kb - p.seg_kb_start[seg]) * BK, pf_m);
           }
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
-          tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
-          tma_load_2d(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN);
+          if (CG == 2) {
+            // both CTAs fill their own smem; all bytes are credited to the leader's full barrier
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            const uint32_t lb = leader_full0 + 8u * stage;
+            tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
+            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
+            tma_load_2d(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -252,11 +306,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -267,12 +321,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (= UMMA_K bf16) inside the 128B swizzle atom: +2 in 16-byte units
-            tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+            if (CG == 2) tc_mma_bf16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+            else tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
           }
-          tc_commit(empty_bar(stage));              // frees the smem slot when the MMAs retire
+          if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));  // frees the smem slot(s) when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));                  // accumulator complete -> epilogue
+        if (CG == 2) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue(s)
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -286,8 +341,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t stg = stg_base + e * STG_BYTES;
     uint8_t* stg_gen = gen_base + (stg - smem_base);
     int acc = 0; uint32_t acc_phase = 0, res_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+    const uint32_t leader_tempty0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : 0u;
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
       const int n_tile0 = n_blk * BN;
       // ---- stage per-column vectors for this tile (double-buffered with the accumulator stage)
       float* vb = vecs + acc * 2 * BN;
@@ -404,7 +460,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (RES != RES_NONE && !OUTF32 && p.ps_out && row_ok) p.ps_out[(size_t)m * (p.N / CPW) + (nc0 / CPW)] = make_float2(psum, psq);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));   // TMEM stage is free for the MMA warp
+      if (lane == 0) {                               // TMEM stage is free for the (leader's) MMA warp
+        if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+      }
       if (!OUTF32) {
         fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
@@ -421,9 +479,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's smem / signal its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -489,38 +549,54 @@ inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int 
   return true;
 }
 
-template <int BN, bool LN, int ACT, int RES, bool OUTF32>
+template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32>;
+  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, Cfg<BN>::NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
-  return cudaGetLastError();
+  if (CG == 1) {
+    kern<<<grid, Cfg<BN, CG>::NUM_THREADS, Cfg<BN, CG>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg<BN, CG>::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
 }
 
-template <int BN>
+template <int BN, int CG>
 inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st,
                             std::string* err) {
   const bool ln = d.csum != nullptr;
   const int res = !d.res ? RES_NONE : (d.res_f32 ? RES_F32_MOD : RES_BF16);
   if (d.out_f32) {
-    if (!ln && d.act == ACT_NONE && res == RES_NONE && !d.out2) return launch_variant<BN, false, ACT_NONE, RES_NONE, true>(maps, p, grid, st);
+    if (!ln && d.act == ACT_NONE && res == RES_NONE && !d.out2) return launch_variant<BN, false, ACT_NONE, RES_NONE, true, CG>(maps, p, grid, st);
   } else if (ln) {
-    if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false>(maps, p, grid, st);
-    if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false>(maps, p, grid, st);
+    if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG>(maps, p, grid, st);
+    if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
   } else {
-    if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, false, ACT_NONE, RES_NONE, false>(maps, p, grid, st);
-    if (d.act == ACT_NONE && res == RES_BF16) return launch_variant<BN, false, ACT_NONE, RES_BF16, false>(maps, p, grid, st);
-    if (d.act == ACT_NONE && res == RES_F32_MOD) return launch_variant<BN, false, ACT_NONE, RES_F32_MOD, false>(maps, p, grid, st);
-    if (d.act == ACT_GELU && res == RES_NONE) return launch_variant<BN, false, ACT_GELU, RES_NONE, false>(maps, p, grid, st);
-    if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, false, ACT_SILU, RES_NONE, false>(maps, p, grid, st);
+    if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, false, ACT_NONE, RES_NONE, false, CG>(maps, p, grid, st);
+    if (d.act == ACT_NONE && res == RES_BF16) return launch_variant<BN, false, ACT_NONE, RES_BF16, false, CG>(maps, p, grid, st);
+    if (d.act == ACT_NONE && res == RES_F32_MOD) return launch_variant<BN, false, ACT_NONE, RES_F32_MOD, false, CG>(maps, p, grid, st);
+    if (d.act == ACT_GELU && res == RES_NONE) return launch_variant<BN, false, ACT_GELU, RES_NONE, false, CG>(maps, p, grid, st);
+    if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, false, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
   }
   *err = "no tcgen05 GEMM variant for this epilogue combination";
   return cudaErrorInvalidValue;
+}
+
+inline int g_cg_override() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DSHEG_TC_CG"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 inline int g_bn_override() {
@@ -529,13 +605,17 @@ inline int g_bn_override() {
   return v;
 }
 
-inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err, int bn_force = 0) {
+inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err, int bn_force = 0, int cg_force = 0) {
   // vector paths need 16-byte aligned rows; every engine buffer satisfies this
   if (!d.out_f32 && ((d.ldo % 8) || (d.N % 64))) { *err = "bf16-output GEMM needs N % 64 == 0 and ldo % 8 == 0"; return cudaErrorInvalidValue; }
   if (d.res && !d.res_f32 && (d.ldr % 8)) { *err = "bf16 residual needs ldr % 8 == 0"; return cudaErrorInvalidValue; }
   if (d.res && d.res_f32 && ((d.ldr % 4) || d.res_mod <= 0)) { *err = "fp32 residual needs ldr % 4 == 0 and res_mod > 0"; return cudaErrorInvalidValue; }
   int bn = bn_force ? bn_force : g_bn_override();
   if (bn != 128 && bn != 256) bn = (d.N % 256 == 0) ? 256 : 128;
+  // CTA pairs (cta_group::2) for the big row counts; tiny problems keep the single-CTA kernel (more tiles in flight)
+  int cg = cg_force ? cg_force : g_cg_override();
+  if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096) ? 2 : 1;
+  if (bn != 256) cg = 1;
   Params p{};
   CUtensorMap maps[8];
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
@@ -549,14 +629,14 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   for (int s = d.nseg; s < 4; ++s) maps[s] = maps[0];
   p.num_kb = kb;
   if (kb * BK != d.Kp) { *err = "GEMM weight K padding does not match the A segments"; return cudaErrorInvalidValue; }
-  if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, bn, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, bn / cg, err)) return cudaErrorInvalidValue;
   maps[5] = maps[6] = maps[7] = maps[4];
   if (!d.out_f32) {  // epilogue boxes: 32 rows x 64 columns of the bf16 output / residual
     if (!make_tmap(&maps[5], d.out, d.M, d.N, d.ldo, 32, err)) return cudaErrorInvalidValue;
     if (d.out2 && !make_tmap(&maps[6], d.out2, d.M, d.N, d.ldo, 32, err)) return cudaErrorInvalidValue;
     if (d.res && !d.res_f32 && !make_tmap(&maps[7], d.res, d.M, d.N, d.ldr, 32, err)) return cudaErrorInvalidValue;
   }
-  p.tiles_m = (d.M + BM - 1) / BM; p.tiles_n = (d.N + bn - 1) / bn;
+  p.tiles_m = (d.M + BM * cg - 1) / (BM * cg); p.tiles_n = (d.N + bn - 1) / bn;   // tiles per CTA (pair)
   p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd;
   p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod;
   p.out = d.out; p.ldo = d.ldo; p.out2 = d.out2;
@@ -565,13 +645,15 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   if ((d.ps_out || d.nullc) && (d.out_f32 || !d.res)) { *err = "fused LN statistics need a bf16-output residual GEMM"; return cudaErrorInvalidValue; }
   if (d.ps_in && (!d.csum || (d.ps_slots & 1))) { *err = "ps_in needs an LN-fold GEMM and an even slot count"; return cudaErrorInvalidValue; }
   const int tiles = p.tiles_m * p.tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int units = num_sms / cg;   // CTAs (or CTA pairs) that can be resident
+  const int grid = (tiles < units ? tiles : units) * cg;
   {
     static int pf = -1;
-    if (pf < 0) { const char* e = getenv("DSHEG_TC_PREFETCH"); pf = e ? atoi(e) : 1; }
+    if (pf < 0) { const char* e = getenv("DSHEG_TC_PREFETCH"); pf = e ? atoi(e) : 0; }
     p.prefetch = pf;
   }
-  return bn == 256 ? dispatch<256>(d, maps, p, grid, st, err) : dispatch<128>(d, maps, p, grid, st, err);
+  if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err);
+  return bn == 256 ? dispatch<256, 1>(d, maps, p, grid, st, err) : dispatch<128, 1>(d, maps, p, grid, st, err);
 }
 
 }  // namespace tc

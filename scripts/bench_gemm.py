@@ -17,14 +17,14 @@ shapes = [("qkv      LN", R, 1536, 512, 1), ("feat1 LN+silu", R1, 1024, 896, 2),
 ms = ctypes.c_float()
 for name, M, N, K, mode in shapes:
     line = f"{name:16s} M={M:7d} N={N:5d} K={K:5d}"
-    for bn in (128, 256):
-        if bn == 256 and N % 256:
-            line += "   bn256:    n/a      "
+    for bn in (256, 2256):   # 256 = single-CTA 128x256 tiles, 2256 = CTA pair (cta_group::2) 256x256 tiles
+        if N % 256:
+            line += "   n/a      "
             continue
         rc = L.dsheg_bench_gemm(M, N, K, mode, bn, 10, ctypes.byref(ms))
         if rc:
             line += f"   bn{bn}: ERR {L.dsheg_last_error(None)}"
             continue
         tf = 2.0 * M * N * K / (ms.value * 1e-3) / 1e12
-        line += f"   bn{bn}: {ms.value * 1e3:8.1f} us {tf:7.1f} TF/s"
+        line += f"   {'pair' if bn > 1000 else 'cta1'}: {ms.value * 1e3:8.1f} us {tf:7.1f} TF/s"
     print(line, flush=True)

@@ -99,7 +99,10 @@ def test_undo_ddpm_merge(L):
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("M,N,K,act,use_res", [(256, 512, 512, 0, True), (77, 103, 129, 0, False), (1000, 1536, 512, 2, False),
                                                (1, 384, 128, 0, False), (300, 1024, 1024, 1, False), (129, 128, 64, 0, True),
-                                               (2000, 256, 256, 0, False), (517, 512, 1024, 0, True), (130, 16384, 2048, 0, False)])
+                                               (2000, 256, 256, 0, False), (517, 512, 1024, 0, True), (130, 16384, 2048, 0, False),
+                                               # M >= 4096 with N % 256 == 0: the CTA-pair (cta_group::2) kernel, ragged last pair
+                                               (4096, 512, 512, 0, True), (5000, 1536, 512, 0, False), (4229, 1024, 1024, 1, False),
+                                               (9001, 512, 1024, 2, False), (4300, 256, 64, 0, True)])
 def test_op_linear(L, prec, M, N, K, act, use_res):
     """fp32: SIMT engine vs fp64.  bf16: tcgen05 engine on bf16-rounded operands / residual, bf16 output when
     N % 32 == 0 (the denoiser's layout); tolerance = bf16 output rounding (2^-8) + the tanh-based activations."""
