@@ -95,6 +95,12 @@ def dist_setup(n_gpus):
     return world, rank, local
 
 
+def cpu_threads():
+    """Threads for the torch-CPU baseline: every core up to 32.  On the 128-core GPU host, torch's intra-op pools get
+    SLOWER beyond that on these matrix sizes (measured: 128 threads -> 3.2 frames/s at B=4; see profiles/r01)."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("DSHEG_CPU_THREADS", "32"))))
+
+
 def oracle_cpu_frames_per_s(cfg, B, steps, warmup, threads):
     """The reference's CPU implementation of the path (oracle port: same torch fp32 op stream), timed on host cores."""
     from diffsheg_b200 import synth
@@ -124,7 +130,7 @@ def run_reference(args):
         return
     from diffsheg_b200 import synth
     cfg = synth.make_cfg("show")
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     B = args.ref_batch
     fps, ms = oracle_cpu_frames_per_s(cfg, B, args.steps, args.warmup, cores)
     sample = f"B={B} of the bs=950 workload per step (SHOW T=88 CFG 1.25 ddim25, all 25 calls); frames/s is batch-linear on CPU"
@@ -269,7 +275,7 @@ def run_ours(args):
             "roofline": roof, "roofline_attention": roof_attn,
             "rowwise": {"ms_per_step": prof["rowwise"]["ms"], "gbs": prof["rowwise"]["work"] / max(prof["rowwise"]["ms"], 1e-9) / 1e6}}
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         fps, cms = oracle_cpu_frames_per_s(cfg, args.ref_batch, 1, 1, cores)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"oracle port (reference torch-CPU op stream), B={args.ref_batch} of the 950-batch, "
@@ -285,7 +291,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=950, help="per-GPU batch (BASELINE configs[1]: 950)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ref-batch", type=int, default=4, help="bounded CPU sample of the workload")
+    ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cuda", type=int, default=0, help="time the reference op stream (oracle port) eagerly on the GPU at this batch")
     args = ap.parse_args()

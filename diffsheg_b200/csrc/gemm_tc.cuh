@@ -614,7 +614,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   if (bn != 128 && bn != 256) bn = (d.N % 256 == 0) ? 256 : 128;
   // CTA pairs (cta_group::2) for the big row counts; tiny problems keep the single-CTA kernel (more tiles in flight)
   int cg = cg_force ? cg_force : g_cg_override();
-  if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096) ? 2 : 1;
+  if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096 && d.Kp >= 512) ? 2 : 1;   // short K loops: single CTAs win (profiles/r01 sweep)
   if (bn != 256) cg = 1;
   Params p{};
   CUtensorMap maps[8];
