@@ -78,6 +78,14 @@ struct dsheg_handle {
   size_t arena_bytes = 0;
   void *H, *QKV, *Z, *Y, *F1, *XF, *HUB[2], *EXPR, *AUD256, *A0, *A1, *XIN, *EMBS[2];
   float *Y32, *O, *MID, *MU, *RSTD, *MU2, *RSTD2, *SIN, *TEH, *TEMB, *SSA, *PIDH, *PIDE[2], *SS[2];
+  float *PRM, *XBUF, *EPSBUF;   // step scalars {t, a, b, cond_scale}; fixed-address x / eps staging for graph replay
+  // CUDA graphs of one denoiser call for small (launch-bound) batches: state 0 = not seen, 1 = ran eagerly once,
+  // 2 = captured; key = B | T << 20 | cfg_pair << 40
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int state = 0; };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
+  int graph_max_rows = 4096;   // B*T above which launches are no longer the bottleneck
   float2 *PS, *CS;      // fused LayerNorm statistics: per-row / per-64-column partials, conditioning partials
   int fuse_stats = 1;   // bf16 + tcgen05 engine: LN statistics come from the producer GEMM epilogues (DSHEG_FUSE_STATS=0 disables)
   int ldE = 0, ldXin = 0, ldO = 0;
@@ -394,14 +402,15 @@ struct Runner {
     return 0;
   }
 
-  int denoise(const float* x, int t_orig, float a, float b, float cond_scale, float* eps_out) {
+  // One denoiser call.  The step scalars (t, a, b, cond_scale) are read from h->PRM on the device; `two` (CFG pair)
+  // is the only step-level host decision, so the launch sequence below is identical for every step of a window.
+  int denoise(const float* x, bool two, float* eps_out) {
     const dsheg_config& c = h->cfg;
     const int B = h->B, T = h->T, R1 = B * T, D = c.latent_dim, E = 4 * D, F = c.ff_size, A = c.audio_dim;
     const int L = c.num_layers, Dtot = c.dim_pose + c.expression_dim;
-    const bool two = c.classifier_free && cond_scale != 1.0f;  // tr:537
     const int G = two ? 2 : 1, R = G * R1;
     // ---- K1: timestep embeddings of the three nets (rows are identical: t = [i]*B, gd:1196)
-    sinus_kernel<<<1, 256, 0, st>>>((float)t_orig, h->freqs, D / 2, h->SIN);
+    sinus_kernel<<<1, 256, 0, st>>>(h->PRM, h->freqs, D / 2, h->SIN);
     LAUNCH_CHECK("sinus");
     {
       GemvBatch g0, g2;
@@ -474,9 +483,8 @@ struct Runner {
       {
         const int wcols = (n == 0) ? h->ldE : nw.feats;
         const size_t ne = (size_t)R1 * wcols;
-        cfg_mix_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->O, h->ldO, R1, nw.feats, two ? 1 : 0, cond_scale, eps_out,
-                                                                          x, Dtot, nw.x_off, a, b, n == 0 ? (TA*)h->EXPR : nullptr,
-                                                                          h->ldE);
+        cfg_mix_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->O, h->ldO, R1, nw.feats, two ? 1 : 0, h->PRM, eps_out,
+                                                                          x, Dtot, nw.x_off, n == 0 ? (TA*)h->EXPR : nullptr, h->ldE);
         LAUNCH_CHECK("cfg_mix");
       }
     }
@@ -532,6 +540,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   const char* att = getenv("DSHEG_ATTN");
   if (att && !strcmp(att, "v1")) h->attn_v2 = 0;
   if (att && !strcmp(att, "v2")) h->attn_v2 = 2;
+  const char* gr = getenv("DSHEG_GRAPHS");
+  if (gr && !strcmp(gr, "0")) h->use_graphs = 0;
   const char* fs = getenv("DSHEG_FUSE_STATS");
   if (fs && !strcmp(fs, "0")) h->fuse_stats = 0;
 
@@ -556,6 +566,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
       {(void**)&h->PIDE[1], (size_t)c.max_batch * E * 4}, {(void**)&h->SS[0], (size_t)c.max_batch * L * 4 * D * 4},
       {(void**)&h->SS[1], (size_t)c.max_batch * L * 4 * D * 4},
       {(void**)&h->PS, R * (D / 64) * sizeof(float2)}, {(void**)&h->CS, R1 * sizeof(float2)},
+      {(void**)&h->PRM, 64}, {(void**)&h->XBUF, (size_t)4096 * (c.dim_pose + c.expression_dim) * 4},
+      {(void**)&h->EPSBUF, (size_t)4096 * (c.dim_pose + c.expression_dim) * 4},
   };
   size_t total = 0;
   for (auto& r : reqs) total += (r.bytes + 1023) / 1024 * 1024;
@@ -590,6 +602,8 @@ void dsheg_destroy(dsheg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (auto& kv : h->tensors) cudaFree(kv.second.ptr);
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->arena) cudaFree(h->arena);
   delete h;
 }
@@ -662,7 +676,39 @@ int dsheg_prepare_window(dsheg_handle* h, const float* mel, const float* hubert,
 int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, float b, float cond_scale, float* eps_out, void* stream) {
   if (!h) return 1;
   if (!h->window_ready) return fail(h, "dsheg_prepare_window has not been called");
-  return with_runner(h, (cudaStream_t)stream, [&](auto& r) { return r.denoise(x, t_orig, a, b, cond_scale, eps_out); });
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool two = h->cfg.classifier_free && cond_scale != 1.0f;  // transformer.py:537
+  step_params_kernel<<<1, 32, 0, st>>>(h->PRM, (float)t_orig, a, b, cond_scale);
+  h->launches++;
+  const int rows1 = h->B * h->T;
+  auto eager = [&]() { return with_runner(h, st, [&](auto& r) { return r.denoise(x, two, eps_out); }); };
+  if (!h->use_graphs || h->profiling || rows1 > h->graph_max_rows) return eager();
+  // ---- launch-bound regime: replay a captured graph of the ~165 launches (identical for every step of the window)
+  const uint64_t key = (uint64_t)h->B | ((uint64_t)h->T << 20) | ((uint64_t)(two ? 1 : 0) << 40);
+  dsheg_handle::GraphEntry& ge = h->graphs[key];
+  if (ge.state == 0) { ge.state = 1; return eager(); }   // first call runs eagerly (lazy module loads, attribute setup)
+  if (ge.state == 1) {
+    if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { ge.state = -1; return eager(); }
+    const int64_t before = h->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc = 1;
+    if (ok) rc = with_runner(h, h->cap_stream, [&](auto& r) { return r.denoise(h->XBUF, two, h->EPSBUF); });
+    if (ok) ok = cudaStreamEndCapture(h->cap_stream, &graph) == cudaSuccess && rc == 0 && graph;
+    ge.launches = h->launches - before;
+    h->launches = before;
+    if (ok) ok = cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) { cudaGetLastError(); ge.state = -1; ge.exec = nullptr; return eager(); }
+    ge.state = 2;
+  }
+  if (ge.state != 2) return eager();
+  const size_t bytes = (size_t)rows1 * (h->cfg.dim_pose + h->cfg.expression_dim) * sizeof(float);
+  CK(cudaMemcpyAsync(h->XBUF, x, bytes, cudaMemcpyDeviceToDevice, st));
+  CK(cudaGraphLaunch(ge.exec, st));
+  CK(cudaMemcpyAsync(eps_out, h->EPSBUF, bytes, cudaMemcpyDeviceToDevice, st));
+  h->launches += ge.launches;
+  return 0;
 }
 
 int64_t dsheg_launch_count(const dsheg_handle* h) { return h ? h->launches : 0; }

@@ -494,9 +494,16 @@ __global__ void mel_stage_kernel(const float* mel, int A, TA* aud256, int ld256,
 // out layer epilogue (tr:585-586) + x0 prediction for the gesture net's conditioning (tr:717-725,749):
 //   eps = G==2 ? o_u + s*(o_c - o_u) : o      written to eps_out[r*Dtot + off + j]
 //   expr[r, j] = a*x - b*eps  (only when expr != nullptr; padding columns zeroed)
+// Step scalars live in a 4-float device buffer {t_orig, a, b, cond_scale} written by step_params_kernel, so that a
+// captured CUDA graph of the denoiser is valid for every diffusion step (nothing step-dependent is baked in).
+__global__ void step_params_kernel(float* prm, float t, float a, float b, float s) {
+  if (threadIdx.x == 0) { prm[0] = t; prm[1] = a; prm[2] = b; prm[3] = s; }
+}
+
 template <typename TA>
-__global__ void cfg_mix_kernel(const float* o, int ldo, int n_rows, int feats, int two, float s, float* eps_out,
-                               const float* x, int Dtot, int off, float a, float b, TA* expr, int ld_expr) {
+__global__ void cfg_mix_kernel(const float* o, int ldo, int n_rows, int feats, int two, const float* prm, float* eps_out,
+                               const float* x, int Dtot, int off, TA* expr, int ld_expr) {
+  const float a = prm[1], b = prm[2], s = prm[3];
   const int wcols = expr ? ld_expr : feats;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n_rows * wcols) return;
@@ -516,10 +523,10 @@ __global__ void cfg_mix_kernel(const float* o, int ldo, int n_rows, int feats, i
 
 // sinusoidal timestep embedding (tr:42-59): [cos(t*f) | sin(t*f)], f uploaded from the host so the
 // arguments are bit-identical to torch's.
-__global__ void sinus_kernel(float t, const float* freqs, int half, float* out) {
+__global__ void sinus_kernel(const float* prm, const float* freqs, int half, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half) return;
-  const float arg = t * freqs[i];
+  const float arg = prm[0] * freqs[i];
   out[i] = cosf(arg);
   out[half + i] = sinf(arg);
 }

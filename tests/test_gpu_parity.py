@@ -2,9 +2,10 @@
 (ctypes) and is checked against the oracle / the committed reference outputs.
 
 Tolerances (relmax = max|got - want| / max|want|):
-  fp32 mode  : 2e-4 on a single denoiser call, 2e-3 on a full 25-step loop (fp32 reassociation only:
-               LayerNorm folds, fused epilogues, different reduction orders)
-  bf16 mode  : 4e-2 on a single call, 8e-2 on a full loop (bf16 operands/activations, fp32 accumulate)
+  fp32 mode  : 2e-5 on a single denoiser call, 2e-4 on a full loop (fp32 reassociation only: LayerNorm folds,
+               fused epilogues, different reduction orders; measured 2e-6 / 3e-5)
+  bf16 mode  : 3e-2 on a single call and on a full loop (bf16 operands/activations, fp32 accumulation and
+               statistics, tanh-form activations in the GEMM epilogues; measured 1.3e-2 / 1e-2)
 """
 import ctypes
 import os
@@ -17,7 +18,7 @@ from diffsheg_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(call=2e-4, loop=2e-3), "bf16": dict(call=4e-2, loop=8e-2)}
+TOL = {"fp32": dict(call=2e-5, loop=2e-4), "bf16": dict(call=3e-2, loop=3e-2)}
 
 
 def relmax(a, b):
