@@ -115,13 +115,12 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     const int c = lane >> 2, w = lane & 3;
     const int rsplit = (T + 1) >> 1;
     const int r_lo = half ? rsplit : 0, r_hi = half ? T : rsplit;
-    float m0 = -INFINITY, m1 = -INFINITY;
+    // pass 1: column max in packed bf16x2 (exact for a max), one HMNMX2 per row
+    __nv_bfloat162 mx2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
 #pragma unroll 8
-    for (int r = r_lo; r < r_hi; ++r) {
-      const float2 v = unpack2(*reinterpret_cast<const uint32_t*>(Ks + swz(r, c) + w * 4));
-      m0 = fmaxf(m0, v.x);
-      m1 = fmaxf(m1, v.y);
-    }
+    for (int r = r_lo; r < r_hi; ++r)
+      mx2 = __hmax2(mx2, *reinterpret_cast<const __nv_bfloat162*>(Ks + swz(r, c) + w * 4));
+    float m0 = __bfloat162float(mx2.x), m1 = __bfloat162float(mx2.y);
     float* myred = red + (head * 2 + half) * HD;
     const float* otred = red + (head * 2 + (half ^ 1)) * HD;
     myred[2 * lane] = m0;
@@ -129,16 +128,18 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     pair_sync(head);
     m0 = fmaxf(m0, otred[2 * lane]);
     m1 = fmaxf(m1, otred[2 * lane + 1]);
+    // pass 2: e = 2^(x*log2e - m*log2e) (one FFMA + one MUFU.EX2 per element), bf16 for the tensor core
+    const float L2E = 1.4426950408889634f;
+    const float n0 = -m0 * L2E, n1 = -m1 * L2E;
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
     for (int r = r_lo; r < r_hi; ++r) {
       uint32_t* p = reinterpret_cast<uint32_t*>(Ks + swz(r, c) + w * 4);
       const float2 v = unpack2(*p);
-      // round first so that the normaliser is the sum of exactly what the tensor core multiplies
-      const __nv_bfloat162 ex = __floats2bfloat162_rn(__expf(v.x - m0), __expf(v.y - m1));
-      s0 += __bfloat162float(ex.x);
-      s1 += __bfloat162float(ex.y);
-      *p = *reinterpret_cast<const uint32_t*>(&ex);
+      const float e0 = exp2f(fmaf(v.x, L2E, n0)), e1 = exp2f(fmaf(v.y, L2E, n1));
+      s0 += e0;
+      s1 += e1;
+      *p = pack2(e0, e1);
     }
     float* myred2 = red2 + (head * 2 + half) * HD;
     myred2[2 * lane] = s0;
@@ -202,30 +203,33 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     const int mat = lane >> 3, rr = lane & 7;
     for (int mt = half; mt < n_mt; mt += 2) {
       // row softmax numerators in registers: this lane holds 16 of the 64 d's of rows g and g+8; the quad holds all
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      // row max in packed bf16x2: registers [ks][0],[ks][2] belong to row g, [ks][1],[ks][3] to row g + 8
+      __nv_bfloat162 ma = __floats2bfloat162_rn(-INFINITY, -INFINITY), mb = ma;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const float2 a0 = unpack2(qa[ks][0]), a1 = unpack2(qa[ks][1]), a2 = unpack2(qa[ks][2]), a3 = unpack2(qa[ks][3]);
-        mx0 = fmaxf(mx0, fmaxf(fmaxf(a0.x, a0.y), fmaxf(a2.x, a2.y)));
-        mx1 = fmaxf(mx1, fmaxf(fmaxf(a1.x, a1.y), fmaxf(a3.x, a3.y)));
+        ma = __hmax2(ma, __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&qa[ks][0]), *reinterpret_cast<const __nv_bfloat162*>(&qa[ks][2])));
+        mb = __hmax2(mb, __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&qa[ks][1]), *reinterpret_cast<const __nv_bfloat162*>(&qa[ks][3])));
       }
+      float mx0 = fmaxf(__bfloat162float(ma.x), __bfloat162float(ma.y)), mx1 = fmaxf(__bfloat162float(mb.x), __bfloat162float(mb.y));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float L2E = 1.4426950408889634f;
+      const float n0 = -mx0 * L2E, n1 = -mx1 * L2E;
       float sm0 = 0.f, sm1 = 0.f;
       uint32_t pa[4][4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const float2 a0 = unpack2(qa[ks][0]), a1 = unpack2(qa[ks][1]), a2 = unpack2(qa[ks][2]), a3 = unpack2(qa[ks][3]);
-        const __nv_bfloat162 e0 = __floats2bfloat162_rn(__expf(a0.x - mx0), __expf(a0.y - mx0));
-        const __nv_bfloat162 e2 = __floats2bfloat162_rn(__expf(a2.x - mx0), __expf(a2.y - mx0));
-        const __nv_bfloat162 e1 = __floats2bfloat162_rn(__expf(a1.x - mx1), __expf(a1.y - mx1));
-        const __nv_bfloat162 e3 = __floats2bfloat162_rn(__expf(a3.x - mx1), __expf(a3.y - mx1));
-        sm0 += __bfloat162float(e0.x) + __bfloat162float(e0.y) + __bfloat162float(e2.x) + __bfloat162float(e2.y);
-        sm1 += __bfloat162float(e1.x) + __bfloat162float(e1.y) + __bfloat162float(e3.x) + __bfloat162float(e3.y);
-        pa[ks][0] = *reinterpret_cast<const uint32_t*>(&e0);
-        pa[ks][1] = *reinterpret_cast<const uint32_t*>(&e1);
-        pa[ks][2] = *reinterpret_cast<const uint32_t*>(&e2);
-        pa[ks][3] = *reinterpret_cast<const uint32_t*>(&e3);
+        const float e00 = exp2f(fmaf(a0.x, L2E, n0)), e01 = exp2f(fmaf(a0.y, L2E, n0));
+        const float e20 = exp2f(fmaf(a2.x, L2E, n0)), e21 = exp2f(fmaf(a2.y, L2E, n0));
+        const float e10 = exp2f(fmaf(a1.x, L2E, n1)), e11 = exp2f(fmaf(a1.y, L2E, n1));
+        const float e30 = exp2f(fmaf(a3.x, L2E, n1)), e31 = exp2f(fmaf(a3.y, L2E, n1));
+        sm0 += (e00 + e01) + (e20 + e21);
+        sm1 += (e10 + e11) + (e30 + e31);
+        pa[ks][0] = pack2(e00, e01);
+        pa[ks][1] = pack2(e10, e11);
+        pa[ks][2] = pack2(e20, e21);
+        pa[ks][3] = pack2(e30, e31);
       }
       sm0 += __shfl_xor_sync(0xffffffffu, sm0, 1); sm0 += __shfl_xor_sync(0xffffffffu, sm0, 2);
       sm1 += __shfl_xor_sync(0xffffffffu, sm1, 1); sm1 += __shfl_xor_sync(0xffffffffu, sm1, 2);

@@ -305,6 +305,45 @@ def test_ddpm_loop_matches_oracle_same_seed(prec):
     assert err < TOL[prec]["loop"]
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_long_form_windows_match_oracle_same_seed(prec):
+    """test_arbitrary_len's overlapped-window loop (show:864-906): 3 windows (88, 88, ragged 72) with overlap 10;
+    window 0 plain DDIM, windows 1.. RePaint-harmonised on the previous tail.  Same CUDA seed as an oracle-driven loop."""
+    from diffsheg_b200 import FusedSpacedDiffusion, generate_long, get_named_beta_schedule, get_windows, space_timesteps
+    from oracle import diffusion as odiff
+    frames, ov, B = 88 + 78 + 62, 10, 2
+    cfg, sd, eng = _engine("show", prec, B, 88)
+    Dm = cfg["net_dim_pose"]
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, frames, seed=6).items()}
+    opt = synth.make_opt(cfg, overlap_len=ov)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    torch.manual_seed(91)
+    got = generate_long(opt, eng, diff, inp["mel"], inp["person_id"], Dm, {"pretrain_aud_feat": inp["hubert"]})
+    assert got.shape == (B, frames, Dm)
+    # oracle-driven restatement of the same window loop
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    d = odiff.OracleDiffusion(1000, "ddim25", overlap_len=ov)
+    mels, hubs = get_windows(inp["mel"], 88, 88 - ov), get_windows(inp["hubert"], 88, 88 - ov)
+    assert [m.shape[1] for m in mels] == [88, 88, 72]
+    torch.manual_seed(91)
+    outs, prev = [], None
+    with torch.no_grad():
+        for ii, (mel, hub) in enumerate(zip(mels, hubs)):
+            T = mel.shape[1]
+            gt = torch.zeros(B, T, Dm, device="cuda")
+            mask = torch.zeros(B, T, Dm, dtype=torch.bool, device="cuda")
+            if ii > 0:
+                mask[:, :ov] = True
+                gt[:, :ov] = prev[:, -ov:]
+            den = odiff.make_denoise(sd_c, cfg, mel, inp["person_id"], hub)
+            prev = d.ddim_sample_loop(den, (B, T, Dm), y={"gt": gt, "outpainting_mask": mask}, device="cuda")
+            outs.append(prev if ii == len(mels) - 1 else prev[:, :88 - ov])
+    want = torch.cat(outs, 1)
+    err = relmax(got, want)
+    print(f"\n[parity] long-form 3 windows {prec}: relmax={err:.3e}")
+    assert err < TOL[prec]["loop"]
+
+
 # ------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE sizes (bf16 mode)
 # ------------------------------------------------------------------------------------------------
