@@ -85,9 +85,12 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(SO_PATH):
-            raise RuntimeError(
-                f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(diffsheg_b200 has no CPU / PyTorch fallback)")
+            try:  # the CUDA library itself is the only implementation: build it if a toolchain is present
+                build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    f"{SO_PATH} not found and could not be built ({e}); build it with "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` (diffsheg_b200 has no CPU / PyTorch fallback)")
         L = ctypes.CDLL(SO_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError here = header/library mismatch

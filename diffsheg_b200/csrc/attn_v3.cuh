@@ -56,6 +56,7 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
   const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w);
   return make_float2(__bfloat162float(v.x), __bfloat162float(v.y));
 }
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // byte offset of 16-B chunk `c` (0..7) of row `r` inside a swizzled [rows][64] bf16 tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -136,7 +137,7 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     for (int r = r_lo; r < r_hi; ++r) {
       uint32_t* p = reinterpret_cast<uint32_t*>(Ks + swz(r, c) + w * 4);
       const float2 v = unpack2(*p);
-      const float e0 = exp2f(fmaf(v.x, L2E, n0)), e1 = exp2f(fmaf(v.y, L2E, n1));
+      const float e0 = ex2f(fmaf(v.x, L2E, n0)), e1 = ex2f(fmaf(v.y, L2E, n1));
       s0 += e0;
       s1 += e1;
       *p = pack2(e0, e1);
@@ -220,10 +221,10 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const float2 a0 = unpack2(qa[ks][0]), a1 = unpack2(qa[ks][1]), a2 = unpack2(qa[ks][2]), a3 = unpack2(qa[ks][3]);
-        const float e00 = exp2f(fmaf(a0.x, L2E, n0)), e01 = exp2f(fmaf(a0.y, L2E, n0));
-        const float e20 = exp2f(fmaf(a2.x, L2E, n0)), e21 = exp2f(fmaf(a2.y, L2E, n0));
-        const float e10 = exp2f(fmaf(a1.x, L2E, n1)), e11 = exp2f(fmaf(a1.y, L2E, n1));
-        const float e30 = exp2f(fmaf(a3.x, L2E, n1)), e31 = exp2f(fmaf(a3.y, L2E, n1));
+        const float e00 = ex2f(fmaf(a0.x, L2E, n0)), e01 = ex2f(fmaf(a0.y, L2E, n0));
+        const float e20 = ex2f(fmaf(a2.x, L2E, n0)), e21 = ex2f(fmaf(a2.y, L2E, n0));
+        const float e10 = ex2f(fmaf(a1.x, L2E, n1)), e11 = ex2f(fmaf(a1.y, L2E, n1));
+        const float e30 = ex2f(fmaf(a3.x, L2E, n1)), e31 = ex2f(fmaf(a3.y, L2E, n1));
         sm0 += (e00 + e01) + (e20 + e21);
         sm1 += (e10 + e11) + (e30 + e31);
         pa[ks][0] = pack2(e00, e01);
@@ -265,35 +266,41 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
     const int col0 = hh * HD + c0 * 8;
     const float* sc = ss + (size_t)(smp % B) * ss_ld;
-    // per-column constants folded once:  t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*G + Bc
+    // per-column constants folded once:  h = t/2,  t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*2G + 2Bc
     float G[16], Bc[16];
 #pragma unroll
     for (int e = 0; e < 16; e += 4) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
       const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + col0 + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + e));
-      G[e] = a.x * (1.f + c4.x); G[e + 1] = a.y * (1.f + c4.y); G[e + 2] = a.z * (1.f + c4.z); G[e + 3] = a.w * (1.f + c4.w);
-      Bc[e] = fmaf(b4.x, 1.f + c4.x, d4.x); Bc[e + 1] = fmaf(b4.y, 1.f + c4.y, d4.y);
-      Bc[e + 2] = fmaf(b4.z, 1.f + c4.z, d4.z); Bc[e + 3] = fmaf(b4.w, 1.f + c4.w, d4.w);
+      G[e] = 0.5f * a.x * (1.f + c4.x); G[e + 1] = 0.5f * a.y * (1.f + c4.y); G[e + 2] = 0.5f * a.z * (1.f + c4.z); G[e + 3] = 0.5f * a.w * (1.f + c4.w);
+      Bc[e] = 0.5f * fmaf(b4.x, 1.f + c4.x, d4.x); Bc[e + 1] = 0.5f * fmaf(b4.y, 1.f + c4.y, d4.y);
+      Bc[e + 2] = 0.5f * fmaf(b4.z, 1.f + c4.z, d4.z); Bc[e + 3] = 0.5f * fmaf(b4.w, 1.f + c4.w, d4.w);
     }
     for (int t = warp; t < T; t += NTHREADS / 32) {
       const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
       const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
       const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
       float v[16];
-      float s = 0.f;
+      float s = 0.f, sq = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float2 p2 = unpack2(w[e]); v[2 * e] = p2.x; v[2 * e + 1] = p2.y; s += p2.x + p2.y; }
-      const float mean = warp_sum(s) * (1.f / D);
-      float var = 0.f;
+      for (int e = 0; e < 8; ++e) {
+        const float2 p2 = unpack2(w[e]);
+        v[2 * e] = p2.x; v[2 * e + 1] = p2.y;
+        s += p2.x + p2.y;
+        sq = fmaf(p2.x, p2.x, fmaf(p2.y, p2.y, sq));
+      }
+      // one pass: y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
 #pragma unroll
-      for (int e = 0; e < 16; ++e) { v[e] -= mean; var = fmaf(v[e], v[e], var); }
-      const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + 1e-5f);
+      for (int o2 = 16; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sq += __shfl_xor_sync(0xffffffffu, sq, o2); }
+      const float mean = s * (1.f / D);
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+      const float nmr = -mean * rstd;
       uint32_t o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
-        const float h0 = 0.5f * fmaf(v[2 * e] * rstd, G[2 * e], Bc[2 * e]);
-        const float h1 = 0.5f * fmaf(v[2 * e + 1] * rstd, G[2 * e + 1], Bc[2 * e + 1]);
+        const float h0 = fmaf(fmaf(v[2 * e], rstd, nmr), G[2 * e], Bc[2 * e]);
+        const float h1 = fmaf(fmaf(v[2 * e + 1], rstd, nmr), G[2 * e + 1], Bc[2 * e + 1]);
         float t0, t1;
         asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
         asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
