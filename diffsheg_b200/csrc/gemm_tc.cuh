@@ -290,10 +290,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
           if (CG == 2) {
             // both CTAs fill their own smem; all bytes are credited to the leader's full barrier
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            // p.prefetch == 2: TIMING EXPERIMENT ONLY (wrong results) -- skip the W fill to model a smem-resident W panel
+            const bool skip_w = p.prefetch == 2 && tile != cta_first;
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), skip_w ? 2 * A_BYTES : 2 * STAGE_BYTES);
             const uint32_t lb = leader_full0 + 8u * stage;
             tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
-            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+            if (!skip_w) tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);

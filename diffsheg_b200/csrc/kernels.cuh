@@ -343,30 +343,41 @@ __global__ void __launch_bounds__(256) ln_mod_silu_sample_bf16_kernel(const bf16
     }
   }
   const size_t row0 = (size_t)smp * T;
-  for (int t = warp; t < T; t += 8) {
+  // two rows per iteration: 4 independent 16-byte loads per lane in flight (the kernel is latency / MLP bound otherwise)
+  for (int t = warp; t < T; t += 16) {
+    const int t2 = t + 8;
+    const bool has2 = t2 < T;
     const bf16* yr = y + (row0 + t) * D;
-    float v[16];
-    unpack8(*reinterpret_cast<const uint4*>(yr + lane * 8), *reinterpret_cast<float(*)[8]>(&v[0]));
-    unpack8(*reinterpret_cast<const uint4*>(yr + 256 + lane * 8), *reinterpret_cast<float(*)[8]>(&v[8]));
-    float s = 0.f;
+    const bf16* yr2 = y + (row0 + (has2 ? t2 : t)) * D;
+    const uint4 a0 = *reinterpret_cast<const uint4*>(yr + lane * 8), a1 = *reinterpret_cast<const uint4*>(yr + 256 + lane * 8);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(yr2 + lane * 8), b1 = *reinterpret_cast<const uint4*>(yr2 + 256 + lane * 8);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) s += v[e];
-    const float mean = warp_sum(s) * (1.f / D);
-    float var = 0.f;
+    for (int rr = 0; rr < 2; ++rr) {
+      if (rr == 1 && !has2) break;
+      float v[16];
+      unpack8(rr == 0 ? a0 : b0, *reinterpret_cast<float(*)[8]>(&v[0]));
+      unpack8(rr == 0 ? a1 : b1, *reinterpret_cast<float(*)[8]>(&v[8]));
+      float s = 0.f, sq = 0.f;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { v[e] -= mean; var = fmaf(v[e], v[e], var); }
-    const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + LN_EPS);
-    float o[16];
+      for (int e = 0; e < 16; ++e) { s += v[e]; sq = fmaf(v[e], v[e], sq); }
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const float hh = 0.5f * fmaf(v[e] * rstd, G[e], Bc[e]);
-      float th;
-      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
-      o[e] = fmaf(hh, th, hh);
+      for (int o2 = 16; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sq += __shfl_xor_sync(0xffffffffu, sq, o2); }
+      const float mean = s * (1.f / D);
+      // FFN output rows are O(1) with |mean| << std: E[x^2] - mean^2 is safe in fp32 (clamped at 0)
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + LN_EPS);
+      const float nmr = -mean * rstd;
+      float o[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float hh = 0.5f * fmaf(fmaf(v[e], rstd, nmr), G[e], Bc[e]);
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+        o[e] = fmaf(hh, th, hh);
+      }
+      bf16* zr = z + (row0 + (rr == 0 ? t : t2)) * D;
+      *reinterpret_cast<uint4*>(zr + lane * 8) = pack8(*reinterpret_cast<float(*)[8]>(&o[0]));
+      *reinterpret_cast<uint4*>(zr + 256 + lane * 8) = pack8(*reinterpret_cast<float(*)[8]>(&o[8]));
     }
-    bf16* zr = z + (row0 + t) * D;
-    *reinterpret_cast<uint4*>(zr + lane * 8) = pack8(*reinterpret_cast<float(*)[8]>(&o[0]));
-    *reinterpret_cast<uint4*>(zr + 256 + lane * 8) = pack8(*reinterpret_cast<float(*)[8]>(&o[8]));
   }
 }
 

@@ -222,6 +222,60 @@ def test_denoise_matches_oracle_variants(prec):
     assert err < TOL[prec]["call"]
 
 
+@pytest.mark.parametrize("prec,name,B,T,over", [
+    ("bf16", "show", 2, 100, {}),                       # T > 96: generic attention kernel + fp32 row scratch in bf16 mode
+    ("bf16", "show", 1, 7, {}),                         # one 16-row m-tile, mostly padding
+    ("bf16", "show", 3, 96, dict(cond_scale=1.15)),     # the shipped inference script's guidance scale, T = 6 full m-tiles
+    ("fp32", "beat", 1, 34, {}),                        # B = 1 with a 1-D person id (transformer.py:502-503)
+])
+def test_denoise_edge_shapes_vs_oracle(prec, name, B, T, over):
+    from oracle.denoiser import unidiffuser_forward
+    cfg, sd, eng = _engine(name, prec, B, T, **over)
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=11).items()}
+    pid = inp["person_id"][0] if (B == 1 and prec == "fp32") else inp["person_id"]
+    eng.prepare_window(inp["mel"], inp["hubert"], pid)
+    a, b = 2.3, 2.07
+    got = eng.denoise(inp["x_T"], 720, a, b)
+    ts = torch.full((B,), 720, dtype=torch.long, device="cuda")
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        want = unidiffuser_forward(sd_c, cfg, inp["x_T"], ts, (torch.tensor(a, device="cuda"), torch.tensor(b, device="cuda")),
+                                   inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float64)
+    err = relmax(got, want)
+    print(f"\n[parity] denoise edge {name} B{B} T{T} {over} {prec}: relmax={err:.3e}")
+    assert torch.isfinite(got).all() and err < TOL[prec]["call"]
+
+
+@pytest.mark.parametrize("opt_over,calls,undos", [(dict(no_resample=True), 15, 0), (dict(addBlend=False, jump_n_sample=2), 27, 12),
+                                                  (dict(no_repaint=True), 25, 0)])
+def test_repaint_flags_match_oracle_same_seed(opt_over, calls, undos):
+    """--no_resample (sch:178-209 with jump 1x1: 15 calls), --addBlend False, --no_repaint (plain 25-step loop that still merges the
+    known frames, gd:1036-1056 / gd:1126) in the strict fp32 mode."""
+    from diffsheg_b200 import FusedSpacedDiffusion, get_named_beta_schedule, space_timesteps
+    import refshim
+    B, T, ov = 2, 34, 4
+    cfg, sd, eng = _engine("beat", "fp32", B, T)
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=2).items()}
+    gt = torch.zeros(B, T, cfg["net_dim_pose"], device="cuda")
+    gt[:, :ov] = torch.randn(B, ov, cfg["net_dim_pose"], device="cuda")
+    mask = torch.zeros(B, T, cfg["net_dim_pose"], dtype=torch.bool, device="cuda")
+    mask[:, :ov] = True
+    y = {"gt": gt, "outpainting_mask": mask}
+    okw = dict(no_resample=opt_over.get("no_resample", False), no_repaint=opt_over.get("no_repaint", False),
+               add_blend=opt_over.get("addBlend", True), jump_n_sample=opt_over.get("jump_n_sample", 5))
+    want = _oracle_loop_cuda(cfg, sd, inp, y, ov, **okw)
+    opt = refshim.make_opt(cfg, overlap_len=ov, **opt_over)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    kw = dict(audio_emb=inp["mel"], length=None, person_id=inp["person_id"], add_cond={"pretrain_aud_feat": inp["hubert"]},
+              y=y, pe_type="pe_sinu")
+    torch.manual_seed(77)
+    out = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), clip_denoised=False, model_kwargs=kw)
+    err = relmax(out, want)
+    print(f"\n[parity] repaint flags {opt_over}: relmax={err:.3e} stats={diff.last_stats}")
+    assert diff.last_stats == {"denoise_calls": calls, "undo_steps": undos}
+    assert err < TOL["fp32"]["loop"]
+
+
 # ------------------------------------------------------------------------------------------------
 # full loops
 # ------------------------------------------------------------------------------------------------
