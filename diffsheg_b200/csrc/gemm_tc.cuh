@@ -276,8 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // prefetch the next tile's A panel into L2 (only when it is a new M-tile: the n-fastest order makes the
         // CTAs of one wave share a panel, so each panel is prefetched by the tiles_n CTAs that will read it)
         const int next = tile + cta_stride;
-        const bool pf = p.prefetch && CG == 1 && next < num_tiles && (next / p.tiles_n) != m_blk;
-        const int pf_m = pf ? (next / p.tiles_n) * BM : 0;
+        const bool pf = p.prefetch == 1 && next < num_tiles && (next / p.tiles_n) != (tile / p.tiles_n);
+        const int pf_m = pf ? ((next / p.tiles_n) * CG + (int)rank) * BM : 0;
         int seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           while (kb >= p.seg_kb_start[seg + 1]) ++seg;

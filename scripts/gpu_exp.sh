@@ -1,12 +1,13 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -s -k "edge_shapes or repaint_flags or long_form" > gpurun_out/t15.log 2>&1; echo "t rc=$?" > gpurun_out/rc15.txt
-timeout 600 python scripts/bench_gemm.py > gpurun_out/gemm_sweep15.log 2>&1
-DSHEG_TC_PREFETCH=2 timeout 600 python scripts/bench_gemm.py > gpurun_out/gemm_sweep15_skipw.log 2>&1
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench15.log 2>&1; echo "bench rc=$?" >> gpurun_out/rc15.txt
-cat gpurun_out/rc15.txt; grep -E "passed|failed|rror" gpurun_out/t15.log | tail -3; grep "parity\]" gpurun_out/t15.log | cut -c1-150
-echo "--- normal"; cut -c1-150 gpurun_out/gemm_sweep15.log | head -7; echo "--- skip W fill (timing model of resident W)"; cut -c1-150 gpurun_out/gemm_sweep15_skipw.log | head -7
+DSHEG_TC_PREFETCH=1 timeout 600 python scripts/bench_gemm.py > gpurun_out/gemm_sweep16_pf.log 2>&1
+DSHEG_TC_PREFETCH=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench16_pf.log 2>&1
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench16.log 2>&1
+bash scripts/gpu_profile.sh > gpurun_out/profile16.log 2>&1
+echo "--- pair prefetch"; cut -c1-150 gpurun_out/gemm_sweep16_pf.log | head -7
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/bench15.log").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], "gemm", d["roofline"]["achieved"], d["roofline"]["ms_per_step"], "attn", d["roofline_attention"]["ms_per_step"], "row", d["rowwise"])
+for f in ("gpurun_out/bench16_pf.log","gpurun_out/bench16.log"):
+    d=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, d["value"], d["ms_per_step"], "gemm", d["roofline"]["achieved"], d["roofline"]["ms_per_step"], "attn", d["roofline_attention"]["ms_per_step"], "row", d["rowwise"]["ms_per_step"])
 PY
+tail -4 gpurun_out/profile16.log
