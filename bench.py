@@ -23,6 +23,9 @@ import torch  # noqa: E402
 METRIC = "motion-frames/sec (ddim25, n_poses=88, bs=950)"
 UNIT = "frames/s"
 CANON_FLOP_PER_FRAME_CALL = 258.83e6  # SHOW + CFG, FlopCounterMode on the reference op stream
+# algorithmic bytes (bf16 A + output + residual, W negligible) of one layer's GEMMs at R = 167 200 rows, cond half 83 600:
+# feat1 (2 KB in + 2 KB out per cond row), feat2 (2+1+1), qkv (1+3), sa_out (1+1+1), ffn1 (1+2), ffn2 (2+1), ffn_out (1+1+1)
+ALGO_GEMM_BYTES_PER_LAYER = 83600 * (4096 + 4096) + 167200 * (4096 + 3072 + 3072 + 3072 + 3072)
 
 
 def peaks():
@@ -258,6 +261,15 @@ def run_ours(args):
                  "share_of_step": at["ms"] / ms if world == 1 else None}
     if rank != 0:
         return
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one layer's 7 GEMM launches)
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01", "final_gemm_ncu_summary.json")))
+        roof["traffic"] = 1e6 * sum(k["dram_read_MB"] + k["dram_write_MB"] for k in ncu) / len(ncu)
+        roof["traffic_note"] = ("mean dram__bytes_read+write per launch over the 7 GEMMs of one layer (ncu --set full, "
+                                "profiles/r01/final_gemm_ncu_summary.json); algorithmic operand+output bytes of the same launches: "
+                                f"{ALGO_GEMM_BYTES_PER_LAYER / 7 / 1e6:.0f} MB per launch")
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
