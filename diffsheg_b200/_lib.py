@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(_HERE, "libdiffsheg_b200.so")
+SO_PATH = os.environ.get("DSHEG_LIB") or os.path.join(_HERE, "libdiffsheg_b200.so")   # DSHEG_LIB: experiment builds
 HEADER = os.path.join(ROOT, "include", "diffsheg_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -44,7 +44,10 @@ template <int BN, int CG = 1> struct Cfg {
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
-  static constexpr int STAGES = CG == 2 ? 4 : (BN == 128 ? 5 : 3);
+#ifndef DSHEG_PAIR_STAGES
+#define DSHEG_PAIR_STAGES 4
+#endif
+  static constexpr int STAGES = CG == 2 ? DSHEG_PAIR_STAGES : (BN == 128 ? 5 : 3);
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
