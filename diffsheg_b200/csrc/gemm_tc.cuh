@@ -33,21 +33,26 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_ACC = 2;
 constexpr int UMMA_K = 16;
 constexpr int CPW = 64;            // accumulator columns per epilogue warp (= one 128-byte bf16 row segment)
-constexpr int STG_BYTES = 32 * CPW * 2;  // per-warp staging box: 32 rows x 64 bf16, 128B-swizzled
+constexpr int STG_BYTES_WIDE = 32 * CPW * 2;   // per-warp staging box: 32 rows x 64 bf16 (128-byte rows, SWIZZLE_128B)
+constexpr int STG_BYTES_NARROW = 32 * 32 * 2;  // 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B), used twice per tile
 constexpr int BAR_BYTES = 512;
 
 // CG = 1: one CTA per tile (128 x BN).  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile:
 // each CTA stages its 128 A rows and HALF of the W tile (128 of the 256 N rows); the pair's tensor cores read both
 // halves, so the smem fill + operand-read traffic per MMA drops by a third.  ncu on the CG = 1 kernel showed it
 // bound by shared-memory bandwidth (TMA fill 96 B/clk + UMMA operand reads 96 B/clk against ~128 B/clk).
-template <int BN, int CG = 1> struct Cfg {
+// NARROW (pair kernels without a bf16 residual): the epilogue box shrinks to 2 KB per warp and is used once per
+// 32-column chunk, which frees 32 KB for a FIFTH pipeline stage -- the pair mainloop is pipeline-depth bound
+// (2 / 3 / 4 stages: 793 / 1085 / 1234 TF/s on the qkv shape, profiles/r01/final_gemm_sweep_pair_stages*.txt).
+template <int BN, int CG = 1, bool NARROW = false> struct Cfg {
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
 #ifndef DSHEG_PAIR_STAGES
 #define DSHEG_PAIR_STAGES 4
 #endif
-  static constexpr int STAGES = CG == 2 ? DSHEG_PAIR_STAGES : (BN == 128 ? 5 : 3);
+  static constexpr int STG_BYTES = NARROW ? STG_BYTES_NARROW : STG_BYTES_WIDE;
+  static constexpr int STAGES = CG == 2 ? (NARROW ? DSHEG_PAIR_STAGES + 1 : DSHEG_PAIR_STAGES) : (BN == 128 ? 5 : 3);
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
@@ -224,8 +229,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
-  using C = Cfg<BN, CG>;
-  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE;
+  constexpr bool NARROW = (CG == 2 && RES != RES_BF16 && !OUTF32);
+  using C = Cfg<BN, CG, NARROW>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE, STG_BYTES = C::STG_BYTES;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
   const int cta_stride = gridDim.x / CG, cta_first = blockIdx.x / CG;   // tiles are walked per CTA (pair)
   extern __shared__ uint8_t smem_raw[];
@@ -362,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       epi_bar_sync<NE * 32>();
       const int m0 = m_blk * BM + q * 32;     // first row of this warp's box
       const int nc0 = n_tile0 + cg * CPW;     // first column of this warp's box
-      if (!OUTF32) {
+      if (!OUTF32 && !NARROW) {
         if (lane == 0) bulk_wait_read0();     // the previous tile's TMA store has finished reading the box
         __syncwarp();
         if (RES == RES_BF16 && lane == 0) {   // residual box by TMA, in flight while the mainloop runs
@@ -434,6 +440,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int j = 0; j < 32; ++j) if (n0 + j < p.N) op[j] = v[j];
             }
           }
+        } else if (NARROW) {
+          // 2 KB box (32 rows x 64 B, SWIZZLE_64B: chunk c of row r at c ^ ((r >> 1) & 3)), reused for every 32-column chunk
+          if (RES != RES_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+          }
+          if (lane == 0) bulk_wait_read0();   // the previous chunk's / tile's TMA store has finished reading the box
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
+            w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
+            w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
+            w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
+            *reinterpret_cast<uint4*>(stg_gen + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = w;
+          }
+          fence_async_smem();                 // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, stg, n0, m0);
+            if (p.out2) tma_store_2d(&tmOut2, stg, n0, m0);
+            bulk_commit();
+          }
         } else {
           // this thread's row of the box: 16-byte chunk c of row `lane` lives at chunk position c ^ (lane & 7)
 #pragma unroll
@@ -468,7 +498,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) {                               // TMEM stage is free for the (leader's) MMA warp
         if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
       }
-      if (!OUTF32) {
+      if (!OUTF32 && !NARROW) {
         fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
@@ -511,11 +541,11 @@ inline EncodeTiledFn get_encode_fn() {
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle,
 // out-of-bounds elements read as zero (ragged M / N / K tails need no padding in memory).
-inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err);
+inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, std::string* err);
 
 // Encoding a tensor map costs ~1 us of host time and a GEMM needs up to 8: cache them (workspace pointers are
 // stable for the life of a handle), which matters for the launch-bound small-batch configurations.
-inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
+inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err, int box_cols = BK) {
   struct Key {
     const void* p; int r, c, l, b;
     bool operator==(const Key& o) const { return p == o.p && r == o.r && c == o.c && l == o.l && b == o.b; }
@@ -529,26 +559,28 @@ inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int
     }
   };
   static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
-  const Key k{ptr, rows, cols, ld, box_rows};
+  const Key k{ptr, rows, cols, ld, box_rows * 1024 + box_cols};
   auto it = cache.find(k);
   if (it != cache.end()) { *map = it->second; return true; }
-  if (!make_tmap_uncached(map, ptr, rows, cols, ld, box_rows, err)) return false;
+  if (!make_tmap_uncached(map, ptr, rows, cols, ld, box_rows, box_cols, err)) return false;
   if (cache.size() > 8192) cache.clear();
   cache.emplace(k, *map);
   return true;
 }
 
-inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
-  // box = [box_rows x 64 columns] = 128-byte rows: operand tiles (K-major) and epilogue boxes share this geometry
+inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, std::string* err) {
+  // box = [box_rows x 64 columns] (128-byte rows, SWIZZLE_128B): operand tiles and wide epilogue boxes;
+  // box = [box_rows x 32 columns] (64-byte rows, SWIZZLE_64B): narrow epilogue boxes
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) { *err = "TMA operand not 16-byte aligned"; return false; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r); return false; }
   return true;
@@ -557,19 +589,20 @@ inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int 
 template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG>;
+  using C = Cfg<BN, CG, (CG == 2 && RES != RES_BF16 && !OUTF32)>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if (CG == 1) {
-    kern<<<grid, Cfg<BN, CG>::NUM_THREADS, Cfg<BN, CG>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+    kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg<BN, CG>::NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -636,9 +669,10 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   if (kb * BK != d.Kp) { *err = "GEMM weight K padding does not match the A segments"; return cudaErrorInvalidValue; }
   if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, bn / cg, err)) return cudaErrorInvalidValue;
   maps[5] = maps[6] = maps[7] = maps[4];
-  if (!d.out_f32) {  // epilogue boxes: 32 rows x 64 columns of the bf16 output / residual
-    if (!make_tmap(&maps[5], d.out, d.M, d.N, d.ldo, 32, err)) return cudaErrorInvalidValue;
-    if (d.out2 && !make_tmap(&maps[6], d.out2, d.M, d.N, d.ldo, 32, err)) return cudaErrorInvalidValue;
+  if (!d.out_f32) {  // epilogue boxes: 32 rows x 64 columns of the bf16 output / residual (32 columns for NARROW kernels)
+    const int bc = (cg == 2 && !(d.res && !d.res_f32)) ? 32 : BK;
+    if (!make_tmap(&maps[5], d.out, d.M, d.N, d.ldo, 32, err, bc)) return cudaErrorInvalidValue;
+    if (d.out2 && !make_tmap(&maps[6], d.out2, d.M, d.N, d.ldo, 32, err, bc)) return cudaErrorInvalidValue;
     if (d.res && !d.res_f32 && !make_tmap(&maps[7], d.res, d.M, d.N, d.ldr, 32, err)) return cudaErrorInvalidValue;
   }
   p.tiles_m = (d.M + BM * cg - 1) / (BM * cg); p.tiles_n = (d.N + bn - 1) / bn;   // tiles per CTA (pair)
