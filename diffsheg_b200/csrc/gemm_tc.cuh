@@ -223,13 +223,13 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
   return x;
 }
 
-template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG>
+template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool NARROW_>
 __global__ void __launch_bounds__(Cfg<BN, CG>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
-  constexpr bool NARROW = (CG == 2 && RES != RES_BF16 && !OUTF32);
+  constexpr bool NARROW = (NARROW_ && CG == 2 && RES != RES_BF16 && !OUTF32);
   using C = Cfg<BN, CG, NARROW>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE, STG_BYTES = C::STG_BYTES;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
@@ -586,10 +586,10 @@ inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int 
   return true;
 }
 
-template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG>
+template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool NARROW_ = false>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG>;
-  using C = Cfg<BN, CG, (CG == 2 && RES != RES_BF16 && !OUTF32)>;
+  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG, NARROW_>;
+  using C = Cfg<BN, CG, (NARROW_ && CG == 2 && RES != RES_BF16 && !OUTF32)>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -612,11 +612,17 @@ inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int 
 
 template <int BN, int CG>
 inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st,
-                            std::string* err) {
+                            std::string* err, bool narrow = false) {
   const bool ln = d.csum != nullptr;
   const int res = !d.res ? RES_NONE : (d.res_f32 ? RES_F32_MOD : RES_BF16);
   if (d.out_f32) {
     if (!ln && d.act == ACT_NONE && res == RES_NONE && !d.out2) return launch_variant<BN, false, ACT_NONE, RES_NONE, true, CG>(maps, p, grid, st);
+  } else if (CG == 2 && narrow && res == RES_NONE) {   // long K loops: 2 KB epilogue boxes, one more pipeline stage
+    if (ln && d.act == ACT_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG, true>(maps, p, grid, st);
+    if (ln && d.act == ACT_SILU) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
+    if (!ln && d.act == ACT_NONE) return launch_variant<BN, false, ACT_NONE, RES_NONE, false, CG, true>(maps, p, grid, st);
+    if (!ln && d.act == ACT_GELU) return launch_variant<BN, false, ACT_GELU, RES_NONE, false, CG, true>(maps, p, grid, st);
+    if (!ln && d.act == ACT_SILU) return launch_variant<BN, false, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
   } else if (ln) {
     if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
@@ -654,6 +660,8 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   int cg = cg_force ? cg_force : g_cg_override();
   if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096 && d.Kp >= 512) ? 2 : 1;   // short K loops: single CTAs win (profiles/r01 sweep)
   if (bn != 256) cg = 1;
+  // K >= 768: the mainloop dominates -> narrow epilogue boxes + 5 stages (K = 512 tiles are epilogue-sensitive: wide boxes)
+  const bool narrow = cg == 2 && !d.out_f32 && !d.res && d.Kp >= 768;
   Params p{};
   CUtensorMap maps[8];
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
@@ -670,7 +678,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   if (!make_tmap(&maps[4], d.w, d.N, d.Kp, d.Kp, bn / cg, err)) return cudaErrorInvalidValue;
   maps[5] = maps[6] = maps[7] = maps[4];
   if (!d.out_f32) {  // epilogue boxes: 32 rows x 64 columns of the bf16 output / residual (32 columns for NARROW kernels)
-    const int bc = (cg == 2 && !(d.res && !d.res_f32)) ? 32 : BK;
+    const int bc = narrow ? 32 : BK;
     if (!make_tmap(&maps[5], d.out, d.M, d.N, d.ldo, 32, err, bc)) return cudaErrorInvalidValue;
     if (d.out2 && !make_tmap(&maps[6], d.out2, d.M, d.N, d.ldo, 32, err, bc)) return cudaErrorInvalidValue;
     if (d.res && !d.res_f32 && !make_tmap(&maps[7], d.res, d.M, d.N, d.ldr, 32, err)) return cudaErrorInvalidValue;
@@ -691,7 +699,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
     if (pf < 0) { const char* e = getenv("DSHEG_TC_PREFETCH"); pf = e ? atoi(e) : 0; }
     p.prefetch = pf;
   }
-  if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err);
+  if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, narrow);
   return bn == 256 ? dispatch<256, 1>(d, maps, p, grid, st, err) : dispatch<128, 1>(d, maps, p, grid, st, err);
 }
 
