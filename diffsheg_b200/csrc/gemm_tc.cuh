@@ -49,16 +49,21 @@ template <int BN, int CG = 1, bool NARROW = false> struct Cfg {
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
 #ifndef DSHEG_PAIR_STAGES
-#define DSHEG_PAIR_STAGES 4
+#define DSHEG_PAIR_STAGES 5
 #endif
   static constexpr int STG_BYTES = NARROW ? STG_BYTES_NARROW : STG_BYTES_WIDE;
   static constexpr int STAGES = CG == 2 ? (NARROW ? DSHEG_PAIR_STAGES + 1 : DSHEG_PAIR_STAGES) : (BN == 128 ? 5 : 3);
+  // pair kernels run at the smem limit: the dynamic smem base is required to be 1024-aligned (checked, traps otherwise)
+  // and the per-tile bias/csum vectors are single-buffered (one extra epilogue barrier per tile)
+  static constexpr int ALIGN_SLACK = CG == 2 ? 0 : 1024;
+  static constexpr int NVEC = CG == 2 ? 1 : NUM_ACC;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
-  static constexpr int VEC_BYTES = NUM_ACC * 2 * BN * 4;
+  static constexpr int VEC_BYTES = NVEC * 2 * BN * 4;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = PIPE_BYTES + NE * STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + VEC_BYTES;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + NE * STG_BYTES + ALIGN_SLACK + BAR_BYTES + VEC_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 };
@@ -234,8 +239,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE, STG_BYTES = C::STG_BYTES;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
   const int cta_stride = gridDim.x / CG, cta_first = blockIdx.x / CG;   // tiles are walked per CTA (pair)
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
+  if (C::ALIGN_SLACK == 0 && smem_base != smem_u32(smem_raw)) __trap();   // pair kernels have no room for slack
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stg_base = smem_base + C::PIPE_BYTES;
   const uint32_t bar_base = stg_base + NE * STG_BYTES;
@@ -357,7 +363,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
       const int n_tile0 = n_blk * BN;
       // ---- stage per-column vectors for this tile (double-buffered with the accumulator stage)
-      float* vb = vecs + acc * 2 * BN;
+      float* vb = vecs + (C::NVEC == 1 ? 0 : acc) * 2 * BN;
+      if (C::NVEC == 1) epi_bar_sync<NE * 32>();   // single buffer: everyone is done reading the previous tile's vectors
       for (int i = etid; i < BN; i += NE * 32) {
         const int n = n_tile0 + i;
         const float bv = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
