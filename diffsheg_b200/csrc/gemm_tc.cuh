@@ -44,19 +44,23 @@ constexpr int BAR_BYTES = 512;
 // NARROW (pair kernels without a bf16 residual): the epilogue box shrinks to 2 KB per warp and is used once per
 // 32-column chunk, which frees 32 KB for a FIFTH pipeline stage -- the pair mainloop is pipeline-depth bound
 // (2 / 3 / 4 stages: 793 / 1085 / 1234 TF/s on the qkv shape, profiles/r01/final_gemm_sweep_pair_stages*.txt).
-template <int BN, int CG = 1, bool NARROW = false> struct Cfg {
+// LONGK (K >= 768, pair kernels): the mainloop dominates, so the kernel runs at the smem limit -- no alignment slack (the
+// dynamic smem base must be 1024-aligned: checked, traps otherwise), single-buffered bias/csum vectors (one extra epilogue
+// barrier per tile) -> 6 stages with narrow boxes, 5 with wide (residual) boxes.  K = 512 tiles are epilogue-sensitive and
+// keep 4 stages, wide boxes and double-buffered vectors (profiles/r01/v8_gemm_sweep.txt vs final_gemm_sweep.txt).
+template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cfg {
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
 #ifndef DSHEG_PAIR_STAGES
-#define DSHEG_PAIR_STAGES 5
+#define DSHEG_PAIR_STAGES 4
 #endif
   static constexpr int STG_BYTES = NARROW ? STG_BYTES_NARROW : STG_BYTES_WIDE;
-  static constexpr int STAGES = CG == 2 ? (NARROW ? DSHEG_PAIR_STAGES + 1 : DSHEG_PAIR_STAGES) : (BN == 128 ? 5 : 3);
+  static constexpr int STAGES = CG == 2 ? (LONGK ? (NARROW ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES) : (BN == 128 ? 5 : 3);
   // pair kernels run at the smem limit: the dynamic smem base is required to be 1024-aligned (checked, traps otherwise)
   // and the per-tile bias/csum vectors are single-buffered (one extra epilogue barrier per tile)
-  static constexpr int ALIGN_SLACK = CG == 2 ? 0 : 1024;
-  static constexpr int NVEC = CG == 2 ? 1 : NUM_ACC;
+  static constexpr int ALIGN_SLACK = (CG == 2 && LONGK) ? 0 : 1024;
+  static constexpr int NVEC = (CG == 2 && LONGK) ? 1 : NUM_ACC;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
@@ -228,14 +232,15 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
   return x;
 }
 
-template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool NARROW_>
+template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool LONGK_>
 __global__ void __launch_bounds__(Cfg<BN, CG>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
-  constexpr bool NARROW = (NARROW_ && CG == 2 && RES != RES_BF16 && !OUTF32);
-  using C = Cfg<BN, CG, NARROW>;
+  constexpr bool LONGK = LONGK_ && CG == 2 && !OUTF32;
+  constexpr bool NARROW = LONGK && RES != RES_BF16;
+  using C = Cfg<BN, CG, NARROW, LONGK>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE, STG_BYTES = C::STG_BYTES;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
   const int cta_stride = gridDim.x / CG, cta_first = blockIdx.x / CG;   // tiles are walked per CTA (pair)
@@ -593,10 +598,10 @@ inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int 
   return true;
 }
 
-template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool NARROW_ = false>
+template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool LONGK_ = false>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG, NARROW_>;
-  using C = Cfg<BN, CG, (NARROW_ && CG == 2 && RES != RES_BF16 && !OUTF32)>;
+  auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG, LONGK_>;
+  using C = Cfg<BN, CG, (LONGK_ && CG == 2 && !OUTF32 && RES != RES_BF16), (LONGK_ && CG == 2 && !OUTF32)>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -619,12 +624,14 @@ inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int 
 
 template <int BN, int CG>
 inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st,
-                            std::string* err, bool narrow = false) {
+                            std::string* err, bool longk = false) {
   const bool ln = d.csum != nullptr;
   const int res = !d.res ? RES_NONE : (d.res_f32 ? RES_F32_MOD : RES_BF16);
   if (d.out_f32) {
     if (!ln && d.act == ACT_NONE && res == RES_NONE && !d.out2) return launch_variant<BN, false, ACT_NONE, RES_NONE, true, CG>(maps, p, grid, st);
-  } else if (CG == 2 && narrow && res == RES_NONE) {   // long K loops: 2 KB epilogue boxes, one more pipeline stage
+  } else if (CG == 2 && longk && !ln && d.act == ACT_NONE && res == RES_BF16) {   // long K, residual: wide boxes, 5 stages
+    return launch_variant<BN, false, ACT_NONE, RES_BF16, false, CG, true>(maps, p, grid, st);
+  } else if (CG == 2 && longk && res == RES_NONE) {   // long K loops: 2 KB epilogue boxes, 6 stages
     if (ln && d.act == ACT_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG, true>(maps, p, grid, st);
     if (ln && d.act == ACT_SILU) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
     if (!ln && d.act == ACT_NONE) return launch_variant<BN, false, ACT_NONE, RES_NONE, false, CG, true>(maps, p, grid, st);
@@ -667,8 +674,9 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   int cg = cg_force ? cg_force : g_cg_override();
   if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096 && d.Kp >= 512) ? 2 : 1;   // short K loops: single CTAs win (profiles/r01 sweep)
   if (bn != 256) cg = 1;
-  // K >= 768: the mainloop dominates -> narrow epilogue boxes + 5 stages (K = 512 tiles are epilogue-sensitive: wide boxes)
-  const bool narrow = cg == 2 && !d.out_f32 && !d.res && d.Kp >= 768;
+  // K >= 768: the mainloop dominates -> deeper ring (and narrow epilogue boxes when there is no bf16 residual box to load)
+  const bool longk = cg == 2 && !d.out_f32 && d.Kp >= 768 && !(d.res && d.res_f32);
+  const bool narrow = longk && !d.res;
   Params p{};
   CUtensorMap maps[8];
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
@@ -706,7 +714,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
     if (pf < 0) { const char* e = getenv("DSHEG_TC_PREFETCH"); pf = e ? atoi(e) : 0; }
     p.prefetch = pf;
   }
-  if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, narrow);
+  if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, longk);
   return bn == 256 ? dispatch<256, 1>(d, maps, p, grid, st, err) : dispatch<128, 1>(d, maps, p, grid, st, err);
 }
 
