@@ -415,6 +415,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int ch = 0; ch < CPW / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
+        if (ch == CPW / 32 - 1) {   // last TMEM read of this warp is complete: hand the accumulator stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+          }
+        }
         const int n0 = nc0 + ch * 32;
         const float* bvec = vb + cg * CPW + ch * 32 + (LN ? 0 : bsel);
         float v[32];
@@ -505,11 +512,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       if (RES != RES_NONE && !OUTF32 && p.ps_out && row_ok) p.ps_out[(size_t)m * (p.N / CPW) + (nc0 / CPW)] = make_float2(psum, psq);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {                               // TMEM stage is free for the (leader's) MMA warp
-        if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
-      }
       if (!OUTF32 && !NARROW) {
         fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
