@@ -620,9 +620,17 @@ int dsheg_load_tensor(dsheg_handle* h, const char* key, const void* host_data, i
   CK(cudaMalloc(&t.ptr, bytes ? bytes : 16));
   CK(cudaMemcpy(t.ptr, host_data, bytes, cudaMemcpyHostToDevice));
   auto it = h->tensors.find(key);
-  if (it != h->tensors.end()) { cudaFree(it->second.ptr); h->tensors.erase(it); }
+  if (it != h->tensors.end()) {
+    // a captured graph may still reference the old allocation: drop every graph before freeing it
+    cudaDeviceSynchronize();
+    for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+    cudaFree(it->second.ptr);
+    h->tensors.erase(it);
+  }
   h->tensors[key] = t;
   h->finalized = false;
+  h->window_ready = false;
   return 0;
 }
 

@@ -713,7 +713,13 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   const int grid = (tiles < units ? tiles : units) * cg;
   {
     static int pf = -1;
-    if (pf < 0) { const char* e = getenv("DSHEG_TC_PREFETCH"); pf = e ? atoi(e) : 0; }
+    if (pf < 0) {
+      const char* e = getenv("DSHEG_TC_PREFETCH");
+      pf = e ? atoi(e) : 0;
+      // 2 = W-fill-skipping TIMING experiment (wrong results): only honoured together with an explicit opt-in
+      if (pf == 2 && !getenv("DSHEG_ALLOW_TIMING_EXPERIMENTS")) pf = 0;
+      if (pf < 0 || pf > 2) pf = 0;
+    }
     p.prefetch = pf;
   }
   if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, longk);

@@ -143,12 +143,18 @@ class FusedGaussianDiffusion:
             return model
         inner = getattr(model, "module", model)  # DDP wrapper, show:271-274
         key = id(inner)
+        # weights may change between calls (train-time evaluation, show:439-502; trainer.load, show:278-292):
+        # Parameter._version counts in-place updates and load_state_dict copies, without a device sync
+        stamp = sum(int(p._version) for p in inner.parameters())
         eng = self._engines.get(key)
+        if eng is not None and getattr(eng, "_weights_stamp", None) != stamp:
+            eng = None
         if eng is None or eng.max_batch < B or eng.max_frames < T:
             dev = next(inner.parameters()).device
             eng = FusedUniDiffuser.from_module(inner, getattr(inner, "opt", self.opt), precision=self.precision,
                                                max_batch=max(B, self.max_batch or 0), max_frames=max(T, 2),
                                                device=dev.index or 0)
+            eng._weights_stamp = stamp
             self._engines[key] = eng
         return eng
 

@@ -1,0 +1,85 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no kernels)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from diffsheg_b200 import (FusedGaussianDiffusion, FusedSpacedDiffusion, build_diffusions, cfg_from_opt, get_windows,
+                           patch_trainer, space_timesteps, synth)
+from oracle import diffusion as odiff
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cfg_from_opt_accepts_the_shipped_configs_and_rejects_the_rest():
+    for name in ("show", "beat"):
+        cfg0 = synth.make_cfg(name)
+        cfg = cfg_from_opt(synth.make_opt(cfg0))
+        for k in ("dim_pose", "expression_dim", "style_dim", "classifier_free", "cond_scale", "net_dim_pose"):
+            assert cfg[k] == cfg0[k], k
+    opt = synth.make_opt(synth.make_cfg("show"))
+    for field, bad in (("model_base", "transformer_decoder"), ("cond_projection", "linear_includeX"), ("unidiffuser", False),
+                       ("encode_hubert", False), ("model_mean_type", "start_x")):
+        o = argparse.Namespace(**vars(opt))
+        setattr(o, field, bad)
+        with pytest.raises(NotImplementedError):
+            cfg_from_opt(o)
+
+
+def test_unsupported_sampler_options_fail_loudly():
+    betas = np.linspace(1e-4, 0.02, 1000)
+    with pytest.raises(NotImplementedError):
+        FusedGaussianDiffusion(betas=betas, model_mean_type="START_X")
+    with pytest.raises(NotImplementedError):
+        FusedGaussianDiffusion(betas=betas, model_var_type="LEARNED_RANGE")
+    with pytest.raises(NotImplementedError):
+        FusedGaussianDiffusion(betas=betas, opt=argparse.Namespace(same_overlap_noisy=True))
+    d = FusedGaussianDiffusion(betas=betas)
+    with pytest.raises(NotImplementedError):  # generate_batch always passes clip_denoised=False (show:173)
+        d.ddim_sample_loop(None, (1, 2, 3), clip_denoised=True, model_kwargs={})
+    with pytest.raises(NotImplementedError):
+        d.p_sample_loop(None, (1, 2, 3), clip_denoised=False, cond_fn=lambda *a: None, model_kwargs={})
+
+
+def test_patch_trainer_swaps_both_sampler_objects():
+    cfg = synth.make_cfg("show")
+
+    class Trainer:  # the two attributes DDPMTrainer_show builds at show:63-80
+        def __init__(self, opt):
+            self.opt, self.diffusion, self.diffusion_ddim_val = opt, object(), object()
+
+    tr = patch_trainer(Trainer(synth.make_opt(cfg, ddim=True)))
+    assert isinstance(tr.diffusion, FusedGaussianDiffusion) and tr.diffusion.num_timesteps == 1000
+    assert isinstance(tr.diffusion_ddim_val, FusedSpacedDiffusion) and tr.diffusion_ddim_val.num_timesteps == 25
+    assert tr.diffusion_ddim_val.timestep_map == list(range(0, 1000, 40))   # 'ddim25' is hard-coded at show:73
+    full, ddim = build_diffusions(synth.make_opt(cfg, ddim=False))
+    assert ddim is None and full.num_timesteps == 1000
+
+
+@pytest.mark.parametrize("n,spec", [(1000, "ddim25"), (1000, "ddim50"), (100, "10,5"), (300, "10,15,20"), (40, "ddim8")])
+def test_space_timesteps_matches_oracle(n, spec):
+    assert space_timesteps(n, spec) == odiff.space_timesteps(n, spec)
+
+
+def test_get_windows_mirrors_the_reference_rule():
+    import torch
+    x = torch.arange(2 * 1800 * 3, dtype=torch.float32).view(2, 1800, 3)
+    w = get_windows(x, 88, 78)
+    assert len(w) == 23 and [t.shape[1] for t in w[-2:]] == [88, 84]
+    assert torch.equal(w[1], x[:, 78:166]) and torch.equal(w[-1], x[:, 22 * 78:])
+    assert len(get_windows(x[:, :88], 88, 78)) == 1 and len(get_windows(x[:, :60], 88, 78)) == 1
+    d = get_windows({"a": x, "b": x * 2}, 88, 78)
+    assert len(d) == 23 and torch.equal(d[3]["b"], w[3] * 2)
+
+
+def test_reference_arm_prints_one_contract_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-batch", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
