@@ -147,7 +147,9 @@ class FusedUniDiffuser:
         hub = (add_cond or {}).get("pretrain_aud_feat")
         if hub is None:
             raise ValueError("add_cond['pretrain_aud_feat'] (HuBERT features) is required (addHubert=True)")
-        key = (audio_emb.data_ptr(), hub.data_ptr(), person_id.data_ptr(), tuple(audio_emb.shape))
+        # same storage AND same in-place version => same window (Tensor._version counts in-place writes, no device sync)
+        key = (audio_emb.data_ptr(), hub.data_ptr(), person_id.data_ptr(), tuple(audio_emb.shape),
+               audio_emb._version, hub._version, person_id._version)
         if getattr(self, "_window_key", None) != key:
             self.prepare_window(audio_emb, hub, person_id)
             self._window_key = key
