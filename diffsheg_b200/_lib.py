@@ -73,6 +73,8 @@ SIGNATURES = {
     "dsheg_undo_step": (ctypes.c_int, [_P, _P, _P, _I64, _F, _F, _P]),
     "dsheg_ddpm_step": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P]),
     "dsheg_repaint_merge": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _P]),
+    "dsheg_inv_standardize": (ctypes.c_int, [_P, _I32, _P, _P, _P, _I32, _I64, _I32, _P]),
+    "dsheg_beat_axis_angle_to_euler": (ctypes.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "dsheg_op_linear": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "dsheg_bench_gemm": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(ctypes.c_float)]),
     "dsheg_op_attention": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),

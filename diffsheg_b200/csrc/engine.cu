@@ -18,6 +18,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "postprocess.cuh"
 #include "sampler.cuh"
 
 using namespace dsheg;
@@ -785,6 +786,25 @@ int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, co
   if (!x || !gt || !mask || !noise || !x_out || n <= 0) { g_create_error = "dsheg_repaint_merge: bad arguments"; return 1; }
   repaint_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, gt, mask, noise, x_out, n, sqrt_ac, sqrt_one_minus_ac);
   return step_done("dsheg_repaint_merge");
+}
+
+// ---- output post-processing -----------------------------------------------------
+int dsheg_inv_standardize(const float* x, int32_t ldx, const float* mean, const float* stdv, float* out, int32_t ldo,
+                          int64_t rows, int32_t D, void* stream) {
+  if (!x || !mean || !stdv || !out || rows <= 0 || D <= 0 || ldx < D || ldo < D) { g_create_error = "dsheg_inv_standardize: bad arguments"; return 1; }
+  inv_standardize_kernel<<<ew_grid(rows * D), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean, stdv, out, ldo, rows, D);
+  return step_done("dsheg_inv_standardize");
+}
+
+int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mean_aa, const float* std_aa, const float* mean_pose,
+                                   const float* std_pose, float* euler_deg, float* out_norm, int64_t rows, int32_t C, void* stream) {
+  if (!x || !mean_aa || !std_aa || rows <= 0 || C <= 0 || C % 3 != 0 || ldx < C || (!euler_deg && !out_norm) ||
+      (out_norm && (!mean_pose || !std_pose))) {
+    g_create_error = "dsheg_beat_axis_angle_to_euler: bad arguments (C must be 3 * joints)"; return 1;
+  }
+  beat_axis_angle_kernel<<<ew_grid(rows * (C / 3)), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean_aa, std_aa, mean_pose, std_pose,
+                                                                                   euler_deg, out_norm, rows, C / 3);
+  return step_done("dsheg_beat_axis_angle_to_euler");
 }
 
 // ---- op-level test entry points --------------------------------------------------------------

@@ -113,6 +113,23 @@ int dsheg_ddpm_step(const float* x, const float* eps, const float* noise, float*
 int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, const float* noise,
                         float* x_out, int64_t n, float sqrt_ac, float sqrt_one_minus_ac, void* stream);
 
+/* ---- output post-processing on the resident sample -------------------------- */
+
+/* datasets/show.py:157-162 inv_standardize as trainers/ddpm_show_trainer.py:913-918 applies it to the sampled motion:
+ * out[r,c] = x[r,c] * std[c] + mean[c].  x / out are fp32 [rows, D] with row strides ldx / ldo (so the gesture /
+ * expression split of show:920-921 is a column window: pass x + split_pos, D = expression_dim, ldx = net_dim_pose). */
+int dsheg_inv_standardize(const float* x, int32_t ldx, const float* mean, const float* std, float* out, int32_t ldo,
+                          int64_t rows, int32_t D, void* stream);
+
+/* trainers/ddpm_beat_trainer.py:1056-1062 (--axis_angle): de-normalise the axis-angle gesture, convert every joint with
+ * datasets/rotation_converter.py:282-296 (axis-angle -> quaternion -> matrix -> XYZ Euler), radians -> degrees, and
+ * re-normalise with the Euler statistics.  x fp32 [rows, >= C] (row stride ldx), C = 3 * joints.
+ * euler_deg [rows, C] (what result2target_vis writes to BVH, beat:1076) and out_norm [rows, C] (the saved .npy,
+ * beat:1061) are dense; either may be NULL. */
+int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mean_aa, const float* std_aa,
+                                   const float* mean_pose, const float* std_pose, float* euler_deg, float* out_norm,
+                                   int64_t rows, int32_t C, void* stream);
+
 /* ---- op-level entry points used by the parity tests -------------------------------------- */
 
 /* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32 or the

@@ -1,0 +1,115 @@
+"""Output post-processing: oracle pinned to the reference's functions; CUDA path vs oracle / goldens.
+
+The GPU tests are new in this round's last hours and have NOT yet run on a B200 (GPU budget exhausted): they are skipped
+unless DSHEG_RUN_UNVALIDATED=1 so that an untested kernel cannot colour the suite either way.  Flip after the first run.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import postprocess as O
+
+REF_RC = "/root/reference/datasets/rotation_converter.py"
+unvalidated = pytest.mark.skipif(os.environ.get("DSHEG_RUN_UNVALIDATED") != "1",
+                                 reason="kernel written after the GPU budget ran out; set DSHEG_RUN_UNVALIDATED=1")
+
+# tolerance: Euler angles in degrees, fp32 trig on both sides; atan2/asin amplify rounding near gimbal lock (|M02| -> 1)
+TOL_DEG = 2e-3
+
+
+def test_oracle_axis_angle_branch_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "postprocess_beat.npz"))
+    euler, out = O.beat_axis_angle_branch(g["x"], g["mean_aa"], g["std_aa"], g["mean_pose"], g["std_pose"])
+    assert np.abs(euler - g["euler_deg"]).max() < TOL_DEG
+    assert np.abs(out - g["out_motions"]).max() < TOL_DEG
+    assert np.isfinite(euler).all()
+
+
+def test_oracle_inv_standardize_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "postprocess_show.npz"))
+    assert np.array_equal(O.inv_standardize(g["x"], g["mean"], g["std"]), g["inv"])   # bit-exact: one mul, one add
+
+
+@pytest.mark.skipif(not os.path.exists(REF_RC), reason="reference checkout not present")
+def test_oracle_euler_matches_live_reference_incl_small_angles():
+    spec = importlib.util.spec_from_file_location("ref_rotation_converter", REF_RC)
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    g = torch.Generator().manual_seed(3)
+    aa = torch.randn(5, 7, 47, 3, generator=g) * 1.5
+    aa[0, 0, 0] = 0.0                                  # exact zero rotation: small-angle branch (rc:219-229)
+    aa[0, 0, 1] = torch.tensor([3e-7, 0.0, -2e-7])
+    aa[0, 0, 2] = torch.tensor([0.0, np.pi, 0.0])       # half turn
+    ref = rc.axis_angle_to_euler_angles(aa).numpy()
+    got = O.axis_angle_to_euler_xyz(aa.numpy())
+    assert np.abs(ref - got).max() < 5e-5
+    # a rotation really is reproduced: Euler XYZ -> matrix (rc:147-172) equals axis-angle -> matrix
+    m1 = rc.euler_angles_to_matrix(torch.from_numpy(got), "XYZ")
+    m2 = rc.axis_angle_to_matrix(aa)
+    assert (m1 - m2).abs().max() < 1e-4
+
+
+def test_host_api_rejects_bad_arguments_without_a_gpu():
+    import diffsheg_b200.postprocess as P
+    with pytest.raises(ValueError):
+        P.inv_standardize(torch.zeros(2, 3, 4), np.zeros(4), np.ones(4))           # not a CUDA tensor
+    with pytest.raises(ValueError):
+        P.axis_angle_to_euler(torch.zeros(2, 3, 4), *[np.zeros(4)] * 4)
+
+
+# ---------------------------------------------------------------------------------------------- GPU (C ABI) ------
+@pytest.mark.gpu
+@unvalidated
+def test_gpu_inv_standardize_bit_exact_and_split(golden_dir):
+    import diffsheg_b200 as dz
+    g = np.load(os.path.join(golden_dir, "postprocess_show.npz"))
+    x = torch.from_numpy(g["x"]).cuda()
+    full = dz.inv_standardize(x, g["mean"], g["std"])
+    assert np.array_equal(full.cpu().numpy(), g["inv"])
+    sp = int(g["split_pos"])
+    opt = type("Opt", (), {"split_pos": sp})()
+    ges, exp = dz.finish_show(opt, x, g["mean"], g["std"])
+    assert np.array_equal(ges, g["inv"][..., :sp]) and np.array_equal(exp, g["inv"][..., sp:])
+
+
+@pytest.mark.gpu
+@unvalidated
+def test_gpu_axis_angle_branch_matches_reference_golden(golden_dir):
+    import diffsheg_b200 as dz
+    g = np.load(os.path.join(golden_dir, "postprocess_beat.npz"))
+    x = torch.from_numpy(g["x"]).cuda()
+    euler, out = dz.axis_angle_to_euler(x, g["mean_aa"], g["std_aa"], g["mean_pose"], g["std_pose"])
+    assert np.abs(euler.cpu().numpy() - g["euler_deg"]).max() < TOL_DEG
+    assert np.abs(out.cpu().numpy() - g["out_motions"]).max() < TOL_DEG
+    # embedded in a wider [B,T,192] sample (gesture first, expression after, beat:1050-1051)
+    wide = torch.cat([x, torch.randn(*x.shape[:2], 51, device="cuda")], -1)
+    opt = type("Opt", (), {"split_pos": 141, "axis_angle": True})()
+    res = dz.finish_beat(opt, wide, g["mean_aa"], g["std_aa"], g["mean_pose"], g["std_pose"])
+    assert np.abs(res["euler_deg"] - g["euler_deg"]).max() < TOL_DEG and np.array_equal(res["axis_angle"], g["x"])
+    assert np.array_equal(res["expression"], wide[..., 141:].cpu().numpy())
+
+
+@pytest.mark.gpu
+@unvalidated
+def test_gpu_axis_angle_full_size_round_trip():
+    """BASELINE-size property: Euler -> matrix equals axis-angle -> matrix (oracle-free), B=2500 x T=34 x 47 joints."""
+    import diffsheg_b200 as dz
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(2500, 34, 141, device="cuda", generator=g)
+    one, zero = np.ones(141, np.float32), np.zeros(141, np.float32)
+    euler, _ = dz.axis_angle_to_euler(x, zero, one, zero, one)
+    e = torch.deg2rad(euler).reshape(-1, 3).double()
+    cx, cy, cz, sx, sy, sz = *(torch.cos(e[:, i]) for i in range(3)), *(torch.sin(e[:, i]) for i in range(3))
+    # R = Rx Ry Rz (rc:147-172): first row and last column suffice to pin the three angles
+    m02, m00, m01, m12, m22 = sy, cy * cz, -cy * sz, -sx * cy, cx * cy
+    aa = x.reshape(-1, 3).double()
+    th = aa.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    k = aa / th
+    K = torch.zeros(aa.shape[0], 3, 3, device="cuda", dtype=torch.float64)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    R = torch.eye(3, device="cuda", dtype=torch.float64) + torch.sin(th)[..., None] * K + (1 - torch.cos(th))[..., None] * (K @ K)
+    for got, want in ((m02, R[:, 0, 2]), (m00, R[:, 0, 0]), (m01, R[:, 0, 1]), (m12, R[:, 1, 2]), (m22, R[:, 2, 2])):
+        assert (got - want).abs().max() < 2e-4   # fp32 trig, amplified near gimbal lock (oracle on CPU: 2e-5 over 1.2 M joints)
