@@ -14,6 +14,7 @@
 #include "../../include/diffsheg_b200.h"
 #include "attn_v2.cuh"
 #include "attn_v3.cuh"
+#include "attn_v4.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -65,7 +66,8 @@ struct dsheg_handle {
   std::unordered_map<std::string, DevTensor> tensors;
   bool finalized = false;
   int gemm_engine = 1;  // 1 = tcgen05 (bf16 mode default), 0 = SIMT
-  int attn_v2 = 1;      // bf16 mode: 1 = tensor-core attention (attn_v3), 2 = previous one-warp-per-head kernel
+  int attn_v2 = 1;      // bf16 mode: 1 = tensor-core attention (attn_v3), 4 = cluster-of-two variant (DSHEG_ATTN=v4, experimental),
+                        // 2 = previous one-warp-per-head kernel
                         // (DSHEG_ATTN=v2), 0 = generic SIMT kernel (DSHEG_ATTN=v1)
   int64_t launches = 0;
   // resolved weights
@@ -327,6 +329,8 @@ struct Runner {
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
     if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 1) {
       av3::attn_v3_kernel<<<n_samples, av3::NTHREADS, av3::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
+    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 4) {
+      av4::attn_v4_kernel<<<2 * n_samples, av4::NTHREADS, av4::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av2::D && H == av2::NH && T <= av2::TP && h->attn_v2 == 2) {
       av2::attn_v2_kernel<<<n_samples, 256, av2::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 64) {
@@ -541,6 +545,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   const char* att = getenv("DSHEG_ATTN");
   if (att && !strcmp(att, "v1")) h->attn_v2 = 0;
   if (att && !strcmp(att, "v2")) h->attn_v2 = 2;
+  if (att && !strcmp(att, "v4")) h->attn_v2 = 4;   // cluster-of-two half-sample CTAs (attn_v4.cuh; experimental)
   const char* gr = getenv("DSHEG_GRAPHS");
   if (gr && !strcmp(gr, "0")) h->use_graphs = 0;
   const char* fs = getenv("DSHEG_FUSE_STATS");
@@ -591,6 +596,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   cudaFuncSetAttribute(attn_kernel<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
   cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
+  cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
   cudaFuncSetAttribute(hubconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
   cudaFuncSetAttribute(hubconv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
   e = cudaGetLastError();
@@ -953,6 +959,10 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
     cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
     av2::attn_v2_kernel<<<Bn, 256, av2::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b, scale_shift,
                                                                             2 * av2::D);
+  } else if (att && !strcmp(att, "v4")) {
+    cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
+    av4::attn_v4_kernel<<<2 * Bn, av4::NTHREADS, av4::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
+                                                                                          scale_shift, 2 * av4::D);
   } else {
     cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
     av3::attn_v3_kernel<<<Bn, av3::NTHREADS, av3::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
