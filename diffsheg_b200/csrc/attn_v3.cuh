@@ -17,7 +17,7 @@
 // (v2 of this kernel -- one warp per head, A^T in registers, profiles/r01 -- was latency bound: IPC 0.35 with
 //  two warps per scheduler and 19 % of the HBM roofline.)
 #pragma once
-#include "common.cuh"
+#include "simt_prims.cuh"
 
 namespace dsheg {
 namespace av3 {
@@ -29,25 +29,9 @@ constexpr int TILE_BYTES = TP * HD * 2;  // 12288
 constexpr int RED_FLOATS = NH * 2 * HD;  // per-(head, half) column partials
 constexpr int SMEM_BYTES = NH * 2 * TILE_BYTES + 2 * RED_FLOATS * 4;
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void pair_sync(int head) { asm volatile("bar.sync %0, 64;" ::"r"(head + 1) : "memory"); }
+using prims::smem_addr; using prims::cp_async16; using prims::cp_async_wait_all; using prims::ldsm_x4; using prims::ldsm_x4_trans;
+using prims::mma_bf16; using prims::ex2f; using prims::tanh_approx;
+__device__ __forceinline__ void pair_sync(int head) { prims::named_bar_sync<64>(head + 1); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -56,7 +40,6 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
   const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w);
   return make_float2(__bfloat162float(v.x), __bfloat162float(v.y));
 }
-__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // byte offset of 16-B chunk `c` (0..7) of row `r` inside a swizzled [rows][64] bf16 tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -77,7 +60,7 @@ __device__ __forceinline__ void load_q_tile(const bf16* qhead, int row0, int T, 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
                const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
-  extern __shared__ __align__(128) uint8_t sm[];
+  DSHEG_DYN_SMEM(sm, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = warp >> 1, half = warp & 1;
   const int g = lane >> 2, q = lane & 3;
@@ -301,9 +284,7 @@ attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
         const float h0 = fmaf(fmaf(v[2 * e], rstd, nmr), G[2 * e], Bc[2 * e]);
         const float h1 = fmaf(fmaf(v[2 * e + 1], rstd, nmr), G[2 * e + 1], Bc[2 * e + 1]);
-        float t0, t1;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        const float t0 = tanh_approx(h0), t1 = tanh_approx(h1);
         o[e] = pack2(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
       }
       uint4* dst = reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0);

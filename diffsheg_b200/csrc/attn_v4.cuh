@@ -27,20 +27,12 @@ constexpr int RED_FLOATS = NH_CTA * 2 * HD;
 constexpr int STAT_FLOATS = 2 * TP;       // (sum, sumsq) per row
 constexpr int SMEM_BYTES = NH_CTA * 2 * TILE_BYTES + 2 * RED_FLOATS * 4 + 2 * STAT_FLOATS * 4;   // 98304 + 4096 + 1536
 
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer, float a, float b) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer));
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
-}
+using prims::cluster_rank; using prims::cluster_barrier; using prims::st_peer_f32x2; using av3::tanh_approx;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
 attn_v4_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
                const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
-  extern __shared__ __align__(128) uint8_t sm[];
+  DSHEG_DYN_SMEM(sm, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hl = warp >> 1, half = warp & 1;           // local head, warp of the pair
   const int g = lane >> 2, q = lane & 3;
@@ -273,9 +265,7 @@ attn_v4_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         const float2 p2 = unpack2(w[e]);
         const float h0 = fmaf(fmaf(p2.x, rstd, nmr), G[2 * e], Bc[2 * e]);
         const float h1 = fmaf(fmaf(p2.y, rstd, nmr), G[2 * e + 1], Bc[2 * e + 1]);
-        float t0, t1;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        const float t0 = tanh_approx(h0), t1 = tanh_approx(h1);
         o[e] = pack2(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
       }
       *reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0) = make_uint4(o[0], o[1], o[2], o[3]);

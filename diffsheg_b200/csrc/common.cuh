@@ -1,7 +1,11 @@
 // Shared device/host helpers for the diffsheg_b200 kernels (sm_100a only).
 #pragma once
+#ifdef DSHEG_EMU
+#include "emu_cuda.h"   // tests/emu: host emulation of the CUDA subset the SIMT kernels use (test infrastructure only)
+#else
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include <string>

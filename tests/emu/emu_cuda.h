@@ -1,0 +1,267 @@
+// TEST INFRASTRUCTURE ONLY -- host emulation of the small slice of CUDA the SIMT kernels use.
+//
+// Compiling a kernel source with g++ -DDSHEG_EMU includes this header instead of <cuda_runtime.h> / <cuda_bf16.h>.
+// Every CUDA thread of a thread-block cluster becomes a fiber (ucontext) inside ONE OS thread; fibers run until they
+// reach a synchronising operation (warp collective, named barrier, __syncthreads, cluster barrier), where they
+// rendezvous.  Scheduling is deterministic round-robin, a pass without progress is reported as a deadlock.
+// What this checks: indexing, swizzles, mma / ldmatrix fragment maps, barrier protocols, DSMEM addressing, arithmetic
+// (fp32 with bf16 roundings where the kernel rounds).  What it cannot check: memory-model / async-proxy ordering, bank
+// conflicts, performance.  Nothing here is linked into libdiffsheg_b200.so.
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __cluster_dims__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __grid_constant__
+
+// ---- vector types ---------------------------------------------------------------------------------------------------
+struct float2 { float x, y; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct __attribute__((aligned(16))) uint4 { uint32_t x, y, z, w; };
+struct uint3 { uint32_t x, y, z; };
+static inline float2 make_float2(float x, float y) { return {x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return {x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return {x, y, z, w}; }
+
+// ---- bf16 (round-to-nearest-even; x is the low half of a bf16x2 word like on the device) ----------------------------------
+struct __nv_bfloat16 { uint16_t bits; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  __nv_bfloat16 h;
+  if ((u & 0x7fffffffu) > 0x7f800000u) { h.bits = 0x7fff; return h; }   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  h.bits = (uint16_t)(u >> 16);
+  return h;
+}
+static inline float __bfloat162float(__nv_bfloat16 h) {
+  const uint32_t u = (uint32_t)h.bits << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline __nv_bfloat162 __floats2bfloat162_rn(float lo, float hi) { return {__float2bfloat16_rn(lo), __float2bfloat16_rn(hi)}; }
+static inline __nv_bfloat16 emu_hmax(__nv_bfloat16 a, __nv_bfloat16 b) {
+  const float fa = __bfloat162float(a), fb = __bfloat162float(b);
+  if (fa != fa) return b;
+  if (fb != fb) return a;
+  return fa > fb ? a : b;
+}
+static inline __nv_bfloat162 __hmax2(__nv_bfloat162 a, __nv_bfloat162 b) { return {emu_hmax(a.x, b.x), emu_hmax(a.y, b.y)}; }
+
+// ---- math ------------------------------------------------------------------------------------------------------------------
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+#define __expf(x) expf(x)   // glibc declares a __expf of its own
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+
+// ---- fibers, CTAs, clusters -----------------------------------------------------------------------------------------------
+namespace emu {
+
+struct Rendezvous {
+  int expected = 0, arrived = 0;
+  uint64_t gen = 0;
+};
+struct Warp {
+  Rendezvous rv;
+  alignas(16) uint8_t slot[2][32][64];   // double-buffered per-lane exchange area of the warp collectives
+};
+struct Cluster;
+struct Cta {
+  std::vector<uint8_t> smem_store;
+  uint8_t* smem = nullptr;   // 1024-aligned
+  size_t smem_bytes = 0;
+  int nthreads = 0;
+  uint3 bid{0, 0, 0};
+  uint32_t rank = 0;
+  Cluster* cluster = nullptr;
+  Rendezvous named[16];
+  std::vector<Warp> warps;
+};
+struct Cluster {
+  std::vector<Cta> ctas;
+  Rendezvous rv;          // barrier.cluster (arrive + wait as one rendezvous, or split: see cluster_arrive / cluster_wait)
+  uint64_t arrive_gen_seen = 0;
+};
+struct Thread {
+  ucontext_t ctx;
+  std::vector<uint8_t> stack;
+  Cta* cta = nullptr;
+  uint3 tid{0, 0, 0};
+  int lane = 0, warp = 0;
+  int parity = 0;          // exchange-slot parity of the next warp collective
+  uint64_t cluster_wait_gen = 0;
+  bool done = false;
+  const char* waiting_on = "";
+};
+struct Launch {
+  uint3 grid{1, 1, 1}, block{1, 1, 1};
+  uint32_t cluster_size = 1;
+};
+
+struct Runtime {
+  ucontext_t sched;
+  Thread* cur = nullptr;
+  Launch launch;
+  uint64_t progress = 0;
+  std::string error;
+  std::function<void()> body;
+};
+inline Runtime& rt() { static Runtime r; return r; }
+inline Thread& self() { return *rt().cur; }
+inline void yield() { Thread* t = rt().cur; swapcontext(&t->ctx, &rt().sched); }
+
+inline void rendezvous(Rendezvous& r, int expected, const char* what) {
+  if (r.arrived == 0) r.expected = expected;
+  else if (r.expected != expected) { rt().error = std::string("mismatched participant count at ") + what; }
+  const uint64_t g = r.gen;
+  if (++r.arrived == r.expected) {
+    r.arrived = 0;
+    ++r.gen;
+    ++rt().progress;
+  } else {
+    self().waiting_on = what;
+    while (r.gen == g) yield();
+    self().waiting_on = "";
+  }
+}
+
+// exchange `bytes` (<= 64) per lane among the 32 lanes of the calling warp; returns the warp's slot array of this collective
+inline uint8_t (*warp_exchange(const void* mine, int bytes, const char* what))[64] {
+  Thread& t = self();
+  Warp& w = t.cta->warps[t.warp];
+  const int p = t.parity;
+  t.parity ^= 1;
+  memcpy(w.slot[p][t.lane], mine, bytes);
+  rendezvous(w.rv, 32, what);
+  return w.slot[p];
+}
+
+inline void trampoline() {
+  rt().body();
+  self().done = true;
+  ++rt().progress;
+  yield();
+}
+
+// Run `body` (a call of the kernel with its arguments) for every thread of a grid; clusters execute one after another.
+inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, size_t smem_bytes, std::function<void()> body,
+                     std::string* err) {
+  Runtime& R = rt();
+  R.body = body;
+  R.error.clear();
+  R.launch.grid = {grid_x, 1, 1};
+  R.launch.block = {block_x, 1, 1};
+  R.launch.cluster_size = cluster_size;
+  if (grid_x % cluster_size || block_x % 32) { *err = "grid / block not a multiple of the cluster size / warp size"; return false; }
+  const size_t nthr = (size_t)cluster_size * block_x;
+  std::vector<std::unique_ptr<Thread>> threads(nthr);
+  for (auto& t : threads) { t.reset(new Thread); t->stack.resize(192 * 1024); }
+  for (uint32_t c0 = 0; c0 < grid_x; c0 += cluster_size) {
+    Cluster cl;
+    cl.ctas.resize(cluster_size);
+    for (uint32_t r = 0; r < cluster_size; ++r) {
+      Cta& c = cl.ctas[r];
+      c.smem_store.assign(smem_bytes + 2048, 0xCD);   // poison: reads of never-written smem show up as garbage
+      c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(c.smem_store.data()) + 1023) & ~(uintptr_t)1023);
+      c.smem_bytes = smem_bytes;
+      c.nthreads = (int)block_x;
+      c.bid = {c0 + r, 0, 0};
+      c.rank = r;
+      c.cluster = &cl;
+      c.warps.resize(block_x / 32);
+      for (uint32_t i = 0; i < block_x; ++i) {
+        Thread& t = *threads[(size_t)r * block_x + i];
+        t.cta = &c;
+        t.tid = {i, 0, 0};
+        t.lane = (int)(i & 31);
+        t.warp = (int)(i >> 5);
+        t.parity = 0;
+        t.cluster_wait_gen = 0;
+        t.done = false;
+        getcontext(&t.ctx);
+        t.ctx.uc_stack.ss_sp = t.stack.data();
+        t.ctx.uc_stack.ss_size = t.stack.size();
+        t.ctx.uc_link = &R.sched;
+        makecontext(&t.ctx, (void (*)())trampoline, 0);
+      }
+    }
+    size_t remaining = nthr;
+    while (remaining) {
+      const uint64_t before = R.progress;
+      remaining = 0;
+      for (auto& tp : threads) {
+        if (tp->done) continue;
+        R.cur = tp.get();
+        swapcontext(&R.sched, &tp->ctx);
+        if (!tp->done) ++remaining;
+      }
+      if (!R.error.empty()) { *err = R.error; return false; }
+      if (remaining && R.progress == before) {
+        std::string msg = "deadlock: ";
+        int shown = 0;
+        for (auto& tp : threads)
+          if (!tp->done && shown++ < 6)
+            msg += "[cta " + std::to_string(tp->cta->bid.x) + " thread " + std::to_string(tp->tid.x) + " waits on " + tp->waiting_on + "] ";
+        *err = msg;
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::self().tid)
+#define blockIdx (emu::self().cta->bid)
+#define blockDim (emu::rt().launch.block)
+#define gridDim (emu::rt().launch.grid)
+
+static inline void __syncthreads() { emu::rendezvous(emu::self().cta->named[0], emu::self().cta->nthreads, "__syncthreads"); }
+static inline void __syncwarp(uint32_t = 0xffffffffu) {
+  emu::Thread& t = emu::self();
+  emu::rendezvous(t.cta->warps[t.warp].rv, 32, "__syncwarp");
+}
+template <class T> static inline T __shfl_xor_sync(uint32_t, T v, int lane_mask) {
+  static_assert(sizeof(T) <= 8, "shuffle of a 32/64-bit value");
+  const int lane = emu::self().lane;
+  uint8_t(*slots)[64] = emu::warp_exchange(&v, sizeof(T), "__shfl_xor_sync");
+  T r;
+  memcpy(&r, slots[(lane ^ lane_mask) & 31], sizeof(T));
+  return r;
+}
+template <class T> static inline T __shfl_sync(uint32_t, T v, int src_lane) {
+  uint8_t(*slots)[64] = emu::warp_exchange(&v, sizeof(T), "__shfl_sync");
+  T r;
+  memcpy(&r, slots[src_lane & 31], sizeof(T));
+  return r;
+}
+static inline size_t __cvta_generic_to_shared(const void* p) {
+  emu::Cta* c = emu::self().cta;
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  if (b < c->smem || b >= c->smem + c->smem_bytes) { emu::rt().error = "__cvta_generic_to_shared: pointer outside this CTA's shared memory"; return 0; }
+  return (size_t)(b - c->smem);
+}

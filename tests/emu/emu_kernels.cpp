@@ -1,0 +1,27 @@
+// TEST INFRASTRUCTURE ONLY -- the attention kernel SOURCES of diffsheg_b200/csrc compiled for the host emulator
+// (g++ -DDSHEG_EMU) behind a small C ABI for tests/test_emu_kernels.py.  Pointers are host pointers; bf16 travels as uint16.
+#include "attn_v3.cuh"
+#include "attn_v4.cuh"
+
+using namespace dsheg;
+
+static std::string g_err;
+
+extern "C" const char* emu_last_error() { return g_err.c_str(); }
+
+// variant: 3 = attn_v3 (one CTA per sample), 4 = attn_v4 (cluster of two half-sample CTAs)
+extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int n_samples, int T, int ssB, const float* ln_g,
+                             const float* ln_b, const float* ss, int ss_ld) {
+  g_err.clear();
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  bf16* zo = reinterpret_cast<bf16*>(z);
+  bool ok = false;
+  if (variant == 3) {
+    ok = emu::run_grid(n_samples, av3::NTHREADS, 1, av3::SMEM_BYTES, [=] { av3::attn_v3_kernel(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
+  } else if (variant == 4) {
+    ok = emu::run_grid(2 * n_samples, av4::NTHREADS, 2, av4::SMEM_BYTES, [=] { av4::attn_v4_kernel(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
+  } else {
+    g_err = "unknown attention variant";
+  }
+  return ok ? 0 : 1;
+}
