@@ -1,0 +1,456 @@
+// Linear-attention core + StylizationBlock prologue, bf16 (D = 512, 8 heads of 64, T <= 96) -- fifth generation.
+// Opt-in (DSHEG_ATTN=v5c1 | v5c2 | v5c4) until its first hardware run; validated thread for thread on the CPU emulator
+// (tests/test_emu_kernels.py).  Same mathematics as attn_v3.cuh (reference transformer.py:112-130 + :86-97):
+//   K' = softmax_t(K)   Q' = softmax_d(Q)   A = K'^T V  [64x64]   Y = Q' A   z = SiLU(LN_512(Y) * (1 + scale) + shift)
+//
+// Why: ncu on v3 (profiles/r01/final_attn_ncu_summary.json) shows DRAM traffic = algorithmic bytes but only 43 % issue-slot
+// utilisation at 66.7k warp-instructions per sample and ONE 205 KB CTA per SM, whose phases serialise (fill, softmax, MMA,
+// LayerNorm store).  v5 attacks both terms:
+//   (1) decomposition: template parameter CL = CTAs per sample (a thread-block cluster).  CL = 1: one CTA, 8 heads (v3's
+//       shape).  CL = 2 / 4: 4 / 2 heads per CTA, 104 / 52 KB, so 2 / 4 CTAs of DIFFERENT samples and phases share an SM and
+//       one's fill overlaps another's math.  The only cross-head quantity -- the LayerNorm (sum, sum of squares) of a row --
+//       is exchanged through distributed shared memory (st.shared::cluster into every peer's table, one cluster barrier) and
+//       summed in rank order, so all CTAs of a sample use bit-identical statistics.
+//   (2) instruction diet (SASS of v3: 8 instructions per K element, 430 per Q m-tile, 400 for the A^T rescale):
+//       * column softmax of K: a lane owns one ROW PHASE (r mod 8) and a 16-column quarter, so the swizzle term is a per-lane
+//         constant, rows advance by an immediate (+1024 B) and all smem traffic is 128-bit (v3: 32-bit + per-row XOR math);
+//       * the softmax denominators come out of the tensor core: column sums of K' = ones[16 x t] . K' and row sums of
+//         Q' = Q' . ones -- a handful of extra HMMAs replace one FADD per element, the shuffle trees and the smem partials,
+//         and they sum exactly the bf16-rounded weights the products use;
+//       * reciprocals are MUFU.RCP (rcp.approx) instead of IEEE divisions with their slow-path branches;
+//       * bf16 -> fp32 unpacking is one ALU instruction per element (shift / mask) instead of PRMT + shift;
+//       * Q m-tiles that lie completely inside the sample are loaded without per-row predicates;
+//       * K and V arrive as two cp.async groups: the column softmax starts as soon as K has landed.
+//       * CL > 1: the LayerNorm pass keeps its packed Y rows in registers across the cluster barrier (one smem read).
+// HBM traffic is unchanged: read q,k,v + write z = 4 * T * 512 * 2 bytes per sample.
+#pragma once
+#include "attn_v3.cuh"
+
+namespace dsheg {
+namespace av5 {
+
+using av3::TP; using av3::HD; using av3::D; using av3::TILE_BYTES;
+using av3::pack2; using av3::swz; using av3::pair_sync;
+using prims::smem_addr; using prims::cp_async16; using prims::cp_async_commit; using prims::cp_async_wait_group;
+using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::ex2f; using prims::tanh_approx; using prims::rcp_approx;
+
+template <int CL> struct Cfg {
+  static_assert(CL == 1 || CL == 2 || CL == 4, "1, 2 or 4 CTAs per sample");
+  static constexpr int NH_CTA = 8 / CL;            // heads per CTA
+  static constexpr int NWARPS = 2 * NH_CTA;        // two warps per head
+  static constexpr int NTHREADS = 32 * NWARPS;
+  static constexpr int COLS = D / CL;              // LayerNorm columns owned by this CTA
+  static constexpr int LPR = COLS / 16;            // lanes per row in the LayerNorm pass (16 columns per lane)
+  static constexpr int RPI = 32 / LPR;             // rows per warp iteration
+  static constexpr int LN_ITERS = TP / (NWARPS * RPI);   // = 6 for every CL
+  static constexpr int MAX_BYTES = NH_CTA * 2 * 32 * 4;  // [head][half][32] packed bf16x2 column maxima
+  static constexpr int SUM_BYTES = NH_CTA * HD * 4;      // [head][64] column sums of K'
+  static constexpr int STAT_BYTES = CL > 1 ? CL * TP * 8 : 0;   // [source rank][row] (sum, sum of squares)
+  static constexpr int SMEM_BYTES = NH_CTA * 2 * TILE_BYTES + MAX_BYTES + SUM_BYTES + STAT_BYTES;
+  static constexpr int CTAS_PER_SM = 512 / NTHREADS;
+};
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+constexpr uint32_t BF2_NEG_INF = 0xFF80FF80u;   // (-inf, -inf)
+constexpr uint32_t BF2_ONES = 0x3F803F80u;      // (1.0, 1.0)
+constexpr float L2E = 1.4426950408889634f;
+
+// Q fragments of one 16-row m-tile straight from global memory; FULL tiles need no row predicates
+template <bool FULL>
+__device__ __forceinline__ void load_q_tile(const bf16* qhead, int row0, int T, int g, int q, uint32_t (&qa)[4][4]) {
+  const int r0 = row0 + g, r1 = row0 + g + 8;
+  const uint32_t* p0 = reinterpret_cast<const uint32_t*>(qhead + (size_t)r0 * (3 * D));
+  const uint32_t* p1 = reinterpret_cast<const uint32_t*>(qhead + (size_t)r1 * (3 * D));
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    qa[ks][0] = (FULL || r0 < T) ? __ldg(p0 + ks * 8 + q) : 0u;
+    qa[ks][1] = (FULL || r1 < T) ? __ldg(p1 + ks * 8 + q) : 0u;
+    qa[ks][2] = (FULL || r0 < T) ? __ldg(p0 + ks * 8 + 4 + q) : 0u;
+    qa[ks][3] = (FULL || r1 < T) ? __ldg(p1 + ks * 8 + 4 + q) : 0u;
+  }
+}
+__device__ __forceinline__ void load_q(const bf16* qhead, int row0, int T, int g, int q, uint32_t (&qa)[4][4]) {
+  if (row0 + 16 <= T) load_q_tile<true>(qhead, row0, T, g, q, qa);   // warp-uniform
+  else load_q_tile<false>(qhead, row0, T, g, q, qa);
+}
+
+template <int CL>
+__global__ void __launch_bounds__(Cfg<CL>::NTHREADS, Cfg<CL>::CTAS_PER_SM)
+attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
+               const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+  using C = Cfg<CL>;
+  DSHEG_DYN_SMEM(sm, 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hl = warp >> 1, half = warp & 1;           // local head, warp of the pair
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t rank = CL > 1 ? prims::cluster_rank() : 0u;
+  if (CL > 1) prims::cluster_arrive_relaxed();         // "this CTA runs": matched by the cluster_wait before the first remote store
+  const int smp = blockIdx.x / CL;
+  const int head = (int)rank * C::NH_CTA + hl;         // global head
+  const size_t row0 = (size_t)smp * T;
+  uint8_t* Ks = sm + hl * 2 * TILE_BYTES;
+  uint8_t* Vs = Ks + TILE_BYTES;
+  uint32_t* colmax = reinterpret_cast<uint32_t*>(sm + C::NH_CTA * 2 * TILE_BYTES);               // [NH_CTA][2][32]
+  float* colsum = reinterpret_cast<float*>(sm + C::NH_CTA * 2 * TILE_BYTES + C::MAX_BYTES);     // [NH_CTA][64]
+  float2* stat = reinterpret_cast<float2*>(sm + C::NH_CTA * 2 * TILE_BYTES + C::MAX_BYTES + C::SUM_BYTES);   // [CL][TP]
+  const uint32_t ks_addr = smem_addr(Ks), vs_addr = smem_addr(Vs);
+  const bf16* qhead = qkv + row0 * (3 * D) + head * HD;
+  const int n_mt = (T + 15) >> 4;  // 16-row tiles that contain valid frames
+  const int Tpad = n_mt * 16;
+
+  // ---- 1. K, then V head tiles -> smem (two cp.async groups).  The pair splits the rows by parity: lane -> row
+  //         2 (lane >> 3) + half + 8 j, 16-byte chunk lane & 7, so (row & 7) -- the swizzle -- is a per-lane constant and both
+  //         the shared and the global address advance by compile-time immediates.
+  {
+    const int rl = 2 * (lane >> 3) + half, c = lane & 7;
+    const uint32_t so = swz(rl, c);
+    const bf16* gp = qhead + (size_t)rl * (3 * D) + c * 8;
+#pragma unroll
+    for (int j = 0; j < TP / 8; ++j)
+      if (rl + 8 * j < T) cp_async16(ks_addr + so + j * 1024, gp + (size_t)j * (8 * 3 * D) + D);
+    cp_async_commit();
+#pragma unroll
+    for (int j = 0; j < TP / 8; ++j)
+      if (rl + 8 * j < T) cp_async16(vs_addr + so + j * 1024, gp + (size_t)j * (8 * 3 * D) + 2 * D);
+    cp_async_commit();
+  }
+  if (half == 0) {
+    for (int i = lane; i < (Tpad - T) * 8; i += 32) {
+      const int r = T + (i >> 3), c = i & 7;
+      *reinterpret_cast<uint4*>(Vs + swz(r, c)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // ---- 2. this warp's first Q m-tile (global -> registers) overlaps the cp.async latency
+  uint32_t qa[4][4];
+  if (half < n_mt) load_q(qhead, half * 16, T, g, q, qa);
+  cp_async_wait_group<1>();   // this thread's K chunks have landed
+  pair_sync(hl);              // ... and the partner's
+
+  // ---- 3. softmax over time per K column.  Lane = (row phase p, column quarter cq): rows r_lo + p + 8 i, columns
+  //         16 cq .. 16 cq + 15 (two 16-byte chunks); (r & 7) is constant per lane, so is the swizzle.
+  {
+    const int p = lane & 7, cq = lane >> 3;
+    const int rsplit = (T + 1) >> 1;
+    const int r_lo = half ? rsplit : 0, r_hi = half ? T : rsplit;
+    const int rfirst = r_lo + p;
+    const int ph = rfirst & 7;
+    uint8_t* base = Ks + rfirst * 128;
+    const int o0 = ((2 * cq) ^ ph) << 4, o1 = ((2 * cq + 1) ^ ph) << 4;
+    constexpr int NIT = TP / 2 / 8;   // a half has at most 48 rows -> 6 rows per lane
+    // pass 1: column maxima in packed bf16x2 (exact for a max)
+    uint32_t mx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx[j] = BF2_NEG_INF;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      if (rfirst + 8 * i < r_hi) {
+        const uint4 a = *reinterpret_cast<const uint4*>(base + i * 1024 + o0);
+        const uint4 b = *reinterpret_cast<const uint4*>(base + i * 1024 + o1);
+        mx[0] = hmax2_u32(mx[0], a.x); mx[1] = hmax2_u32(mx[1], a.y); mx[2] = hmax2_u32(mx[2], a.z); mx[3] = hmax2_u32(mx[3], a.w);
+        mx[4] = hmax2_u32(mx[4], b.x); mx[5] = hmax2_u32(mx[5], b.y); mx[6] = hmax2_u32(mx[6], b.z); mx[7] = hmax2_u32(mx[7], b.w);
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {   // across the 8 row phases (lane bits 0..2)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx[j] = hmax2_u32(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], m));
+    }
+    uint32_t* mymax = colmax + (hl * 2 + half) * 32 + cq * 8;
+    const uint32_t* otmax = colmax + (hl * 2 + (half ^ 1)) * 32 + cq * 8;
+    if (p == 0) {
+      *reinterpret_cast<uint4*>(mymax) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+      *reinterpret_cast<uint4*>(mymax + 4) = make_uint4(mx[4], mx[5], mx[6], mx[7]);
+    }
+    pair_sync(hl);
+    {
+      const uint4 a = *reinterpret_cast<const uint4*>(otmax), b = *reinterpret_cast<const uint4*>(otmax + 4);
+      mx[0] = hmax2_u32(mx[0], a.x); mx[1] = hmax2_u32(mx[1], a.y); mx[2] = hmax2_u32(mx[2], a.z); mx[3] = hmax2_u32(mx[3], a.w);
+      mx[4] = hmax2_u32(mx[4], b.x); mx[5] = hmax2_u32(mx[5], b.y); mx[6] = hmax2_u32(mx[6], b.z); mx[7] = hmax2_u32(mx[7], b.w);
+    }
+    // pass 2: e = 2^(x*log2e - m*log2e), one FFMA + one MUFU.EX2 per element, bf16 for the tensor core, in place
+    float nm[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { nm[2 * j] = -bf_lo(mx[j]) * L2E; nm[2 * j + 1] = -bf_hi(mx[j]) * L2E; }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      if (rfirst + 8 * i < r_hi) {
+        uint4* pa = reinterpret_cast<uint4*>(base + i * 1024 + o0);
+        uint4* pb = reinterpret_cast<uint4*>(base + i * 1024 + o1);
+        const uint4 a = *pa, b = *pb;
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          e[j] = pack2(ex2f(fmaf(bf_lo(w[j]), L2E, nm[2 * j])), ex2f(fmaf(bf_hi(w[j]), L2E, nm[2 * j + 1])));
+        *pa = make_uint4(e[0], e[1], e[2], e[3]);
+        *pb = make_uint4(e[4], e[5], e[6], e[7]);
+      }
+    }
+    if (half == 1) {
+      for (int i = lane; i < (Tpad - T) * 8; i += 32) {
+        const int r = T + (i >> 3), cc = i & 7;
+        *reinterpret_cast<uint4*>(Ks + swz(r, cc)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    cp_async_wait_group<0>();   // this thread's V chunks
+    pair_sync(hl);              // K' (numerators) and V complete in smem
+  }
+
+  // ---- 3b. column sums of K' on the tensor core: ones[16 x 16] . K'[16 x 8] per k-step; this warp covers d = 32*half .. +31
+  {
+    const int mat = lane >> 3, rr = lane & 7;
+    const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
+    float cs[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { cs[nt][0] = cs[nt][1] = cs[nt][2] = cs[nt][3] = 0.f; }
+    for (int kt = 0; kt < n_mt; ++kt) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int r = kt * 16 + rr + ((mat & 1) << 3), c = 2 * (2 * half + np) + (mat >> 1);
+        ldsm_x4_trans(ks_addr + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(cs[2 * np], ones, b0, b1);
+        mma_bf16(cs[2 * np + 1], ones, b2, b3);
+      }
+    }
+    if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<float2*>(colsum + hl * HD + 32 * half + 8 * nt + 2 * q) = make_float2(cs[nt][0], cs[nt][1]);
+    }
+  }
+
+  // ---- 4. A^T[l][d] = sum_t V[t][l] K'[t][d] for this warp's l-half (two 16-row m-tiles)
+  float acc[2][8][4];
+  {
+    const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
+    for (int kt = 0; kt < n_mt; ++kt) {  // 16 frames per k-step
+      uint32_t a0[4], a1[4];
+      {
+        const int r = kt * 16 + rr + ((mat >> 1) << 3);
+        ldsm_x4_trans(vs_addr + swz(r, 4 * half + (mat & 1)), a0[0], a0[1], a0[2], a0[3]);
+        ldsm_x4_trans(vs_addr + swz(r, 4 * half + 2 + (mat & 1)), a1[0], a1[1], a1[2], a1[3]);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // two d n-tiles per ldmatrix.x4
+        uint32_t b0, b1, b2, b3;
+        const int r = kt * 16 + rr + ((mat & 1) << 3), c = 2 * np + (mat >> 1);
+        ldsm_x4_trans(ks_addr + swz(r, c), b0, b1, b2, b3);
+        mma_bf16(acc[0][2 * np], a0, b0, b1);
+        mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
+        mma_bf16(acc[1][2 * np], a1, b0, b1);
+        mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
+      }
+    }
+  }
+  pair_sync(hl);  // both warps are done reading K' and V (and have published their column sums): K's tile receives A^T, V's tile Y
+  {
+    const float* csum = colsum + hl * HD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 s2 = *reinterpret_cast<const float2*>(csum + 8 * nt + 2 * q);
+      const float i0 = rcp_approx(s2.x), i1 = rcp_approx(s2.y);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int l = 32 * half + 16 * mi + g;
+        *reinterpret_cast<uint32_t*>(Ks + swz(l, nt) + q * 4) = pack2(acc[mi][nt][0] * i0, acc[mi][nt][1] * i1);
+        *reinterpret_cast<uint32_t*>(Ks + swz(l + 8, nt) + q * 4) = pack2(acc[mi][nt][2] * i0, acc[mi][nt][3] * i1);
+      }
+    }
+  }
+  pair_sync(hl);  // A^T[l][d] (bf16, 64 x 64) complete
+
+  // ---- 5. Y[t][l] = softmax_d(Q)[t][:] . A for this warp's m-tiles (mt = half, half+2, ...); bf16 Y -> V tile
+  {
+    const int mat = lane >> 3, rr = lane & 7;
+    for (int mt = half; mt < n_mt; mt += 2) {
+      // row max in packed bf16x2: registers [ks][0],[ks][2] belong to row g, [ks][1],[ks][3] to row g + 8
+      uint32_t ma = BF2_NEG_INF, mb = BF2_NEG_INF;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        ma = hmax2_u32(ma, hmax2_u32(qa[ks][0], qa[ks][2]));
+        mb = hmax2_u32(mb, hmax2_u32(qa[ks][1], qa[ks][3]));
+      }
+      float mx0 = fmaxf(bf_lo(ma), bf_hi(ma)), mx1 = fmaxf(bf_lo(mb), bf_hi(mb));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float n0 = -mx0 * L2E, n1 = -mx1 * L2E;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        pa[ks][0] = pack2(ex2f(fmaf(bf_lo(qa[ks][0]), L2E, n0)), ex2f(fmaf(bf_hi(qa[ks][0]), L2E, n0)));
+        pa[ks][1] = pack2(ex2f(fmaf(bf_lo(qa[ks][1]), L2E, n1)), ex2f(fmaf(bf_hi(qa[ks][1]), L2E, n1)));
+        pa[ks][2] = pack2(ex2f(fmaf(bf_lo(qa[ks][2]), L2E, n0)), ex2f(fmaf(bf_hi(qa[ks][2]), L2E, n0)));
+        pa[ks][3] = pack2(ex2f(fmaf(bf_lo(qa[ks][3]), L2E, n1)), ex2f(fmaf(bf_hi(qa[ks][3]), L2E, n1)));
+      }
+      if (mt + 2 < n_mt) load_q(qhead, (mt + 2) * 16, T, g, q, qa);  // prefetch under the MMAs
+      float y[8][4], rs[4] = {0.f, 0.f, 0.f, 0.f};   // rs: row sums of the numerators = Q' . ones (rows g, g + 8 in [0], [2])
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f; }
+#pragma unroll
+      for (int kd = 0; kd < 4; ++kd) {
+        mma_bf16(rs, pa[kd], BF2_ONES, BF2_ONES);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // B fragments of two l n-tiles per ldmatrix.x4 from A^T[l][d]
+          uint32_t b0, b1, b2, b3;
+          const int r = 16 * np + rr + ((mat >> 1) << 3), c = 2 * kd + (mat & 1);
+          ldsm_x4(ks_addr + swz(r, c), b0, b1, b2, b3);
+          mma_bf16(y[2 * np], pa[kd], b0, b1);
+          mma_bf16(y[2 * np + 1], pa[kd], b2, b3);
+        }
+      }
+      const float r0 = rcp_approx(rs[0]), r1 = rcp_approx(rs[2]);
+      const int ra = mt * 16 + g, rb = ra + 8;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(Vs + swz(ra, nt) + q * 4) = pack2(y[nt][0] * r0, y[nt][1] * r0);
+        *reinterpret_cast<uint32_t*>(Vs + swz(rb, nt) + q * 4) = pack2(y[nt][2] * r1, y[nt][3] * r1);
+      }
+    }
+  }
+  __syncthreads();  // this CTA's heads of Y are in smem
+
+  // ---- 6. StylizationBlock prologue: LN(512) * (1 + scale) + shift, SiLU over this CTA's COLS columns.
+  //         A lane covers 16 columns of one row; LPR lanes make a row, a warp handles RPI rows per iteration.
+  {
+    const int sub = lane % C::LPR, rsel = lane / C::LPR;
+    const int hh = sub >> 2, c0 = (sub & 3) * 2;          // local head, first of the lane's two 16-byte chunks
+    const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
+    const int col0 = (int)rank * C::COLS + sub * 16;       // global column
+    const float* sc = ss + (size_t)(smp % B) * ss_ld;
+    // per-column constants folded once:  h = t/2,  t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*2G + 2Bc
+    float G[16], Bc[16];
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + col0 + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + e));
+      G[e] = 0.5f * a.x * (1.f + c4.x); G[e + 1] = 0.5f * a.y * (1.f + c4.y); G[e + 2] = 0.5f * a.z * (1.f + c4.z); G[e + 3] = 0.5f * a.w * (1.f + c4.w);
+      Bc[e] = 0.5f * fmaf(b4.x, 1.f + c4.x, d4.x); Bc[e + 1] = 0.5f * fmaf(b4.y, 1.f + c4.y, d4.y);
+      Bc[e + 2] = 0.5f * fmaf(b4.z, 1.f + c4.z, d4.z); Bc[e + 3] = 0.5f * fmaf(b4.w, 1.f + c4.w, d4.w);
+    }
+    auto finish_row = [&](int t, const float (&v)[16], float s, float sq) {
+      // normalise, modulate, SiLU, store: the LPR lanes of a row write COLS * 2 contiguous bytes
+      const float mean = s * (1.f / D);
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+      const float nmr = -mean * rstd;
+      uint32_t o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
+        const float h0 = fmaf(fmaf(v[2 * e], rstd, nmr), G[2 * e], Bc[2 * e]);
+        const float h1 = fmaf(fmaf(v[2 * e + 1], rstd, nmr), G[2 * e + 1], Bc[2 * e + 1]);
+        o[e] = pack2(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+      }
+      uint4* dst = reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    };
+    if constexpr (CL == 1) {
+      // one CTA holds the whole row: statistics and normalisation in one pass, one warp per row
+      for (int t = warp; t < T; t += C::NWARPS) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
+        const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
+        const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float v[16], s = 0.f, sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[2 * e] = bf_lo(w[e]); v[2 * e + 1] = bf_hi(w[e]);
+          s += v[2 * e] + v[2 * e + 1];
+          sq = fmaf(v[2 * e], v[2 * e], fmaf(v[2 * e + 1], v[2 * e + 1], sq));
+        }
+        // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sq += __shfl_xor_sync(0xffffffffu, sq, o2); }
+        finish_row(t, v, s, sq);
+      }
+    } else {
+      uint32_t w[C::LN_ITERS][8];
+      float ps[C::LN_ITERS], pq[C::LN_ITERS];
+      // 6a. load the lane's 16 columns of each of its rows (kept packed in registers across the cluster barrier), reduce
+      //     (sum, sum of squares) over the row's LPR lanes
+#pragma unroll
+      for (int i = 0; i < C::LN_ITERS; ++i) {
+        const int t = (i * C::NWARPS + warp) * C::RPI + rsel;
+        float s = 0.f, sq = 0.f;
+        if (t < T) {
+          const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
+          const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
+          w[i][0] = u0.x; w[i][1] = u0.y; w[i][2] = u0.z; w[i][3] = u0.w; w[i][4] = u1.x; w[i][5] = u1.y; w[i][6] = u1.z; w[i][7] = u1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float lo = bf_lo(w[i][e]), hi = bf_hi(w[i][e]);
+            s += lo + hi;
+            sq = fmaf(lo, lo, fmaf(hi, hi, sq));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[i][e] = 0u;
+        }
+#pragma unroll
+        for (int o2 = C::LPR / 2; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sq += __shfl_xor_sync(0xffffffffu, sq, o2); }
+        ps[i] = s; pq[i] = sq;
+      }
+      // 6b. publish this CTA's partials into every CTA's table (slot = source rank), one cluster barrier, sum in rank order
+      prims::cluster_wait();   // every CTA of the cluster has started: its shared memory may be written
+#pragma unroll
+      for (int i = 0; i < C::LN_ITERS; ++i) {
+        const int t = (i * C::NWARPS + warp) * C::RPI + rsel;
+        if (t < T && sub < CL) {   // lane `sub` of the row serves CTA (rank + sub) % CL; sub == 0 is the local table
+          const uint32_t dst = (rank + (uint32_t)sub) % CL;
+          prims::st_peer_f32x2(smem_addr(stat + rank * TP + t), dst, ps[i], pq[i]);
+        }
+      }
+      prims::cluster_barrier();   // all tables complete and visible (release / acquire at cluster scope); no remote access after this
+      // 6c. total statistics in rank order (bit-identical in every CTA of the sample), then normalise and store
+#pragma unroll
+      for (int i = 0; i < C::LN_ITERS; ++i) {
+        const int t = (i * C::NWARPS + warp) * C::RPI + rsel;
+        if (t < T) {
+          float s = 0.f, sq = 0.f;
+#pragma unroll
+          for (int r = 0; r < CL; ++r) { const float2 st2 = stat[r * TP + t]; s += st2.x; sq += st2.y; }
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[2 * e] = bf_lo(w[i][e]); v[2 * e + 1] = bf_hi(w[i][e]); }
+          finish_row(t, v, s, sq);
+        }
+      }
+    }
+  }
+}
+
+#ifndef DSHEG_EMU
+// host launcher: CL > 1 kernels run as thread-block clusters of CL CTAs (one cluster per sample)
+template <int CL>
+inline cudaError_t launch_attn_v5(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
+                                  const float* ss, int ss_ld, cudaStream_t st) {
+  using C = Cfg<CL>;
+  auto kern = attn_v5_kernel<CL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_samples * CL); cfg.blockDim = dim3(C::NTHREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, qkv, z, T, ssB, ln_g, ln_b, ss, ss_ld);
+}
+#endif  // DSHEG_EMU
+
+}  // namespace av5
+}  // namespace dsheg

@@ -15,6 +15,7 @@
 #include "attn_v2.cuh"
 #include "attn_v3.cuh"
 #include "attn_v4.cuh"
+#include "attn_v5.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -331,6 +332,12 @@ struct Runner {
       av3::attn_v3_kernel<<<n_samples, av3::NTHREADS, av3::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 4) {
       av4::attn_v4_kernel<<<2 * n_samples, av4::NTHREADS, av4::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
+    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 >= 51 && h->attn_v2 <= 54) {
+      // attn_v5<CL>: instruction-diet kernel as 1 / 2 / 4 CTAs per sample (DSHEG_ATTN=v5c1 | v5c2 | v5c4; experimental)
+      cudaError_t le = h->attn_v2 == 51 ? av5::launch_attn_v5<1>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
+                     : h->attn_v2 == 52 ? av5::launch_attn_v5<2>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
+                                        : av5::launch_attn_v5<4>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
+      if (le != cudaSuccess) return fail(h, std::string("attn_v5 launch: ") + cudaGetErrorString(le));
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av2::D && H == av2::NH && T <= av2::TP && h->attn_v2 == 2) {
       av2::attn_v2_kernel<<<n_samples, 256, av2::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 64) {
@@ -546,6 +553,9 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (att && !strcmp(att, "v1")) h->attn_v2 = 0;
   if (att && !strcmp(att, "v2")) h->attn_v2 = 2;
   if (att && !strcmp(att, "v4")) h->attn_v2 = 4;   // cluster-of-two half-sample CTAs (attn_v4.cuh; experimental)
+  if (att && !strcmp(att, "v5c1")) h->attn_v2 = 51;  // attn_v5.cuh, 1 / 2 / 4 CTAs per sample (experimental)
+  if (att && !strcmp(att, "v5c2")) h->attn_v2 = 52;
+  if (att && !strcmp(att, "v5c4")) h->attn_v2 = 54;
   const char* gr = getenv("DSHEG_GRAPHS");
   if (gr && !strcmp(gr, "0")) h->use_graphs = 0;
   const char* fs = getenv("DSHEG_FUSE_STATS");
@@ -959,6 +969,12 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
     cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
     av2::attn_v2_kernel<<<Bn, 256, av2::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b, scale_shift,
                                                                             2 * av2::D);
+  } else if (att && !strncmp(att, "v5c", 3) && (att[3] == '1' || att[3] == '2' || att[3] == '4') && !att[4]) {
+    const cudaStream_t s5 = (cudaStream_t)stream;
+    cudaError_t le = att[3] == '1' ? av5::launch_attn_v5<1>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
+                   : att[3] == '2' ? av5::launch_attn_v5<2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
+                                   : av5::launch_attn_v5<4>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5);
+    if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (v5): ") + cudaGetErrorString(le); return 1; }
   } else if (att && !strcmp(att, "v4")) {
     cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
     av4::attn_v4_kernel<<<2 * Bn, av4::NTHREADS, av4::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,

@@ -94,6 +94,7 @@ template <int NTHREADS> inline void named_bar_sync(int id) {
   emu::rendezvous(emu::self().cta->named[id], NTHREADS, "bar.sync (named)");
 }
 inline float ex2f(float x) { return exp2f(x); }
+inline float rcp_approx(float x) { return 1.0f / x; }
 inline float tanh_approx(float x) { return tanhf(x); }
 
 inline uint32_t cluster_rank() { return emu::self().cta->rank; }
@@ -104,6 +105,7 @@ inline void cluster_arrive() {
   t.cluster_wait_gen = cl.rv.gen;
   if (++cl.rv.arrived == expected) { cl.rv.arrived = 0; ++cl.rv.gen; ++emu::rt().progress; }
 }
+inline void cluster_arrive_relaxed() { cluster_arrive(); }
 inline void cluster_wait() {
   emu::Thread& t = emu::self();
   emu::Cluster& cl = *t.cta->cluster;
