@@ -26,7 +26,7 @@ def lib():
     if _lib is None:
         if _stale():
             os.makedirs(os.path.dirname(_SO), exist_ok=True)
-            cmd = ["g++", "-O2", "-std=c++17", "-DDSHEG_EMU", "-Wno-unknown-pragmas", "-Wno-attributes", "-fPIC", "-shared",
+            cmd = ["g++", "-O2", "-std=c++17", "-DDSHEG_EMU", "-Wno-unknown-pragmas", "-Wno-attributes", "-ffp-contract=off", "-fPIC", "-shared",
                    "-I", _HERE, "-I", CSRC, "-o", _SO, os.path.join(_HERE, "emu_kernels.cpp")]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:

@@ -1,8 +1,12 @@
 // TEST INFRASTRUCTURE ONLY -- the attention kernel SOURCES of diffsheg_b200/csrc compiled for the host emulator
 // (g++ -DDSHEG_EMU) behind a small C ABI for tests/test_emu_kernels.py.  Pointers are host pointers; bf16 travels as uint16.
+#include <algorithm>
+
 #include "attn_v3.cuh"
 #include "attn_v4.cuh"
 #include "attn_v5.cuh"
+#include "postprocess.cuh"
+#include "sampler.cuh"
 
 using namespace dsheg;
 
@@ -31,4 +35,36 @@ extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int 
     g_err = "unknown attention variant";
   }
   return ok ? 0 : 1;
+}
+
+// ---- elementwise kernels: a small grid of 256-thread CTAs, grid-stride like on the device --------------------------------------
+static int ew(long long n, std::function<void()> body) {
+  g_err.clear();
+  const int grid = (int)std::max<long long>(1, std::min<long long>(4, (n + 255) / 256));
+  return emu::run_grid(grid, 256, 1, 0, body, &g_err) ? 0 : 1;
+}
+
+extern "C" int emu_inv_standardize(const float* x, int ldx, const float* mean, const float* stdv, float* out, int ldo, long long rows, int D) {
+  return ew(rows * D, [=] { inv_standardize_kernel(x, ldx, mean, stdv, out, ldo, rows, D); });
+}
+extern "C" int emu_beat_axis_angle(const float* x, int ldx, const float* mean_aa, const float* std_aa, const float* mean_pose,
+                                   const float* std_pose, float* euler_deg, float* out_norm, long long rows, int joints) {
+  return ew(rows * joints, [=] { beat_axis_angle_kernel(x, ldx, mean_aa, std_aa, mean_pose, std_pose, euler_deg, out_norm, rows, joints); });
+}
+extern "C" int emu_ddim_step(const float* x, const float* eps, float* x_out, float* pred_out, long long n, int T, int D, float a, float b,
+                             float sqrt_acp, float sqrt_1m_acp, const float* gt, const unsigned char* mask, const float* noise2,
+                             int blend, int overlap_len) {
+  DdimArgs p{x, eps, x_out, pred_out, n, T, D, a, b, sqrt_acp, sqrt_1m_acp, gt, mask, noise2, blend, overlap_len};
+  return ew(n, [=] { ddim_step_kernel(p); });
+}
+extern "C" int emu_undo_step(const float* x, const float* noise, float* out, long long n, float c1, float c2) {
+  return ew(n, [=] { undo_step_kernel(x, noise, out, n, c1, c2); });
+}
+extern "C" int emu_ddpm_step(const float* x, const float* eps, const float* noise, float* out, float* pred_out, long long n, float a,
+                             float b, float c1, float c2, float sigma) {
+  return ew(n, [=] { ddpm_step_kernel(x, eps, noise, out, pred_out, n, a, b, c1, c2, sigma); });
+}
+extern "C" int emu_repaint_merge(const float* x, const float* gt, const unsigned char* mask, const float* noise, float* out, long long n,
+                                 float c1, float c2) {
+  return ew(n, [=] { repaint_merge_kernel(x, gt, mask, noise, out, n, c1, c2); });
 }
