@@ -1,0 +1,109 @@
+"""First hardware run of the kernels written without GPU access (validated so far only on the CPU emulator, tests/emu):
+attention v4 / v5<1,2,4> and the post-processing kernels.  Prints one PASS / FAIL line per item plus the attention
+bandwidth of every variant inside a real denoiser call, and writes the same to gpurun_out/first_hw_run.json.
+
+Run by tests/test_zz_first_hw_run.py in a SUBPROCESS (a faulting kernel must not poison the CUDA context of the parity
+suite) and by scripts/gpu_round2_first.sh.  Exit code 0 = everything passed."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]
+results = {}
+
+
+def record(name, ok, **info):
+    results[name] = dict(ok=bool(ok), **info)
+    print(("PASS " if ok else "FAIL ") + name + (" " + json.dumps(info) if info else ""), flush=True)
+
+
+def pytest_items():
+    env = dict(os.environ, DSHEG_RUN_UNVALIDATED="1")
+    items = [("postprocess kernels (tests/test_postprocess.py)", ["tests/test_postprocess.py", "-k", "gpu_"])]
+    items += [(f"attention op {v} (test_op_attention_bf16_tensor_core)", ["tests/test_gpu_parity.py", "-k", f"op_attention_bf16 and {v}"])
+              for v in VARIANTS]   # one process per variant: a faulting kernel poisons only its own CUDA context
+    for name, sel in items:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + sel, cwd=ROOT, env=env,
+                               capture_output=True, text=True, timeout=120)
+            tail = (r.stdout + r.stderr).strip().splitlines()[-3:]
+            record(name, r.returncode == 0, seconds=round(time.time() - t0, 1), tail=tail)
+        except subprocess.TimeoutExpired:
+            record(name, False, error="timeout")
+
+
+def in_loop(batch, var):
+    """Default attention vs ONE variant inside dsheg_denoise (SHOW, CFG): output agreement and attention GB/s."""
+    import torch
+    from diffsheg_b200 import FusedUniDiffuser, synth
+    cfg = synth.make_cfg("show")
+    sd = synth.make_state_dict(cfg, seed=1)
+    T = cfg["n_poses"]
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, batch, T, seed=2).items()}
+    base = None
+    for v in (None, var):
+        name = f"denoise B={batch} attention={v or 'v3 (default)'}"
+        if v:
+            os.environ["DSHEG_ATTN"] = v
+        else:
+            os.environ.pop("DSHEG_ATTN", None)
+        eng = FusedUniDiffuser(sd, cfg, precision="bf16", max_batch=batch, max_frames=T)
+        eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+        out = torch.empty_like(inp["x_T"])
+        for _ in range(2):
+            eng.denoise(inp["x_T"], 480, 1.8, 1.5, out=out)
+        eng.profile_begin()
+        for _ in range(2):
+            eng.denoise(inp["x_T"], 480, 1.8, 1.5, out=out)
+        at = eng.profile_end()["attention"]
+        torch.cuda.synchronize()
+        gbs = at["work"] / (at["ms"] * 1e-3) / 1e9 if at["ms"] > 0 else 0.0
+        if base is None:
+            base = out.clone()
+            record(name, bool(torch.isfinite(out).all()), attention_gbs=round(gbs), attention_ms=round(at["ms"], 3))
+        else:
+            err = float((out - base).abs().max() / base.abs().max())
+            record(name, err < 2e-2 and bool(torch.isfinite(out).all()), relmax_vs_default=err, attention_gbs=round(gbs),
+                   attention_ms=round(at["ms"], 3))
+        del eng
+
+
+def child(var):
+    """One variant per process: a faulting kernel poisons only its own CUDA context."""
+    for batch in (3, int(os.environ.get("DSHEG_FIRST_RUN_BATCH", "950"))):
+        try:
+            in_loop(batch, var)
+        except Exception as e:  # noqa: BLE001
+            record(f"denoise B={batch} attention={var}", False, error=repr(e)[:300])
+            break
+    print("RESULTS " + json.dumps(results), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        child(sys.argv[2])
+        sys.exit(0)
+    pytest_items()
+    for var in VARIANTS:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--variant", var], cwd=ROOT, capture_output=True, text=True,
+                               timeout=150)
+            got = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULTS ")]
+            if got:
+                for k, v in json.loads(got[-1][8:]).items():
+                    if not (k.endswith("(default)") and k in results):
+                        results[k] = v
+                        print(("PASS " if v["ok"] else "FAIL ") + k + " " + json.dumps({a: b for a, b in v.items() if a != "ok"}), flush=True)
+            else:
+                record(f"in-loop {var}", False, rc=r.returncode, tail=(r.stdout + r.stderr).strip().splitlines()[-3:])
+        except subprocess.TimeoutExpired:
+            record(f"in-loop {var}", False, error="timeout")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "first_hw_run.json"), "w") as f:
+        json.dump(results, f, indent=1)
+    sys.exit(0 if all(r["ok"] for r in results.values()) else 1)
