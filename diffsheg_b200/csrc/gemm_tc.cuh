@@ -56,11 +56,19 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cf
 #define DSHEG_PAIR_STAGES 4
 #endif
   static constexpr int STG_BYTES = NARROW ? STG_BYTES_NARROW : STG_BYTES_WIDE;
-  static constexpr int STAGES = CG == 2 ? (LONGK ? (NARROW ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES) : (BN == 128 ? 5 : 3);
+  // -DDSHEG_K512_DEEP=1 (experiment build, scripts/build_variants.sh): the K = 512 pair kernels also run at the smem limit --
+  // WIDE boxes kept, no alignment slack, single-buffered vectors -> a FIFTH stage (5 * 32 KB + 64 KB + 2.5 KB = 226.5 KB).
+  // Round 1 only measured "6 stages + narrow boxes" for these shapes (slower); the stage sweep says depth itself helps.
+#ifndef DSHEG_K512_DEEP
+#define DSHEG_K512_DEEP 0
+#endif
+  static constexpr bool AT_LIMIT = CG == 2 && (LONGK || DSHEG_K512_DEEP);
+  static constexpr int STAGES = CG == 2 ? (LONGK ? (NARROW ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES + (DSHEG_K512_DEEP ? 1 : 0))
+                                        : (BN == 128 ? 5 : 3);
   // pair kernels run at the smem limit: the dynamic smem base is required to be 1024-aligned (checked, traps otherwise)
   // and the per-tile bias/csum vectors are single-buffered (one extra epilogue barrier per tile)
-  static constexpr int ALIGN_SLACK = (CG == 2 && LONGK) ? 0 : 1024;
-  static constexpr int NVEC = (CG == 2 && LONGK) ? 1 : NUM_ACC;
+  static constexpr int ALIGN_SLACK = AT_LIMIT ? 0 : 1024;
+  static constexpr int NVEC = AT_LIMIT ? 1 : NUM_ACC;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
