@@ -255,7 +255,7 @@ def run_ours(args):
             "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
             "launches_per_step": g["count"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / ms if world == 1 else None,
             "executed_flops_per_step": g["work"]}
-    roof_attn = {"kernel": "attn_kernel (linear attention + LN/modulate/SiLU)", "bound": "hbm", "achieved": attn_gbs,
+    roof_attn = {"kernel": "attn_%s kernel (linear attention + LN/modulate/SiLU)" % (os.environ.get("DSHEG_ATTN") or "v3"), "bound": "hbm", "achieved": attn_gbs,
                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": attn_gbs / pk["hbm_gbs"], "traffic": None,
                  "peak_source": pk["source"], "launches_per_step": at["count"], "ms_per_step": at["ms"],
                  "share_of_step": at["ms"] / ms if world == 1 else None}
@@ -268,6 +268,14 @@ def run_ours(args):
         roof["traffic_note"] = ("mean dram__bytes_read+write per launch over the 7 GEMMs of one layer (ncu --set full, "
                                 "profiles/r01/final_gemm_ncu_summary.json); algorithmic operand+output bytes of the same launches: "
                                 f"{ALGO_GEMM_BYTES_PER_LAYER / 7 / 1e6:.0f} MB per launch")
+    except Exception:
+        pass
+    try:   # same for the attention kernel (default kernel attn_v3; one launch, SHOW B=950 CFG)
+        na = json.load(open(os.path.join(ROOT, "profiles", "r01", "final_attn_ncu_summary.json")))
+        if not os.environ.get("DSHEG_ATTN"):
+            roof_attn["traffic"] = 1e6 * (na["dram__bytes_read.sum"][0] + na["dram__bytes_write.sum"][0])
+            roof_attn["traffic_note"] = ("dram__bytes_read+write of one launch (ncu --set full, profiles/r01/final_attn_ncu_summary.json); "
+                                         f"algorithmic bytes of the same launch: {at['work'] / max(at['count'], 1) / 1e6:.0f} MB")
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -303,7 +311,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=950, help="per-GPU batch (BASELINE configs[1]: 950)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample of the workload")
+    ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample of the workload (about 10 s of CPU work per loop)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cuda", type=int, default=0, help="time the reference op stream (oracle port) eagerly on the GPU at this batch")
     args = ap.parse_args()
