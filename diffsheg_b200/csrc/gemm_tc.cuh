@@ -434,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+#ifndef DSHEG_EMU
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -449,6 +450,7 @@ inline EncodeTiledFn get_encode_fn() {
   }
   return fn;
 }
+#endif  // DSHEG_EMU
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64], 128B swizzle,
 // out-of-bounds elements read as zero (ragged M / N / K tails need no padding in memory).
@@ -482,6 +484,12 @@ inline bool make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int
 inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, std::string* err) {
   // box = [box_rows x 64 columns] (128-byte rows, SWIZZLE_128B): operand tiles and wide epilogue boxes;
   // box = [box_rows x 32 columns] (64-byte rows, SWIZZLE_64B): narrow epilogue boxes
+#ifdef DSHEG_EMU   // tests/emu: the emulated tensor map records the same geometry (emu_tc_prims.h)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) { *err = "TMA operand not 16-byte aligned"; return false; }
+  map->base = ptr; map->cols = (uint64_t)cols; map->rows = (uint64_t)rows; map->ld_bytes = (uint64_t)ld * 2;
+  map->box_cols = (uint32_t)box_cols; map->box_rows = (uint32_t)box_rows; map->swizzle_bytes = box_cols == 32 ? 64 : 128;
+  return true;
+#else
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) { *err = "TMA operand not 16-byte aligned"; return false; }
@@ -495,12 +503,25 @@ inline bool make_tmap_uncached(CUtensorMap* map, const void* ptr, int rows, int 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r); return false; }
   return true;
+#endif
 }
+
+#ifdef DSHEG_EMU
+inline std::string& g_emu_error() { static std::string e; return e; }
+#endif
 
 template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool LONGK_ = false>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG, LONGK_>;
   using C = Cfg<BN, CG, (LONGK_ && CG == 2 && !OUTF32 && RES != RES_BF16), (LONGK_ && CG == 2 && !OUTF32)>;
+#ifdef DSHEG_EMU   // tests/emu: run the grid on the thread-level emulator (clusters of CG CTAs)
+  (void)st;
+  const CUtensorMap m0 = maps[0], m1 = maps[1], m2 = maps[2], m3 = maps[3], m4 = maps[4], m5 = maps[5], m6 = maps[6], m7 = maps[7];
+  static std::string emu_err;
+  const bool ok = emu::run_grid(grid, C::NUM_THREADS, CG, C::SMEM_BYTES, [=] { kern(m0, m1, m2, m3, m4, m5, m6, m7, p); }, &emu_err);
+  if (!ok) { g_emu_error() = emu_err; return cudaErrorLaunchFailure; }
+  return cudaSuccess;
+#else
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -519,6 +540,7 @@ inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int 
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+#endif
 }
 
 template <int BN, int CG>

@@ -8,29 +8,47 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "diffsheg_b200", "csrc")
-_SO = os.path.join(_HERE, "_build", "libemu_kernels.so")
 _lib = None
+_libs = {}
 
 
-def _stale():
-    if not os.path.exists(_SO):
+def _stale(so):
+    if not os.path.exists(so):
         return True
-    m = os.path.getmtime(_SO)
+    m = os.path.getmtime(so)
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".h", ".cpp"))]
     srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     return any(os.path.getmtime(s) > m for s in srcs)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if _stale():
-            os.makedirs(os.path.dirname(_SO), exist_ok=True)
-            cmd = ["g++", "-O2", "-std=c++17", "-DDSHEG_EMU", "-Wno-unknown-pragmas", "-Wno-attributes", "-ffp-contract=off", "-fPIC", "-shared",
-                   "-I", _HERE, "-I", CSRC, "-o", _SO, os.path.join(_HERE, "emu_kernels.cpp")]
+def _load(name, defines=()):
+    key = (name,) + tuple(defines)
+    if key not in _libs:
+        tag = name + "".join("_" + d.replace("=", "") for d in defines)
+        so = os.path.join(_HERE, "_build", f"lib{tag}.so")
+        if _stale(so):
+            os.makedirs(os.path.dirname(so), exist_ok=True)
+            cmd = ["g++", "-O2", "-std=c++17", "-DDSHEG_EMU", "-Wno-unknown-pragmas", "-Wno-attributes", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared",
+                   "-I", _HERE, "-I", CSRC] + ["-D" + d for d in defines] + ["-o", so, os.path.join(_HERE, name + ".cpp")]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError("emulator build failed:\n" + res.stderr)
-        _lib = ctypes.CDLL(_SO)
+        _libs[key] = ctypes.CDLL(so)
+    return _libs[key]
+
+
+def lib():
+    """SIMT / mma.sync kernels (attention, sampler steps, post-processing)."""
+    global _lib
+    if _lib is None:
+        _lib = _load("emu_kernels")
         _lib.emu_last_error.restype = ctypes.c_char_p
     return _lib
+
+
+def gemm_lib(*defines):
+    """The tcgen05 GEMM (gemm_tc.cuh) on the mbarrier / TMA / tcgen05 models of emu_tc_prims.h; `defines` selects an
+    experiment build (e.g. "DSHEG_K512_DEEP=1")."""
+    L = _load("emu_gemm", defines)
+    L.emu_gemm_last_error.restype = ctypes.c_char_p
+    return L

@@ -79,6 +79,11 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 
+// ---- the sliver of the runtime API the host-side launch code mentions ------------------------------------------------------
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorLaunchFailure = 719 };
+
 // ---- fibers, CTAs, clusters -----------------------------------------------------------------------------------------------
 namespace emu {
 
@@ -101,6 +106,7 @@ struct Cta {
   Cluster* cluster = nullptr;
   Rendezvous named[16];
   std::vector<Warp> warps;
+  std::shared_ptr<void> ext;   // per-CTA state of optional models (emu_tc_prims.h: mbarriers, TMEM); fresh for every CTA
 };
 struct Cluster {
   std::vector<Cta> ctas;

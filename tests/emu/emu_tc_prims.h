@@ -1,0 +1,253 @@
+// TEST INFRASTRUCTURE ONLY -- host models of diffsheg_b200/csrc/tc_prims.cuh (same names and signatures) for the thread-level
+// emulator (emu_cuda.h).  What is modelled, from the PTX ISA / CUDA documentation the kernel was written against:
+//   mbarrier      : {expected arrivals, pending arrivals, pending tx bytes, phase}; a phase completes when pending == 0 and
+//                   tx == 0; try_wait.parity(P) succeeds once the phase of parity P has completed (phase bit != P)
+//   TMA 2-D tiles : box [rows x cols] of a row-major bf16 tensor, out-of-bounds reads are zero and writes are clipped;
+//                   SWIZZLE_128B / 64B = XOR of smem address bits [4,7) with bits [7,10) (64B: [4,6) with [7,9));
+//                   a load credits box-bytes to its mbarrier (complete_tx); the cta_group::2 form credits the LEADER's
+//   tcgen05.mma   : kind::f16, D[M x N] (+)= A[M x 16] . B[N x 16]^T, fp32 accumulate in TMEM; operands from smem through
+//                   K-major SWIZZLE_128B descriptors (start address >> 4, SBO = 1024 B per 8 rows, the same address-bit
+//                   XOR); cta_group::2: M = 256 -- rows 0..127 from the leader's smem / TMEM, 128..255 from the peer's;
+//                   each CTA supplies HALF of the N rows of B.  Executed synchronously at issue, so tcgen05.commit
+//                   arrives immediately (the real ordering guarantees are a superset).
+//   tcgen05.ld    : 32x32b.x32 -- thread `lane` of the warp reads 32 consecutive columns of TMEM lane (base + lane)
+//   TMEM          : 128 lanes x 512 fp32 columns per CTA; alloc returns base 0
+// Not modelled: async-proxy / generic-proxy ordering (fence.proxy.async), TMEM allocation contention, timing.
+#pragma once
+#include <unordered_map>
+
+#include "emu_cuda.h"
+
+struct CUtensorMap {   // emulated tensor map: row-major bf16 [rows, cols], leading dimension in bytes
+  const void* base = nullptr;
+  uint64_t cols = 0, rows = 0, ld_bytes = 0;
+  uint32_t box_cols = 0, box_rows = 0;
+  int swizzle_bytes = 128;
+};
+
+#define DSHEG_TC_DYN_SMEM(name) uint8_t* name = emu::self().cta->smem
+
+namespace emu {
+struct MBar { int expected = 0, pending = 0; long long tx = 0; uint32_t phase = 0; bool init = false; };
+struct TcState {
+  std::unordered_map<uint32_t, MBar> bars;   // keyed by smem offset
+  std::vector<float> tmem;                    // [128][512]
+};
+inline TcState& tc_state(const Cta* c) {
+  Cta* cc = const_cast<Cta*>(c);
+  if (!cc->ext) {
+    auto s = std::make_shared<TcState>();
+    s->tmem.assign(128 * 512, 0.0f);
+    cc->ext = s;
+  }
+  return *static_cast<TcState*>(cc->ext.get());
+}
+// resolve a shared::cta offset or a mapa-encoded shared::cluster address to (CTA, offset)
+inline Cta* resolve(uint32_t addr, uint32_t* off) {
+  Cta* me = self().cta;
+  if (addr & 0x80000000u) {
+    const uint32_t rank = (addr >> 24) & 0x7Fu;
+    *off = addr & 0x00FFFFFFu;
+    if (rank >= me->cluster->ctas.size()) { rt().error = "cluster address: rank outside the cluster"; return me; }
+    return &me->cluster->ctas[rank];
+  }
+  *off = addr;
+  return me;
+}
+inline MBar& bar_at(uint32_t addr, const char* what) {
+  uint32_t off;
+  Cta* c = resolve(addr, &off);
+  if (off & 7u) rt().error = std::string(what) + ": mbarrier address not 8-byte aligned";
+  MBar& b = tc_state(c).bars[off];
+  if (!b.init && std::string(what) != "mbarrier.init") rt().error = std::string(what) + ": mbarrier used before mbarrier.init";
+  return b;
+}
+inline void bar_check_complete(MBar& b) {
+  if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.expected; }
+  ++rt().progress;
+}
+inline void bar_arrive(uint32_t addr, const char* what) {
+  MBar& b = bar_at(addr, what);
+  if (b.pending <= 0) { rt().error = std::string(what) + ": more arrivals than the mbarrier expects"; return; }
+  --b.pending;
+  bar_check_complete(b);
+}
+inline void bar_complete_tx(uint32_t addr, long long bytes) {
+  MBar& b = bar_at(addr, "complete_tx");
+  b.tx -= bytes;
+  bar_check_complete(b);
+}
+// Adversarial timing: EMU_DELAY_TMEM_LD / EMU_DELAY_TMA / EMU_DELAY_MMA = number of scheduler passes the calling thread
+// sits out before the operation.  The round-robin schedule makes every role equally "fast"; slowing one role down exposes
+// protocol bugs that need a particular interleaving (a TMEM stage or smem slot handed back before its last read, ...).
+inline void delay(const char* env_name) {
+  const char* e = getenv(env_name);
+  const int n = e ? atoi(e) : 0;
+  for (int i = 0; i < n; ++i) { ++rt().progress; yield(); }
+}
+inline uint32_t swizzle_addr(uint32_t a, int swizzle_bytes) {
+  if (swizzle_bytes == 128) return a ^ (((a >> 7) & 7u) << 4);
+  if (swizzle_bytes == 64) return a ^ (((a >> 7) & 3u) << 4);
+  return a;
+}
+}  // namespace emu
+
+namespace dsheg {
+namespace tc {
+
+inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+inline void mbar_init(uint32_t bar, uint32_t count) {
+  emu::MBar& b = emu::bar_at(bar, "mbarrier.init");
+  b.expected = b.pending = (int)count; b.tx = 0; b.phase = 0; b.init = true;
+}
+inline void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  emu::bar_at(bar, "mbarrier.arrive.expect_tx").tx += bytes;
+  emu::bar_arrive(bar, "mbarrier.arrive.expect_tx");
+}
+inline void mbar_arrive(uint32_t bar) { emu::bar_arrive(bar, "mbarrier.arrive"); }
+inline uint64_t globaltimer_ns() { return 0; }   // the watchdog never fires: deadlocks are reported by the scheduler
+inline uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  emu::MBar& b = emu::bar_at(bar, "mbarrier.try_wait");
+  if (((b.phase ^ parity) & 1u) != 0) return 1;
+  emu::self().waiting_on = "mbarrier.try_wait";
+  emu::yield();
+  emu::self().waiting_on = "";
+  return 0;
+}
+
+// ---- TMA ------------------------------------------------------------------------------------------------------------------
+inline void tma_copy(const CUtensorMap* m, emu::Cta* cta, uint32_t smem_off, int c0, int c1, bool load) {
+  if (smem_off % (m->swizzle_bytes == 128 ? 1024 : (m->swizzle_bytes == 64 ? 512 : 16)))
+    emu::rt().error = "TMA: shared-memory box not aligned to its swizzle atom";
+  const uint32_t row_bytes = m->box_cols * 2;
+  if ((size_t)smem_off + (size_t)row_bytes * m->box_rows > cta->smem_bytes) { emu::rt().error = "TMA: box outside shared memory"; return; }
+  for (uint32_t r = 0; r < m->box_rows; ++r) {
+    for (uint32_t c = 0; c < m->box_cols; ++c) {
+      const long long gr = (long long)c1 + r, gc = (long long)c0 + c;
+      const bool inb = gr >= 0 && gc >= 0 && (uint64_t)gr < m->rows && (uint64_t)gc < m->cols;
+      uint8_t* sp = cta->smem + emu::swizzle_addr(smem_off + r * row_bytes + c * 2, m->swizzle_bytes);
+      uint8_t* gp = const_cast<uint8_t*>(static_cast<const uint8_t*>(m->base)) + (size_t)gr * m->ld_bytes + (size_t)gc * 2;
+      if (load) { if (inb) memcpy(sp, gp, 2); else memset(sp, 0, 2); }
+      else if (inb) memcpy(gp, sp, 2);
+    }
+  }
+}
+inline void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  emu::delay("EMU_DELAY_TMA");
+  tma_copy(map, emu::self().cta, dst, c0, c1, true);
+  emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
+}
+inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
+inline void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+  emu::delay("EMU_DELAY_TMA");
+  tma_copy(map, emu::self().cta, dst, c0, c1, true);
+  emu::bar_complete_tx(leader_bar, (long long)map->box_cols * 2 * map->box_rows);
+}
+inline void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) { tma_copy(map, emu::self().cta, src, c0, c1, false); }
+inline void bulk_commit() {}
+inline void bulk_wait_read0() {}
+inline void bulk_wait0() {}
+inline void fence_async_smem() {}
+
+// ---- tcgen05 ---------------------------------------------------------------------------------------------------------------
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+inline void tc_commit(uint32_t bar) { emu::bar_arrive(bar, "tcgen05.commit"); }
+inline void tc_commit_pair(uint32_t bar) {   // multicast mask 0b11: the same barrier offset in both CTAs of the pair
+  uint32_t off;
+  emu::resolve(bar, &off);
+  for (uint32_t r = 0; r < 2; ++r) emu::bar_arrive(0x80000000u | (r << 24) | off, "tcgen05.commit (pair)");
+}
+inline float emu_bf16_at(const emu::Cta* c, uint32_t addr) {
+  if ((size_t)addr + 2 > c->smem_bytes) { emu::rt().error = "tcgen05.mma: operand read outside shared memory"; return 0.f; }
+  uint16_t h;
+  memcpy(&h, c->smem + addr, 2);
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// element (row, k) of a K-major SWIZZLE_128B operand described by `desc` (k < 16: one UMMA_K slice)
+inline float emu_operand(const emu::Cta* c, uint64_t desc, int row, int k) {
+  const uint32_t start = (uint32_t)(desc & 0x3FFFu) << 4;
+  const uint32_t sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
+  const uint32_t layout = (uint32_t)(desc >> 61) & 7u;
+  if (layout != 2 || sbo != 1024) emu::rt().error = "tcgen05.mma: the emulator models K-major SWIZZLE_128B descriptors with SBO = 1024 only";
+  const uint32_t lin = start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
+  return emu_bf16_at(c, emu::swizzle_addr(lin, 128));
+}
+inline void emu_mma(int cg, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
+  emu::delay("EMU_DELAY_MMA");
+  emu::Cta* me = emu::self().cta;
+  if (cg == 2 && me->rank != 0) { emu::rt().error = "tcgen05.mma.cta_group::2 issued by the non-leader CTA"; return; }
+  if (M != 128 * cg || N % 16 || N < 16 || N > 256 || (tmem_d >> 16) != 0 || (tmem_d & 0xFFFFu) + (uint32_t)N > 512u) {
+    emu::rt().error = "tcgen05.mma: unsupported instruction descriptor / TMEM address in the emulator";
+    return;
+  }
+  const int col0 = (int)(tmem_d & 0xFFFFu);
+  std::vector<float> a((size_t)M * 16), b((size_t)N * 16);
+  for (int m = 0; m < M; ++m) {
+    const emu::Cta* c = cg == 2 ? &me->cluster->ctas[m / 128] : me;
+    for (int k = 0; k < 16; ++k) a[(size_t)m * 16 + k] = emu_operand(c, desc_a, m % 128, k);
+  }
+  const int n_per_cta = N / cg;
+  for (int n = 0; n < N; ++n) {
+    const emu::Cta* c = cg == 2 ? &me->cluster->ctas[n / n_per_cta] : me;
+    for (int k = 0; k < 16; ++k) b[(size_t)n * 16 + k] = emu_operand(c, desc_b, n % n_per_cta, k);
+  }
+  for (int m = 0; m < M; ++m) {
+    emu::Cta* c = cg == 2 ? &me->cluster->ctas[m / 128] : me;
+    float* d = emu::tc_state(c).tmem.data() + (size_t)(m % 128) * 512 + col0;
+    const float* am = &a[(size_t)m * 16];
+    for (int n = 0; n < N; ++n) {
+      const float* bn = &b[(size_t)n * 16];
+      float s = 0.f;
+      for (int k = 0; k < 16; ++k) s += am[k] * bn[k];
+      d[n] = accumulate ? d[n] + s : s;
+    }
+  }
+  ++emu::rt().progress;
+}
+inline void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { emu_mma(1, tmem_d, da, db, idesc, acc); }
+inline void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { emu_mma(2, tmem_d, da, db, idesc, acc); }
+inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  emu::delay("EMU_DELAY_TMEM_LD");
+  emu::Thread& t = emu::self();
+  const uint32_t lane_base = taddr >> 16, col = taddr & 0xFFFFu;
+  if (lane_base != (uint32_t)(t.warp & 3) * 32u) emu::rt().error = "tcgen05.ld: a warp may only touch the TMEM lane quadrant (warp id % 4)";
+  if (lane_base + 32 > 128 || col + 32 > 512) { emu::rt().error = "tcgen05.ld: TMEM address out of range"; return; }
+  const float* src = emu::tc_state(t.cta).tmem.data() + (size_t)(lane_base + t.lane) * 512 + col;
+  memcpy(r, src, 32 * 4);
+  __syncwarp();   // .sync.aligned: the warp executes it together
+}
+template <int CG, int COLS> inline void tmem_alloc(uint32_t slot) {
+  static_assert(COLS == 32 || COLS == 64 || COLS == 128 || COLS == 256 || COLS == 512, "TMEM allocations are powers of two >= 32 columns");
+  emu::Cta* c = emu::self().cta;
+  if (emu::self().lane == 0) { const uint32_t base = 0; memcpy(c->smem + slot, &base, 4); }
+  __syncwarp();
+}
+template <int CG, int COLS> inline void tmem_dealloc(uint32_t) { __syncwarp(); }
+
+// ---- cluster ----------------------------------------------------------------------------------------------------------------
+inline uint32_t cluster_ctarank() { return emu::self().cta->rank; }
+inline void cluster_sync_all() {
+  emu::Thread& t = emu::self();
+  emu::Cluster& cl = *t.cta->cluster;
+  emu::rendezvous(cl.rv, (int)cl.ctas.size() * t.cta->nthreads, "barrier.cluster");
+}
+inline uint32_t mapa_rank(uint32_t saddr, uint32_t rank) { return 0x80000000u | (rank << 24) | (saddr & 0x00FFFFFFu); }
+inline void mbar_arrive_cluster(uint32_t cluster_addr) { emu::bar_arrive(cluster_addr, "mbarrier.arrive (cluster)"); }
+template <int NTHREADS> inline void epi_bar_sync() { emu::rendezvous(emu::self().cta->named[1], NTHREADS, "bar.sync 1 (epilogue)"); }
+inline void fence_mbarrier_init() {}
+inline void prefetch_tensormap(const CUtensorMap*) {}
+inline void trap() {
+  emu::rt().error = "__trap() executed";
+  emu::self().done = true;
+  ++emu::rt().progress;
+  emu::yield();
+}
+inline float tanh_fast(float x) { return tanhf(x); }
+
+}  // namespace tc
+}  // namespace dsheg

@@ -1,0 +1,227 @@
+"""The tcgen05 GEMM kernel SOURCE (diffsheg_b200/csrc/gemm_tc.cuh, kernel and host-side launch code) executed on the CPU by
+the thread-level emulator with host models of mbarrier / TMA / tcgen05 / TMEM (tests/emu/emu_tc_prims.h), checked against a
+float64 evaluation of the same bf16 operands.  Covers what a GPU-less change can break: the producer / MMA / epilogue
+pipeline protocol (stage and accumulator parities, early TMEM hand-off, CTA-pair barriers), tensor-map coordinates and
+zero-filled ragged edges, the virtual-concat K walk, every epilogue variant the engine uses, the persistent tile walk.
+The kernel is hardware-validated (tests/test_gpu_parity.py::test_op_linear on the B200); agreeing with it anchors the models."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import emu
+
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+
+
+class Args(ctypes.Structure):
+    _fields_ = [("M", ctypes.c_int32), ("N", ctypes.c_int32), ("nseg", ctypes.c_int32),
+                ("seg_k", ctypes.c_int32 * 4), ("seg_ld", ctypes.c_int32 * 4), ("seg_ptr", ctypes.c_void_p * 4),
+                ("w", ctypes.c_void_p), ("Kp", ctypes.c_int32),
+                ("bias", ctypes.c_void_p), ("csum", ctypes.c_void_p), ("mu", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+                ("act", ctypes.c_int32), ("res", ctypes.c_void_p), ("ldr", ctypes.c_int32), ("res_mod", ctypes.c_int32),
+                ("res_f32", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("out_f32", ctypes.c_int32),
+                ("out2", ctypes.c_void_p), ("ps_out", ctypes.c_void_p), ("nullc", ctypes.c_void_p), ("n_uncond", ctypes.c_int32),
+                ("ps_in", ctypes.c_void_p), ("cs_in", ctypes.c_void_p), ("ps_slots", ctypes.c_int32), ("ps_P", ctypes.c_int32),
+                ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32)]
+
+
+def bf16_bits(t):
+    return np.ascontiguousarray(t.bfloat16().view(torch.int16).numpy())
+
+
+def bits_to_f64(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).view(torch.bfloat16).double()
+
+
+def ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def r64(k):
+    return (k + 63) // 64 * 64
+
+
+def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, dup=False, stats_out=False, n_uncond=0,
+             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None):
+    """Builds operands like the engine does (K laid out per segment padded to 64), runs the emulated kernel, returns
+    (got, want, extras)."""
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    Kp = sum(r64(k) for k in seg_ks)
+    segs, keep = [], []
+    Wfull = torch.zeros(N, Kp)
+    off = 0
+    A_cat = []
+    for k in seg_ks:
+        ld = r64(k) + 64                                   # a wider buffer: exercises the leading dimension
+        a = torch.zeros(M, ld)
+        a[:, :k] = rnd(M, k)
+        a[:, k:] = 7.0                                     # garbage beyond the segment width must never be read as data...
+        Wfull[:, off:off + k] = rnd(N, k) / np.sqrt(sum(seg_ks))
+        ab = bf16_bits(a)
+        keep.append(ab)
+        segs.append((ab, ld, k))
+        A_cat.append(bits_to_f64(ab)[:, :k])
+        off += r64(k)                                      # ...W is zero there anyway only up to the 64-padding
+    # columns k..r64(k) of a segment ARE read (TMA box = 64 columns) unless clipped by the tensor map's width k -> zero fill
+    Wb = bf16_bits(Wfull)
+    Wd = bits_to_f64(Wb)
+    Wcols = torch.cat([Wd[:, o:o + k] for o, k in zip(np.cumsum([0] + [r64(k) for k in seg_ks[:-1]]), seg_ks)], 1)
+    acc = torch.cat(A_cat, 1) @ Wcols.T
+    bias = rnd(N).float().numpy()
+    a = Args()
+    a.M, a.N, a.nseg, a.Kp = M, N, len(seg_ks), Kp
+    for i, (ab, ld, k) in enumerate(segs):
+        a.seg_k[i], a.seg_ld[i], a.seg_ptr[i] = k, ld, ptr(ab)
+    a.w, a.bias, a.act = ptr(Wb), ptr(bias), act
+    want = acc.clone()
+    extras = {}
+    if ln:
+        csum = Wcols.sum(1).float().numpy()
+        mu, rstd = rnd(M).float().numpy() * 0.1, (rnd(M).abs() + 0.5).float().numpy()
+        keep += [csum, mu, rstd]
+        a.csum = ptr(csum)
+        if ps_in:   # statistics rebuilt from 8 (sum, sumsq) partials per row, plus a conditioning partial
+            P = 512 + 37
+            tot_s = torch.from_numpy(mu.astype(np.float64)) * P
+            var = 1.0 / torch.from_numpy(rstd.astype(np.float64)) ** 2 - 1e-5
+            tot_q = (var + torch.from_numpy(mu.astype(np.float64)) ** 2) * P
+            w8 = torch.softmax(rnd(M, 9), 1).double()
+            parts = torch.stack([tot_s[:, None] * w8, tot_q[:, None] * w8], -1).float()     # [M, 9, 2]
+            ps = np.ascontiguousarray(parts[:, :8].numpy())
+            cs = np.ascontiguousarray(parts[:, 8].numpy())
+            keep += [ps, cs]
+            a.ps_in, a.cs_in, a.ps_slots, a.ps_P = ptr(ps), ptr(cs), 8, P
+            sx = parts[..., 0].double().sum(1)
+            sq = parts[..., 1].double().sum(1)
+            mean = sx / P
+            rs = 1.0 / torch.sqrt(torch.clamp(sq / P - mean * mean, min=0) + 1e-5)
+            want = rs[:, None] * (acc - mean[:, None] * torch.from_numpy(csum.astype(np.float64))[None])
+        else:
+            a.mu, a.rstd = ptr(mu), ptr(rstd)
+            want = torch.from_numpy(rstd.astype(np.float64))[:, None] * (acc - torch.from_numpy(mu.astype(np.float64))[:, None] * torch.from_numpy(csum.astype(np.float64))[None])
+    want = want + torch.from_numpy(bias.astype(np.float64))
+    if n_uncond:
+        nullc = rnd(N).float().numpy()
+        keep.append(nullc)
+        a.nullc, a.n_uncond = ptr(nullc), n_uncond
+        want[:n_uncond] += torch.from_numpy(nullc.astype(np.float64))
+    if act == ACT_SILU:
+        want = torch.nn.functional.silu(want)
+    elif act == ACT_GELU:
+        want = torch.nn.functional.gelu(want)
+    if res == "bf16":
+        r = bf16_bits(rnd(M, N))
+        keep.append(r)
+        a.res, a.ldr = ptr(r), N
+        want = want + bits_to_f64(r)
+    elif res == "f32mod":
+        mod = 88
+        r = np.ascontiguousarray(rnd(mod, N).float().numpy())
+        keep.append(r)
+        a.res, a.ldr, a.res_mod, a.res_f32 = ptr(r), N, mod, 1
+        want = want + torch.from_numpy(r.astype(np.float64))[torch.arange(M) % mod]
+    if out_f32:
+        out = np.full((M, N), np.nan, np.float32)
+    else:
+        out = np.full((M, N), 0x7FC0, np.int16)            # bf16 NaN: unwritten outputs are caught
+    a.out, a.ldo, a.out_f32 = ptr(out), N, int(out_f32)
+    out2 = None
+    if dup:
+        out2 = np.full((M, N), 0x7FC0, np.int16)
+        a.out2 = ptr(out2)
+    if stats_out:
+        ps_o = np.full((M, N // 64, 2), np.nan, np.float32)
+        a.ps_out = ptr(ps_o)
+        extras["ps_out"] = ps_o
+    a.num_sms, a.bn_force, a.cg_force = num_sms, bn, cg
+    L = lib or emu.gemm_lib()
+    rc = L.emu_gemm_tc(ctypes.byref(a))
+    assert rc == 0, L.emu_gemm_last_error().decode()
+    got = torch.from_numpy(out).double() if out_f32 else bits_to_f64(out)
+    if dup:
+        assert np.array_equal(out, out2)
+    extras["want_f64"] = want
+    return got, want, extras
+
+
+def check(got, want, out_f32=False, tanh_gelu=False):
+    assert torch.isfinite(got).all(), "an output element was never written"
+    err = float((got - want).abs().max() / want.abs().max())
+    # fp32 accumulation of bf16 products + (bf16 output rounding 2^-9 | tanh-form GELU 5e-4)
+    assert err < (2e-5 if out_f32 else (8e-3 if not tanh_gelu else 9e-3)), err
+
+
+def test_single_cta_bias_only_smoke():
+    got, want, _ = run_gemm(256, 256, [128], cg=1)
+    check(got, want)
+
+
+# (M, N, segment widths, options): every epilogue variant launch_gemm_tc dispatches for the engine, single CTAs and CTA pairs,
+# ragged M / N / K, persistent walks with more tiles than CTAs (accumulator and stage parities wrap several times)
+CASES = [
+    # single-CTA kernels (BN = 256 and 128)
+    dict(M=300, N=512, ks=[192], cg=1, num_sms=2),                                   # 3 x 2 tiles on 2 CTAs
+    dict(M=129, N=128, ks=[64], cg=1, res="bf16"),                                   # BN = 128, TMA residual boxes
+    dict(M=77, N=103, ks=[129], cg=1, out_f32=True),                                 # ragged everything, fp32 scalar stores
+    dict(M=200, N=256, ks=[256], cg=1, ln=True, act=ACT_SILU),
+    dict(M=140, N=512, ks=[232], cg=1, res="f32mod", dup=True, num_sms=2),           # joint_embed + PE, dual store (CFG halves)
+    dict(M=260, N=384, ks=[128], cg=1, act=ACT_GELU),                                # N % 256 != 0 -> BN = 128
+    # CTA pairs (cta_group::2), K = 512 class: 4 stages, wide boxes
+    dict(M=600, N=512, ks=[512], cg=2, num_sms=4, res="bf16", stats_out=True, n_uncond=300),   # sa_out / ffn_out (+ LN partials, nullc)
+    dict(M=520, N=768, ks=[512], cg=2, num_sms=4, ln=True),                           # qkv-like, 3 n-tiles, ragged last pair
+    dict(M=512, N=512, ks=[512], cg=2, num_sms=2, ln=True, ps_in=True),               # statistics rebuilt from producer partials
+    dict(M=300, N=1024, ks=[512], cg=2, num_sms=4, act=ACT_GELU),                     # ffn1
+    # CTA pairs, K >= 768 class: deep ring, narrow (2 KB) boxes without residual, wide with
+    dict(M=520, N=512, ks=[1024], cg=2, num_sms=2),                                   # ffn2: 6 stages, narrow boxes
+    dict(M=300, N=512, ks=[1024], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=100),   # feat2: 5 stages, wide boxes
+    dict(M=270, N=1024, ks=[512, 128, 128, 103], cg=2, num_sms=4, ln=True, act=ACT_SILU),        # feat1: virtual concat, 999 -> 1024
+    dict(M=256, N=256, ks=[768], cg=2, num_sms=2, dup=True),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "M{M}-N{N}-K{k}-cg{cg}{x}".format(
+    M=c["M"], N=c["N"], k="+".join(map(str, c["ks"])), cg=c["cg"],
+    x="".join("-" + k for k in ("ln", "res", "out_f32", "dup", "stats_out", "ps_in") if c.get(k)) + ("-act%d" % c["act"] if c.get("act") else "")))
+def test_gemm_kernel_source_on_emulator(case):
+    c = dict(case)
+    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
+    got, want, extras = run_gemm(M, N, ks, **c)
+    check(got, want, out_f32=c.get("out_f32", False), tanh_gelu=c.get("act") == ACT_GELU)
+    if "ps_out" in extras:   # per-row, per-64-column (sum, sum of squares) of the values the epilogue stored (before bf16 rounding)
+        w = extras["want_f64"].reshape(M, N // 64, 64)
+        ps = torch.from_numpy(extras["ps_out"]).double()
+        assert torch.isfinite(ps).all()
+        assert float((ps[..., 0] - w.sum(-1)).abs().max()) < 2e-3 * float(w.abs().sum(-1).max())
+        assert float((ps[..., 1] - (w * w).sum(-1)).abs().max()) < 2e-3 * float((w * w).sum(-1).max())
+
+
+ADVERSARIAL = [dict(M=600, N=512, ks=[512], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=300),
+               dict(M=520, N=512, ks=[1024], cg=2, num_sms=2),
+               dict(M=300, N=512, ks=[192], cg=1, num_sms=2, ln=True)]
+
+
+@pytest.mark.parametrize("slow", ["EMU_DELAY_TMEM_LD", "EMU_DELAY_TMA", "EMU_DELAY_MMA"])
+@pytest.mark.parametrize("case", ADVERSARIAL, ids=["pair-k512-res", "pair-k1024-narrow", "cta1-ln"])
+def test_gemm_pipeline_protocol_under_adversarial_timing(case, slow, monkeypatch):
+    """The round-robin emulator makes producer, MMA issuer and epilogue equally fast.  Slowing ONE role down (it sits out 40
+    scheduler passes before each of its operations) forces the interleavings in which a protocol bug shows -- e.g. handing a
+    TMEM accumulator back before its last tcgen05.ld corrupts the output under EMU_DELAY_TMEM_LD (checked by mutation when
+    the knob was added).  The real kernel must be insensitive to all of them."""
+    monkeypatch.setenv(slow, "40")
+    c = dict(case)
+    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
+    got, want, _ = run_gemm(M, N, ks, **c)
+    check(got, want)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["cg"] == 2 and c["ks"] == [512]], ids=lambda c: f"M{c['M']}-N{c['N']}")
+def test_k512_deep_ring_experiment_build(case):
+    """-DDSHEG_K512_DEEP=1 (scripts/build_variants.sh): K = 512 pair kernels with a fifth stage, no alignment slack and
+    single-buffered epilogue vectors -- never run on hardware; its barrier bookkeeping is checked here."""
+    c = dict(case)
+    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
+    got, want, _ = run_gemm(M, N, ks, lib=emu.gemm_lib("DSHEG_K512_DEEP=1"), **c)
+    check(got, want, tanh_gelu=c.get("act") == ACT_GELU)
