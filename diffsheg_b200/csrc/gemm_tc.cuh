@@ -17,7 +17,7 @@
 //   * A is a VIRTUAL CONCAT of up to 4 row-major segments (one tensor map each): the feat_proj input
 //     cat(h, audio, hubert, expr) (transformer.py:304-310) is never materialised.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-3 idle, 4.. = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-3 idle (2 = W producer in the split-ring build), 4.. = epilogue.
 #pragma once
 #include <unordered_map>
 
@@ -60,7 +60,21 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cf
 #ifndef DSHEG_K512_DEEP
 #define DSHEG_K512_DEEP 0
 #endif
-  static constexpr bool AT_LIMIT = CG == 2 && (LONGK || DSHEG_K512_DEEP);
+  // -DDSHEG_SPLIT_RINGS=1 (experiment build): the K = 512 pair kernels stage A and W in SEPARATE rings with separate producer
+  // threads -- a DEEP A ring (the A panel streams from HBM: ~1.2 us of latency to cover; round 1's L2 prefetch of the next A
+  // panel gave +15 % on ffn1) and a SHALLOW W ring (W panels are L2-resident).  Same smem as 5 unified stages buys 7 A + 3 W.
+#ifndef DSHEG_SPLIT_RINGS
+#define DSHEG_SPLIT_RINGS 0
+#endif
+#ifndef DSHEG_SPLIT_A
+#define DSHEG_SPLIT_A 7
+#endif
+#ifndef DSHEG_SPLIT_W
+#define DSHEG_SPLIT_W 3
+#endif
+  static constexpr bool SPLIT = CG == 2 && !LONGK && DSHEG_SPLIT_RINGS;
+  static constexpr int SA = DSHEG_SPLIT_A, SW = DSHEG_SPLIT_W;
+  static constexpr bool AT_LIMIT = CG == 2 && (LONGK || DSHEG_K512_DEEP || SPLIT);
   static constexpr int STAGES = CG == 2 ? (LONGK ? (NARROW ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES + (DSHEG_K512_DEEP ? 1 : 0))
                                         : (BN == 128 ? 5 : 3);
   // pair kernels run at the smem limit: the dynamic smem base is required to be 1024-aligned (checked, traps otherwise)
@@ -71,7 +85,9 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cf
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
   static constexpr int VEC_BYTES = NVEC * 2 * BN * 4;
-  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int PIPE_BYTES = SPLIT ? SA * A_BYTES + SW * B_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int NBAR_RING = SPLIT ? 2 * (SA + SW) : 2 * STAGES;   // ring barriers (full + empty)
+  static_assert((NBAR_RING + 2 * NUM_ACC + NE + 1) * 8 <= BAR_BYTES, "barrier block too small");
   static constexpr int SMEM_BYTES = PIPE_BYTES + NE * STG_BYTES + ALIGN_SLACK + BAR_BYTES + VEC_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -156,10 +172,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t bar_base = stg_base + NE * STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
-  auto res_bar = [&](int e) { return bar_base + 8u * (2 * STAGES + 2 * NUM_ACC + e); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC + NE);
+#if DSHEG_SPLIT_RINGS
+  // split rings (C::SPLIT): [full_a SA][empty_a SA][full_w SW][empty_w SW] take the place of [full STAGES][empty STAGES]
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto empty_a = [&](int s) { return bar_base + 8u * (C::SA + s); };
+  auto full_w = [&](int s) { return bar_base + 8u * (2 * C::SA + s); };
+  auto empty_w = [&](int s) { return bar_base + 8u * (2 * C::SA + C::SW + s); };
+#endif
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (C::NBAR_RING + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (C::NBAR_RING + NUM_ACC + a); };
+  auto res_bar = [&](int e) { return bar_base + 8u * (C::NBAR_RING + 2 * NUM_ACC + e); };
+  const uint32_t tmem_slot = bar_base + 8u * (C::NBAR_RING + 2 * NUM_ACC + NE);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - smem_base));
   float* vecs = reinterpret_cast<float*>(gen_base + (bar_base - smem_base) + BAR_BYTES);  // [NUM_ACC][2][BN]
 
@@ -167,6 +190,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
+#if DSHEG_SPLIT_RINGS
+    if (C::SPLIT) { for (int s = 0; s < 2 * (C::SA + C::SW); ++s) mbar_init(bar_base + 8u * s, 1); } else
+#endif
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NE * CG); }
     for (int e = 0; e < NE; ++e) mbar_init(res_bar(e), 1);
@@ -184,6 +210,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+#if DSHEG_SPLIT_RINGS   // experiment build only: the default translation unit is token-identical to the validated kernel
+  if (C::SPLIT && (warp == 0 || warp == 2)) {
+    // ================= split rings: warp 0 streams A (deep ring), warp 2 streams W (shallow ring) =================
+    if (lane == 0) {
+      const bool is_a = warp == 0;
+      const int nst = is_a ? C::SA : C::SW;
+      const uint32_t ring0 = is_a ? smem_base : smem_base + C::SA * A_BYTES;
+      const uint32_t slot_bytes = is_a ? A_BYTES : C::B_BYTES;
+      const uint32_t full0 = is_a ? full_a(0) : full_w(0), empty0 = is_a ? empty_a(0) : empty_w(0);
+      const uint32_t leader_full0 = mapa_rank(full0, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+        const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
+        int seg = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          while (kb >= p.seg_kb_start[seg + 1]) ++seg;
+          mbar_wait(empty0 + 8u * stage, phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(full0 + 8u * stage, 2 * slot_bytes);   // both CTAs' bytes land on the leader's barrier
+          const uint32_t dst = ring0 + stage * slot_bytes, lb = leader_full0 + 8u * stage;
+          if (is_a) {
+            const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
+            tma_load_2d_pair(ma, lb, dst, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
+          } else {
+            tma_load_2d_pair(&tmW, lb, dst, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else
+#endif
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -228,15 +286,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ================= MMA issuer =================
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
+#if DSHEG_SPLIT_RINGS
+      int wstage = 0; uint32_t wphase = 0;   // W ring of the split-ring build
+#endif
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
+#if DSHEG_SPLIT_RINGS
+          if (C::SPLIT) { mbar_wait(full_a(stage), phase); mbar_wait(full_w(wstage), wphase); } else
+#endif
           mbar_wait(full_bar(stage), phase);        // TMA bytes have landed
           tc_fence_after();
+#if DSHEG_SPLIT_RINGS
+          const uint32_t sa = C::SPLIT ? smem_base + stage * A_BYTES : smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = C::SPLIT ? smem_base + C::SA * A_BYTES + wstage * C::B_BYTES : sa + A_BYTES;
+#else
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#endif
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -244,6 +313,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (CG == 2) tc_mma_bf16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
             else tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
           }
+#if DSHEG_SPLIT_RINGS
+          if (C::SPLIT) {   // frees the A slot and the W slot (in both CTAs) when the MMAs retire
+            tc_commit_pair(empty_a(stage)); tc_commit_pair(empty_w(wstage));
+            if (++stage == C::SA) { stage = 0; phase ^= 1; }
+            if (++wstage == C::SW) { wstage = 0; wphase ^= 1; }
+            continue;
+          }
+#endif
           if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));  // frees the smem slot(s) when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

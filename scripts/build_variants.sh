@@ -11,4 +11,7 @@ build() { echo "building $1: $2"; $NVCC $FLAGS $2 -o build_variants/libdiffsheg_
 build k512deep "-DDSHEG_K512_DEEP=1" &     # K = 512 pair GEMMs: 5 stages with wide epilogue boxes
 build stages3 "-DDSHEG_PAIR_STAGES=3" &    # control: one stage less everywhere (reproduces the round-1 sweep direction)
 wait
+build split73 "-DDSHEG_SPLIT_RINGS=1" &                                    # K = 512 pair GEMMs: A ring 7 deep, W ring 3 deep, two producers
+build split64 "-DDSHEG_SPLIT_RINGS=1 -DDSHEG_SPLIT_A=6 -DDSHEG_SPLIT_W=4" &
+wait
 ls -la build_variants

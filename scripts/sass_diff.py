@@ -2,6 +2,7 @@
 """Compare two builds of the library kernel by kernel at the SASS level: `sass_diff.py old.so new.so`.
 Lists kernels whose instruction stream changed, disappeared or is new -- the check used before committing a refactor of
 hardware-validated kernels while no GPU is available (an identical instruction stream cannot change behaviour)."""
+import collections
 import re
 import subprocess
 import sys
@@ -23,8 +24,14 @@ def kernels(lib):
 
 if __name__ == "__main__":
     a, b = kernels(sys.argv[1]), kernels(sys.argv[2])
-    changed = [k for k in a if k in b and a[k] != b[k]]
-    print(f"{len(a)} -> {len(b)} kernels; identical: {sum(1 for k in a if k in b and a[k] == b[k])}")
+    def opcodes(ins):   # mnemonic + modifiers, operands and predicates dropped: invariant under register renaming / scheduling
+        return collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", i).split()[0] for i in ins)
+
+    differ = [k for k in a if k in b and a[k] != b[k]]
+    changed = [k for k in differ if opcodes(a[k]) != opcodes(b[k])]
+    realloc = [k for k in differ if opcodes(a[k]) == opcodes(b[k])]
+    print(f"{len(a)} -> {len(b)} kernels; identical: {sum(1 for k in a if k in b and a[k] == b[k])}; "
+          f"same opcode mix, different register allocation / order: {len(realloc)}")
     for title, ks in (("changed", changed), ("removed", [k for k in a if k not in b]), ("new", [k for k in b if k not in a])):
         for k in ks:
             print(f"  {title}: {k}  ({len(a.get(k, []))} -> {len(b.get(k, []))} instructions)")

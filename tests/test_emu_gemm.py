@@ -225,3 +225,24 @@ def test_k512_deep_ring_experiment_build(case):
     M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
     got, want, _ = run_gemm(M, N, ks, lib=emu.gemm_lib("DSHEG_K512_DEEP=1"), **c)
     check(got, want, tanh_gelu=c.get("act") == ACT_GELU)
+
+
+@pytest.mark.parametrize("rings", [(7, 3), (2, 1), (3, 5)], ids=lambda r: f"A{r[0]}W{r[1]}")
+@pytest.mark.parametrize("case", [c for c in CASES if c["cg"] == 2 and c["ks"] == [512]], ids=lambda c: f"M{c['M']}-N{c['N']}")
+def test_split_ring_experiment_build(case, rings):
+    """-DDSHEG_SPLIT_RINGS=1: separate A (deep) and W (shallow) rings with separate producer threads for the K = 512 pair
+    kernels (never run on hardware).  Ring depths that do not divide the 8 k-blocks of a tile make the two stage counters
+    wrap at different times; (2, 1) is the minimal pipeline."""
+    c = dict(case)
+    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
+    L = emu.gemm_lib("DSHEG_SPLIT_RINGS=1", f"DSHEG_SPLIT_A={rings[0]}", f"DSHEG_SPLIT_W={rings[1]}")
+    got, want, _ = run_gemm(M, N, ks, lib=L, **c)
+    check(got, want, tanh_gelu=c.get("act") == ACT_GELU)
+
+
+@pytest.mark.parametrize("slow", ["EMU_DELAY_TMEM_LD", "EMU_DELAY_TMA", "EMU_DELAY_MMA"])
+def test_split_ring_build_under_adversarial_timing(slow, monkeypatch):
+    monkeypatch.setenv(slow, "40")
+    L = emu.gemm_lib("DSHEG_SPLIT_RINGS=1", "DSHEG_SPLIT_A=7", "DSHEG_SPLIT_W=3")
+    got, want, _ = run_gemm(600, 512, [512], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=300, lib=L)
+    check(got, want)
