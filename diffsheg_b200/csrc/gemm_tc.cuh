@@ -714,9 +714,11 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
       pf = e ? atoi(e) : 0;
       // 2 = W-fill-skipping TIMING experiment (wrong results): only honoured together with an explicit opt-in
       if (pf == 2 && !getenv("DSHEG_ALLOW_TIMING_EXPERIMENTS")) pf = 0;
-      if (pf < 0 || pf > 2) pf = 0;
+      if (pf < 0 || pf > 3) pf = 0;
     }
-    p.prefetch = pf;
+    // 3 = selective: only the tensor-bound GEMMs without a residual stream (round 1, global prefetch: ffn1 +15 %, but the
+    // HBM-bound residual GEMMs lost 9 % because the prefetch competes with their residual / output traffic)
+    p.prefetch = pf == 3 ? ((d.res || d.out_f32) ? 0 : 1) : pf;
   }
   if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, longk);
   return bn == 256 ? dispatch<256, 1>(d, maps, p, grid, st, err) : dispatch<128, 1>(d, maps, p, grid, st, err);
