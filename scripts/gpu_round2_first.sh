@@ -1,31 +1,54 @@
 #!/bin/bash
-# FIRST gpurun call of round 2: everything written after round 1's GPU budget ran out, in one box session.
-#   1. full racecheck log of the CTA-pair GEMMs (B=24), see profiles/r01/NOTES_next_round.md "Open: racecheck"
-#   2. the gated tests (postprocess kernels, attention v4) with DSHEG_RUN_UNVALIDATED=1
-#   3. attention v3 vs v4 inside the real loop (bench.py, same box, back to back) + memcheck/racecheck of v4
-#   4. post-processing bandwidth
+# FIRST gpurun call of the next round: everything written while no GPU was available, in ONE box session (~12 min).
+# All of it is CPU-validated on the thread-level emulator (tests/test_emu_*.py); this call gives the hardware verdict and the
+# numbers that decide which candidates become defaults.
+#   1. first_hw_run.py   : post-processing kernels, attention v4 / v5c1 / v5c2 / v5c4 -- op parity, agreement with the default
+#                          inside dsheg_denoise, attention GB/s per variant at B = 3 and B = 950 (one subprocess per variant)
+#   2. GEMM candidates   : isolated shape sweep + full bench.py per experiment build (DSHEG_LIB) and prefetch mode
+#   3. bench.py          : default vs the best attention variant, back to back on this box
+#   4. racecheck         : full log of the CTA-pair GEMMs at B = 24 (open item in profiles/r01/NOTES_next_round.md)
+# Usage: bash scripts/build_variants.sh   (here, no GPU needed; the .so files travel)   then
+#        gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
-timeout 300 compute-sanitizer --tool racecheck python scripts/prof_denoise.py --batch 24 --calls 1 > gpurun_out/r2_racecheck_pairs_B24.log 2>&1
-echo "racecheck pairs rc=$?" > gpurun_out/r2_rc.txt
-DSHEG_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_postprocess.py tests/test_gpu_parity.py -m gpu -q -s -k "postprocess or gpu_inv or gpu_axis or op_attention_bf16" > gpurun_out/r2_unvalidated_tests.log 2>&1
-echo "unvalidated tests rc=$?" >> gpurun_out/r2_rc.txt
-DSHEG_ATTN=v4 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_denoise.py --batch 3 --calls 1 > gpurun_out/r2_v4_memcheck.log 2>&1
-echo "v4 memcheck rc=$?" >> gpurun_out/r2_rc.txt
-DSHEG_ATTN=v4 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/prof_denoise.py --batch 2 --calls 1 > gpurun_out/r2_v4_racecheck.log 2>&1
-echo "v4 racecheck rc=$?" >> gpurun_out/r2_rc.txt
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_attn_v3.json 2> gpurun_out/r2_bench_attn_v3.err
-DSHEG_ATTN=v4 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_attn_v4.json 2> gpurun_out/r2_bench_attn_v4.err
-timeout 300 python scripts/bench_postprocess.py > gpurun_out/r2_postprocess_bw.txt 2>&1
-cat gpurun_out/r2_rc.txt
-grep -c "Race reported\|hazard" gpurun_out/r2_racecheck_pairs_B24.log; grep -E "Write access|Read access" gpurun_out/r2_racecheck_pairs_B24.log | sed 's/(CUtensorMap.*//' | sort | uniq -c | sort -rn | head -8
-tail -3 gpurun_out/r2_unvalidated_tests.log
+O=gpurun_out
+[ -f build_variants/libdiffsheg_b200_split73.so ] || bash scripts/build_variants.sh > $O/r2_build_variants.log 2>&1
+timeout 700 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
+
+# ---- GEMM candidates: isolated sweep (dsheg_bench_gemm, 10 iterations per shape) and the real loop
+for v in default k512deep split73 split64; do
+  lib=""; [ $v != default ] && lib="$PWD/build_variants/libdiffsheg_b200_$v.so"
+  DSHEG_LIB=$lib timeout 200 python scripts/bench_gemm.py > $O/r2_gemm_sweep_$v.txt 2>&1
+  DSHEG_LIB=$lib timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_$v.json 2> $O/r2_bench_gemm_$v.err
+done
+DSHEG_TC_PREFETCH=3 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_prefetch3.json 2> $O/r2_bench_gemm_prefetch3.err
+DSHEG_TC_PREFETCH=3 DSHEG_LIB=$PWD/build_variants/libdiffsheg_b200_split73.so timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_split73_prefetch3.json 2> $O/r2_bench_gemm_split73_prefetch3.err
+
+# ---- attention variants in the real loop
+for a in v4 v5c1 v5c2 v5c4; do
+  DSHEG_ATTN=$a timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_$a.json 2> $O/r2_bench_attn_$a.err
+done
+
+# ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)
+for a in v5c1 v5c2 v5c4; do
+  DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_denoise.py --batch 3 --calls 1 > $O/r2_${a}_memcheck.log 2>&1; echo "$a memcheck rc=$?" >> $O/r2_rc.txt
+  DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/prof_denoise.py --batch 2 --calls 1 > $O/r2_${a}_racecheck.log 2>&1; echo "$a racecheck rc=$?" >> $O/r2_rc.txt
+done
+timeout 300 compute-sanitizer --tool racecheck python scripts/prof_denoise.py --batch 24 --calls 1 > $O/r2_racecheck_pairs_B24.log 2>&1; echo "racecheck pairs rc=$?" >> $O/r2_rc.txt
+timeout 200 python scripts/bench_postprocess.py > $O/r2_postprocess_bw.txt 2>&1
+
+# ---- summary
+cat $O/r2_rc.txt
+grep -E "^(PASS|FAIL)" $O/r2_first_hw_run.log | cut -c1-220
 python - <<'PY'
-import json
-for v in ("v3", "v4"):
+import glob, json, os
+for f in sorted(glob.glob("gpurun_out/r2_bench_*.json")):
     try:
-        d = json.loads(open(f"gpurun_out/r2_bench_attn_{v}.json").read().strip().splitlines()[-1])
-        print(v, round(d["value"]), "frames/s; attention", d.get("roofline_attention", {}).get("achieved"), "GB/s")
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f"{os.path.basename(f):44s} {d['value']:10.0f} frames/s  gemm {d['roofline']['achieved']:7.1f} TF/s ({d['roofline']['ms_per_step']:6.1f} ms)"
+              f"  attention {d['roofline_attention']['achieved']:6.0f} GB/s ({d['roofline_attention']['ms_per_step']:6.1f} ms)  sm {d['clocks']['sm_mhz']}")
     except Exception as e:  # noqa: BLE001
-        print(v, "failed:", e)
+        print(os.path.basename(f), "failed:", e)
 PY
-cat gpurun_out/r2_postprocess_bw.txt
+for v in default k512deep split73 split64; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2 " $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
+grep -c "Race reported\|hazard" $O/r2_racecheck_pairs_B24.log; grep -E "Write access|Read access" $O/r2_racecheck_pairs_B24.log | sed 's/(CUtensorMap.*//' | sort | uniq -c | sort -rn | head -8
+cat $O/r2_postprocess_bw.txt
