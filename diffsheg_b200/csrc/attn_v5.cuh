@@ -79,10 +79,13 @@ __device__ __forceinline__ void load_q(const bf16* qhead, int row0, int T, int g
   else load_q_tile<false>(qhead, row0, T, g, q, qa);
 }
 
-template <int CL>
+// QPRE: the Q columns of `qkv` already hold the unnormalised row-softmax numerators exp(q - rowmax_head) and `qsum`
+// [rows][8] their per-(row, head) sums -- written by the QKV GEMM's ACT_QSOFT epilogue (gemm_tc.cuh), whose ALUs idle under the
+// tensor pipe.  Step 5 then feeds the loaded fragments straight to the tensor core (no max, no exp, no pack).
+template <int CL, bool QPRE = false>
 __global__ void __launch_bounds__(Cfg<CL>::NTHREADS, Cfg<CL>::CTAS_PER_SM)
 attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
-               const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+               const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld, const float* __restrict__ qsum = nullptr) {
   using C = Cfg<CL>;
   DSHEG_DYN_SMEM(sm, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -273,6 +276,15 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
   {
     const int mat = lane >> 3, rr = lane & 7;
     for (int mt = half; mt < n_mt; mt += 2) {
+      uint32_t pa[4][4];
+      float qs0 = 1.f, qs1 = 1.f;
+      if (QPRE) {
+        const int ra_ = mt * 16 + g, rb_ = ra_ + 8;
+        if (ra_ < T) qs0 = __ldg(qsum + (row0 + ra_) * 8 + head);
+        if (rb_ < T) qs1 = __ldg(qsum + (row0 + rb_) * 8 + head);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) { pa[ks][0] = qa[ks][0]; pa[ks][1] = qa[ks][1]; pa[ks][2] = qa[ks][2]; pa[ks][3] = qa[ks][3]; }
+      } else {
       // row max in packed bf16x2: registers [ks][0],[ks][2] belong to row g, [ks][1],[ks][3] to row g + 8
       uint32_t ma = BF2_NEG_INF, mb = BF2_NEG_INF;
 #pragma unroll
@@ -284,7 +296,6 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float n0 = -mx0 * L2E, n1 = -mx1 * L2E;
-      uint32_t pa[4][4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         pa[ks][0] = pack2(ex2f(fmaf(bf_lo(qa[ks][0]), L2E, n0)), ex2f(fmaf(bf_hi(qa[ks][0]), L2E, n0)));
@@ -292,13 +303,14 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         pa[ks][2] = pack2(ex2f(fmaf(bf_lo(qa[ks][2]), L2E, n0)), ex2f(fmaf(bf_hi(qa[ks][2]), L2E, n0)));
         pa[ks][3] = pack2(ex2f(fmaf(bf_lo(qa[ks][3]), L2E, n1)), ex2f(fmaf(bf_hi(qa[ks][3]), L2E, n1)));
       }
+      }
       if (mt + 2 < n_mt) load_q(qhead, (mt + 2) * 16, T, g, q, qa);  // prefetch under the MMAs
       float y[8][4], rs[4] = {0.f, 0.f, 0.f, 0.f};   // rs: row sums of the numerators = Q' . ones (rows g, g + 8 in [0], [2])
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) { y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f; }
 #pragma unroll
       for (int kd = 0; kd < 4; ++kd) {
-        mma_bf16(rs, pa[kd], BF2_ONES, BF2_ONES);
+        if (!QPRE) mma_bf16(rs, pa[kd], BF2_ONES, BF2_ONES);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {  // B fragments of two l n-tiles per ldmatrix.x4 from A^T[l][d]
           uint32_t b0, b1, b2, b3;
@@ -308,7 +320,7 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
           mma_bf16(y[2 * np + 1], pa[kd], b2, b3);
         }
       }
-      const float r0 = rcp_approx(rs[0]), r1 = rcp_approx(rs[2]);
+      const float r0 = rcp_approx(QPRE ? qs0 : rs[0]), r1 = rcp_approx(QPRE ? qs1 : rs[2]);
       const int ra = mt * 16 + g, rb = ra + 8;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -430,11 +442,11 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
 
 #ifndef DSHEG_EMU
 // host launcher: CL > 1 kernels run as thread-block clusters of CL CTAs (one cluster per sample)
-template <int CL>
+template <int CL, bool QPRE = false>
 inline cudaError_t launch_attn_v5(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
-                                  const float* ss, int ss_ld, cudaStream_t st) {
+                                  const float* ss, int ss_ld, cudaStream_t st, const float* qsum = nullptr) {
   using C = Cfg<CL>;
-  auto kern = attn_v5_kernel<CL>;
+  auto kern = attn_v5_kernel<CL, QPRE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -448,7 +460,7 @@ inline cudaError_t launch_attn_v5(const bf16* qkv, bf16* z, int n_samples, int T
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, qkv, z, T, ssB, ln_g, ln_b, ss, ss_ld);
+  return cudaLaunchKernelEx(&cfg, kern, qkv, z, T, ssB, ln_g, ln_b, ss, ss_ld, qsum);
 }
 #endif  // DSHEG_EMU
 

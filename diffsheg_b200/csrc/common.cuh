@@ -14,7 +14,9 @@ namespace dsheg {
 
 typedef __nv_bfloat16 bf16;
 
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+// ACT_QSOFT (tcgen05 engine, LN-fold GEMMs only): columns < GemmDesc::qsoft_cols are written as the UNNORMALISED row softmax
+// numerators exp(v - max over the 64-column head) and the per-(row, head) denominators go to GemmDesc::qsum; other columns plain
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QSOFT = 3 };
 
 // ---- activation-type traits: float (fp32 mode) or bf16 (bf16 mode) -------------------------
 template <typename T> struct AT;
@@ -85,6 +87,9 @@ struct GemmDesc {
   const float2* cs_in = nullptr;  // [M] (sum, sumsq) of the conditioning part of the virtual concat, or null
   int ps_slots = 0;
   int ps_P = 0;                   // number of elements the LayerNorm runs over
+  // ---- ACT_QSOFT: softmax_d(Q) numerators in the epilogue of the fused QKV projection (transformer.py:122) -------------
+  float* qsum = nullptr;          // [M][qsoft_cols / 64] row sums of the numerators (fp32)
+  int qsoft_cols = 0;             // leading columns (multiple of 64) that hold Q
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

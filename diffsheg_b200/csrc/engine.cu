@@ -88,6 +88,7 @@ struct dsheg_handle {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int state = 0; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
+  int qsoft = 0;               // DSHEG_QSOFT=1: ACT_QSOFT epilogue of the QKV GEMM + attn_v5<CL, QPRE> (experimental)
   int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
   int graph_max_rows = 4096;   // B*T above which launches are no longer the bottleneck
   float2 *PS, *CS;      // fused LayerNorm statistics: per-row / per-64-column partials, conditioning partials
@@ -322,6 +323,12 @@ struct Runner {
     gq.a[0] = seg(hcur, ldc, D); gq.nseg = 1; gq.M = rows;
     gq.csum = L.qkv.csum;
     gq.out = h->QKV; gq.ldo = 3 * D;
+    // DSHEG_QSOFT=1 (experimental, with attn_v5): softmax_d(Q) numerators + row sums come out of the QKV epilogue (tr:122);
+    // the fp32 row scratch of the generic attention kernel (unused on this path) holds the [rows][8] sums
+    const bool v5_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP &&
+                         h->attn_v2 >= 51 && h->attn_v2 <= 54;
+    const bool qpre = v5_attn && h->qsoft && h->gemm_engine == 1;
+    if (qpre) { gq.act = ACT_QSOFT; gq.qsum = h->Y32; gq.qsoft_cols = D; }
     if (gemm(gq, L.qkv, "qkv")) return 1;
     // K9 + K10 prologue: linear attention, then LN * (1+scale) + shift, SiLU
     const int n_samples = rows / T;
@@ -334,9 +341,17 @@ struct Runner {
       av4::attn_v4_kernel<<<2 * n_samples, av4::NTHREADS, av4::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 >= 51 && h->attn_v2 <= 54) {
       // attn_v5<CL>: instruction-diet kernel as 1 / 2 / 4 CTAs per sample (DSHEG_ATTN=v5c1 | v5c2 | v5c4; experimental)
-      cudaError_t le = h->attn_v2 == 51 ? av5::launch_attn_v5<1>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-                     : h->attn_v2 == 52 ? av5::launch_attn_v5<2>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-                                        : av5::launch_attn_v5<4>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
+      const bf16* qp = (const bf16*)h->QKV; bf16* zp = (bf16*)h->Z;
+      cudaError_t le;
+      if (qpre) {
+        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1, true>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
+           : h->attn_v2 == 52 ? av5::launch_attn_v5<2, true>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
+                              : av5::launch_attn_v5<4, true>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32);
+      } else {
+        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
+           : h->attn_v2 == 52 ? av5::launch_attn_v5<2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
+                              : av5::launch_attn_v5<4>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
+      }
       if (le != cudaSuccess) return fail(h, std::string("attn_v5 launch: ") + cudaGetErrorString(le));
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av2::D && H == av2::NH && T <= av2::TP && h->attn_v2 == 2) {
       av2::attn_v2_kernel<<<n_samples, 256, av2::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
@@ -556,6 +571,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (att && !strcmp(att, "v5c1")) h->attn_v2 = 51;  // attn_v5.cuh, 1 / 2 / 4 CTAs per sample (experimental)
   if (att && !strcmp(att, "v5c2")) h->attn_v2 = 52;
   if (att && !strcmp(att, "v5c4")) h->attn_v2 = 54;
+  const char* qso = getenv("DSHEG_QSOFT");
+  h->qsoft = (qso && !strcmp(qso, "1")) ? 1 : 0;   // Q row-softmax in the QKV GEMM epilogue (needs an attn_v5 variant)
   const char* gr = getenv("DSHEG_GRAPHS");
   if (gr && !strcmp(gr, "0")) h->use_graphs = 0;
   const char* fs = getenv("DSHEG_FUSE_STATS");

@@ -106,6 +106,7 @@ struct Params {
   float2* ps_out; const float* nullc; int n_uncond;
   const float2* ps_in; const float2* cs_in; int ps_slots; float ps_invP;
   int prefetch;
+  float* qsum; int qsoft_cols;   // ACT_QSOFT (appended: the offsets of the fields above are part of the validated kernels)
 };
 
 // ---- spin on an mbarrier phase (PTX primitives: tc_prims.cuh) ---------------------------------------------------------------
@@ -386,6 +387,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (RES == RES_BF16) { mbar_wait(res_bar(e), res_phase); res_phase ^= 1; }
+      if (ACT == ACT_QSOFT && LN && !OUTF32 && !NARROW && RES == RES_NONE && nc0 < p.qsoft_cols) {
+        // ---- softmax_d(Q) numerators (transformer.py:122): this warp's 64 columns are exactly one head of Q.  Two passes
+        //      over TMEM (reads are cheap, the GEMM's ALUs idle under the tensor pipe): row max, then exp2 + row sum.
+        //      The attention kernel multiplies by 1 / qsum after its Q'.A product, so nothing is normalised here.
+        const float* bvec = vb + cg * CPW;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int ch = 0; ch < CPW / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bvec + ch * 32 + j), c4 = *reinterpret_cast<const float4*>(bvec + BN + ch * 32 + j);
+            mx = fmaxf(mx, fmaxf(fmaxf(fmaf(rs, __uint_as_float(r[j]), fmaf(rm, c4.x, b4.x)), fmaf(rs, __uint_as_float(r[j + 1]), fmaf(rm, c4.y, b4.y))),
+                                 fmaxf(fmaf(rs, __uint_as_float(r[j + 2]), fmaf(rm, c4.z, b4.z)), fmaf(rs, __uint_as_float(r[j + 3]), fmaf(rm, c4.w, b4.w)))));
+          }
+        }
+        const float L2E = 1.4426950408889634f;
+        const float nmx = -mx * L2E;
+        float qs = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < CPW / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
+          if (ch == CPW / 32 - 1) {   // last TMEM read of this warp: hand the accumulator stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+            }
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bvec + ch * 32 + j), c4 = *reinterpret_cast<const float4*>(bvec + BN + ch * 32 + j);
+            v[j] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j]), fmaf(rm, c4.x, b4.x)), L2E, nmx));
+            v[j + 1] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j + 1]), fmaf(rm, c4.y, b4.y)), L2E, nmx));
+            v[j + 2] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j + 2]), fmaf(rm, c4.z, b4.z)), L2E, nmx));
+            v[j + 3] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j + 3]), fmaf(rm, c4.w, b4.w)), L2E, nmx));
+            qs += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
+            w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
+            w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
+            w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
+            *reinterpret_cast<uint4*>(stg_gen + lane * 128 + (((ch * 4 + u) ^ (lane & 7)) << 4)) = w;
+          }
+        }
+        if (row_ok) p.qsum[(size_t)m * (p.qsoft_cols / CPW) + (nc0 / CPW)] = qs;
+      } else
 #pragma unroll
       for (int ch = 0; ch < CPW / 32; ++ch) {
         uint32_t r[32];
@@ -636,6 +690,7 @@ inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Pa
     if (!ln && d.act == ACT_GELU) return launch_variant<BN, false, ACT_GELU, RES_NONE, false, CG, true>(maps, p, grid, st);
     if (!ln && d.act == ACT_SILU) return launch_variant<BN, false, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
   } else if (ln) {
+    if (d.act == ACT_QSOFT && res == RES_NONE) return launch_variant<BN, true, ACT_QSOFT, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
   } else {
@@ -702,6 +757,11 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   p.out = d.out; p.ldo = d.ldo; p.out2 = d.out2;
   p.ps_out = d.ps_out; p.nullc = d.nullc; p.n_uncond = d.n_uncond;
   p.ps_in = d.ps_in; p.cs_in = d.cs_in; p.ps_slots = d.ps_slots; p.ps_invP = d.ps_P > 0 ? 1.0f / (float)d.ps_P : 0.f;
+  p.qsum = d.qsum; p.qsoft_cols = d.qsoft_cols;
+  if (d.act == ACT_QSOFT && (!d.csum || !d.qsum || d.qsoft_cols <= 0 || (d.qsoft_cols % CPW) || d.qsoft_cols > d.N || d.res || d.out_f32 || d.out2 || d.Kp >= 768)) {
+    *err = "ACT_QSOFT needs an LN-fold bf16-output GEMM with K < 768, no residual / duplicate store, qsum and qsoft_cols % 64 == 0";
+    return cudaErrorInvalidValue;
+  }
   if ((d.ps_out || d.nullc) && (d.out_f32 || !d.res)) { *err = "fused LN statistics need a bf16-output residual GEMM"; return cudaErrorInvalidValue; }
   if (d.ps_in && (!d.csum || (d.ps_slots & 1))) { *err = "ps_in needs an LN-fold GEMM and an even slot count"; return cudaErrorInvalidValue; }
   const int tiles = p.tiles_m * p.tiles_n;

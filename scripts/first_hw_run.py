@@ -13,6 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]
+LOOP_ONLY = ["v5c1+qsoft", "v5c4+qsoft"]   # + DSHEG_QSOFT=1: Q row-softmax in the QKV GEMM epilogue (needs the whole denoiser)
 results = {}
 
 
@@ -48,10 +49,12 @@ def in_loop(batch, var):
     base = None
     for v in (None, var):
         name = f"denoise B={batch} attention={v or 'v3 (default)'}"
+        os.environ.pop("DSHEG_ATTN", None)
+        os.environ.pop("DSHEG_QSOFT", None)
         if v:
-            os.environ["DSHEG_ATTN"] = v
-        else:
-            os.environ.pop("DSHEG_ATTN", None)
+            os.environ["DSHEG_ATTN"] = v.split("+")[0]
+            if v.endswith("+qsoft"):
+                os.environ["DSHEG_QSOFT"] = "1"
         eng = FusedUniDiffuser(sd, cfg, precision="bf16", max_batch=batch, max_frames=T)
         eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
         out = torch.empty_like(inp["x_T"])
@@ -89,7 +92,7 @@ if __name__ == "__main__":
         child(sys.argv[2])
         sys.exit(0)
     pytest_items()
-    for var in VARIANTS:
+    for var in VARIANTS + LOOP_ONLY:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--variant", var], cwd=ROOT, capture_output=True, text=True,
                                timeout=150)

@@ -27,6 +27,10 @@ DSHEG_TC_PREFETCH=3 DSHEG_LIB=$PWD/build_variants/libdiffsheg_b200_split73.so ti
 for a in v4 v5c1 v5c2 v5c4; do
   DSHEG_ATTN=$a timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_$a.json 2> $O/r2_bench_attn_$a.err
 done
+# Q row-softmax moved into the QKV GEMM epilogue (ACT_QSOFT) + attn_v5<CL, QPRE>: watch BOTH the attention and the gemm column
+for a in v5c1 v5c4; do
+  DSHEG_ATTN=$a DSHEG_QSOFT=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_${a}_qsoft.json 2> $O/r2_bench_attn_${a}_qsoft.err
+done
 
 # ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)
 for a in v5c1 v5c2 v5c4; do

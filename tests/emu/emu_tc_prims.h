@@ -247,6 +247,7 @@ inline void trap() {
   ++emu::rt().progress;
   emu::yield();
 }
+inline float ex2_fast(float x) { return exp2f(x); }
 inline float tanh_fast(float x) { return tanhf(x); }
 
 }  // namespace tc

@@ -12,7 +12,7 @@ import torch
 
 import emu
 
-ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_QSOFT = 0, 1, 2, 3
 
 
 class Args(ctypes.Structure):
@@ -24,7 +24,8 @@ class Args(ctypes.Structure):
                 ("res_f32", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("out_f32", ctypes.c_int32),
                 ("out2", ctypes.c_void_p), ("ps_out", ctypes.c_void_p), ("nullc", ctypes.c_void_p), ("n_uncond", ctypes.c_int32),
                 ("ps_in", ctypes.c_void_p), ("cs_in", ctypes.c_void_p), ("ps_slots", ctypes.c_int32), ("ps_P", ctypes.c_int32),
-                ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32)]
+                ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32),
+                ("qsum", ctypes.c_void_p), ("qsoft_cols", ctypes.c_int32)]
 
 
 def bf16_bits(t):
@@ -44,7 +45,7 @@ def r64(k):
 
 
 def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, dup=False, stats_out=False, n_uncond=0,
-             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None):
+             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, qsoft_cols=0):
     """Builds operands like the engine does (K laid out per segment padded to 64), runs the emulated kernel, returns
     (got, want, extras)."""
     g = torch.Generator().manual_seed(seed)
@@ -108,6 +109,15 @@ def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, d
         keep.append(nullc)
         a.nullc, a.n_uncond = ptr(nullc), n_uncond
         want[:n_uncond] += torch.from_numpy(nullc.astype(np.float64))
+    extras["raw"] = want.clone()
+    if act == ACT_QSOFT:   # leading qsoft_cols columns: unnormalised softmax numerators per 64-column head + their row sums
+        qsum = np.full((M, qsoft_cols // 64), np.nan, np.float32)
+        keep.append(qsum)
+        a.qsum, a.qsoft_cols = ptr(qsum), qsoft_cols
+        qv = want[:, :qsoft_cols].reshape(M, -1, 64)
+        e = torch.exp(qv - qv.max(-1, keepdim=True).values)
+        extras["qsum"], extras["qsum_want"] = qsum, e.sum(-1)
+        want = torch.cat([e.reshape(M, qsoft_cols), want[:, qsoft_cols:]], 1)
     if act == ACT_SILU:
         want = torch.nn.functional.silu(want)
     elif act == ACT_GELU:
@@ -144,6 +154,7 @@ def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, d
     if dup:
         assert np.array_equal(out, out2)
     extras["want_f64"] = want
+    extras["out_bits"] = None if out_f32 else out
     return got, want, extras
 
 
@@ -246,3 +257,35 @@ def test_split_ring_build_under_adversarial_timing(slow, monkeypatch):
     L = emu.gemm_lib("DSHEG_SPLIT_RINGS=1", "DSHEG_SPLIT_A=7", "DSHEG_SPLIT_W=3")
     got, want, _ = run_gemm(600, 512, [512], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=300, lib=L)
     check(got, want)
+
+
+@pytest.mark.parametrize("M,N,qc,cg,num_sms", [(300, 768, 256, 1, 2), (520, 1536, 512, 2, 2), (300, 512, 512, 2, 2), (140, 384, 128, 1, 1)])
+def test_q_softmax_epilogue(M, N, qc, cg, num_sms):
+    """ACT_QSOFT (opt-in, DSHEG_QSOFT=1): the LN-fold QKV projection writes exp(q - rowmax_head) for the Q columns and the
+    per-(row, head) sums next to it (transformer.py:122 moved into the producing GEMM); K and V columns stay plain."""
+    got, want, ex = run_gemm(M, N, [512], ln=True, act=ACT_QSOFT, qsoft_cols=qc, cg=cg, num_sms=num_sms)
+    assert torch.isfinite(got).all()
+    # numerators are in (0, 1], plain columns O(1): compare both halves on their own scale
+    assert float((got[:, :qc] - want[:, :qc]).abs().max()) < 6e-3           # bf16 rounding of values <= 1 + exp of an fp32 argument
+    if qc < N:
+        assert float((got[:, qc:] - want[:, qc:]).abs().max() / want[:, qc:].abs().max()) < 8e-3
+    qs = torch.from_numpy(ex["qsum"]).double()
+    assert torch.isfinite(qs).all()
+    assert float(((qs - ex["qsum_want"]) / ex["qsum_want"]).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("variant", [151, 154])
+def test_qkv_epilogue_softmax_feeds_attention_end_to_end(variant):
+    """GEMM (ACT_QSOFT) -> attention (QPRE), both kernel sources on the emulator, against the float64 attention of the
+    float64 QKV projection: the pair of opt-in kernels implements transformer.py:119-128 + :92-96 together."""
+    import test_emu_kernels as tk
+    Bn, T = 2, 34
+    got, want, ex = run_gemm(Bn * T, 1536, [512], ln=True, act=ACT_QSOFT, qsoft_cols=512, cg=1, num_sms=2, seed=4)
+    qkv_dev = bits_to_f64(ex["out_bits"]).float().reshape(Bn, T, 1536)          # what the attention kernel reads
+    qsum = torch.from_numpy(ex["qsum"])
+    g, b = 1 + 0.1 * torch.randn(512), 0.1 * torch.randn(512)
+    ss = 0.5 * torch.randn(Bn, 1024)
+    z = tk.run_attention(variant, qkv_dev, g, b, ss, qsum=qsum)
+    ref = tk.reference(ex["raw"].reshape(Bn, T, 1536), g, b, ss)                   # reference() rounds its input to bf16 like the engine's QKV buffer
+    err = float((z - ref).abs().max() / ref.abs().max())
+    assert torch.isfinite(z).all() and err < 1.5e-2, err

@@ -20,14 +20,15 @@ def _from_bits(a):
     return torch.from_numpy(a.copy()).view(torch.bfloat16).double()
 
 
-def run_attention(variant, qkv, g, b, ss):
+def run_attention(variant, qkv, g, b, ss, qsum=None):
     Bn, T, _ = qkv.shape
     L = emu.lib()
     q = _bf16_bits(qkv)
+    qs = np.ascontiguousarray(qsum.float().numpy()) if qsum is not None else None
     z = np.zeros((Bn, T, 512), dtype=np.int16)
     gg, bb, s = (x.float().numpy().copy() for x in (g, b, ss))
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = L.emu_attention(variant, P(q), P(z), Bn, T, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1])
+    rc = L.emu_attention(variant, P(q), P(z), Bn, T, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], P(qs) if qs is not None else None)
     assert rc == 0, L.emu_last_error().decode()
     return _from_bits(z)
 
@@ -80,6 +81,24 @@ def test_cluster_variants_agree_with_their_single_cta_form(T):
             got = run_attention(variant, qkv, g, b, ss)
             assert float((got - base).abs().max() / base.abs().max()) < 8e-3   # <= 1 bf16 ulp of the largest output
             assert float((got != base).double().mean()) < 0.02
+
+
+@pytest.mark.parametrize("variant", [151, 152, 154])
+@pytest.mark.parametrize("Bn,T", [(2, 88), (1, 34), (1, 13)])
+def test_attention_with_q_softmax_done_by_the_gemm_epilogue(variant, Bn, T):
+    """QPRE: the Q columns arrive as unnormalised softmax numerators (bf16) with their fp32 row sums, as the QKV GEMM's
+    ACT_QSOFT epilogue writes them (tests/test_emu_gemm.py::test_q_softmax_epilogue); the result must equal the attention
+    of the ORIGINAL q."""
+    qkv, g, b, ss = _case(Bn, T, None, seed=3)
+    qkv = qkv.bfloat16().float()
+    want = reference(qkv, g, b, ss)
+    q = qkv[..., :512].double().view(Bn, T, 8, 64)
+    e = torch.exp(q - q.max(-1, keepdim=True).values)
+    pre = qkv.clone()
+    pre[..., :512] = e.reshape(Bn, T, 512).float()
+    got = run_attention(variant, pre, g, b, ss, qsum=e.sum(-1).reshape(Bn * T, 8))
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-2
 
 
 # ------------------------------------------------------------------------------------------------------------------------
