@@ -285,7 +285,9 @@ def run_ours(args):
                                    "ddim_sample_loop = 25 denoiser calls (CFG pair) + 25 fused DDIM updates",
                        "per_gpu_batch": B, "global_batch": total_B, "frames_per_step": frames, "parallelism": f"dp{world}",
                        "l2": "per-call activations (>1 GB) and conditioning (385 MB) exceed the 126 MB L2; no explicit flush",
-                       "precision": args.precision, "final_all_gather": world > 1},
+                       "precision": args.precision, "final_all_gather": world > 1,
+                       # experiment switches in effect (empty = the shipped defaults), so variant runs describe themselves
+                       "switches": {k: v for k, v in os.environ.items() if k.startswith("DSHEG_") and v}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world,
