@@ -79,14 +79,20 @@ __device__ __forceinline__ void load_q(const bf16* qhead, int row0, int T, int g
   else load_q_tile<false>(qhead, row0, T, g, q, qa);
 }
 
-// QPRE: the Q columns of `qkv` already hold the unnormalised row-softmax numerators exp(q - rowmax_head) and `qsum`
+// PRE = 1 (QPRE): the Q columns of `qkv` already hold the unnormalised row-softmax numerators exp(q - rowmax_head) and `qsum`
 // [rows][8] their per-(row, head) sums -- written by the QKV GEMM's ACT_QSOFT epilogue (gemm_tc.cuh), whose ALUs idle under the
 // tensor pipe.  Step 5 then feeds the loaded fragments straight to the tensor core (no max, no exp, no pack).
-template <int CL, bool QPRE = false>
+// PRE = 2 (EXPO): the Q AND K columns hold exp(value - static shift) (ACT_EXPO epilogue; softmax is shift-invariant and the
+// packer proves the exponent range, pack.py:expo_shift).  Step 3 (column maxima + exponentials of K) disappears, step 5 is the
+// QPRE one, and both denominators come out of the tensor core (ones . K', Q' . ones): no exp / max / pack is left in this
+// kernel outside the LayerNorm pass -- 56 k -> about 30 k warp-instructions per sample.
+template <int CL, int PRE = 0>
 __global__ void __launch_bounds__(Cfg<CL>::NTHREADS, Cfg<CL>::CTAS_PER_SM)
 attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
                const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld, const float* __restrict__ qsum = nullptr) {
   using C = Cfg<CL>;
+  constexpr bool QPRE = PRE == 1;     // Q numerators + their sums from global memory
+  constexpr bool EXPO = PRE == 2;     // Q and K numerators precomputed, sums on the tensor core
   DSHEG_DYN_SMEM(sm, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hl = warp >> 1, half = warp & 1;           // local head, warp of the pair
@@ -131,12 +137,14 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
   // ---- 2. this warp's first Q m-tile (global -> registers) overlaps the cp.async latency
   uint32_t qa[4][4];
   if (half < n_mt) load_q(qhead, half * 16, T, g, q, qa);
-  cp_async_wait_group<1>();   // this thread's K chunks have landed
-  pair_sync(hl);              // ... and the partner's
+  if (!EXPO) {
+    cp_async_wait_group<1>();   // this thread's K chunks have landed
+    pair_sync(hl);              // ... and the partner's
+  }
 
   // ---- 3. softmax over time per K column.  Lane = (row phase p, column quarter cq): rows r_lo + p + 8 i, columns
   //         16 cq .. 16 cq + 15 (two 16-byte chunks); (r & 7) is constant per lane, so is the swizzle.
-  {
+  if (!EXPO) {
     const int p = lane & 7, cq = lane >> 3;
     const int rsplit = (T + 1) >> 1;
     const int r_lo = half ? rsplit : 0, r_hi = half ? T : rsplit;
@@ -194,6 +202,8 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         *pb = make_uint4(e[4], e[5], e[6], e[7]);
       }
     }
+  }
+  {
     if (half == 1) {
       for (int i = lane; i < (Tpad - T) * 8; i += 32) {
         const int r = T + (i >> 3), cc = i & 7;
@@ -278,10 +288,12 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     for (int mt = half; mt < n_mt; mt += 2) {
       uint32_t pa[4][4];
       float qs0 = 1.f, qs1 = 1.f;
-      if (QPRE) {
-        const int ra_ = mt * 16 + g, rb_ = ra_ + 8;
-        if (ra_ < T) qs0 = __ldg(qsum + (row0 + ra_) * 8 + head);
-        if (rb_ < T) qs1 = __ldg(qsum + (row0 + rb_) * 8 + head);
+      if (QPRE || EXPO) {
+        if (QPRE) {
+          const int ra_ = mt * 16 + g, rb_ = ra_ + 8;
+          if (ra_ < T) qs0 = __ldg(qsum + (row0 + ra_) * 8 + head);
+          if (rb_ < T) qs1 = __ldg(qsum + (row0 + rb_) * 8 + head);
+        }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) { pa[ks][0] = qa[ks][0]; pa[ks][1] = qa[ks][1]; pa[ks][2] = qa[ks][2]; pa[ks][3] = qa[ks][3]; }
       } else {
@@ -320,8 +332,10 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
           mma_bf16(y[2 * np + 1], pa[kd], b2, b3);
         }
       }
-      const float r0 = rcp_approx(QPRE ? qs0 : rs[0]), r1 = rcp_approx(QPRE ? qs1 : rs[2]);
       const int ra = mt * 16 + g, rb = ra + 8;
+      // EXPO: zero-filled Q rows beyond T have zero sums (the other modes exponentiate the fill to 1): keep their Y rows at 0
+      const float r0 = (EXPO && ra >= T) ? 0.f : rcp_approx(QPRE ? qs0 : rs[0]);
+      const float r1 = (EXPO && rb >= T) ? 0.f : rcp_approx(QPRE ? qs1 : rs[2]);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         *reinterpret_cast<uint32_t*>(Vs + swz(ra, nt) + q * 4) = pack2(y[nt][0] * r0, y[nt][1] * r0);
@@ -442,11 +456,11 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
 
 #ifndef DSHEG_EMU
 // host launcher: CL > 1 kernels run as thread-block clusters of CL CTAs (one cluster per sample)
-template <int CL, bool QPRE = false>
+template <int CL, int PRE = 0>
 inline cudaError_t launch_attn_v5(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
                                   const float* ss, int ss_ld, cudaStream_t st, const float* qsum = nullptr) {
   using C = Cfg<CL>;
-  auto kern = attn_v5_kernel<CL, QPRE>;
+  auto kern = attn_v5_kernel<CL, PRE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);

@@ -16,7 +16,10 @@ typedef __nv_bfloat16 bf16;
 
 // ACT_QSOFT (tcgen05 engine, LN-fold GEMMs only): columns < GemmDesc::qsoft_cols are written as the UNNORMALISED row softmax
 // numerators exp(v - max over the 64-column head) and the per-(row, head) denominators go to GemmDesc::qsum; other columns plain
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QSOFT = 3 };
+// ACT_EXPO (tcgen05 engine, LN-fold GEMMs only): columns < GemmDesc::expo_cols are written as exp(v - eshift[n]) -- softmax
+// numerators with a STATIC shift (softmax is shift-invariant; the packer proves |v - eshift| <= 60 for every possible input,
+// diffsheg_b200/pack.py:expo_shift) -- so the attention kernel neither searches maxima nor exponentiates; other columns plain
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QSOFT = 3, ACT_EXPO = 4 };
 
 // ---- activation-type traits: float (fp32 mode) or bf16 (bf16 mode) -------------------------
 template <typename T> struct AT;
@@ -90,6 +93,9 @@ struct GemmDesc {
   // ---- ACT_QSOFT: softmax_d(Q) numerators in the epilogue of the fused QKV projection (transformer.py:122) -------------
   float* qsum = nullptr;          // [M][qsoft_cols / 64] row sums of the numerators (fp32)
   int qsoft_cols = 0;             // leading columns (multiple of 64) that hold Q
+  // ---- ACT_EXPO: exp(v - eshift[n]) for the leading expo_cols columns (Q and K of the fused QKV projection, tr:122-123) ---
+  const float* eshift = nullptr;  // [expo_cols] static per-column shifts (Q: 0, K: folded bias), fp32
+  int expo_cols = 0;              // leading columns (multiple of 64) written as exponentials
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -45,6 +45,7 @@ struct LinW {
 struct LayerW {
   LinW feat1, feat2, qkv, sa_out, ffn1, ffn2, ffn_out;
   const float* nullc = nullptr;
+  const float* qkv_eshift = nullptr;   // optional: static softmax shifts of the Q | K columns (pack.py:expo_shift), [2 D]
   const float *sa_g = nullptr, *sa_b = nullptr, *ffn_g = nullptr, *ffn_b = nullptr;
   bool has_feat = false;
 };
@@ -89,6 +90,7 @@ struct dsheg_handle {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   int qsoft = 0;               // DSHEG_QSOFT=1: ACT_QSOFT epilogue of the QKV GEMM + attn_v5<CL, QPRE> (experimental)
+  int expo = 0;                // DSHEG_EXPO=1: ACT_EXPO epilogue (Q and K softmax numerators with static shifts) + attn_v5<CL, 2> (experimental)
   int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
   int graph_max_rows = 4096;   // B*T above which launches are no longer the bottleneck
   float2 *PS, *CS;      // fused LayerNorm statistics: per-row / per-64-column partials, conditioning partials
@@ -205,6 +207,11 @@ struct Resolver {
       if (has_null) L.nullc = f32(p + ".nullc", {D});
     }
     L.qkv = lin(p + ".qkv", 3 * D, round_up(D, 64), true);
+    {   // optional tensor: the packer emits it only when it can prove the exponent range (absent => ACT_EXPO stays off for this layer)
+      auto it = h->tensors.find(p + ".qkv.eshift");
+      if (it != h->tensors.end() && it->second.dtype == DSHEG_DTYPE_F32 && it->second.shape == std::vector<int64_t>{2 * D})
+        L.qkv_eshift = reinterpret_cast<const float*>(it->second.ptr);
+    }
     L.sa_g = f32(p + ".sa.g", {D});
     L.sa_b = f32(p + ".sa.b", {D});
     L.sa_out = lin(p + ".sa_out", D, round_up(D, 64), false);
@@ -327,8 +334,12 @@ struct Runner {
     // the fp32 row scratch of the generic attention kernel (unused on this path) holds the [rows][8] sums
     const bool v5_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP &&
                          h->attn_v2 >= 51 && h->attn_v2 <= 54;
-    const bool qpre = v5_attn && h->qsoft && h->gemm_engine == 1;
+    // DSHEG_EXPO=1 (experimental, with attn_v5; wins over QSOFT): Q AND K numerators exp(v - static shift) from the epilogue
+    // (tr:122-123), for the layers whose packed weights carry provably safe shifts
+    const bool kpre = v5_attn && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
+    const bool qpre = v5_attn && h->qsoft && h->gemm_engine == 1 && !kpre;
     if (qpre) { gq.act = ACT_QSOFT; gq.qsum = h->Y32; gq.qsoft_cols = D; }
+    if (kpre) { gq.act = ACT_EXPO; gq.eshift = L.qkv_eshift; gq.expo_cols = 2 * D; }
     if (gemm(gq, L.qkv, "qkv")) return 1;
     // K9 + K10 prologue: linear attention, then LN * (1+scale) + shift, SiLU
     const int n_samples = rows / T;
@@ -343,10 +354,14 @@ struct Runner {
       // attn_v5<CL>: instruction-diet kernel as 1 / 2 / 4 CTAs per sample (DSHEG_ATTN=v5c1 | v5c2 | v5c4; experimental)
       const bf16* qp = (const bf16*)h->QKV; bf16* zp = (bf16*)h->Z;
       cudaError_t le;
-      if (qpre) {
-        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1, true>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
-           : h->attn_v2 == 52 ? av5::launch_attn_v5<2, true>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
-                              : av5::launch_attn_v5<4, true>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32);
+      if (kpre) {
+        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1, 2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
+           : h->attn_v2 == 52 ? av5::launch_attn_v5<2, 2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
+                              : av5::launch_attn_v5<4, 2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
+      } else if (qpre) {
+        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1, 1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
+           : h->attn_v2 == 52 ? av5::launch_attn_v5<2, 1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
+                              : av5::launch_attn_v5<4, 1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32);
       } else {
         le = h->attn_v2 == 51 ? av5::launch_attn_v5<1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
            : h->attn_v2 == 52 ? av5::launch_attn_v5<2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
@@ -573,6 +588,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (att && !strcmp(att, "v5c4")) h->attn_v2 = 54;
   const char* qso = getenv("DSHEG_QSOFT");
   h->qsoft = (qso && !strcmp(qso, "1")) ? 1 : 0;   // Q row-softmax in the QKV GEMM epilogue (needs an attn_v5 variant)
+  const char* exo = getenv("DSHEG_EXPO");
+  h->expo = (exo && !strcmp(exo, "1")) ? 1 : 0;    // Q and K numerators with static shifts in the QKV epilogue (needs an attn_v5 variant)
   const char* gr = getenv("DSHEG_GRAPHS");
   if (gr && !strcmp(gr, "0")) h->use_graphs = 0;
   const char* fs = getenv("DSHEG_FUSE_STATS");

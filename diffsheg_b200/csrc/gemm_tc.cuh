@@ -107,6 +107,7 @@ struct Params {
   const float2* ps_in; const float2* cs_in; int ps_slots; float ps_invP;
   int prefetch;
   float* qsum; int qsoft_cols;   // ACT_QSOFT (appended: the offsets of the fields above are part of the validated kernels)
+  const float* eshift; int expo_cols;   // ACT_EXPO (appended likewise)
 };
 
 // ---- spin on an mbarrier phase (PTX primitives: tc_prims.cuh) ---------------------------------------------------------------
@@ -352,6 +353,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         vb[i] = bv;
         if (LN) vb[BN + i] = n < p.N ? __ldg(p.csum + n) : 0.f;
         else if (RES != RES_NONE && p.nullc) vb[BN + i] = bv + (n < p.N ? __ldg(p.nullc + n) : 0.f);
+        if (ACT == ACT_EXPO && LN && n < p.expo_cols) {   // exponent columns: everything pre-scaled by log2(e), shift folded into the bias
+          vb[i] = (bv - __ldg(p.eshift + n)) * 1.4426950408889634f;
+          vb[BN + i] *= 1.4426950408889634f;
+        }
       }
       epi_bar_sync<NE * 32>();
       const int m0 = m_blk * BM + q * 32;     // first row of this warp's box
@@ -381,6 +386,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           rs = __ldg(p.rstd + m); rm = -rs * __ldg(p.mu + m);
         }
       }
+      // ACT_EXPO: this warp's 64 columns are exponent columns (Q or K) or plain ones (V) as a whole (expo_cols % 64 == 0);
+      // with the staged vectors pre-scaled, scaling rs alone yields log2(e) * (v - eshift) from the same two FFMAs
+      const bool expo = ACT == ACT_EXPO && LN && nc0 < p.expo_cols;
+      if (ACT == ACT_EXPO && expo) rs *= 1.4426950408889634f;
       // rows of the CFG-null half take bias + nullc (slot 1) instead of bias (slot 0)
       const int bsel = (!LN && RES != RES_NONE && p.nullc && m < p.n_uncond) ? BN : 0;
       float psum = 0.f, psq = 0.f;
@@ -465,6 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           } else {
             t0 += b4.x; t1 += b4.y; t2 += b4.z; t3 += b4.w;
           }
+          if (ACT == ACT_EXPO && expo) { t0 = ex2_fast(t0); t1 = ex2_fast(t1); t2 = ex2_fast(t2); t3 = ex2_fast(t3); }
           v[j] = act_fast<ACT>(t0); v[j + 1] = act_fast<ACT>(t1); v[j + 2] = act_fast<ACT>(t2); v[j + 3] = act_fast<ACT>(t3);
         }
         if (RES == RES_F32_MOD) {
@@ -691,6 +701,7 @@ inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Pa
     if (!ln && d.act == ACT_SILU) return launch_variant<BN, false, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
   } else if (ln) {
     if (d.act == ACT_QSOFT && res == RES_NONE) return launch_variant<BN, true, ACT_QSOFT, RES_NONE, false, CG>(maps, p, grid, st);
+    if (d.act == ACT_EXPO && res == RES_NONE) return launch_variant<BN, true, ACT_EXPO, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
   } else {
@@ -760,6 +771,11 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   p.qsum = d.qsum; p.qsoft_cols = d.qsoft_cols;
   if (d.act == ACT_QSOFT && (!d.csum || !d.qsum || d.qsoft_cols <= 0 || (d.qsoft_cols % CPW) || d.qsoft_cols > d.N || d.res || d.out_f32 || d.out2 || d.Kp >= 768)) {
     *err = "ACT_QSOFT needs an LN-fold bf16-output GEMM with K < 768, no residual / duplicate store, qsum and qsoft_cols % 64 == 0";
+    return cudaErrorInvalidValue;
+  }
+  p.eshift = d.eshift; p.expo_cols = d.expo_cols;
+  if (d.act == ACT_EXPO && (!d.csum || !d.eshift || d.expo_cols <= 0 || (d.expo_cols % CPW) || d.expo_cols > d.N || d.res || d.out_f32 || d.Kp >= 768)) {
+    *err = "ACT_EXPO needs an LN-fold bf16-output GEMM with K < 768, no residual, eshift and expo_cols % 64 == 0";
     return cudaErrorInvalidValue;
   }
   if ((d.ps_out || d.nullc) && (d.out_f32 || !d.res)) { *err = "fused LN statistics need a bf16-output residual GEMM"; return cudaErrorInvalidValue; }

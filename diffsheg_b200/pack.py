@@ -11,6 +11,8 @@ exact up to floating-point reassociation:
   (after bf16 rounding) so the subtraction cancels exactly.
 * ``*.nullc``: under classifier-free guidance the whole feat_proj input row of the uncond half is the
   learned ``null_cond_emb`` (tr:326-332), so feat_proj(null) is one constant vector per layer.
+* ``*.qkv.eshift`` (optional): static softmax shifts for the Q | K columns when ``expo_shift`` can prove the exponent range
+  for every possible input (enables the opt-in ACT_EXPO epilogue + attn_v5<CL, PRE = 2> pair).
 * ``*.hub``: BatchNorm1d (eval) folded into the first Conv1d of hubert_encoder (tr:436-442).
 * K axes of GEMM weights are laid out per A-segment, each padded to a multiple of 64
   (h | audio_proj | hubert | expr for feat1).
@@ -24,6 +26,31 @@ import numpy as np
 import torch
 
 F32, BF16 = 0, 1
+
+# ACT_EXPO (gemm_tc.cuh) writes softmax numerators exp(v - shift) with STATIC shifts; |v - shift| must stay below this bound
+# (natural-log units) for EVERY possible input, so that neither the numerators (e^+-60 = 1e+-26) nor their sums over up to
+# 96 frames / 64 channels, nor the K'^T V and Q' A products (|V| < 1e6), leave the fp32 / bf16 exponent range
+EXPO_LIMIT = 60.0
+
+
+def expo_shift(stored_w, bias, D):
+    """Static softmax shifts for the Q | K columns of an LN-folded QKV projection, or None when no safe ones exist.
+
+    The GEMM computes v[n] = xhat . W'[n] + b'[n] with xhat = (h - mean) * rstd, the LayerNorm-ed hidden row (tr:119-123):
+    sum(xhat) = 0 and ||xhat||_2 <= sqrt(P), whatever h is.  Cauchy-Schwarz on the centred weight row gives
+    |v[n] - b'[n]| <= R[n] = sqrt(P) * ||W'[n] - mean(W'[n])||_2  for every input.  softmax is shift-invariant, so
+      * K (softmax over time, tr:123, one shift per column): shift = b'[n], exponent within +-R[n];
+      * Q (softmax over the 64 channels of a head, tr:122, one shift per row and head): shift = 0, exponent within +-(R[n] + |b'[n]|)
+    are exact replacements for the running maxima as long as the exponents stay inside EXPO_LIMIT.  `stored_w` are the weights
+    AS STORED (bf16-rounded), so the bound is about the numbers the tensor core multiplies.  Returns [2 D] float64."""
+    P = stored_w.shape[1]
+    w = stored_w[:2 * D]
+    R = math.sqrt(P) * (w - w.mean(dim=1, keepdim=True)).norm(dim=1) * 1.01   # 1 %: fp32 accumulation and statistics
+    q_bound = (R[:D] + bias[:D].abs()).max()
+    k_bound = R[D:].max()
+    if not (torch.isfinite(R).all() and float(q_bound) <= EXPO_LIMIT and float(k_bound) <= EXPO_LIMIT):
+        return None
+    return torch.cat([torch.zeros(D, dtype=torch.float64), bias[D:2 * D].to(torch.float64)])
 
 
 def _r64(k):
@@ -76,6 +103,7 @@ class Packer:
         stored = self.put_w(name + ".w", Wp, widths)
         self.put_f32(name + ".b", b + W @ beta)
         self.put_f32(name + ".csum", stored.sum(dim=1))
+        return stored, b + W @ beta
 
     def mlp(self, name, key0, key2, pad_k=False):
         w0 = self.g(key0 + ".weight")
@@ -106,7 +134,10 @@ class Packer:
         sa = key + ".sa_block"
         Wqkv = torch.cat([g(sa + ".query.weight"), g(sa + ".key.weight"), g(sa + ".value.weight")], 0)
         bqkv = torch.cat([g(sa + ".query.bias"), g(sa + ".key.bias"), g(sa + ".value.bias")], 0)
-        self.lin_ln_fold(name + ".qkv", Wqkv, bqkv, g(sa + ".norm.weight"), g(sa + ".norm.bias"))
+        stored, bfold = self.lin_ln_fold(name + ".qkv", Wqkv, bqkv, g(sa + ".norm.weight"), g(sa + ".norm.bias"))
+        es = expo_shift(stored, bfold, Wqkv.shape[0] // 3)   # optional tensor: present only when static shifts are provably safe
+        if es is not None:
+            self.put_f32(name + ".qkv.eshift", es)
         self.put_f32(name + ".sa.g", g(sa + ".proj_out.norm.weight"))
         self.put_f32(name + ".sa.b", g(sa + ".proj_out.norm.bias"))
         self.lin(name + ".sa_out", sa + ".proj_out.out_layers.2")

@@ -1,5 +1,5 @@
 #!/bin/bash
-# FIRST gpurun call of the next round: everything written while no GPU was available, in ONE box session (~12 min).
+# FIRST gpurun call of the next round: everything written while no GPU was available, in ONE box session (~35 min).
 # All of it is CPU-validated on the thread-level emulator (tests/test_emu_*.py); this call gives the hardware verdict and the
 # numbers that decide which candidates become defaults.
 #   1. first_hw_run.py   : post-processing kernels, attention v4 / v5c1 / v5c2 / v5c4 -- op parity, agreement with the default
@@ -8,11 +8,11 @@
 #   3. bench.py          : default vs the best attention variant, back to back on this box
 #   4. racecheck         : full log of the CTA-pair GEMMs at B = 24 (open item in profiles/r01/NOTES_next_round.md)
 # Usage: bash scripts/build_variants.sh   (here, no GPU needed; the .so files travel)   then
-#        gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
+#        gpurun --timeout 2700 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
 O=gpurun_out
 [ -f build_variants/libdiffsheg_b200_split73.so ] || bash scripts/build_variants.sh > $O/r2_build_variants.log 2>&1
-timeout 700 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
+timeout 1300 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
 
 # ---- GEMM candidates: isolated sweep (dsheg_bench_gemm, 10 iterations per shape) and the real loop
 for v in default k512deep split73 split64; do
@@ -30,6 +30,12 @@ done
 # Q row-softmax moved into the QKV GEMM epilogue (ACT_QSOFT) + attn_v5<CL, QPRE>: watch BOTH the attention and the gemm column
 for a in v5c1 v5c4; do
   DSHEG_ATTN=$a DSHEG_QSOFT=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_${a}_qsoft.json 2> $O/r2_bench_attn_${a}_qsoft.err
+done
+
+# Q AND K softmax numerators with static, pack-time-proven shifts from the QKV epilogue (ACT_EXPO) + attn_v5<CL, 2>: the attention
+# kernel loses every exp / max outside its LayerNorm pass (static SASS 2872 -> 2096 for CL = 1); again watch BOTH columns
+for a in v5c1 v5c2 v5c4; do
+  DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_${a}_expo.json 2> $O/r2_bench_attn_${a}_expo.err
 done
 
 # ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)

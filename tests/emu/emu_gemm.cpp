@@ -26,6 +26,8 @@ struct EmuGemmArgs {
   int32_t num_sms, bn_force, cg_force;
   float* qsum;
   int32_t qsoft_cols;
+  const float* eshift;
+  int32_t expo_cols;
 };
 
 static std::string g_err;
@@ -43,6 +45,7 @@ extern "C" int emu_gemm_tc(const EmuGemmArgs* a) {
   d.ps_in = reinterpret_cast<const float2*>(a->ps_in); d.cs_in = reinterpret_cast<const float2*>(a->cs_in);
   d.ps_slots = a->ps_slots; d.ps_P = a->ps_P;
   d.qsum = a->qsum; d.qsoft_cols = a->qsoft_cols;
+  d.eshift = a->eshift; d.expo_cols = a->expo_cols;
   std::string terr;
   const cudaError_t e = tc::launch_gemm_tc(d, a->num_sms, nullptr, &terr, a->bn_force, a->cg_force);
   if (e != cudaSuccess) { g_err = terr + " " + tc::g_emu_error(); return 1; }

@@ -15,7 +15,8 @@ static std::string g_err;
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
 
 // variant: 3 = attn_v3 (one CTA per sample), 4 = attn_v4 (cluster of two half-sample CTAs), 51 / 52 / 54 = attn_v5<CL = 1 / 2 / 4>
-// 151 / 152 / 154 = attn_v5<CL, QPRE = true>: Q columns hold softmax numerators, `qsum` [rows][8] their sums (else unused)
+// 151 / 152 / 154 = attn_v5<CL, PRE = 1>: Q columns hold softmax numerators, `qsum` [rows][8] their sums (else unused)
+// 251 / 252 / 254 = attn_v5<CL, PRE = 2>: Q and K columns hold exp(value - static shift) (ACT_EXPO epilogue), no side table
 extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int n_samples, int T, int ssB, const float* ln_g,
                              const float* ln_b, const float* ss, int ss_ld, const float* qsum) {
   g_err.clear();
@@ -33,11 +34,17 @@ extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int 
   } else if (variant == 54) {
     ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
   } else if (variant == 151) {
-    ok = emu::run_grid(n_samples, av5::Cfg<1>::NTHREADS, 1, av5::Cfg<1>::SMEM_BYTES, [=] { av5::attn_v5_kernel<1, true>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
+    ok = emu::run_grid(n_samples, av5::Cfg<1>::NTHREADS, 1, av5::Cfg<1>::SMEM_BYTES, [=] { av5::attn_v5_kernel<1, 1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
   } else if (variant == 152) {
-    ok = emu::run_grid(2 * n_samples, av5::Cfg<2>::NTHREADS, 2, av5::Cfg<2>::SMEM_BYTES, [=] { av5::attn_v5_kernel<2, true>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
+    ok = emu::run_grid(2 * n_samples, av5::Cfg<2>::NTHREADS, 2, av5::Cfg<2>::SMEM_BYTES, [=] { av5::attn_v5_kernel<2, 1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
   } else if (variant == 154) {
-    ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4, true>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
+    ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4, 1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
+  } else if (variant == 251) {
+    ok = emu::run_grid(n_samples, av5::Cfg<1>::NTHREADS, 1, av5::Cfg<1>::SMEM_BYTES, [=] { av5::attn_v5_kernel<1, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
+  } else if (variant == 252) {
+    ok = emu::run_grid(2 * n_samples, av5::Cfg<2>::NTHREADS, 2, av5::Cfg<2>::SMEM_BYTES, [=] { av5::attn_v5_kernel<2, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
+  } else if (variant == 254) {
+    ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
   } else {
     g_err = "unknown attention variant";
   }

@@ -12,7 +12,7 @@ import torch
 
 import emu
 
-ACT_NONE, ACT_SILU, ACT_GELU, ACT_QSOFT = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_QSOFT, ACT_EXPO = 0, 1, 2, 3, 4
 
 
 class Args(ctypes.Structure):
@@ -25,7 +25,8 @@ class Args(ctypes.Structure):
                 ("out2", ctypes.c_void_p), ("ps_out", ctypes.c_void_p), ("nullc", ctypes.c_void_p), ("n_uncond", ctypes.c_int32),
                 ("ps_in", ctypes.c_void_p), ("cs_in", ctypes.c_void_p), ("ps_slots", ctypes.c_int32), ("ps_P", ctypes.c_int32),
                 ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32),
-                ("qsum", ctypes.c_void_p), ("qsoft_cols", ctypes.c_int32)]
+                ("qsum", ctypes.c_void_p), ("qsoft_cols", ctypes.c_int32),
+                ("eshift", ctypes.c_void_p), ("expo_cols", ctypes.c_int32)]
 
 
 def bf16_bits(t):
@@ -45,7 +46,7 @@ def r64(k):
 
 
 def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, dup=False, stats_out=False, n_uncond=0,
-             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, qsoft_cols=0):
+             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, qsoft_cols=0, expo_cols=0, expo_q_cols=0):
     """Builds operands like the engine does (K laid out per segment padded to 64), runs the emulated kernel, returns
     (got, want, extras)."""
     g = torch.Generator().manual_seed(seed)
@@ -118,6 +119,15 @@ def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, d
         e = torch.exp(qv - qv.max(-1, keepdim=True).values)
         extras["qsum"], extras["qsum_want"] = qsum, e.sum(-1)
         want = torch.cat([e.reshape(M, qsoft_cols), want[:, qsoft_cols:]], 1)
+    if act == ACT_EXPO:    # leading expo_cols columns: exp(v - eshift[n]) with static per-column shifts
+        eshift = 3.0 * rnd(expo_cols)
+        if expo_q_cols:    # a row softmax (Q) tolerates one shift per 64-column head only; the column softmax (K) any per-column shift
+            eshift[:expo_q_cols] = eshift[:expo_q_cols:64].repeat_interleave(64)
+        eshift = eshift.float().numpy()
+        keep.append(eshift)
+        a.eshift, a.expo_cols = ptr(eshift), expo_cols
+        extras["eshift"] = torch.from_numpy(eshift.astype(np.float64))
+        want = torch.cat([torch.exp(want[:, :expo_cols] - extras["eshift"]), want[:, expo_cols:]], 1)
     if act == ACT_SILU:
         want = torch.nn.functional.silu(want)
     elif act == ACT_GELU:
@@ -287,5 +297,35 @@ def test_qkv_epilogue_softmax_feeds_attention_end_to_end(variant):
     ss = 0.5 * torch.randn(Bn, 1024)
     z = tk.run_attention(variant, qkv_dev, g, b, ss, qsum=qsum)
     ref = tk.reference(ex["raw"].reshape(Bn, T, 1536), g, b, ss)                   # reference() rounds its input to bf16 like the engine's QKV buffer
+    err = float((z - ref).abs().max() / ref.abs().max())
+    assert torch.isfinite(z).all() and err < 1.5e-2, err
+
+
+@pytest.mark.parametrize("M,N,ec,cg,num_sms,ps", [(300, 768, 512, 1, 2, False), (520, 1536, 1024, 2, 2, True), (300, 512, 512, 2, 2, False),
+                                                  (140, 384, 128, 1, 1, True)])
+def test_exponential_epilogue(M, N, ec, cg, num_sms, ps):
+    """ACT_EXPO (opt-in, DSHEG_EXPO=1): the LN-fold QKV projection writes exp(v - eshift[n]) for its leading columns (Q and K:
+    softmax numerators with static shifts, transformer.py:122-123 moved into the producing GEMM) and the rest plain."""
+    got, want, ex = run_gemm(M, N, [512], ln=True, act=ACT_EXPO, expo_cols=ec, cg=cg, num_sms=num_sms, ps_in=ps, seed=7)
+    assert torch.isfinite(got).all()
+    rel = ((got[:, :ec] - want[:, :ec]) / want[:, :ec]).abs().max()
+    assert float(rel) < 6e-3, float(rel)        # bf16 rounding (2^-9) + ex2.approx of an fp32 argument, RELATIVE: exponentials span decades
+    if ec < N:
+        assert float((got[:, ec:] - want[:, ec:]).abs().max() / want[:, ec:].abs().max()) < 8e-3
+
+
+@pytest.mark.parametrize("variant,cg", [(251, 1), (254, 2)])
+def test_qkv_exponential_epilogue_feeds_attention_end_to_end(variant, cg):
+    """GEMM (ACT_EXPO) -> attention (PRE = 2), both kernel sources on the emulator, against the float64 attention of the
+    float64 QKV projection: the pair of opt-in kernels implements transformer.py:119-128 + :92-96 together, without a single
+    maximum search."""
+    import test_emu_kernels as tk
+    Bn, T = 2, 34
+    got, want, ex = run_gemm(Bn * T, 1536, [512], ln=True, act=ACT_EXPO, expo_cols=1024, expo_q_cols=512, cg=cg, num_sms=2, seed=4)
+    qkv_dev = bits_to_f64(ex["out_bits"]).float().reshape(Bn, T, 1536)          # what the attention kernel reads
+    g, b = 1 + 0.1 * torch.randn(512), 0.1 * torch.randn(512)
+    ss = 0.5 * torch.randn(Bn, 1024)
+    z = tk.run_attention(variant, qkv_dev, g, b, ss)
+    ref = tk.reference(ex["raw"].reshape(Bn, T, 1536), g, b, ss)
     err = float((z - ref).abs().max() / ref.abs().max())
     assert torch.isfinite(z).all() and err < 1.5e-2, err

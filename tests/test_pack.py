@@ -46,6 +46,52 @@ def test_bf16_pack_is_rounded_fp32_pack_and_csum_consistent():
     assert float(w32[:, 512 + 256 + 128 + 51:].abs().max()) == 0.0
 
 
+def test_static_softmax_shifts_bound_every_input():
+    """pack.py:expo_shift -- the ACT_EXPO epilogue replaces the running maxima of softmax_d(Q) / softmax_t(K) (tr:122-123) by
+    static shifts; the packer must PROVE |value - shift| <= EXPO_LIMIT for every hidden row.  Checked against the worst-case
+    rows (LayerNorm output aligned with a weight row: the Cauchy-Schwarz bound is attained up to the 1 % slack) and against
+    weights for which no safe shift exists (the optional tensor must then be absent)."""
+    from diffsheg_b200.pack import EXPO_LIMIT, expo_shift
+    cfg = synth.make_cfg("show")
+    sd = synth.make_state_dict(cfg, seed=1)
+    packed = pack_state_dict(sd, cfg, "bf16", max_frames=8)
+    D = cfg["latent_dim"]
+    for name in ("ges.l0", "exp.l7"):
+        W = packed[name + ".qkv.w"][0].double()
+        b = packed[name + ".qkv.b"][0].double()
+        es = packed[name + ".qkv.eshift"][0].double()
+        assert es.shape == (2 * D,) and float(es[:D].abs().max()) == 0.0 and torch.equal(es[D:], b[D:2 * D].float().double())
+        g = torch.Generator().manual_seed(3)
+        worst = 0.0
+        for n in list(range(0, 2 * D, 97)) + [2 * D - 1]:
+            wc = W[n] - W[n].mean()
+            for sign in (1.0, -1.0):
+                # the hidden row whose LayerNorm output is +-sqrt(P) * wc / ||wc|| (any offset / scale of h gives the same xhat)
+                h = 5.0 + 3.0 * sign * wc / wc.norm()
+                xhat = (h - h.mean()) / torch.sqrt(h.var(unbiased=False) + 1e-5)
+                v = W[:2 * D] @ xhat + b[:2 * D]
+                worst = max(worst, float((v - es).abs().max()))
+        for _ in range(4):   # random rows are far inside
+            h = torch.randn(D, generator=g).double() * 10 + 3
+            xhat = (h - h.mean()) / torch.sqrt(h.var(unbiased=False) + 1e-5)
+            assert float((W[:2 * D] @ xhat + b[:2 * D] - es).abs().max()) < worst
+        assert worst <= EXPO_LIMIT
+        # the proven radius is attained (to the slack) by the aligned rows: the bound is tight, not vacuous
+        R = (W[:2 * D] - W[:2 * D].mean(1, keepdim=True)).norm(dim=1) * D ** 0.5
+        assert worst > 0.9 * float(R.max())
+    # no safe static shift: large K weights, or a large Q bias (Q is shifted by 0) -> no tensor, the engine keeps the max-search kernels
+    W = packed["ges.l0.qkv.w"][0].double()
+    b = packed["ges.l0.qkv.b"][0].double()
+    assert expo_shift(W, b, D) is not None
+    assert expo_shift(W * 40.0, b, D) is None
+    bq = b.clone()
+    bq[5] = EXPO_LIMIT
+    assert expo_shift(W, bq, D) is None
+    bk = b.clone()
+    bk[D + 5] = 1e4     # a K bias of any size is harmless: it IS the shift
+    assert expo_shift(W, bk, D) is not None
+
+
 def test_library_exports_every_declared_symbol():
     from diffsheg_b200 import _lib
     _lib.build()
