@@ -22,6 +22,8 @@
 //       * Q m-tiles that lie completely inside the sample are loaded without per-row predicates;
 //       * K and V arrive as two cp.async groups: the column softmax starts as soon as K has landed.
 //       * CL > 1: the LayerNorm pass keeps its packed Y rows in registers across the cluster barrier (one smem read).
+//       * packed fp32 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): exponent arguments, the A^T and Y rescales, LayerNorm
+//         statistics, normalise / modulate / SiLU all process a bf16 PAIR per issue slot, in full fp32 precision.
 // HBM traffic is unchanged: read q,k,v + write z = 4 * T * 512 * 2 bytes per sample.
 #pragma once
 #include "attn_v3.cuh"
@@ -33,6 +35,7 @@ using av3::TP; using av3::HD; using av3::D; using av3::TILE_BYTES;
 using av3::pack2; using av3::swz; using av3::pair_sync;
 using prims::smem_addr; using prims::cp_async16; using prims::cp_async_commit; using prims::cp_async_wait_group;
 using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::ex2f; using prims::tanh_approx; using prims::rcp_approx;
+using prims::ffma2; using prims::fadd2; using prims::fmul2;
 
 template <int CL> struct Cfg {
   static_assert(CL == 1 || CL == 2 || CL == 4, "1, 2 or 4 CTAs per sample");
@@ -52,6 +55,12 @@ template <int CL> struct Cfg {
 
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float2 bf_pair(uint32_t w) { return make_float2(bf_lo(w), bf_hi(w)); }   // feeds FFMA2 / FADD2 / FMUL2
+// 2^(x * log2e + n) for a packed bf16 pair: one FFMA2, two MUFU.EX2, one pack
+__device__ __forceinline__ uint32_t exp2_pair(uint32_t w, float2 n) {
+  const float2 a = ffma2(bf_pair(w), make_float2(1.4426950408889634f, 1.4426950408889634f), n);
+  return pack2(ex2f(a.x), ex2f(a.y));
+}
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
   const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
@@ -183,10 +192,10 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
       mx[0] = hmax2_u32(mx[0], a.x); mx[1] = hmax2_u32(mx[1], a.y); mx[2] = hmax2_u32(mx[2], a.z); mx[3] = hmax2_u32(mx[3], a.w);
       mx[4] = hmax2_u32(mx[4], b.x); mx[5] = hmax2_u32(mx[5], b.y); mx[6] = hmax2_u32(mx[6], b.z); mx[7] = hmax2_u32(mx[7], b.w);
     }
-    // pass 2: e = 2^(x*log2e - m*log2e), one FFMA + one MUFU.EX2 per element, bf16 for the tensor core, in place
-    float nm[16];
+    // pass 2: e = 2^(x*log2e - m*log2e), half an FFMA2 + one MUFU.EX2 per element, bf16 for the tensor core, in place
+    float2 nm[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { nm[2 * j] = -bf_lo(mx[j]) * L2E; nm[2 * j + 1] = -bf_hi(mx[j]) * L2E; }
+    for (int j = 0; j < 8; ++j) nm[j] = make_float2(-bf_lo(mx[j]) * L2E, -bf_hi(mx[j]) * L2E);
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
       if (rfirst + 8 * i < r_hi) {
@@ -196,8 +205,7 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t e[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          e[j] = pack2(ex2f(fmaf(bf_lo(w[j]), L2E, nm[2 * j])), ex2f(fmaf(bf_hi(w[j]), L2E, nm[2 * j + 1])));
+        for (int j = 0; j < 8; ++j) e[j] = exp2_pair(w[j], nm[j]);
         *pa = make_uint4(e[0], e[1], e[2], e[3]);
         *pb = make_uint4(e[4], e[5], e[6], e[7]);
       }
@@ -271,12 +279,13 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float2 s2 = *reinterpret_cast<const float2*>(csum + 8 * nt + 2 * q);
-      const float i0 = rcp_approx(s2.x), i1 = rcp_approx(s2.y);
+      const float2 inv = make_float2(rcp_approx(s2.x), rcp_approx(s2.y));
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         const int l = 32 * half + 16 * mi + g;
-        *reinterpret_cast<uint32_t*>(Ks + swz(l, nt) + q * 4) = pack2(acc[mi][nt][0] * i0, acc[mi][nt][1] * i1);
-        *reinterpret_cast<uint32_t*>(Ks + swz(l + 8, nt) + q * 4) = pack2(acc[mi][nt][2] * i0, acc[mi][nt][3] * i1);
+        const float2 lo = fmul2(make_float2(acc[mi][nt][0], acc[mi][nt][1]), inv), hi = fmul2(make_float2(acc[mi][nt][2], acc[mi][nt][3]), inv);
+        *reinterpret_cast<uint32_t*>(Ks + swz(l, nt) + q * 4) = pack2(lo.x, lo.y);
+        *reinterpret_cast<uint32_t*>(Ks + swz(l + 8, nt) + q * 4) = pack2(hi.x, hi.y);
       }
     }
   }
@@ -307,13 +316,13 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
       float mx0 = fmaxf(bf_lo(ma), bf_hi(ma)), mx1 = fmaxf(bf_lo(mb), bf_hi(mb));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float n0 = -mx0 * L2E, n1 = -mx1 * L2E;
+      const float2 n0 = make_float2(-mx0 * L2E, -mx0 * L2E), n1 = make_float2(-mx1 * L2E, -mx1 * L2E);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        pa[ks][0] = pack2(ex2f(fmaf(bf_lo(qa[ks][0]), L2E, n0)), ex2f(fmaf(bf_hi(qa[ks][0]), L2E, n0)));
-        pa[ks][1] = pack2(ex2f(fmaf(bf_lo(qa[ks][1]), L2E, n1)), ex2f(fmaf(bf_hi(qa[ks][1]), L2E, n1)));
-        pa[ks][2] = pack2(ex2f(fmaf(bf_lo(qa[ks][2]), L2E, n0)), ex2f(fmaf(bf_hi(qa[ks][2]), L2E, n0)));
-        pa[ks][3] = pack2(ex2f(fmaf(bf_lo(qa[ks][3]), L2E, n1)), ex2f(fmaf(bf_hi(qa[ks][3]), L2E, n1)));
+        pa[ks][0] = exp2_pair(qa[ks][0], n0);
+        pa[ks][1] = exp2_pair(qa[ks][1], n1);
+        pa[ks][2] = exp2_pair(qa[ks][2], n0);
+        pa[ks][3] = exp2_pair(qa[ks][3], n1);
       }
       }
       if (mt + 2 < n_mt) load_q(qhead, (mt + 2) * 16, T, g, q, qa);  // prefetch under the MMAs
@@ -338,8 +347,9 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
       const float r1 = (EXPO && rb >= T) ? 0.f : rcp_approx(QPRE ? qs1 : rs[2]);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        *reinterpret_cast<uint32_t*>(Vs + swz(ra, nt) + q * 4) = pack2(y[nt][0] * r0, y[nt][1] * r0);
-        *reinterpret_cast<uint32_t*>(Vs + swz(rb, nt) + q * 4) = pack2(y[nt][2] * r1, y[nt][3] * r1);
+        const float2 ya = fmul2(make_float2(y[nt][0], y[nt][1]), make_float2(r0, r0)), yb = fmul2(make_float2(y[nt][2], y[nt][3]), make_float2(r1, r1));
+        *reinterpret_cast<uint32_t*>(Vs + swz(ra, nt) + q * 4) = pack2(ya.x, ya.y);
+        *reinterpret_cast<uint32_t*>(Vs + swz(rb, nt) + q * 4) = pack2(yb.x, yb.y);
       }
     }
   }
@@ -354,27 +364,35 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     const int col0 = (int)rank * C::COLS + sub * 16;       // global column
     const float* sc = ss + (size_t)(smp % B) * ss_ld;
     // per-column constants folded once:  h = t/2,  t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*2G + 2Bc
-    float G[16], Bc[16];
+    float2 G[8], Bc[8];     // column pairs: every elementwise step below is a packed FFMA2 (two columns per issue slot)
 #pragma unroll
     for (int e = 0; e < 16; e += 4) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
       const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + col0 + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + e));
-      G[e] = 0.5f * a.x * (1.f + c4.x); G[e + 1] = 0.5f * a.y * (1.f + c4.y); G[e + 2] = 0.5f * a.z * (1.f + c4.z); G[e + 3] = 0.5f * a.w * (1.f + c4.w);
-      Bc[e] = 0.5f * fmaf(b4.x, 1.f + c4.x, d4.x); Bc[e + 1] = 0.5f * fmaf(b4.y, 1.f + c4.y, d4.y);
-      Bc[e + 2] = 0.5f * fmaf(b4.z, 1.f + c4.z, d4.z); Bc[e + 3] = 0.5f * fmaf(b4.w, 1.f + c4.w, d4.w);
+      G[e / 2] = make_float2(0.5f * a.x * (1.f + c4.x), 0.5f * a.y * (1.f + c4.y));
+      G[e / 2 + 1] = make_float2(0.5f * a.z * (1.f + c4.z), 0.5f * a.w * (1.f + c4.w));
+      Bc[e / 2] = make_float2(0.5f * fmaf(b4.x, 1.f + c4.x, d4.x), 0.5f * fmaf(b4.y, 1.f + c4.y, d4.y));
+      Bc[e / 2 + 1] = make_float2(0.5f * fmaf(b4.z, 1.f + c4.z, d4.z), 0.5f * fmaf(b4.w, 1.f + c4.w, d4.w));
     }
-    auto finish_row = [&](int t, const float (&v)[16], float s, float sq) {
+    // (sum, sum of squares) of a lane's 16 packed columns: 8 FADD2 + 8 FFMA2
+    auto lane_stats = [&](const uint32_t (&w)[8], float& s, float& sq) {
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float2 v = bf_pair(w[e]); s2 = fadd2(s2, v); q2 = ffma2(v, v, q2); }
+      s = s2.x + s2.y; sq = q2.x + q2.y;
+    };
+    auto finish_row = [&](int t, const uint32_t (&w)[8], float s, float sq) {
       // normalise, modulate, SiLU, store: the LPR lanes of a row write COLS * 2 contiguous bytes
       const float mean = s * (1.f / D);
       const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
-      const float nmr = -mean * rstd;
+      const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
       uint32_t o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
-        const float h0 = fmaf(fmaf(v[2 * e], rstd, nmr), G[2 * e], Bc[2 * e]);
-        const float h1 = fmaf(fmaf(v[2 * e + 1], rstd, nmr), G[2 * e + 1], Bc[2 * e + 1]);
-        o[e] = pack2(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+        const float2 h = ffma2(ffma2(bf_pair(w[e]), rs2, nm2), G[e], Bc[e]);
+        const float2 r = ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+        o[e] = pack2(r.x, r.y);
       }
       uint4* dst = reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0);
       dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -386,17 +404,12 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
         const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
         const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-        float v[16], s = 0.f, sq = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[2 * e] = bf_lo(w[e]); v[2 * e + 1] = bf_hi(w[e]);
-          s += v[2 * e] + v[2 * e + 1];
-          sq = fmaf(v[2 * e], v[2 * e], fmaf(v[2 * e + 1], v[2 * e + 1], sq));
-        }
+        float s, sq;
+        lane_stats(w, s, sq);
         // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sq += __shfl_xor_sync(0xffffffffu, sq, o2); }
-        finish_row(t, v, s, sq);
+        finish_row(t, w, s, sq);
       }
     } else {
       uint32_t w[C::LN_ITERS][8];
@@ -411,12 +424,7 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
           const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
           const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
           w[i][0] = u0.x; w[i][1] = u0.y; w[i][2] = u0.z; w[i][3] = u0.w; w[i][4] = u1.x; w[i][5] = u1.y; w[i][6] = u1.z; w[i][7] = u1.w;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float lo = bf_lo(w[i][e]), hi = bf_hi(w[i][e]);
-            s += lo + hi;
-            sq = fmaf(lo, lo, fmaf(hi, hi, sq));
-          }
+          lane_stats(w[i], s, sq);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) w[i][e] = 0u;
@@ -444,10 +452,7 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
           float s = 0.f, sq = 0.f;
 #pragma unroll
           for (int r = 0; r < CL; ++r) { const float2 st2 = stat[r * TP + t]; s += st2.x; sq += st2.y; }
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { v[2 * e] = bf_lo(w[i][e]); v[2 * e + 1] = bf_hi(w[i][e]); }
-          finish_row(t, v, s, sq);
+          finish_row(t, w[i], s, sq);
         }
       }
     }

@@ -96,6 +96,9 @@ template <int NTHREADS> inline void named_bar_sync(int id) {
 inline float ex2f(float x) { return exp2f(x); }
 inline float rcp_approx(float x) { return 1.0f / x; }
 inline float tanh_approx(float x) { return tanhf(x); }
+inline float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 
 inline uint32_t cluster_rank() { return emu::self().cta->rank; }
 inline void cluster_arrive() {
