@@ -32,6 +32,10 @@ def needs_build():
 
 def build(force=False, verbose=False):
     """Compile diffsheg_b200/csrc/engine.cu (which includes every kernel) in-tree."""
+    if os.environ.get("DSHEG_LIB"):   # an experiment build (scripts/build_variants.sh): never overwrite it with a default build
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"DSHEG_LIB={SO_PATH} does not exist (build it with scripts/build_variants.sh)")
+        return SO_PATH
     if not force and not needs_build():
         return SO_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -60,6 +60,7 @@ __device__ __forceinline__ void load_q_tile(const bf16* qhead, int row0, int T, 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_v3_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
                const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+  DSHEG_PDL_ENTER();
   DSHEG_DYN_SMEM(sm, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = warp >> 1, half = warp & 1;

@@ -99,6 +99,7 @@ template <int CL, int PRE = 0>
 __global__ void __launch_bounds__(Cfg<CL>::NTHREADS, Cfg<CL>::CTAS_PER_SM)
 attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
                const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld, const float* __restrict__ qsum = nullptr) {
+  DSHEG_PDL_ENTER();
   using C = Cfg<CL>;
   constexpr bool QPRE = PRE == 1;     // Q numerators + their sums from global memory
   constexpr bool EXPO = PRE == 2;     // Q and K numerators precomputed, sums on the tensor core
@@ -475,10 +476,19 @@ inline cudaError_t launch_attn_v5(const bf16* qkv, bf16* z, int n_samples, int T
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_samples * CL); cfg.blockDim = dim3(C::NTHREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+#if DSHEG_PDL_ATTRS   // experiment build: programmatic dependent launch (the kernel starts with DSHEG_PDL_ENTER)
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+#endif
+  cfg.attrs = attr; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, qkv, z, T, ssB, ln_g, ln_b, ss, ss_ld, qsum);
 }
 #endif  // DSHEG_EMU

@@ -10,6 +10,43 @@
 
 #include <string>
 
+// ---- programmatic dependent launch (experiment build -DDSHEG_PDL=1, scripts/build_variants.sh; default: expands to nothing) --
+// DSHEG_PDL_TRIGGER: the next kernel of the stream may start its prologue (block scheduling, barrier / TMEM setup, constant
+// loads) while this grid is still running.  DSHEG_PDL_WAIT: blocks until every grid this one depends on has completed and
+// flushed its memory; it precedes the first access to anything a previous kernel wrote (or still reads).  Kernels launched
+// WITHOUT the attribute (engine.cu: DSHEG_LAUNCH) keep classic stream order, so adoption can be partial.
+#if defined(DSHEG_PDL) && DSHEG_PDL && !defined(DSHEG_EMU)
+#define DSHEG_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define DSHEG_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define DSHEG_PDL_TRIGGER() ((void)0)
+#define DSHEG_PDL_WAIT() ((void)0)
+#endif
+#define DSHEG_PDL_ENTER() do { DSHEG_PDL_TRIGGER(); DSHEG_PDL_WAIT(); } while (0)
+
+// Host side: DSHEG_LAUNCH(kernel, grid, block, smem, stream, args...) is the plain <<<>>> launch in the default build and a
+// launch with cudaLaunchAttributeProgrammaticStreamSerialization in the PDL build.  ONLY kernels that execute DSHEG_PDL_WAIT
+// before their first dependent access may be launched through it.
+#if defined(DSHEG_PDL) && DSHEG_PDL && !defined(DSHEG_EMU)
+namespace dsheg {
+template <typename... KA, typename... A>
+inline cudaError_t pdl_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... a) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(a)...);
+}
+}  // namespace dsheg
+#define DSHEG_LAUNCH(kern, grid, block, smem, st, ...) dsheg::pdl_launch(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#define DSHEG_PDL_ATTRS 1
+#else
+#define DSHEG_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+#define DSHEG_PDL_ATTRS 0
+#endif
+
 namespace dsheg {
 
 typedef __nv_bfloat16 bf16;

@@ -293,7 +293,7 @@ struct Runner {
         prof_begin(h, st, PROF_ROW, fb * sizeof(TA));
       }
       if (std::is_same<TA, bf16>::value)
-        feat_prep_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+        DSHEG_LAUNCH(feat_prep_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, 
             (bf16*)hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
       else
         feat_prep_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
@@ -320,7 +320,7 @@ struct Runner {
     } else {
     prof_begin(h, st, PROF_ROW, (double)rows * D * sizeof(TA));
     if (std::is_same<TA, bf16>::value)
-      rowstats_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>((const bf16*)hcur, ldc, D, rows, h->MU2, h->RSTD2);
+      DSHEG_LAUNCH(rowstats_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, (const bf16*)hcur, ldc, D, rows, h->MU2, h->RSTD2);
     else
       rowstats_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(hcur, ldc, D, rows, h->MU2, h->RSTD2);
     prof_end(h, st);
@@ -347,7 +347,7 @@ struct Runner {
     // algorithmic traffic: read q,k,v + write z, all in the activation type (4*rows*D*sizeof)
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
     if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 1) {
-      av3::attn_v3_kernel<<<n_samples, av3::NTHREADS, av3::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
+      DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 4) {
       av4::attn_v4_kernel<<<2 * n_samples, av4::NTHREADS, av4::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 >= 51 && h->attn_v2 <= 54) {
@@ -394,9 +394,9 @@ struct Runner {
     if (gemm(f2, L.ffn2, "ffn2")) return 1;
     prof_begin(h, st, PROF_ROW, 2.0 * rows * D * sizeof(TA));
     if (std::is_same<TA, bf16>::value && D == 512)
-      ln_mod_silu_sample_bf16_kernel<<<rows / T, 256, 0, st>>>((const bf16*)h->Y, (bf16*)h->Z, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
+      DSHEG_LAUNCH(ln_mod_silu_sample_bf16_kernel, rows / T, 256, 0, st, (const bf16*)h->Y, (bf16*)h->Z, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
     else if (std::is_same<TA, bf16>::value)
-      ln_mod_silu_bf16_kernel<<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+      DSHEG_LAUNCH(ln_mod_silu_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, 
           (const bf16*)h->Y, D, (bf16*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
     else
       ln_mod_silu_kernel<TA, TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
@@ -452,7 +452,7 @@ struct Runner {
     const int L = c.num_layers, Dtot = c.dim_pose + c.expression_dim;
     const int G = two ? 2 : 1, R = G * R1;
     // ---- K1: timestep embeddings of the three nets (rows are identical: t = [i]*B, gd:1196)
-    sinus_kernel<<<1, 256, 0, st>>>(h->PRM, h->freqs, D / 2, h->SIN);
+    DSHEG_LAUNCH(sinus_kernel, 1, 256, 0, st, h->PRM, h->freqs, D / 2, h->SIN);
     LAUNCH_CHECK("sinus");
     {
       GemvBatch g0, g2;
@@ -461,21 +461,21 @@ struct Runner {
         g0.p[i] = {h->SIN, tes[i]->w0, tes[i]->b0, h->TEH + i * E};
         g2.p[i] = {h->TEH + i * E, tes[i]->w2, tes[i]->b2, h->TEMB + i * E};
       }
-      gemv_kernel<<<dim3((E + 7) / 8, 3), 256, 0, st>>>(g0, E, D, ACT_SILU, 0);
+      DSHEG_LAUNCH(gemv_kernel, dim3((E + 7) / 8, 3), 256, 0, st, g0, E, D, ACT_SILU, 0);
       LAUNCH_CHECK("time_embed.0");
-      gemv_kernel<<<dim3((E + 7) / 8, 3), 256, 0, st>>>(g2, E, E, ACT_NONE, 0);
+      DSHEG_LAUNCH(gemv_kernel, dim3((E + 7) / 8, 3), 256, 0, st, g2, E, E, ACT_NONE, 0);
       LAUNCH_CHECK("time_embed.2");
       // K3 (audio layer): both StylizationBlocks' emb_layers, one row
       GemvBatch ga;
       ga.p[0] = {h->TEMB, h->ssa_w, h->ssa_b, h->SSA};
       ga.p[1] = ga.p[0]; ga.p[2] = ga.p[0];
-      gemv_kernel<<<dim3((4 * A + 7) / 8, 1), 256, 0, st>>>(ga, 4 * A, E, ACT_NONE, 1);
+      DSHEG_LAUNCH(gemv_kernel, dim3((4 * A + 7) / 8, 1), 256, 0, st, ga, 4 * A, E, ACT_NONE, 1);
       LAUNCH_CHECK("aud_ss");
     }
     // ---- K3: scale/shift of all 2L StylizationBlocks per net, one GEMM [B,2048] x [2048, 2L*2D]
     for (int n = 0; n < 2; ++n) {
       const size_t ne = (size_t)B * E;
-      embs_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->TEMB + (1 + n) * E, h->PIDE[n], (TA*)h->EMBS[n], B, E);
+      DSHEG_LAUNCH(embs_kernel<TA>, (unsigned)((ne + 255) / 256), 256, 0, st, h->TEMB + (1 + n) * E, h->PIDE[n], (TA*)h->EMBS[n], B, E);
       LAUNCH_CHECK("embs");
       GemmDesc g;
       g.a[0] = seg(h->EMBS[n], E, E); g.nseg = 1; g.M = B; g.out = h->SS[n]; g.ldo = L * 4 * D; g.out_f32 = 1;
@@ -492,7 +492,7 @@ struct Runner {
       if (gemm(gx, nw.audproj, "audio_proj")) return 1;
       {
         const size_t ne = (size_t)R1 * h->ldXin;
-        cast_pad_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(x, Dtot, nw.x_off, nw.feats, (TA*)h->XIN, h->ldXin, R1);
+        DSHEG_LAUNCH(cast_pad_kernel<TA>, (unsigned)((ne + 255) / 256), 256, 0, st, x, Dtot, nw.x_off, nw.feats, (TA*)h->XIN, h->ldXin, R1);
         LAUNCH_CHECK("cast_pad");
       }
       TA* Hu = (TA*)h->H;
@@ -509,7 +509,7 @@ struct Runner {
       if (n == 1) extra[n_extra++] = seg(h->EXPR, h->ldE, c.expression_dim);  // tr:506-507,533-535
       const bool fused = std::is_same<TA, bf16>::value && h->gemm_engine == 1 && h->fuse_stats && D == 512;
       if (fused) {
-        cond_stats_bf16_kernel<<<(R1 + 7) / 8, 256, 0, st>>>(extra[0], extra[1], n_extra > 2 ? extra[2] : extra[0], n_extra, R1, h->CS);
+        DSHEG_LAUNCH(cond_stats_bf16_kernel, (R1 + 7) / 8, 256, 0, st, extra[0], extra[1], n_extra > 2 ? extra[2] : extra[0], n_extra, R1, h->CS);
         LAUNCH_CHECK("cond_stats");
       }
       for (int l = 0; l < L; ++l) {
@@ -525,7 +525,7 @@ struct Runner {
       {
         const int wcols = (n == 0) ? h->ldE : nw.feats;
         const size_t ne = (size_t)R1 * wcols;
-        cfg_mix_kernel<TA><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->O, h->ldO, R1, nw.feats, two ? 1 : 0, h->PRM, eps_out,
+        DSHEG_LAUNCH(cfg_mix_kernel<TA>, (unsigned)((ne + 255) / 256), 256, 0, st, h->O, h->ldO, R1, nw.feats, two ? 1 : 0, h->PRM, eps_out,
                                                                           x, Dtot, nw.x_off, n == 0 ? (TA*)h->EXPR : nullptr, h->ldE);
         LAUNCH_CHECK("cfg_mix");
       }
@@ -738,7 +738,7 @@ int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, floa
   if (!h->window_ready) return fail(h, "dsheg_prepare_window has not been called");
   cudaStream_t st = (cudaStream_t)stream;
   const bool two = h->cfg.classifier_free && cond_scale != 1.0f;  // transformer.py:537
-  step_params_kernel<<<1, 32, 0, st>>>(h->PRM, (float)t_orig, a, b, cond_scale);
+  DSHEG_LAUNCH(step_params_kernel, 1, 32, 0, st, h->PRM, (float)t_orig, a, b, cond_scale);
   h->launches++;
   const int rows1 = h->B * h->T;
   auto eager = [&]() { return with_runner(h, st, [&](auto& r) { return r.denoise(x, two, eps_out); }); };
@@ -813,14 +813,14 @@ int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, i
   p.x = x; p.eps = eps; p.x_out = x_out; p.pred_out = pred_xstart_out; p.n = n; p.T = T; p.D = D;
   p.a = sqrt_recip_ac; p.b = sqrt_recipm1_ac; p.sqrt_acp = sqrt_ac_prev; p.sqrt_1m_acp = sqrt_one_minus_ac_prev;
   p.gt = gt; p.mask = mask; p.noise2 = noise2; p.blend = blend; p.overlap_len = overlap_len;
-  ddim_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p);
+  DSHEG_LAUNCH(ddim_step_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, p);
   return step_done("dsheg_ddim_step");
 }
 
 int dsheg_undo_step(const float* x, const float* noise, float* x_out, int64_t n, float sqrt_one_minus_beta, float sqrt_beta,
                     void* stream) {
   if (!x || !noise || !x_out || n <= 0) { g_create_error = "dsheg_undo_step: bad arguments"; return 1; }
-  undo_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, noise, x_out, n, sqrt_one_minus_beta, sqrt_beta);
+  DSHEG_LAUNCH(undo_step_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, x, noise, x_out, n, sqrt_one_minus_beta, sqrt_beta);
   return step_done("dsheg_undo_step");
 }
 

@@ -160,6 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
+  DSHEG_PDL_TRIGGER();   // PDL build: the next kernel may begin its own prologue now (it still waits for this grid's completion)
   constexpr bool LONGK = LONGK_ && CG == 2 && !OUTF32;
   constexpr bool NARROW = LONGK && RES != RES_BF16;
   using C = Cfg<BN, CG, NARROW, LONGK>;
@@ -211,6 +212,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (CG == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // PDL build: barriers, TMEM and tensor-map prefetches above touch nothing a previous kernel wrote; operands, residuals,
+  // statistics and outputs below do
+  DSHEG_PDL_WAIT();
 
 #if DSHEG_SPLIT_RINGS   // experiment build only: the default translation unit is token-identical to the validated kernel
   if (C::SPLIT && (warp == 0 || warp == 2)) {
@@ -670,16 +674,21 @@ inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int 
     attr_set = true;
   }
   if (CG == 1) {
-    kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+    DSHEG_LAUNCH(kern, grid, C::NUM_THREADS, C::SMEM_BYTES, st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+#if DSHEG_PDL_ATTRS   // experiment build: programmatic dependent launch (the kernel executes DSHEG_PDL_WAIT after its prologue)
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 2;
+#endif
   return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
 #endif
 }

@@ -140,6 +140,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // every segment row 16-byte aligned.
 __global__ void feat_prep_bf16_kernel(bf16* h, int ldh, int D, int n_uncond, int n_rows, const float* nullc, Seg s1, Seg s2,
                                       Seg s3, int nseg_extra, float* mu, float* rstd) {
+  DSHEG_PDL_ENTER();
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= n_rows) return;
@@ -210,6 +211,7 @@ __global__ void feat_prep_bf16_kernel(bf16* h, int ldh, int D, int n_uncond, int
 // (sum, sum of squares) of the conditioning part (xf | hubert [| expr]) of the feat_proj input row: step-wide
 // constant across the 8 layers of a net, combined with the residual-stream partials in the feat1 epilogue.
 __global__ void cond_stats_bf16_kernel(Seg s1, Seg s2, Seg s3, int nseg, int n_rows, float2* cs) {
+  DSHEG_PDL_ENTER();
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= n_rows) return;
@@ -234,6 +236,7 @@ __global__ void cond_stats_bf16_kernel(Seg s1, Seg s2, Seg s3, int nseg, int n_r
 
 // rowstats for bf16, D % 8 == 0, D <= 1024
 __global__ void rowstats_bf16_kernel(const bf16* x, int ld, int D, int n_rows, float* mu, float* rstd) {
+  DSHEG_PDL_ENTER();
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= n_rows) return;
@@ -267,6 +270,7 @@ __global__ void rowstats_bf16_kernel(const bf16* x, int ld, int D, int n_rows, f
 // ln_mod_silu for bf16 in / bf16 out, D % 8 == 0, D <= 512
 __global__ void ln_mod_silu_bf16_kernel(const bf16* y, int ldy, bf16* z, int ldz, int D, int n_rows, int T, int B, const float* g,
                                         const float* b, const float* ss, int ss_ld) {
+  DSHEG_PDL_ENTER();
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= n_rows) return;
@@ -325,6 +329,7 @@ __global__ void ln_mod_silu_bf16_kernel(const bf16* y, int ldy, bf16* z, int ldz
 // instructions on g/b/scale/shift than on data).  SiLU(x) = h + h*tanh(h), h = x/2 (MUFU.TANH).
 __global__ void __launch_bounds__(256) ln_mod_silu_sample_bf16_kernel(const bf16* y, bf16* z, int T, int B, const float* g,
                                                                       const float* b, const float* ss, int ss_ld) {
+  DSHEG_PDL_ENTER();
   constexpr int D = 512;
   const int smp = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const float* sc = ss + (size_t)(smp % B) * ss_ld;
@@ -484,6 +489,7 @@ inline size_t attn_smem_bytes(int T) { return (size_t)(3 * T * (HD + 1) + HD * (
 // xin[r, 0..ld) = cast(x[r*Dtot + off + j]) for j < feats, 0 for the K padding.
 template <typename TA>
 __global__ void cast_pad_kernel(const float* x, int Dtot, int off, int feats, TA* xin, int ld, int n_rows) {
+  DSHEG_PDL_ENTER();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n_rows * ld) return;
   const int r = (int)(i / ld), j = (int)(i % ld);
@@ -508,12 +514,14 @@ __global__ void mel_stage_kernel(const float* mel, int A, TA* aud256, int ld256,
 // Step scalars live in a 4-float device buffer {t_orig, a, b, cond_scale} written by step_params_kernel, so that a
 // captured CUDA graph of the denoiser is valid for every diffusion step (nothing step-dependent is baked in).
 __global__ void step_params_kernel(float* prm, float t, float a, float b, float s) {
+  DSHEG_PDL_ENTER();
   if (threadIdx.x == 0) { prm[0] = t; prm[1] = a; prm[2] = b; prm[3] = s; }
 }
 
 template <typename TA>
 __global__ void cfg_mix_kernel(const float* o, int ldo, int n_rows, int feats, int two, const float* prm, float* eps_out,
                                const float* x, int Dtot, int off, TA* expr, int ld_expr) {
+  DSHEG_PDL_ENTER();
   const float a = prm[1], b = prm[2], s = prm[3];
   const int wcols = expr ? ld_expr : feats;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -535,6 +543,7 @@ __global__ void cfg_mix_kernel(const float* o, int ldo, int n_rows, int feats, i
 // sinusoidal timestep embedding (tr:42-59): [cos(t*f) | sin(t*f)], f uploaded from the host so the
 // arguments are bit-identical to torch's.
 __global__ void sinus_kernel(const float* prm, const float* freqs, int half, float* out) {
+  DSHEG_PDL_ENTER();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half) return;
   const float arg = prm[0] * freqs[i];
@@ -547,6 +556,7 @@ __global__ void sinus_kernel(const float* prm, const float* freqs, int half, flo
 struct GemvProb { const float* in; const float* w; const float* b; float* out; };
 struct GemvBatch { GemvProb p[3]; };
 __global__ void gemv_kernel(GemvBatch gb, int N, int K, int act, int in_silu) {
+  DSHEG_PDL_ENTER();
   const GemvProb pr = gb.p[blockIdx.y];
   const int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -565,6 +575,7 @@ __global__ void gemv_kernel(GemvBatch gb, int N, int K, int act, int in_silu) {
 // embs[b, :] = SiLU(temb + pide[b, :])   (tr:559 then the SiLU of every emb_layers, tr:75-78)
 template <typename TA>
 __global__ void embs_kernel(const float* temb, const float* pide, TA* embs, int B, int E) {
+  DSHEG_PDL_ENTER();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * E) return;
   AT<TA>::st(embs + i, silu_f(temb[i % E] + pide[i]));

@@ -46,12 +46,14 @@ __device__ __forceinline__ float ddim_one(const DdimArgs& p, long long i, float 
 }
 
 __global__ void ddim_step_kernel(const DdimArgs p) {
+  DSHEG_PDL_ENTER();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride)
     p.x_out[i] = ddim_one(p, i, p.x[i], p.eps[i]);
 }
 
 __global__ void undo_step_kernel(const float* x, const float* noise, float* out, long long n, float c1, float c2) {
+  DSHEG_PDL_ENTER();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = __fadd_rn(__fmul_rn(c1, x[i]), __fmul_rn(c2, noise[i]));

@@ -14,4 +14,5 @@ wait
 build split73 "-DDSHEG_SPLIT_RINGS=1" &                                    # K = 512 pair GEMMs: A ring 7 deep, W ring 3 deep, two producers
 build split64 "-DDSHEG_SPLIT_RINGS=1 -DDSHEG_SPLIT_A=6 -DDSHEG_SPLIT_W=4" &
 wait
+build pdl "-DDSHEG_PDL=1"                                                  # programmatic dependent launch in every bf16 hot-path kernel (griddepcontrol)
 ls -la build_variants

@@ -11,7 +11,7 @@
 #        gpurun --timeout 2700 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
 O=gpurun_out
-[ -f build_variants/libdiffsheg_b200_split73.so ] || bash scripts/build_variants.sh > $O/r2_build_variants.log 2>&1
+[ -f build_variants/libdiffsheg_b200_split73.so ] && [ -f build_variants/libdiffsheg_b200_pdl.so ] || bash scripts/build_variants.sh > $O/r2_build_variants.log 2>&1
 timeout 1300 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
 
 # ---- GEMM candidates: isolated sweep (dsheg_bench_gemm, 10 iterations per shape) and the real loop
@@ -38,6 +38,14 @@ for a in v5c1 v5c2 v5c4; do
   DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_${a}_expo.json 2> $O/r2_bench_attn_${a}_expo.err
 done
 
+# ---- programmatic dependent launch build (griddepcontrol in every bf16 hot-path kernel): parity first, then the latency-bound single-clip
+#      configs (B = 1: about 165 dependent kernels per call) and the headline
+PDL=$PWD/build_variants/libdiffsheg_b200_pdl.so
+DSHEG_LIB=$PDL timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "denoise or loop or rows_are_independent" > $O/r2_pdl_parity.log 2>&1; echo "pdl parity rc=$?" >> $O/r2_rc.txt
+timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_default.jsonl 2>&1
+DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_pdl.jsonl 2>&1
+DSHEG_LIB=$PDL timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_pdl.json 2> $O/r2_bench_gemm_pdl.err
+
 # ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)
 for a in v5c1 v5c2 v5c4; do
   DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_denoise.py --batch 3 --calls 1 > $O/r2_${a}_memcheck.log 2>&1; echo "$a memcheck rc=$?" >> $O/r2_rc.txt
@@ -62,3 +70,4 @@ PY
 for v in default k512deep split73 split64; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2 " $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
 grep -c "Race reported\|hazard" $O/r2_racecheck_pairs_B24.log; grep -E "Write access|Read access" $O/r2_racecheck_pairs_B24.log | sed 's/(CUtensorMap.*//' | sort | uniq -c | sort -rn | head -8
 cat $O/r2_postprocess_bw.txt
+echo "== single clip (config 1), default vs PDL build"; cat $O/r2_configs1_default.jsonl $O/r2_configs1_pdl.jsonl | cut -c1-200; tail -2 $O/r2_pdl_parity.log
