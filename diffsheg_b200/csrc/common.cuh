@@ -56,7 +56,10 @@ typedef __nv_bfloat16 bf16;
 // ACT_EXPO (tcgen05 engine, LN-fold GEMMs only): columns < GemmDesc::expo_cols are written as exp(v - eshift[n]) -- softmax
 // numerators with a STATIC shift (softmax is shift-invariant; the packer proves |v - eshift| <= 60 for every possible input,
 // diffsheg_b200/pack.py:expo_shift) -- so the attention kernel neither searches maxima nor exponentiates; other columns plain
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QSOFT = 3, ACT_EXPO = 4 };
+// ACT_LNMS (tcgen05 engine, CTA-pair kernel, N == 512, K >= 768): the StylizationBlock prologue of the FFN (tr:92-96) fused into
+// the producing GEMM -- z = SiLU(LN_512(acc + bias) * (1 + scale) + shift): one CTA pair keeps BOTH 256-column halves of its
+// 256 rows in the two TMEM accumulator stages, so full-row statistics never leave the SM and `y` is never written
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QSOFT = 3, ACT_EXPO = 4, ACT_LNMS = 5 };
 
 // ---- activation-type traits: float (fp32 mode) or bf16 (bf16 mode) -------------------------
 template <typename T> struct AT;
@@ -133,6 +136,11 @@ struct GemmDesc {
   // ---- ACT_EXPO: exp(v - eshift[n]) for the leading expo_cols columns (Q and K of the fused QKV projection, tr:122-123) ---
   const float* eshift = nullptr;  // [expo_cols] static per-column shifts (Q: 0, K: folded bias), fp32
   int expo_cols = 0;              // leading columns (multiple of 64) written as exponentials
+  // ---- ACT_LNMS: LayerNorm (gamma, beta over the N == 512 output columns) + per-sample modulation + SiLU in the epilogue -----
+  const float* lnms_g = nullptr;  // [N] LayerNorm weight
+  const float* lnms_b = nullptr;  // [N] LayerNorm bias
+  const float* lnms_ss = nullptr; // [lnms_B][lnms_ld]: scale at [0, N), shift at [N, 2 N) of sample (row / lnms_T) % lnms_B
+  int lnms_ld = 0, lnms_B = 0, lnms_T = 0;
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

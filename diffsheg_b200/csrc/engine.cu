@@ -90,6 +90,7 @@ struct dsheg_handle {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   int qsoft = 0;               // DSHEG_QSOFT=1: ACT_QSOFT epilogue of the QKV GEMM + attn_v5<CL, QPRE> (experimental)
+  int fuse_lnms = 0;           // DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS, experimental)
   int expo = 0;                // DSHEG_EXPO=1: ACT_EXPO epilogue (Q and K softmax numerators with static shifts) + attn_v5<CL, 2> (experimental)
   int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
   int graph_max_rows = 4096;   // B*T above which launches are no longer the bottleneck
@@ -391,7 +392,17 @@ struct Runner {
     if (gemm(f1, L.ffn1, "ffn1")) return 1;
     GemmDesc f2;
     f2.a[0] = seg(h->F1, F, F); f2.nseg = 1; f2.M = rows; f2.out = h->Y; f2.ldo = D;
+    // DSHEG_FUSE_LNMS=1 (experimental): the StylizationBlock prologue (LayerNorm, modulation, SiLU; tr:92-96) runs in the epilogue
+    // of linear2 -- a CTA pair holds both 256-column halves of its rows in TMEM -- so `y` is never written and the row-wise pass
+    // below disappears.  Needs the CTA-pair long-K kernel: bf16, tcgen05 engine, D == 512, rows >= 4096, F >= 768.
+    const bool fuse_lnms = std::is_same<TA, bf16>::value && h->fuse_lnms && h->gemm_engine == 1 && D == 512 && rows >= 4096 && F >= 768 &&
+                           tc::g_cg_override() != 1 && tc::g_bn_override() != 128;
+    if (fuse_lnms) {
+      f2.act = ACT_LNMS; f2.out = h->Z;
+      f2.lnms_g = L.ffn_g; f2.lnms_b = L.ffn_b; f2.lnms_ss = ss + 2 * D; f2.lnms_ld = ss_ld; f2.lnms_B = ssB; f2.lnms_T = T;
+    }
     if (gemm(f2, L.ffn2, "ffn2")) return 1;
+    if (!fuse_lnms) {
     prof_begin(h, st, PROF_ROW, 2.0 * rows * D * sizeof(TA));
     if (std::is_same<TA, bf16>::value && D == 512)
       DSHEG_LAUNCH(ln_mod_silu_sample_bf16_kernel, rows / T, 256, 0, st, (const bf16*)h->Y, (bf16*)h->Z, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
@@ -403,6 +414,7 @@ struct Runner {
           (const TA*)h->Y, D, (TA*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
     prof_end(h, st);
     LAUNCH_CHECK("ln_mod_silu");
+    }
     GemmDesc fo;
     fo.a[0] = seg(h->Z, D, D); fo.nseg = 1; fo.M = rows;
     fo.res = hmid; fo.ldr = D; fo.out = hout; fo.ldo = ld_hout;
@@ -588,6 +600,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (att && !strcmp(att, "v5c4")) h->attn_v2 = 54;
   const char* qso = getenv("DSHEG_QSOFT");
   h->qsoft = (qso && !strcmp(qso, "1")) ? 1 : 0;   // Q row-softmax in the QKV GEMM epilogue (needs an attn_v5 variant)
+  const char* fl = getenv("DSHEG_FUSE_LNMS");
+  h->fuse_lnms = (fl && !strcmp(fl, "1")) ? 1 : 0;
   const char* exo = getenv("DSHEG_EXPO");
   h->expo = (exo && !strcmp(exo, "1")) ? 1 : 0;    // Q and K numerators with static shifts in the QKV epilogue (needs an attn_v5 variant)
   const char* gr = getenv("DSHEG_GRAPHS");

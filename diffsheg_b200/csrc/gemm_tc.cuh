@@ -46,7 +46,10 @@ constexpr int BAR_BYTES = 512;
 // dynamic smem base must be 1024-aligned: checked, traps otherwise), single-buffered bias/csum vectors (one extra epilogue
 // barrier per tile) -> 6 stages with narrow boxes, 5 with wide (residual) boxes.  K = 512 tiles are epilogue-sensitive and
 // keep 4 stages, wide boxes and double-buffered vectors (profiles/r01/v8_gemm_sweep.txt vs final_gemm_sweep.txt).
-template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cfg {
+// ROWLN (ACT_LNMS): full-row LayerNorm epilogue over both accumulator stages; 5 stages, narrow boxes, and a vector block that
+// holds bias | gamma/2 | beta/2 for all 512 columns plus double-buffered per-(column group, row) statistics partials.
+template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false, bool ROWLN = false> struct Cfg {
+  static_assert(!ROWLN || (CG == 2 && NARROW && LONGK), "the full-row LayerNorm epilogue exists for the long-K CTA-pair kernel only");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
@@ -75,7 +78,7 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cf
   static constexpr bool SPLIT = CG == 2 && !LONGK && DSHEG_SPLIT_RINGS;
   static constexpr int SA = DSHEG_SPLIT_A, SW = DSHEG_SPLIT_W;
   static constexpr bool AT_LIMIT = CG == 2 && (LONGK || DSHEG_K512_DEEP || SPLIT);
-  static constexpr int STAGES = CG == 2 ? (LONGK ? (NARROW ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES + (DSHEG_K512_DEEP ? 1 : 0))
+  static constexpr int STAGES = CG == 2 ? (LONGK ? ((NARROW && !ROWLN) ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES + (DSHEG_K512_DEEP ? 1 : 0))
                                         : (BN == 128 ? 5 : 3);
   // pair kernels run at the smem limit: the dynamic smem base is required to be 1024-aligned (checked, traps otherwise)
   // and the per-tile bias/csum vectors are single-buffered (one extra epilogue barrier per tile)
@@ -84,7 +87,7 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false> struct Cf
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // W rows staged by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
-  static constexpr int VEC_BYTES = NVEC * 2 * BN * 4;
+  static constexpr int VEC_BYTES = ROWLN ? 3 * (2 * BN) * 4 + 2 * (BN / CPW) * BM * 8 : NVEC * 2 * BN * 4;
   static constexpr int PIPE_BYTES = SPLIT ? SA * A_BYTES + SW * B_BYTES : STAGES * STAGE_BYTES;
   static constexpr int NBAR_RING = SPLIT ? 2 * (SA + SW) : 2 * STAGES;   // ring barriers (full + empty)
   static_assert((NBAR_RING + 2 * NUM_ACC + NE + 1) * 8 <= BAR_BYTES, "barrier block too small");
@@ -108,6 +111,7 @@ struct Params {
   int prefetch;
   float* qsum; int qsoft_cols;   // ACT_QSOFT (appended: the offsets of the fields above are part of the validated kernels)
   const float* eshift; int expo_cols;   // ACT_EXPO (appended likewise)
+  const float* lnms_g; const float* lnms_b; const float* lnms_ss; int lnms_ld, lnms_B, lnms_T;   // ACT_LNMS (appended likewise)
 };
 
 // ---- spin on an mbarrier phase (PTX primitives: tc_prims.cuh) ---------------------------------------------------------------
@@ -163,7 +167,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   DSHEG_PDL_TRIGGER();   // PDL build: the next kernel may begin its own prologue now (it still waits for this grid's completion)
   constexpr bool LONGK = LONGK_ && CG == 2 && !OUTF32;
   constexpr bool NARROW = LONGK && RES != RES_BF16;
-  using C = Cfg<BN, CG, NARROW, LONGK>;
+  constexpr bool ROWLN = ACT == ACT_LNMS;   // both n-tiles of a row panel per CTA pair, LayerNorm over the full 2 * BN-column row
+  using C = Cfg<BN, CG, NARROW, LONGK, ROWLN>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE, STG_BYTES = C::STG_BYTES;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
   const int cta_stride = gridDim.x / CG, cta_first = blockIdx.x / CG;   // tiles are walked per CTA (pair)
@@ -191,6 +196,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int num_tiles = p.tiles_m * p.tiles_n;
+  // persistent tile walk (tiles are numbered n-fastest).  Default: every cta_stride-th tile.  ROWLN (tiles_n == 2): a CTA pair
+  // takes BOTH n-tiles of every cta_stride-th row panel back to back, so accumulator stage s always holds columns [s BN, (s+1) BN)
+  const int tile_first = ROWLN ? cta_first * 2 : cta_first;
+  auto tile_next = [&](int tile) { return ROWLN ? ((tile & 1) ? tile + 2 * cta_stride - 1 : tile + 1) : tile + cta_stride; };
 
   if (warp == 0 && lane == 0) {
 #if DSHEG_SPLIT_RINGS
@@ -227,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t full0 = is_a ? full_a(0) : full_w(0), empty0 = is_a ? empty_a(0) : empty_w(0);
       const uint32_t leader_full0 = mapa_rank(full0, 0);
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
         const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
         int seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -253,11 +262,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t leader_full0 = CG == 2 ? mapa_rank(full_bar(0), 0) : 0u;
-      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
         const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
         // prefetch the next tile's A panel into L2 (only when it is a new M-tile: the n-fastest order makes the
         // CTAs of one wave share a panel, so each panel is prefetched by the tiles_n CTAs that will read it)
-        const int next = tile + cta_stride;
+        const int next = tile_next(tile);
         const bool pf = p.prefetch == 1 && next < num_tiles && (next / p.tiles_n) != (tile / p.tiles_n);
         const int pf_m = pf ? ((next / p.tiles_n) * CG + (int)rank) * BM : 0;
         int seg = 0;
@@ -296,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int wstage = 0; uint32_t wphase = 0;   // W ring of the split-ring build
 #endif
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -345,7 +354,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* stg_gen = gen_base + (stg - smem_base);
     int acc = 0; uint32_t acc_phase = 0, res_phase = 0;
     const uint32_t leader_tempty0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : 0u;
-    for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+    if constexpr (ROWLN) {
+      // ===== ACT_LNMS: z = SiLU(LN(acc + bias) * (1 + scale) + shift) over the FULL row (tr:92-96 fused into ffn.linear2) =====
+      // A thread owns one row and the 64-column group `cg` of BOTH accumulator stages (columns s*BN + cg*64 ..): pass 1 reads
+      // them for (sum, sum of squares), the four column-group warps of a lane quadrant exchange partials through smem, pass 2
+      // re-reads TMEM (cheap), normalises, modulates with the row's sample, applies SiLU and stores 32-column boxes by TMA.
+      constexpr int NC = 2 * BN;                       // row width (= p.N)
+      float* bvec = vecs;                              // [NC] bias
+      float* ghalf = vecs + NC;                        // [NC] gamma / 2   (SiLU(x) = h + h tanh(h) with h = x / 2)
+      float* bhalf = vecs + 2 * NC;                    // [NC] beta / 2
+      float2* part = reinterpret_cast<float2*>(vecs + 3 * NC);   // [2][BN / CPW][BM]
+      for (int i = etid; i < NC; i += NE * 32) {
+        bvec[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+        ghalf[i] = 0.5f * __ldg(p.lnms_g + i);
+        bhalf[i] = 0.5f * __ldg(p.lnms_b + i);
+      }
+      epi_bar_sync<NE * 32>();
+      int pbuf = 0;
+      for (int unit = cta_first; unit < p.tiles_m; unit += cta_stride) {
+        const int m0 = (unit * CG + (int)rank) * BM + q * 32;
+        const int m = m0 + lane;
+        const bool row_ok = m < p.M;
+        mbar_wait(tfull_bar(0), acc_phase);
+        mbar_wait(tfull_bar(1), acc_phase);
+        tc_fence_after();
+        // ---- pass 1: statistics of this thread's 2 x 64 columns
+        float sx = 0.f, sq = 0.f;
+#pragma unroll
+        for (int stn = 0; stn < 2; ++stn) {
+#pragma unroll
+          for (int ch = 0; ch < CPW / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stn * BN + cg * CPW + ch * 32), r);
+            const float* bb = bvec + stn * BN + cg * CPW + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bb + j);
+              const float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+              const float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
+              sx += (v0 + v1) + (v2 + v3);
+              sq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, sq))));
+            }
+          }
+        }
+        float2* mypart = part + (size_t)pbuf * (BN / CPW) * BM;
+        mypart[cg * BM + q * 32 + lane] = make_float2(sx, sq);
+        // one barrier per panel: the partials are double-buffered, so nobody can overwrite buffer b before every warp has
+        // read it (a warp writes b again only after the NEXT panel's barrier, which needs all reads of this one)
+        epi_bar_sync<NE * 32>();
+        sx = 0.f; sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < BN / CPW; ++c) { const float2 t2 = mypart[c * BM + q * 32 + lane]; sx += t2.x; sq += t2.y; }   // fixed order
+        pbuf ^= 1;
+        const float mean = sx * (1.f / NC);
+        const float rstd = rsqrtf(fmaxf(sq * (1.f / NC) - mean * mean, 0.f) + 1e-5f);
+        const float nmr = -mean * rstd;
+        const float* sc = p.lnms_ss + (size_t)((row_ok ? m / p.lnms_T : 0) % p.lnms_B) * p.lnms_ld;
+        // ---- pass 2: normalise, modulate, SiLU, store
+#pragma unroll 1
+        for (int stn = 0; stn < 2; ++stn) {
+#pragma unroll
+          for (int ch = 0; ch < CPW / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stn * BN + cg * CPW + ch * 32), r);
+            if (ch == CPW / 32 - 1) {   // last TMEM read of this stage by this warp: hand it back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * stn);
+            }
+            const int n0 = stn * BN + cg * CPW + ch * 32;
+            // 2 KB box (32 rows x 64 B, SWIZZLE_64B: chunk c of row r at c ^ ((r >> 1) & 3)), reused for every 32-column chunk
+            if (lane == 0) bulk_wait_read0();   // the previous chunk's TMA store has finished reading the box
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {       // 8 columns at a time: compute, pack, store (keeps the live registers low)
+              float o[8];
+#pragma unroll
+              for (int k4 = 0; k4 < 8; k4 += 4) {
+                const int c = n0 + u * 8 + k4;
+                const float4 b4 = *reinterpret_cast<const float4*>(bvec + c);
+                const float4 g4 = *reinterpret_cast<const float4*>(ghalf + c), e4 = *reinterpret_cast<const float4*>(bhalf + c);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c)), h4 = __ldg(reinterpret_cast<const float4*>(sc + NC + c));
+                const float bi[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {e4.x, e4.y, e4.z, e4.w};
+                const float s1[4] = {s4.x, s4.y, s4.z, s4.w}, s2[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float one_s = 1.f + s1[e2];
+                  // h = x / 2,  x = ((v - mean) rstd gamma + beta) (1 + scale) + shift
+                  const float hh = fmaf(fmaf(__uint_as_float(r[u * 8 + k4 + e2]) + bi[e2], rstd, nmr), gg[e2] * one_s, fmaf(be[e2], one_s, 0.5f * s2[e2]));
+                  o[k4 + e2] = fmaf(hh, tanh_fast(hh), hh);
+                }
+              }
+              uint4 w;
+              w.x = pack_bf16x2(o[0], o[1]);
+              w.y = pack_bf16x2(o[2], o[3]);
+              w.z = pack_bf16x2(o[4], o[5]);
+              w.w = pack_bf16x2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(stg_gen + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = w;
+            }
+            fence_async_smem();                 // generic-proxy smem writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmOut, stg, n0, m0);
+              bulk_commit();
+            }
+          }
+        }
+        acc_phase ^= 1;
+      }
+    } else
+    for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
       const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
       const int n_tile0 = n_blk * BN;
       // ---- stage per-column vectors for this tile (double-buffered with the accumulator stage)
@@ -658,7 +776,7 @@ inline std::string& g_emu_error() { static std::string e; return e; }
 template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool LONGK_ = false>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG, LONGK_>;
-  using C = Cfg<BN, CG, (LONGK_ && CG == 2 && !OUTF32 && RES != RES_BF16), (LONGK_ && CG == 2 && !OUTF32)>;
+  using C = Cfg<BN, CG, (LONGK_ && CG == 2 && !OUTF32 && RES != RES_BF16), (LONGK_ && CG == 2 && !OUTF32), ACT == ACT_LNMS>;
 #ifdef DSHEG_EMU   // tests/emu: run the grid on the thread-level emulator (clusters of CG CTAs)
   (void)st;
   const CUtensorMap m0 = maps[0], m1 = maps[1], m2 = maps[2], m3 = maps[3], m4 = maps[4], m5 = maps[5], m6 = maps[6], m7 = maps[7];
@@ -703,6 +821,9 @@ inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Pa
   } else if (CG == 2 && longk && !ln && d.act == ACT_NONE && res == RES_BF16) {   // long K, residual: wide boxes, 5 stages
     return launch_variant<BN, false, ACT_NONE, RES_BF16, false, CG, true>(maps, p, grid, st);
   } else if (CG == 2 && longk && res == RES_NONE) {   // long K loops: 2 KB epilogue boxes, 6 stages
+    if constexpr (BN == 256 && CG == 2) {
+      if (!ln && d.act == ACT_LNMS) return launch_variant<BN, false, ACT_LNMS, RES_NONE, false, CG, true>(maps, p, grid, st);
+    }
     if (ln && d.act == ACT_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG, true>(maps, p, grid, st);
     if (ln && d.act == ACT_SILU) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
     if (!ln && d.act == ACT_NONE) return launch_variant<BN, false, ACT_NONE, RES_NONE, false, CG, true>(maps, p, grid, st);
@@ -782,6 +903,12 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
     *err = "ACT_QSOFT needs an LN-fold bf16-output GEMM with K < 768, no residual / duplicate store, qsum and qsoft_cols % 64 == 0";
     return cudaErrorInvalidValue;
   }
+  p.lnms_g = d.lnms_g; p.lnms_b = d.lnms_b; p.lnms_ss = d.lnms_ss; p.lnms_ld = d.lnms_ld; p.lnms_B = d.lnms_B; p.lnms_T = d.lnms_T;
+  if (d.act == ACT_LNMS && (cg != 2 || !longk || d.N != 2 * bn || d.csum || d.res || d.out_f32 || d.out2 || !d.lnms_g || !d.lnms_b ||
+                            !d.lnms_ss || d.lnms_B <= 0 || d.lnms_T <= 0 || (d.lnms_ld % 4))) {
+    *err = "ACT_LNMS needs the CTA-pair long-K kernel (M >= 4096, K >= 768) with N == 512, bf16 output, no LN fold / residual / duplicate store, and the LayerNorm / modulation operands";
+    return cudaErrorInvalidValue;
+  }
   p.eshift = d.eshift; p.expo_cols = d.expo_cols;
   if (d.act == ACT_EXPO && (!d.csum || !d.eshift || d.expo_cols <= 0 || (d.expo_cols % CPW) || d.expo_cols > d.N || d.res || d.out_f32 || d.Kp >= 768)) {
     *err = "ACT_EXPO needs an LN-fold bf16-output GEMM with K < 768, no residual, eshift and expo_cols % 64 == 0";
@@ -789,7 +916,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   }
   if ((d.ps_out || d.nullc) && (d.out_f32 || !d.res)) { *err = "fused LN statistics need a bf16-output residual GEMM"; return cudaErrorInvalidValue; }
   if (d.ps_in && (!d.csum || (d.ps_slots & 1))) { *err = "ps_in needs an LN-fold GEMM and an even slot count"; return cudaErrorInvalidValue; }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = d.act == ACT_LNMS ? p.tiles_m : p.tiles_m * p.tiles_n;   // ACT_LNMS: a pair owns whole row panels (both n-tiles)
   const int units = num_sms / cg;   // CTAs (or CTA pairs) that can be resident
   const int grid = (tiles < units ? tiles : units) * cg;
   {
@@ -804,6 +931,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
     // 3 = selective: only the tensor-bound GEMMs without a residual stream (round 1, global prefetch: ffn1 +15 %, but the
     // HBM-bound residual GEMMs lost 9 % because the prefetch competes with their residual / output traffic)
     p.prefetch = pf == 3 ? ((d.res || d.out_f32) ? 0 : 1) : pf;
+    if (d.act == ACT_LNMS) p.prefetch = 0;
   }
   if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, longk);
   return bn == 256 ? dispatch<256, 1>(d, maps, p, grid, st, err) : dispatch<128, 1>(d, maps, p, grid, st, err);

@@ -14,7 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]
 LOOP_ONLY = ["v5c1+qsoft", "v5c4+qsoft",   # + DSHEG_QSOFT=1: Q row-softmax in the QKV GEMM epilogue (needs the whole denoiser)
-             "v5c1+expo", "v5c2+expo", "v5c4+expo"]   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
+             "v5c1+expo", "v5c2+expo", "v5c4+expo",   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
+             "default+lnms",                          # + DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS)
+             "v5c4+expo+lnms"]                        # everything at once
 results = {}
 
 
@@ -53,12 +55,14 @@ def in_loop(batch, var):
         os.environ.pop("DSHEG_ATTN", None)
         os.environ.pop("DSHEG_QSOFT", None)
         os.environ.pop("DSHEG_EXPO", None)
+        os.environ.pop("DSHEG_FUSE_LNMS", None)
         if v:
-            os.environ["DSHEG_ATTN"] = v.split("+")[0]
-            if v.endswith("+qsoft"):
-                os.environ["DSHEG_QSOFT"] = "1"
-            if v.endswith("+expo"):
-                os.environ["DSHEG_EXPO"] = "1"
+            parts = v.split("+")
+            if parts[0] != "default":
+                os.environ["DSHEG_ATTN"] = parts[0]
+            for flag, env in (("qsoft", "DSHEG_QSOFT"), ("expo", "DSHEG_EXPO"), ("lnms", "DSHEG_FUSE_LNMS")):
+                if flag in parts[1:]:
+                    os.environ[env] = "1"
         eng = FusedUniDiffuser(sd, cfg, precision="bf16", max_batch=batch, max_frames=T)
         eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
         out = torch.empty_like(inp["x_T"])

@@ -38,6 +38,11 @@ for a in v5c1 v5c2 v5c4; do
   DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_${a}_expo.json 2> $O/r2_bench_attn_${a}_expo.err
 done
 
+# ffn.linear2 + LayerNorm / modulate / SiLU in ONE GEMM (ACT_LNMS: a CTA pair keeps both 256-column halves of its rows in TMEM): the
+# ln_mod_silu pass ("rowwise" column, about 41 ms per step) disappears, the ffn2 GEMM loses one ring stage and gains an exposed epilogue
+DSHEG_FUSE_LNMS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_lnms.json 2> $O/r2_bench_gemm_lnms.err
+DSHEG_ATTN=v5c4 DSHEG_EXPO=1 DSHEG_FUSE_LNMS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_all_v5c4_expo_lnms.json 2> $O/r2_bench_all_v5c4_expo_lnms.err
+
 # ---- programmatic dependent launch build (griddepcontrol in every bf16 hot-path kernel): parity first, then the latency-bound single-clip
 #      configs (B = 1: about 165 dependent kernels per call) and the headline
 PDL=$PWD/build_variants/libdiffsheg_b200_pdl.so
@@ -62,7 +67,7 @@ import glob, json, os
 for f in sorted(glob.glob("gpurun_out/r2_bench_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        print(f"{os.path.basename(f):44s} {d['value']:10.0f} frames/s  gemm {d['roofline']['achieved']:7.1f} TF/s ({d['roofline']['ms_per_step']:6.1f} ms)"
+        print(f"{os.path.basename(f):44s} {d['value']:10.0f} frames/s  gemm {d['roofline']['achieved']:7.1f} TF/s ({d['roofline']['ms_per_step']:6.1f} ms)  rowwise {d.get('rowwise', {}).get('ms_per_step', 0):5.1f} ms"
               f"  attention {d['roofline_attention']['achieved']:6.0f} GB/s ({d['roofline_attention']['ms_per_step']:6.1f} ms)  sm {d['clocks']['sm_mhz']}")
     except Exception as e:  # noqa: BLE001
         print(os.path.basename(f), "failed:", e)

@@ -12,7 +12,7 @@ import torch
 
 import emu
 
-ACT_NONE, ACT_SILU, ACT_GELU, ACT_QSOFT, ACT_EXPO = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_QSOFT, ACT_EXPO, ACT_LNMS = 0, 1, 2, 3, 4, 5
 
 
 class Args(ctypes.Structure):
@@ -26,7 +26,9 @@ class Args(ctypes.Structure):
                 ("ps_in", ctypes.c_void_p), ("cs_in", ctypes.c_void_p), ("ps_slots", ctypes.c_int32), ("ps_P", ctypes.c_int32),
                 ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32),
                 ("qsum", ctypes.c_void_p), ("qsoft_cols", ctypes.c_int32),
-                ("eshift", ctypes.c_void_p), ("expo_cols", ctypes.c_int32)]
+                ("eshift", ctypes.c_void_p), ("expo_cols", ctypes.c_int32),
+                ("lnms_g", ctypes.c_void_p), ("lnms_b", ctypes.c_void_p), ("lnms_ss", ctypes.c_void_p),
+                ("lnms_ld", ctypes.c_int32), ("lnms_B", ctypes.c_int32), ("lnms_T", ctypes.c_int32)]
 
 
 def bf16_bits(t):
@@ -46,7 +48,7 @@ def r64(k):
 
 
 def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, dup=False, stats_out=False, n_uncond=0,
-             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, qsoft_cols=0, expo_cols=0, expo_q_cols=0):
+             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, qsoft_cols=0, expo_cols=0, expo_q_cols=0, lnms_T=0, lnms_B=0):
     """Builds operands like the engine does (K laid out per segment padded to 64), runs the emulated kernel, returns
     (got, want, extras)."""
     g = torch.Generator().manual_seed(seed)
@@ -128,6 +130,15 @@ def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, d
         a.eshift, a.expo_cols = ptr(eshift), expo_cols
         extras["eshift"] = torch.from_numpy(eshift.astype(np.float64))
         want = torch.cat([torch.exp(want[:, :expo_cols] - extras["eshift"]), want[:, expo_cols:]], 1)
+    if act == ACT_LNMS:    # StylizationBlock prologue over the full row: SiLU(LN(v) * (1 + scale) + shift), sample = row // T
+        lg, lb = (1 + 0.2 * rnd(N)).float().numpy(), (0.2 * rnd(N)).float().numpy()
+        ss = np.ascontiguousarray((0.5 * rnd(lnms_B, 2 * N + 4)).float().numpy())        # ld = 2 N + 4: exercises the row stride
+        keep += [lg, lb, ss]
+        a.lnms_g, a.lnms_b, a.lnms_ss, a.lnms_ld, a.lnms_B, a.lnms_T = ptr(lg), ptr(lb), ptr(ss), 2 * N + 4, lnms_B, lnms_T
+        idx = (torch.arange(M) // lnms_T) % lnms_B
+        sst = torch.from_numpy(ss.astype(np.float64))[idx]
+        yn = torch.nn.functional.layer_norm(want, (N,), torch.from_numpy(lg.astype(np.float64)), torch.from_numpy(lb.astype(np.float64)), 1e-5)
+        want = torch.nn.functional.silu(yn * (1 + sst[:, :N]) + sst[:, N:2 * N])
     if act == ACT_SILU:
         want = torch.nn.functional.silu(want)
     elif act == ACT_GELU:
@@ -329,3 +340,19 @@ def test_qkv_exponential_epilogue_feeds_attention_end_to_end(variant, cg):
     ref = tk.reference(ex["raw"].reshape(Bn, T, 1536), g, b, ss)
     err = float((z - ref).abs().max() / ref.abs().max())
     assert torch.isfinite(z).all() and err < 1.5e-2, err
+
+
+@pytest.mark.parametrize("M,K,T,B,num_sms", [(600, 1024, 88, 3, 2), (1100, 768, 34, 2, 4), (256, 1024, 7, 40, 2), (700, 1024, 88, 2, 6)])
+def test_full_row_layernorm_modulate_silu_epilogue(M, K, T, B, num_sms):
+    """ACT_LNMS (opt-in, DSHEG_FUSE_LNMS=1): ffn.linear2 + the StylizationBlock prologue (transformer.py:178-181 + :92-96) in ONE
+    kernel -- a CTA pair owns both 256-column tiles of its row panel (one per TMEM accumulator stage), so LayerNorm statistics
+    span the full 512-wide row; persistent walks with more panels than pairs wrap the stage / accumulator parities."""
+    got, want, _ = run_gemm(M, 512, [K], act=ACT_LNMS, lnms_T=T, lnms_B=B, cg=2, num_sms=num_sms, seed=11)
+    check(got, want)
+
+
+@pytest.mark.parametrize("slow", ["EMU_DELAY_TMEM_LD", "EMU_DELAY_TMA", "EMU_DELAY_MMA"])
+def test_full_row_layernorm_epilogue_under_adversarial_timing(slow, monkeypatch):
+    monkeypatch.setenv(slow, "40")
+    got, want, _ = run_gemm(900, 512, [1024], act=ACT_LNMS, lnms_T=88, lnms_B=5, cg=2, num_sms=2, seed=12)
+    check(got, want)
