@@ -49,6 +49,9 @@ PDL=$PWD/build_variants/libdiffsheg_b200_pdl.so
 DSHEG_LIB=$PDL timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "denoise or loop or rows_are_independent" > $O/r2_pdl_parity.log 2>&1; echo "pdl parity rc=$?" >> $O/r2_rc.txt
 timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_default.jsonl 2>&1
 DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_pdl.jsonl 2>&1
+# single clip: 128-wide tiles double the CTAs that stream W and deepen the ring (5 stages) -- candidate heuristic for tiles < SMs / 4
+DSHEG_TC_BN=128 timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_bn128.jsonl 2>&1
+DSHEG_TC_BN=128 DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_bn128_pdl.jsonl 2>&1
 DSHEG_LIB=$PDL timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_pdl.json 2> $O/r2_bench_gemm_pdl.err
 
 # ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)
@@ -75,4 +78,4 @@ PY
 for v in default k512deep split73 split64; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2 " $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
 grep -c "Race reported\|hazard" $O/r2_racecheck_pairs_B24.log; grep -E "Write access|Read access" $O/r2_racecheck_pairs_B24.log | sed 's/(CUtensorMap.*//' | sort | uniq -c | sort -rn | head -8
 cat $O/r2_postprocess_bw.txt
-echo "== single clip (config 1), default vs PDL build"; cat $O/r2_configs1_default.jsonl $O/r2_configs1_pdl.jsonl | cut -c1-200; tail -2 $O/r2_pdl_parity.log
+echo "== single clip (config 1), default vs PDL build"; for f in default pdl bn128 bn128_pdl; do echo "-- $f"; cut -c1-200 $O/r2_configs1_$f.jsonl; done; tail -2 $O/r2_pdl_parity.log
