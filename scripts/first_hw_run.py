@@ -86,7 +86,10 @@ def in_loop(batch, var):
 
 def child(var):
     """One variant per process: a faulting kernel poisons only its own CUDA context."""
-    for batch in (3, int(os.environ.get("DSHEG_FIRST_RUN_BATCH", "950"))):   # DSHEG_FIRST_RUN_BATCH=0: parity at B = 3 only
+    # B = 3: single-CTA GEMM variants; B = 24 (4 224 rows): the CTA-pair variants, the only ones ACT_LNMS exists for and the
+    # ones ACT_EXPO / ACT_QSOFT run as at the headline batch; DSHEG_FIRST_RUN_BATCH=0: no full-size run
+    batches = [3] + ([24] if "+" in var else []) + [int(os.environ.get("DSHEG_FIRST_RUN_BATCH", "950"))]
+    for batch in batches:
         if batch <= 0:
             continue
         try:
@@ -105,7 +108,7 @@ if __name__ == "__main__":
     for var in VARIANTS + LOOP_ONLY:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--variant", var], cwd=ROOT, capture_output=True, text=True,
-                               timeout=150)
+                               timeout=240)
             got = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULTS ")]
             if got:
                 for k, v in json.loads(got[-1][8:]).items():

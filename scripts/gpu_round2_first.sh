@@ -1,18 +1,18 @@
 #!/bin/bash
-# FIRST gpurun call of the next round: everything written while no GPU was available, in ONE box session (~35 min).
+# FIRST gpurun call of the next round: everything written while no GPU was available, in ONE box session (~50 min; split it at the section comments if the budget is tight).
 # All of it is CPU-validated on the thread-level emulator (tests/test_emu_*.py); this call gives the hardware verdict and the
 # numbers that decide which candidates become defaults.
-#   1. first_hw_run.py   : post-processing kernels, attention v4 / v5c1 / v5c2 / v5c4 -- op parity, agreement with the default
-#                          inside dsheg_denoise, attention GB/s per variant at B = 3 and B = 950 (one subprocess per variant)
+#   1. first_hw_run.py   : post-processing kernels, attention v4 / v5c1 / v5c2 / v5c4 (+ qsoft / expo / lnms combinations) -- op parity and
+#                          agreement with the default inside dsheg_denoise at B = 3 (one subprocess per variant)
 #   2. GEMM candidates   : isolated shape sweep + full bench.py per experiment build (DSHEG_LIB) and prefetch mode
 #   3. bench.py          : default vs the best attention variant, back to back on this box
 #   4. racecheck         : full log of the CTA-pair GEMMs at B = 24 (open item in profiles/r01/NOTES_next_round.md)
 # Usage: bash scripts/build_variants.sh   (here, no GPU needed; the .so files travel)   then
-#        gpurun --timeout 2700 -- 'bash scripts/gpu_round2_first.sh'
+#        gpurun --timeout 3600 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
 O=gpurun_out
 [ -f build_variants/libdiffsheg_b200_split73.so ] && [ -f build_variants/libdiffsheg_b200_pdl.so ] || bash scripts/build_variants.sh > $O/r2_build_variants.log 2>&1
-timeout 1300 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
+DSHEG_FIRST_RUN_BATCH=0 timeout 1300 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
 
 # ---- GEMM candidates: isolated sweep (dsheg_bench_gemm, 10 iterations per shape) and the real loop
 for v in default k512deep split73 split64; do
@@ -55,7 +55,7 @@ DSHEG_TC_BN=128 DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $
 DSHEG_LIB=$PDL timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_pdl.json 2> $O/r2_bench_gemm_pdl.err
 
 # ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)
-for a in v5c1 v5c2 v5c4; do
+for a in v5c1 v5c4; do
   DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_denoise.py --batch 3 --calls 1 > $O/r2_${a}_memcheck.log 2>&1; echo "$a memcheck rc=$?" >> $O/r2_rc.txt
   DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/prof_denoise.py --batch 2 --calls 1 > $O/r2_${a}_racecheck.log 2>&1; echo "$a racecheck rc=$?" >> $O/r2_rc.txt
 done
