@@ -102,7 +102,7 @@ struct dsheg_handle {
   bool window_ready = false;
   // optional per-kernel-class timing (bench.py's roofline pass): CUDA events around each launch
   bool profiling = false;
-  struct ProfRec { cudaEvent_t e0, e1; int cat; double work; };
+  struct ProfRec { cudaEvent_t e0, e1; int cat; double work; const char* name; };   // name: static string (per-kernel table, DSHEG_PROF_TABLE=1)
   std::vector<ProfRec> prof;
 };
 
@@ -136,9 +136,10 @@ int fail(dsheg_handle* h, const std::string& msg) {
 
 // categories: 0 = GEMM (work = FLOPs), 1 = attention (work = algorithmic bytes), 2 = row-wise LN/stat kernels (bytes)
 enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROW = 2, PROF_NCAT = 3 };
-inline void prof_begin(dsheg_handle* h, cudaStream_t st, int cat, double work) {
+inline void prof_begin(dsheg_handle* h, cudaStream_t st, int cat, double work, const char* name = nullptr) {
   if (!h->profiling) return;
   dsheg_handle::ProfRec r;
+  r.name = name;
   cudaEventCreate(&r.e0);
   cudaEventCreate(&r.e1);
   r.cat = cat;
@@ -236,7 +237,7 @@ struct Runner {
     cudaError_t e;
     double ktrue = 0;
     for (int s = 0; s < d.nseg; ++s) ktrue += d.a[s].k;
-    prof_begin(h, st, PROF_GEMM, 2.0 * d.M * (double)d.N * ktrue);
+    prof_begin(h, st, PROF_GEMM, 2.0 * d.M * (double)d.N * ktrue, name);
     if (std::is_same<TA, bf16>::value && h->gemm_engine == 1) {
       std::string terr;
       e = tc::launch_gemm_tc(d, h->num_sms, st, &terr);
@@ -799,14 +800,36 @@ int dsheg_profile_end(dsheg_handle* h, double* ms, double* work, int64_t* count)
   h->profiling = false;
   CK(cudaDeviceSynchronize());
   for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; work[c] = 0; count[c] = 0; }
+  // DSHEG_PROF_TABLE=1: per-kernel-name breakdown of the profiled region on stderr (which GEMM shapes lose in the loop what they
+  // reach in isolation -- scripts/bench_gemm.py -- is the question every tuning round starts with)
+  const char* tb = getenv("DSHEG_PROF_TABLE");
+  const bool table = tb && !strcmp(tb, "1");
+  struct Agg { double ms = 0, work = 0; long n = 0; int cat = 0; };
+  std::vector<std::pair<std::string, Agg>> rows;
   for (auto& r : h->prof) {
     float t = 0.f;
     cudaEventElapsedTime(&t, r.e0, r.e1);
     ms[r.cat] += t; work[r.cat] += r.work; count[r.cat] += 1;
+    if (table) {
+      const std::string key = r.name ? r.name : (r.cat == PROF_ATTN ? "attention" : (r.cat == PROF_ROW ? "rowwise" : "gemm"));
+      size_t i = 0;
+      while (i < rows.size() && rows[i].first != key) ++i;
+      if (i == rows.size()) { rows.emplace_back(key, Agg{}); rows[i].second.cat = r.cat; }
+      rows[i].second.ms += t; rows[i].second.work += r.work; rows[i].second.n += 1;
+    }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
   h->prof.clear();
+  if (table) {
+    fprintf(stderr, "[dsheg profile] %-12s %7s %10s %12s\n", "kernel", "count", "ms", "rate");
+    for (auto& kv : rows) {
+      const Agg& a = kv.second;
+      const double rate = a.ms > 0 ? a.work / (a.ms * 1e-3) : 0.0;
+      fprintf(stderr, "[dsheg profile] %-12s %7ld %10.3f %9.1f %s\n", kv.first.c_str(), a.n, a.ms,
+              a.cat == PROF_GEMM ? rate / 1e12 : rate / 1e9, a.cat == PROF_GEMM ? "TF/s" : "GB/s");
+    }
+  }
   return 0;
 }
 

@@ -10,6 +10,7 @@
 # Usage: bash scripts/build_variants.sh   (here, no GPU needed; the .so files travel)   then
 #        gpurun --timeout 3600 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
+export DSHEG_PROF_TABLE=1   # per-kernel-name table of every profiled region on stderr (the .err file of each bench run)
 O=gpurun_out
 [ -f build_variants/libdiffsheg_b200_split73.so ] && [ -f build_variants/libdiffsheg_b200_pdl.so ] || bash scripts/build_variants.sh > $O/r2_build_variants.log 2>&1
 DSHEG_FIRST_RUN_BATCH=0 timeout 1300 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
