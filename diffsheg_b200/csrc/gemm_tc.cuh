@@ -158,6 +158,25 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
   return x;
 }
 
+// -DDSHEG_EPI_PACKED=1 (experiment build): the LayerNorm fold, bias add and activations of the generic epilogue run on packed fp32
+// (FFMA2 / FMUL2 / FADD2, column pairs): the K = 512 tiles are epilogue-sensitive, and the GELU epilogue spends 7 fp32
+// instructions per element (3.5 packed + MUFU.TANH).  Same arithmetic, same rounding; default build unchanged.
+#ifndef DSHEG_EPI_PACKED
+#define DSHEG_EPI_PACKED 0
+#endif
+template <int ACT> __device__ __forceinline__ float2 act_fast2(float2 x) {
+  if (ACT == ACT_SILU) {
+    const float2 h = fmul2(x, make_float2(0.5f, 0.5f));
+    return ffma2(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
+  }
+  if (ACT == ACT_GELU) {
+    const float2 h = fmul2(x, make_float2(0.5f, 0.5f));
+    const float2 u = fmul2(x, ffma2(make_float2(0.0356774081f, 0.0356774081f), fmul2(x, x), make_float2(0.7978845608f, 0.7978845608f)));
+    return ffma2(h, make_float2(tanh_fast(u.x), tanh_fast(u.y)), h);
+  }
+  return x;
+}
+
 template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool LONGK_>
 __global__ void __launch_bounds__(Cfg<BN, CG>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -588,6 +607,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bvec + j);
+#if DSHEG_EPI_PACKED
+          {
+            float2 p0 = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), p1 = make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (LN) {
+              const float4 c4 = *reinterpret_cast<const float4*>(bvec + BN + j);
+              const float2 rs2 = make_float2(rs, rs), rm2 = make_float2(rm, rm);
+              p0 = ffma2(rs2, p0, ffma2(rm2, make_float2(c4.x, c4.y), make_float2(b4.x, b4.y)));
+              p1 = ffma2(rs2, p1, ffma2(rm2, make_float2(c4.z, c4.w), make_float2(b4.z, b4.w)));
+            } else {
+              p0 = fadd2(p0, make_float2(b4.x, b4.y));
+              p1 = fadd2(p1, make_float2(b4.z, b4.w));
+            }
+            if (ACT == ACT_EXPO && expo) { p0 = make_float2(ex2_fast(p0.x), ex2_fast(p0.y)); p1 = make_float2(ex2_fast(p1.x), ex2_fast(p1.y)); }
+            p0 = act_fast2<ACT>(p0); p1 = act_fast2<ACT>(p1);
+            v[j] = p0.x; v[j + 1] = p0.y; v[j + 2] = p1.x; v[j + 3] = p1.y;
+            continue;
+          }
+#endif
           float t0 = __uint_as_float(r[j]), t1 = __uint_as_float(r[j + 1]), t2 = __uint_as_float(r[j + 2]), t3 = __uint_as_float(r[j + 3]);
           if (LN) {
             const float4 c4 = *reinterpret_cast<const float4*>(bvec + BN + j);

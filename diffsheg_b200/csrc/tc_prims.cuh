@@ -143,6 +143,10 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE operations per lane and issue slot (experiment build -DDSHEG_EPI_PACKED=1)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
 }  // namespace tc
 }  // namespace dsheg

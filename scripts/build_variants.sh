@@ -14,5 +14,7 @@ wait
 build split73 "-DDSHEG_SPLIT_RINGS=1" &                                    # K = 512 pair GEMMs: A ring 7 deep, W ring 3 deep, two producers
 build split64 "-DDSHEG_SPLIT_RINGS=1 -DDSHEG_SPLIT_A=6 -DDSHEG_SPLIT_W=4" &
 wait
+build epipacked "-DDSHEG_EPI_PACKED=1" &                                   # GEMM epilogue math on packed fp32 (FFMA2 / FMUL2 / FADD2)
 build pdl "-DDSHEG_PDL=1"                                                  # programmatic dependent launch in every bf16 hot-path kernel (griddepcontrol)
+wait
 ls -la build_variants

@@ -16,7 +16,7 @@ O=gpurun_out
 DSHEG_FIRST_RUN_BATCH=0 timeout 1300 python scripts/first_hw_run.py > $O/r2_first_hw_run.log 2>&1; echo "first_hw_run rc=$?" > $O/r2_rc.txt
 
 # ---- GEMM candidates: isolated sweep (dsheg_bench_gemm, 10 iterations per shape) and the real loop
-for v in default k512deep split73 split64; do
+for v in default k512deep split73 split64 epipacked; do
   lib=""; [ $v != default ] && lib="$PWD/build_variants/libdiffsheg_b200_$v.so"
   DSHEG_LIB=$lib timeout 200 python scripts/bench_gemm.py > $O/r2_gemm_sweep_$v.txt 2>&1
   DSHEG_LIB=$lib timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_$v.json 2> $O/r2_bench_gemm_$v.err
@@ -76,7 +76,7 @@ for f in sorted(glob.glob("gpurun_out/r2_bench_*.json")):
     except Exception as e:  # noqa: BLE001
         print(os.path.basename(f), "failed:", e)
 PY
-for v in default k512deep split73 split64; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2 " $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
+for v in default k512deep split73 split64 epipacked; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2 " $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
 grep -c "Race reported\|hazard" $O/r2_racecheck_pairs_B24.log; grep -E "Write access|Read access" $O/r2_racecheck_pairs_B24.log | sed 's/(CUtensorMap.*//' | sort | uniq -c | sort -rn | head -8
 cat $O/r2_postprocess_bw.txt
 echo "== single clip (config 1), default vs PDL build"; for f in default pdl bn128 bn128_pdl; do echo "-- $f"; cut -c1-200 $O/r2_configs1_$f.jsonl; done; tail -2 $O/r2_pdl_parity.log

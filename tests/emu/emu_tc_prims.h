@@ -249,6 +249,9 @@ inline void trap() {
 }
 inline float ex2_fast(float x) { return exp2f(x); }
 inline float tanh_fast(float x) { return tanhf(x); }
+inline float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float2 fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 
 }  // namespace tc
 }  // namespace dsheg

@@ -259,6 +259,23 @@ def test_k512_deep_ring_experiment_build(case):
     check(got, want, tanh_gelu=c.get("act") == ACT_GELU)
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if c.get("ln") or c.get("act") or c["cg"] == 1], ids=lambda c: f"M{c['M']}-N{c['N']}-cg{c['cg']}")
+def test_packed_fp32_epilogue_experiment_build(case):
+    """-DDSHEG_EPI_PACKED=1: LayerNorm fold, bias and SiLU / GELU on FFMA2 / FMUL2 / FADD2 column pairs (same arithmetic; the
+    emulator checks the pairing and the per-variant plumbing, hardware will tell whether the K = 512 tiles gain from it)."""
+    c = dict(case)
+    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
+    got, want, _ = run_gemm(M, N, ks, lib=emu.gemm_lib("DSHEG_EPI_PACKED=1"), **c)
+    check(got, want, out_f32=c.get("out_f32", False), tanh_gelu=c.get("act") == ACT_GELU)
+
+
+def test_packed_fp32_epilogue_build_with_exponential_columns():
+    got, want, ex = run_gemm(520, 1536, [512], ln=True, act=ACT_EXPO, expo_cols=1024, cg=2, num_sms=2, ps_in=True, seed=7,
+                             lib=emu.gemm_lib("DSHEG_EPI_PACKED=1"))
+    assert float(((got[:, :1024] - want[:, :1024]) / want[:, :1024]).abs().max()) < 6e-3
+    assert float((got[:, 1024:] - want[:, 1024:]).abs().max() / want[:, 1024:].abs().max()) < 8e-3
+
+
 @pytest.mark.parametrize("rings", [(7, 3), (2, 1), (3, 5)], ids=lambda r: f"A{r[0]}W{r[1]}")
 @pytest.mark.parametrize("case", [c for c in CASES if c["cg"] == 2 and c["ks"] == [512]], ids=lambda c: f"M{c['M']}-N{c['N']}")
 def test_split_ring_experiment_build(case, rings):
