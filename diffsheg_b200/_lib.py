@@ -80,6 +80,7 @@ SIGNATURES = {
     "dsheg_inv_standardize": (ctypes.c_int, [_P, _I32, _P, _P, _P, _I32, _I64, _I32, _P]),
     "dsheg_beat_axis_angle_to_euler": (ctypes.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "dsheg_op_linear": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "dsheg_op_linear_fused": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "dsheg_bench_gemm": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(ctypes.c_float)]),
     "dsheg_op_attention": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "dsheg_op_attention_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P]),

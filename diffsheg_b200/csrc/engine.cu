@@ -965,6 +965,46 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
   return 0;
 }
 
+// Op-level entry for the FUSED epilogue modes of the tcgen05 engine (test path only; bf16 operands / output like dsheg_op_linear):
+//   mode 4 (ACT_EXPO): out = rstd (A W^T - mu csum) + bias, its leading `i0` columns written as exp(. - eshift[n]);
+//                      aux0 = mu [M], aux1 = rstd [M], aux2 = eshift [i0], aux3 = csum [N] (row sums of the bf16-rounded W)
+//   mode 5 (ACT_LNMS): out = SiLU(LN_N(A W^T + bias) (1 + scale) + shift), N == 512;
+//                      aux0 = gamma [N], aux1 = beta [N], aux2 = scale|shift table [i1][i0] (row stride i0), i1 = table rows, i2 = T
+int dsheg_op_linear_fused(int32_t mode, const float* A, const float* W, const float* bias, const float* aux0, const float* aux1,
+                          const float* aux2, const float* aux3, float* out, int32_t M, int32_t N, int32_t K, int32_t i0, int32_t i1,
+                          int32_t i2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((mode != ACT_EXPO && mode != ACT_LNMS) || !A || !W || !out || (N % 64) || (K % 64)) {
+    g_create_error = "op_linear_fused: mode must be 4 (ACT_EXPO) or 5 (ACT_LNMS), N % 64 == 0, K % 64 == 0";
+    return 1;
+  }
+  bf16 *Ab = nullptr, *Wb = nullptr, *Ob = nullptr;
+  const bool ok = cudaMalloc(&Ab, (size_t)M * K * 2) == cudaSuccess && cudaMalloc(&Wb, (size_t)N * K * 2) == cudaSuccess &&
+                  cudaMalloc(&Ob, (size_t)M * N * 2) == cudaSuccess;
+  if (!ok) { g_create_error = "op_linear_fused: cudaMalloc"; return 1; }
+  f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, M, K, Ab, K);
+  f32_to_bf16_pad_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(W, N, K, Wb, K);
+  GemmDesc d;
+  d.nseg = 1; d.M = M; d.N = N; d.bias = bias; d.act = mode;
+  d.a[0].ptr = Ab; d.a[0].ld = K; d.a[0].k = K; d.w = Wb; d.Kp = K;
+  d.out = Ob; d.ldo = N;
+  if (mode == ACT_EXPO) { d.mu = aux0; d.rstd = aux1; d.eshift = aux2; d.csum = aux3; d.expo_cols = i0; }
+  else { d.lnms_g = aux0; d.lnms_b = aux1; d.lnms_ss = aux2; d.lnms_ld = i0; d.lnms_B = i1; d.lnms_T = i2; }
+  std::string terr;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = tc::launch_gemm_tc(d, sms, st, &terr);
+  if (e == cudaSuccess) bf16_to_f32_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(Ob, out, (size_t)M * N);
+  const cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(Ab); cudaFree(Wb); cudaFree(Ob);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    g_create_error = "op_linear_fused: " + terr + " " + cudaGetErrorString(e != cudaSuccess ? e : e2);
+    return 1;
+  }
+  return 0;
+}
+
 // Times one tcgen05 GEMM shape (bf16, device-resident random-ish data): mode 0 bias, 1 LN+bias, 2 LN+bias+SiLU,
 // 3 bias+bf16 residual (in place), 4 bias+GELU; bn = 0 (auto) / 128 / 256.  Returns the mean ms over `iters`.
 int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out) {
@@ -1043,6 +1083,14 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
                                                                             2 * av2::D);
   } else if (att && !strncmp(att, "v5c", 3) && (att[3] == '1' || att[3] == '2' || att[3] == '4') && !att[4]) {
     const cudaStream_t s5 = (cudaStream_t)stream;
+    const char* exo = getenv("DSHEG_EXPO");   // "1": the Q and K columns of `qkv` already hold exp(value - shift) (attn_v5<CL, 2>)
+    if (exo && !strcmp(exo, "1")) {
+      cudaError_t le2 = att[3] == '1' ? av5::launch_attn_v5<1, 2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
+                      : att[3] == '2' ? av5::launch_attn_v5<2, 2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
+                                      : av5::launch_attn_v5<4, 2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5);
+      if (le2 != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (v5, expo): ") + cudaGetErrorString(le2); return 1; }
+      return step_done("dsheg_op_attention_bf16");
+    }
     cudaError_t le = att[3] == '1' ? av5::launch_attn_v5<1>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
                    : att[3] == '2' ? av5::launch_attn_v5<2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
                                    : av5::launch_attn_v5<4>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5);

@@ -140,6 +140,17 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
                     const float* residual, float* out, int32_t M, int32_t N, int32_t K, int32_t act,
                     void* stream);
 
+/* The fused epilogue modes of the tcgen05 engine on one GEMM (test path only; bf16 operands / output, N % 64 == 0, K % 64 == 0):
+ *   mode 4: out = rstd (A W^T - mu csum) + bias with its leading i0 columns written as exp(. - eshift[n]) -- the softmax
+ *           numerators of transformer.py:122-123 with static shifts; aux0 = mu [M], aux1 = rstd [M], aux2 = eshift [i0],
+ *           aux3 = csum [N] (row sums of the bf16-rounded W);
+ *   mode 5: out = SiLU(LayerNorm_N(A W^T + bias) (1 + scale) + shift) -- ffn.linear2 + StylizationBlock prologue
+ *           (transformer.py:178-181, 92-96), N == 512, M >= 4096, K >= 768; aux0 = gamma [N], aux1 = beta [N],
+ *           aux2 = [i1][i0] table (scale at [0,N), shift at [N,2N), row = (m / i2) mod i1), i0 = row stride, i2 = frames per sample. */
+int dsheg_op_linear_fused(int32_t mode, const float* A, const float* W, const float* bias, const float* aux0,
+                          const float* aux1, const float* aux2, const float* aux3, float* out, int32_t M, int32_t N,
+                          int32_t K, int32_t i0, int32_t i1, int32_t i2, void* stream);
+
 /* Device timing of one tcgen05 GEMM shape (tuning / roofline aid): mode 0 bias, 1 LN-fold+bias,
  * 2 LN-fold+bias+SiLU, 3 bias+bf16 residual, 4 bias+GELU; bn 0 = auto, 128 or 256. */
 int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out);

@@ -30,6 +30,10 @@ def pytest_items():
     items = [("postprocess kernels (tests/test_postprocess.py)", ["tests/test_postprocess.py", "-k", "gpu_"])]
     items += [(f"attention op {v} (test_op_attention_bf16_tensor_core)", ["tests/test_gpu_parity.py", "-k", f"op_attention_bf16 and {v}"])
               for v in VARIANTS]   # one process per variant: a faulting kernel poisons only its own CUDA context
+    items += [("GEMM op ACT_EXPO (test_op_linear_exponential_epilogue)", ["tests/test_gpu_parity.py", "-k", "exponential_epilogue"]),
+              ("GEMM op ACT_LNMS (test_op_linear_layernorm_modulate_silu_epilogue)", ["tests/test_gpu_parity.py", "-k", "layernorm_modulate_silu_epilogue"])]
+    items += [(f"attention op {v} + static-shift numerators", ["tests/test_gpu_parity.py", "-k", f"static_shift_numerators and {v}"])
+              for v in ("v5c1", "v5c2", "v5c4")]
     for name, sel in items:
         t0 = time.time()
         try:
