@@ -7,6 +7,8 @@
 #   2. GEMM candidates   : isolated shape sweep + full bench.py per experiment build (DSHEG_LIB) and prefetch mode
 #   3. bench.py          : default vs the best attention variant, back to back on this box
 #   4. racecheck         : full log of the CTA-pair GEMMs at B = 24 (open item in profiles/r01/NOTES_next_round.md)
+# NB the variant libraries are loaded through the same ctypes table as the default one: after ANY change under diffsheg_b200/csrc or
+# include/, rebuild them HERE (bash scripts/build_variants.sh, about 5 min) before the gpurun call -- a stale variant fails to load.
 # Usage: bash scripts/build_variants.sh   (here, no GPU needed; the .so files travel)   then
 #        gpurun --timeout 3600 -- 'bash scripts/gpu_round2_first.sh'
 mkdir -p gpurun_out
