@@ -14,6 +14,14 @@ static std::string g_err;
 
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
 
+// dynamic per-lane operation counts since the last reset: {cp.async 16 B, ldmatrix, mma.sync, ex2, tanh, rcp, packed fp32}
+extern "C" void emu_op_counters(unsigned long long* out, int reset) {
+  prims::OpCounters& c = prims::op_counters();
+  const unsigned long long v[7] = {c.cp_async16, c.ldsm, c.mma, c.ex2, c.tanh, c.rcp, c.packed_fp32};
+  for (int i = 0; i < 7; ++i) out[i] = v[i];
+  if (reset) c = prims::OpCounters{};
+}
+
 // variant: 3 = attn_v3 (one CTA per sample), 4 = attn_v4 (cluster of two half-sample CTAs), 51 / 52 / 54 = attn_v5<CL = 1 / 2 / 4>
 // 151 / 152 / 154 = attn_v5<CL, PRE = 1>: Q columns hold softmax numerators, `qsum` [rows][8] their sums (else unused)
 // 251 / 252 / 254 = attn_v5<CL, PRE = 2>: Q and K columns hold exp(value - static shift) (ACT_EXPO epilogue), no side table

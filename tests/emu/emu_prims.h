@@ -13,6 +13,11 @@
 namespace dsheg {
 namespace prims {
 
+// dynamic operation counts (per LANE; the emulator is one OS thread, so plain counters): what a kernel variant executes per sample
+// on the pipes that bound the attention kernels -- MUFU (ex2 / tanh / rcp), tensor (mma), shared-memory matrix loads, cp.async
+struct OpCounters { unsigned long long cp_async16, ldsm, mma, ex2, tanh, rcp, packed_fp32; };
+inline OpCounters& op_counters() { static OpCounters c{}; return c; }
+
 inline uint8_t* smem_ptr(uint32_t addr, size_t bytes, const char* what) {
   emu::Cta* c = emu::self().cta;
   if ((size_t)addr + bytes > c->smem_bytes) {
@@ -23,6 +28,7 @@ inline uint8_t* smem_ptr(uint32_t addr, size_t bytes, const char* what) {
 }
 inline uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 inline void cp_async16(uint32_t dst, const void* src) {
+  ++op_counters().cp_async16;
   if (dst & 15u) emu::rt().error = "cp.async 16: misaligned shared destination";
   if (reinterpret_cast<uintptr_t>(src) & 15u) emu::rt().error = "cp.async 16: misaligned global source";
   memcpy(smem_ptr(dst, 16, "cp.async"), src, 16);
@@ -32,6 +38,7 @@ template <int N> inline void cp_async_wait_group() {}
 inline void cp_async_wait_all() {}
 
 inline void ldsm_common(uint32_t addr, bool trans, uint32_t (&r)[4]) {
+  ++op_counters().ldsm;
   if (addr & 15u) emu::rt().error = "ldmatrix: row address not 16-byte aligned";
   const int lane = emu::self().lane, g = lane >> 2, q = lane & 3;
   uint8_t(*slots)[64] = emu::warp_exchange(&addr, 4, "ldmatrix");
@@ -69,6 +76,7 @@ inline float bf16_half(uint32_t w, int hi) {
   return f;
 }
 inline void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  ++op_counters().mma;
   const int lane = emu::self().lane, g = lane >> 2, q = lane & 3;
   uint32_t mine[6] = {a[0], a[1], a[2], a[3], b0, b1};
   uint8_t(*slots)[64] = emu::warp_exchange(mine, sizeof(mine), "mma.sync");
@@ -93,12 +101,12 @@ template <int NTHREADS> inline void named_bar_sync(int id) {
   if (id < 1 || id > 15) { emu::rt().error = "bar.sync: barrier id out of range"; return; }
   emu::rendezvous(emu::self().cta->named[id], NTHREADS, "bar.sync (named)");
 }
-inline float ex2f(float x) { return exp2f(x); }
-inline float rcp_approx(float x) { return 1.0f / x; }
-inline float tanh_approx(float x) { return tanhf(x); }
-inline float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-inline float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-inline float2 fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float ex2f(float x) { ++op_counters().ex2; return exp2f(x); }
+inline float rcp_approx(float x) { ++op_counters().rcp; return 1.0f / x; }
+inline float tanh_approx(float x) { ++op_counters().tanh; return tanhf(x); }
+inline float2 ffma2(float2 a, float2 b, float2 c) { ++op_counters().packed_fp32; return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float2 fadd2(float2 a, float2 b) { ++op_counters().packed_fp32; return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 fmul2(float2 a, float2 b) { ++op_counters().packed_fp32; return make_float2(a.x * b.x, a.y * b.y); }
 
 inline uint32_t cluster_rank() { return emu::self().cta->rank; }
 inline void cluster_arrive() {

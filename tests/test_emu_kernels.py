@@ -124,6 +124,37 @@ def test_attention_with_both_softmax_numerators_done_by_the_gemm_epilogue(varian
     assert float((got - want).abs().max() / want.abs().max()) < 1e-2
 
 
+def _op_counts(variant, qkv, g, b, ss, **kw):
+    L = emu.lib()
+    buf = (ctypes.c_ulonglong * 7)()
+    L.emu_op_counters(buf, 1)
+    run_attention(variant, qkv, g, b, ss, **kw)
+    L.emu_op_counters(buf, 1)
+    names = ("cp_async16", "ldsm", "mma", "ex2", "tanh", "rcp", "packed_fp32")
+    return {n: buf[i] / 32.0 / qkv.shape[0] for i, n in enumerate(names)}     # warp-instructions per sample
+
+
+def test_dynamic_operation_counts_per_sample(capsys):
+    """What each attention generation EXECUTES per sample (T = 88) on the pipes that bound it -- MUFU, tensor, ldmatrix, cp.async --
+    counted by the emulator's primitives (ALU instructions are not counted: see the static SASS accounting in DESIGN 3.2).
+    Pins the claims of DESIGN 3.2: the static-shift variant issues no exponential at all and a third of v3's MUFU operations."""
+    Bn, T = 1, 88
+    qkv, g, b, ss = _case(Bn, T, None, seed=1)
+    rows = {"v3": _op_counts(3, qkv, g, b, ss), "v5c1": _op_counts(51, qkv, g, b, ss), "v5c4": _op_counts(54, qkv, g, b, ss),
+            "v5c1+expo": _op_counts(251, qkv, g, b, ss), "v5c4+expo": _op_counts(254, qkv, g, b, ss)}
+    with capsys.disabled():
+        print("\n[emulator] warp-level operations per sample (T = 88): " + "  ".join(f"{k}" for k in next(iter(rows.values()))))
+        for name, c in rows.items():
+            print(f"[emulator] {name:10s} " + "  ".join(f"{v:9.0f}" for v in c.values()))
+    elems = T * 512 / 32.0                               # one warp-wide op per 32 elements
+    assert rows["v3"]["ex2"] >= 2 * elems                 # exp of every q and k element
+    assert rows["v5c1+expo"]["ex2"] == 0 and rows["v5c4+expo"]["ex2"] == 0
+    assert rows["v5c1+expo"]["tanh"] <= 1.1 * elems       # SiLU only (rows are padded to the warp schedule)
+    mufu = lambda c: c["ex2"] + c["tanh"] + c["rcp"]
+    assert mufu(rows["v5c1+expo"]) < 0.45 * mufu(rows["v3"])
+    assert rows["v5c1"]["cp_async16"] == rows["v3"]["cp_async16"]      # same fill traffic: K and V tiles, 16 bytes per lane-op
+
+
 # ------------------------------------------------------------------------------------------------------------------------
 # elementwise kernels: sampler steps (sampler.cuh) and output post-processing (postprocess.cuh) on the emulator
 # ------------------------------------------------------------------------------------------------------------------------
