@@ -144,9 +144,7 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
       *reinterpret_cast<uint4*>(Vs + swz(r, c)) = make_uint4(0, 0, 0, 0);
     }
   }
-  // ---- 2. this warp's first Q m-tile (global -> registers) overlaps the cp.async latency
-  uint32_t qa[4][4];
-  if (half < n_mt) load_q(qhead, half * 16, T, g, q, qa);
+  uint32_t qa[4][4];   // this warp's current Q m-tile (loaded after step 4: 16 registers less through the A^T accumulation)
   if (!EXPO) {
     cp_async_wait_group<1>();   // this thread's K chunks have landed
     pair_sync(hl);              // ... and the partner's
@@ -223,34 +221,15 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
     pair_sync(hl);              // K' (numerators) and V complete in smem
   }
 
-  // ---- 3b. column sums of K' on the tensor core: ones[16 x 16] . K'[16 x 8] per k-step; this warp covers d = 32*half .. +31
+  // ---- 4. A^T[l][d] = sum_t V[t][l] K'[t][d] for this warp's l-half (two 16-row m-tiles), and -- on the same K' fragments --
+  //         the column sums of K' on the tensor core: ones[16 x 16] . K'[16 x 8] per k-step; this warp covers d = 32*half .. +31
+  float acc[2][8][4];
   {
     const int mat = lane >> 3, rr = lane & 7;
     const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
     float cs[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) { cs[nt][0] = cs[nt][1] = cs[nt][2] = cs[nt][3] = 0.f; }
-    for (int kt = 0; kt < n_mt; ++kt) {
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        uint32_t b0, b1, b2, b3;
-        const int r = kt * 16 + rr + ((mat & 1) << 3), c = 2 * (2 * half + np) + (mat >> 1);
-        ldsm_x4_trans(ks_addr + swz(r, c), b0, b1, b2, b3);
-        mma_bf16(cs[2 * np], ones, b0, b1);
-        mma_bf16(cs[2 * np + 1], ones, b2, b3);
-      }
-    }
-    if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-        *reinterpret_cast<float2*>(colsum + hl * HD + 32 * half + 8 * nt + 2 * q) = make_float2(cs[nt][0], cs[nt][1]);
-    }
-  }
-
-  // ---- 4. A^T[l][d] = sum_t V[t][l] K'[t][d] for this warp's l-half (two 16-row m-tiles)
-  float acc[2][8][4];
-  {
-    const int mat = lane >> 3, rr = lane & 7;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -271,10 +250,21 @@ attn_v5_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
         mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
         mma_bf16(acc[1][2 * np], a1, b0, b1);
         mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
+        if ((np >> 1) == half) {   // warp-uniform: d n-tiles 4 half .. 4 half + 3 belong to this warp's column-sum share
+          mma_bf16(cs[2 * (np & 1)], ones, b0, b1);
+          mma_bf16(cs[2 * (np & 1) + 1], ones, b2, b3);
+        }
       }
+    }
+    if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<float2*>(colsum + hl * HD + 32 * half + 8 * nt + 2 * q) = make_float2(cs[nt][0], cs[nt][1]);
     }
   }
   pair_sync(hl);  // both warps are done reading K' and V (and have published their column sums): K's tile receives A^T, V's tile Y
+  // ---- 2. this warp's first Q m-tile (global -> registers); its latency hides under the A^T rescale below
+  if (half < n_mt) load_q(qhead, half * 16, T, g, q, qa);
   {
     const float* csum = colsum + hl * HD;
 #pragma unroll
