@@ -15,8 +15,9 @@ sys.path.insert(0, ROOT)
 VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]
 LOOP_ONLY = ["v5c1+qsoft", "v5c4+qsoft",   # + DSHEG_QSOFT=1: Q row-softmax in the QKV GEMM epilogue (needs the whole denoiser)
              "v5c1+expo", "v5c2+expo", "v5c4+expo",   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
+             "v6+expo",                               # attn_v6: 4 warps per head, 64 registers, 32 warps per SM (needs the EXPO numerators)
              "default+lnms",                          # + DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS)
-             "v5c4+expo+lnms"]                        # everything at once
+             "v6+expo+lnms"]                        # everything at once
 results = {}
 
 
@@ -33,7 +34,7 @@ def pytest_items():
     items += [("GEMM op ACT_EXPO (test_op_linear_exponential_epilogue)", ["tests/test_gpu_parity.py", "-k", "exponential_epilogue"]),
               ("GEMM op ACT_LNMS (test_op_linear_layernorm_modulate_silu_epilogue)", ["tests/test_gpu_parity.py", "-k", "layernorm_modulate_silu_epilogue"])]
     items += [(f"attention op {v} + static-shift numerators", ["tests/test_gpu_parity.py", "-k", f"static_shift_numerators and {v}"])
-              for v in ("v5c1", "v5c2", "v5c4")]
+              for v in ("v5c1", "v5c2", "v5c4", "v6")]
     for name, sel in items:
         t0 = time.time()
         try:

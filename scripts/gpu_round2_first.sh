@@ -37,14 +37,16 @@ done
 
 # Q AND K softmax numerators with static, pack-time-proven shifts from the QKV epilogue (ACT_EXPO) + attn_v5<CL, 2>: the attention
 # kernel loses every exp / max outside its LayerNorm pass (static SASS 2872 -> 2096 for CL = 1); again watch BOTH columns
-for a in v5c1 v5c2 v5c4; do
+for a in v5c1 v5c2 v5c4 v6; do
   DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_attn_${a}_expo.json 2> $O/r2_bench_attn_${a}_expo.err
 done
 
 # ffn.linear2 + LayerNorm / modulate / SiLU in ONE GEMM (ACT_LNMS: a CTA pair keeps both 256-column halves of its rows in TMEM): the
 # ln_mod_silu pass ("rowwise" column, about 41 ms per step) disappears, the ffn2 GEMM loses one ring stage and gains an exposed epilogue
 DSHEG_FUSE_LNMS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_lnms.json 2> $O/r2_bench_gemm_lnms.err
-DSHEG_ATTN=v5c4 DSHEG_EXPO=1 DSHEG_FUSE_LNMS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_all_v5c4_expo_lnms.json 2> $O/r2_bench_all_v5c4_expo_lnms.err
+for a in v5c4 v6; do
+  DSHEG_ATTN=$a DSHEG_EXPO=1 DSHEG_FUSE_LNMS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_all_${a}_expo_lnms.json 2> $O/r2_bench_all_${a}_expo_lnms.err
+done
 
 # ---- programmatic dependent launch build (griddepcontrol in every bf16 hot-path kernel): parity first, then the latency-bound single-clip
 #      configs (B = 1: about 165 dependent kernels per call) and the headline
@@ -58,9 +60,9 @@ DSHEG_TC_BN=128 DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $
 DSHEG_LIB=$PDL timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2_bench_gemm_pdl.json 2> $O/r2_bench_gemm_pdl.err
 
 # ---- sanitizers: v5 variants (memcheck + racecheck at small batch), CTA-pair GEMM racecheck (full log)
-for a in v5c1 v5c4; do
-  DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_denoise.py --batch 3 --calls 1 > $O/r2_${a}_memcheck.log 2>&1; echo "$a memcheck rc=$?" >> $O/r2_rc.txt
-  DSHEG_ATTN=$a timeout 200 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/prof_denoise.py --batch 2 --calls 1 > $O/r2_${a}_racecheck.log 2>&1; echo "$a racecheck rc=$?" >> $O/r2_rc.txt
+for a in v5c1 v5c4 v6; do
+  DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_denoise.py --batch 3 --calls 1 > $O/r2_${a}_memcheck.log 2>&1; echo "$a memcheck rc=$?" >> $O/r2_rc.txt
+  DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 200 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/prof_denoise.py --batch 2 --calls 1 > $O/r2_${a}_racecheck.log 2>&1; echo "$a racecheck rc=$?" >> $O/r2_rc.txt
 done
 timeout 300 compute-sanitizer --tool racecheck python scripts/prof_denoise.py --batch 24 --calls 1 > $O/r2_racecheck_pairs_B24.log 2>&1; echo "racecheck pairs rc=$?" >> $O/r2_rc.txt
 timeout 200 python scripts/bench_postprocess.py > $O/r2_postprocess_bw.txt 2>&1
