@@ -12,12 +12,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]
-LOOP_ONLY = ["v5c1+qsoft", "v5c4+qsoft",   # + DSHEG_QSOFT=1: Q row-softmax in the QKV GEMM epilogue (needs the whole denoiser)
-             "v5c1+expo", "v5c2+expo", "v5c4+expo",   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
-             "v6+expo",                               # attn_v6: 4 warps per head, 64 registers, 32 warps per SM (needs the EXPO numerators)
-             "default+lnms",                          # + DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS)
-             "v6+expo+lnms"]                        # everything at once
+VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]   # op-level parity for all four; in-loop agreement below
+LOOP_ONLY = ["v5c1+expo", "v5c4+expo",   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
+             "v6+expo",                   # attn_v6: 4 warps per head, 64 registers, 32 warps per SM (needs the EXPO numerators)
+             "default+lnms",              # + DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS)
+             "v6+expo+lnms",              # everything at once
+             "v5c4+qsoft"]                # + DSHEG_QSOFT=1: Q row-softmax only (superseded by EXPO when that wins)
 results = {}
 
 
