@@ -22,10 +22,10 @@ def test_first_hardware_run_of_unvalidated_kernels():
     try:
         # parity only (B = 3): the B = 950 bandwidth comparison belongs to scripts/gpu_round2_first.sh, not to the test suite
         r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "first_hw_run.py")], cwd=ROOT, capture_output=True,
-                           text=True, timeout=480, env=dict(os.environ, DSHEG_FIRST_RUN_BATCH="0"))
+                           text=True, timeout=1500, env=dict(os.environ, DSHEG_FIRST_RUN_BATCH="0"))
     except subprocess.TimeoutExpired as e:
         print((e.stdout or b"").decode(errors="replace")[-3000:] if isinstance(e.stdout, bytes) else (e.stdout or "")[-3000:])
-        pytest.xfail("first hardware run timed out after 480 s (see the report above)")
+        pytest.xfail("first hardware run timed out after 1500 s (see the report above)")
     print("\n[first hardware run]\n" + r.stdout[-6000:])
     if r.returncode != 0:
         print(r.stderr[-3000:])
