@@ -28,9 +28,11 @@ import torch
 F32, BF16 = 0, 1
 
 # ACT_EXPO (gemm_tc.cuh) writes softmax numerators exp(v - shift) with STATIC shifts; |v - shift| must stay below this bound
-# (natural-log units) for EVERY possible input, so that neither the numerators (e^+-60 = 1e+-26) nor their sums over up to
-# 96 frames / 64 channels, nor the K'^T V and Q' A products (|V| < 1e6), leave the fp32 / bf16 exponent range
-EXPO_LIMIT = 60.0
+# (natural-log units) for EVERY possible input, so that neither the numerators (e^+-72 = 2e+-31, normal numbers in bf16 and fp32)
+# nor their sums over up to 96 frames / 64 channels, nor the K'^T V and Q' A products with |V| <= EXPO_V_LIMIT
+# (96 * e^72 * 1e3 = 2e36 < 3.4e38) leave the fp32 / bf16 exponent range
+EXPO_LIMIT = 72.0
+EXPO_V_LIMIT = 1.0e3
 
 
 def expo_shift(stored_w, bias, D):
@@ -44,11 +46,12 @@ def expo_shift(stored_w, bias, D):
     are exact replacements for the running maxima as long as the exponents stay inside EXPO_LIMIT.  `stored_w` are the weights
     AS STORED (bf16-rounded), so the bound is about the numbers the tensor core multiplies.  Returns [2 D] float64."""
     P = stored_w.shape[1]
-    w = stored_w[:2 * D]
+    w = stored_w[:3 * D]
     R = math.sqrt(P) * (w - w.mean(dim=1, keepdim=True)).norm(dim=1) * 1.01   # 1 %: fp32 accumulation and statistics
     q_bound = (R[:D] + bias[:D].abs()).max()
-    k_bound = R[D:].max()
-    if not (torch.isfinite(R).all() and float(q_bound) <= EXPO_LIMIT and float(k_bound) <= EXPO_LIMIT):
+    k_bound = R[D:2 * D].max()
+    v_bound = (R[2 * D:] + bias[2 * D:3 * D].abs()).max()    # |V| itself enters the products linearly
+    if not (torch.isfinite(R).all() and float(q_bound) <= EXPO_LIMIT and float(k_bound) <= EXPO_LIMIT and float(v_bound) <= EXPO_V_LIMIT):
         return None
     return torch.cat([torch.zeros(D, dtype=torch.float64), bias[D:2 * D].to(torch.float64)])
 

@@ -258,8 +258,8 @@ def test_op_attention_with_static_shift_numerators(L, Bn, T, variant, monkeypatc
     g, b = 1 + 0.1 * torch.randn(D, device="cuda"), 0.1 * torch.randn(D, device="cuda")
     ss = 0.5 * torch.randn(Bn, 2 * D, device="cuda")
     q, k, v = qkv.double().split(D, dim=-1)
-    sq = (20 * torch.randn(Bn, T, H, 1, device="cuda").double()).clamp(-50, 50)
-    sk = (20 * torch.randn(Bn, 1, D, device="cuda").double()).clamp(-50, 50)
+    sq = (25 * torch.randn(Bn, T, H, 1, device="cuda").double()).clamp(-64, 64)
+    sk = (25 * torch.randn(Bn, 1, D, device="cuda").double()).clamp(-64, 64)
     pre = qkv.clone()
     pre[..., :D] = torch.exp(q.view(Bn, T, H, -1) - sq).reshape(Bn, T, D).bfloat16()
     pre[..., D:2 * D] = torch.exp(k - sk).bfloat16()
