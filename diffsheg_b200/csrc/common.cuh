@@ -134,7 +134,7 @@ struct GemmDesc {
   float* qsum = nullptr;          // [M][qsoft_cols / 64] row sums of the numerators (fp32)
   int qsoft_cols = 0;             // leading columns (multiple of 64) that hold Q
   // ---- ACT_EXPO: exp(v - eshift[n]) for the leading expo_cols columns (Q and K of the fused QKV projection, tr:122-123) ---
-  const float* eshift = nullptr;  // [expo_cols] static per-column shifts (Q: 0, K: folded bias), fp32
+  const float* eshift = nullptr;  // [expo_cols] static per-column shifts (Q: one value per head, K: folded bias), fp32
   int expo_cols = 0;              // leading columns (multiple of 64) written as exponentials
   // ---- ACT_LNMS: LayerNorm (gamma, beta over the N == 512 output columns) + per-sample modulation + SiLU in the epilogue -----
   const float* lnms_g = nullptr;  // [N] LayerNorm weight

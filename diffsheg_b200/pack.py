@@ -35,25 +35,27 @@ EXPO_LIMIT = 72.0
 EXPO_V_LIMIT = 1.0e3
 
 
-def expo_shift(stored_w, bias, D):
+def expo_shift(stored_w, bias, D, head_dim=64):
     """Static softmax shifts for the Q | K columns of an LN-folded QKV projection, or None when no safe ones exist.
 
     The GEMM computes v[n] = xhat . W'[n] + b'[n] with xhat = (h - mean) * rstd, the LayerNorm-ed hidden row (tr:119-123):
     sum(xhat) = 0 and ||xhat||_2 <= sqrt(P), whatever h is.  Cauchy-Schwarz on the centred weight row gives
     |v[n] - b'[n]| <= R[n] = sqrt(P) * ||W'[n] - mean(W'[n])||_2  for every input.  softmax is shift-invariant, so
       * K (softmax over time, tr:123, one shift per column): shift = b'[n], exponent within +-R[n];
-      * Q (softmax over the 64 channels of a head, tr:122, one shift per row and head): shift = 0, exponent within +-(R[n] + |b'[n]|)
+      * Q (softmax over the 64 channels of a head, tr:122, one shift per row and head): shift = mean of b' over the head,
+        exponent within +-(R[n] + |b'[n] - shift|)
     are exact replacements for the running maxima as long as the exponents stay inside EXPO_LIMIT.  `stored_w` are the weights
     AS STORED (bf16-rounded), so the bound is about the numbers the tensor core multiplies.  Returns [2 D] float64."""
     P = stored_w.shape[1]
     w = stored_w[:3 * D]
     R = math.sqrt(P) * (w - w.mean(dim=1, keepdim=True)).norm(dim=1) * 1.01   # 1 %: fp32 accumulation and statistics
-    q_bound = (R[:D] + bias[:D].abs()).max()
+    q_shift = bias[:D].to(torch.float64).reshape(-1, head_dim).mean(dim=1, keepdim=True).expand(-1, head_dim).reshape(D)
+    q_bound = (R[:D] + (bias[:D] - q_shift).abs()).max()
     k_bound = R[D:2 * D].max()
     v_bound = (R[2 * D:] + bias[2 * D:3 * D].abs()).max()    # |V| itself enters the products linearly
     if not (torch.isfinite(R).all() and float(q_bound) <= EXPO_LIMIT and float(k_bound) <= EXPO_LIMIT and float(v_bound) <= EXPO_V_LIMIT):
         return None
-    return torch.cat([torch.zeros(D, dtype=torch.float64), bias[D:2 * D].to(torch.float64)])
+    return torch.cat([q_shift, bias[D:2 * D].to(torch.float64)])
 
 
 def _r64(k):
@@ -138,7 +140,8 @@ class Packer:
         Wqkv = torch.cat([g(sa + ".query.weight"), g(sa + ".key.weight"), g(sa + ".value.weight")], 0)
         bqkv = torch.cat([g(sa + ".query.bias"), g(sa + ".key.bias"), g(sa + ".value.bias")], 0)
         stored, bfold = self.lin_ln_fold(name + ".qkv", Wqkv, bqkv, g(sa + ".norm.weight"), g(sa + ".norm.bias"))
-        es = expo_shift(stored, bfold, Wqkv.shape[0] // 3)   # optional tensor: present only when static shifts are provably safe
+        Dm = Wqkv.shape[0] // 3
+        es = expo_shift(stored, bfold, Dm, Dm // self.cfg["num_heads"])   # optional tensor: present only when static shifts are provably safe
         if es is not None:
             self.put_f32(name + ".qkv.eshift", es)
         self.put_f32(name + ".sa.g", g(sa + ".proj_out.norm.weight"))
