@@ -14,8 +14,8 @@
 //   * Y = Q' A: a warp owns one l-half and every second m-tile (16 accumulator registers); Q fragments are loaded just in time;
 //   * LayerNorm pass: 8 columns per lane (16 registers of folded constants), rows re-read from shared memory after the
 //     cluster barrier instead of being carried across it;
-// so the kernel fits __launch_bounds__(256, 4): 64 registers, 4 CTAs (clusters of 4 = one sample, 2 heads per CTA) = 32 warps
-// per SM -- twice the latency-hiding of v5 at the same 53 KB of shared memory per CTA.  The price is redundancy: the four warps
+// so the kernel fits 64 registers: __launch_bounds__(256, 4) as clusters of 4 CTAs (2 heads each, 53 KB) or (512, 2) as clusters of 2
+// (4 heads each, 101 KB) = 32 warps per SM either way -- twice the latency-hiding of v5 at the same shared-memory footprint.  The price is redundancy: the four warps
 // of a head each read all K' fragments (+29 % ldmatrix) and the two l-halves both load Q and sum its rows (+12 % mma).
 // HBM traffic is unchanged: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample.
 #pragma once
@@ -31,27 +31,32 @@ using prims::smem_addr; using prims::cp_async16; using prims::cp_async_commit; u
 using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::tanh_approx; using prims::rcp_approx;
 using prims::ffma2; using prims::fadd2; using prims::fmul2;
 
-constexpr int CL = 4;                       // CTAs per sample (one thread-block cluster)
-constexpr int NH_CTA = 8 / CL;              // heads per CTA
-constexpr int WPH = 4;                      // warps per head
-constexpr int NWARPS = NH_CTA * WPH;        // 8
-constexpr int NTHREADS = 32 * NWARPS;       // 256
-constexpr int COLS = D / CL;                // LayerNorm columns owned by this CTA (128)
-constexpr int LPR = COLS / 8;               // lanes per row in the LayerNorm pass (8 columns per lane)
-constexpr int RPI = 32 / LPR;               // rows per warp iteration (2)
-constexpr int LN_ITERS = TP / (NWARPS * RPI);   // 6
-constexpr int SUM_BYTES = NH_CTA * HD * 4;      // [head][64] column sums of K'
-constexpr int STAT_BYTES = CL * TP * 8;         // [source rank][row] (sum, sum of squares)
-constexpr int SMEM_BYTES = NH_CTA * 2 * TILE_BYTES + SUM_BYTES + STAT_BYTES;   // 49152 + 512 + 3072
-constexpr int CTAS_PER_SM = 4;
-static_assert(TP % (NWARPS * RPI) == 0 && TP % 16 == 0, "row schedule");
+constexpr int WPH = 4;                        // warps per head
+template <int CL> struct Cfg {                // CL = CTAs per sample (one thread-block cluster): 4 (2 heads, 256 threads) or 2 (4 heads, 512)
+  static_assert(CL == 2 || CL == 4, "2 or 4 CTAs per sample");
+  static constexpr int NH_CTA = 8 / CL;              // heads per CTA
+  static constexpr int NWARPS = NH_CTA * WPH;        // 8 / 16
+  static constexpr int NTHREADS = 32 * NWARPS;       // 256 / 512
+  static constexpr int COLS = D / CL;                // LayerNorm columns owned by this CTA (128 / 256)
+  static constexpr int LPR = COLS / 8;               // lanes per row in the LayerNorm pass (8 columns per lane)
+  static constexpr int RPI = 32 / LPR;               // rows per warp iteration (2 / 1)
+  static constexpr int LN_ITERS = TP / (NWARPS * RPI);   // 6
+  static constexpr int SUM_BYTES = NH_CTA * HD * 4;      // [head][64] column sums of K'
+  static constexpr int STAT_BYTES = CL * TP * 8;         // [source rank][row] (sum, sum of squares)
+  static constexpr int SMEM_BYTES = NH_CTA * 2 * TILE_BYTES + SUM_BYTES + STAT_BYTES;   // 52 736 / 101 376
+  static constexpr int CTAS_PER_SM = 1024 / NTHREADS;    // 32 warps per SM either way
+  static_assert(TP % (NWARPS * RPI) == 0 && TP % 16 == 0, "row schedule");
+};
 
 __device__ __forceinline__ void head_sync(int hl) { prims::named_bar_sync<32 * WPH>(hl + 1); }
 
-__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM)
+template <int CL>
+__global__ void __launch_bounds__(Cfg<CL>::NTHREADS, Cfg<CL>::CTAS_PER_SM)
 attn_v6_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B, const float* __restrict__ ln_g,
                const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
   DSHEG_PDL_ENTER();
+  using C = Cfg<CL>;
+  constexpr int NH_CTA = C::NH_CTA, NWARPS = C::NWARPS, COLS = C::COLS, LPR = C::LPR, RPI = C::RPI, LN_ITERS = C::LN_ITERS, SUM_BYTES = C::SUM_BYTES;
   DSHEG_DYN_SMEM(sm, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hl = warp >> 2, wq = warp & 3;             // local head, warp of the head's quartet
@@ -249,18 +254,21 @@ attn_v6_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
 }
 
 #ifndef DSHEG_EMU
-// host launcher: thread-block clusters of 4 CTAs (one cluster per sample)
+// host launcher: thread-block clusters of CL CTAs (one cluster per sample)
+template <int CL>
 inline cudaError_t launch_attn_v6(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
                                   const float* ss, int ss_ld, cudaStream_t st) {
+  using C = Cfg<CL>;
+  auto kern = attn_v6_kernel<CL>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_samples * CL); cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(n_samples * CL); cfg.blockDim = dim3(C::NTHREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
   attr[na].id = cudaLaunchAttributeClusterDimension;
@@ -272,7 +280,7 @@ inline cudaError_t launch_attn_v6(const bf16* qkv, bf16* z, int n_samples, int T
   ++na;
 #endif
   cfg.attrs = attr; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, attn_v6_kernel, qkv, z, T, ssB, ln_g, ln_b, ss, ss_ld);
+  return cudaLaunchKernelEx(&cfg, kern, qkv, z, T, ssB, ln_g, ln_b, ss, ss_ld);
 }
 #endif  // DSHEG_EMU
 

@@ -101,7 +101,7 @@ def test_attention_with_q_softmax_done_by_the_gemm_epilogue(variant, Bn, T):
     assert float((got - want).abs().max() / want.abs().max()) < 1e-2
 
 
-@pytest.mark.parametrize("variant", [251, 252, 254, 6])
+@pytest.mark.parametrize("variant", [251, 252, 254, 6, 62])
 @pytest.mark.parametrize("Bn,T,spread", [(2, 88, 1.0), (1, 34, 12.0), (1, 13, 30.0), (1, 96, 3.0), (1, 16, 5.0), (2, 17, 5.0), (1, 7, 5.0)])
 def test_attention_with_both_softmax_numerators_done_by_the_gemm_epilogue(variant, Bn, T, spread):
     """EXPO (PRE = 2): Q and K columns arrive as exp(value - static shift) in bf16 (ACT_EXPO epilogue), with shifts that are
@@ -142,11 +142,11 @@ def test_dynamic_operation_counts_per_sample(capsys):
     qkv, g, b, ss = _case(Bn, T, None, seed=1)
     rows = {"v3": _op_counts(3, qkv, g, b, ss), "v5c1": _op_counts(51, qkv, g, b, ss), "v5c4": _op_counts(54, qkv, g, b, ss),
             "v5c1+expo": _op_counts(251, qkv, g, b, ss), "v5c4+expo": _op_counts(254, qkv, g, b, ss),
-            "v6 (+expo)": _op_counts(6, qkv, g, b, ss)}
+            "v6 (+expo)": _op_counts(6, qkv, g, b, ss), "v6c2 (+expo)": _op_counts(62, qkv, g, b, ss)}
     with capsys.disabled():
         print("\n[emulator] warp-level operations per sample (T = 88): " + "  ".join(f"{k}" for k in next(iter(rows.values()))))
         for name, c in rows.items():
-            print(f"[emulator] {name:10s} " + "  ".join(f"{v:9.0f}" for v in c.values()))
+            print(f"[emulator] {name:12s} " + "  ".join(f"{v:9.0f}" for v in c.values()))
     elems = T * 512 / 32.0                               # one warp-wide op per 32 elements
     assert rows["v3"]["ex2"] >= 2 * elems                 # exp of every q and k element
     assert rows["v5c1+expo"]["ex2"] == 0 and rows["v5c4+expo"]["ex2"] == 0
