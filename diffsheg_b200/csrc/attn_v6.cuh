@@ -9,14 +9,14 @@
 // Why another kernel: v3 / v5 hold 16 warps per SM (512 threads x 128 registers = the whole register file) and issue on 43 % of
 // the slots.  With the softmaxes gone from the kernel, the register hogs are the A^T accumulators (64 per lane) and the packed
 // rows the LayerNorm pass keeps across the cluster barrier.  v6 gives a head FOUR warps instead of two:
-//   * A^T: one 16-row m-tile of l per warp (32 accumulator registers instead of 64); the K' column sums ride on the same
-//     fragments (ones . K' on the tensor core), 16 columns per warp;
+//   * A^T: one 32 x 32 quadrant (l-half x d-half) per warp (32 accumulator registers instead of 64); the K' column sums ride on
+//     the same fragments (ones . K' on the tensor core), 16 columns per warp;
 //   * Y = Q' A: a warp owns one l-half and every second m-tile (16 accumulator registers); Q fragments are loaded just in time;
 //   * LayerNorm pass: 8 columns per lane (16 registers of folded constants), rows re-read from shared memory after the
 //     cluster barrier instead of being carried across it;
 // so the kernel fits 64 registers: __launch_bounds__(256, 4) as clusters of 4 CTAs (2 heads each, 53 KB) or (512, 2) as clusters of 2
-// (4 heads each, 101 KB) = 32 warps per SM either way -- twice the latency-hiding of v5 at the same shared-memory footprint.  The price is redundancy: the four warps
-// of a head each read all K' fragments (+29 % ldmatrix) and the two l-halves both load Q and sum its rows (+12 % mma).
+// (4 heads each, 101 KB) = 32 warps per SM either way -- twice the latency-hiding of v5 at the same shared-memory footprint.  The price is redundancy: a quadrant warp
+// re-reads its half of V and of K' (+14 % ldmatrix) and the two l-halves both load Q and sum its rows (+5 % mma).
 // HBM traffic is unchanged: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample.
 #pragma once
 #include "attn_v5.cuh"
@@ -101,43 +101,57 @@ attn_v6_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
   cp_async_wait_group<0>();   // this thread's chunks
   head_sync(hl);              // ... and those of the head's other threads: K' and V complete in smem
 
-  // ---- 2. A^T[l][d] = sum_t V[t][l] K'[t][d] for this warp's 16 l-rows, and -- on the same K' fragments -- the column sums
-  //         of K' for d = 16 wq .. 16 wq + 15 (ones[16 x 16] . K'[16 x 8] on the tensor core)
+  // ---- 2. A^T[l][d] = sum_t V[t][l] K'[t][d]: the head's four warps take the four 32 x 32 quadrants (l-half lq, d-half dq), so a
+  //         warp reads half of V and half of K' per k-step (4 ldmatrix.x4 for 8 mma).  On the same K' fragments: the column sums of
+  //         K' for d = 32 dq + 16 lq .. + 15 (ones[16 x 16] . K'[16 x 8] on the tensor core)
   {
-    float acc[8][4], cs[2][4];
+    const int lq = wq & 1, dq = wq >> 1;
+    float acc[2][4][4], cs[2][4];
     const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-    cs[0][0] = cs[0][1] = cs[0][2] = cs[0][3] = cs[1][0] = cs[1][1] = cs[1][2] = cs[1][3] = 0.f;
-    for (int kt = 0; kt < n_mt; ++kt) {  // 16 frames per k-step
-      uint32_t a[4];
-      ldsm_x4_trans(vs_addr + swz(kt * 16 + rr + ((mat >> 1) << 3), 2 * wq + (mat & 1)), a[0], a[1], a[2], a[3]);
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {  // two d n-tiles per ldmatrix.x4
+      for (int nt = 0; nt < 4; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
+    cs[0][0] = cs[0][1] = cs[0][2] = cs[0][3] = cs[1][0] = cs[1][1] = cs[1][2] = cs[1][3] = 0.f;
+#pragma unroll 1
+    for (int kt = 0; kt < n_mt; ++kt) {  // 16 frames per k-step
+      uint32_t a0[4], a1[4];
+      {
+        const int r = kt * 16 + rr + ((mat >> 1) << 3);
+        ldsm_x4_trans(vs_addr + swz(r, 4 * lq + (mat & 1)), a0[0], a0[1], a0[2], a0[3]);
+        ldsm_x4_trans(vs_addr + swz(r, 4 * lq + 2 + (mat & 1)), a1[0], a1[1], a1[2], a1[3]);
+      }
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {  // two d n-tiles per ldmatrix.x4
         uint32_t b0, b1, b2, b3;
-        ldsm_x4_trans(ks_addr + swz(kt * 16 + rr + ((mat & 1) << 3), 2 * np + (mat >> 1)), b0, b1, b2, b3);
-        mma_bf16(acc[2 * np], a, b0, b1);
-        mma_bf16(acc[2 * np + 1], a, b2, b3);
-        if (np == wq) {   // warp-uniform
+        ldsm_x4_trans(ks_addr + swz(kt * 16 + rr + ((mat & 1) << 3), 4 * dq + 2 * np + (mat >> 1)), b0, b1, b2, b3);
+        mma_bf16(acc[0][2 * np], a0, b0, b1);
+        mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
+        mma_bf16(acc[1][2 * np], a1, b0, b1);
+        mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
+        if (np == lq) {   // warp-uniform: the two warps of a d-half share its column sums
           mma_bf16(cs[0], ones, b0, b1);
           mma_bf16(cs[1], ones, b2, b3);
         }
       }
     }
     if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
-      *reinterpret_cast<float2*>(colsum + hl * HD + 16 * wq + 2 * q) = make_float2(cs[0][0], cs[0][1]);
-      *reinterpret_cast<float2*>(colsum + hl * HD + 16 * wq + 8 + 2 * q) = make_float2(cs[1][0], cs[1][1]);
+      *reinterpret_cast<float2*>(colsum + hl * HD + 32 * dq + 16 * lq + 2 * q) = make_float2(cs[0][0], cs[0][1]);
+      *reinterpret_cast<float2*>(colsum + hl * HD + 32 * dq + 16 * lq + 8 + 2 * q) = make_float2(cs[1][0], cs[1][1]);
     }
     head_sync(hl);  // all four warps are done reading K' and V and have published their column sums: K's tile receives A^T
-    const float* csum = colsum + hl * HD;
-    const int l = 16 * wq + g;
+    const float* csum = colsum + hl * HD + 32 * dq;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) {
       const float2 s2 = *reinterpret_cast<const float2*>(csum + 8 * nt + 2 * q);
       const float2 inv = make_float2(rcp_approx(s2.x), rcp_approx(s2.y));
-      const float2 lo = fmul2(make_float2(acc[nt][0], acc[nt][1]), inv), hi = fmul2(make_float2(acc[nt][2], acc[nt][3]), inv);
-      *reinterpret_cast<uint32_t*>(Ks + swz(l, nt) + q * 4) = pack2(lo.x, lo.y);
-      *reinterpret_cast<uint32_t*>(Ks + swz(l + 8, nt) + q * 4) = pack2(hi.x, hi.y);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int l = 32 * lq + 16 * mi + g;
+        const float2 lo = fmul2(make_float2(acc[mi][nt][0], acc[mi][nt][1]), inv), hi = fmul2(make_float2(acc[mi][nt][2], acc[mi][nt][3]), inv);
+        *reinterpret_cast<uint32_t*>(Ks + swz(l, 4 * dq + nt) + q * 4) = pack2(lo.x, lo.y);
+        *reinterpret_cast<uint32_t*>(Ks + swz(l + 8, 4 * dq + nt) + q * 4) = pack2(hi.x, hi.y);
+      }
     }
   }
   head_sync(hl);  // A^T[l][d] (bf16, 64 x 64) complete; V's tile receives Y
