@@ -32,20 +32,20 @@ using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using p
 using prims::ffma2; using prims::fadd2; using prims::fmul2;
 
 constexpr int WPH = 4;                        // warps per head
-template <int CL> struct Cfg {                // CL = CTAs per sample (one thread-block cluster): 4 (2 heads, 256 threads) or 2 (4 heads, 512)
-  static_assert(CL == 2 || CL == 4, "2 or 4 CTAs per sample");
+template <int CL> struct Cfg {                // CL = CTAs per sample: a cluster of 4 (2 heads, 256 threads) or 2 (4 heads, 512), or ONE CTA of 1024
+  static_assert(CL == 1 || CL == 2 || CL == 4, "1, 2 or 4 CTAs per sample");
   static constexpr int NH_CTA = 8 / CL;              // heads per CTA
   static constexpr int NWARPS = NH_CTA * WPH;        // 8 / 16
   static constexpr int NTHREADS = 32 * NWARPS;       // 256 / 512
   static constexpr int COLS = D / CL;                // LayerNorm columns owned by this CTA (128 / 256)
-  static constexpr int LPR = COLS / 8;               // lanes per row in the LayerNorm pass (8 columns per lane)
+  static constexpr int LPR = CL == 1 ? 32 : COLS / 8;   // lanes per row in the LayerNorm pass (8 columns per lane; CL = 1: two-phase pass)
   static constexpr int RPI = 32 / LPR;               // rows per warp iteration (2 / 1)
-  static constexpr int LN_ITERS = TP / (NWARPS * RPI);   // 6
+  static constexpr int LN_ITERS = CL == 1 ? 2 * TP / NWARPS : TP / (NWARPS * RPI);   // 6
   static constexpr int SUM_BYTES = NH_CTA * HD * 4;      // [head][64] column sums of K'
-  static constexpr int STAT_BYTES = CL * TP * 8;         // [source rank][row] (sum, sum of squares)
+  static constexpr int STAT_BYTES = CL * TP * 8;         // [source rank][row] (sum, sum of squares); CL = 1: [row] (mean, rstd)
   static constexpr int SMEM_BYTES = NH_CTA * 2 * TILE_BYTES + SUM_BYTES + STAT_BYTES;   // 52 736 / 101 376
   static constexpr int CTAS_PER_SM = 1024 / NTHREADS;    // 32 warps per SM either way
-  static_assert(TP % (NWARPS * RPI) == 0 && TP % 16 == 0, "row schedule");
+  static_assert((CL == 1 || TP % (NWARPS * RPI) == 0) && TP % 16 == 0 && (2 * TP) % NWARPS == 0, "row schedule");
 };
 
 __device__ __forceinline__ void head_sync(int hl) { prims::named_bar_sync<32 * WPH>(hl + 1); }
@@ -62,8 +62,8 @@ attn_v6_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
   const int hl = warp >> 2, wq = warp & 3;             // local head, warp of the head's quartet
   const int g = lane >> 2, q = lane & 3;
   const int mat = lane >> 3, rr = lane & 7;            // ldmatrix: matrix index / row inside the matrix
-  const uint32_t rank = prims::cluster_rank();
-  prims::cluster_arrive_relaxed();                     // "this CTA runs": matched by the cluster_wait before the first remote store
+  const uint32_t rank = CL > 1 ? prims::cluster_rank() : 0u;
+  if (CL > 1) prims::cluster_arrive_relaxed();         // "this CTA runs": matched by the cluster_wait before the first remote store
   const int smp = blockIdx.x / CL;
   const int head = (int)rank * NH_CTA + hl;            // global head
   const size_t row0 = (size_t)smp * T;
@@ -193,7 +193,62 @@ attn_v6_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int B,
   // ---- 4. StylizationBlock prologue: LN(512) * (1 + scale) + shift, SiLU over this CTA's 128 columns.  A lane covers 8 columns
   //         of one row; 16 lanes make a row, a warp handles 2 rows per iteration.  The LayerNorm (sum, sum of squares) of a row
   //         is the only cross-CTA quantity: exchanged through distributed shared memory, summed in rank order.
-  {
+  if constexpr (CL == 1) {
+    // One CTA holds whole rows, no cluster: (a) statistics -- a warp per row, 16 columns per lane, no constants needed -- into
+    // stat[row] = (mean, rstd); CTA barrier; (b) normalise half-rows: warp parity selects the column half (so the folded
+    // constants are loaded once per lane), 8 columns per lane, 32 lanes x 8 columns = 256 columns per warp pass.
+    for (int t = warp; t < T; t += NWARPS) {
+      const int hh = lane >> 2, c0 = (lane & 3) * 2;
+      const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
+      const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
+      const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
+      const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float2 v = bf_pair(w[e]); s2 = fadd2(s2, v); q2 = ffma2(v, v, q2); }
+      float s = s2.x + s2.y, sq = q2.x + q2.y;
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sq += __shfl_xor_sync(0xffffffffu, sq, o2); }
+      if (lane == 0) {
+        const float mean = s * (1.f / D);
+        // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
+        stat[t] = make_float2(mean, rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f));
+      }
+    }
+    __syncthreads();
+    const int hsel = warp & 1;                              // column half of this warp
+    const int hh = 4 * hsel + (lane >> 3), c0 = lane & 7;   // head, 16-byte chunk of that head's row
+    const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
+    const int col0 = 256 * hsel + lane * 8;                 // global column
+    const float* sc = ss + (size_t)(smp % B) * ss_ld;
+    float2 G[4], Bc[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + col0 + e)), d4 = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + e));
+      G[e / 2] = make_float2(0.5f * a.x * (1.f + c4.x), 0.5f * a.y * (1.f + c4.y));
+      G[e / 2 + 1] = make_float2(0.5f * a.z * (1.f + c4.z), 0.5f * a.w * (1.f + c4.w));
+      Bc[e / 2] = make_float2(0.5f * fmaf(b4.x, 1.f + c4.x, d4.x), 0.5f * fmaf(b4.y, 1.f + c4.y, d4.y));
+      Bc[e / 2 + 1] = make_float2(0.5f * fmaf(b4.z, 1.f + c4.z, d4.z), 0.5f * fmaf(b4.w, 1.f + c4.w, d4.w));
+    }
+#pragma unroll 1
+    for (int t = warp >> 1; t < T; t += NWARPS / 2) {
+      const float2 st2 = stat[t];
+      const float2 rs2 = make_float2(st2.y, st2.y), nm2 = make_float2(-st2.x * st2.y, -st2.x * st2.y);
+      const uint4 u = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
+        const float2 h = ffma2(ffma2(bf_pair(w[e]), rs2, nm2), G[e], Bc[e]);
+        const float2 r = ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+        o[e] = pack2(r.x, r.y);
+      }
+      // the 32 lanes of a warp write 512 contiguous bytes of the row
+      *reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
     const int sub = lane & (LPR - 1), rsel = lane / LPR;
     const int hh = sub >> 3, c0 = sub & 7;                  // local head, 16-byte chunk of that head's row
     const uint8_t* Yh = sm + hh * 2 * TILE_BYTES + TILE_BYTES;
@@ -285,9 +340,11 @@ inline cudaError_t launch_attn_v6(const bf16* qkv, bf16* z, int n_samples, int T
   cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  attr[na].id = cudaLaunchAttributeClusterDimension;
-  attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-  ++na;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
 #if DSHEG_PDL_ATTRS
   attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[na].val.programmaticStreamSerializationAllowed = 1;

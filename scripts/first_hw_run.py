@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]   # op-level parity for all four; in-loop agreement below
 LOOP_ONLY = ["v5c1+expo", "v5c4+expo",   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
-             "v6c2+expo",                 # attn_v6 as clusters of two 512-thread CTAs
+             "v6c2+expo", "v6c1+expo",    # attn_v6 as clusters of two 512-thread CTAs / as one 1024-thread CTA without a cluster
              "v6+expo",                   # attn_v6: 4 warps per head, 64 registers, 32 warps per SM (needs the EXPO numerators)
              "default+lnms",              # + DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS)
              "v6+expo+lnms",              # everything at once
@@ -35,7 +35,7 @@ def pytest_items():
     items += [("GEMM op ACT_EXPO (test_op_linear_exponential_epilogue)", ["tests/test_gpu_parity.py", "-k", "exponential_epilogue"]),
               ("GEMM op ACT_LNMS (test_op_linear_layernorm_modulate_silu_epilogue)", ["tests/test_gpu_parity.py", "-k", "layernorm_modulate_silu_epilogue"])]
     items += [(f"attention op {v} + static-shift numerators", ["tests/test_gpu_parity.py", "-k", f"static_shift_numerators and {v}"])
-              for v in ("v5c1", "v5c2", "v5c4", "v6", "v6c2")]
+              for v in ("v5c1", "v5c2", "v5c4", "v6", "v6c2", "v6c1")]
     for name, sel in items:
         t0 = time.time()
         try:

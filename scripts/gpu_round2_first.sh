@@ -30,7 +30,7 @@ for a in v5c1 v5c2 v5c4; do
 done
 # ... and with Q AND K softmax numerators (static, pack-time-proven shifts) from the QKV epilogue (ACT_EXPO): attn_v5<CL, 2> has no
 # exp / max left outside its LayerNorm pass, attn_v6 additionally runs 32 warps per SM.  Watch BOTH columns (attention down, gemm up?)
-for a in v5c1 v5c4 v6 v6c2; do
+for a in v5c1 v5c4 v6 v6c2 v6c1; do
   DSHEG_ATTN=$a DSHEG_EXPO=1 timeout 300 $B > $O/r2_bench_attn_${a}_expo.json 2> $O/r2_bench_attn_${a}_expo.err
 done
 

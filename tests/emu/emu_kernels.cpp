@@ -56,6 +56,8 @@ extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int 
     ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
   } else if (variant == 6) {   // attn_v6: 4 warps per head, 64 registers, static-shift numerators (same input contract as 25x)
     ok = emu::run_grid(4 * n_samples, av6::Cfg<4>::NTHREADS, 4, av6::Cfg<4>::SMEM_BYTES, [=] { av6::attn_v6_kernel<4>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
+  } else if (variant == 61) {  // attn_v6 as ONE 1024-thread CTA per sample (no cluster, two-phase LayerNorm pass)
+    ok = emu::run_grid(n_samples, av6::Cfg<1>::NTHREADS, 1, av6::Cfg<1>::SMEM_BYTES, [=] { av6::attn_v6_kernel<1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
   } else if (variant == 62) {  // attn_v6 as clusters of two 512-thread CTAs (4 heads each)
     ok = emu::run_grid(2 * n_samples, av6::Cfg<2>::NTHREADS, 2, av6::Cfg<2>::SMEM_BYTES, [=] { av6::attn_v6_kernel<2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
   } else {

@@ -101,7 +101,7 @@ def test_attention_with_q_softmax_done_by_the_gemm_epilogue(variant, Bn, T):
     assert float((got - want).abs().max() / want.abs().max()) < 1e-2
 
 
-@pytest.mark.parametrize("variant", [251, 252, 254, 6, 62])
+@pytest.mark.parametrize("variant", [251, 252, 254, 6, 62, 61])
 @pytest.mark.parametrize("Bn,T,spread", [(2, 88, 1.0), (1, 34, 12.0), (1, 13, 30.0), (1, 96, 3.0), (1, 16, 5.0), (2, 17, 5.0), (1, 7, 5.0)])
 def test_attention_with_both_softmax_numerators_done_by_the_gemm_epilogue(variant, Bn, T, spread):
     """EXPO (PRE = 2): Q and K columns arrive as exp(value - static shift) in bf16 (ACT_EXPO epilogue), with shifts that are

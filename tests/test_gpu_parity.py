@@ -245,7 +245,7 @@ def test_op_linear_layernorm_modulate_silu_epilogue(L, M, K, T, B):
 
 
 @unvalidated
-@pytest.mark.parametrize("variant", ["v5c1", "v5c2", "v5c4", "v6", "v6c2"])
+@pytest.mark.parametrize("variant", ["v5c1", "v5c2", "v5c4", "v6", "v6c2", "v6c1"])
 @pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (1, 96), (2, 16), (1, 7)])
 def test_op_attention_with_static_shift_numerators(L, Bn, T, variant, monkeypatch):
     """attn_v5<CL, 2> / attn_v6: the Q and K columns hold exp(value - shift) with shifts that are NOT the maxima (per (row, head) for Q, per
