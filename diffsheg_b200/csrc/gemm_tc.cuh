@@ -394,13 +394,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int m0 = (unit * CG + (int)rank) * BM + q * 32;
         const int m = m0 + lane;
         const bool row_ok = m < p.M;
-        mbar_wait(tfull_bar(0), acc_phase);
-        mbar_wait(tfull_bar(1), acc_phase);
-        tc_fence_after();
-        // ---- pass 1: statistics of this thread's 2 x 64 columns
+        // ---- pass 1: statistics of this thread's 2 x 64 columns; stage 0 is read while the MMAs still fill stage 1
         float sx = 0.f, sq = 0.f;
 #pragma unroll
         for (int stn = 0; stn < 2; ++stn) {
+          mbar_wait(tfull_bar(stn), acc_phase);
+          tc_fence_after();
 #pragma unroll
           for (int ch = 0; ch < CPW / 32; ++ch) {
             uint32_t r[32];
