@@ -56,9 +56,9 @@ typedef __nv_bfloat16 bf16;
 // ACT_EXPO (tcgen05 engine, LN-fold GEMMs only): columns < GemmDesc::expo_cols are written as exp(v - eshift[n]) -- softmax
 // numerators with a STATIC shift (softmax is shift-invariant; the packer proves |v - eshift| <= 72 for every possible input,
 // diffsheg_b200/pack.py:expo_shift) -- so the attention kernel neither searches maxima nor exponentiates; other columns plain
-// ACT_LNMS (tcgen05 engine, CTA-pair kernel, N == 512, K >= 768): the StylizationBlock prologue of the FFN (tr:92-96) fused into
-// the producing GEMM -- z = SiLU(LN_512(acc + bias) * (1 + scale) + shift): one CTA pair keeps BOTH 256-column halves of its
-// 256 rows in the two TMEM accumulator stages, so full-row statistics never leave the SM and `y` is never written
+// ACT_LNMS (tcgen05 engine, 256-wide tiles, N == 512): the StylizationBlock prologue of the FFN (tr:92-96) fused into
+// the producing GEMM -- z = SiLU(LN_512(acc + bias) * (1 + scale) + shift): one CTA (pair) keeps BOTH 256-column halves of its
+// 128 (256) rows in the two TMEM accumulator stages, so full-row statistics never leave the SM and `y` is never written
 enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QSOFT = 3, ACT_EXPO = 4, ACT_LNMS = 5 };
 
 // ---- activation-type traits: float (fp32 mode) or bf16 (bf16 mode) -------------------------

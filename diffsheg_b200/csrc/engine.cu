@@ -403,9 +403,8 @@ struct Runner {
     f2.a[0] = seg(h->F1, F, F); f2.nseg = 1; f2.M = rows; f2.out = h->Y; f2.ldo = D;
     // DSHEG_FUSE_LNMS=1 (experimental): the StylizationBlock prologue (LayerNorm, modulation, SiLU; tr:92-96) runs in the epilogue
     // of linear2 -- a CTA pair holds both 256-column halves of its rows in TMEM -- so `y` is never written and the row-wise pass
-    // below disappears.  Needs the CTA-pair long-K kernel: bf16, tcgen05 engine, D == 512, rows >= 4096, F >= 768.
-    const bool fuse_lnms = std::is_same<TA, bf16>::value && h->fuse_lnms && h->gemm_engine == 1 && D == 512 && rows >= 4096 && F >= 768 &&
-                           tc::g_cg_override() != 1 && tc::g_bn_override() != 128;
+    // below disappears.  Needs 256-wide tiles: bf16, tcgen05 engine, D == 512 (CTA pairs for rows >= 4096, single CTAs below).
+    const bool fuse_lnms = std::is_same<TA, bf16>::value && h->fuse_lnms && h->gemm_engine == 1 && D == 512 && tc::g_bn_override() != 128;
     if (fuse_lnms) {
       f2.act = ACT_LNMS; f2.out = h->Z;
       f2.lnms_g = L.ffn_g; f2.lnms_b = L.ffn_b; f2.lnms_ss = ss + 2 * D; f2.lnms_ld = ss_ld; f2.lnms_B = ssB; f2.lnms_T = T;

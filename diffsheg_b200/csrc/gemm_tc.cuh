@@ -49,7 +49,7 @@ constexpr int BAR_BYTES = 512;
 // ROWLN (ACT_LNMS): full-row LayerNorm epilogue over both accumulator stages; 5 stages, narrow boxes, and a vector block that
 // holds bias | gamma/2 | beta/2 for all 512 columns plus double-buffered per-(column group, row) statistics partials.
 template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false, bool ROWLN = false> struct Cfg {
-  static_assert(!ROWLN || (CG == 2 && NARROW && LONGK), "the full-row LayerNorm epilogue exists for the long-K CTA-pair kernel only");
+  static_assert(!ROWLN || (BN == 256 && NARROW && (CG == 1 || LONGK)), "the full-row LayerNorm epilogue: 256-wide tiles, narrow boxes; pairs need K >= 768");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
@@ -185,8 +185,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmOut2, const __grid_constant__ CUtensorMap tmRes, const Params p) {
   DSHEG_PDL_TRIGGER();   // PDL build: the next kernel may begin its own prologue now (it still waits for this grid's completion)
   constexpr bool LONGK = LONGK_ && CG == 2 && !OUTF32;
-  constexpr bool NARROW = LONGK && RES != RES_BF16;
-  constexpr bool ROWLN = ACT == ACT_LNMS;   // both n-tiles of a row panel per CTA pair, LayerNorm over the full 2 * BN-column row
+  constexpr bool ROWLN = ACT == ACT_LNMS;   // both n-tiles of a row panel per CTA (pair), LayerNorm over the full 2 * BN-column row
+  constexpr bool NARROW = (LONGK && RES != RES_BF16) || ROWLN;
   using C = Cfg<BN, CG, NARROW, LONGK, ROWLN>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, NE = C::NE, STG_BYTES = C::STG_BYTES;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
@@ -438,7 +438,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (ch == CPW / 32 - 1) {   // last TMEM read of this stage by this warp: hand it back to the MMA issuer
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * stn);
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * stn); else mbar_arrive(tempty_bar(stn));
+              }
             }
             const int n0 = stn * BN + cg * CPW + ch * 32;
             // 2 KB box (32 rows x 64 B, SWIZZLE_64B: chunk c of row r at c ^ ((r >> 1) & 3)), reused for every 32-column chunk
@@ -812,7 +814,7 @@ inline std::string& g_emu_error() { static std::string e; return e; }
 template <int BN, bool LN, int ACT, int RES, bool OUTF32, int CG, bool LONGK_ = false>
 inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, LN, ACT, RES, OUTF32, CG, LONGK_>;
-  using C = Cfg<BN, CG, (LONGK_ && CG == 2 && !OUTF32 && RES != RES_BF16), (LONGK_ && CG == 2 && !OUTF32), ACT == ACT_LNMS>;
+  using C = Cfg<BN, CG, ((LONGK_ && CG == 2 && !OUTF32 && RES != RES_BF16) || ACT == ACT_LNMS), (LONGK_ && CG == 2 && !OUTF32), ACT == ACT_LNMS>;
 #ifdef DSHEG_EMU   // tests/emu: run the grid on the thread-level emulator (clusters of CG CTAs)
   (void)st;
   const CUtensorMap m0 = maps[0], m1 = maps[1], m2 = maps[2], m3 = maps[3], m4 = maps[4], m5 = maps[5], m6 = maps[6], m7 = maps[7];
@@ -876,6 +878,9 @@ inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Pa
     if (d.act == ACT_NONE && res == RES_F32_MOD) return launch_variant<BN, false, ACT_NONE, RES_F32_MOD, false, CG>(maps, p, grid, st);
     if (d.act == ACT_GELU && res == RES_NONE) return launch_variant<BN, false, ACT_GELU, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, false, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
+    if constexpr (BN == 256 && CG == 1) {   // small batches: the full-row LayerNorm epilogue on single CTAs (128 rows x 512 columns of TMEM)
+      if (d.act == ACT_LNMS && res == RES_NONE) return launch_variant<BN, false, ACT_LNMS, RES_NONE, false, CG>(maps, p, grid, st);
+    }
   }
   *err = "no tcgen05 GEMM variant for this epilogue combination";
   return cudaErrorInvalidValue;
@@ -904,9 +909,10 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   int cg = cg_force ? cg_force : g_cg_override();
   if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096 && d.Kp >= 512) ? 2 : 1;   // short K loops: single CTAs win (profiles/r01 sweep)
   if (bn != 256) cg = 1;
+  if (d.act == ACT_LNMS && d.Kp < 768) cg = 1;   // the pair form of the full-row LayerNorm epilogue is built on the long-K configuration
   // K >= 768: the mainloop dominates -> deeper ring (and narrow epilogue boxes when there is no bf16 residual box to load)
   const bool longk = cg == 2 && !d.out_f32 && d.Kp >= 768 && !(d.res && d.res_f32);
-  const bool narrow = longk && !d.res;
+  const bool narrow = (longk && !d.res) || d.act == ACT_LNMS;
   Params p{};
   CUtensorMap maps[8];
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
@@ -940,9 +946,9 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
     return cudaErrorInvalidValue;
   }
   p.lnms_g = d.lnms_g; p.lnms_b = d.lnms_b; p.lnms_ss = d.lnms_ss; p.lnms_ld = d.lnms_ld; p.lnms_B = d.lnms_B; p.lnms_T = d.lnms_T;
-  if (d.act == ACT_LNMS && (cg != 2 || !longk || d.N != 2 * bn || d.csum || d.res || d.out_f32 || d.out2 || !d.lnms_g || !d.lnms_b ||
+  if (d.act == ACT_LNMS && (bn != 256 || (cg == 2 && !longk) || d.N != 2 * bn || d.csum || d.res || d.out_f32 || d.out2 || !d.lnms_g || !d.lnms_b ||
                             !d.lnms_ss || d.lnms_B <= 0 || d.lnms_T <= 0 || (d.lnms_ld % 4))) {
-    *err = "ACT_LNMS needs the CTA-pair long-K kernel (M >= 4096, K >= 768) with N == 512, bf16 output, no LN fold / residual / duplicate store, and the LayerNorm / modulation operands";
+    *err = "ACT_LNMS needs 256-wide tiles with N == 512 (CTA pairs: K >= 768), bf16 output, no LN fold / residual / duplicate store, and the LayerNorm / modulation operands";
     return cudaErrorInvalidValue;
   }
   p.eshift = d.eshift; p.expo_cols = d.expo_cols;

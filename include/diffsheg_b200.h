@@ -145,7 +145,7 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
  *           numerators of transformer.py:122-123 with static shifts; aux0 = mu [M], aux1 = rstd [M], aux2 = eshift [i0],
  *           aux3 = csum [N] (row sums of the bf16-rounded W);
  *   mode 5: out = SiLU(LayerNorm_N(A W^T + bias) (1 + scale) + shift) -- ffn.linear2 + StylizationBlock prologue
- *           (transformer.py:178-181, 92-96), N == 512, M >= 4096, K >= 768; aux0 = gamma [N], aux1 = beta [N],
+ *           (transformer.py:178-181, 92-96), N == 512 (CTA pairs for M >= 4096 and K >= 768, single CTAs otherwise); aux0 = gamma [N], aux1 = beta [N],
  *           aux2 = [i1][i0] table (scale at [0,N), shift at [N,2N), row = (m / i2) mod i1), i0 = row stride, i2 = frames per sample. */
 int dsheg_op_linear_fused(int32_t mode, const float* A, const float* W, const float* bias, const float* aux0,
                           const float* aux1, const float* aux2, const float* aux3, float* out, int32_t M, int32_t N,

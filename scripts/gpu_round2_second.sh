@@ -27,6 +27,7 @@ DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_pd
 # single clip: 128-wide tiles double the CTAs that stream W and deepen the ring (5 stages) -- candidate heuristic for tiles < SMs / 4
 DSHEG_TC_BN=128 timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_bn128.jsonl 2>&1
 DSHEG_TC_BN=128 DSHEG_LIB=$PDL timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_bn128_pdl.jsonl 2>&1
+DSHEG_FUSE_LNMS=1 timeout 200 python scripts/bench_configs.py 1 > $O/r2_configs1_lnms.jsonl 2>&1   # single-CTA form of the fused LayerNorm GEMM: 17 launches less per call
 DSHEG_LIB=$PDL timeout 300 $B > $O/r2_bench_gemm_pdl.json 2> $O/r2_bench_gemm_pdl.err
 
 # ---- the variants the first call left out
@@ -42,4 +43,4 @@ cat $O/r2b_rc.txt
 python scripts/gpu_round2_summary.py
 grep -c "Race reported\|hazard" $O/r2_racecheck_pairs_B24.log; grep -E "Write access|Read access" $O/r2_racecheck_pairs_B24.log | sed 's/(CUtensorMap.*//' | sort | uniq -c | sort -rn | head -8
 cat $O/r2_postprocess_bw.txt
-echo "== single clip (config 1): default / PDL / BN=128 / both"; for f in default pdl bn128 bn128_pdl; do echo "-- $f"; cut -c1-200 $O/r2_configs1_$f.jsonl; done; tail -2 $O/r2_pdl_parity.log
+echo "== single clip (config 1): default / PDL / BN=128 / both"; for f in default pdl bn128 bn128_pdl lnms; do echo "-- $f"; cut -c1-200 $O/r2_configs1_$f.jsonl; done; tail -2 $O/r2_pdl_parity.log

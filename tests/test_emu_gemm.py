@@ -359,17 +359,20 @@ def test_qkv_exponential_epilogue_feeds_attention_end_to_end(variant, cg):
     assert torch.isfinite(z).all() and err < 1.5e-2, err
 
 
-@pytest.mark.parametrize("M,K,T,B,num_sms", [(600, 1024, 88, 3, 2), (1100, 768, 34, 2, 4), (256, 1024, 7, 40, 2), (700, 1024, 88, 2, 6)])
-def test_full_row_layernorm_modulate_silu_epilogue(M, K, T, B, num_sms):
+@pytest.mark.parametrize("M,K,T,B,num_sms,cg", [(600, 1024, 88, 3, 2, 2), (1100, 768, 34, 2, 4, 2), (256, 1024, 7, 40, 2, 2), (700, 1024, 88, 2, 6, 2),
+                                                  # single CTAs (small batches): 128 rows x 512 columns of TMEM per CTA, any K
+                                                  (176, 1024, 88, 1, 4, 1), (34, 1024, 34, 1, 2, 1), (300, 512, 34, 3, 1, 1), (520, 1024, 88, 2, 2, 1)])
+def test_full_row_layernorm_modulate_silu_epilogue(M, K, T, B, num_sms, cg):
     """ACT_LNMS (opt-in, DSHEG_FUSE_LNMS=1): ffn.linear2 + the StylizationBlock prologue (transformer.py:178-181 + :92-96) in ONE
     kernel -- a CTA pair owns both 256-column tiles of its row panel (one per TMEM accumulator stage), so LayerNorm statistics
     span the full 512-wide row; persistent walks with more panels than pairs wrap the stage / accumulator parities."""
-    got, want, _ = run_gemm(M, 512, [K], act=ACT_LNMS, lnms_T=T, lnms_B=B, cg=2, num_sms=num_sms, seed=11)
+    got, want, _ = run_gemm(M, 512, [K], act=ACT_LNMS, lnms_T=T, lnms_B=B, cg=cg, num_sms=num_sms, seed=11)
     check(got, want)
 
 
+@pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("slow", ["EMU_DELAY_TMEM_LD", "EMU_DELAY_TMA", "EMU_DELAY_MMA"])
-def test_full_row_layernorm_epilogue_under_adversarial_timing(slow, monkeypatch):
+def test_full_row_layernorm_epilogue_under_adversarial_timing(slow, cg, monkeypatch):
     monkeypatch.setenv(slow, "40")
-    got, want, _ = run_gemm(600, 512, [1024], act=ACT_LNMS, lnms_T=88, lnms_B=5, cg=2, num_sms=2, seed=12)
+    got, want, _ = run_gemm(600 if cg == 2 else 400, 512, [1024], act=ACT_LNMS, lnms_T=88, lnms_B=5, cg=cg, num_sms=2, seed=12)
     check(got, want)

@@ -221,9 +221,11 @@ def test_op_linear_exponential_epilogue(L, M, N, ec):
 
 
 @unvalidated
-@pytest.mark.parametrize("M,K,T,B", [(4224, 1024, 88, 24), (5000, 768, 34, 7), (4096, 1024, 7, 600), (167200, 1024, 88, 950)])
+@pytest.mark.parametrize("M,K,T,B", [(4224, 1024, 88, 24), (5000, 768, 34, 7), (4096, 1024, 7, 600), (167200, 1024, 88, 950),
+                                     # rows < 4096 / K < 768: single CTAs (128 rows x 512 TMEM columns each)
+                                     (176, 1024, 88, 1), (34, 1024, 34, 1), (520, 512, 34, 3), (5000, 512, 88, 30)])
 def test_op_linear_layernorm_modulate_silu_epilogue(L, M, K, T, B):
-    """ACT_LNMS: ffn.linear2 + the StylizationBlock prologue (tr:178-181 + :92-96) in one CTA-pair GEMM."""
+    """ACT_LNMS: ffn.linear2 + the StylizationBlock prologue (tr:178-181 + :92-96) in one GEMM (CTA pairs or single CTAs)."""
     torch.manual_seed(M + K)
     N = 512
     A = torch.randn(M, K, device="cuda")
