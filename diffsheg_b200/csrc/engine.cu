@@ -17,6 +17,7 @@
 #include "attn_v4.cuh"
 #include "attn_v5.cuh"
 #include "attn_v6.cuh"
+#include "attn_small.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -91,6 +92,7 @@ struct dsheg_handle {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   int qsoft = 0;               // DSHEG_QSOFT=1: ACT_QSOFT epilogue of the QKV GEMM + attn_v5<CL, QPRE> (experimental)
+  int attn_aud = 0;            // DSHEG_ATTN_AUD=1: attn_small.cuh for the audio encoder layer (D = 128, 8 heads of 16; experimental)
   int fuse_lnms = 0;           // DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS, experimental)
   int expo = 0;                // DSHEG_EXPO=1: ACT_EXPO epilogue (Q and K softmax numerators with static shifts) + attn_v5<CL, 2> (experimental)
   int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
@@ -383,6 +385,10 @@ struct Runner {
     } else if (HD == 64) {
       attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
                                                                           L.sa_g, L.sa_b, ss, ss_ld);
+    } else if (std::is_same<TA, bf16>::value && HD == 16 && D == asmall::D && H == asmall::NH && T <= asmall::TP && h->attn_aud) {
+      // DSHEG_ATTN_AUD=1 (experimental): the audio encoder's attention with all 8 heads processed at once (attn_small.cuh)
+      DSHEG_LAUNCH(asmall::attn_d128_kernel, n_samples, asmall::NTHREADS, asmall::smem_bytes(T), st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB,
+                   L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 16) {
       attn_kernel<TA, 16><<<n_samples, 256, attn_smem_bytes<16>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
                                                                           L.sa_g, L.sa_b, ss, ss_ld);
@@ -611,6 +617,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (att && !strcmp(att, "v6c1")) h->attn_v2 = 61;  // ... as ONE 1024-thread CTA per sample (no cluster)
   const char* qso = getenv("DSHEG_QSOFT");
   h->qsoft = (qso && !strcmp(qso, "1")) ? 1 : 0;   // Q row-softmax in the QKV GEMM epilogue (needs an attn_v5 variant)
+  const char* aa = getenv("DSHEG_ATTN_AUD");
+  h->attn_aud = (aa && !strcmp(aa, "1")) ? 1 : 0;
   const char* fl = getenv("DSHEG_FUSE_LNMS");
   h->fuse_lnms = (fl && !strcmp(fl, "1")) ? 1 : 0;
   const char* exo = getenv("DSHEG_EXPO");
@@ -665,6 +673,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   cudaFuncSetAttribute(attn_kernel<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
   cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
+  if (h->attn_aud)       // opt-in kernel (same rule)
+    cudaFuncSetAttribute(asmall::attn_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmall::smem_bytes(c.max_frames < asmall::TP ? c.max_frames : asmall::TP));
   if (h->attn_v2 == 4)   // opt-in kernel: keep the default create path free of calls that have not run on hardware
     cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
   cudaFuncSetAttribute(hubconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);

@@ -16,8 +16,9 @@ VARIANTS = ["v4", "v5c1", "v5c2", "v5c4"]   # op-level parity for all four; in-l
 LOOP_ONLY = ["v5c1+expo", "v5c4+expo",   # + DSHEG_EXPO=1: Q and K numerators with static shifts from the epilogue, attn_v5<CL, 2>
              "v6c2+expo", "v6c1+expo",    # attn_v6 as clusters of two 512-thread CTAs / as one 1024-thread CTA without a cluster
              "v6+expo",                   # attn_v6: 4 warps per head, 64 registers, 32 warps per SM (needs the EXPO numerators)
+             "default+aud",               # + DSHEG_ATTN_AUD=1: attn_small.cuh for the audio encoder layer (all 8 heads of 16 at once)
              "default+lnms",              # + DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS)
-             "v6+expo+lnms",              # everything at once
+             "v6+expo+lnms+aud",          # everything at once
              "v5c4+qsoft"]                # + DSHEG_QSOFT=1: Q row-softmax only (superseded by EXPO when that wins)
 results = {}
 
@@ -62,11 +63,12 @@ def in_loop(batch, var):
         os.environ.pop("DSHEG_QSOFT", None)
         os.environ.pop("DSHEG_EXPO", None)
         os.environ.pop("DSHEG_FUSE_LNMS", None)
+        os.environ.pop("DSHEG_ATTN_AUD", None)
         if v:
             parts = v.split("+")
             if parts[0] != "default":
                 os.environ["DSHEG_ATTN"] = parts[0]
-            for flag, env in (("qsoft", "DSHEG_QSOFT"), ("expo", "DSHEG_EXPO"), ("lnms", "DSHEG_FUSE_LNMS")):
+            for flag, env in (("qsoft", "DSHEG_QSOFT"), ("expo", "DSHEG_EXPO"), ("lnms", "DSHEG_FUSE_LNMS"), ("aud", "DSHEG_ATTN_AUD")):
                 if flag in parts[1:]:
                     os.environ[env] = "1"
         eng = FusedUniDiffuser(sd, cfg, precision="bf16", max_batch=batch, max_frames=T)

@@ -37,8 +37,10 @@ done
 # ---- ffn.linear2 + LayerNorm / modulate / SiLU in ONE GEMM (ACT_LNMS): the "rowwise" column (about 41 ms per step) should disappear,
 #      the ffn2 GEMM loses one ring stage and gains an exposed epilogue
 DSHEG_FUSE_LNMS=1 timeout 300 $B > $O/r2_bench_gemm_lnms.json 2> $O/r2_bench_gemm_lnms.err
+# the audio encoder's attention (D = 128, 8 heads of 16) with all heads at once instead of the generic head-by-head kernel (336 us per call)
+DSHEG_ATTN_AUD=1 timeout 300 $B > $O/r2_bench_attn_aud.json 2> $O/r2_bench_attn_aud.err
 for a in v5c4 v6; do
-  DSHEG_ATTN=$a DSHEG_EXPO=1 DSHEG_FUSE_LNMS=1 timeout 300 $B > $O/r2_bench_all_${a}_expo_lnms.json 2> $O/r2_bench_all_${a}_expo_lnms.err
+  DSHEG_ATTN=$a DSHEG_EXPO=1 DSHEG_FUSE_LNMS=1 DSHEG_ATTN_AUD=1 timeout 300 $B > $O/r2_bench_all_${a}_expo_lnms_aud.json 2> $O/r2_bench_all_${a}_expo_lnms_aud.err
 done
 
 # ---- summary

@@ -6,6 +6,7 @@
 #include "attn_v4.cuh"
 #include "attn_v5.cuh"
 #include "attn_v6.cuh"
+#include "attn_small.cuh"
 #include "postprocess.cuh"
 #include "sampler.cuh"
 
@@ -64,6 +65,15 @@ extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int 
     g_err = "unknown attention variant";
   }
   return ok ? 0 : 1;
+}
+
+// audio-layer attention (D = 128, 8 heads of 16): qkv [n_samples, T, 384], z [n_samples, T, 128]
+extern "C" int emu_attention_d128(const uint16_t* qkv, uint16_t* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
+                                  const float* ss, int ss_ld) {
+  g_err.clear();
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  bf16* zo = reinterpret_cast<bf16*>(z);
+  return emu::run_grid(n_samples, asmall::NTHREADS, 1, asmall::smem_bytes(T), [=] { asmall::attn_d128_kernel(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err) ? 0 : 1;
 }
 
 // ---- elementwise kernels: a small grid of 256-thread CTAs, grid-stride like on the device --------------------------------------

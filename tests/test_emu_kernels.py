@@ -124,6 +124,28 @@ def test_attention_with_both_softmax_numerators_done_by_the_gemm_epilogue(varian
     assert float((got - want).abs().max() / want.abs().max()) < 1e-2
 
 
+@pytest.mark.parametrize("Bn,T,nb", [(2, 88, None), (3, 34, 1), (1, 96, None), (2, 7, None), (1, 30, None)])
+def test_audio_layer_attention_all_heads_at_once(Bn, T, nb):
+    """attn_small.cuh (opt-in, DSHEG_ATTN_AUD=1): the encoder_aud attention (D = 128, 8 heads of 16) with all heads processed at once
+    instead of the generic head-by-head SIMT kernel; same fp64 reference as the 512-wide kernels, evaluated at D = 128."""
+    torch.manual_seed(T)
+    D = 128
+    qkv = 1.5 * torch.randn(Bn, T, 3 * D)
+    g, b = 1 + 0.1 * torch.randn(D), 0.1 * torch.randn(D)
+    ss = 0.5 * torch.randn(nb or Bn, 2 * D)
+    L = emu.lib()
+    q = _bf16_bits(qkv)
+    z = np.zeros((Bn, T, D), dtype=np.int16)
+    gg, bb, s = (x.float().numpy().copy() for x in (g, b, ss))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = L.emu_attention_d128(P(q), P(z), Bn, T, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1])
+    assert rc == 0, L.emu_last_error().decode()
+    got = _from_bits(z)
+    want = reference(qkv, g, b, ss)
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max() / want.abs().max()) < 6e-3      # fp32 math on bf16 inputs, bf16 output rounding
+
+
 def _op_counts(variant, qkv, g, b, ss, **kw):
     L = emu.lib()
     buf = (ctypes.c_ulonglong * 7)()
