@@ -1026,7 +1026,8 @@ int dsheg_op_linear_fused(int32_t mode, const float* A, const float* W, const fl
 }
 
 // Times one tcgen05 GEMM shape (bf16, device-resident random-ish data): mode 0 bias, 1 LN+bias, 2 LN+bias+SiLU,
-// 3 bias+bf16 residual (in place), 4 bias+GELU; bn = 0 (auto) / 128 / 256.  Returns the mean ms over `iters`.
+// 3 bias+bf16 residual (in place), 4 bias+GELU, 5 LN+bias with exponential Q | K columns (ACT_EXPO), 6 bias + full-row LayerNorm /
+// modulate / SiLU (ACT_LNMS, N == 512); bn = 0 (auto) / 128 / 256.  Returns the mean ms over `iters`.
 int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out) {
   const int cg = bn >= 1000 ? 2 : (bn >= 100 ? 1 : 0);   // bn = 2256 selects the CTA-pair kernel explicitly, 128/256 the single-CTA one
   if (bn >= 1000) bn -= 2000;
@@ -1049,6 +1050,13 @@ int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, 
   if (mode == 2) d.act = ACT_SILU;
   if (mode == 3) { d.res = Ob; d.ldr = N; }
   if (mode == 4) d.act = ACT_GELU;
+  if (mode == 5) {   // LN-fold + exponential columns (ACT_EXPO): the qkv projection with static-shift softmax numerators
+    d.csum = vec + N; d.mu = vec + 2 * N; d.rstd = vec + 2 * N + M;
+    d.act = ACT_EXPO; d.eshift = vec; d.expo_cols = (2 * N / 3) / 64 * 64;
+  }
+  if (mode == 6) {   // full-row LayerNorm / modulate / SiLU epilogue (ACT_LNMS, N == 512): one "sample" spanning all rows
+    d.act = ACT_LNMS; d.lnms_g = vec; d.lnms_b = vec; d.lnms_ss = vec; d.lnms_ld = 2 * N; d.lnms_B = 1; d.lnms_T = M;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -152,7 +152,8 @@ int dsheg_op_linear_fused(int32_t mode, const float* A, const float* W, const fl
                           int32_t K, int32_t i0, int32_t i1, int32_t i2, void* stream);
 
 /* Device timing of one tcgen05 GEMM shape (tuning / roofline aid): mode 0 bias, 1 LN-fold+bias,
- * 2 LN-fold+bias+SiLU, 3 bias+bf16 residual, 4 bias+GELU; bn 0 = auto, 128 or 256. */
+ * 2 LN-fold+bias+SiLU, 3 bias+bf16 residual, 4 bias+GELU, 5 LN-fold+bias with exponential leading columns (ACT_EXPO),
+ * 6 bias + full-row LayerNorm / modulate / SiLU (ACT_LNMS, N == 512); bn 0 = auto, 128 or 256. */
 int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, int32_t iters, float* ms_out);
 
 /* Linear self-attention core + Stylization prologue on one [Bn,T,3D] qkv tensor

@@ -12,7 +12,7 @@ L = _lib.lib()
 R, R1 = 167200, 83600
 shapes = [("qkv      LN", R, 1536, 512, 1), ("feat1 LN+silu", R1, 1024, 896, 2), ("feat1g LN+silu", R1, 1024, 1024, 2),
           ("feat2 +res", R1, 512, 1024, 3), ("sa_out +res", R, 512, 512, 3), ("ffn1 gelu", R, 1024, 512, 4),
-          ("ffn2 bias", R, 512, 1024, 0), ("aud qkv", R1, 384, 128, 1), ("aud ffn1", R1, 1024, 128, 4),
+          ("ffn2 bias", R, 512, 1024, 0), ("qkv LN+expo", R, 1536, 512, 5), ("ffn2 +lnms", R, 512, 1024, 6), ("aud qkv", R1, 384, 128, 1), ("aud ffn1", R1, 1024, 128, 4),
           ("aud ffn2", R1, 128, 1024, 0), ("audproj", R1, 256, 256, 0)]
 ms = ctypes.c_float()
 for name, M, N, K, mode in shapes:

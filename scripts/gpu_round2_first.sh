@@ -47,4 +47,4 @@ done
 cat $O/r2_rc.txt
 grep -E "^(PASS|FAIL)" $O/r2_first_hw_run.log | cut -c1-220
 python scripts/gpu_round2_summary.py
-for v in default k512deep split73 epipacked; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2 " $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
+for v in default k512deep split73 epipacked; do echo "== gemm sweep $v"; grep -E "qkv|sa_out|ffn1|ffn2" $O/r2_gemm_sweep_$v.txt | cut -c1-140; done
