@@ -20,8 +20,9 @@ constexpr int D = 128, NH = 8, HD = 16, TP = 96;
 constexpr int NTHREADS = 512;
 constexpr int LD = D + 4;                 // fp32 row stride of the staged tiles (16-byte aligned rows, rows land on different banks)
 constexpr int ALD = 20;                   // row stride of A[h][d][.] (float4-aligned)
+constexpr int AHS = HD * ALD + 16;        // head stride of A: consecutive heads sit 16 banks apart (conflict-free float4 reads in step 4)
 constexpr int NPART = NTHREADS / D;       // 4 row partitions for the column-parallel passes
-inline int smem_bytes(int T) { return (3 * T * LD + NH * HD * ALD + 2 * NPART * D + D) * 4; }
+inline int smem_bytes(int T) { return (3 * T * LD + NH * AHS + 2 * NPART * D + D) * 4; }
 
 __device__ __forceinline__ float bflo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bfhi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -42,8 +43,8 @@ attn_d128_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int 
   float* Qs = sm;                          // [T][LD]  q, then exp(q - rowmax) / rowsum
   float* Ks = Qs + T * LD;                 // [T][LD]  k, then exp(k - colmax) (unnormalised), then Y
   float* Vs = Ks + T * LD;                 // [T][LD]
-  float* As = Vs + T * LD;                 // [NH][HD][ALD]
-  float* red = As + NH * HD * ALD;         // [2][NPART][D] column partials (max, then sum)
+  float* As = Vs + T * LD;                 // [NH][AHS] = [NH][HD][ALD] + padding
+  float* red = As + NH * AHS;         // [2][NPART][D] column partials (max, then sum)
   float* inv = red + 2 * NPART * D;        // [D] 1 / column sum
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int smp = blockIdx.x;
@@ -119,7 +120,7 @@ attn_d128_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int 
     }
     __syncthreads();   // inv[] complete (and every thread is done reading the column partials)
     const float r = inv[h * HD + d];
-    *reinterpret_cast<float4*>(As + (h * HD + d) * ALD + l4) = make_float4(a0 * r, a1 * r, a2 * r, a3 * r);
+    *reinterpret_cast<float4*>(As + h * AHS + d * ALD + l4) = make_float4(a0 * r, a1 * r, a2 * r, a3 * r);
   }
   __syncthreads();     // A complete; nobody reads K' any more: its tile receives Y
 
@@ -127,13 +128,17 @@ attn_d128_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ z, int T, int 
   for (int s = tid; s < T * 32; s += NTHREADS) {
     const int t = s >> 5, c4 = (s & 31) * 4, h = c4 >> 4, l4 = c4 & 15;
     const float* qp = Qs + t * LD + h * HD;
-    const float* ap = As + h * HD * ALD + l4;
+    const float* ap = As + h * AHS + l4;
     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      const float qv = qp[d];
-      const float4 a = *reinterpret_cast<const float4*>(ap + d * ALD);
-      y0 = fmaf(qv, a.x, y0); y1 = fmaf(qv, a.y, y1); y2 = fmaf(qv, a.z, y2); y3 = fmaf(qv, a.w, y3);
+    for (int d = 0; d < HD; d += 4) {
+      const float4 q4 = *reinterpret_cast<const float4*>(qp + d);   // 16-byte loads: a quarter-warp touches two heads only
+      const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + (d + e) * ALD);
+        y0 = fmaf(qv[e], a.x, y0); y1 = fmaf(qv[e], a.y, y1); y2 = fmaf(qv[e], a.z, y2); y3 = fmaf(qv[e], a.w, y3);
+      }
     }
     *reinterpret_cast<float4*>(Ks + t * LD + c4) = make_float4(y0, y1, y2, y3);
   }
