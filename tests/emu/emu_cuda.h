@@ -216,16 +216,41 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
         makecontext(&t.ctx, (void (*)())trampoline, 0);
       }
     }
+    // Scheduling order of a pass.  Any order is a legal execution (threads only rendezvous at synchronising operations), so code
+    // that is correct must give the same results under all of them; EMU_SCHED=reverse runs the threads last-to-first, EMU_SCHED=shuffle
+    // draws a new pseudo-random order for every pass and lets random warps sit passes out (deterministic LCG) -- the emulator's stand-in for compute-sanitizer racecheck:
+    // a missing barrier between a producer and a consumer shows up as a wrong result or a NaN under at least one of the orders.
+    const char* sched_env = getenv("EMU_SCHED");
+    const int sched_mode = !sched_env ? 0 : (!strcmp(sched_env, "reverse") ? 1 : (!strcmp(sched_env, "shuffle") ? 2 : 0));
+    std::vector<uint32_t> order(nthr);
+    for (uint32_t i = 0; i < nthr; ++i) order[i] = sched_mode == 1 ? (uint32_t)(nthr - 1 - i) : i;
+    uint64_t lcg = 0x9E3779B97F4A7C15ull;
     size_t remaining = nthr;
     while (remaining) {
       const uint64_t before = R.progress;
       remaining = 0;
-      for (auto& tp : threads) {
+      if (sched_mode == 2)
+        for (size_t i = nthr - 1; i > 0; --i) {
+          lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+          std::swap(order[i], order[(size_t)((lcg >> 33) % (i + 1))]);
+        }
+      // shuffle mode also lets every WARP sit out a pass with probability 1/2 (a fresh draw per pass), so a warp can fall arbitrarily far
+      // behind its neighbours: stores before a collective of one warp vs. loads after a collective of another are then really unordered
+      bool skipped = false;
+      std::vector<uint8_t> sit_out;
+      if (sched_mode == 2) {
+        sit_out.resize((nthr + 31) / 32);
+        for (auto& b : sit_out) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; b = (uint8_t)((lcg >> 40) & 1); }
+      }
+      for (uint32_t oi = 0; oi < nthr; ++oi) {
+        auto& tp = threads[order[oi]];
         if (tp->done) continue;
+        if (sched_mode == 2 && sit_out[order[oi] / 32]) { skipped = true; ++remaining; continue; }
         R.cur = tp.get();
         swapcontext(&R.sched, &tp->ctx);
         if (!tp->done) ++remaining;
       }
+      if (skipped && R.progress == before) continue;   // nobody who ran made progress, but some warps sat out: not a deadlock
       if (!R.error.empty()) { *err = R.error; return false; }
       if (remaining && R.progress == before) {
         std::string msg = "deadlock: ";

@@ -376,3 +376,27 @@ def test_full_row_layernorm_epilogue_under_adversarial_timing(slow, cg, monkeypa
     monkeypatch.setenv(slow, "40")
     got, want, _ = run_gemm(520 if cg == 2 else 270, 512, [768], act=ACT_LNMS, lnms_T=88, lnms_B=5, cg=cg, num_sms=2, seed=12)
     check(got, want)
+
+
+@pytest.mark.parametrize("sched", ["reverse", "shuffle"])
+@pytest.mark.parametrize("kw", [dict(M=520, N=512, ks=[1024], act=ACT_LNMS, lnms_T=88, lnms_B=3, cg=2, num_sms=2),
+                                dict(M=300, N=512, ks=[768], act=ACT_LNMS, lnms_T=34, lnms_B=2, cg=1, num_sms=2),
+                                dict(M=520, N=768, ks=[512], ln=True, act=ACT_EXPO, expo_cols=512, cg=2, num_sms=2, ps_in=True),
+                                dict(M=600, N=512, ks=[512], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=300),
+                                dict(M=300, N=1024, ks=[512], cg=2, num_sms=4, act=ACT_GELU),
+                                dict(M=270, N=1024, ks=[512, 128, 128, 103], cg=2, num_sms=4, ln=True, act=ACT_SILU),
+                                dict(M=520, N=512, ks=[1024], cg=2, num_sms=2),
+                                dict(M=140, N=512, ks=[232], cg=1, res="f32mod", dup=True, num_sms=2),
+                                dict(M=260, N=384, ks=[128], cg=1, act=ACT_GELU)],
+                         ids=["lnms-pair", "lnms-cta1", "expo-pair", "residual-pair", "gelu-pair", "feat1-pair", "longk-narrow-pair",
+                              "joint-cta1", "bn128-cta1"])
+def test_gemm_is_independent_of_the_thread_schedule(kw, sched, monkeypatch):
+    """Emulator stand-in for racecheck (see tests/emu/emu_cuda.h EMU_SCHED): reversed and per-pass shuffled thread orders must give
+    bit-identical outputs -- the epilogue's shared-memory exchanges (statistics partials, staged vectors, TMA boxes) included."""
+    k = dict(kw)
+    M, N, ks = k.pop("M"), k.pop("N"), k.pop("ks")
+    _, _, ex0 = run_gemm(M, N, ks, seed=31, **k)
+    base = ex0["out_bits"].copy()
+    monkeypatch.setenv("EMU_SCHED", sched)
+    _, _, ex1 = run_gemm(M, N, ks, seed=31, **k)
+    assert np.array_equal(base, ex1["out_bits"])

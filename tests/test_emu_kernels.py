@@ -146,6 +146,46 @@ def test_audio_layer_attention_all_heads_at_once(Bn, T, nb):
     assert float((got - want).abs().max() / want.abs().max()) < 6e-3      # fp32 math on bf16 inputs, bf16 output rounding
 
 
+@pytest.mark.parametrize("sched", ["reverse", "shuffle"])
+@pytest.mark.parametrize("variant", [3, 4, 51, 52, 54, 254, 6, 62, 61])
+def test_attention_is_independent_of_the_thread_schedule(variant, sched, monkeypatch):
+    """The emulator's stand-in for racecheck: the same launch under a reversed and under a per-pass shuffled thread order must
+    reproduce the default order's output BIT FOR BIT -- a missing barrier between a producer and a consumer does not."""
+    Bn, T = 2, 40
+    qkv, g, b, ss = _case(Bn, T, None, seed=2)
+    qkv = qkv.bfloat16().float()
+    if variant in (254, 6, 62, 61):   # static-shift numerators
+        q = qkv[..., :512].double().view(Bn, T, 8, 64)
+        pre = qkv.clone()
+        pre[..., :512] = torch.exp(q - 3.0).reshape(Bn, T, 512).float()
+        pre[..., 512:1024] = torch.exp(qkv[..., 512:1024].double() + 2.0).float()
+        qkv = pre
+    base = run_attention(variant, qkv, g, b, ss)
+    monkeypatch.setenv("EMU_SCHED", sched)
+    got = run_attention(variant, qkv, g, b, ss)
+    assert torch.isfinite(got).all() and torch.equal(got, base)
+
+
+@pytest.mark.parametrize("sched", ["reverse", "shuffle"])
+def test_audio_layer_attention_is_independent_of_the_thread_schedule(sched, monkeypatch):
+    torch.manual_seed(5)
+    Bn, T, D = 2, 40, 128
+    qkv = 1.5 * torch.randn(Bn, T, 3 * D)
+    g, b, ss = 1 + 0.1 * torch.randn(D), 0.1 * torch.randn(D), 0.5 * torch.randn(Bn, 2 * D)
+    L = emu.lib()
+    q = _bf16_bits(qkv)
+    gg, bb, s = (x.float().numpy().copy() for x in (g, b, ss))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    outs = []
+    for mode in (None, sched):
+        if mode:
+            monkeypatch.setenv("EMU_SCHED", mode)
+        z = np.zeros((Bn, T, D), dtype=np.int16)
+        assert L.emu_attention_d128(P(q), P(z), Bn, T, Bn, P(gg), P(bb), P(s), ss.shape[1]) == 0, L.emu_last_error().decode()
+        outs.append(z)
+    assert np.array_equal(outs[0], outs[1])
+
+
 def _op_counts(variant, qkv, g, b, ss, **kw):
     L = emu.lib()
     buf = (ctypes.c_ulonglong * 7)()
