@@ -225,6 +225,7 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
     std::vector<uint32_t> order(nthr);
     for (uint32_t i = 0; i < nthr; ++i) order[i] = sched_mode == 1 ? (uint32_t)(nthr - 1 - i) : i;
     uint64_t lcg = 0x9E3779B97F4A7C15ull;
+    if (const char* seed_env = getenv("EMU_SCHED_SEED")) lcg ^= strtoull(seed_env, nullptr, 10) * 0xD1342543DE82EF95ull;   // other interleavings
     size_t remaining = nthr;
     while (remaining) {
       const uint64_t before = R.progress;
