@@ -820,7 +820,8 @@ inline cudaError_t launch_variant(const CUtensorMap* maps, const Params& p, int 
   const CUtensorMap m0 = maps[0], m1 = maps[1], m2 = maps[2], m3 = maps[3], m4 = maps[4], m5 = maps[5], m6 = maps[6], m7 = maps[7];
   static std::string emu_err;
   const bool ok = emu::run_grid(grid, C::NUM_THREADS, CG, C::SMEM_BYTES, [=] { kern(m0, m1, m2, m3, m4, m5, m6, m7, p); }, &emu_err);
-  if (!ok) { g_emu_error() = emu_err; return cudaErrorLaunchFailure; }
+  if (!ok) { g_emu_error() = emu_err; tma_stores_drained(); return cudaErrorLaunchFailure; }
+  if (!tma_stores_drained()) { g_emu_error() = "a TMA store was still pending (no cp.async.bulk.wait_group) when its thread exited"; return cudaErrorLaunchFailure; }
   return cudaSuccess;
 #else
   static bool attr_set = false;

@@ -143,10 +143,32 @@ inline void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
   emu::bar_complete_tx(leader_bar, (long long)map->box_cols * 2 * map->box_rows);
 }
-inline void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) { tma_copy(map, emu::self().cta, src, c0, c1, false); }
+// TMA stores are ASYNCHRONOUS: the engine may read the shared-memory box at any time until the issuing thread's
+// cp.async.bulk.wait_group(.read) returns.  The model reads it at the LATEST legal moment -- at that wait -- so a kernel that reuses
+// a box without waiting stores the overwritten data and fails its parity check; a store that is never waited for before the CTA
+// exits is reported (launch_variant checks tma_stores_drained after the grid).
+struct PendingStore { CUtensorMap map; emu::Cta* cta; uint32_t src; int c0, c1; };
+inline std::unordered_map<emu::Thread*, std::vector<PendingStore>>& pending_stores() {
+  static std::unordered_map<emu::Thread*, std::vector<PendingStore>> p;
+  return p;
+}
+inline void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  pending_stores()[&emu::self()].push_back(PendingStore{*map, emu::self().cta, src, c0, c1});
+}
 inline void bulk_commit() {}
-inline void bulk_wait_read0() {}
-inline void bulk_wait0() {}
+inline void tma_flush_stores() {
+  auto it = pending_stores().find(&emu::self());
+  if (it == pending_stores().end()) return;
+  for (const PendingStore& s : it->second) tma_copy(&s.map, s.cta, s.src, s.c0, s.c1, false);
+  pending_stores().erase(it);
+}
+inline void bulk_wait_read0() { tma_flush_stores(); }
+inline void bulk_wait0() { tma_flush_stores(); }
+inline bool tma_stores_drained() {
+  const bool ok = pending_stores().empty();
+  pending_stores().clear();
+  return ok;
+}
 inline void fence_async_smem() {}
 
 // ---- tcgen05 ---------------------------------------------------------------------------------------------------------------
