@@ -30,6 +30,7 @@ extern "C" void emu_op_counters(unsigned long long* out, int reset) {
 extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int n_samples, int T, int ssB, const float* ln_g,
                              const float* ln_b, const float* ss, int ss_ld, const float* qsum) {
   g_err.clear();
+  prims::async_copies().clear();
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* zo = reinterpret_cast<bf16*>(z);
   bool ok = false;
@@ -71,6 +72,7 @@ extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int 
 extern "C" int emu_attention_d128(const uint16_t* qkv, uint16_t* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
                                   const float* ss, int ss_ld) {
   g_err.clear();
+  prims::async_copies().clear();
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* zo = reinterpret_cast<bf16*>(z);
   return emu::run_grid(n_samples, asmall::NTHREADS, 1, asmall::smem_bytes(T), [=] { asmall::attn_d128_kernel(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err) ? 0 : 1;

@@ -6,6 +6,9 @@
 //                                  C/D {(g, 2q), (g, 2q+1), (g+8, 2q), (g+8, 2q+1)}
 // Shared-memory "addresses" are byte offsets into the CTA's emulated window; cluster addresses carry the target rank.
 #pragma once
+#include <unordered_map>
+#include <vector>
+
 #include "emu_cuda.h"
 
 #define DSHEG_DYN_SMEM(name, align) uint8_t* name = emu::self().cta->smem
@@ -27,15 +30,43 @@ inline uint8_t* smem_ptr(uint32_t addr, size_t bytes, const char* what) {
   return c->smem + addr;
 }
 inline uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// cp.async is ASYNCHRONOUS: a copy is only guaranteed to have landed when the issuing thread's cp.async.wait_group / wait_all
+// returns.  The model performs it at that LATEST legal moment (per-thread commit groups, oldest first), so a tile that is read before
+// the wait -- or by another thread before a barrier that follows the owner's wait -- shows its stale contents and fails parity.
+struct PendingCopy { uint32_t dst; const void* src; };
+struct AsyncCopies { std::vector<PendingCopy> open; std::vector<std::vector<PendingCopy>> groups; };
+inline std::unordered_map<emu::Thread*, AsyncCopies>& async_copies() {
+  static std::unordered_map<emu::Thread*, AsyncCopies> m;
+  return m;
+}
 inline void cp_async16(uint32_t dst, const void* src) {
   ++op_counters().cp_async16;
   if (dst & 15u) emu::rt().error = "cp.async 16: misaligned shared destination";
   if (reinterpret_cast<uintptr_t>(src) & 15u) emu::rt().error = "cp.async 16: misaligned global source";
-  memcpy(smem_ptr(dst, 16, "cp.async"), src, 16);
+  smem_ptr(dst, 16, "cp.async");   // bounds check at issue
+  async_copies()[&emu::self()].open.push_back(PendingCopy{dst, src});
 }
-inline void cp_async_commit() {}
-template <int N> inline void cp_async_wait_group() {}
-inline void cp_async_wait_all() {}
+inline void cp_async_land(const std::vector<PendingCopy>& g) {
+  for (const PendingCopy& c : g) memcpy(smem_ptr(c.dst, 16, "cp.async"), c.src, 16);
+}
+inline void cp_async_commit() {
+  AsyncCopies& a = async_copies()[&emu::self()];
+  a.groups.push_back(std::move(a.open));
+  a.open.clear();
+}
+template <int N> inline void cp_async_wait_group() {   // at most N of the most recent groups may still be in flight
+  auto it = async_copies().find(&emu::self());
+  if (it == async_copies().end()) return;
+  AsyncCopies& a = it->second;
+  while ((int)a.groups.size() > N) { cp_async_land(a.groups.front()); a.groups.erase(a.groups.begin()); }
+}
+inline void cp_async_wait_all() {
+  auto it = async_copies().find(&emu::self());
+  if (it == async_copies().end()) return;
+  for (auto& g : it->second.groups) cp_async_land(g);
+  cp_async_land(it->second.open);
+  async_copies().erase(it);
+}
 
 inline void ldsm_common(uint32_t addr, bool trans, uint32_t (&r)[4]) {
   ++op_counters().ldsm;
