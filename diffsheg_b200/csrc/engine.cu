@@ -29,7 +29,22 @@ using namespace dsheg;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // errors of the handle-less entry points (per calling thread)
+
+// Makes the handle's device current for one entry point and restores the caller's device on the way out
+// (the library must not change the process's current device under torch).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) { err = cudaSetDevice(device); switched = err == cudaSuccess; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 struct DevTensor {
   void* ptr = nullptr;
@@ -589,7 +604,8 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
     return 1;
   }
   if (cfg->precision != DSHEG_PREC_FP32 && cfg->precision != DSHEG_PREC_BF16) { g_create_error = "bad precision"; return 1; }
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard dg(device);
+  cudaError_t e = dg.err;
   if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return 1; }
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
@@ -687,7 +703,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
 
 void dsheg_destroy(dsheg_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard dg(h->device);
   for (auto& kv : h->tensors) cudaFree(kv.second.ptr);
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -698,14 +714,18 @@ void dsheg_destroy(dsheg_handle* h) {
 int dsheg_load_tensor(dsheg_handle* h, const char* key, const void* host_data, int32_t dtype, const int64_t* shape, int32_t ndim) {
   if (!h || !key || !host_data) return 1;
   if (dtype != DSHEG_DTYPE_F32 && dtype != DSHEG_DTYPE_BF16) return fail(h, "bad dtype");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  CK(dg.err);
   DevTensor t;
   t.dtype = dtype;
   t.numel = 1;
   for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
   const size_t bytes = t.numel * (dtype == DSHEG_DTYPE_F32 ? 4 : 2);
   CK(cudaMalloc(&t.ptr, bytes ? bytes : 16));
-  CK(cudaMemcpy(t.ptr, host_data, bytes, cudaMemcpyHostToDevice));
+  {
+    cudaError_t ce = cudaMemcpy(t.ptr, host_data, bytes, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(t.ptr); CK(ce); }
+  }
   auto it = h->tensors.find(key);
   if (it != h->tensors.end()) {
     // a captured graph may still reference the old allocation: drop every graph before freeing it
@@ -761,7 +781,8 @@ int dsheg_prepare_window(dsheg_handle* h, const float* mel, const float* hubert,
   if (!h) return 1;
   if (!h->finalized) return fail(h, "weights not finalized");
   if (B < 1 || B > h->cfg.max_batch || T < 2 || T > h->cfg.max_frames) return fail(h, "window shape exceeds the workspace (max_batch/max_frames)");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg(h->device);
+  CK(dg.err);
   h->B = B; h->T = T;
   int rc = with_runner(h, (cudaStream_t)stream, [&](auto& r) { return r.prepare_window(mel, hubert, person_id, B, T); });
   h->window_ready = rc == 0;
@@ -771,6 +792,8 @@ int dsheg_prepare_window(dsheg_handle* h, const float* mel, const float* hubert,
 int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, float b, float cond_scale, float* eps_out, void* stream) {
   if (!h) return 1;
   if (!h->window_ready) return fail(h, "dsheg_prepare_window has not been called");
+  DeviceGuard dg(h->device);
+  CK(dg.err);
   cudaStream_t st = (cudaStream_t)stream;
   const bool two = h->cfg.classifier_free && cond_scale != 1.0f;  // transformer.py:537
   DSHEG_LAUNCH(step_params_kernel, 1, 32, 0, st, h->PRM, (float)t_orig, a, b, cond_scale);
@@ -818,6 +841,8 @@ int dsheg_profile_begin(dsheg_handle* h) {
 int dsheg_profile_end(dsheg_handle* h, double* ms, double* work, int64_t* count) {
   if (!h || !ms || !work || !count) return 1;
   h->profiling = false;
+  DeviceGuard dg(h->device);
+  CK(dg.err);
   CK(cudaDeviceSynchronize());
   for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; work[c] = 0; count[c] = 0; }
   // DSHEG_PROF_TABLE=1: per-kernel-name breakdown of the profiled region on stderr (which GEMM shapes lose in the loop what they
@@ -854,7 +879,12 @@ int dsheg_profile_end(dsheg_handle* h, double* ms, double* work, int64_t* count)
 }
 
 // ---- stateless sampler steps ---------------------------------------------------------------
-static std::string g_step_error;
+// These have no handle: the device is the one that owns the first data pointer (the caller's stream lives there too).
+static int device_of(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeDevice) { cudaGetLastError(); int d = 0; cudaGetDevice(&d); return d; }
+  return at.device;
+}
 static int step_done(const char* name) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_create_error = std::string(name) + ": " + cudaGetErrorString(e); return 1; }
@@ -866,6 +896,7 @@ int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, i
                     const uint8_t* mask, const float* noise2, int32_t blend, int32_t overlap_len, float* pred_xstart_out,
                     void* stream) {
   if (!x || !eps || !x_out || n <= 0 || (mask && (!gt || !noise2))) { g_create_error = "dsheg_ddim_step: bad arguments"; return 1; }
+  DeviceGuard dg(device_of(x));
   DdimArgs p;
   p.x = x; p.eps = eps; p.x_out = x_out; p.pred_out = pred_xstart_out; p.n = n; p.T = T; p.D = D;
   p.a = sqrt_recip_ac; p.b = sqrt_recipm1_ac; p.sqrt_acp = sqrt_ac_prev; p.sqrt_1m_acp = sqrt_one_minus_ac_prev;
@@ -877,6 +908,7 @@ int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, i
 int dsheg_undo_step(const float* x, const float* noise, float* x_out, int64_t n, float sqrt_one_minus_beta, float sqrt_beta,
                     void* stream) {
   if (!x || !noise || !x_out || n <= 0) { g_create_error = "dsheg_undo_step: bad arguments"; return 1; }
+  DeviceGuard dg(device_of(x));
   DSHEG_LAUNCH(undo_step_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, x, noise, x_out, n, sqrt_one_minus_beta, sqrt_beta);
   return step_done("dsheg_undo_step");
 }
@@ -884,6 +916,7 @@ int dsheg_undo_step(const float* x, const float* noise, float* x_out, int64_t n,
 int dsheg_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, int64_t n, float sqrt_recip_ac,
                     float sqrt_recipm1_ac, float coef1, float coef2, float sigma, float* pred_xstart_out, void* stream) {
   if (!x || !eps || !noise || !x_out || n <= 0) { g_create_error = "dsheg_ddpm_step: bad arguments"; return 1; }
+  DeviceGuard dg(device_of(x));
   ddpm_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, x_out, pred_xstart_out, n, sqrt_recip_ac,
                                                                  sqrt_recipm1_ac, coef1, coef2, sigma);
   return step_done("dsheg_ddpm_step");
@@ -892,6 +925,7 @@ int dsheg_ddpm_step(const float* x, const float* eps, const float* noise, float*
 int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, const float* noise, float* x_out, int64_t n,
                         float sqrt_ac, float sqrt_one_minus_ac, void* stream) {
   if (!x || !gt || !mask || !noise || !x_out || n <= 0) { g_create_error = "dsheg_repaint_merge: bad arguments"; return 1; }
+  DeviceGuard dg(device_of(x));
   repaint_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, gt, mask, noise, x_out, n, sqrt_ac, sqrt_one_minus_ac);
   return step_done("dsheg_repaint_merge");
 }
@@ -900,6 +934,7 @@ int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, co
 int dsheg_inv_standardize(const float* x, int32_t ldx, const float* mean, const float* stdv, float* out, int32_t ldo,
                           int64_t rows, int32_t D, void* stream) {
   if (!x || !mean || !stdv || !out || rows <= 0 || D <= 0 || ldx < D || ldo < D) { g_create_error = "dsheg_inv_standardize: bad arguments"; return 1; }
+  DeviceGuard dg(device_of(x));
   inv_standardize_kernel<<<ew_grid(rows * D), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean, stdv, out, ldo, rows, D);
   return step_done("dsheg_inv_standardize");
 }
@@ -910,6 +945,7 @@ int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mea
       (out_norm && (!mean_pose || !std_pose))) {
     g_create_error = "dsheg_beat_axis_angle_to_euler: bad arguments (C must be 3 * joints)"; return 1;
   }
+  DeviceGuard dg(device_of(x));
   beat_axis_angle_kernel<<<ew_grid(rows * (C / 3)), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean_aa, std_aa, mean_pose, std_pose,
                                                                                    euler_deg, out_norm, rows, C / 3);
   return step_done("dsheg_beat_axis_angle_to_euler");

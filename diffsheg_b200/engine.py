@@ -47,8 +47,9 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The caller's current stream ON THE GIVEN DEVICE (an engine may live on a GPU that is not torch's current one)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class FusedUniDiffuser:
@@ -109,10 +110,12 @@ class FusedUniDiffuser:
             person_id = person_id.unsqueeze(0)  # tr:502-503
         B, T = mel.shape[0], mel.shape[1]
         assert hubert.shape[:2] == (B, T) and person_id.shape[0] == B, "conditioning shapes disagree"
-        _lib.check(self._L.dsheg_prepare_window(self._h, _ptr(mel), _ptr(hubert), _ptr(person_id), B, T, _stream()),
-                   self._h, "dsheg_prepare_window")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.dsheg_prepare_window(self._h, _ptr(mel), _ptr(hubert), _ptr(person_id), B, T,
+                                                    _stream(self.device)), self._h, "dsheg_prepare_window")
         self._keep = (mel, hubert, person_id)  # async kernels read these: keep them alive
         self._window = (B, T)
+        self._window_key = None                # an explicit prepare_window supersedes whatever __call__ cached
 
     def denoise(self, x, t_orig, a, b, cond_scale=None, out=None):
         """eps = UniDiffuser.forward(x, [t_orig]*B, sqrt_alphas=(a, b), <window conditioning>)."""
@@ -123,8 +126,9 @@ class FusedUniDiffuser:
         if out is None:
             out = torch.empty_like(x)
         s = self.cond_scale if cond_scale is None else float(cond_scale)
-        _lib.check(self._L.dsheg_denoise(self._h, _ptr(x), int(t_orig), float(a), float(b), s, _ptr(out), _stream()),
-                   self._h, "dsheg_denoise")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.dsheg_denoise(self._h, _ptr(x), int(t_orig), float(a), float(b), s, _ptr(out),
+                                             _stream(self.device)), self._h, "dsheg_denoise")
         return out
 
     def launch_count(self):
@@ -147,12 +151,16 @@ class FusedUniDiffuser:
         hub = (add_cond or {}).get("pretrain_aud_feat")
         if hub is None:
             raise ValueError("add_cond['pretrain_aud_feat'] (HuBERT features) is required (addHubert=True)")
-        # same storage AND same in-place version => same window (Tensor._version counts in-place writes, no device sync)
-        key = (audio_emb.data_ptr(), hub.data_ptr(), person_id.data_ptr(), tuple(audio_emb.shape),
-               audio_emb._version, hub._version, person_id._version)
-        if getattr(self, "_window_key", None) != key:
+        # the SAME tensor objects with the same in-place version => same window (Tensor._version counts in-place writes,
+        # no device sync).  The key holds strong references to the caller's tensors: comparing addresses alone would
+        # match a freed-and-reallocated buffer of the next window / clip and silently reuse stale conditioning.
+        src = (audio_emb, hub, person_id)
+        key = getattr(self, "_window_key", None)
+        same = key is not None and all(a is b for a, b in zip(key[0], src)) and \
+            key[1] == tuple(t._version for t in src) and key[2] == tuple(tuple(t.shape) for t in src)
+        if not same:
             self.prepare_window(audio_emb, hub, person_id)
-            self._window_key = key
+            self._window_key = (src, tuple(t._version for t in src), tuple(tuple(t.shape) for t in src))
         t0 = int(ts.reshape(-1)[0])
         if ts.numel() > 1 and not bool((ts == t0).all()):
             raise NotImplementedError("per-sample timesteps are not supported (the samplers use t = [i]*B)")

@@ -43,7 +43,7 @@ def inv_standardize(motion, mean, std, columns=None):
     with torch.cuda.device(dev):
         src = flat[:, lo:]
         _lib.check(_lib.lib().dsheg_inv_standardize(_ptr(src), flat.stride(0), _ptr(m), _ptr(s), _ptr(out), D, flat.shape[0], D,
-                                                    _stream()), None, "inv_standardize")
+                                                    _stream(dev)), None, "inv_standardize")
     return out.reshape(*motion.shape[:-1], D)
 
 
@@ -61,7 +61,7 @@ def axis_angle_to_euler(motion, mean_aa, std_aa, mean_pose, std_pose, channels=N
     out = torch.empty_like(euler)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().dsheg_beat_axis_angle_to_euler(_ptr(flat), flat.stride(0), _ptr(st[0]), _ptr(st[1]), _ptr(st[2]),
-                                                             _ptr(st[3]), _ptr(euler), _ptr(out), flat.shape[0], C, _stream()),
+                                                             _ptr(st[3]), _ptr(euler), _ptr(out), flat.shape[0], C, _stream(dev)),
                    None, "axis_angle_to_euler")
     shape = (*motion.shape[:-1], C)
     return euler.reshape(shape), out.reshape(shape)

@@ -30,8 +30,12 @@ def build_diffusions(opt, precision="bf16", max_batch=None):
 def patch_trainer(trainer, precision="bf16", max_batch=None):
     """Swap the sampler objects of a reference DDPMTrainer_show / DDPMTrainer_beat in place."""
     full, ddim = build_diffusions(trainer.opt, precision=precision, max_batch=max_batch)
+    # the trainer also TRAINS through self.diffusion (training_losses, show:132; q_sample; the schedule sampler built on it,
+    # show:53): the fused object answers the sampling entry points and hands every other attribute to the original
+    full._fallback = getattr(trainer, "diffusion", None)
     trainer.diffusion = full
     if ddim is not None:
+        ddim._fallback = getattr(trainer, "diffusion_ddim_val", None)
         trainer.diffusion_ddim_val = ddim
     return trainer
 
@@ -65,16 +69,21 @@ def get_windows(x, size, step):
     return out
 
 
-def generate_long(opt, encoder, diffusion, audio_emb, p_id, dim_pose, add_cond):
+def generate_long(opt, encoder, diffusion, audio_emb, p_id, dim_pose, add_cond, motions=None):
     """show:864-906: sequential windows of one (batch of) clip(s); returns [B, frames, dim_pose] on the GPU.
 
     Unlike the reference there is no per-window D2H copy (show:897): windows are concatenated on
-    the device and the caller copies once.
+    the device and the caller copies once.  ``motions`` ([B, frames, dim_pose]) is only read for
+    ``opt.fix_very_first`` (show:885-888: the first window repaints its head from the tail of its own
+    ground-truth window).
     """
     n_poses, ov = opt.n_poses, opt.overlap_len
     step = n_poses - ov
+    fix_first = bool(getattr(opt, "fix_very_first", False)) and ov > 0
+    if fix_first and motions is None:
+        raise ValueError("opt.fix_very_first needs the ground-truth motions (show:885-888)")
     audio_list = get_windows(audio_emb, n_poses, step)
-    cond_list = get_windows(add_cond, n_poses, step)
+    cond_list = get_windows(add_cond, n_poses, step) if add_cond else [add_cond or {}] * len(audio_list)
     outs, prev = [], None
     for ii, (aud, cond) in enumerate(zip(audio_list, cond_list)):
         inpaint = {}
@@ -85,6 +94,9 @@ def generate_long(opt, encoder, diffusion, audio_emb, p_id, dim_pose, add_cond):
             if ii > 0:
                 mask[:, :ov, :] = True
                 gt[:, :ov, :] = prev[:, -ov:, :].to(aud.device)
+            elif fix_first:
+                mask[:, :ov, :] = True
+                gt[:, :ov, :] = get_windows(motions, n_poses, step)[0][:, -ov:, :].to(aud.device)
             inpaint = {"gt": gt, "outpainting_mask": mask}
         prev = generate_batch(opt, encoder, diffusion, aud, p_id, dim_pose, cond, inpaint)
         outs.append(prev if ii == len(audio_list) - 1 else prev[:, :step])

@@ -107,3 +107,65 @@ def test_hardware_session_scripts_reference_what_exists():
     fh = open(os.path.join(root, "scripts", "first_hw_run.py")).read()
     for v in set(re.findall(r'"(v\d\w*)(?:\+[\w+]+)?"', fh)):
         assert v in attn_ok, v
+
+
+def test_model_protocol_never_reuses_a_freed_windows_conditioning():
+    """SEAM #1 caches the step-invariant window work by the IDENTITY of the caller's tensors (strong references), not by
+    address: a next window whose freshly allocated tensors land on the freed addresses must be prepared again."""
+    import torch
+    from diffsheg_b200.engine import FusedUniDiffuser
+    eng = FusedUniDiffuser.__new__(FusedUniDiffuser)   # host logic only: no library, no GPU
+    eng.device = torch.device("cpu")
+    prepared = []
+    eng.prepare_window = lambda a, h, p: (prepared.append((a, h, p)), setattr(eng, "_window_key", None))
+    eng.denoise = lambda x, t0, a, b: x
+    eng._f32 = lambda t: t
+
+    def call(mel, hub, pid):
+        return eng(torch.zeros(1, 4, 6), torch.full((1,), 40), sqrt_alphas=(1.5, 1.1), audio_emb=mel, person_id=pid,
+                   add_cond={"pretrain_aud_feat": hub})
+
+    mel, hub, pid = torch.zeros(1, 4, 8), torch.zeros(1, 4, 16), torch.zeros(1, 4)
+    call(mel, hub, pid)
+    call(mel, hub, pid)
+    assert len(prepared) == 1                                  # same objects, same versions: one preparation per window
+    mel.add_(1.0)
+    call(mel, hub, pid)
+    assert len(prepared) == 2                                  # in-place update of the conditioning is seen (Tensor._version)
+    addr = mel.data_ptr()
+    del mel
+    for _ in range(64):                                        # same shape, usually the same address, version 0 again
+        mel2 = torch.zeros(1, 4, 8)
+        if mel2.data_ptr() == addr:
+            break
+    call(mel2, hub, pid)
+    assert len(prepared) == 3 and prepared[-1][0] is mel2      # a NEW tensor is a new window, whatever its address
+
+
+def test_patched_trainer_keeps_the_training_half_of_the_reference_object():
+    cfg = synth.make_cfg("show")
+
+    class RefDiffusion:   # stands for models/gaussian_diffusion.py::GaussianDiffusion (training_losses gd:1319, q_sample gd:423)
+        def training_losses(self, *a, **k):
+            return "ref-losses"
+
+    class Trainer:
+        def __init__(self, opt):
+            self.opt, self.diffusion, self.diffusion_ddim_val = opt, RefDiffusion(), RefDiffusion()
+
+    tr = patch_trainer(Trainer(synth.make_opt(cfg, ddim=True)))
+    assert tr.diffusion.training_losses() == "ref-losses" and tr.diffusion_ddim_val.training_losses() == "ref-losses"
+    assert tr.diffusion.num_timesteps == 1000                   # the fused object's own attributes win
+    with pytest.raises(AttributeError):
+        tr.diffusion.no_such_thing
+    with pytest.raises(AttributeError):                          # without a reference object there is nothing to fall back to
+        FusedGaussianDiffusion(betas=np.linspace(1e-4, 0.02, 10)).training_losses
+
+
+def test_generate_long_rejects_fix_very_first_without_motions():
+    import torch
+    from diffsheg_b200 import generate_long
+    opt = synth.make_opt(synth.make_cfg("show"), ddim=True)
+    opt.overlap_len, opt.fix_very_first = 10, True
+    with pytest.raises(ValueError):
+        generate_long(opt, None, None, torch.zeros(1, 200, 128), torch.zeros(1, 4), 232, {"pretrain_aud_feat": torch.zeros(1, 200, 1024)})
