@@ -1,0 +1,385 @@
+// Linear-attention core + StylizationBlock prologue, bf16 (D = 512, 8 heads of 64, T <= 96) -- PERSISTENT, TMA-STAGED.
+//
+// Mathematics (reference transformer.py:112-130 + :86-97), input contract = the ACT_EXPO epilogue of the QKV GEMM
+// (gemm_tc.cuh): the Q and K columns of `qkv` hold exp(value - static shift) (softmax is shift-invariant; the packer proves
+// the exponent range, pack.py:expo_shift), V is plain:
+//   A = K'^T V / colsum(K')  [64 x 64 per head]     Y = Q' A / rowsum(Q')     z = SiLU(LN_512(Y) * (1 + scale) + shift)
+//
+// Why this shape.  Every earlier generation (attn_v3 / v5 / v6: one CTA or cluster per sample, cp.async fill -> barrier ->
+// math -> barrier -> LayerNorm -> store) plateaued at 1.9 - 2.4 TB/s whatever its occupancy (16 or 32 warps per SM) or
+// instruction count (67 k -> 35 k warp-instructions per sample): a CTA's load phase and its math phase never overlap, and CTAs
+// that start together stay in step, so HBM idles while the SMs compute and vice versa (profiles/r02).  Here the loads are
+// taken out of the compute warps altogether:
+//   * ONE persistent CTA per SM walks samples blockIdx.x, + gridDim.x, ...; a producer warp streams (sample, head) tiles with
+//     TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B -- the same XOR layout the ldmatrix code always used) into an 8-deep ring of
+//     12 KB tiles guarded by full / empty mbarriers, so the next units' K' / V -- and the next SAMPLE's, during the LayerNorm
+//     pass -- are in flight while the tensor cores work.  The 3-D tensor map (column, frame, sample) zero-fills frames
+//     T .. Tpad-1, which removes the fill / zero / predicate code of the older kernels.
+//   * 16 consumer warps = 4 groups of 4 warps; a group takes one head of the sample at a time (heads g and g + 4):
+//       A^T: one 32 x 32 quadrant per warp on mma.sync (K' column sums on the same fragments: ones . K'), normalised into the
+//            unit's K' slot; the V slot goes back to the producer right after the accumulation, the K' slot after the Y product;
+//       Y:   a warp owns whole 16-row m-tiles: Q' fragments by ldmatrix from the head's Q' tile, row sums on the tensor core
+//            (Q' . ones), bf16 Y written IN PLACE over the warp's own Q' rows (the Q' region doubles as the sample's Y buffer);
+//     then, after one barrier of the consumer warps, the LayerNorm / modulate / SiLU pass: a warp per row, 16 columns per lane,
+//     statistics and normalisation in one pass, 1 KB coalesced stores.  The Q' region is handed back through an mbarrier the
+//     producer waits on before it loads the next sample's Q'.
+//   * the producer warp's 32 lanes also fold the sample's LayerNorm / modulation constants (gamma, beta, scale, shift -> G, Bc per
+//     column) into a 4 KB shared table one sample ahead, so the LayerNorm pass starts from shared memory instead of exposing
+//     an L2 round trip per sample in all 16 warps (ncu on the first version: 14 % of all stall samples), and prefetches the
+//     next sample's Q' tiles into L2 while the current sample is being multiplied.
+// HBM traffic: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample (unchanged).
+#pragma once
+#include "attn_v5.cuh"
+#include "gemm_tc.cuh"   // tc:: mbarrier wait with watchdog, tensor-map encoder entry point
+
+namespace dsheg {
+namespace atm {
+
+using av3::TP; using av3::HD; using av3::D; using av3::TILE_BYTES;
+using av3::pack2; using av3::swz;
+using av5::bf_pair; using av5::BF2_ONES;
+using prims::smem_addr; using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::tanh_approx; using prims::rcp_approx;
+using prims::ffma2; using prims::fadd2; using prims::fmul2;
+
+constexpr int NH = 8;                          // heads
+constexpr int NGRP = 4, WPG = 4;               // consumer groups, warps per group
+constexpr int NCW = NGRP * WPG;                // consumer warps
+constexpr int NTHREADS = 32 * (NCW + 1);       // + the producer warp (the LAST warp of the CTA)
+constexpr int NST = 10;                        // ring stages (K' / V tiles; a K' slot later holds the head's normalised A^T)
+constexpr int QY_OFF = 0;                                   // [8 heads] Q' tiles, overwritten in place by Y
+constexpr int RING_OFF = QY_OFF + NH * TILE_BYTES;          // [NST] K' / V tiles
+constexpr int SUM_OFF = RING_OFF + NST * TILE_BYTES;        // [NGRP][64] column sums of K'
+constexpr int TAB_OFF = SUM_OFF + NGRP * HD * 4;            // G[512] | Bc[512]: folded LayerNorm / modulation constants of the sample in the LayerNorm pass
+constexpr int TAB_BYTES = D * 2 * 4;
+constexpr int BAR_OFF = TAB_OFF + TAB_BYTES;                // full[NST] empty[NST] qfull[8] qy_empty
+constexpr int NBAR = 2 * NST + NH + 1;
+constexpr int SMEM_BYTES = BAR_OFF + ((NBAR * 8 + 127) / 128) * 128;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(NST % 2 == 0 && TP % 16 == 0, "a unit's K' and V tiles share one ring wrap count");
+
+__device__ __forceinline__ void group_sync(int grp) { prims::named_bar_sync<32 * WPG>(grp + 1); }          // ids 1 .. 4
+__device__ __forceinline__ void consumer_sync() { prims::named_bar_sync<32 * NCW>(NGRP + 1); }             // id 5
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z, int n_samples, int T, int B,
+                const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+  DSHEG_PDL_ENTER();
+  DSHEG_TC_DYN_SMEM(sm);
+  const uint32_t sbase = tc::smem_u32(sm);
+  if (sbase & 1023u) tc::trap();   // SWIZZLE_128B tiles: the dynamic smem base must be 1024-byte aligned (no room for slack)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_mt = (T + 15) >> 4;            // 16-frame tiles that contain valid frames
+  const uint32_t tile_tx = (uint32_t)n_mt * 16u * 128u;   // bytes one TMA box delivers (frames T .. Tpad-1 arrive as zeros)
+  auto full_bar = [&](int s) { return sbase + BAR_OFF + 8u * s; };
+  auto empty_bar = [&](int s) { return sbase + BAR_OFF + 8u * (NST + s); };
+  auto qfull_bar = [&](int h) { return sbase + BAR_OFF + 8u * (2 * NST + h); };
+  const uint32_t qy_empty_bar = sbase + BAR_OFF + 8u * (2 * NST + NH);
+  float* const tabG = reinterpret_cast<float*>(sm + TAB_OFF);   // [512] G  = gamma (1 + scale) / 2
+  float* const tabB = tabG + D;                                  // [512] Bc = (beta (1 + scale) + shift) / 2
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), WPG); }
+    for (int h = 0; h < NH; ++h) tc::mbar_init(qfull_bar(h), 1);
+    tc::mbar_init(qy_empty_bar, NCW);
+    tc::fence_mbarrier_init();
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    // ========== producer warp: lane 0 issues every TMA load of this CTA; all 32 lanes fold the LayerNorm constants ==========
+    if (lane == 0) tc::prefetch_tensormap(&tmQKV);
+    const int col0 = lane * 16;
+    float gam[16], bet[16];   // sample-invariant: LayerNorm weight / bias of this lane's 16 columns
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + e));
+      gam[e] = a.x; gam[e + 1] = a.y; gam[e + 2] = a.z; gam[e + 3] = a.w;
+      bet[e] = b4.x; bet[e + 1] = b4.y; bet[e + 2] = b4.z; bet[e + 3] = b4.w;
+    }
+    uint32_t kv = 0;   // ring tile counter (K' and V tiles, in consumption order)
+    int i = 0;
+    for (int smp = blockIdx.x; smp < n_samples; smp += gridDim.x, ++i) {
+      // the sample's modulation row (scale | shift): in flight while the first K' / V tiles are issued
+      const float* sc = ss + (size_t)(smp % B) * ss_ld;
+      float4 c4[4], d4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        c4[e] = __ldg(reinterpret_cast<const float4*>(sc + col0 + 4 * e));
+        d4[e] = __ldg(reinterpret_cast<const float4*>(sc + D + col0 + 4 * e));
+      }
+      for (int h = 0; h < NH; ++h) {
+        if (h == NGRP) {
+          // The ring now holds (or is waiting for) the K' / V of the sample's first NGRP heads -- issued while the
+          // consumers were still in the previous sample's LayerNorm pass.  The Q' tiles and the constant table go into
+          // memory that pass reads: wait until all consumer warps have handed it back.
+          tc::mbar_wait(qy_empty_bar, (uint32_t)((i & 1) ^ 1));
+          // per-column constants:  h = t/2,  t = ((v-mean)*rstd*g + b)*(1+scale) + shift = (v-mean)*rstd*2G + 2Bc
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sx = 1.f + c4[e].x, sy = 1.f + c4[e].y, sz = 1.f + c4[e].z, sw = 1.f + c4[e].w;
+            *reinterpret_cast<float4*>(tabG + col0 + 4 * e) =
+                make_float4(0.5f * gam[4 * e] * sx, 0.5f * gam[4 * e + 1] * sy, 0.5f * gam[4 * e + 2] * sz, 0.5f * gam[4 * e + 3] * sw);
+            *reinterpret_cast<float4*>(tabB + col0 + 4 * e) =
+                make_float4(0.5f * fmaf(bet[4 * e], sx, d4[e].x), 0.5f * fmaf(bet[4 * e + 1], sy, d4[e].y),
+                            0.5f * fmaf(bet[4 * e + 2], sz, d4[e].z), 0.5f * fmaf(bet[4 * e + 3], sw, d4[e].w));
+          }
+          __syncwarp();   // the table is complete before lane 0's arrive (release) on the Q' barriers the consumers acquire
+          if (lane == 0) {
+            for (int hh = 0; hh < NH; ++hh) {
+              tc::mbar_arrive_expect_tx(qfull_bar(hh), tile_tx);
+              tc::tma_load_3d(&tmQKV, qfull_bar(hh), sbase + QY_OFF + hh * TILE_BYTES, hh * HD, 0, smp);
+            }
+          }
+        }
+        for (int j = 0; j < 2; ++j, ++kv) {   // K' then V of head h
+          const int slot = (int)(kv % NST);
+          tc::mbar_wait(empty_bar(slot), ((kv / NST) & 1u) ^ 1u);
+          if (lane == 0) {
+            tc::mbar_arrive_expect_tx(full_bar(slot), tile_tx);
+            tc::tma_load_3d(&tmQKV, full_bar(slot), sbase + RING_OFF + slot * TILE_BYTES, (1 + j) * D + h * HD, 0, smp);
+          }
+        }
+      }
+      // pull the NEXT sample's Q' tiles into L2 while this one is being multiplied (they are loaded in one burst after its LayerNorm pass)
+      if (lane < NH && smp + (int)gridDim.x < n_samples) tc::tma_prefetch_l2_3d(&tmQKV, lane * HD, 0, smp + (int)gridDim.x);
+    }
+    return;
+  }
+
+  // ======================================================= consumers =======================================================
+  const int grp = warp >> 2, wq = warp & 3;        // group, warp of the group's quartet
+  const int g = lane >> 2, q = lane & 3;           // mma fragment coordinates
+  const int mat = lane >> 3, rr = lane & 7;        // ldmatrix: matrix index / row inside the matrix
+  float* const colsum = reinterpret_cast<float*>(sm + SUM_OFF) + grp * HD;
+  int i = 0;
+  for (int smp = blockIdx.x; smp < n_samples; smp += gridDim.x, ++i) {
+    const size_t row0 = (size_t)smp * T;
+#pragma unroll 1
+    for (int rd = 0; rd < NH / NGRP; ++rd) {
+      const int h = grp + NGRP * rd;
+      const uint32_t kidx = 2u * (uint32_t)(i * NH + h);
+      const int kslot = (int)(kidx % NST), vslot = kslot + 1;
+      const uint32_t par = (kidx / NST) & 1u;
+      uint8_t* const ks_ptr = sm + RING_OFF + kslot * TILE_BYTES;
+      const uint32_t ks_addr = sbase + RING_OFF + kslot * TILE_BYTES, vs_addr = sbase + RING_OFF + vslot * TILE_BYTES;
+      tc::mbar_wait(full_bar(kslot), par);
+      tc::mbar_wait(full_bar(vslot), par);
+
+      // ---- A^T[l][d] = sum_t V[t][l] K'[t][d]: the group's four warps take the four 32 x 32 quadrants (l-half lq, d-half dq);
+      //      on the same K' fragments the column sums of K' for d = 32 dq + 16 lq .. + 15 (ones[16 x 16] . K'[16 x 8])
+      {
+        const int lq = wq & 1, dq = wq >> 1;
+        float acc[2][4][4], cs[2][4];
+        const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
+        cs[0][0] = cs[0][1] = cs[0][2] = cs[0][3] = cs[1][0] = cs[1][1] = cs[1][2] = cs[1][3] = 0.f;
+#pragma unroll 2
+        for (int kt = 0; kt < n_mt; ++kt) {   // 16 frames per k-step
+          uint32_t a0[4], a1[4];
+          {
+            const int r = kt * 16 + rr + ((mat >> 1) << 3);
+            ldsm_x4_trans(vs_addr + swz(r, 4 * lq + (mat & 1)), a0[0], a0[1], a0[2], a0[3]);
+            ldsm_x4_trans(vs_addr + swz(r, 4 * lq + 2 + (mat & 1)), a1[0], a1[1], a1[2], a1[3]);
+          }
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {    // two d n-tiles per ldmatrix.x4
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_trans(ks_addr + swz(kt * 16 + rr + ((mat & 1) << 3), 4 * dq + 2 * np + (mat >> 1)), b0, b1, b2, b3);
+            mma_bf16(acc[0][2 * np], a0, b0, b1);
+            mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
+            mma_bf16(acc[1][2 * np], a1, b0, b1);
+            mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
+            if (np == lq) {   // warp-uniform: the two warps of a d-half share its column sums
+              mma_bf16(cs[0], ones, b0, b1);
+              mma_bf16(cs[1], ones, b2, b3);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(empty_bar(vslot));   // this warp is done with V (only ever read): slot -> producer
+        if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
+          *reinterpret_cast<float2*>(colsum + 32 * dq + 16 * lq + 2 * q) = make_float2(cs[0][0], cs[0][1]);
+          *reinterpret_cast<float2*>(colsum + 32 * dq + 16 * lq + 8 + 2 * q) = make_float2(cs[1][0], cs[1][1]);
+        }
+        group_sync(grp);   // all four warps are done reading K' and have published their column sums: the K' slot receives A^T
+        const float* csum = colsum + 32 * dq;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float2 s2 = *reinterpret_cast<const float2*>(csum + 8 * nt + 2 * q);
+          const float2 inv = make_float2(rcp_approx(s2.x), rcp_approx(s2.y));
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const int l = 32 * lq + 16 * mi + g;
+            const float2 lo = fmul2(make_float2(acc[mi][nt][0], acc[mi][nt][1]), inv), hi = fmul2(make_float2(acc[mi][nt][2], acc[mi][nt][3]), inv);
+            *reinterpret_cast<uint32_t*>(ks_ptr + swz(l, 4 * dq + nt) + q * 4) = pack2(lo.x, lo.y);
+            *reinterpret_cast<uint32_t*>(ks_ptr + swz(l + 8, 4 * dq + nt) + q * 4) = pack2(hi.x, hi.y);
+          }
+        }
+      }
+      group_sync(grp);   // A^T[l][d] (bf16, 64 x 64) complete
+
+      // ---- Y[t][l] = Q'[t][:] . A / rowsum(Q'): a warp owns whole m-tiles (mt = wq, wq + 4), so bf16 Y replaces the
+      //      warp's own Q' rows in place.  Row sums on the tensor core (Q' . ones): exactly the bf16 weights the product uses.
+      tc::mbar_wait(qfull_bar(h), (uint32_t)(i & 1));
+      {
+        uint8_t* const qy_ptr = sm + QY_OFF + h * TILE_BYTES;
+        const uint32_t qy_addr = sbase + QY_OFF + h * TILE_BYTES;
+#pragma unroll 1
+        for (int mt = wq; mt < n_mt; mt += WPG) {
+          uint32_t pa[4][4];
+#pragma unroll
+          for (int kd = 0; kd < 4; ++kd)   // A fragments: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15) of the 16 x 16 block
+            ldsm_x4(qy_addr + swz(mt * 16 + rr + ((mat & 1) << 3), 2 * kd + (mat >> 1)), pa[kd][0], pa[kd][1], pa[kd][2], pa[kd][3]);
+          float y[8][4], rs[4] = {0.f, 0.f, 0.f, 0.f};   // rs: rows g, g + 8 in [0], [2]
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) { y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f; }
+#pragma unroll
+          for (int kd = 0; kd < 4; ++kd) {
+            mma_bf16(rs, pa[kd], BF2_ONES, BF2_ONES);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {   // B fragments of two l n-tiles per ldmatrix.x4 from A^T[l][d]
+              uint32_t b0, b1, b2, b3;
+              ldsm_x4(ks_addr + swz(16 * np + rr + ((mat >> 1) << 3), 2 * kd + (mat & 1)), b0, b1, b2, b3);
+              mma_bf16(y[2 * np], pa[kd], b0, b1);
+              mma_bf16(y[2 * np + 1], pa[kd], b2, b3);
+            }
+          }
+          const int ra = mt * 16 + g, rb = ra + 8;
+          // zero-filled Q' rows beyond T have zero sums: keep their Y rows at 0
+          const float r0 = ra >= T ? 0.f : rcp_approx(rs[0]), r1 = rb >= T ? 0.f : rcp_approx(rs[2]);
+          __syncwarp();   // every lane's Q' fragments are in registers before any lane overwrites the rows
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const float2 ya = fmul2(make_float2(y[nt][0], y[nt][1]), make_float2(r0, r0)), yb = fmul2(make_float2(y[nt][2], y[nt][3]), make_float2(r1, r1));
+            *reinterpret_cast<uint32_t*>(qy_ptr + swz(ra, nt) + q * 4) = pack2(ya.x, ya.y);
+            *reinterpret_cast<uint32_t*>(qy_ptr + swz(rb, nt) + q * 4) = pack2(yb.x, yb.y);
+          }
+        }
+      }
+      // this warp is done with A^T: the K' slot -> producer.  The slot was WRITTEN through the generic proxy (A^T) and will be
+      // written by TMA (async proxy) next: order the two.
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty_bar(kslot));
+    }
+    consumer_sync();   // all 8 heads of Y are in the Q' / Y region
+
+    // ---- StylizationBlock prologue: LN(512) * (1 + scale) + shift, SiLU.  A warp per row, a lane covers 16 columns (two
+    //      16-byte chunks of one head's tile): statistics and normalisation in one pass, 1 KB contiguous per warp store;
+    //      two rows in flight per warp.
+    {
+      const int hh = lane >> 2, c0 = (lane & 3) * 2;
+      const uint8_t* Yh = sm + QY_OFF + hh * TILE_BYTES;
+      const int col0 = lane * 16;
+      float2 G[8], Bc[8];   // the producer warp folded them for this sample (visible: every warp acquired a Q' barrier after it)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 a = *reinterpret_cast<const float4*>(tabG + col0 + 4 * e), b4 = *reinterpret_cast<const float4*>(tabB + col0 + 4 * e);
+        G[2 * e] = make_float2(a.x, a.y); G[2 * e + 1] = make_float2(a.z, a.w);
+        Bc[2 * e] = make_float2(b4.x, b4.y); Bc[2 * e + 1] = make_float2(b4.z, b4.w);
+      }
+      auto load_row = [&](int t, uint32_t (&w)[8]) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0));
+        const uint4 u1 = *reinterpret_cast<const uint4*>(Yh + swz(t, c0 + 1));
+        w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w; w[4] = u1.x; w[5] = u1.y; w[6] = u1.z; w[7] = u1.w;
+      };
+      auto lane_stats = [&](const uint32_t (&w)[8], float& s, float& sq) {   // two independent chains per statistic
+        float2 sa = bf_pair(w[0]), sb = bf_pair(w[1]);
+        float2 qa = fmul2(sa, sa), qb = fmul2(sb, sb);
+#pragma unroll
+        for (int e = 2; e < 8; e += 2) {
+          const float2 va = bf_pair(w[e]), vb = bf_pair(w[e + 1]);
+          sa = fadd2(sa, va); sb = fadd2(sb, vb); qa = ffma2(va, va, qa); qb = ffma2(vb, vb, qb);
+        }
+        const float2 s2 = fadd2(sa, sb), q2 = fadd2(qa, qb);
+        s = s2.x + s2.y; sq = q2.x + q2.y;
+      };
+      auto finish_row = [&](int t, const uint32_t (&w)[8], float s, float sq) {
+        const float mean = s * (1.f / D);
+        // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
+        const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+        const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
+        uint32_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // SiLU(x) = h + h*tanh(h), h = x/2 (exact identity; MUFU.TANH)
+          const float2 hv = ffma2(ffma2(bf_pair(w[e]), rs2, nm2), G[e], Bc[e]);
+          const float2 r = ffma2(hv, make_float2(tanh_approx(hv.x), tanh_approx(hv.y)), hv);
+          o[e] = pack2(r.x, r.y);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + col0);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      };
+#pragma unroll 1
+      for (int t = warp; t < T; t += 2 * NCW) {
+        const int t2 = t + NCW;
+        const bool two = t2 < T;   // warp-uniform
+        uint32_t wa[8], wb[8];
+        load_row(t, wa);
+        load_row(two ? t2 : t, wb);
+        float s0, q0, s1, q1;
+        lane_stats(wa, s0, q0);
+        lane_stats(wb, s1, q1);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o2); q0 += __shfl_xor_sync(0xffffffffu, q0, o2);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o2); q1 += __shfl_xor_sync(0xffffffffu, q1, o2);
+        }
+        finish_row(t, wa, s0, q0);
+        if (two) finish_row(t2, wb, s1, q1);
+      }
+    }
+    // hand the Q' / Y region (and the constant table) back: this warp's generic-proxy accesses are ordered before the
+    // producer's next TMA writes
+    tc::fence_async_smem();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(qy_empty_bar);
+  }
+}
+
+#ifndef DSHEG_EMU
+// (column, frame, sample) view of qkv [n_samples * T, 1536] bf16; box = 64 columns x Tpad frames of one sample.
+inline bool make_qkv_tmap(CUtensorMap* map, const void* qkv, int n_samples, int T, std::string* err) {
+  struct Key { const void* p; int n, t; bool operator==(const Key& o) const { return p == o.p && n == o.n && t == o.t; } };
+  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.t << 48); } };
+  static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+  const Key k{qkv, n_samples, T};
+  auto it = cache.find(k);
+  if (it != cache.end()) { *map = it->second; return true; }
+  tc::EncodeTiledFn fn = tc::get_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  if (reinterpret_cast<uintptr_t>(qkv) & 15) { *err = "qkv not 16-byte aligned"; return false; }
+  const int Tpad = (T + 15) / 16 * 16;
+  cuuint64_t gdim[3] = {(cuuint64_t)(3 * D), (cuuint64_t)T, (cuuint64_t)n_samples};
+  cuuint64_t gstr[2] = {(cuuint64_t)(3 * D) * 2, (cuuint64_t)T * (3 * D) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)Tpad, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (qkv, 3-D) failed, CUresult " + std::to_string((int)r); return false; }
+  if (cache.size() > 1024) cache.clear();
+  cache.emplace(k, *map);
+  return true;
+}
+
+inline cudaError_t launch_attn_tma(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
+                                   const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap map;
+  if (!make_qkv_tmap(&map, qkv, n_samples, T, err)) return cudaErrorInvalidValue;
+  const int grid = n_samples < num_sms ? n_samples : num_sms;
+  DSHEG_LAUNCH(attn_tma_kernel, grid, NTHREADS, SMEM_BYTES, st, map, z, n_samples, T, ssB, ln_g, ln_b, ss, ss_ld);
+  return cudaGetLastError();
+}
+#endif  // DSHEG_EMU
+
+}  // namespace atm
+}  // namespace dsheg

@@ -18,6 +18,7 @@
 #include "attn_v5.cuh"
 #include "attn_v6.cuh"
 #include "attn_small.cuh"
+#include "attn_tma.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -353,7 +354,7 @@ struct Runner {
     // DSHEG_QSOFT=1 (experimental, with attn_v5): softmax_d(Q) numerators + row sums come out of the QKV epilogue (tr:122);
     // the fp32 row scratch of the generic attention kernel (unused on this path) holds the [rows][8] sums
     const bool v5_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP &&
-                         ((h->attn_v2 >= 51 && h->attn_v2 <= 54) || h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64);
+                         ((h->attn_v2 >= 51 && h->attn_v2 <= 54) || h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64 || h->attn_v2 == 7);
     // DSHEG_EXPO=1 (experimental, with attn_v5; wins over QSOFT): Q AND K numerators exp(v - static shift) from the epilogue
     // (tr:122-123), for the layers whose packed weights carry provably safe shifts
     const bool kpre = v5_attn && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
@@ -366,14 +367,18 @@ struct Runner {
     const int HD = D / H;
     // algorithmic traffic: read q,k,v + write z, all in the activation type (4*rows*D*sizeof)
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
-    if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && (h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64) && kpre) {
+    if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 7 && kpre) {
+      std::string terr;
+      const cudaError_t le = atm::launch_attn_tma((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr);
+      if (le != cudaSuccess) return fail(h, std::string("attn_tma launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
+    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && (h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64) && kpre) {
       // attn_v6 (DSHEG_ATTN=v6 | v6c2, experimental): 4 warps per head, 64 registers, 32 warps per SM; consumes the ACT_EXPO numerators
       const cudaError_t le = h->attn_v2 == 64 ? av6::launch_attn_v6<4>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
                            : h->attn_v2 == 62 ? av6::launch_attn_v6<2>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
                                               : av6::launch_attn_v6<1>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
       if (le != cudaSuccess) return fail(h, std::string("attn_v6 launch: ") + cudaGetErrorString(le));
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP &&
-               (h->attn_v2 == 1 || h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64)) {   // v6 without provably safe shifts for this layer: the validated kernel
+               (h->attn_v2 == 1 || h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64 || h->attn_v2 == 7)) {   // v6 / tma without provably safe shifts for this layer: the validated kernel
       DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 4) {
       av4::attn_v4_kernel<<<2 * n_samples, av4::NTHREADS, av4::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
@@ -631,6 +636,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (att && !strcmp(att, "v6")) h->attn_v2 = 64;    // attn_v6.cuh as clusters of 4 CTAs; needs DSHEG_EXPO=1 (layers without static shifts fall back to attn_v3)
   if (att && !strcmp(att, "v6c2")) h->attn_v2 = 62;  // ... as clusters of 2 CTAs of 512 threads
   if (att && !strcmp(att, "v6c1")) h->attn_v2 = 61;  // ... as ONE 1024-thread CTA per sample (no cluster)
+  if (att && !strcmp(att, "tma")) h->attn_v2 = 7;    // attn_tma.cuh: persistent, TMA-staged; needs DSHEG_EXPO=1 (layers without static shifts fall back to attn_v3)
   const char* qso = getenv("DSHEG_QSOFT");
   h->qsoft = (qso && !strcmp(qso, "1")) ? 1 : 0;   // Q row-softmax in the QKV GEMM epilogue (needs an attn_v5 variant)
   const char* aa = getenv("DSHEG_ATTN_AUD");
@@ -1165,6 +1171,13 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
                    : att[3] == '2'  ? av6::launch_attn_v6<2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s6)
                                     : av6::launch_attn_v6<1>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s6);
     if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (v6): ") + cudaGetErrorString(le); return 1; }
+  } else if (att && !strcmp(att, "tma")) {   // input contract: Q and K columns hold exp(value - shift)
+    std::string terr;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t le = atm::launch_attn_tma((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr);
+    if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (tma): ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
   } else if (att && !strcmp(att, "v4")) {
     cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
     av4::attn_v4_kernel<<<2 * Bn, av4::NTHREADS, av4::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,

@@ -1,11 +1,14 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu).  Everything calls through the C ABI
 (ctypes) and is checked against the oracle / the committed reference outputs.
 
-Tolerances (relmax = max|got - want| / max|want|):
-  fp32 mode  : 2e-5 on a single denoiser call, 2e-4 on a full loop (fp32 reassociation only: LayerNorm folds,
-               fused epilogues, different reduction orders; measured 2e-6 / 3e-5)
-  bf16 mode  : 3e-2 on a single call and on a full loop (bf16 operands/activations, fp32 accumulation and
-               statistics, tanh-form activations in the GEMM epilogues; measured 1.3e-2 / 1e-2)
+Gates (tests/parity_util.py: relmax = max|d| / max|want| over the tensor, per_channel = worst pose channel on its OWN scale,
+rel_rms = ||d||_2 / ||want||_2), set at about 2x the largest value measured on B200 (profiles/r02/parity_report.json, which also
+holds the fp64 justification: |mode - fp64| next to the reference's own |fp32 - fp64|):
+  fp32 mode : fp32 reassociation only (LayerNorm folds, fused epilogues, reduction orders): as close to fp64 as the reference's
+              own fp32 arithmetic (k = |ours - fp64| / |ref_fp32 - fp64| = 0.9 .. 1.1).  Measured: call 1.8e-6 / 3.0e-6 / 1.5e-6,
+              ddim25 loop 9e-7 / 1.3e-6 / 8e-7, 63-call RePaint loop 3e-5, DDPM 2e-5 (re-noising amplifies last-bit differences)
+  bf16 mode : bf16 operands / activations, fp32 accumulation and statistics, tanh-form activations.
+              Measured: call 1.15e-2 / 2.4e-2 / 1.0e-2, loops (incl. the B=950 headline size) 8.2e-3 / 1.3e-2 / 7.0e-3
 """
 import ctypes
 import os
@@ -18,7 +21,17 @@ from diffsheg_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(call=2e-5, loop=2e-4), "bf16": dict(call=3e-2, loop=3e-2)}
+from parity_util import check as parity_check, fmt as parity_fmt, parity_metrics
+
+TOL = {"fp32": dict(call=dict(relmax=6e-6, per_channel=1e-5, rel_rms=5e-6), loop=dict(relmax=1e-4, per_channel=2e-4, rel_rms=1e-4)),
+       "bf16": dict(call=dict(relmax=2.5e-2, per_channel=5e-2, rel_rms=2.2e-2), loop=dict(relmax=2e-2, per_channel=3e-2, rel_rms=1.6e-2))}
+
+
+def gate(got, want, prec, kind, what):
+    m = parity_metrics(got, want)
+    print(f"\n[parity] {what} {prec}: {parity_fmt(m)}")
+    parity_check(m, TOL[prec][kind], f"{what} {prec}")
+    return m
 
 
 def relmax(a, b):
@@ -247,8 +260,8 @@ def test_op_linear_layernorm_modulate_silu_epilogue(L, M, K, T, B):
 
 
 @unvalidated
-@pytest.mark.parametrize("variant", ["v5c1", "v5c2", "v5c4", "v6", "v6c2", "v6c1"])
-@pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (1, 96), (2, 16), (1, 7)])
+@pytest.mark.parametrize("variant", ["v5c1", "v5c2", "v5c4", "v6", "v6c2", "v6c1", "tma"])
+@pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (1, 96), (2, 16), (1, 7), (301, 88), (150, 33)])
 def test_op_attention_with_static_shift_numerators(L, Bn, T, variant, monkeypatch):
     """attn_v5<CL, 2> / attn_v6: the Q and K columns hold exp(value - shift) with shifts that are NOT the maxima (per (row, head) for Q, per
     (sample, column) for K); the result must equal the attention of the original q, k."""
@@ -299,10 +312,8 @@ def test_denoise_matches_reference_golden(golden_dir, prec, name, B, T, t_resp):
     eng.prepare_window(inp["mel"].cuda(), inp["hubert"].cuda(), inp["person_id"].cuda())
     eps = eng.denoise(inp["x_T"].cuda(), int(g["t_orig"]), float(g["a"]), float(g["b"]))
     torch.cuda.synchronize()
-    err = relmax(eps, torch.from_numpy(g["eps"]))
-    print(f"\n[parity] denoise {name} B{B} T{T} t{t_resp} {prec}: relmax={err:.3e}")
     assert torch.isfinite(eps).all()
-    assert err < TOL[prec]["call"]
+    gate(eps, torch.from_numpy(g["eps"]), prec, "call", f"denoise {name} B{B} T{T} t{t_resp} vs reference golden")
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -321,9 +332,7 @@ def test_denoise_matches_oracle_variants(prec):
     with torch.no_grad():
         want = unidiffuser_forward(sd_c, cfg, inp["x_T"], ts, (torch.tensor(a, device="cuda"), torch.tensor(b, device="cuda")),
                                    inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float64)
-    err = relmax(got, want)
-    print(f"\n[parity] denoise show nocfg T40 {prec} vs fp64 oracle: relmax={err:.3e}")
-    assert err < TOL[prec]["call"]
+    gate(got, want, prec, "call", "denoise show nocfg T40 vs fp64 oracle")
 
 
 @pytest.mark.parametrize("prec,name,B,T,over", [
@@ -345,9 +354,8 @@ def test_denoise_edge_shapes_vs_oracle(prec, name, B, T, over):
     with torch.no_grad():
         want = unidiffuser_forward(sd_c, cfg, inp["x_T"], ts, (torch.tensor(a, device="cuda"), torch.tensor(b, device="cuda")),
                                    inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float64)
-    err = relmax(got, want)
-    print(f"\n[parity] denoise edge {name} B{B} T{T} {over} {prec}: relmax={err:.3e}")
-    assert torch.isfinite(got).all() and err < TOL[prec]["call"]
+    assert torch.isfinite(got).all()
+    gate(got, want, prec, "call", f"denoise edge {name} B{B} T{T} {over}")
 
 
 @pytest.mark.parametrize("opt_over,calls,undos", [(dict(no_resample=True), 15, 0), (dict(addBlend=False, jump_n_sample=2), 27, 12),
@@ -374,10 +382,8 @@ def test_repaint_flags_match_oracle_same_seed(opt_over, calls, undos):
               y=y, pe_type="pe_sinu")
     torch.manual_seed(77)
     out = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), clip_denoised=False, model_kwargs=kw)
-    err = relmax(out, want)
-    print(f"\n[parity] repaint flags {opt_over}: relmax={err:.3e} stats={diff.last_stats}")
     assert diff.last_stats == {"denoise_calls": calls, "undo_steps": undos}
-    assert err < TOL["fp32"]["loop"]
+    gate(out, want, "fp32", "loop", f"repaint flags {opt_over}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -400,10 +406,8 @@ def test_ddim25_loop_matches_reference_golden(golden_dir, prec, fn, name, B, T):
     kw = dict(audio_emb=inp["mel"].cuda(), length=None, person_id=inp["person_id"].cuda(),
               add_cond={"pretrain_aud_feat": inp["hubert"].cuda()}, y={}, pe_type="pe_sinu")
     out = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), noise=x_T, clip_denoised=False, model_kwargs=kw)
-    err = relmax(out, torch.from_numpy(g["sample"]))
-    print(f"\n[parity] ddim25 loop {name} B{B} {prec}: relmax={err:.3e}  calls={diff.last_stats}")
     assert diff.last_stats["denoise_calls"] == 25
-    assert err < TOL[prec]["loop"]
+    gate(out, torch.from_numpy(g["sample"]), prec, "loop", f"ddim25 loop {name} B{B} vs reference golden")
 
 
 def _oracle_loop_cuda(cfg, sd, inp, y, ov, ddim=True, steps=1000, seed=77, **kw):
@@ -440,10 +444,8 @@ def test_harmonize_loop_matches_oracle_same_seed(prec, name, B, T, ov, jn):
               add_cond={"pretrain_aud_feat": inp["hubert"]}, y=y, pe_type="pe_sinu")
     torch.manual_seed(77)
     out = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), clip_denoised=False, model_kwargs=kw)
-    err = relmax(out, want)
-    print(f"\n[parity] harmonize loop {name} ov{ov} jn{jn} {prec}: relmax={err:.3e} stats={diff.last_stats}")
     assert diff.last_stats == ({"denoise_calls": 63, "undo_steps": 48} if jn == 5 else {"denoise_calls": 27, "undo_steps": 12})
-    assert err < TOL[prec]["loop"]
+    gate(out, want, prec, "loop", f"harmonize loop {name} ov{ov} jn{jn}")
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -458,9 +460,7 @@ def test_ddpm_loop_matches_oracle_same_seed(prec):
               add_cond={"pretrain_aud_feat": inp["hubert"]}, y={}, pe_type="pe_sinu")
     torch.manual_seed(77)
     out = diff.p_sample_loop(eng, (2, 34, cfg["net_dim_pose"]), clip_denoised=False, model_kwargs=kw)
-    err = relmax(out, want)
-    print(f"\n[parity] ddpm40 loop beat {prec}: relmax={err:.3e}")
-    assert err < TOL[prec]["loop"]
+    gate(out, want, prec, "loop", "ddpm40 loop beat")
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -497,14 +497,36 @@ def test_long_form_windows_match_oracle_same_seed(prec):
             prev = d.ddim_sample_loop(den, (B, T, Dm), y={"gt": gt, "outpainting_mask": mask}, device="cuda")
             outs.append(prev if ii == len(mels) - 1 else prev[:, :88 - ov])
     want = torch.cat(outs, 1)
-    err = relmax(got, want)
-    print(f"\n[parity] long-form 3 windows {prec}: relmax={err:.3e}")
-    assert err < TOL[prec]["loop"]
+    gate(got, want, prec, "loop", "long-form 3 windows")
 
 
 # ------------------------------------------------------------------------------------------------
-# size-independent properties at BASELINE sizes (bf16 mode)
+# the HEADLINE size against the oracle itself (BASELINE config 2), then size-independent properties (bf16 mode)
 # ------------------------------------------------------------------------------------------------
+def test_ddim25_loop_at_the_headline_size_matches_the_fp32_oracle():
+    """SHOW n_poses=88, ddim25, CFG 1.25, B=950 -- the benchmarked configuration in the benchmarked (bf16) mode -- against the
+    fp32 oracle (the reference's op stream, eager torch, TF32 off) on the same GPU with the same injected x_T (about 14 s)."""
+    from diffsheg_b200 import FusedSpacedDiffusion, get_named_beta_schedule, space_timesteps
+    from oracle import diffusion as odiff
+    B, T = 950, 88
+    cfg, sd, eng = _engine("show", "bf16", B, T)
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=2).items()}
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=synth.make_opt(cfg), betas=get_named_beta_schedule("linear", 1000))
+    kw = dict(audio_emb=inp["mel"], length=None, person_id=inp["person_id"], add_cond={"pretrain_aud_feat": inp["hubert"]},
+              y={}, pe_type="pe_sinu")
+    got = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), noise=inp["x_T"], clip_denoised=False, model_kwargs=kw)
+    del eng
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    den = odiff.make_denoise(sd_c, cfg, inp["mel"], inp["person_id"], inp["hubert"])
+    with torch.no_grad():
+        want = odiff.OracleDiffusion(1000, "ddim25").ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"], device="cuda")
+    assert torch.isfinite(got).all()
+    gate(got, want, "bf16", "loop", "ddim25 loop SHOW B=950 (config 2) vs fp32 oracle")
+
+
+
 def test_batch_rows_are_independent_at_full_size():
     """Samples never interact: row i of a B=950 SHOW/CFG call must equal, bit for bit, the same
     sample run in a batch of 2 -- also pins tile/stripe indexing of every kernel at the headline size."""
