@@ -3,8 +3,10 @@
 n_poses=88, bs=950).  One "step" = one full ddim_sample_loop over one batch of synthetic input
 (25 denoiser calls + 25 fused DDIM updates).  Contract: see the task statement / DESIGN.md section 6.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1a|1b|1c|2|3|4|5] [--precision bf16|tf32|fp32]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+The default line (config 2, bf16) also carries: `parity` (the timed mode against the fp32 oracle, live), `ref_cuda` (the reference op
+stream run eagerly on the same GPU, fp32 and TF32: the denominator of north_star's >= 10x target), `cpu_baseline`.
 """
 import argparse
 import json
@@ -140,70 +142,156 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SHOW n_poses=88 ddim25 cond_scale=1.25 batch=950 (configs[1])", "sample": sample},
+            "config": {"workload": "SHOW n_poses=88 ddim25 cond_scale=1.25 batch=950 (configs[1])", "sample": sample, "same_config": False,
+                       "note": "CPU arm: oracle port on host cores, bounded B-sample of the 950-batch (frames/s is batch-linear on CPU)"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def run_ref_cuda(args):
-    """R-cuda row of BASELINE.md: the reference's eager torch op stream (oracle port) on the SAME GPU, fp32, torch default
-    matmul precision (TF32 off) and with TF32 on -- the denominator of north_star's >= 10x target.  Informational."""
+# ---- BASELINE.json configurations.  "2" is the one the metric is quoted on and the default ------------------------
+CONFIGS = {
+    "1a": dict(net="beat", batch=1, desc="BEAT n_poses=34 ddim25 overlap 0, single clip (configs[0]): 25 denoiser calls"),
+    "1b": dict(net="beat", batch=1, overlap=4, desc="BEAT n_poses=34 ddim25 overlap 4, single clip: RePaint schedule, 63 calls + 48 re-noise steps"),
+    "1c": dict(net="show", batch=1, desc="SHOW n_poses=88 ddim25 CFG 1.25, single clip: 25 denoiser calls (CFG pair)"),
+    "2": dict(net="show", batch=950, scaling="weak",
+              desc="SHOW n_poses=88 ddim25 cond_scale=1.25 batch=950 per GPU (configs[1]); one step = one ddim_sample_loop = 25 denoiser "
+                   "calls (CFG pair) + 25 fused DDIM updates"),
+    "3": dict(net="beat", batch=2500, ddim=False, desc="BEAT n_poses=34 ddpm1000 (p_sample_loop, no respacing) batch=2500 (configs[2]); one step = 1000 calls"),
+    "4": dict(net="show", batch=8, long_frames=1800, overlap=10, scaling="strong",
+              desc="SHOW long-form: 8 clips of 60 s (1800 frames), windows of 88 with overlap 10 (23 per clip: 25 calls, then 63 calls + 48 "
+                   "re-noise steps each), clips sharded over the GPUs (configs[3])"),
+    "5": dict(net="show", batch=4096, scaling="strong",
+              desc="SHOW n_poses=88 ddim25 CFG 1.25, GLOBAL batch 4096 split over the GPUs (configs[4])"),
+}
+
+
+def live_parity(cfg, precision, B=16):
+    """The timed mode against the fp32 oracle (reference op stream, eager torch, TF32 off) on this GPU: one 25-step DDIM loop on
+    B samples of the same synthetic distribution, same injected x_T.  Metrics: tests/parity_util.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from diffsheg_b200 import FusedSpacedDiffusion, FusedUniDiffuser, generate_batch, get_named_beta_schedule, space_timesteps, synth
+    from oracle import diffusion as odiff
+    from parity_util import parity_metrics
+    T, Dm = cfg["n_poses"], cfg["net_dim_pose"]
+    sd = synth.make_state_dict(cfg, seed=1)
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=2).items()}
+    eng = FusedUniDiffuser(sd, cfg, precision=precision, max_batch=B, max_frames=T, device=torch.cuda.current_device())
+    opt = synth.make_opt(cfg)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000), precision=precision)
+    got = generate_batch(opt, eng, diff, inp["mel"], inp["person_id"], Dm, {"pretrain_aud_feat": inp["hubert"]}, {}, noise=inp["x_T"])
+    tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    den = odiff.make_denoise(sd_c, cfg, inp["mel"], inp["person_id"], inp["hubert"])
+    with torch.no_grad():
+        want = odiff.OracleDiffusion(1000, "ddim25").ddim_sample_loop(den, (B, T, Dm), y={}, noise=inp["x_T"], device="cuda")
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+    m = parity_metrics(got, want)
+    out = {"mode": precision, "against": f"fp32 oracle (eager torch-cuda, TF32 off), ddim25 loop, B={B}, same x_T", **m}
+    try:   # the same comparison at the full B=950 size and the fp64 justification live in the committed report
+        rep = json.load(open(os.path.join(ROOT, "profiles", "r02", "parity_report.json")))
+        full = rep["cases"].get("ddim25_loop_show_B950_T88_full_size", {}).get(precision + "_vs_oracle_fp32")
+        if full:
+            out["full_size_B950"] = {**full, "source": "profiles/r02/parity_report.json (scripts/parity_report.py on B200)"}
+    except Exception:
+        pass
+    return out
+
+
+def ref_cuda_rows(cfg, B):
+    """R-cuda: the reference's eager torch op stream (oracle port) on the SAME GPU, fp32 with torch's default matmul precision
+    (TF32 off) and with TF32 on -- the denominator of north_star's >= 10x target.  No generate_src_mask host syncs,
+    i.e. an upper bound on the real reference.  One 25-step loop each at the full batch, after a small-batch warm-up."""
     from diffsheg_b200 import synth
     from oracle import diffusion as odiff
-    cfg = synth.make_cfg("show")
-    B, T = args.ref_cuda, cfg["n_poses"]
+    T, Dm = cfg["n_poses"], cfg["net_dim_pose"]
     sd = {k: v.cuda() for k, v in synth.make_state_dict(cfg, seed=1).items()}
-    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=2).items()}
-    d = odiff.OracleDiffusion(1000, "ddim25")
-    den = odiff.make_denoise(sd, cfg, inp["mel"], inp["person_id"], inp["hubert"])
     rows = {}
     for name, tf32 in (("fp32", False), ("tf32", True)):
         torch.backends.cuda.matmul.allow_tf32 = tf32
         torch.backends.cudnn.allow_tf32 = tf32
-        with torch.no_grad():
-            d.ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"], device="cuda")  # warm-up
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            d.ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"], device="cuda")
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        rows[name] = {"ms_per_step": ms, "frames_per_s": B * T / (ms / 1e3)}
-    print(json.dumps({"impl": "reference-op-stream torch-cuda eager (oracle port)", "metric": METRIC, "unit": UNIT, "batch": B,
-                      "note": "no generate_src_mask host syncs (SURVEY F8): an upper bound on the real reference", "rows": rows}))
+        for b, timed_run in ((32, False), (B, True)):
+            inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, b, T, seed=2).items()}
+            den = odiff.make_denoise(sd, cfg, inp["mel"], inp["person_id"], inp["hubert"])
+            with torch.no_grad():
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                odiff.OracleDiffusion(1000, "ddim25").ddim_sample_loop(den, (b, T, Dm), y={}, noise=inp["x_T"], device="cuda")
+                e1.record()
+                torch.cuda.synchronize()
+            if timed_run:
+                ms = e0.elapsed_time(e1)
+                rows[name] = {"ms_per_step": ms, "frames_per_s": b * T / (ms / 1e3)}
+            del inp, den
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return rows
 
 
 def run_ours(args):
-    from diffsheg_b200 import FusedSpacedDiffusion, FusedUniDiffuser, generate_batch, get_named_beta_schedule, space_timesteps, synth
-    from diffsheg_b200.dist import gather_motion
+    from diffsheg_b200 import (FusedGaussianDiffusion, FusedSpacedDiffusion, FusedUniDiffuser, generate_batch, generate_long,
+                               get_named_beta_schedule, space_timesteps, synth)
+    from diffsheg_b200.dist import gather_motion, shard_range
     world, rank, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    cfg = synth.make_cfg("show")
-    B, T, Dm = args.batch, cfg["n_poses"], cfg["net_dim_pose"]
+    C = CONFIGS[args.config]
+    cfg = synth.make_cfg(C["net"])
+    T, Dm = cfg["n_poses"], cfg["net_dim_pose"]
+    scaling = C.get("scaling", "weak")
+    ddim, overlap, long_frames = C.get("ddim", True), C.get("overlap", 0), C.get("long_frames", 0)
+    # weak: every GPU takes the config's batch; strong: the GLOBAL batch (pre-drawn inputs AND noise, one seed) is cut into
+    # contiguous rank slices, so the gathered result does not depend on the number of GPUs (SURVEY 8e)
+    per_gpu = args.batch or C["batch"]
+    if scaling == "strong":
+        total_B = per_gpu
+        lo, hi = shard_range(total_B, rank, world)
+        frames_in = long_frames or T
+        glob = synth.make_inputs(cfg, total_B, frames_in, seed=100)
+        inp = {k: v[lo:hi].contiguous() for k, v in glob.items()}
+        del glob
+        B = hi - lo
+    else:
+        B, total_B = per_gpu, per_gpu * world
+        inp = synth.make_inputs(cfg, B, long_frames or T, seed=100 + rank)
+    if B < 1:
+        raise SystemExit(f"config {args.config}: global batch {total_B} cannot be split over {world} GPUs")
     sd = synth.make_state_dict(cfg, seed=1)
     eng = FusedUniDiffuser(sd, cfg, precision=args.precision, max_batch=B, max_frames=T, device=local)
-    opt = synth.make_opt(cfg)
-    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000),
-                                precision=args.precision)
-    inp = synth.make_inputs(cfg, B, T, seed=100 + rank)
+    steps_total = 1000
+    opt = synth.make_opt(cfg, ddim=ddim, diffusion_steps=steps_total, overlap_len=overlap)
+    betas = get_named_beta_schedule("linear", steps_total)
+    diff = (FusedSpacedDiffusion(space_timesteps(steps_total, "ddim25"), opt=opt, betas=betas, precision=args.precision) if ddim
+            else FusedGaussianDiffusion(opt=opt, betas=betas, precision=args.precision))
     host = {k: inp[k].pin_memory() for k in ("mel", "hubert", "person_id")}
+    x_T = inp["x_T"].to(dev) if not long_frames else None     # pre-drawn initial noise (windows of a long clip draw their own)
     devin = {k: v.to(dev) for k, v in host.items()}
-    out_host = torch.empty(B, T, Dm).pin_memory()
-    total_B = B * world
+    frames_per_sample = long_frames or T
+    out_host = torch.empty(B, frames_per_sample, Dm).pin_memory()
+    y = {}
+    if overlap and not long_frames:   # config 1b: one repainted window (first `overlap` frames known)
+        y = {"gt": torch.randn(B, T, Dm, device=dev), "outpainting_mask": torch.zeros(B, T, Dm, dtype=torch.bool, device=dev)}
+        y["outpainting_mask"][:, :overlap] = True
+
+    def sample(mel, hub, pid):
+        if long_frames:
+            torch.manual_seed(1234 + rank)
+            return generate_long(opt, eng, diff, mel, pid, Dm, {"pretrain_aud_feat": hub})
+        return generate_batch(opt, eng, diff, mel, pid, Dm, {"pretrain_aud_feat": hub}, y, noise=x_T)
 
     def step_resident():
-        out = generate_batch(opt, eng, diff, devin["mel"], devin["person_id"], Dm, {"pretrain_aud_feat": devin["hubert"]}, {})
+        out = sample(devin["mel"], devin["hubert"], devin["person_id"])
         return gather_motion(out, total_B) if world > 1 else out
 
     def step_e2e():
         mel = host["mel"].to(dev, non_blocking=True)
         hub = host["hubert"].to(dev, non_blocking=True)
         pid = host["person_id"].to(dev, non_blocking=True)
-        out = generate_batch(opt, eng, diff, mel, pid, Dm, {"pretrain_aud_feat": hub}, {})
-        out_host.copy_(out, non_blocking=True)   # every rank reads its own result back; rank 0 also gathers
+        out = sample(mel, hub, pid)
+        out_host.copy_(out, non_blocking=True)   # every rank reads its own result back; the all-gather stays in the timed region
         return gather_motion(out, total_B) if world > 1 else out
 
     def barrier():
@@ -234,7 +322,7 @@ def run_ours(args):
         ms = timed(step_resident, args.steps)
     launches = (eng.launch_count() - launches0) + (diff.step_launches - steps0)
     clocks = cs.summary()
-    frames = total_B * T
+    frames = total_B * frames_per_sample
     value = frames / (ms / 1e3)
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -250,58 +338,73 @@ def run_ours(args):
     g, at = prof["gemm"], prof["attention"]
     gemm_tflops = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     attn_gbs = at["work"] / (at["ms"] * 1e-3) / 1e9 if at["ms"] > 0 else 0.0
-    roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16, all per-step GEMMs)" if args.precision == "bf16" else "gemm_simt_kernel (fp32)",
-            "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+    gemm_kernel = {"bf16": "gemm_tc_kernel (tcgen05 kind::f16, bf16 operands; all per-step GEMMs)",
+                   "tf32": "gemm_tf32_kernel (tcgen05 kind::tf32, fp32 activations; all per-step GEMMs)",
+                   "fp32": "gemm_simt_kernel (fp32 SIMT parity engine)"}[args.precision]
+    gemm_peak = pk["bf16_tflops_sustained"] * (0.5 if args.precision == "tf32" else 1.0)
+    roof = {"kernel": gemm_kernel, "bound": "tensor", "achieved": gemm_tflops, "peak": gemm_peak, "unit": "TFLOP/s",
+            "frac": gemm_tflops / gemm_peak, "traffic": None,
+            "peak_source": pk["source"] + ", sustained" + (" bf16 / 2 (dense TF32 rate is half the bf16 rate)" if args.precision == "tf32" else ""),
             "launches_per_step": g["count"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / ms if world == 1 else None,
             "executed_flops_per_step": g["work"]}
-    roof_attn = {"kernel": "attn_%s kernel (linear attention + LN/modulate/SiLU)" % (os.environ.get("DSHEG_ATTN") or "v3"), "bound": "hbm", "achieved": attn_gbs,
-                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": attn_gbs / pk["hbm_gbs"], "traffic": None,
-                 "peak_source": pk["source"], "launches_per_step": at["count"], "ms_per_step": at["ms"],
-                 "share_of_step": at["ms"] / ms if world == 1 else None}
+    attn_kernel = ("attn_tma_kernel (persistent, TMA-staged linear attention + LN/modulate/SiLU; attn_small for the audio layer)"
+                   if args.precision == "bf16" else "attn_kernel (generic fp32 SIMT linear attention)")
+    roof_attn = {"kernel": attn_kernel, "bound": "hbm", "achieved": attn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                 "frac": attn_gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "launches_per_step": at["count"],
+                 "ms_per_step": at["ms"], "share_of_step": at["ms"] / ms if world == 1 else None}
     if rank != 0:
         return
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one layer's 7 GEMM launches)
+    # DRAM traffic per launch of the two kernel families from the committed `ncu --set full` captures of THIS build's kernels
+    # (profiles/r02/ncu_traffic.json names the kernels it was captured from; a renamed / replaced kernel reads as null)
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01", "final_gemm_ncu_summary.json")))
-        roof["traffic"] = 1e6 * sum(k["dram_read_MB"] + k["dram_write_MB"] for k in ncu) / len(ncu)
-        roof["traffic_note"] = ("mean dram__bytes_read+write per launch over the 7 GEMMs of one layer (ncu --set full, "
-                                "profiles/r01/final_gemm_ncu_summary.json); algorithmic operand+output bytes of the same launches: "
-                                f"{ALGO_GEMM_BYTES_PER_LAYER / 7 / 1e6:.0f} MB per launch")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")))
+        if args.precision == "bf16" and args.config in ("2", "5") and not any(k.startswith("DSHEG_") and v for k, v in os.environ.items()):
+            ge, ae = tr.get("gemm_tc_kernel"), tr.get("attn_tma_kernel")
+            if ge:
+                roof["traffic"] = ge["dram_bytes_per_launch"]
+                roof["traffic_note"] = ge["note"] + f"; algorithmic operand+output bytes of the same launches: {ALGO_GEMM_BYTES_PER_LAYER / 7 / 1e6:.0f} MB per launch"
+            if ae:
+                roof_attn["traffic"] = ae["dram_bytes_per_launch"]
+                roof_attn["traffic_note"] = ae["note"] + f"; algorithmic bytes of one layer launch at B=950: {4 * 167200 * 512 * 2 / 1e6:.0f} MB"
     except Exception:
         pass
-    try:   # same for the attention kernel (default kernel attn_v3; one launch, SHOW B=950 CFG)
-        na = json.load(open(os.path.join(ROOT, "profiles", "r01", "final_attn_ncu_summary.json")))
-        if not os.environ.get("DSHEG_ATTN"):
-            roof_attn["traffic"] = 1e6 * (na["dram__bytes_read.sum"][0] + na["dram__bytes_write.sum"][0])
-            roof_attn["traffic_note"] = ("dram__bytes_read+write of one launch (ncu --set full, profiles/r01/final_attn_ncu_summary.json); "
-                                         f"algorithmic bytes of the same launch: {at['work'] / max(at['count'], 1) / 1e6:.0f} MB")
-    except Exception:
-        pass
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "SHOW n_poses=88 ddim25 cond_scale=1.25 batch=950 per GPU (configs[1]); one step = one "
-                                   "ddim_sample_loop = 25 denoiser calls (CFG pair) + 25 fused DDIM updates",
+    metric = METRIC if args.config == "2" else f"motion-frames/sec ({C['desc'].split(':')[0].split(';')[0]})"
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": C["desc"], "id": args.config,
                        "per_gpu_batch": B, "global_batch": total_B, "frames_per_step": frames, "parallelism": f"dp{world}",
-                       "l2": "per-call activations (>1 GB) and conditioning (385 MB) exceed the 126 MB L2; no explicit flush",
+                       "l2": "per-call activations and conditioning exceed the 126 MB L2 at batch >= 64; no explicit flush" if B * T >= 4096
+                             else "launch-bound regime (working set < L2): the step is a dependent chain of ~170 small kernels replayed from a CUDA graph",
                        "precision": args.precision, "final_all_gather": world > 1,
+                       "inputs": "pre-drawn with one global seed and sliced by rank (result independent of the GPU count)" if scaling == "strong"
+                                 else "per-rank seed",
                        # experiment switches in effect (empty = the shipped defaults), so variant runs describe themselves
                        "switches": {k: v for k, v in os.environ.items() if k.startswith("DSHEG_") and v}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world,
-                    "api": "diffsheg_b200.generate_batch (trainers' generate_batch seam) with pinned host mel/HuBERT/person-id in, pinned host motion out"},
+                    "api": "diffsheg_b200.generate_batch / generate_long (the trainers' generate_batch seam) with pinned host mel/HuBERT/person-id in, pinned host motion out"},
             "gpu_launches": launches,
-            "model_tflops": frames * 25 * CANON_FLOP_PER_FRAME_CALL / (ms / 1e3) / 1e12,
             "roofline": roof, "roofline_attention": roof_attn,
             "rowwise": {"ms_per_step": prof["rowwise"]["ms"], "gbs": prof["rowwise"]["work"] / max(prof["rowwise"]["ms"], 1e-9) / 1e6}}
-    if world == 1 and not args.no_cpu_baseline:
-        cores = cpu_threads()
-        fps, cms = oracle_cpu_frames_per_s(cfg, args.ref_batch, 1, 1, cores)
-        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"oracle port (reference torch-CPU op stream), B={args.ref_batch} of the 950-batch, "
-                                          f"full 25-step loop, 1 warm-up + 1 timed ({cms / 1e3:.1f} s)"}
+    if C["net"] == "show" and ddim and not long_frames:
+        line["model_tflops"] = frames * 25 * CANON_FLOP_PER_FRAME_CALL / (ms / 1e3) / 1e12
+    if world == 1:
+        del eng
+        torch.cuda.empty_cache()
+        if not args.no_parity and ddim and not long_frames:
+            line["parity"] = live_parity(cfg, args.precision)
+        if args.config == "2" and not args.no_ref_cuda:
+            rows = ref_cuda_rows(cfg, per_gpu)
+            line["ref_cuda"] = {"impl": "reference op stream, eager torch-cuda (oracle port) on this GPU, batch %d" % per_gpu, "rows": rows,
+                                "speedup_vs_fp32": value / rows["fp32"]["frames_per_s"], "speedup_vs_tf32": value / rows["tf32"]["frames_per_s"]}
+        if not args.no_cpu_baseline:
+            cores = cpu_threads()
+            fps, cms = oracle_cpu_frames_per_s(synth.make_cfg("show"), args.ref_batch, 1, 1, cores)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"oracle port (reference torch-CPU op stream), SHOW T=88 CFG ddim25, B={args.ref_batch} of the "
+                                              f"950-batch, full 25-step loop, 1 warm-up + 1 timed ({cms / 1e3:.1f} s); batch-linear on CPU"}
     print(json.dumps(line))
 
 
@@ -311,16 +414,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=950, help="per-GPU batch (BASELINE configs[1]: 950)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: 2, the one the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="override the config's batch (per GPU for weak, global for strong scaling)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample of the workload (about 10 s of CPU work per loop)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-cuda", type=int, default=0, help="time the reference op stream (oracle port) eagerly on the GPU at this batch")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference op stream eagerly on the GPU (about 20 s)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the live parity check of the timed mode against the fp32 oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.ref_cuda:
-        run_ref_cuda(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, "include", "diffsheg_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "tf32": 2}   # tf32: fp32 activations + tcgen05 kind::tf32 GEMMs
 
 
 def _sources():
@@ -83,7 +83,7 @@ SIGNATURES = {
     "dsheg_op_linear_fused": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "dsheg_bench_gemm": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(ctypes.c_float)]),
     "dsheg_op_attention": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
-    "dsheg_op_attention_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "dsheg_op_attention_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
 }
 
 

@@ -5,11 +5,12 @@
 // the exponent range, pack.py:expo_shift), V is plain:
 //   A = K'^T V / colsum(K')  [64 x 64 per head]     Y = Q' A / rowsum(Q')     z = SiLU(LN_512(Y) * (1 + scale) + shift)
 //
-// Why this shape.  Every earlier generation (attn_v3 / v5 / v6: one CTA or cluster per sample, cp.async fill -> barrier ->
-// math -> barrier -> LayerNorm -> store) plateaued at 1.9 - 2.4 TB/s whatever its occupancy (16 or 32 warps per SM) or
-// instruction count (67 k -> 35 k warp-instructions per sample): a CTA's load phase and its math phase never overlap, and CTAs
-// that start together stay in step, so HBM idles while the SMs compute and vice versa (profiles/r02).  Here the loads are
-// taken out of the compute warps altogether:
+// Why this shape.  Every earlier generation (attn_v3, and round 2's v5 / v6 experiments: one CTA or cluster per sample, cp.async
+// fill -> barrier -> math -> barrier -> LayerNorm -> store) plateaued at 1.9 - 2.4 TB/s in the sampling loop whatever its
+// occupancy (16 or 32 warps per SM) or instruction count (67 k -> 35 k warp-instructions per sample): ncu showed the L1 data pipe
+// 71 - 80 % busy (cp.async fills and, above all, the 32-bit __ldg loads of the Q fragments: 155 k of 289 k LSU wavefronts per
+// SM), a load phase and a math phase that never overlap, and CTAs that start together and stay in step (profiles/r02/call2).
+// Here the loads are taken out of the compute warps -- and out of the LSU -- altogether:
 //   * ONE persistent CTA per SM walks samples blockIdx.x, + gridDim.x, ...; a producer warp streams (sample, head) tiles with
 //     TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B -- the same XOR layout the ldmatrix code always used) into an 8-deep ring of
 //     12 KB tiles guarded by full / empty mbarriers, so the next units' K' / V -- and the next SAMPLE's, during the LayerNorm
@@ -29,7 +30,7 @@
 //     next sample's Q' tiles into L2 while the current sample is being multiplied.
 // HBM traffic: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample (unchanged).
 #pragma once
-#include "attn_v5.cuh"
+#include "attn_v3.cuh"
 #include "gemm_tc.cuh"   // tc:: mbarrier wait with watchdog, tensor-map encoder entry point
 
 namespace dsheg {
@@ -37,9 +38,11 @@ namespace atm {
 
 using av3::TP; using av3::HD; using av3::D; using av3::TILE_BYTES;
 using av3::pack2; using av3::swz;
-using av5::bf_pair; using av5::BF2_ONES;
 using prims::smem_addr; using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::tanh_approx; using prims::rcp_approx;
 using prims::ffma2; using prims::fadd2; using prims::fmul2;
+
+constexpr uint32_t BF2_ONES = 0x3F803F80u;      // bf16x2 (1.0, 1.0)
+__device__ __forceinline__ float2 bf_pair(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }   // feeds FFMA2 / FADD2
 
 constexpr int NH = 8;                          // heads
 constexpr int NGRP = 4, WPG = 4;               // consumer groups, warps per group

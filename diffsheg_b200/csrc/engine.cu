@@ -12,16 +12,13 @@
 #include <vector>
 
 #include "../../include/diffsheg_b200.h"
-#include "attn_v2.cuh"
 #include "attn_v3.cuh"
-#include "attn_v4.cuh"
-#include "attn_v5.cuh"
-#include "attn_v6.cuh"
 #include "attn_small.cuh"
 #include "attn_tma.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tf32.cuh"
 #include "kernels.cuh"
 #include "postprocess.cuh"
 #include "sampler.cuh"
@@ -86,9 +83,10 @@ struct dsheg_handle {
   std::unordered_map<std::string, DevTensor> tensors;
   bool finalized = false;
   int gemm_engine = 1;  // 1 = tcgen05 (bf16 mode default), 0 = SIMT
-  int attn_v2 = 1;      // bf16 mode: 1 = tensor-core attention (attn_v3), 4 = cluster-of-two variant (DSHEG_ATTN=v4, experimental),
-                        // 2 = previous one-warp-per-head kernel
-                        // (DSHEG_ATTN=v2), 0 = generic SIMT kernel (DSHEG_ATTN=v1)
+  // bf16 mode attention: 2 = persistent TMA-staged kernel on the ACT_EXPO numerators (attn_tma.cuh; default), falling back per
+  // layer to 1 = attn_v3 (in-kernel softmaxes) when the packer found no provably safe static shifts (DSHEG_ATTN=v3 forces it),
+  // 0 = generic SIMT kernel (DSHEG_ATTN=v1; also what T > 96 and the fp32 / tf32 modes use)
+  int attn_mode = 2;
   int64_t launches = 0;
   // resolved weights
   const float* freqs = nullptr;
@@ -107,10 +105,10 @@ struct dsheg_handle {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int state = 0; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
-  int qsoft = 0;               // DSHEG_QSOFT=1: ACT_QSOFT epilogue of the QKV GEMM + attn_v5<CL, QPRE> (experimental)
-  int attn_aud = 0;            // DSHEG_ATTN_AUD=1: attn_small.cuh for the audio encoder layer (D = 128, 8 heads of 16; experimental)
-  int fuse_lnms = 0;           // DSHEG_FUSE_LNMS=1: ffn.linear2 + LayerNorm / modulate / SiLU in one GEMM (ACT_LNMS, experimental)
-  int expo = 0;                // DSHEG_EXPO=1: ACT_EXPO epilogue (Q and K softmax numerators with static shifts) + attn_v5<CL, 2> (experimental)
+  // bisecting switches (all on by default; hardware-validated in round 2, profiles/r02):
+  int attn_aud = 1;            // DSHEG_ATTN_AUD=0: generic kernel instead of attn_small.cuh for the audio encoder layer (D = 128, 8 heads of 16)
+  int fuse_lnms = 1;           // DSHEG_FUSE_LNMS=0: separate ln_mod_silu pass instead of the ACT_LNMS epilogue of ffn.linear2 (rows >= 4096)
+  int expo = 1;                // DSHEG_EXPO=0: plain QKV epilogue + attn_v3 instead of ACT_EXPO numerators + attn_tma
   int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
   int graph_max_rows = 4096;   // B*T above which launches are no longer the bottleneck
   float2 *PS, *CS;      // fused LayerNorm statistics: per-row / per-64-column partials, conditioning partials
@@ -261,6 +259,10 @@ struct Runner {
       std::string terr;
       e = tc::launch_gemm_tc(d, h->num_sms, st, &terr);
       if (e != cudaSuccess && !terr.empty()) return fail(h, std::string("gemm ") + name + ": " + terr);
+    } else if (std::is_same<TA, float>::value && h->cfg.precision == DSHEG_PREC_TF32 && h->gemm_engine == 1 && d.M >= 16 && t32::tf32_eligible(d)) {
+      std::string terr;   // tf32 mode: tensor cores for every GEMM the TMA path can take; tiny / odd-shaped ones stay on the fp32 SIMT kernel
+      e = t32::launch_gemm_tf32(d, st, &terr);
+      if (e != cudaSuccess && !terr.empty()) return fail(h, std::string("gemm ") + name + " (tf32): " + terr);
     } else {
       e = launch_gemm_simt<TA, TW>(d, st);
     }
@@ -351,15 +353,10 @@ struct Runner {
     gq.a[0] = seg(hcur, ldc, D); gq.nseg = 1; gq.M = rows;
     gq.csum = L.qkv.csum;
     gq.out = h->QKV; gq.ldo = 3 * D;
-    // DSHEG_QSOFT=1 (experimental, with attn_v5): softmax_d(Q) numerators + row sums come out of the QKV epilogue (tr:122);
-    // the fp32 row scratch of the generic attention kernel (unused on this path) holds the [rows][8] sums
-    const bool v5_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP &&
-                         ((h->attn_v2 >= 51 && h->attn_v2 <= 54) || h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64 || h->attn_v2 == 7);
-    // DSHEG_EXPO=1 (experimental, with attn_v5; wins over QSOFT): Q AND K numerators exp(v - static shift) from the epilogue
-    // (tr:122-123), for the layers whose packed weights carry provably safe shifts
-    const bool kpre = v5_attn && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
-    const bool qpre = v5_attn && h->qsoft && h->gemm_engine == 1 && !kpre && h->attn_v2 < 60;
-    if (qpre) { gq.act = ACT_QSOFT; gq.qsum = h->Y32; gq.qsoft_cols = D; }
+    // Softmax numerators from the epilogue (tr:122-123): Q and K leave the QKV GEMM as exp(v - static shift) for the layers whose
+    // packed weights carry provably safe shifts (pack.py:expo_shift); attn_tma consumes them.  Other layers: plain epilogue + attn_v3.
+    const bool tc_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP;
+    const bool kpre = tc_attn && h->attn_mode == 2 && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
     if (kpre) { gq.act = ACT_EXPO; gq.eshift = L.qkv_eshift; gq.expo_cols = 2 * D; }
     if (gemm(gq, L.qkv, "qkv")) return 1;
     // K9 + K10 prologue: linear attention, then LN * (1+scale) + shift, SiLU
@@ -367,41 +364,12 @@ struct Runner {
     const int HD = D / H;
     // algorithmic traffic: read q,k,v + write z, all in the activation type (4*rows*D*sizeof)
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
-    if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 7 && kpre) {
+    if (kpre) {
       std::string terr;
       const cudaError_t le = atm::launch_attn_tma((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr);
       if (le != cudaSuccess) return fail(h, std::string("attn_tma launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
-    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && (h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64) && kpre) {
-      // attn_v6 (DSHEG_ATTN=v6 | v6c2, experimental): 4 warps per head, 64 registers, 32 warps per SM; consumes the ACT_EXPO numerators
-      const cudaError_t le = h->attn_v2 == 64 ? av6::launch_attn_v6<4>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-                           : h->attn_v2 == 62 ? av6::launch_attn_v6<2>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-                                              : av6::launch_attn_v6<1>((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
-      if (le != cudaSuccess) return fail(h, std::string("attn_v6 launch: ") + cudaGetErrorString(le));
-    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP &&
-               (h->attn_v2 == 1 || h->attn_v2 == 61 || h->attn_v2 == 62 || h->attn_v2 == 64 || h->attn_v2 == 7)) {   // v6 / tma without provably safe shifts for this layer: the validated kernel
+    } else if (tc_attn && h->attn_mode >= 1) {   // no provably safe shifts for this layer (or DSHEG_ATTN=v3 / DSHEG_EXPO=0): softmaxes in the kernel
       DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
-    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 == 4) {
-      av4::attn_v4_kernel<<<2 * n_samples, av4::NTHREADS, av4::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
-    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av3::D && H == av3::NH && T <= av3::TP && h->attn_v2 >= 51 && h->attn_v2 <= 54) {
-      // attn_v5<CL>: instruction-diet kernel as 1 / 2 / 4 CTAs per sample (DSHEG_ATTN=v5c1 | v5c2 | v5c4; experimental)
-      const bf16* qp = (const bf16*)h->QKV; bf16* zp = (bf16*)h->Z;
-      cudaError_t le;
-      if (kpre) {
-        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1, 2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-           : h->attn_v2 == 52 ? av5::launch_attn_v5<2, 2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-                              : av5::launch_attn_v5<4, 2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
-      } else if (qpre) {
-        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1, 1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
-           : h->attn_v2 == 52 ? av5::launch_attn_v5<2, 1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32)
-                              : av5::launch_attn_v5<4, 1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st, h->Y32);
-      } else {
-        le = h->attn_v2 == 51 ? av5::launch_attn_v5<1>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-           : h->attn_v2 == 52 ? av5::launch_attn_v5<2>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st)
-                              : av5::launch_attn_v5<4>(qp, zp, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, st);
-      }
-      if (le != cudaSuccess) return fail(h, std::string("attn_v5 launch: ") + cudaGetErrorString(le));
-    } else if (std::is_same<TA, bf16>::value && HD == 64 && D == av2::D && H == av2::NH && T <= av2::TP && h->attn_v2 == 2) {
-      av2::attn_v2_kernel<<<n_samples, 256, av2::SMEM_BYTES, st>>>((const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 64) {
       attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
                                                                           L.sa_g, L.sa_b, ss, ss_ld);
@@ -427,10 +395,11 @@ struct Runner {
     if (gemm(f1, L.ffn1, "ffn1")) return 1;
     GemmDesc f2;
     f2.a[0] = seg(h->F1, F, F); f2.nseg = 1; f2.M = rows; f2.out = h->Y; f2.ldo = D;
-    // DSHEG_FUSE_LNMS=1 (experimental): the StylizationBlock prologue (LayerNorm, modulation, SiLU; tr:92-96) runs in the epilogue
-    // of linear2 -- a CTA pair holds both 256-column halves of its rows in TMEM -- so `y` is never written and the row-wise pass
-    // below disappears.  Needs 256-wide tiles: bf16, tcgen05 engine, D == 512 (CTA pairs for rows >= 4096, single CTAs below).
-    const bool fuse_lnms = std::is_same<TA, bf16>::value && h->fuse_lnms && h->gemm_engine == 1 && D == 512 && tc::g_bn_override() != 128;
+    // The StylizationBlock prologue (LayerNorm, modulation, SiLU; tr:92-96) runs in the epilogue of linear2 -- a CTA pair holds
+    // both 256-column halves of its rows in TMEM -- so `y` is never written and the row-wise pass below disappears (-30 ms of
+    // row-wise time against +22 ms of GEMM time per B = 950 step).  bf16, tcgen05 engine, D == 512, rows >= 4096 (the single-CTA
+    // form measured SLOWER than the separate pass in the launch-bound single-clip configurations: 725 vs 787 frames/s).
+    const bool fuse_lnms = std::is_same<TA, bf16>::value && h->fuse_lnms && h->gemm_engine == 1 && D == 512 && rows >= 4096 && tc::g_bn_override() != 128;
     if (fuse_lnms) {
       f2.act = ACT_LNMS; f2.out = h->Z;
       f2.lnms_g = L.ffn_g; f2.lnms_b = L.ffn_b; f2.lnms_ss = ss + 2 * D; f2.lnms_ld = ss_ld; f2.lnms_B = ssB; f2.lnms_T = T;
@@ -608,7 +577,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
     g_create_error = "unsupported configuration (need latent 512 / 8 heads of 64, audio 128 / 8 heads of 16)";
     return 1;
   }
-  if (cfg->precision != DSHEG_PREC_FP32 && cfg->precision != DSHEG_PREC_BF16) { g_create_error = "bad precision"; return 1; }
+  if (cfg->precision != DSHEG_PREC_FP32 && cfg->precision != DSHEG_PREC_BF16 && cfg->precision != DSHEG_PREC_TF32) { g_create_error = "bad precision"; return 1; }
   DeviceGuard dg(device);
   cudaError_t e = dg.err;
   if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return 1; }
@@ -627,24 +596,14 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   const char* eng = getenv("DSHEG_GEMM_ENGINE");
   if (eng && !strcmp(eng, "simt")) h->gemm_engine = 0;
   const char* att = getenv("DSHEG_ATTN");
-  if (att && !strcmp(att, "v1")) h->attn_v2 = 0;
-  if (att && !strcmp(att, "v2")) h->attn_v2 = 2;
-  if (att && !strcmp(att, "v4")) h->attn_v2 = 4;   // cluster-of-two half-sample CTAs (attn_v4.cuh; experimental)
-  if (att && !strcmp(att, "v5c1")) h->attn_v2 = 51;  // attn_v5.cuh, 1 / 2 / 4 CTAs per sample (experimental)
-  if (att && !strcmp(att, "v5c2")) h->attn_v2 = 52;
-  if (att && !strcmp(att, "v5c4")) h->attn_v2 = 54;
-  if (att && !strcmp(att, "v6")) h->attn_v2 = 64;    // attn_v6.cuh as clusters of 4 CTAs; needs DSHEG_EXPO=1 (layers without static shifts fall back to attn_v3)
-  if (att && !strcmp(att, "v6c2")) h->attn_v2 = 62;  // ... as clusters of 2 CTAs of 512 threads
-  if (att && !strcmp(att, "v6c1")) h->attn_v2 = 61;  // ... as ONE 1024-thread CTA per sample (no cluster)
-  if (att && !strcmp(att, "tma")) h->attn_v2 = 7;    // attn_tma.cuh: persistent, TMA-staged; needs DSHEG_EXPO=1 (layers without static shifts fall back to attn_v3)
-  const char* qso = getenv("DSHEG_QSOFT");
-  h->qsoft = (qso && !strcmp(qso, "1")) ? 1 : 0;   // Q row-softmax in the QKV GEMM epilogue (needs an attn_v5 variant)
+  if (att && !strcmp(att, "v1")) h->attn_mode = 0;
+  if (att && !strcmp(att, "v3")) h->attn_mode = 1;
   const char* aa = getenv("DSHEG_ATTN_AUD");
-  h->attn_aud = (aa && !strcmp(aa, "1")) ? 1 : 0;
+  if (aa && !strcmp(aa, "0")) h->attn_aud = 0;
   const char* fl = getenv("DSHEG_FUSE_LNMS");
-  h->fuse_lnms = (fl && !strcmp(fl, "1")) ? 1 : 0;
+  if (fl && !strcmp(fl, "0")) h->fuse_lnms = 0;
   const char* exo = getenv("DSHEG_EXPO");
-  h->expo = (exo && !strcmp(exo, "1")) ? 1 : 0;    // Q and K numerators with static shifts in the QKV epilogue (needs an attn_v5 variant)
+  if (exo && !strcmp(exo, "0")) h->expo = 0;
   const char* gr = getenv("DSHEG_GRAPHS");
   if (gr && !strcmp(gr, "0")) h->use_graphs = 0;
   const char* fs = getenv("DSHEG_FUSE_STATS");
@@ -693,12 +652,9 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   cudaFuncSetAttribute(attn_kernel<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn64);
   cudaFuncSetAttribute(attn_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(attn_kernel<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
-  cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
   cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
-  if (h->attn_aud)       // opt-in kernel (same rule)
+  if (h->attn_aud)
     cudaFuncSetAttribute(asmall::attn_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmall::smem_bytes(c.max_frames < asmall::TP ? c.max_frames : asmall::TP));
-  if (h->attn_v2 == 4)   // opt-in kernel: keep the default create path free of calls that have not run on hardware
-    cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
   cudaFuncSetAttribute(hubconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
   cudaFuncSetAttribute(hubconv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
   e = cudaGetLastError();
@@ -977,7 +933,7 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
   GemmDesc d;
   d.nseg = 1; d.M = M; d.N = N; d.bias = bias; d.act = act;
   const int Kp = round_up(K, 64);
-  if (precision == DSHEG_PREC_FP32) {
+  if (precision == DSHEG_PREC_FP32 || precision == DSHEG_PREC_TF32) {
     // the SIMT kernel reads W with row stride Kp: repack when K is not a multiple of 64
     float* Wp = nullptr;
     if (Kp != K) {
@@ -987,10 +943,17 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
     }
     d.a[0].ptr = A; d.a[0].ld = K; d.a[0].k = K; d.w = Wp ? Wp : W; d.Kp = Kp;
     d.res = residual; d.ldr = N; d.res_f32 = 1; d.out = out; d.ldo = N; d.out_f32 = 1;
-    cudaError_t e = launch_gemm_simt<float, float>(d, st);
-    cudaStreamSynchronize(st);
+    cudaError_t e;
+    std::string terr;
+    if (precision == DSHEG_PREC_TF32) {
+      if (!t32::tf32_eligible(d)) { if (Wp) cudaFree(Wp); g_create_error = "op_linear tf32: operands must be 16-byte aligned with K % 4 == 0"; return 1; }
+      e = t32::launch_gemm_tf32(d, st, &terr);
+    } else {
+      e = launch_gemm_simt<float, float>(d, st);
+    }
+    const cudaError_t e2 = cudaStreamSynchronize(st);
     if (Wp) cudaFree(Wp);
-    if (e != cudaSuccess) { g_create_error = std::string("op_linear simt: ") + cudaGetErrorString(e); return 1; }
+    if (e != cudaSuccess || e2 != cudaSuccess) { g_create_error = std::string("op_linear fp32/tf32: ") + terr + " " + cudaGetErrorString(e != cudaSuccess ? e : e2); return 1; }
     return step_done("dsheg_op_linear");
   }
   // bf16 engine: bf16 operands; bf16 output + bf16 residual when N % 32 == 0 (the engine's layout), else fp32 output
@@ -1144,48 +1107,20 @@ int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, c
 }
 
 int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_b, const float* scale_shift, void* z, int32_t Bn,
-                            int32_t T, void* stream) {
+                            int32_t T, int32_t numerators, void* stream) {
   if (T > av3::TP || T < 1) { g_create_error = "op_attention_bf16: T must be <= 96"; return 1; }
-  const char* att = getenv("DSHEG_ATTN");
-  if (att && !strcmp(att, "v2")) {
-    cudaFuncSetAttribute(av2::attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::SMEM_BYTES);
-    av2::attn_v2_kernel<<<Bn, 256, av2::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b, scale_shift,
-                                                                            2 * av2::D);
-  } else if (att && !strncmp(att, "v5c", 3) && (att[3] == '1' || att[3] == '2' || att[3] == '4') && !att[4]) {
-    const cudaStream_t s5 = (cudaStream_t)stream;
-    const char* exo = getenv("DSHEG_EXPO");   // "1": the Q and K columns of `qkv` already hold exp(value - shift) (attn_v5<CL, 2>)
-    if (exo && !strcmp(exo, "1")) {
-      cudaError_t le2 = att[3] == '1' ? av5::launch_attn_v5<1, 2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
-                      : att[3] == '2' ? av5::launch_attn_v5<2, 2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
-                                      : av5::launch_attn_v5<4, 2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5);
-      if (le2 != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (v5, expo): ") + cudaGetErrorString(le2); return 1; }
-      return step_done("dsheg_op_attention_bf16");
-    }
-    cudaError_t le = att[3] == '1' ? av5::launch_attn_v5<1>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
-                   : att[3] == '2' ? av5::launch_attn_v5<2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5)
-                                   : av5::launch_attn_v5<4>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s5);
-    if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (v5): ") + cudaGetErrorString(le); return 1; }
-  } else if (att && (!strcmp(att, "v6") || !strcmp(att, "v6c2") || !strcmp(att, "v6c1"))) {   // input contract: Q and K columns hold exp(value - shift)
-    const cudaStream_t s6 = (cudaStream_t)stream;
-    cudaError_t le = !att[2]        ? av6::launch_attn_v6<4>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s6)
-                   : att[3] == '2'  ? av6::launch_attn_v6<2>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s6)
-                                    : av6::launch_attn_v6<1>((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, s6);
-    if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (v6): ") + cudaGetErrorString(le); return 1; }
-  } else if (att && !strcmp(att, "tma")) {   // input contract: Q and K columns hold exp(value - shift)
+  DeviceGuard dg(device_of(qkv));
+  if (numerators) {   // input contract of the engine's default path: Q and K columns hold exp(value - shift) (ACT_EXPO epilogue)
     std::string terr;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t le = atm::launch_attn_tma((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr);
     if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (tma): ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
-  } else if (att && !strcmp(att, "v4")) {
-    cudaFuncSetAttribute(av4::attn_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av4::SMEM_BYTES);
-    av4::attn_v4_kernel<<<2 * Bn, av4::NTHREADS, av4::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
-                                                                                          scale_shift, 2 * av4::D);
-  } else {
+  } else {            // plain q, k, v: softmaxes inside the kernel (the per-layer fallback)
     cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
-    av3::attn_v3_kernel<<<Bn, av3::NTHREADS, av3::SMEM_BYTES, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
-                                                                                      scale_shift, 2 * av3::D);
+    DSHEG_LAUNCH(av3::attn_v3_kernel, Bn, av3::NTHREADS, av3::SMEM_BYTES, (cudaStream_t)stream, (const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
+                 scale_shift, 2 * av3::D);
   }
   return step_done("dsheg_op_attention_bf16");
 }

@@ -53,32 +53,13 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false, bool ROWL
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel uses 256-wide tiles");
   static constexpr int NE = BN / 16;  // epilogue warps
   static constexpr int NUM_THREADS = 128 + NE * 32;
-#ifndef DSHEG_PAIR_STAGES
-#define DSHEG_PAIR_STAGES 4
-#endif
+  // pair kernels: 4 ring stages for K = 512 (epilogue-sensitive: wide boxes, double-buffered vectors), 5 / 6 for K >= 768.
+  // Measured and rejected on B200 (profiles/r02/call1): a fifth stage for K = 512 (-2 % in the loop), separate A / W rings
+  // with two producer threads (7 + 3 and 6 + 4: -2 ... -5 %), L2 prefetch of the next A panel (-4 %).
+  static constexpr int PAIR_STAGES = 4;
   static constexpr int STG_BYTES = NARROW ? STG_BYTES_NARROW : STG_BYTES_WIDE;
-  // -DDSHEG_K512_DEEP=1 (experiment build, scripts/build_variants.sh): the K = 512 pair kernels also run at the smem limit --
-  // WIDE boxes kept, no alignment slack, single-buffered vectors -> a FIFTH stage (5 * 32 KB + 64 KB + 2.5 KB = 226.5 KB).
-  // Round 1 only measured "6 stages + narrow boxes" for these shapes (slower); the stage sweep says depth itself helps.
-#ifndef DSHEG_K512_DEEP
-#define DSHEG_K512_DEEP 0
-#endif
-  // -DDSHEG_SPLIT_RINGS=1 (experiment build): the K = 512 pair kernels stage A and W in SEPARATE rings with separate producer
-  // threads -- a DEEP A ring (the A panel streams from HBM: ~1.2 us of latency to cover; round 1's L2 prefetch of the next A
-  // panel gave +15 % on ffn1) and a SHALLOW W ring (W panels are L2-resident).  Same smem as 5 unified stages buys 7 A + 3 W.
-#ifndef DSHEG_SPLIT_RINGS
-#define DSHEG_SPLIT_RINGS 0
-#endif
-#ifndef DSHEG_SPLIT_A
-#define DSHEG_SPLIT_A 7
-#endif
-#ifndef DSHEG_SPLIT_W
-#define DSHEG_SPLIT_W 3
-#endif
-  static constexpr bool SPLIT = CG == 2 && !LONGK && DSHEG_SPLIT_RINGS;
-  static constexpr int SA = DSHEG_SPLIT_A, SW = DSHEG_SPLIT_W;
-  static constexpr bool AT_LIMIT = CG == 2 && (LONGK || DSHEG_K512_DEEP || SPLIT);
-  static constexpr int STAGES = CG == 2 ? (LONGK ? ((NARROW && !ROWLN) ? DSHEG_PAIR_STAGES + 2 : DSHEG_PAIR_STAGES + 1) : DSHEG_PAIR_STAGES + (DSHEG_K512_DEEP ? 1 : 0))
+  static constexpr bool AT_LIMIT = CG == 2 && LONGK;
+  static constexpr int STAGES = CG == 2 ? (LONGK ? ((NARROW && !ROWLN) ? PAIR_STAGES + 2 : PAIR_STAGES + 1) : PAIR_STAGES)
                                         : (BN == 128 ? 5 : 3);
   // pair kernels run at the smem limit: the dynamic smem base is required to be 1024-aligned (checked, traps otherwise)
   // and the per-tile bias/csum vectors are single-buffered (one extra epilogue barrier per tile)
@@ -88,8 +69,8 @@ template <int BN, int CG = 1, bool NARROW = false, bool LONGK = false, bool ROWL
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
   static constexpr int VEC_BYTES = ROWLN ? 3 * (2 * BN) * 4 + 2 * (BN / CPW) * BM * 8 : NVEC * 2 * BN * 4;
-  static constexpr int PIPE_BYTES = SPLIT ? SA * A_BYTES + SW * B_BYTES : STAGES * STAGE_BYTES;
-  static constexpr int NBAR_RING = SPLIT ? 2 * (SA + SW) : 2 * STAGES;   // ring barriers (full + empty)
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int NBAR_RING = 2 * STAGES;   // ring barriers (full + empty)
   static_assert((NBAR_RING + 2 * NUM_ACC + NE + 1) * 8 <= BAR_BYTES, "barrier block too small");
   static constexpr int SMEM_BYTES = PIPE_BYTES + NE * STG_BYTES + ALIGN_SLACK + BAR_BYTES + VEC_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
@@ -108,8 +89,6 @@ struct Params {
   void* out; int ldo; void* out2;
   float2* ps_out; const float* nullc; int n_uncond;
   const float2* ps_in; const float2* cs_in; int ps_slots; float ps_invP;
-  int prefetch;
-  float* qsum; int qsoft_cols;   // ACT_QSOFT (appended: the offsets of the fields above are part of the validated kernels)
   const float* eshift; int expo_cols;   // ACT_EXPO (appended likewise)
   const float* lnms_g; const float* lnms_b; const float* lnms_ss; int lnms_ld, lnms_B, lnms_T;   // ACT_LNMS (appended likewise)
 };
@@ -158,12 +137,10 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
   return x;
 }
 
-// -DDSHEG_EPI_PACKED=1 (experiment build): the LayerNorm fold, bias add and activations of the generic epilogue run on packed fp32
-// (FFMA2 / FMUL2 / FADD2, column pairs): the K = 512 tiles are epilogue-sensitive, and the GELU epilogue spends 7 fp32
-// instructions per element (3.5 packed + MUFU.TANH).  Same arithmetic, same rounding; default build unchanged.
-#ifndef DSHEG_EPI_PACKED
-#define DSHEG_EPI_PACKED 0
-#endif
+// The LayerNorm fold, bias add and activations of the generic epilogue run on packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2, column
+// pairs): the K = 512 tiles are epilogue-sensitive and the GELU epilogue would spend 7 scalar fp32 instructions per element
+// (3.5 packed + MUFU.TANH).  Same arithmetic, same rounding as the scalar form; measured on B200: ffn1 1165 -> 1224 TF/s
+// isolated, +1.6 % in the sampling loop (profiles/r02/call1).
 template <int ACT> __device__ __forceinline__ float2 act_fast2(float2 x) {
   if (ACT == ACT_SILU) {
     const float2 h = fmul2(x, make_float2(0.5f, 0.5f));
@@ -199,13 +176,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t bar_base = stg_base + NE * STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-#if DSHEG_SPLIT_RINGS
-  // split rings (C::SPLIT): [full_a SA][empty_a SA][full_w SW][empty_w SW] take the place of [full STAGES][empty STAGES]
-  auto full_a = [&](int s) { return bar_base + 8u * s; };
-  auto empty_a = [&](int s) { return bar_base + 8u * (C::SA + s); };
-  auto full_w = [&](int s) { return bar_base + 8u * (2 * C::SA + s); };
-  auto empty_w = [&](int s) { return bar_base + 8u * (2 * C::SA + C::SW + s); };
-#endif
   auto tfull_bar = [&](int a) { return bar_base + 8u * (C::NBAR_RING + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (C::NBAR_RING + NUM_ACC + a); };
   auto res_bar = [&](int e) { return bar_base + 8u * (C::NBAR_RING + 2 * NUM_ACC + e); };
@@ -221,9 +191,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   auto tile_next = [&](int tile) { return ROWLN ? ((tile & 1) ? tile + 2 * cta_stride - 1 : tile + 1) : tile + cta_stride; };
 
   if (warp == 0 && lane == 0) {
-#if DSHEG_SPLIT_RINGS
-    if (C::SPLIT) { for (int s = 0; s < 2 * (C::SA + C::SW); ++s) mbar_init(bar_base + 8u * s, 1); } else
-#endif
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NE * CG); }
     for (int e = 0; e < NE; ++e) mbar_init(res_bar(e), 1);
@@ -244,38 +211,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // statistics and outputs below do
   DSHEG_PDL_WAIT();
 
-#if DSHEG_SPLIT_RINGS   // experiment build only: the default translation unit is token-identical to the validated kernel
-  if (C::SPLIT && (warp == 0 || warp == 2)) {
-    // ================= split rings: warp 0 streams A (deep ring), warp 2 streams W (shallow ring) =================
-    if (lane == 0) {
-      const bool is_a = warp == 0;
-      const int nst = is_a ? C::SA : C::SW;
-      const uint32_t ring0 = is_a ? smem_base : smem_base + C::SA * A_BYTES;
-      const uint32_t slot_bytes = is_a ? A_BYTES : C::B_BYTES;
-      const uint32_t full0 = is_a ? full_a(0) : full_w(0), empty0 = is_a ? empty_a(0) : empty_w(0);
-      const uint32_t leader_full0 = mapa_rank(full0, 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
-        const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
-        int seg = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          while (kb >= p.seg_kb_start[seg + 1]) ++seg;
-          mbar_wait(empty0 + 8u * stage, phase ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(full0 + 8u * stage, 2 * slot_bytes);   // both CTAs' bytes land on the leader's barrier
-          const uint32_t dst = ring0 + stage * slot_bytes, lb = leader_full0 + 8u * stage;
-          if (is_a) {
-            const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
-            tma_load_2d_pair(ma, lb, dst, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
-          } else {
-            tma_load_2d_pair(&tmW, lb, dst, kb * BK, n_blk * BN + (int)rank * (BN / 2));
-          }
-          if (++stage == nst) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    __syncwarp();
-  } else
-#endif
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -283,29 +218,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t leader_full0 = CG == 2 ? mapa_rank(full_bar(0), 0) : 0u;
       for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
         const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
-        // prefetch the next tile's A panel into L2 (only when it is a new M-tile: the n-fastest order makes the
-        // CTAs of one wave share a panel, so each panel is prefetched by the tiles_n CTAs that will read it)
-        const int next = tile_next(tile);
-        const bool pf = p.prefetch == 1 && next < num_tiles && (next / p.tiles_n) != (tile / p.tiles_n);
-        const int pf_m = pf ? ((next / p.tiles_n) * CG + (int)rank) * BM : 0;
         int seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           while (kb >= p.seg_kb_start[seg + 1]) ++seg;
-          if (pf && (kb % p.tiles_n) == n_blk) {   // the tiles_n CTAs sharing the next panel split its k-blocks
-            const CUtensorMap* mp = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
-            tma_prefetch_l2_2d(mp, (kb - p.seg_kb_start[seg]) * BK, pf_m);
-          }
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
           if (CG == 2) {
             // both CTAs fill their own smem; all bytes are credited to the leader's full barrier
-            // p.prefetch == 2: TIMING EXPERIMENT ONLY (wrong results) -- skip the W fill to model a smem-resident W panel
-            const bool skip_w = p.prefetch == 2 && tile != cta_first;
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), skip_w ? 2 * A_BYTES : 2 * STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             const uint32_t lb = leader_full0 + 8u * stage;
             tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
-            if (!skip_w) tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
@@ -320,26 +244,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ================= MMA issuer =================
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
-#if DSHEG_SPLIT_RINGS
-      int wstage = 0; uint32_t wphase = 0;   // W ring of the split-ring build
-#endif
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-#if DSHEG_SPLIT_RINGS
-          if (C::SPLIT) { mbar_wait(full_a(stage), phase); mbar_wait(full_w(wstage), wphase); } else
-#endif
           mbar_wait(full_bar(stage), phase);        // TMA bytes have landed
           tc_fence_after();
-#if DSHEG_SPLIT_RINGS
-          const uint32_t sa = C::SPLIT ? smem_base + stage * A_BYTES : smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = C::SPLIT ? smem_base + C::SA * A_BYTES + wstage * C::B_BYTES : sa + A_BYTES;
-#else
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-#endif
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -347,14 +260,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (CG == 2) tc_mma_bf16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
             else tc_mma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
           }
-#if DSHEG_SPLIT_RINGS
-          if (C::SPLIT) {   // frees the A slot and the W slot (in both CTAs) when the MMAs retire
-            tc_commit_pair(empty_a(stage)); tc_commit_pair(empty_w(wstage));
-            if (++stage == C::SA) { stage = 0; phase ^= 1; }
-            if (++wstage == C::SW) { wstage = 0; wphase ^= 1; }
-            continue;
-          }
-#endif
           if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));  // frees the smem slot(s) when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -538,59 +443,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (RES == RES_BF16) { mbar_wait(res_bar(e), res_phase); res_phase ^= 1; }
-      if (ACT == ACT_QSOFT && LN && !OUTF32 && !NARROW && RES == RES_NONE && nc0 < p.qsoft_cols) {
-        // ---- softmax_d(Q) numerators (transformer.py:122): this warp's 64 columns are exactly one head of Q.  Two passes
-        //      over TMEM (reads are cheap, the GEMM's ALUs idle under the tensor pipe): row max, then exp2 + row sum.
-        //      The attention kernel multiplies by 1 / qsum after its Q'.A product, so nothing is normalised here.
-        const float* bvec = vb + cg * CPW;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int ch = 0; ch < CPW / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bvec + ch * 32 + j), c4 = *reinterpret_cast<const float4*>(bvec + BN + ch * 32 + j);
-            mx = fmaxf(mx, fmaxf(fmaxf(fmaf(rs, __uint_as_float(r[j]), fmaf(rm, c4.x, b4.x)), fmaf(rs, __uint_as_float(r[j + 1]), fmaf(rm, c4.y, b4.y))),
-                                 fmaxf(fmaf(rs, __uint_as_float(r[j + 2]), fmaf(rm, c4.z, b4.z)), fmaf(rs, __uint_as_float(r[j + 3]), fmaf(rm, c4.w, b4.w)))));
-          }
-        }
-        const float L2E = 1.4426950408889634f;
-        const float nmx = -mx * L2E;
-        float qs = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < CPW / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * CPW + ch * 32), r);
-          if (ch == CPW / 32 - 1) {   // last TMEM read of this warp: hand the accumulator stage back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
-            }
-          }
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bvec + ch * 32 + j), c4 = *reinterpret_cast<const float4*>(bvec + BN + ch * 32 + j);
-            v[j] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j]), fmaf(rm, c4.x, b4.x)), L2E, nmx));
-            v[j + 1] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j + 1]), fmaf(rm, c4.y, b4.y)), L2E, nmx));
-            v[j + 2] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j + 2]), fmaf(rm, c4.z, b4.z)), L2E, nmx));
-            v[j + 3] = ex2_fast(fmaf(fmaf(rs, __uint_as_float(r[j + 3]), fmaf(rm, c4.w, b4.w)), L2E, nmx));
-            qs += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 w;
-            w.x = pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]);
-            w.y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
-            w.z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]);
-            w.w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
-            *reinterpret_cast<uint4*>(stg_gen + lane * 128 + (((ch * 4 + u) ^ (lane & 7)) << 4)) = w;
-          }
-        }
-        if (row_ok) p.qsum[(size_t)m * (p.qsoft_cols / CPW) + (nc0 / CPW)] = qs;
-      } else
 #pragma unroll
       for (int ch = 0; ch < CPW / 32; ++ch) {
         uint32_t r[32];
@@ -608,7 +460,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bvec + j);
-#if DSHEG_EPI_PACKED
           {
             float2 p0 = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), p1 = make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             if (LN) {
@@ -623,19 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (ACT == ACT_EXPO && expo) { p0 = make_float2(ex2_fast(p0.x), ex2_fast(p0.y)); p1 = make_float2(ex2_fast(p1.x), ex2_fast(p1.y)); }
             p0 = act_fast2<ACT>(p0); p1 = act_fast2<ACT>(p1);
             v[j] = p0.x; v[j + 1] = p0.y; v[j + 2] = p1.x; v[j + 3] = p1.y;
-            continue;
           }
-#endif
-          float t0 = __uint_as_float(r[j]), t1 = __uint_as_float(r[j + 1]), t2 = __uint_as_float(r[j + 2]), t3 = __uint_as_float(r[j + 3]);
-          if (LN) {
-            const float4 c4 = *reinterpret_cast<const float4*>(bvec + BN + j);
-            t0 = fmaf(rs, t0, fmaf(rm, c4.x, b4.x)); t1 = fmaf(rs, t1, fmaf(rm, c4.y, b4.y));
-            t2 = fmaf(rs, t2, fmaf(rm, c4.z, b4.z)); t3 = fmaf(rs, t3, fmaf(rm, c4.w, b4.w));
-          } else {
-            t0 += b4.x; t1 += b4.y; t2 += b4.z; t3 += b4.w;
-          }
-          if (ACT == ACT_EXPO && expo) { t0 = ex2_fast(t0); t1 = ex2_fast(t1); t2 = ex2_fast(t2); t3 = ex2_fast(t3); }
-          v[j] = act_fast<ACT>(t0); v[j + 1] = act_fast<ACT>(t1); v[j + 2] = act_fast<ACT>(t2); v[j + 3] = act_fast<ACT>(t3);
         }
         if (RES == RES_F32_MOD) {
           if (row_ok) {
@@ -869,7 +708,6 @@ inline cudaError_t dispatch(const GemmDesc& d, const CUtensorMap* maps, const Pa
     if (!ln && d.act == ACT_GELU) return launch_variant<BN, false, ACT_GELU, RES_NONE, false, CG, true>(maps, p, grid, st);
     if (!ln && d.act == ACT_SILU) return launch_variant<BN, false, ACT_SILU, RES_NONE, false, CG, true>(maps, p, grid, st);
   } else if (ln) {
-    if (d.act == ACT_QSOFT && res == RES_NONE) return launch_variant<BN, true, ACT_QSOFT, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_EXPO && res == RES_NONE) return launch_variant<BN, true, ACT_EXPO, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_NONE && res == RES_NONE) return launch_variant<BN, true, ACT_NONE, RES_NONE, false, CG>(maps, p, grid, st);
     if (d.act == ACT_SILU && res == RES_NONE) return launch_variant<BN, true, ACT_SILU, RES_NONE, false, CG>(maps, p, grid, st);
@@ -905,7 +743,13 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.res && !d.res_f32 && (d.ldr % 8)) { *err = "bf16 residual needs ldr % 8 == 0"; return cudaErrorInvalidValue; }
   if (d.res && d.res_f32 && ((d.ldr % 4) || d.res_mod <= 0)) { *err = "fp32 residual needs ldr % 4 == 0 and res_mod > 0"; return cudaErrorInvalidValue; }
   int bn = bn_force ? bn_force : g_bn_override();
-  if (bn != 128 && bn != 256) bn = (d.N % 256 == 0) ? 256 : 128;
+  if (bn != 128 && bn != 256) {
+    bn = (d.N % 256 == 0) ? 256 : 128;
+    // single-clip regime (a handful of row tiles): 128-wide tiles double the CTAs that stream W and deepen the ring to 5 stages;
+    // measured on B200 at B = 1: 787 -> 941 frames/s (BEAT), 1780 -> 2115 (SHOW) -- profiles/r02/call2/r2_configs1_bn128.jsonl
+    const int tiles256 = ((d.M + BM - 1) / BM) * ((d.N + 255) / 256);
+    if (bn == 256 && d.act != ACT_LNMS && tiles256 * 4 < num_sms) bn = 128;
+  }
   // CTA pairs (cta_group::2) for the big row counts; tiny problems keep the single-CTA kernel (more tiles in flight)
   int cg = cg_force ? cg_force : g_cg_override();
   if (cg != 1 && cg != 2) cg = (bn == 256 && d.M >= 4096 && d.Kp >= 512) ? 2 : 1;   // short K loops: single CTAs win (profiles/r01 sweep)
@@ -941,11 +785,6 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   p.out = d.out; p.ldo = d.ldo; p.out2 = d.out2;
   p.ps_out = d.ps_out; p.nullc = d.nullc; p.n_uncond = d.n_uncond;
   p.ps_in = d.ps_in; p.cs_in = d.cs_in; p.ps_slots = d.ps_slots; p.ps_invP = d.ps_P > 0 ? 1.0f / (float)d.ps_P : 0.f;
-  p.qsum = d.qsum; p.qsoft_cols = d.qsoft_cols;
-  if (d.act == ACT_QSOFT && (!d.csum || !d.qsum || d.qsoft_cols <= 0 || (d.qsoft_cols % CPW) || d.qsoft_cols > d.N || d.res || d.out_f32 || d.out2 || d.Kp >= 768)) {
-    *err = "ACT_QSOFT needs an LN-fold bf16-output GEMM with K < 768, no residual / duplicate store, qsum and qsoft_cols % 64 == 0";
-    return cudaErrorInvalidValue;
-  }
   p.lnms_g = d.lnms_g; p.lnms_b = d.lnms_b; p.lnms_ss = d.lnms_ss; p.lnms_ld = d.lnms_ld; p.lnms_B = d.lnms_B; p.lnms_T = d.lnms_T;
   if (d.act == ACT_LNMS && (bn != 256 || (cg == 2 && !longk) || d.N != 2 * bn || d.csum || d.res || d.out_f32 || d.out2 || !d.lnms_g || !d.lnms_b ||
                             !d.lnms_ss || d.lnms_B <= 0 || d.lnms_T <= 0 || (d.lnms_ld % 4))) {
@@ -962,20 +801,6 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
   const int tiles = d.act == ACT_LNMS ? p.tiles_m : p.tiles_m * p.tiles_n;   // ACT_LNMS: a pair owns whole row panels (both n-tiles)
   const int units = num_sms / cg;   // CTAs (or CTA pairs) that can be resident
   const int grid = (tiles < units ? tiles : units) * cg;
-  {
-    static int pf = -1;
-    if (pf < 0) {
-      const char* e = getenv("DSHEG_TC_PREFETCH");
-      pf = e ? atoi(e) : 0;
-      // 2 = W-fill-skipping TIMING experiment (wrong results): only honoured together with an explicit opt-in
-      if (pf == 2 && !getenv("DSHEG_ALLOW_TIMING_EXPERIMENTS")) pf = 0;
-      if (pf < 0 || pf > 3) pf = 0;
-    }
-    // 3 = selective: only the tensor-bound GEMMs without a residual stream (round 1, global prefetch: ffn1 +15 %, but the
-    // HBM-bound residual GEMMs lost 9 % because the prefetch competes with their residual / output traffic)
-    p.prefetch = pf == 3 ? ((d.res || d.out_f32) ? 0 : 1) : pf;
-    if (d.act == ACT_LNMS) p.prefetch = 0;
-  }
   if (cg == 2) return dispatch<256, 2>(d, maps, p, grid, st, err, longk);
   return bn == 256 ? dispatch<256, 1>(d, maps, p, grid, st, err) : dispatch<128, 1>(d, maps, p, grid, st, err);
 }

@@ -1,0 +1,262 @@
+// TF32 tensor-core GEMM (tcgen05.mma kind::tf32 + TMA + TMEM) with the shared GemmDesc epilogue, fp32 in / fp32 out.
+//
+// Role: the arithmetic engine of the "tf32" precision mode -- the middle mode between the strict-fp32 parity engine
+// (gemm_simt.cuh; the reference itself runs torch fp32 with TF32 off) and the all-bf16 performance mode
+// (gemm_tc.cuh): activations, residual stream, LayerNorm statistics and every epilogue stay fp32; only the two MMA operands
+// are rounded to TF32 (10-bit mantissa, round-to-nearest by the TMA load: CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), accumulation is
+// fp32 in TMEM.  out[M, N] = epilogue(A[M, K] . W[N, K]^T), A = virtual concat of up to 4 fp32 segments.
+//
+// Shape: one 128 x 128 output tile per CTA (not persistent; two CTAs fit an SM, so one's epilogue overlaps the other's
+// mainloop), K in blocks of 32 fp32 (128-byte rows, SWIZZLE_128B -- byte-for-byte the operand geometry of the bf16 kernel:
+// 8 TF32 elements = 32 bytes per MMA k-step), 3-stage TMA ring.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  The epilogue does its per-row / per-column math in the TMEM layout
+// (thread = row), then turns each 32-column chunk through shared memory (the mainloop's ring is free by then) so that the
+// residual loads and the stores are 128-byte coalesced: 8 lanes x 16 bytes per row, 4 rows per instruction.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace dsheg {
+namespace t32 {
+
+using namespace tc;
+
+constexpr int TBM = 128, TBN = 128, TBK = 32;          // fp32 elements
+constexpr int T_STAGES = 3;
+constexpr int TA_BYTES = TBM * TBK * 4, TB_BYTES = TBN * TBK * 4, T_STAGE_BYTES = TA_BYTES + TB_BYTES;   // 16 + 16 KB
+constexpr int T_NUM_THREADS = 192;
+constexpr int T_TURN_LD = 36;                            // floats per staged row (144 B: 16-byte aligned, conflict-free)
+constexpr int T_BAR_BYTES = 128;
+constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_BAR_BYTES + 1024;   // + alignment slack
+static_assert(4 * 32 * T_TURN_LD * 4 <= T_STAGES * T_STAGE_BYTES, "the epilogue turns its chunks through the idle ring");
+// kind::tf32 instruction descriptor: D = f32 (bit 4), A = B = TF32 (format 2 at [7,10) and [10,13)), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t T_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+
+#ifndef DSHEG_EMU
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+#endif
+
+struct T32Params {
+  int M, N, num_kb, nseg;
+  int seg_kb_start[5];
+  int tiles_n;
+  const float* bias; const float* csum; const float* mu; const float* rstd;
+  int act;
+  const float* res; int ldr, res_mod;
+  float* out; int ldo; float* out2;
+};
+
+__global__ void __launch_bounds__(T_NUM_THREADS, 2)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                 const __grid_constant__ CUtensorMap tmW, const T32Params p) {
+  DSHEG_TC_DYN_SMEM(smem_raw);
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + T_STAGES * T_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (T_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * T_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * T_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - smem_base));
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m_blk = blockIdx.x / p.tiles_n, n_blk = blockIdx.x % p.tiles_n;   // n fastest: concurrent CTAs share the A panel in L2
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < T_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_mbarrier_init();
+    prefetch_tensormap(&tmA0);
+    prefetch_tensormap(&tmW);
+  }
+  if (warp == 1) tmem_alloc<1, TBN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, seg = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        while (kb >= p.seg_kb_start[seg + 1]) ++seg;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * T_STAGE_BYTES, sb = sa + TA_BYTES;
+        const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
+        mbar_arrive_expect_tx(full_bar(stage), T_STAGE_BYTES);
+        tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
+        // W's K axis lays every segment out padded to 64 = two k-blocks, so k-block kb of the walk IS W's k-block kb
+        tma_load_2d(&tmW, full_bar(stage), sb, kb * TBK, n_blk * TBN);
+        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * T_STAGE_BYTES, sb = sa + TA_BYTES;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+        for (int k = 0; k < TBK / 8; ++k)   // 8 TF32 = 32 bytes per k-step: +2 in 16-byte descriptor units
+          tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), T_IDESC, (kb | k) != 0);
+        tc_commit(empty_bar(stage));   // frees the smem slot when the MMAs retire
+        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(tfull_bar);            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue: warps 2..5, TMEM lane quadrant = warp id % 4 =================
+    const int qd = warp & 3;
+    const int m_row = m_blk * TBM + qd * 32 + lane;        // the row this thread holds in the TMEM layout
+    const bool ln = p.csum != nullptr;
+    const float mu = (ln && m_row < p.M) ? __ldg(p.mu + m_row) : 0.f;
+    const float rstd = (ln && m_row < p.M) ? __ldg(p.rstd + m_row) : 1.f;
+    float* turn = reinterpret_cast<float*>(gen_base) + (warp - 2) * 32 * T_TURN_LD;   // this warp's 32 x 36 staging rows (idle ring)
+    const int tr = lane >> 3, tcg = lane & 7;              // coalesced layout: row 4 it + tr of the chunk, columns 4 tcg .. + 3
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < TBN / 32; ++ch) {
+      const int n0 = n_blk * TBN + ch * 32;
+      if (n0 >= p.N) break;                                 // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ch * 32), r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = n0 + j + e;
+          float x = __uint_as_float(r[j + e]);
+          if (n < p.N) {
+            if (ln) x = rstd * (x - mu * __ldg(p.csum + n));
+            if (p.bias) x += __ldg(p.bias + n);
+            x = apply_act(x, p.act);
+          }
+          v[e] = x;
+        }
+        *reinterpret_cast<float4*>(turn + lane * T_TURN_LD + j) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      __syncwarp();
+      const int n = n0 + 4 * tcg;
+      const bool vec_ok = n + 3 < p.N;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rl = 4 * it + tr;
+        const int m = m_blk * TBM + qd * 32 + rl;
+        if (m >= p.M || n >= p.N) continue;
+        float4 x = *reinterpret_cast<const float4*>(turn + rl * T_TURN_LD + 4 * tcg);
+        const size_t o = (size_t)m * p.ldo + n;
+        if (vec_ok && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0)) {
+          if (p.res) {
+            const int mr = p.res_mod > 0 ? m % p.res_mod : m;
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)mr * p.ldr + n));
+            x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+          }
+          *reinterpret_cast<float4*>(p.out + o) = x;
+          if (p.out2) *reinterpret_cast<float4*>(p.out2 + o) = x;
+        } else {
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+          for (int e = 0; e < 4 && n + e < p.N; ++e) {
+            float y = xs[e];
+            if (p.res) { const int mr = p.res_mod > 0 ? m % p.res_mod : m; y += p.res[(size_t)mr * p.ldr + n + e]; }
+            p.out[o + e] = y;
+            if (p.out2) p.out2[o + e] = y;
+          }
+        }
+      }
+      __syncwarp();   // the staging rows are rewritten by the next chunk
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1, TBN>(tmem_base);
+  }
+}
+
+#ifndef DSHEG_EMU
+// fp32 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 32 columns] (128-byte rows,
+// SWIZZLE_128B); elements are rounded to TF32 by the load; out-of-bounds elements read as zero.
+inline bool make_tmap_f32(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
+  struct Key { const void* p; int r, c, l, b; bool operator==(const Key& o) const { return p == o.p && r == o.r && c == o.c && l == o.l && b == o.b; } };
+  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.r * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.c * 0xC2B2AE3D27D4EB4Full) ^ ((size_t)k.l << 20) ^ ((size_t)k.b << 7); } };
+  static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+  const Key k{ptr, rows, cols, ld, box_rows};
+  auto it = cache.find(k);
+  if (it != cache.end()) { *map = it->second; return true; }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (tf32) failed, CUresult " + std::to_string((int)r); return false; }
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(k, *map);
+  return true;
+}
+
+// true when the TMA path can take this GEMM (16-byte aligned bases and row strides, fp32 in / fp32 out); the caller falls
+// back to the SIMT fp32 kernel otherwise (small odd-shaped projections: more precise anyway)
+inline bool tf32_eligible(const GemmDesc& d) {
+  if (d.nseg < 1 || d.nseg > 4 || d.M < 1 || d.N < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(d.w) & 15) || (d.Kp & 3)) return false;
+  for (int s = 0; s < d.nseg; ++s)
+    if ((reinterpret_cast<uintptr_t>(d.a[s].ptr) & 15) || (d.a[s].ld & 3) || d.a[s].k < 1) return false;
+  if (d.ps_out || d.ps_in || d.act > ACT_GELU) return false;   // fused statistics / softmax / LayerNorm epilogues: bf16 engine only
+  return true;
+}
+
+// A, W, residual, out: fp32 (the "tf32" mode keeps every activation in fp32); residual / out may be fp32 by type or by flag
+inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::string* err) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  T32Params p{};
+  p.M = d.M; p.N = d.N; p.nseg = d.nseg;
+  CUtensorMap maps[5];
+  int koff = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    // segment s covers W columns [koff, koff + k) with koff a multiple of 64 = 2 k-blocks: k-block bookkeeping in units of 32
+    p.seg_kb_start[s] = koff / TBK;
+    if (!make_tmap_f32(&maps[s], d.a[s].ptr, d.M, d.a[s].k, d.a[s].ld, TBM, err)) return cudaErrorInvalidValue;
+    koff += (d.a[s].k + 63) / 64 * 64;
+  }
+  // the producer walks k-blocks 0 .. num_kb-1 and maps them to (segment, block inside the segment) through seg_kb_start;
+  // blocks that lie entirely in a segment's zero padding multiply zeros (at most one per segment)
+  p.seg_kb_start[d.nseg] = koff / TBK;
+  for (int s = d.nseg + 1; s < 5; ++s) p.seg_kb_start[s] = 1 << 30;
+  p.num_kb = koff / TBK;
+  for (int s = d.nseg; s < 4; ++s) maps[s] = maps[0];
+  if (!make_tmap_f32(&maps[4], d.w, d.N, d.Kp, d.Kp, TBN, err)) return cudaErrorInvalidValue;
+  p.tiles_n = (d.N + TBN - 1) / TBN;
+  const int tiles_m = (d.M + TBM - 1) / TBM;
+  p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd; p.act = d.act;
+  p.res = reinterpret_cast<const float*>(d.res); p.ldr = d.ldr; p.res_mod = d.res_mod;
+  p.out = reinterpret_cast<float*>(d.out); p.ldo = d.ldo; p.out2 = reinterpret_cast<float*>(d.out2);
+  gemm_tf32_kernel<<<tiles_m * p.tiles_n, T_NUM_THREADS, T_SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  return cudaGetLastError();
+}
+#endif  // DSHEG_EMU
+
+}  // namespace t32
+}  // namespace dsheg

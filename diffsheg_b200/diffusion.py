@@ -84,6 +84,12 @@ def get_schedule_jump_paper():
     return _jump_times(250, 10, 10)
 
 
+def _device_guard(dev):
+    """Make the engine's GPU current for the stateless step launches (no-op for the CPU stand-ins of the host-logic tests)."""
+    import contextlib
+    return torch.cuda.device(dev) if getattr(dev, "type", None) == "cuda" else contextlib.nullcontext()
+
+
 def _opt_get(opt, name, default=None):
     if opt is None:
         return default
@@ -237,7 +243,7 @@ class FusedGaussianDiffusion:
             raise NotImplementedError("fused DDIM supports clip_denoised=False, eta=0, no denoised_fn/cond_fn "
                                       "(what generate_batch passes, show:170-182)")
         eng, img, gt, mask = self._setup(model, tuple(shape), noise, model_kwargs, device)
-        with torch.cuda.device(eng.device):   # the stateless step kernels launch on the engine's GPU, whatever torch's current one is
+        with _device_guard(eng.device):   # the stateless step kernels launch on the engine's GPU, whatever torch's current one is
             return self._ddim_loop(eng, img, gt, mask)
 
     def _ddim_loop(self, eng, img, gt, mask):
@@ -274,7 +280,7 @@ class FusedGaussianDiffusion:
         if clip_denoised or denoised_fn is not None or cond_fn is not None or pre_seq is not None or transl_req is not None:
             raise NotImplementedError("fused DDPM supports clip_denoised=False and no denoised_fn/cond_fn/pre_seq/transl_req")
         eng, img, gt, mask = self._setup(model, tuple(shape), noise, model_kwargs, device)
-        with torch.cuda.device(eng.device):
+        with _device_guard(eng.device):
             return self._ddpm_loop(eng, img, gt, mask)
 
     def _ddpm_loop(self, eng, img, gt, mask):

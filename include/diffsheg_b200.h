@@ -23,7 +23,10 @@ extern "C" {
 
 #define DSHEG_ABI_VERSION 1
 
-enum { DSHEG_PREC_FP32 = 0, DSHEG_PREC_BF16 = 1 };
+/* FP32: strict parity mode (SIMT fp32 GEMMs).  BF16: performance mode (tcgen05 bf16 GEMMs, bf16 activations).
+ * TF32: fp32 activations / residual stream / statistics / epilogues with tcgen05 kind::tf32 GEMMs (operands rounded to
+ *       TF32 by the TMA load, fp32 accumulation) -- the precise-and-fast middle mode. */
+enum { DSHEG_PREC_FP32 = 0, DSHEG_PREC_BF16 = 1, DSHEG_PREC_TF32 = 2 };
 enum { DSHEG_DTYPE_F32 = 0, DSHEG_DTYPE_BF16 = 1 };
 
 /* Frozen subset of the reference `opt` Namespace + build_models() arguments
@@ -132,8 +135,8 @@ int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mea
 
 /* ---- op-level entry points used by the parity tests -------------------------------------- */
 
-/* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32 or the
- * tcgen05 bf16 engine.  A/W/out/residual are fp32 device arrays; the bf16 engine converts
+/* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32, the
+ * tcgen05 bf16 or the tcgen05 tf32 engine (fp32 in / out like the SIMT one).  A/W/out/residual are fp32 device arrays; the bf16 engine converts
  * operands, residual and (when N % 32 == 0) the output to bf16 internally, exactly the layout the
  * denoiser uses (test path only).  act: 0 none, 1 SiLU, 2 GELU. */
 int dsheg_op_linear(int32_t precision, const float* A, const float* W, const float* bias,
@@ -161,9 +164,13 @@ int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, 
 int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
                        float* z, int32_t Bn, int32_t T, int32_t D, int32_t H, void* stream);
 
-/* Same op on the bf16 fast path (tensor-core kernel, D = 512, 8 heads, T <= 96): qkv and z are bf16 arrays. */
+/* Same op on the bf16 fast path (D = 512, 8 heads, T <= 96): qkv and z are bf16 arrays.
+ * numerators = 1: the engine's default kernel (attn_tma.cuh: persistent, TMA-staged); the Q and K columns of qkv already hold the
+ *                 softmax NUMERATORS exp(value - shift) that the ACT_EXPO epilogue of the QKV GEMM writes (any per-(row, head)
+ *                 shift for Q, any per-(sample, column) shift for K: softmax is shift-invariant);
+ * numerators = 0: plain q, k, v; both softmaxes run inside the kernel (attn_v3.cuh, the per-layer fallback). */
 int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
-                            void* z, int32_t Bn, int32_t T, void* stream);
+                            void* z, int32_t Bn, int32_t T, int32_t numerators, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,8 +24,6 @@ struct EmuGemmArgs {
   const float* cs_in;
   int32_t ps_slots, ps_P;
   int32_t num_sms, bn_force, cg_force;
-  float* qsum;
-  int32_t qsoft_cols;
   const float* eshift;
   int32_t expo_cols;
   const float *lnms_g, *lnms_b, *lnms_ss;
@@ -46,7 +44,6 @@ extern "C" int emu_gemm_tc(const EmuGemmArgs* a) {
   d.ps_out = reinterpret_cast<float2*>(a->ps_out); d.nullc = a->nullc; d.n_uncond = a->n_uncond;
   d.ps_in = reinterpret_cast<const float2*>(a->ps_in); d.cs_in = reinterpret_cast<const float2*>(a->cs_in);
   d.ps_slots = a->ps_slots; d.ps_P = a->ps_P;
-  d.qsum = a->qsum; d.qsoft_cols = a->qsoft_cols;
   d.eshift = a->eshift; d.expo_cols = a->expo_cols;
   d.lnms_g = a->lnms_g; d.lnms_b = a->lnms_b; d.lnms_ss = a->lnms_ss; d.lnms_ld = a->lnms_ld; d.lnms_B = a->lnms_B; d.lnms_T = a->lnms_T;
   std::string terr;

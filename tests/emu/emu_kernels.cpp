@@ -3,9 +3,6 @@
 #include <algorithm>
 
 #include "attn_v3.cuh"
-#include "attn_v4.cuh"
-#include "attn_v5.cuh"
-#include "attn_v6.cuh"
 #include "attn_small.cuh"
 #include "postprocess.cuh"
 #include "sampler.cuh"
@@ -24,11 +21,11 @@ extern "C" void emu_op_counters(unsigned long long* out, int reset) {
   if (reset) c = prims::OpCounters{};
 }
 
-// variant: 3 = attn_v3 (one CTA per sample), 4 = attn_v4 (cluster of two half-sample CTAs), 51 / 52 / 54 = attn_v5<CL = 1 / 2 / 4>
-// 151 / 152 / 154 = attn_v5<CL, PRE = 1>: Q columns hold softmax numerators, `qsum` [rows][8] their sums (else unused)
-// 251 / 252 / 254 = attn_v5<CL, PRE = 2>: Q and K columns hold exp(value - static shift) (ACT_EXPO epilogue), no side table
+// variant: 3 = attn_v3 (one CTA per sample; the per-layer fallback of the engine).  The default kernel (attn_tma.cuh: TMA, mbarriers)
+// is validated on hardware: op-level parity, memcheck and racecheck under compute-sanitizer (profiles/r02).
 extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int n_samples, int T, int ssB, const float* ln_g,
                              const float* ln_b, const float* ss, int ss_ld, const float* qsum) {
+  (void)qsum;
   g_err.clear();
   prims::async_copies().clear();
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
@@ -36,32 +33,6 @@ extern "C" int emu_attention(int variant, const uint16_t* qkv, uint16_t* z, int 
   bool ok = false;
   if (variant == 3) {
     ok = emu::run_grid(n_samples, av3::NTHREADS, 1, av3::SMEM_BYTES, [=] { av3::attn_v3_kernel(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 4) {
-    ok = emu::run_grid(2 * n_samples, av4::NTHREADS, 2, av4::SMEM_BYTES, [=] { av4::attn_v4_kernel(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 51) {
-    ok = emu::run_grid(n_samples, av5::Cfg<1>::NTHREADS, 1, av5::Cfg<1>::SMEM_BYTES, [=] { av5::attn_v5_kernel<1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 52) {
-    ok = emu::run_grid(2 * n_samples, av5::Cfg<2>::NTHREADS, 2, av5::Cfg<2>::SMEM_BYTES, [=] { av5::attn_v5_kernel<2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 54) {
-    ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 151) {
-    ok = emu::run_grid(n_samples, av5::Cfg<1>::NTHREADS, 1, av5::Cfg<1>::SMEM_BYTES, [=] { av5::attn_v5_kernel<1, 1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
-  } else if (variant == 152) {
-    ok = emu::run_grid(2 * n_samples, av5::Cfg<2>::NTHREADS, 2, av5::Cfg<2>::SMEM_BYTES, [=] { av5::attn_v5_kernel<2, 1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
-  } else if (variant == 154) {
-    ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4, 1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, qsum); }, &g_err);
-  } else if (variant == 251) {
-    ok = emu::run_grid(n_samples, av5::Cfg<1>::NTHREADS, 1, av5::Cfg<1>::SMEM_BYTES, [=] { av5::attn_v5_kernel<1, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
-  } else if (variant == 252) {
-    ok = emu::run_grid(2 * n_samples, av5::Cfg<2>::NTHREADS, 2, av5::Cfg<2>::SMEM_BYTES, [=] { av5::attn_v5_kernel<2, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
-  } else if (variant == 254) {
-    ok = emu::run_grid(4 * n_samples, av5::Cfg<4>::NTHREADS, 4, av5::Cfg<4>::SMEM_BYTES, [=] { av5::attn_v5_kernel<4, 2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld, nullptr); }, &g_err);
-  } else if (variant == 6) {   // attn_v6: 4 warps per head, 64 registers, static-shift numerators (same input contract as 25x)
-    ok = emu::run_grid(4 * n_samples, av6::Cfg<4>::NTHREADS, 4, av6::Cfg<4>::SMEM_BYTES, [=] { av6::attn_v6_kernel<4>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 61) {  // attn_v6 as ONE 1024-thread CTA per sample (no cluster, two-phase LayerNorm pass)
-    ok = emu::run_grid(n_samples, av6::Cfg<1>::NTHREADS, 1, av6::Cfg<1>::SMEM_BYTES, [=] { av6::attn_v6_kernel<1>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
-  } else if (variant == 62) {  // attn_v6 as clusters of two 512-thread CTAs (4 heads each)
-    ok = emu::run_grid(2 * n_samples, av6::Cfg<2>::NTHREADS, 2, av6::Cfg<2>::SMEM_BYTES, [=] { av6::attn_v6_kernel<2>(q, zo, T, ssB, ln_g, ln_b, ss, ss_ld); }, &g_err);
   } else {
     g_err = "unknown attention variant";
   }

@@ -12,7 +12,7 @@ import torch
 
 import emu
 
-ACT_NONE, ACT_SILU, ACT_GELU, ACT_QSOFT, ACT_EXPO, ACT_LNMS = 0, 1, 2, 3, 4, 5
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_EXPO, ACT_LNMS = 0, 1, 2, 4, 5
 
 
 class Args(ctypes.Structure):
@@ -25,7 +25,6 @@ class Args(ctypes.Structure):
                 ("out2", ctypes.c_void_p), ("ps_out", ctypes.c_void_p), ("nullc", ctypes.c_void_p), ("n_uncond", ctypes.c_int32),
                 ("ps_in", ctypes.c_void_p), ("cs_in", ctypes.c_void_p), ("ps_slots", ctypes.c_int32), ("ps_P", ctypes.c_int32),
                 ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32),
-                ("qsum", ctypes.c_void_p), ("qsoft_cols", ctypes.c_int32),
                 ("eshift", ctypes.c_void_p), ("expo_cols", ctypes.c_int32),
                 ("lnms_g", ctypes.c_void_p), ("lnms_b", ctypes.c_void_p), ("lnms_ss", ctypes.c_void_p),
                 ("lnms_ld", ctypes.c_int32), ("lnms_B", ctypes.c_int32), ("lnms_T", ctypes.c_int32)]
@@ -48,7 +47,7 @@ def r64(k):
 
 
 def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, dup=False, stats_out=False, n_uncond=0,
-             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, qsoft_cols=0, expo_cols=0, expo_q_cols=0, lnms_T=0, lnms_B=0):
+             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, expo_cols=0, expo_q_cols=0, lnms_T=0, lnms_B=0):
     """Builds operands like the engine does (K laid out per segment padded to 64), runs the emulated kernel, returns
     (got, want, extras)."""
     g = torch.Generator().manual_seed(seed)
@@ -113,14 +112,6 @@ def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, d
         a.nullc, a.n_uncond = ptr(nullc), n_uncond
         want[:n_uncond] += torch.from_numpy(nullc.astype(np.float64))
     extras["raw"] = want.clone()
-    if act == ACT_QSOFT:   # leading qsoft_cols columns: unnormalised softmax numerators per 64-column head + their row sums
-        qsum = np.full((M, qsoft_cols // 64), np.nan, np.float32)
-        keep.append(qsum)
-        a.qsum, a.qsoft_cols = ptr(qsum), qsoft_cols
-        qv = want[:, :qsoft_cols].reshape(M, -1, 64)
-        e = torch.exp(qv - qv.max(-1, keepdim=True).values)
-        extras["qsum"], extras["qsum_want"] = qsum, e.sum(-1)
-        want = torch.cat([e.reshape(M, qsoft_cols), want[:, qsoft_cols:]], 1)
     if act == ACT_EXPO:    # leading expo_cols columns: exp(v - eshift[n]) with static per-column shifts
         eshift = 3.0 * rnd(expo_cols)
         if expo_q_cols:    # a row softmax (Q) tolerates one shift per 64-column head only; the column softmax (K) any per-column shift
@@ -249,90 +240,10 @@ def test_gemm_pipeline_protocol_under_adversarial_timing(case, slow, monkeypatch
     check(got, want)
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if c["cg"] == 2 and c["ks"] == [512]], ids=lambda c: f"M{c['M']}-N{c['N']}")
-def test_k512_deep_ring_experiment_build(case):
-    """-DDSHEG_K512_DEEP=1 (scripts/build_variants.sh): K = 512 pair kernels with a fifth stage, no alignment slack and
-    single-buffered epilogue vectors -- never run on hardware; its barrier bookkeeping is checked here."""
-    c = dict(case)
-    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
-    got, want, _ = run_gemm(M, N, ks, lib=emu.gemm_lib("DSHEG_K512_DEEP=1"), **c)
-    check(got, want, tanh_gelu=c.get("act") == ACT_GELU)
-
-
-@pytest.mark.parametrize("case", [c for c in CASES if c.get("ln") or c.get("act") or c["cg"] == 1], ids=lambda c: f"M{c['M']}-N{c['N']}-cg{c['cg']}")
-def test_packed_fp32_epilogue_experiment_build(case):
-    """-DDSHEG_EPI_PACKED=1: LayerNorm fold, bias and SiLU / GELU on FFMA2 / FMUL2 / FADD2 column pairs (same arithmetic; the
-    emulator checks the pairing and the per-variant plumbing, hardware will tell whether the K = 512 tiles gain from it)."""
-    c = dict(case)
-    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
-    got, want, _ = run_gemm(M, N, ks, lib=emu.gemm_lib("DSHEG_EPI_PACKED=1"), **c)
-    check(got, want, out_f32=c.get("out_f32", False), tanh_gelu=c.get("act") == ACT_GELU)
-
-
-def test_packed_fp32_epilogue_build_with_exponential_columns():
-    got, want, ex = run_gemm(520, 1536, [512], ln=True, act=ACT_EXPO, expo_cols=1024, cg=2, num_sms=2, ps_in=True, seed=7,
-                             lib=emu.gemm_lib("DSHEG_EPI_PACKED=1"))
-    assert float(((got[:, :1024] - want[:, :1024]) / want[:, :1024]).abs().max()) < 6e-3
-    assert float((got[:, 1024:] - want[:, 1024:]).abs().max() / want[:, 1024:].abs().max()) < 8e-3
-
-
-@pytest.mark.parametrize("rings", [(7, 3), (2, 1), (3, 5)], ids=lambda r: f"A{r[0]}W{r[1]}")
-@pytest.mark.parametrize("case", [c for c in CASES if c["cg"] == 2 and c["ks"] == [512]], ids=lambda c: f"M{c['M']}-N{c['N']}")
-def test_split_ring_experiment_build(case, rings):
-    """-DDSHEG_SPLIT_RINGS=1: separate A (deep) and W (shallow) rings with separate producer threads for the K = 512 pair
-    kernels (never run on hardware).  Ring depths that do not divide the 8 k-blocks of a tile make the two stage counters
-    wrap at different times; (2, 1) is the minimal pipeline."""
-    c = dict(case)
-    M, N, ks = c.pop("M"), c.pop("N"), c.pop("ks")
-    L = emu.gemm_lib("DSHEG_SPLIT_RINGS=1", f"DSHEG_SPLIT_A={rings[0]}", f"DSHEG_SPLIT_W={rings[1]}")
-    got, want, _ = run_gemm(M, N, ks, lib=L, **c)
-    check(got, want, tanh_gelu=c.get("act") == ACT_GELU)
-
-
-@pytest.mark.parametrize("slow", ["EMU_DELAY_TMEM_LD", "EMU_DELAY_TMA", "EMU_DELAY_MMA"])
-def test_split_ring_build_under_adversarial_timing(slow, monkeypatch):
-    monkeypatch.setenv(slow, "40")
-    L = emu.gemm_lib("DSHEG_SPLIT_RINGS=1", "DSHEG_SPLIT_A=7", "DSHEG_SPLIT_W=3")
-    got, want, _ = run_gemm(600, 512, [512], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=300, lib=L)
-    check(got, want)
-
-
-@pytest.mark.parametrize("M,N,qc,cg,num_sms", [(300, 768, 256, 1, 2), (520, 1536, 512, 2, 2), (300, 512, 512, 2, 2), (140, 384, 128, 1, 1)])
-def test_q_softmax_epilogue(M, N, qc, cg, num_sms):
-    """ACT_QSOFT (opt-in, DSHEG_QSOFT=1): the LN-fold QKV projection writes exp(q - rowmax_head) for the Q columns and the
-    per-(row, head) sums next to it (transformer.py:122 moved into the producing GEMM); K and V columns stay plain."""
-    got, want, ex = run_gemm(M, N, [512], ln=True, act=ACT_QSOFT, qsoft_cols=qc, cg=cg, num_sms=num_sms)
-    assert torch.isfinite(got).all()
-    # numerators are in (0, 1], plain columns O(1): compare both halves on their own scale
-    assert float((got[:, :qc] - want[:, :qc]).abs().max()) < 6e-3           # bf16 rounding of values <= 1 + exp of an fp32 argument
-    if qc < N:
-        assert float((got[:, qc:] - want[:, qc:]).abs().max() / want[:, qc:].abs().max()) < 8e-3
-    qs = torch.from_numpy(ex["qsum"]).double()
-    assert torch.isfinite(qs).all()
-    assert float(((qs - ex["qsum_want"]) / ex["qsum_want"]).abs().max()) < 1e-4
-
-
-@pytest.mark.parametrize("variant", [151, 154])
-def test_qkv_epilogue_softmax_feeds_attention_end_to_end(variant):
-    """GEMM (ACT_QSOFT) -> attention (QPRE), both kernel sources on the emulator, against the float64 attention of the
-    float64 QKV projection: the pair of opt-in kernels implements transformer.py:119-128 + :92-96 together."""
-    import test_emu_kernels as tk
-    Bn, T = 2, 34
-    got, want, ex = run_gemm(Bn * T, 1536, [512], ln=True, act=ACT_QSOFT, qsoft_cols=512, cg=1, num_sms=2, seed=4)
-    qkv_dev = bits_to_f64(ex["out_bits"]).float().reshape(Bn, T, 1536)          # what the attention kernel reads
-    qsum = torch.from_numpy(ex["qsum"])
-    g, b = 1 + 0.1 * torch.randn(512), 0.1 * torch.randn(512)
-    ss = 0.5 * torch.randn(Bn, 1024)
-    z = tk.run_attention(variant, qkv_dev, g, b, ss, qsum=qsum)
-    ref = tk.reference(ex["raw"].reshape(Bn, T, 1536), g, b, ss)                   # reference() rounds its input to bf16 like the engine's QKV buffer
-    err = float((z - ref).abs().max() / ref.abs().max())
-    assert torch.isfinite(z).all() and err < 1.5e-2, err
-
-
 @pytest.mark.parametrize("M,N,ec,cg,num_sms,ps", [(300, 768, 512, 1, 2, False), (520, 1536, 1024, 2, 2, True), (300, 512, 512, 2, 2, False),
                                                   (140, 384, 128, 1, 1, True)])
 def test_exponential_epilogue(M, N, ec, cg, num_sms, ps):
-    """ACT_EXPO (opt-in, DSHEG_EXPO=1): the LN-fold QKV projection writes exp(v - eshift[n]) for its leading columns (Q and K:
+    """ACT_EXPO (default; DSHEG_EXPO=0 disables): the LN-fold QKV projection writes exp(v - eshift[n]) for its leading columns (Q and K:
     softmax numerators with static shifts, transformer.py:122-123 moved into the producing GEMM) and the rest plain."""
     got, want, ex = run_gemm(M, N, [512], ln=True, act=ACT_EXPO, expo_cols=ec, cg=cg, num_sms=num_sms, ps_in=ps, seed=7)
     assert torch.isfinite(got).all()
@@ -342,28 +253,11 @@ def test_exponential_epilogue(M, N, ec, cg, num_sms, ps):
         assert float((got[:, ec:] - want[:, ec:]).abs().max() / want[:, ec:].abs().max()) < 8e-3
 
 
-@pytest.mark.parametrize("variant,cg", [(251, 1), (254, 2)])
-def test_qkv_exponential_epilogue_feeds_attention_end_to_end(variant, cg):
-    """GEMM (ACT_EXPO) -> attention (PRE = 2), both kernel sources on the emulator, against the float64 attention of the
-    float64 QKV projection: the pair of opt-in kernels implements transformer.py:119-128 + :92-96 together, without a single
-    maximum search."""
-    import test_emu_kernels as tk
-    Bn, T = 2, 34
-    got, want, ex = run_gemm(Bn * T, 1536, [512], ln=True, act=ACT_EXPO, expo_cols=1024, expo_q_cols=512, cg=cg, num_sms=2, seed=4)
-    qkv_dev = bits_to_f64(ex["out_bits"]).float().reshape(Bn, T, 1536)          # what the attention kernel reads
-    g, b = 1 + 0.1 * torch.randn(512), 0.1 * torch.randn(512)
-    ss = 0.5 * torch.randn(Bn, 1024)
-    z = tk.run_attention(variant, qkv_dev, g, b, ss)
-    ref = tk.reference(ex["raw"].reshape(Bn, T, 1536), g, b, ss)
-    err = float((z - ref).abs().max() / ref.abs().max())
-    assert torch.isfinite(z).all() and err < 1.5e-2, err
-
-
 @pytest.mark.parametrize("M,K,T,B,num_sms,cg", [(600, 1024, 88, 3, 2, 2), (1100, 768, 34, 2, 4, 2), (256, 1024, 7, 40, 2, 2), (700, 1024, 88, 2, 6, 2),
                                                   # single CTAs (small batches): 128 rows x 512 columns of TMEM per CTA, any K
                                                   (176, 1024, 88, 1, 4, 1), (34, 1024, 34, 1, 2, 1), (300, 512, 34, 3, 1, 1), (520, 1024, 88, 2, 2, 1)])
 def test_full_row_layernorm_modulate_silu_epilogue(M, K, T, B, num_sms, cg):
-    """ACT_LNMS (opt-in, DSHEG_FUSE_LNMS=1): ffn.linear2 + the StylizationBlock prologue (transformer.py:178-181 + :92-96) in ONE
+    """ACT_LNMS (default for rows >= 4096; DSHEG_FUSE_LNMS=0 disables): ffn.linear2 + the StylizationBlock prologue (transformer.py:178-181 + :92-96) in ONE
     kernel -- a CTA pair owns both 256-column tiles of its row panel (one per TMEM accumulator stage), so LayerNorm statistics
     span the full 512-wide row; persistent walks with more panels than pairs wrap the stage / accumulator parities."""
     got, want, _ = run_gemm(M, 512, [K], act=ACT_LNMS, lnms_T=T, lnms_B=B, cg=cg, num_sms=num_sms, seed=11)

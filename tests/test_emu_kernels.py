@@ -55,7 +55,7 @@ def _case(Bn, T, nb=None, seed=0):
     return qkv, g, b, ss
 
 
-VARIANTS = [3, 4, 51, 52, 54]   # attn_v3, attn_v4, attn_v5<CL = 1, 2, 4>
+VARIANTS = [3]   # attn_v3 (the engine's per-layer fallback); round 2's v4 / v5 / v6 experiments lost on hardware and are gone
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -69,64 +69,9 @@ def test_attention_kernel_source_on_emulator(variant, Bn, T, nb):
     assert err < 1e-2, err     # bf16 intermediates and output (the GPU test gates the same quantity at 3e-2)
 
 
-@pytest.mark.parametrize("T", [88, 34, 13])
-def test_cluster_variants_agree_with_their_single_cta_form(T):
-    """A cluster decomposition changes only WHERE the LayerNorm row statistics are reduced, not the arithmetic: v4 agrees
-    with v3, and v5<2>, v5<4> agree with v5<1>, to the last bf16 bit except where the split statistics round differently.
-    (v5 differs from v3 by design: its softmax denominators sum the bf16-rounded weights on the tensor core.)"""
-    qkv, g, b, ss = _case(2, T, None, seed=5)
-    for base_v, others in ((3, (4,)), (51, (52, 54))):
-        base = run_attention(base_v, qkv, g, b, ss)
-        for variant in others:
-            got = run_attention(variant, qkv, g, b, ss)
-            assert float((got - base).abs().max() / base.abs().max()) < 8e-3   # <= 1 bf16 ulp of the largest output
-            assert float((got != base).double().mean()) < 0.02
-
-
-@pytest.mark.parametrize("variant", [151, 152, 154])
-@pytest.mark.parametrize("Bn,T", [(2, 88), (1, 34), (1, 13)])
-def test_attention_with_q_softmax_done_by_the_gemm_epilogue(variant, Bn, T):
-    """QPRE: the Q columns arrive as unnormalised softmax numerators (bf16) with their fp32 row sums, as the QKV GEMM's
-    ACT_QSOFT epilogue writes them (tests/test_emu_gemm.py::test_q_softmax_epilogue); the result must equal the attention
-    of the ORIGINAL q."""
-    qkv, g, b, ss = _case(Bn, T, None, seed=3)
-    qkv = qkv.bfloat16().float()
-    want = reference(qkv, g, b, ss)
-    q = qkv[..., :512].double().view(Bn, T, 8, 64)
-    e = torch.exp(q - q.max(-1, keepdim=True).values)
-    pre = qkv.clone()
-    pre[..., :512] = e.reshape(Bn, T, 512).float()
-    got = run_attention(variant, pre, g, b, ss, qsum=e.sum(-1).reshape(Bn * T, 8))
-    assert torch.isfinite(got).all()
-    assert float((got - want).abs().max() / want.abs().max()) < 1e-2
-
-
-@pytest.mark.parametrize("variant", [251, 252, 254, 6, 62, 61])
-@pytest.mark.parametrize("Bn,T,spread", [(2, 88, 1.0), (1, 34, 12.0), (1, 13, 30.0), (1, 96, 3.0), (1, 16, 5.0), (2, 17, 5.0), (1, 7, 5.0)])
-def test_attention_with_both_softmax_numerators_done_by_the_gemm_epilogue(variant, Bn, T, spread):
-    """EXPO (PRE = 2): Q and K columns arrive as exp(value - static shift) in bf16 (ACT_EXPO epilogue), with shifts that are
-    NOT the maxima -- per (row, head) for Q, per (sample, column) for K, up to e^+-70 away from the values -- and no side table: both
-    denominators come out of the tensor core.  Softmax is shift-invariant, so the result must equal the attention of the
-    ORIGINAL q, k (reference() evaluates them in float64)."""
-    qkv, g, b, ss = _case(Bn, T, None, seed=5)
-    qkv = qkv.bfloat16().float()
-    want = reference(qkv, g, b, ss)
-    gen = torch.Generator().manual_seed(T)
-    q = qkv[..., :512].double().view(Bn, T, 8, 64)
-    k = qkv[..., 512:1024].double()
-    sq = (spread * torch.randn(Bn, T, 8, 1, generator=gen).double()).clamp(-64, 64)   # any per-(row, head) constant ...
-    sk = (spread * torch.randn(Bn, 1, 512, generator=gen).double()).clamp(-64, 64)    # ... / per-(sample, column) constant within the packer's proven range (|v - shift| <= 72)
-    pre = qkv.clone()
-    pre[..., :512] = torch.exp(q - sq).reshape(Bn, T, 512).float()
-    pre[..., 512:1024] = torch.exp(k - sk).float()
-    got = run_attention(variant, pre, g, b, ss)
-    assert torch.isfinite(got).all()
-    assert float((got - want).abs().max() / want.abs().max()) < 1e-2
-
-
 @pytest.mark.parametrize("Bn,T,nb", [(2, 88, None), (3, 34, 1), (1, 96, None), (2, 7, None), (1, 30, None)])
 def test_audio_layer_attention_all_heads_at_once(Bn, T, nb):
-    """attn_small.cuh (opt-in, DSHEG_ATTN_AUD=1): the encoder_aud attention (D = 128, 8 heads of 16) with all heads processed at once
+    """attn_small.cuh (default for the audio layer; DSHEG_ATTN_AUD=0 disables): the encoder_aud attention (D = 128, 8 heads of 16) with all heads processed at once
     instead of the generic head-by-head SIMT kernel; same fp64 reference as the 512-wide kernels, evaluated at D = 128."""
     torch.manual_seed(T)
     D = 128
@@ -147,19 +92,13 @@ def test_audio_layer_attention_all_heads_at_once(Bn, T, nb):
 
 
 @pytest.mark.parametrize("sched", ["reverse", "shuffle"])
-@pytest.mark.parametrize("variant", [3, 4, 51, 52, 54, 254, 6, 62, 61])
+@pytest.mark.parametrize("variant", [3])
 def test_attention_is_independent_of_the_thread_schedule(variant, sched, monkeypatch):
     """The emulator's stand-in for racecheck: the same launch under a reversed and under a per-pass shuffled thread order must
     reproduce the default order's output BIT FOR BIT -- a missing barrier between a producer and a consumer does not."""
     Bn, T = 2, 40
     qkv, g, b, ss = _case(Bn, T, None, seed=2)
     qkv = qkv.bfloat16().float()
-    if variant in (254, 6, 62, 61):   # static-shift numerators
-        q = qkv[..., :512].double().view(Bn, T, 8, 64)
-        pre = qkv.clone()
-        pre[..., :512] = torch.exp(q - 3.0).reshape(Bn, T, 512).float()
-        pre[..., 512:1024] = torch.exp(qkv[..., 512:1024].double() + 2.0).float()
-        qkv = pre
     base = run_attention(variant, qkv, g, b, ss)
     monkeypatch.setenv("EMU_SCHED", sched)
     got = run_attention(variant, qkv, g, b, ss)
@@ -197,25 +136,15 @@ def _op_counts(variant, qkv, g, b, ss, **kw):
 
 
 def test_dynamic_operation_counts_per_sample(capsys):
-    """What each attention generation EXECUTES per sample (T = 88) on the pipes that bound it -- MUFU, tensor, ldmatrix, cp.async --
-    counted by the emulator's primitives (ALU instructions are not counted: see the static SASS accounting in DESIGN 3.2).
-    Pins the claims of DESIGN 3.2: the static-shift variant issues no exponential at all and a third of v3's MUFU operations."""
+    """What attn_v3 EXECUTES per sample (T = 88) on the pipes that bound it, counted by the emulator's primitives."""
     Bn, T = 1, 88
     qkv, g, b, ss = _case(Bn, T, None, seed=1)
-    rows = {"v3": _op_counts(3, qkv, g, b, ss), "v5c1": _op_counts(51, qkv, g, b, ss), "v5c4": _op_counts(54, qkv, g, b, ss),
-            "v5c1+expo": _op_counts(251, qkv, g, b, ss), "v5c4+expo": _op_counts(254, qkv, g, b, ss),
-            "v6 (+expo)": _op_counts(6, qkv, g, b, ss), "v6c2 (+expo)": _op_counts(62, qkv, g, b, ss)}
+    c = _op_counts(3, qkv, g, b, ss)
     with capsys.disabled():
-        print("\n[emulator] warp-level operations per sample (T = 88): " + "  ".join(f"{k}" for k in next(iter(rows.values()))))
-        for name, c in rows.items():
-            print(f"[emulator] {name:12s} " + "  ".join(f"{v:9.0f}" for v in c.values()))
+        print("\n[emulator] attn_v3 warp-level operations per sample (T = 88): " + "  ".join(f"{k}={v:.0f}" for k, v in c.items()))
     elems = T * 512 / 32.0                               # one warp-wide op per 32 elements
-    assert rows["v3"]["ex2"] >= 2 * elems                 # exp of every q and k element
-    assert rows["v5c1+expo"]["ex2"] == 0 and rows["v5c4+expo"]["ex2"] == 0
-    assert rows["v5c1+expo"]["tanh"] <= 1.1 * elems       # SiLU only (rows are padded to the warp schedule)
-    mufu = lambda c: c["ex2"] + c["tanh"] + c["rcp"]
-    assert mufu(rows["v5c1+expo"]) < 0.45 * mufu(rows["v3"])
-    assert rows["v5c1"]["cp_async16"] == rows["v3"]["cp_async16"]      # same fill traffic: K and V tiles, 16 bytes per lane-op
+    assert c["ex2"] >= 2 * elems                         # exp of every q and k element
+    assert c["cp_async16"] == 2 * 8 * T * 8 / 32.0       # K and V tiles: 8 heads x T rows x 8 chunks of 16 bytes
 
 
 # ------------------------------------------------------------------------------------------------------------------------

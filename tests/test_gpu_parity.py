@@ -24,13 +24,18 @@ pytestmark = pytest.mark.gpu
 from parity_util import check as parity_check, fmt as parity_fmt, parity_metrics
 
 TOL = {"fp32": dict(call=dict(relmax=6e-6, per_channel=1e-5, rel_rms=5e-6), loop=dict(relmax=1e-4, per_channel=2e-4, rel_rms=1e-4)),
+       # tf32 mode (fp32 activations, TF32 tensor-core GEMMs): provisional gates until its first measurement lands in profiles/r02
+       "tf32": dict(call=dict(relmax=4e-3, per_channel=8e-3, rel_rms=4e-3), loop=dict(relmax=4e-3, per_channel=8e-3, rel_rms=4e-3)),
        "bf16": dict(call=dict(relmax=2.5e-2, per_channel=5e-2, rel_rms=2.2e-2), loop=dict(relmax=2e-2, per_channel=3e-2, rel_rms=1.6e-2))}
 
 
 def gate(got, want, prec, kind, what):
     m = parity_metrics(got, want)
     print(f"\n[parity] {what} {prec}: {parity_fmt(m)}")
-    parity_check(m, TOL[prec][kind], f"{what} {prec}")
+    tol = dict(TOL[prec][kind])
+    if want.numel() // want.shape[-1] < 32:
+        tol.pop("per_channel")   # a channel's own scale is not defined by a handful of frames (B x T = 7 in the smallest edge case)
+    parity_check(m, tol, f"{what} {prec}")
     return m
 
 
@@ -110,7 +115,7 @@ def test_undo_ddpm_merge(L):
 # ------------------------------------------------------------------------------------------------
 # op level
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
 @pytest.mark.parametrize("M,N,K,act,use_res", [(256, 512, 512, 0, True), (77, 103, 129, 0, False), (1000, 1536, 512, 2, False),
                                                (1, 384, 128, 0, False), (300, 1024, 1024, 1, False), (129, 128, 64, 0, True),
                                                (2000, 256, 256, 0, False), (517, 512, 1024, 0, True), (130, 16384, 2048, 0, False),
@@ -126,7 +131,9 @@ def test_op_linear(L, prec, M, N, K, act, use_res):
     bias = torch.randn(N, device="cuda")
     res = torch.randn(M, N, device="cuda") if use_res else None
     out = torch.full((M, N), float("nan"), device="cuda")
-    rc = L.dsheg_op_linear(0 if prec == "fp32" else 1, P(A), P(W), P(bias), P(res), P(out), M, N, K, act, S())
+    if prec == "tf32" and K % 4:
+        pytest.skip("the TMA path needs 16-byte aligned rows (the engine keeps such GEMMs on the fp32 SIMT kernel)")
+    rc = L.dsheg_op_linear({"fp32": 0, "bf16": 1, "tf32": 2}[prec], P(A), P(W), P(bias), P(res), P(out), M, N, K, act, S())
     assert rc == 0, L.dsheg_last_error(None)
     if prec == "bf16":
         A, W = A.bfloat16().float(), W.bfloat16().float()
@@ -143,6 +150,8 @@ def test_op_linear(L, prec, M, N, K, act, use_res):
     assert torch.isfinite(out).all()
     if prec == "fp32":
         assert err < 1e-5
+    elif prec == "tf32":
+        assert err < 1.5e-3   # operands rounded to 10-bit mantissas (2^-11 each), fp32 accumulation, exact epilogue
     else:
         assert err < (2e-5 if N % 32 else 6e-3)
 
@@ -165,29 +174,16 @@ def test_op_attention(L, Bn, T, D, H):
     assert relmax(z, want) < 2e-5
 
 
-def _attn_variants():
-    # v4 (cluster of two half-sample CTAs) and v5 (instruction diet, 1 / 2 / 4 CTAs per sample) were written after round 1's
-    # GPU budget was spent: they are validated on the CPU emulator (tests/test_emu_kernels.py) and stay opt-in on the GPU until
-    # their first hardware run (tests/test_zz_first_hw_run.py runs them in an isolated subprocess)
-    v = [None]
-    if os.environ.get("DSHEG_RUN_UNVALIDATED") == "1":
-        v += ["v4", "v5c1", "v5c2", "v5c4"]
-    return v
-
-
-@pytest.mark.parametrize("variant", _attn_variants())
 @pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (2, 84), (1, 30), (5, 96), (2, 16), (1, 7)])
-def test_op_attention_bf16_tensor_core(L, Bn, T, variant, monkeypatch):
-    """mma.sync attention kernel vs an fp64 evaluation of the same bf16 inputs (bf16 output rounding: 2^-8)."""
-    if variant:
-        monkeypatch.setenv("DSHEG_ATTN", variant)   # read by dsheg_op_attention_bf16 at call time
+def test_op_attention_bf16_tensor_core(L, Bn, T):
+    """attn_v3 (plain q, k, v: the per-layer fallback) vs an fp64 evaluation of the same bf16 inputs (bf16 output rounding: 2^-8)."""
     torch.manual_seed(T)
     D, H = 512, 8
     qkv = (1.5 * torch.randn(Bn, T, 3 * D, device="cuda")).bfloat16()
     g, b = 1 + 0.1 * torch.randn(D, device="cuda"), 0.1 * torch.randn(D, device="cuda")
     ss = 0.5 * torch.randn(Bn, 2 * D, device="cuda")
     z = torch.zeros(Bn, T, D, device="cuda", dtype=torch.bfloat16)
-    assert L.dsheg_op_attention_bf16(P(qkv), P(g), P(b), P(ss), P(z), Bn, T, S()) == 0, L.dsheg_last_error(None)
+    assert L.dsheg_op_attention_bf16(P(qkv), P(g), P(b), P(ss), P(z), Bn, T, 0, S()) == 0, L.dsheg_last_error(None)
     q, k, v = qkv.double().split(D, dim=-1)
     q = torch.softmax(q.view(Bn, T, H, -1), dim=-1)
     k = torch.softmax(k.view(Bn, T, H, -1), dim=1)
@@ -201,13 +197,7 @@ def test_op_attention_bf16_tensor_core(L, Bn, T, variant, monkeypatch):
     assert err < 3e-2
 
 
-# ---- fused epilogue modes written after round 1's GPU budget was spent: emulator-validated (tests/test_emu_gemm.py), opt-in on the
-#      GPU until their first hardware run (scripts/first_hw_run.py); the gate comes off together with the opt-in switches
-unvalidated = pytest.mark.skipif(os.environ.get("DSHEG_RUN_UNVALIDATED") != "1",
-                                 reason="first hardware run pending (DSHEG_RUN_UNVALIDATED=1 runs it)")
-
-
-@unvalidated
+# ---- fused epilogue modes of the tcgen05 engine (first hardware run: round 2, profiles/r02/call1)
 @pytest.mark.parametrize("M,N,ec", [(300, 768, 512), (4224, 1536, 1024), (5000, 512, 512), (140, 384, 128)])
 def test_op_linear_exponential_epilogue(L, M, N, ec):
     """ACT_EXPO: LN-fold projection whose leading columns leave as exp(v - static shift) (softmax numerators of tr:122-123)."""
@@ -233,7 +223,6 @@ def test_op_linear_exponential_epilogue(L, M, N, ec):
         assert relmax(out[:, ec:], want[:, ec:]) < 6e-3
 
 
-@unvalidated
 @pytest.mark.parametrize("M,K,T,B", [(4224, 1024, 88, 24), (5000, 768, 34, 7), (4096, 1024, 7, 600), (167200, 1024, 88, 950),
                                      # rows < 4096 / K < 768: single CTAs (128 rows x 512 TMEM columns each)
                                      (176, 1024, 88, 1), (34, 1024, 34, 1), (520, 512, 34, 3), (5000, 512, 88, 30)])
@@ -259,14 +248,11 @@ def test_op_linear_layernorm_modulate_silu_epilogue(L, M, K, T, B):
     assert torch.isfinite(out).all() and err < 6e-3
 
 
-@unvalidated
-@pytest.mark.parametrize("variant", ["v5c1", "v5c2", "v5c4", "v6", "v6c2", "v6c1", "tma"])
-@pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (1, 96), (2, 16), (1, 7), (301, 88), (150, 33)])
-def test_op_attention_with_static_shift_numerators(L, Bn, T, variant, monkeypatch):
-    """attn_v5<CL, 2> / attn_v6: the Q and K columns hold exp(value - shift) with shifts that are NOT the maxima (per (row, head) for Q, per
-    (sample, column) for K); the result must equal the attention of the original q, k."""
-    monkeypatch.setenv("DSHEG_ATTN", variant)
-    monkeypatch.setenv("DSHEG_EXPO", "1")
+@pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (1, 96), (2, 16), (1, 7), (301, 88), (150, 33), (1900, 88)])
+def test_op_attention_with_static_shift_numerators(L, Bn, T):
+    """attn_tma (the default kernel): the Q and K columns hold exp(value - shift) with shifts that are NOT the maxima (per (row, head)
+    for Q, per (sample, column) for K); the result must equal the attention of the original q, k.  Bn > 148: several samples per
+    persistent CTA (ring wrap-around, Q' / Y region hand-over); Bn = 1900: the headline launch."""
     torch.manual_seed(T)
     D, H = 512, 8
     qkv = (1.5 * torch.randn(Bn, T, 3 * D, device="cuda")).bfloat16()
@@ -279,7 +265,7 @@ def test_op_attention_with_static_shift_numerators(L, Bn, T, variant, monkeypatc
     pre[..., :D] = torch.exp(q.view(Bn, T, H, -1) - sq).reshape(Bn, T, D).bfloat16()
     pre[..., D:2 * D] = torch.exp(k - sk).bfloat16()
     z = torch.zeros(Bn, T, D, device="cuda", dtype=torch.bfloat16)
-    assert L.dsheg_op_attention_bf16(P(pre), P(g), P(b), P(ss), P(z), Bn, T, S()) == 0, L.dsheg_last_error(None)
+    assert L.dsheg_op_attention_bf16(P(pre), P(g), P(b), P(ss), P(z), Bn, T, 1, S()) == 0, L.dsheg_last_error(None)
     qs = torch.softmax(q.view(Bn, T, H, -1), dim=-1)
     ks = torch.softmax(k.view(Bn, T, H, -1), dim=1)
     att = torch.einsum("bnhd,bnhl->bhdl", ks, v.view(Bn, T, H, -1))
@@ -288,7 +274,7 @@ def test_op_attention_with_static_shift_numerators(L, Bn, T, variant, monkeypatc
     want = torch.nn.functional.silu(yn * (1 + ss[:, None, :D].double()) + ss[:, None, D:].double())
     torch.cuda.synchronize()
     err = relmax(z.float(), want)
-    print(f"\n[parity] attention {variant} static-shift numerators Bn{Bn} T{T}: relmax={err:.3e}")
+    print(f"\n[parity] attention (TMA, static-shift numerators) Bn{Bn} T{T}: relmax={err:.3e}")
     assert err < 3e-2
 
 
@@ -302,7 +288,7 @@ def _engine(name, prec, B, T, **cfg_over):
     return cfg, sd, FusedUniDiffuser(sd, cfg, precision=prec, max_batch=B, max_frames=T)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
 @pytest.mark.parametrize("name,B,T,t_resp", [("show", 2, 88, 12), ("show", 3, 84, 0),
                                               ("beat", 2, 34, 24), ("beat", 1, 30, 3)])
 def test_denoise_matches_reference_golden(golden_dir, prec, name, B, T, t_resp):
@@ -333,6 +319,29 @@ def test_denoise_matches_oracle_variants(prec):
         want = unidiffuser_forward(sd_c, cfg, inp["x_T"], ts, (torch.tensor(a, device="cuda"), torch.tensor(b, device="cuda")),
                                    inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float64)
     gate(got, want, prec, "call", "denoise show nocfg T40 vs fp64 oracle")
+
+
+@pytest.mark.parametrize("switch", ["DSHEG_EXPO=0", "DSHEG_ATTN=v3", "DSHEG_ATTN=v1", "DSHEG_FUSE_LNMS=0", "DSHEG_ATTN_AUD=0", "DSHEG_FUSE_STATS=0"])
+def test_denoise_bisecting_switches_keep_parity(golden_dir, switch, monkeypatch):
+    """Every default-on fusion has an off switch (read at dsheg_create) that routes through the kernel it replaced: plain QKV epilogue +
+    attn_v3 (also the per-layer fallback when the packer finds no provably safe softmax shifts), the generic attention kernel, the
+    separate ln_mod_silu pass, the generic audio-layer attention, separate LayerNorm statistics.  B = 50: rows >= 4096 (CTA pairs)."""
+    k, v = switch.split("=")
+    monkeypatch.setenv(k, v)
+    from oracle.denoiser import unidiffuser_forward
+    B, T = 50, 88
+    cfg, sd, eng = _engine("show", "bf16", B, T)
+    inp = {kk: vv.cuda() for kk, vv in synth.make_inputs(cfg, B, T, seed=5).items()}
+    eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+    a, b = 1.8, 1.5
+    got = eng.denoise(inp["x_T"], 480, a, b)
+    ts = torch.full((B,), 480, dtype=torch.long, device="cuda")
+    sd_c = {kk: vv.cuda() for kk, vv in sd.items()}
+    with torch.no_grad():
+        want = unidiffuser_forward(sd_c, cfg, inp["x_T"], ts, (torch.tensor(a, device="cuda"), torch.tensor(b, device="cuda")),
+                                   inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float32)
+    assert torch.isfinite(got).all()
+    gate(got, want, "bf16", "call", f"denoise show B{B} with {switch}")
 
 
 @pytest.mark.parametrize("prec,name,B,T,over", [
@@ -389,7 +398,7 @@ def test_repaint_flags_match_oracle_same_seed(opt_over, calls, undos):
 # ------------------------------------------------------------------------------------------------
 # full loops
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
 @pytest.mark.parametrize("fn,name,B,T", [("loop_show_B1_T88_ov0_ddim25.npz", "show", 1, 88),
                                          ("loop_beat_B2_T34_ov0_ddim25.npz", "beat", 2, 34)])
 def test_ddim25_loop_matches_reference_golden(golden_dir, prec, fn, name, B, T):
@@ -422,7 +431,7 @@ def _oracle_loop_cuda(cfg, sd, inp, y, ov, ddim=True, steps=1000, seed=77, **kw)
         return fn(den, (B, T, cfg["net_dim_pose"]), y=y, device="cuda")
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
 @pytest.mark.parametrize("name,B,T,ov,jn", [("show", 2, 88, 10, 5), ("beat", 1, 34, 4, 2)])
 def test_harmonize_loop_matches_oracle_same_seed(prec, name, B, T, ov, jn):
     """RePaint path: same CUDA generator seed => our loop and the oracle (eager torch on the same GPU,

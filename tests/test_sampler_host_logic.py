@@ -92,7 +92,7 @@ class OracleEngine(FusedUniDiffuser):
 def cpu_sampler(monkeypatch):
     monkeypatch.setattr(D, "_lib", FakeLibModule)
     monkeypatch.setattr(D, "_ptr", lambda t: t)
-    monkeypatch.setattr(D, "_stream", lambda: None)
+    monkeypatch.setattr(D, "_stream", lambda device=None: None)
 
 
 def relmax(a, b):
