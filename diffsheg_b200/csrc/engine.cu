@@ -857,7 +857,7 @@ int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, i
                     float sqrt_recipm1_ac, float sqrt_ac_prev, float sqrt_one_minus_ac_prev, const float* gt,
                     const uint8_t* mask, const float* noise2, int32_t blend, int32_t overlap_len, float* pred_xstart_out,
                     void* stream) {
-  if (!x || !eps || !x_out || n <= 0 || (mask && (!gt || !noise2))) { g_create_error = "dsheg_ddim_step: bad arguments"; return 1; }
+  if (!x || !eps || !x_out || n <= 0 || (mask && !gt)) { g_create_error = "dsheg_ddim_step: bad arguments"; return 1; }
   DeviceGuard dg(device_of(x));
   DdimArgs p;
   p.x = x; p.eps = eps; p.x_out = x_out; p.pred_out = pred_xstart_out; p.n = n; p.T = T; p.D = D;

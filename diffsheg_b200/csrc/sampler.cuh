@@ -28,7 +28,8 @@ __device__ __forceinline__ float ddim_one(const DdimArgs& p, long long i, float 
   float s = __fadd_rn(__fmul_rn(pred, p.sqrt_acp), __fmul_rn(p.sqrt_1m_acp, e2));
   if (p.pred_out) p.pred_out[i] = pred;
   if (p.mask) {  // RePaint merge (gd:1036-1056)
-    float wg = __fadd_rn(__fmul_rn(p.sqrt_acp, p.gt[i]), __fmul_rn(p.sqrt_1m_acp, p.noise2[i]));
+    // noise2 == nullptr: `gt` already IS the noisy known part (--same_overlap_noisy: the previous window's saved tail, gd:1040-1042)
+    float wg = p.noise2 ? __fadd_rn(__fmul_rn(p.sqrt_acp, p.gt[i]), __fmul_rn(p.sqrt_1m_acp, p.noise2[i])) : p.gt[i];
     if (p.blend) {
       const int t = (int)((i / p.D) % p.T);
       if (t < p.overlap_len) {

@@ -113,8 +113,10 @@ class FusedGaussianDiffusion:
             raise NotImplementedError("only ModelVarType.FIXED_SMALL is supported")
         if rescale_timesteps:
             raise NotImplementedError("rescale_timesteps=True is not used by the reference trainers")
-        if _opt_get(opt, "same_overlap_noisy", False) or _opt_get(opt, "fix_head_var", False):
-            raise NotImplementedError("same_overlap_noisy / fix_head_var are not supported")
+        if _opt_get(opt, "fix_head_var", False):
+            raise NotImplementedError("fix_head_var is not supported")
+        self.same_overlap_noisy = bool(_opt_get(opt, "same_overlap_noisy", False))
+        self.saved_noisy_tail = {}   # gd:389-390: respaced step -> the sample's last overlap_len frames after that step
         self.opt = opt
         self.precision, self.max_batch = precision, max_batch
         betas = np.array(betas, dtype=np.float64)
@@ -199,6 +201,9 @@ class FusedGaussianDiffusion:
                 mask = (m != 0).expand(shape).contiguous().view(torch.uint8)   # any mask dtype -> one byte per element
                 assert mask.numel() == img.numel()
                 gt = y["gt"].to(device=dev, dtype=torch.float32).expand(shape).contiguous()
+        self._prev_tail = None
+        if self.same_overlap_noisy and mask is not None and int(y.get("clip_idx", 0)) > 0:
+            self._prev_tail = y["previous_noisy_tail"]   # gd:1040-1042: window ii > 0 re-uses the noisy tail window ii-1 saved per step
         return eng, img, gt, mask
 
     # -- fused steps --------------------------------------------------------------------------------
@@ -212,13 +217,18 @@ class FusedGaussianDiffusion:
         torch.randn_like(img)                         # gd:1023: drawn even though eta = 0
         noise2, blend, ov = None, 0, int(_opt_get(self.opt, "overlap_len", 0) or 0)
         if mask is not None:
-            noise2 = torch.randn_like(img)            # gd:1047
+            if self._prev_tail is not None:           # gd:1040-1042: the known frames arrive already noised (no draw here)
+                gt[:, :ov] = self._prev_tail[int(t)].to(gt.device)
+            else:
+                noise2 = torch.randn_like(img)        # gd:1047
             blend = int(bool(sqrt_1m < np.float32(0.2)) and bool(_opt_get(self.opt, "addBlend", True)))
         B, T, Dm = img.shape
         _lib.check(L.dsheg_ddim_step(_ptr(img), _ptr(eps), _ptr(out), img.numel(), T, Dm, float(a), float(b),
                                      float(sqrt_acp), float(sqrt_1m), _ptr(gt), _ptr(mask), _ptr(noise2), blend, ov,
                                      None, _stream(img.device)), None, "dsheg_ddim_step")
         self.step_launches += 1
+        if self.same_overlap_noisy:                   # gd:1058-1060
+            self.saved_noisy_tail[int(t)] = out[..., -ov:, :].clone()
         return out
 
     def _undo(self, img, t, out):
@@ -270,6 +280,11 @@ class FusedGaussianDiffusion:
                 self._ddim_step(eng, img, eps, i, gt, mask, img)
                 calls += 1
         self.last_stats = dict(denoise_calls=calls, undo_steps=undos)
+        if self.same_overlap_noisy:   # gd:1155-1159 (the dict is keyed by the respaced step; the reference keys it by str(tensor t))
+            # NB the SAME dict object every call, never cleared -- like the reference (gd:389-390, :1156): the caller hands it back
+            # as y['previous_noisy_tail'], so a step the jump schedule visits again reads the tail THIS window saved on its
+            # previous visit, not the previous window's
+            return {"sample": img, "saved_noisy_tail": self.saved_noisy_tail}
         return img
 
     # -- DDPM ---------------------------------------------------------------------------------------

@@ -84,7 +84,8 @@ def generate_long(opt, encoder, diffusion, audio_emb, p_id, dim_pose, add_cond, 
         raise ValueError("opt.fix_very_first needs the ground-truth motions (show:885-888)")
     audio_list = get_windows(audio_emb, n_poses, step)
     cond_list = get_windows(add_cond, n_poses, step) if add_cond else [add_cond or {}] * len(audio_list)
-    outs, prev = [], None
+    outs, prev, prev_tail = [], None, None
+    same_noisy = bool(getattr(opt, "same_overlap_noisy", False)) and ov > 0 and bool(getattr(opt, "ddim", False))
     for ii, (aud, cond) in enumerate(zip(audio_list, cond_list)):
         inpaint = {}
         if ov > 0:
@@ -97,7 +98,11 @@ def generate_long(opt, encoder, diffusion, audio_emb, p_id, dim_pose, add_cond, 
             elif fix_first:
                 mask[:, :ov, :] = True
                 gt[:, :ov, :] = get_windows(motions, n_poses, step)[0][:, -ov:, :].to(aud.device)
-            inpaint = {"gt": gt, "outpainting_mask": mask}
+            inpaint = {"gt": gt, "outpainting_mask": mask, "clip_idx": ii}   # beat:1006
+            if ii > 0 and same_noisy:
+                inpaint["previous_noisy_tail"] = prev_tail                      # beat:1022-1023
         prev = generate_batch(opt, encoder, diffusion, aud, p_id, dim_pose, cond, inpaint)
+        if same_noisy:                                                          # beat:1026-1028
+            prev, prev_tail = prev["sample"], prev["saved_noisy_tail"]
         outs.append(prev if ii == len(audio_list) - 1 else prev[:, :step])
     return torch.cat(outs, dim=1)

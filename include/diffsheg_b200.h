@@ -94,7 +94,9 @@ int dsheg_profile_end(dsheg_handle* h, double* ms, double* work, int64_t* count)
 /* ddim_sample, eta = 0 (gaussian_diffusion.py:976-1066): x_out = DDIM update of (x, eps),
  * then, when gt/mask are given, the RePaint merge :1034-1056 with noise2 and the linear
  * overlap blend (blend != 0, first overlap_len frames).  n = B*T*D elements, frame stride
- * D, T frames per sample.  gt/mask/noise2 may be NULL (no repaint).  mask: 1 byte/element. */
+ * D, T frames per sample.  gt/mask/noise2 may be NULL (no repaint).  mask: 1 byte/element.
+ * gt and mask given but noise2 NULL: gt already holds the NOISY known frames (--same_overlap_noisy, :1040-1042: the tail the
+ * previous window saved at this very step) and is merged as is. */
 int dsheg_ddim_step(const float* x, const float* eps, float* x_out, int64_t n, int32_t T, int32_t D,
                     float sqrt_recip_ac, float sqrt_recipm1_ac, float sqrt_ac_prev,
                     float sqrt_one_minus_ac_prev, const float* gt, const uint8_t* mask,

@@ -102,7 +102,7 @@ class OracleDiffusion:
 
     def __init__(self, num_steps=1000, respacing=None, overlap_len=0, add_blend=True,
                  jump_length=3, jump_n_sample=5, no_resample=False, no_repaint=False,
-                 timestep_respacing="ddim25"):
+                 timestep_respacing="ddim25", same_overlap_noisy=False):
         base_betas = linear_betas(num_steps)
         if respacing is None:
             betas = base_betas
@@ -133,6 +133,8 @@ class OracleDiffusion:
         self.jump_length, self.jump_n_sample = jump_length, jump_n_sample
         self.no_resample, self.no_repaint = no_resample, no_repaint
         self.timestep_respacing = timestep_respacing
+        self.same_overlap_noisy = same_overlap_noisy   # gd:389-390
+        self.saved_noisy_tail = {}
 
     # -- helpers ---------------------------------------------------------------------------
     @staticmethod
@@ -175,13 +177,19 @@ class OracleDiffusion:
         if self._has_mask(y):  # gd:1036-1056
             mask = y["outpainting_mask"]
             noise_weight = torch.sqrt(1 - alpha_bar_prev)
-            gt = y["gt"].to(x.dtype)
-            weighed_gt = torch.sqrt(alpha_bar_prev) * gt + noise_weight * torch.randn_like(xo)
+            if self.same_overlap_noisy and y["clip_idx"] > 0:   # gd:1040-1042 (weighed_gt ALIASES y['gt'], no noise is drawn)
+                weighed_gt = y["gt"]
+                weighed_gt[:, :self.overlap_len] = y["previous_noisy_tail"][t]
+            else:
+                gt = y["gt"].to(x.dtype)
+                weighed_gt = torch.sqrt(alpha_bar_prev) * gt + noise_weight * torch.randn_like(xo)
             if float(noise_weight) < 0.2 and self.add_blend:
                 ov = self.overlap_len
                 lw = torch.linspace(0, 1, ov, device=x.device).to(x.dtype).view(1, -1, 1)
                 weighed_gt[:, :ov, :] = weighed_gt[:, :ov, :] * (1 - lw) + xo[:, :ov, :] * lw
             xo = weighed_gt * mask + xo * ~mask
+        if self.same_overlap_noisy:   # gd:1058-1060 (keyed by the respaced step; the reference uses str(tensor t))
+            self.saved_noisy_tail[t] = xo[..., -self.overlap_len:, :].clone()
         return xo, pred_xstart
 
     def p_sample(self, denoise, x, t, y, pred_xstart_prev=None):
@@ -222,6 +230,8 @@ class OracleDiffusion:
                 img, _ = self.ddim_sample(denoise, img, i, y)
                 if trace is not None:
                     trace.append(img.clone())
+        if self.same_overlap_noisy:   # gd:1155-1159: the dict object itself (aliased by the caller's previous_noisy_tail)
+            return {"sample": img, "saved_noisy_tail": self.saved_noisy_tail}
         return img
 
     def p_sample_loop(self, denoise, shape, y=None, noise=None, device="cpu", dtype=torch.float32,

@@ -550,3 +550,62 @@ def test_batch_rows_are_independent_at_full_size():
         eng.prepare_window(inp["mel"][sl], inp["hubert"][sl], inp["person_id"][sl])
         small = eng.denoise(inp["x_T"][sl].contiguous(), 520, 1.5, 1.1)
         assert torch.equal(small, big[sl]), f"rows {lo}..{lo + 1} differ"
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler control flow on the real step kernels: DDPM RePaint loop (gd:843-920) and --same_overlap_noisy (gd:1040-1060),
+# toy denoiser on the GPU (the sampler code does not care what produces eps), oracle with the same CUDA seed.
+# The oracle's own control flow is pinned to the REAL reference by tests/test_sampler_host_logic.py (CPU).
+# ------------------------------------------------------------------------------------------------
+def test_ddpm_repaint_loop_on_the_step_kernels_matches_oracle_same_seed():
+    import test_sampler_host_logic as H
+    from diffsheg_b200 import FusedGaussianDiffusion, get_named_beta_schedule
+    from oracle import diffusion as odiff
+    gt, mask = (t.cuda() for t in H._toy_inpaint())
+    opt = synth.make_opt(synth.make_cfg("beat"), ddim=False, overlap_len=H.TOV)
+    diff = FusedGaussianDiffusion(opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    eng = H.ToyEngine("cuda")
+    shape = (H.TB, H.TT, H.TD)
+    torch.manual_seed(77)
+    got = diff.p_sample_loop(eng, shape, clip_denoised=False, model_kwargs=H._toy_kwargs({"gt": gt.clone(), "outpainting_mask": mask}, "cuda"))
+    assert diff.last_stats == {"denoise_calls": 2410, "undo_steps": 2160}
+    torch.manual_seed(77)
+    want = odiff.OracleDiffusion(1000, None, overlap_len=H.TOV).p_sample_loop(lambda x, t, a, b: H.toy_eps(x, t), shape,
+                                                                                 y={"gt": gt.clone(), "outpainting_mask": mask}, device="cuda")
+    err = relmax(got, want)
+    print(f"\n[parity] DDPM RePaint loop (2410 calls, 2160 re-noise steps) on the step kernels: relmax={err:.3e}")
+    assert err < 2e-4
+
+
+def test_same_overlap_noisy_chain_on_the_step_kernels_matches_oracle_same_seed():
+    import test_sampler_host_logic as H
+    from diffsheg_b200 import FusedSpacedDiffusion, get_named_beta_schedule, space_timesteps
+    from oracle import diffusion as odiff
+    opt = synth.make_opt(synth.make_cfg("beat"), overlap_len=H.TOV, same_overlap_noisy=True)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    eng = H.ToyEngine("cuda")
+    shape = (H.TB, H.TT, H.TD)
+
+    def chain(loop):
+        samples, prev, tail = [], None, None
+        for ii in range(3):
+            gtw = torch.zeros(shape, device="cuda")
+            maskw = torch.zeros(shape, dtype=torch.bool, device="cuda")
+            y = {"gt": gtw, "outpainting_mask": maskw, "clip_idx": ii}
+            if ii > 0:
+                maskw[:, :H.TOV] = True
+                gtw[:, :H.TOV] = prev[:, -H.TOV:]
+                y["previous_noisy_tail"] = tail
+            out = loop(y)
+            prev, tail = out["sample"], out["saved_noisy_tail"]
+            samples.append(prev.clone())
+        return torch.stack(samples)
+
+    torch.manual_seed(78)
+    got = chain(lambda y: diff.ddim_sample_loop(eng, shape, clip_denoised=False, model_kwargs=H._toy_kwargs(y, "cuda")))
+    d = odiff.OracleDiffusion(1000, "ddim25", overlap_len=H.TOV, same_overlap_noisy=True)
+    torch.manual_seed(78)
+    want = chain(lambda y: d.ddim_sample_loop(lambda x, t, a, b: H.toy_eps(x, t), shape, y=y, device="cuda"))
+    err = relmax(got, want)
+    print(f"\n[parity] --same_overlap_noisy chain of 3 windows on the step kernels: relmax={err:.3e}")
+    assert len(eng.calls) == 25 + 63 + 63 and err < 2e-4

@@ -37,7 +37,7 @@ def test_unsupported_sampler_options_fail_loudly():
     with pytest.raises(NotImplementedError):
         FusedGaussianDiffusion(betas=betas, model_var_type="LEARNED_RANGE")
     with pytest.raises(NotImplementedError):
-        FusedGaussianDiffusion(betas=betas, opt=argparse.Namespace(same_overlap_noisy=True))
+        FusedGaussianDiffusion(betas=betas, opt=argparse.Namespace(fix_head_var=True))
     d = FusedGaussianDiffusion(betas=betas)
     with pytest.raises(NotImplementedError):  # generate_batch always passes clip_denoised=False (show:173)
         d.ddim_sample_loop(None, (1, 2, 3), clip_denoised=True, model_kwargs={})

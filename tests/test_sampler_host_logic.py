@@ -25,7 +25,7 @@ class FakeLib:
         e2 = (f(a) * x - px) / f(b)
         s = px * f(sacp) + f(s1m) * e2
         if mask is not None:
-            wg = f(sacp) * gt + f(s1m) * noise2
+            wg = f(sacp) * gt + f(s1m) * noise2 if noise2 is not None else gt.clone()
             if blend:
                 lw = torch.linspace(0, 1, ov).view(1, -1, 1)
                 wg[:, :ov] = wg[:, :ov] * (1 - lw) + s[:, :ov] * lw
@@ -144,3 +144,118 @@ def test_product_ddpm_loop_orchestration_matches_reference(cpu_sampler, golden_d
     out = diff.p_sample_loop(eng, (2, 34, cfg["net_dim_pose"]), clip_denoised=False, model_kwargs=kw)
     assert diff.last_stats == {"denoise_calls": 40, "undo_steps": 0} and eng.calls == list(range(39, -1, -1))
     assert relmax(out.numpy(), g["sample"]) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# control flow the network-driven goldens do not reach: the DDPM RePaint loop (gd:843-920) and --same_overlap_noisy
+# (gd:1040-1042, :1058-1060, :1155-1159).  Fixtures: the REAL reference sampler driving a closed-form toy denoiser
+# (tests/golden/make_golden_sampler.py); product and oracle are both pinned to them here.
+# ------------------------------------------------------------------------------------------------------------------------
+TB, TT, TD, TOV = 2, 12, 6, 3
+
+
+def toy_eps(x, t_orig):
+    return 0.9 * torch.tanh(0.7 * x.flip(-1) + 0.3 * x.roll(1, 1) + 0.002 * float(t_orig))
+
+
+class ToyEngine(FusedUniDiffuser):
+    """The sampler's view of an engine, arithmetic by the toy denoiser (any device)."""
+
+    def __init__(self, device="cpu"):
+        self.device = torch.device(device)
+        self.cond_scale, self.max_batch, self.max_frames, self.calls = 1.0, 1 << 30, 1 << 30, []
+
+    def __del__(self):
+        pass
+
+    def prepare_window(self, mel, hubert, person_id):
+        pass
+
+    def denoise(self, x, t_orig, a, b, cond_scale=None, out=None):
+        self.calls.append(int(t_orig))
+        out.copy_(toy_eps(x, t_orig))
+        return out
+
+
+def _toy_kwargs(y, device="cpu"):
+    z = torch.zeros(TB, TT, 1, device=device)
+    return dict(audio_emb=z, length=None, person_id=torch.zeros(TB, 1, device=device), add_cond={"pretrain_aud_feat": z}, y=y, pe_type="pe_sinu")
+
+
+def _toy_inpaint(seed=5):
+    g = torch.Generator().manual_seed(seed)
+    gt = torch.zeros(TB, TT, TD)
+    gt[:, :TOV] = torch.randn(TB, TOV, TD, generator=g)
+    mask = torch.zeros(TB, TT, TD, dtype=torch.bool)
+    mask[:, :TOV] = True
+    return gt, mask
+
+
+def test_product_and_oracle_ddpm_repaint_loop_match_reference(cpu_sampler, golden_dir):
+    """p_sample_loop with known frames: get_schedule_jump_paper (t_T = 250, jump 10 x 10): 2 410 denoiser calls, 2 160 re-noise
+    steps with t_shift = 1 (gd:912-917), the known frames merged BEFORE every call but the first (gd:727-745)."""
+    from oracle import diffusion as odiff
+    g = np.load(os.path.join(golden_dir, "sampler_ddpm_harmonize_toy.npz"))
+    gt, mask = _toy_inpaint()
+    eng = ToyEngine()
+    opt = synth.make_opt(synth.make_cfg("beat"), ddim=False, overlap_len=TOV)
+    diff = FusedGaussianDiffusion(opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    torch.manual_seed(int(g["seed"]))
+    out = diff.p_sample_loop(eng, (TB, TT, TD), clip_denoised=False, model_kwargs=_toy_kwargs({"gt": gt.clone(), "outpainting_mask": mask}))
+    assert diff.last_stats == {"denoise_calls": int(g["calls"]), "undo_steps": 2160}
+    assert (eng.calls[0], eng.calls[-1]) == (int(g["first_t"]), int(g["last_t"]))
+    assert relmax(out.numpy(), g["sample"]) < 2e-4
+    d = odiff.OracleDiffusion(1000, None, overlap_len=TOV)
+    torch.manual_seed(int(g["seed"]))
+    want = d.p_sample_loop(lambda x, t, a, b: toy_eps(x, t), (TB, TT, TD), y={"gt": gt.clone(), "outpainting_mask": mask})
+    assert relmax(want.numpy(), g["sample"]) < 2e-4
+
+
+def _same_overlap_chain(loop, alias_ok=True):
+    """beat:1003-1028: three windows; window ii > 0 repaints its head from the tails window ii-1 saved at every step."""
+    samples, prev, tail = [], None, None
+    for ii in range(3):
+        gtw = torch.zeros(TB, TT, TD)
+        maskw = torch.zeros(TB, TT, TD, dtype=torch.bool)
+        y = {"gt": gtw, "outpainting_mask": maskw, "clip_idx": ii}
+        if ii > 0:
+            maskw[:, :TOV] = True
+            gtw[:, :TOV] = prev[:, -TOV:]
+            y["previous_noisy_tail"] = tail
+        out = loop(y)
+        prev, tail = out["sample"], out["saved_noisy_tail"]
+        samples.append(prev.clone())
+    return torch.stack(samples)
+
+
+def test_product_and_oracle_same_overlap_noisy_chain_match_reference(cpu_sampler, golden_dir):
+    from oracle import diffusion as odiff
+    g = np.load(os.path.join(golden_dir, "sampler_same_overlap_noisy_toy.npz"))
+    eng = ToyEngine()
+    opt = synth.make_opt(synth.make_cfg("beat"), overlap_len=TOV, same_overlap_noisy=True)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    torch.manual_seed(int(g["seed"]))
+    got = _same_overlap_chain(lambda y: diff.ddim_sample_loop(eng, (TB, TT, TD), clip_denoised=False, model_kwargs=_toy_kwargs(y)))
+    assert len(eng.calls) == int(g["calls"]) == 25 + 63 + 63
+    assert relmax(got.numpy(), g["samples"]) < 2e-4
+    d = odiff.OracleDiffusion(1000, "ddim25", overlap_len=TOV, same_overlap_noisy=True)
+    torch.manual_seed(int(g["seed"]))
+    want = _same_overlap_chain(lambda y: d.ddim_sample_loop(lambda x, t, a, b: toy_eps(x, t), (TB, TT, TD), y=y))
+    assert relmax(want.numpy(), g["samples"]) < 2e-4
+
+
+def test_generate_long_threads_the_noisy_tails_between_windows(cpu_sampler):
+    """The product's own window loop (trainer.generate_long) under --same_overlap_noisy equals the hand-written beat:1003-1028 chain."""
+    from diffsheg_b200 import generate_long
+    frames = TT + 2 * (TT - TOV)
+    opt = synth.make_opt(synth.make_cfg("beat"), overlap_len=TOV, same_overlap_noisy=True, n_poses=TT)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    z = torch.zeros(TB, frames, 1)
+    torch.manual_seed(31)
+    got = generate_long(opt, ToyEngine(), diff, z, torch.zeros(TB, 1), TD, {"pretrain_aud_feat": z})
+    diff2 = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    eng2 = ToyEngine()
+    torch.manual_seed(31)
+    chain = _same_overlap_chain(lambda y: diff2.ddim_sample_loop(eng2, (TB, TT, TD), clip_denoised=False, model_kwargs=_toy_kwargs(y)))
+    want = torch.cat([chain[0][:, :TT - TOV], chain[1][:, :TT - TOV], chain[2]], 1)
+    assert got.shape == (TB, frames, TD) and torch.equal(got, want)
