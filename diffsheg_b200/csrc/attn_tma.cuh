@@ -63,16 +63,22 @@ static_assert(NST % 2 == 0 && TP % 16 == 0, "a unit's K' and V tiles share one r
 __device__ __forceinline__ void group_sync(int grp) { prims::named_bar_sync<32 * WPG>(grp + 1); }          // ids 1 .. 4
 __device__ __forceinline__ void consumer_sync() { prims::named_bar_sync<32 * NCW>(NGRP + 1); }             // id 5
 
+// Self-attention (transformer.py:112-130): tmQ and tmKV both view the fused qkv tensor [rows, 1536], kcol = 512, vcol = 1024, Tkv = T.
+// Cross-attention (LinearTemporalCrossAttention, transformer.py:133-166): tmQ views q' [n_samples * T, 512], tmKV views the
+// conditioning's projections [n_samples * Tkv, 1024] (k' | v), kcol = 0, vcol = 512: Tkv frames of K' / V per sample, T of Q'.
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z, int n_samples, int T, int B,
+attn_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int kcol, int vcol,
+                bf16* __restrict__ z, int n_samples, int T, int Tkv, int B,
                 const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
   DSHEG_PDL_ENTER();
   DSHEG_TC_DYN_SMEM(sm);
   const uint32_t sbase = tc::smem_u32(sm);
   if (sbase & 1023u) tc::trap();   // SWIZZLE_128B tiles: the dynamic smem base must be 1024-byte aligned (no room for slack)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_mt = (T + 15) >> 4;            // 16-frame tiles that contain valid frames
-  const uint32_t tile_tx = (uint32_t)n_mt * 16u * 128u;   // bytes one TMA box delivers (frames T .. Tpad-1 arrive as zeros)
+  const int n_mt = (T + 15) >> 4;            // 16-frame tiles of Q' / Y that contain valid frames
+  const int n_kt = (Tkv + 15) >> 4;          // ... of K' / V
+  const uint32_t q_tx = (uint32_t)n_mt * 16u * 128u;    // bytes one TMA box delivers (frames T .. Tpad-1 arrive as zeros)
+  const uint32_t kv_tx = (uint32_t)n_kt * 16u * 128u;
   auto full_bar = [&](int s) { return sbase + BAR_OFF + 8u * s; };
   auto empty_bar = [&](int s) { return sbase + BAR_OFF + 8u * (NST + s); };
   auto qfull_bar = [&](int h) { return sbase + BAR_OFF + 8u * (2 * NST + h); };
@@ -89,7 +95,7 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z,
 
   if (warp == NCW) {
     // ========== producer warp: lane 0 issues every TMA load of this CTA; all 32 lanes fold the LayerNorm constants ==========
-    if (lane == 0) tc::prefetch_tensormap(&tmQKV);
+    if (lane == 0) { tc::prefetch_tensormap(&tmQ); tc::prefetch_tensormap(&tmKV); }
     const int col0 = lane * 16;
     float gam[16], bet[16];   // sample-invariant: LayerNorm weight / bias of this lane's 16 columns
 #pragma unroll
@@ -128,8 +134,8 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z,
           __syncwarp();   // the table is complete before lane 0's arrive (release) on the Q' barriers the consumers acquire
           if (lane == 0) {
             for (int hh = 0; hh < NH; ++hh) {
-              tc::mbar_arrive_expect_tx(qfull_bar(hh), tile_tx);
-              tc::tma_load_3d(&tmQKV, qfull_bar(hh), sbase + QY_OFF + hh * TILE_BYTES, hh * HD, 0, smp);
+              tc::mbar_arrive_expect_tx(qfull_bar(hh), q_tx);
+              tc::tma_load_3d(&tmQ, qfull_bar(hh), sbase + QY_OFF + hh * TILE_BYTES, hh * HD, 0, smp);
             }
           }
         }
@@ -137,13 +143,13 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z,
           const int slot = (int)(kv % NST);
           tc::mbar_wait(empty_bar(slot), ((kv / NST) & 1u) ^ 1u);
           if (lane == 0) {
-            tc::mbar_arrive_expect_tx(full_bar(slot), tile_tx);
-            tc::tma_load_3d(&tmQKV, full_bar(slot), sbase + RING_OFF + slot * TILE_BYTES, (1 + j) * D + h * HD, 0, smp);
+            tc::mbar_arrive_expect_tx(full_bar(slot), kv_tx);
+            tc::tma_load_3d(&tmKV, full_bar(slot), sbase + RING_OFF + slot * TILE_BYTES, (j ? vcol : kcol) + h * HD, 0, smp);
           }
         }
       }
       // pull the NEXT sample's Q' tiles into L2 while this one is being multiplied (they are loaded in one burst after its LayerNorm pass)
-      if (lane < NH && smp + (int)gridDim.x < n_samples) tc::tma_prefetch_l2_3d(&tmQKV, lane * HD, 0, smp + (int)gridDim.x);
+      if (lane < NH && smp + (int)gridDim.x < n_samples) tc::tma_prefetch_l2_3d(&tmQ, lane * HD, 0, smp + (int)gridDim.x);
     }
     return;
   }
@@ -179,7 +185,7 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z,
           for (int nt = 0; nt < 4; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
         cs[0][0] = cs[0][1] = cs[0][2] = cs[0][3] = cs[1][0] = cs[1][1] = cs[1][2] = cs[1][3] = 0.f;
 #pragma unroll 2
-        for (int kt = 0; kt < n_mt; ++kt) {   // 16 frames per k-step
+        for (int kt = 0; kt < n_kt; ++kt) {   // 16 frames per k-step
           uint32_t a0[4], a1[4];
           {
             const int r = kt * 16 + rr + ((mat >> 1) << 3);
@@ -344,43 +350,57 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ z,
 }
 
 #ifndef DSHEG_EMU
-// (column, frame, sample) view of qkv [n_samples * T, 1536] bf16; box = 64 columns x Tpad frames of one sample.
-inline bool make_qkv_tmap(CUtensorMap* map, const void* qkv, int n_samples, int T, std::string* err) {
-  struct Key { const void* p; int n, t; bool operator==(const Key& o) const { return p == o.p && n == o.n && t == o.t; } };
-  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.t << 48); } };
+// (column, frame, sample) view of a bf16 tensor [n_samples * T, cols]; box = 64 columns x Tpad frames of one sample.
+inline bool make_frames_tmap(CUtensorMap* map, const void* base, int cols, int n_samples, int T, std::string* err) {
+  struct Key { const void* p; int c, n, t; bool operator==(const Key& o) const { return p == o.p && c == o.c && n == o.n && t == o.t; } };
+  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.t << 48) ^ ((size_t)k.c << 32); } };
   static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
-  const Key k{qkv, n_samples, T};
+  const Key k{base, cols, n_samples, T};
   auto it = cache.find(k);
   if (it != cache.end()) { *map = it->second; return true; }
   tc::EncodeTiledFn fn = tc::get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
-  if (reinterpret_cast<uintptr_t>(qkv) & 15) { *err = "qkv not 16-byte aligned"; return false; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (cols % 8)) { *err = "attention operand not 16-byte aligned"; return false; }
   const int Tpad = (T + 15) / 16 * 16;
-  cuuint64_t gdim[3] = {(cuuint64_t)(3 * D), (cuuint64_t)T, (cuuint64_t)n_samples};
-  cuuint64_t gstr[2] = {(cuuint64_t)(3 * D) * 2, (cuuint64_t)T * (3 * D) * 2};
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)n_samples};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)T * cols * 2};
   cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)Tpad, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (qkv, 3-D) failed, CUresult " + std::to_string((int)r); return false; }
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (3-D frames view) failed, CUresult " + std::to_string((int)r); return false; }
   if (cache.size() > 1024) cache.clear();
   cache.emplace(k, *map);
   return true;
 }
 
-inline cudaError_t launch_attn_tma(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
-                                   const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+inline cudaError_t launch_attn_tma_qkv(const CUtensorMap& mq, const CUtensorMap& mkv, int kcol, int vcol, bf16* z, int n_samples, int T, int Tkv,
+                                       int ssB, const float* ln_g, const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  CUtensorMap map;
-  if (!make_qkv_tmap(&map, qkv, n_samples, T, err)) return cudaErrorInvalidValue;
   const int grid = n_samples < num_sms ? n_samples : num_sms;
-  DSHEG_LAUNCH(attn_tma_kernel, grid, NTHREADS, SMEM_BYTES, st, map, z, n_samples, T, ssB, ln_g, ln_b, ss, ss_ld);
+  DSHEG_LAUNCH(attn_tma_kernel, grid, NTHREADS, SMEM_BYTES, st, mq, mkv, kcol, vcol, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld);
   return cudaGetLastError();
+}
+
+// self-attention on the fused projection qkv [n_samples * T, 1536] (q' | k' | v)
+inline cudaError_t launch_attn_tma(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
+                                   const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+  CUtensorMap map;
+  if (!make_frames_tmap(&map, qkv, 3 * D, n_samples, T, err)) return cudaErrorInvalidValue;
+  return launch_attn_tma_qkv(map, map, D, 2 * D, z, n_samples, T, T, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
+}
+
+// cross-attention (transformer.py:133-166): q' [n_samples * T, 512] from the motion stream, kv [n_samples * Tkv, 1024] (k' | v) from the conditioning
+inline cudaError_t launch_cross_attn_tma(const bf16* q, const bf16* kv, bf16* z, int n_samples, int T, int Tkv, int ssB, const float* ln_g,
+                                         const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+  CUtensorMap mq, mkv;
+  if (!make_frames_tmap(&mq, q, D, n_samples, T, err) || !make_frames_tmap(&mkv, kv, 2 * D, n_samples, Tkv, err)) return cudaErrorInvalidValue;
+  return launch_attn_tma_qkv(mq, mkv, 0, D, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
 }
 #endif  // DSHEG_EMU
 

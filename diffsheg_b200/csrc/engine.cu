@@ -1125,4 +1125,21 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
   return step_done("dsheg_op_attention_bf16");
 }
 
+// LinearTemporalCrossAttention core + Stylization prologue (transformer.py:133-166, then :92-96 up to the SiLU) at op level: the
+// reference only builds it for --model_base transformer_decoder, a configuration its own UniDiffuser cannot run, so
+// the engine never dispatches it; the kernel is the default attention kernel with separate Q and K / V sources and lengths.
+int dsheg_op_cross_attention_bf16(const void* q, const void* kv, const float* ln_g, const float* ln_b, const float* scale_shift, void* z,
+                                  int32_t Bn, int32_t T, int32_t N, void* stream) {
+  if (T > av3::TP || T < 1 || N > av3::TP || N < 1) { g_create_error = "op_cross_attention_bf16: T and N must be in 1..96"; return 1; }
+  DeviceGuard dg(device_of(q));
+  std::string terr;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t le = atm::launch_cross_attn_tma((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms,
+                                              (cudaStream_t)stream, &terr);
+  if (le != cudaSuccess) { g_create_error = std::string("op_cross_attention_bf16: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
+  return step_done("dsheg_op_cross_attention_bf16");
+}
+
 }  // extern "C"

@@ -174,6 +174,12 @@ int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, c
 int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
                             void* z, int32_t Bn, int32_t T, int32_t numerators, void* stream);
 
+/* LinearTemporalCrossAttention core + Stylization prologue (transformer.py:133-166, then :92-96 up to the SiLU), bf16:
+ * q [Bn, T, 512] holds the Q numerators exp(query - shift), kv [Bn, N, 1024] = (K numerators exp(key - shift) | value) of the
+ * conditioning sequence (N frames, any N <= 96), z [Bn, T, 512].  Same kernel as numerators = 1 above with separate sources. */
+int dsheg_op_cross_attention_bf16(const void* q, const void* kv, const float* ln_g, const float* ln_b,
+                                  const float* scale_shift, void* z, int32_t Bn, int32_t T, int32_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

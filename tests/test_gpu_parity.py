@@ -609,3 +609,33 @@ def test_same_overlap_noisy_chain_on_the_step_kernels_matches_oracle_same_seed()
     err = relmax(got, want)
     print(f"\n[parity] --same_overlap_noisy chain of 3 windows on the step kernels: relmax={err:.3e}")
     assert len(eng.calls) == 25 + 63 + 63 and err < 2e-4
+
+
+@pytest.mark.parametrize("Bn,T,N", [(3, 88, 88), (2, 34, 60), (2, 88, 17), (200, 40, 96), (1, 7, 3)])
+def test_op_cross_attention_with_static_shift_numerators(L, Bn, T, N):
+    """LinearTemporalCrossAttention (tr:133-166) + Stylization prologue at op level: Q from the motion stream (T frames), K / V from a
+    conditioning sequence of N != T frames; attn_tma with separate sources.  Inputs are the numerators exp(. - shift) (ACT_EXPO
+    contract); the result must equal the cross-attention of the original q, k (softmax is shift-invariant)."""
+    torch.manual_seed(T + N)
+    D, H = 512, 8
+    q = (1.5 * torch.randn(Bn, T, D, device="cuda")).bfloat16()
+    kv = (1.5 * torch.randn(Bn, N, 2 * D, device="cuda")).bfloat16()
+    g, b = 1 + 0.1 * torch.randn(D, device="cuda"), 0.1 * torch.randn(D, device="cuda")
+    ss = 0.5 * torch.randn(Bn, 2 * D, device="cuda")
+    qd, kd, vd = q.double(), kv.double()[..., :D], kv.double()[..., D:]
+    sq = (10 * torch.randn(Bn, T, H, 1, device="cuda").double()).clamp(-64, 64)
+    sk = (10 * torch.randn(Bn, 1, D, device="cuda").double()).clamp(-64, 64)
+    qn = torch.exp(qd.view(Bn, T, H, -1) - sq).reshape(Bn, T, D).bfloat16().contiguous()
+    kvn = torch.cat([torch.exp(kd - sk).bfloat16(), kv[..., D:]], -1).contiguous()
+    z = torch.zeros(Bn, T, D, device="cuda", dtype=torch.bfloat16)
+    assert L.dsheg_op_cross_attention_bf16(P(qn), P(kvn), P(g), P(b), P(ss), P(z), Bn, T, N, S()) == 0, L.dsheg_last_error(None)
+    qs = torch.softmax(qd.view(Bn, T, H, -1), dim=-1)                 # tr:158
+    ks = torch.softmax(kd.view(Bn, N, H, -1), dim=1)                  # tr:159
+    att = torch.einsum("bnhd,bnhl->bhdl", ks, vd.view(Bn, N, H, -1))  # tr:163
+    y = torch.einsum("bnhd,bhdl->bnhl", qs, att).reshape(Bn, T, D)    # tr:164
+    yn = torch.nn.functional.layer_norm(y, (D,), g.double(), b.double(), 1e-5)
+    want = torch.nn.functional.silu(yn * (1 + ss[:, None, :D].double()) + ss[:, None, D:].double())
+    torch.cuda.synchronize()
+    err = relmax(z.float(), want)
+    print(f"\n[parity] cross-attention (TMA, static-shift numerators) Bn{Bn} T{T} N{N}: relmax={err:.3e}")
+    assert torch.isfinite(z.float()).all() and err < 3e-2

@@ -131,3 +131,30 @@ def test_denoiser_matches_live_reference_nocfg_show():
                     add_cond={"pretrain_aud_feat": inp["hubert"]}, pe_type="pe_sinu", y={})
         got = unidiffuser_forward(sd, cfg, inp["x_T"], ts, (a, b), inp["mel"], inp["person_id"], inp["hubert"])
     assert relmax(got.numpy(), ref.numpy()) < 2e-5
+
+
+@have_ref
+def test_cross_attention_restatement_matches_the_live_reference_module():
+    """The formula the GPU op test (test_op_cross_attention_with_static_shift_numerators) checks against IS the reference's
+    LinearTemporalCrossAttention core (tr:153-164): same einsums, softmax over the head dim for Q and over the N conditioning
+    frames for K."""
+    import sys
+    if refshim.REF not in sys.path:
+        sys.path.insert(0, refshim.REF)
+    from models.transformer import LinearTemporalCrossAttention
+    torch.manual_seed(0)
+    B, T, N, D, A, H = 2, 9, 5, 64, 32, 4
+    m = LinearTemporalCrossAttention(seq_len=T, latent_dim=D, aud_latent_dim=A, num_head=H, dropout=0.0, time_embed_dim=48).eval()
+    for p in m.parameters():
+        torch.nn.init.normal_(p, std=0.2)
+    x, xf, emb = torch.randn(B, T, D), torch.randn(B, N, A), torch.randn(B, 48)
+    with torch.no_grad():
+        ref = m(x, xf, emb)
+        q = m.query(m.norm(x)).view(B, T, H, -1).softmax(-1)
+        k = m.key(m.text_norm(xf)).view(B, N, H, -1).softmax(1)
+        v = m.value(m.text_norm(xf)).view(B, N, H, -1)
+        y = torch.einsum("bnhd,bhdl->bnhl", q, torch.einsum("bnhd,bnhl->bhdl", k, v)).reshape(B, T, D)
+        e = m.proj_out.emb_layers(emb).unsqueeze(1)
+        scale, shift = e.chunk(2, dim=2)
+        got = x + m.proj_out.out_layers(m.proj_out.norm(y) * (1 + scale) + shift)
+    assert relmax(got.numpy(), ref.numpy()) < 1e-6
