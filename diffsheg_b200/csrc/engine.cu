@@ -913,6 +913,16 @@ int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mea
   return step_done("dsheg_beat_axis_angle_to_euler");
 }
 
+int dsheg_resample_linear(const float* in, float* out, int32_t B, int32_t n_in, int32_t n_out, int32_t C, void* stream) {
+  if (!in || !out || B < 1 || n_in < 1 || n_out < 1 || C < 4 || (C & 3) || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    g_create_error = "dsheg_resample_linear: bad arguments (C % 4 == 0, 16-byte aligned arrays)"; return 1;
+  }
+  DeviceGuard dg(device_of(in));
+  const long long total4 = (long long)B * n_out * (C / 4);
+  resample_linear_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(in, out, n_in, n_out, C, total4);
+  return step_done("dsheg_resample_linear");
+}
+
 // ---- op-level test entry points --------------------------------------------------------------
 namespace {
 __global__ void bf16_to_f32_kernel(const bf16* in, float* out, size_t n) {

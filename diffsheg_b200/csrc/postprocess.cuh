@@ -60,4 +60,30 @@ __global__ void beat_axis_angle_kernel(const float* __restrict__ x, int ldx, con
   }
 }
 
+// ---- SURVEY 8 row f1 (the part that needs no network weights): HuBERT features resampled to the motion frame rate ----------------
+// F.interpolate(x.swapaxes(-1,-2), size=n_out, mode='linear', align_corners=True).swapaxes(-1,-2)  (show:1082, datasets/show.py:98,
+// datasets/beat.py:445): out[b, i, c] = (1 - l) in[b, i0, c] + l in[b, i0 + 1, c], src = i (n_in - 1) / (n_out - 1), i0 = floor(src),
+// l = src - i0 -- the operation order of ATen's upsample_linear1d (fp32 index arithmetic).  One thread per 4 channels.
+__global__ void resample_linear_kernel(const float* __restrict__ in, float* __restrict__ out, int n_in, int n_out, int C, long long total4) {
+  const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+  const int C4 = C >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const int c4 = (int)(i % C4);
+    const long long r = i / C4;
+    const int io = (int)(r % n_out);
+    const long long b = r / n_out;
+    const float src = __fmul_rn(scale, (float)io);
+    const int i0 = (int)src;
+    const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    const float l1 = __fsub_rn(src, (float)i0), l0 = __fsub_rn(1.0f, l1);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in + (b * n_in + i0) * (long long)C) + c4);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(in + (b * n_in + i1) * (long long)C) + c4);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(l0, a.x), __fmul_rn(l1, d.x)); o.y = __fadd_rn(__fmul_rn(l0, a.y), __fmul_rn(l1, d.y));
+    o.z = __fadd_rn(__fmul_rn(l0, a.z), __fmul_rn(l1, d.z)); o.w = __fadd_rn(__fmul_rn(l0, a.w), __fmul_rn(l1, d.w));
+    reinterpret_cast<float4*>(out + (b * n_out + io) * (long long)C)[c4] = o;
+  }
+}
+
 }  // namespace dsheg

@@ -67,6 +67,22 @@ def axis_angle_to_euler(motion, mean_aa, std_aa, mean_pose, std_pose, channels=N
     return euler.reshape(shape), out.reshape(shape)
 
 
+def resample_features(feat, n_out):
+    """show:1082 / datasets/show.py:98: ``F.interpolate(feat.swapaxes(-1,-2), size=n_out, mode='linear', align_corners=True)
+    .swapaxes(-1,-2)`` for HuBERT features ``[B, n_in, C]`` (or ``[n_in, C]``) on the device, without the two transposes."""
+    if not (torch.is_tensor(feat) and feat.is_cuda):
+        raise ValueError("resample_features expects a CUDA tensor")
+    squeeze = feat.dim() == 2
+    x = (feat.unsqueeze(0) if squeeze else feat).to(torch.float32).contiguous()
+    B, n_in, C = x.shape
+    if C % 4:
+        raise ValueError(f"channel count must be a multiple of 4, got {C}")
+    out = torch.empty(B, int(n_out), C, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().dsheg_resample_linear(_ptr(x), _ptr(out), B, n_in, int(n_out), C, _stream(x.device)), None, "resample_linear")
+    return out[0] if squeeze else out
+
+
 def _to_host(t):
     """One D2H into pinned memory; returns a numpy view (the arrays the trainers hand to np.save)."""
     host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

@@ -135,6 +135,11 @@ int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mea
                                    const float* mean_pose, const float* std_pose, float* euler_deg, float* out_norm,
                                    int64_t rows, int32_t C, void* stream);
 
+/* Audio front-end, the part without network weights: HuBERT features [B, n_in, C] resampled to the motion
+ * frame rate [B, n_out, C] -- F.interpolate(mode='linear', align_corners=True) along the frame axis
+ * (trainers/ddpm_show_trainer.py:1082, datasets/show.py:98, datasets/beat.py:445).  fp32, C % 4 == 0. */
+int dsheg_resample_linear(const float* in, float* out, int32_t B, int32_t n_in, int32_t n_out, int32_t C, void* stream);
+
 /* ---- op-level entry points used by the parity tests -------------------------------------- */
 
 /* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32, the

@@ -117,3 +117,18 @@ def test_gpu_axis_angle_full_size_round_trip():
     assert not bool(nans[R[:, 0, 2].abs() < 1 - 1e-6].any())   # NaN only where fp32 rounding can push |M02| past 1 (torch.asin too)
     for err, err_lock in zip(errs, errs_lock):
         assert err < 2e-4 and err_lock < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n_in,n_out,C", [(1, 2999, 1800, 1024), (3, 50, 88, 1024), (2, 88, 88, 128), (1, 1, 34, 8), (2, 7, 1, 16)])
+def test_gpu_linear_resample_matches_torch_interpolate(B, n_in, n_out, C):
+    """f1 (the part without network weights): HuBERT features resampled to the motion frame rate (show:1082) vs the very torch call
+    the reference makes, on the same GPU."""
+    import diffsheg_b200 as dz
+    g = torch.Generator(device="cuda").manual_seed(n_in)
+    x = torch.randn(B, n_in, C, device="cuda", generator=g)
+    want = torch.nn.functional.interpolate(x.swapaxes(-1, -2), size=n_out, mode="linear", align_corners=True).swapaxes(-1, -2)
+    got = dz.resample_features(x, n_out)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())     # same fp32 index arithmetic, last-bit rounding only
+    assert torch.equal(dz.resample_features(x[0], n_out), got[0])
