@@ -27,6 +27,8 @@ def gather_motion(local, total, group=None):
     """All-gather the per-rank [b_r, T, D] results into [total, T, D] on every rank (NCCL on GPUs)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
+    if local.is_cuda and dist.get_backend(group) == "gloo":   # single-GPU hosts testing the sharded path: exchange through the host
+        return gather_motion(local.cpu(), total, group).to(local.device)
     world = dist.get_world_size(group)
     sizes = [shard_range(total, r, world) for r in range(world)]
     mx = max(hi - lo for lo, hi in sizes)

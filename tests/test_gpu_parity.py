@@ -7,6 +7,8 @@ holds the fp64 justification: |mode - fp64| next to the reference's own |fp32 - 
   fp32 mode : fp32 reassociation only (LayerNorm folds, fused epilogues, reduction orders): as close to fp64 as the reference's
               own fp32 arithmetic (k = |ours - fp64| / |ref_fp32 - fp64| = 0.9 .. 1.1).  Measured: call 1.8e-6 / 3.0e-6 / 1.5e-6,
               ddim25 loop 9e-7 / 1.3e-6 / 8e-7, 63-call RePaint loop 3e-5, DDPM 2e-5 (re-noising amplifies last-bit differences)
+  tf32 mode : fp32 activations, residual stream, statistics and epilogues (exact erf GELU); only the GEMM operands are rounded to
+              TF32 (tcgen05 kind::tf32, fp32 accumulation).  Measured: call 8.7e-4 / 1.7e-3 / 7.4e-4, loops (incl. B=950) 7.3e-4 / 1.2e-3 / 6.1e-4
   bf16 mode : bf16 operands / activations, fp32 accumulation and statistics, tanh-form activations.
               Measured: call 1.15e-2 / 2.4e-2 / 1.0e-2, loops (incl. the B=950 headline size) 8.2e-3 / 1.3e-2 / 7.0e-3
 """
@@ -24,8 +26,7 @@ pytestmark = pytest.mark.gpu
 from parity_util import check as parity_check, fmt as parity_fmt, parity_metrics
 
 TOL = {"fp32": dict(call=dict(relmax=6e-6, per_channel=1e-5, rel_rms=5e-6), loop=dict(relmax=1e-4, per_channel=2e-4, rel_rms=1e-4)),
-       # tf32 mode (fp32 activations, TF32 tensor-core GEMMs): provisional gates until its first measurement lands in profiles/r02
-       "tf32": dict(call=dict(relmax=4e-3, per_channel=8e-3, rel_rms=4e-3), loop=dict(relmax=4e-3, per_channel=8e-3, rel_rms=4e-3)),
+       "tf32": dict(call=dict(relmax=2e-3, per_channel=4e-3, rel_rms=1.6e-3), loop=dict(relmax=2e-3, per_channel=4e-3, rel_rms=1.6e-3)),
        "bf16": dict(call=dict(relmax=2.5e-2, per_channel=5e-2, rel_rms=2.2e-2), loop=dict(relmax=2e-2, per_channel=3e-2, rel_rms=1.6e-2))}
 
 
@@ -131,8 +132,9 @@ def test_op_linear(L, prec, M, N, K, act, use_res):
     bias = torch.randn(N, device="cuda")
     res = torch.randn(M, N, device="cuda") if use_res else None
     out = torch.full((M, N), float("nan"), device="cuda")
-    if prec == "tf32" and K % 4:
-        pytest.skip("the TMA path needs 16-byte aligned rows (the engine keeps such GEMMs on the fp32 SIMT kernel)")
+    if prec == "tf32" and K % 4:   # the TMA path needs 16-byte aligned rows: the op entry refuses loudly (the engine keeps such GEMMs on the fp32 SIMT kernel)
+        assert L.dsheg_op_linear(2, P(A), P(W), P(bias), P(res), P(out), M, N, K, act, S()) != 0 and b"16-byte" in L.dsheg_last_error(None)
+        return
     rc = L.dsheg_op_linear({"fp32": 0, "bf16": 1, "tf32": 2}[prec], P(A), P(W), P(bias), P(res), P(out), M, N, K, act, S())
     assert rc == 0, L.dsheg_last_error(None)
     if prec == "bf16":
@@ -537,19 +539,21 @@ def test_ddim25_loop_at_the_headline_size_matches_the_fp32_oracle():
 
 
 def test_batch_rows_are_independent_at_full_size():
-    """Samples never interact: row i of a B=950 SHOW/CFG call must equal, bit for bit, the same
-    sample run in a batch of 2 -- also pins tile/stripe indexing of every kernel at the headline size."""
-    B = 950
+    """Samples never interact: row i of a B=950 SHOW/CFG call must equal, bit for bit, the same sample run in a batch of
+    24 -- also pins tile / stripe / persistent-CTA indexing of every kernel at the headline size.  (Both sizes are in the
+    rows >= 4096 regime: CTA-pair GEMMs and the fused LayerNorm epilogue of ffn.linear2; the launch-bound regime below it uses
+    128-wide single-CTA tiles and a separate LayerNorm pass, i.e. a different -- equally valid -- rounding of `y`.)"""
+    B, nb = 950, 24
     cfg, sd, eng = _engine("show", "bf16", B, 88)
     inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, 88, seed=4).items()}
     eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
     big = eng.denoise(inp["x_T"], 520, 1.5, 1.1).clone()
     assert torch.isfinite(big).all()
-    for lo in (0, 474, 948):
-        sl = slice(lo, lo + 2)
+    for lo in (0, 463, 926):
+        sl = slice(lo, lo + nb)
         eng.prepare_window(inp["mel"][sl], inp["hubert"][sl], inp["person_id"][sl])
         small = eng.denoise(inp["x_T"][sl].contiguous(), 520, 1.5, 1.1)
-        assert torch.equal(small, big[sl]), f"rows {lo}..{lo + 1} differ"
+        assert torch.equal(small, big[sl]), f"rows {lo}..{lo + nb - 1} differ"
 
 
 # ------------------------------------------------------------------------------------------------
