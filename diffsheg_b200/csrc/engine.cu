@@ -374,7 +374,7 @@ struct Runner {
       attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
                                                                           L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 16 && D == asmall::D && H == asmall::NH && T <= asmall::TP && h->attn_aud) {
-      // DSHEG_ATTN_AUD=1 (experimental): the audio encoder's attention with all 8 heads processed at once (attn_small.cuh)
+      // the audio encoder's attention with all 8 heads processed at once (attn_small.cuh; DSHEG_ATTN_AUD=0: generic kernel below)
       DSHEG_LAUNCH(asmall::attn_d128_kernel, n_samples, asmall::NTHREADS, asmall::smem_bytes(T), st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB,
                    L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 16) {
