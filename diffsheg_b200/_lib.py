@@ -84,6 +84,7 @@ SIGNATURES = {
     "dsheg_op_linear_fused": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "dsheg_bench_gemm": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(ctypes.c_float)]),
     "dsheg_op_attention": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "dsheg_op_attention_tf32": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "dsheg_op_attention_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "dsheg_op_cross_attention_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
 }

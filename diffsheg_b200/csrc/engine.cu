@@ -15,6 +15,7 @@
 #include "attn_v3.cuh"
 #include "attn_small.cuh"
 #include "attn_tma.cuh"
+#include "attn_tf32.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -370,6 +371,10 @@ struct Runner {
       if (le != cudaSuccess) return fail(h, std::string("attn_tma launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
     } else if (tc_attn && h->attn_mode >= 1) {   // no provably safe shifts for this layer (or DSHEG_ATTN=v3 / DSHEG_EXPO=0): softmaxes in the kernel
       DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
+    } else if (std::is_same<TA, float>::value && HD == 64 && h->cfg.precision == DSHEG_PREC_TF32 && h->gemm_engine == 1) {
+      // tf32 mode: the two products of a head on mma.sync TF32, softmaxes / sums / LayerNorm exact fp32 (attn_tf32.cuh)
+      at32::attn_tf32_kernel<<<n_samples, at32::NTHREADS, at32::smem_bytes(T), st>>>((const float*)h->QKV, h->Y32, (float*)h->Z, T, D, H, ssB,
+                                                                                       L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 64) {
       attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
                                                                           L.sa_g, L.sa_b, ss, ss_ld);
@@ -653,6 +658,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   cudaFuncSetAttribute(attn_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(attn_kernel<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn16);
   cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
+  cudaFuncSetAttribute(at32::attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at32::smem_bytes(c.max_frames));
   if (h->attn_aud)
     cudaFuncSetAttribute(asmall::attn_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmall::smem_bytes(c.max_frames < asmall::TP ? c.max_frames : asmall::TP));
   cudaFuncSetAttribute(hubconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HC_TR + 2) * c.hubert_dim * 4);
@@ -1114,6 +1120,21 @@ int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, c
   cudaFree(y32);
   if (e != cudaSuccess) { g_create_error = std::string("op_attention: ") + cudaGetErrorString(e); return 1; }
   return step_done("dsheg_op_attention");
+}
+
+int dsheg_op_attention_tf32(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift, float* z, int32_t Bn,
+                            int32_t T, int32_t D, int32_t H, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H < 1 || D != 64 * H || T < 1 || at32::smem_bytes(T) > 227 * 1024) { g_create_error = "op_attention_tf32: heads of 64, T within the shared-memory budget"; return 1; }
+  DeviceGuard dg(device_of(qkv));
+  float* y32 = nullptr;
+  if (cudaMalloc(&y32, (size_t)Bn * T * D * 4) != cudaSuccess) { g_create_error = "op_attention_tf32: cudaMalloc"; return 1; }
+  cudaFuncSetAttribute(at32::attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at32::smem_bytes(T));
+  at32::attn_tf32_kernel<<<Bn, at32::NTHREADS, at32::smem_bytes(T), st>>>(qkv, y32, z, T, D, H, Bn, ln_g, ln_b, scale_shift, 2 * D);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(y32);
+  if (e != cudaSuccess) { g_create_error = std::string("op_attention_tf32: ") + cudaGetErrorString(e); return 1; }
+  return step_done("dsheg_op_attention_tf32");
 }
 
 int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_b, const float* scale_shift, void* z, int32_t Bn,

@@ -6,9 +6,8 @@
 // are rounded to TF32 (10-bit mantissa, round-to-nearest by the TMA load: CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), accumulation is
 // fp32 in TMEM.  out[M, N] = epilogue(A[M, K] . W[N, K]^T), A = virtual concat of up to 4 fp32 segments.
 //
-// Shape: one 128 x 128 output tile per CTA (not persistent; two CTAs fit an SM, so one's epilogue overlaps the other's
-// mainloop), K in blocks of 32 fp32 (128-byte rows, SWIZZLE_128B -- byte-for-byte the operand geometry of the bf16 kernel:
-// 8 TF32 elements = 32 bytes per MMA k-step), 3-stage TMA ring.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// Shape: one output tile per CTA or CTA pair (not persistent; see TCfg), K in blocks of 32 fp32 (128-byte rows, SWIZZLE_128B --
+// byte-for-byte the operand geometry of the bf16 kernel: 8 TF32 elements = 32 bytes per MMA k-step), 3 / 4-stage TMA ring.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..5 = epilogue (one TMEM lane quadrant each).  The epilogue does its per-row / per-column math in the TMEM layout
 // (thread = row), then turns each 32-column chunk through shared memory (the mainloop's ring is free by then) so that the
 // residual loads and the stores are 128-byte coalesced: 8 lanes x 16 bytes per row, 4 rows per instruction.
@@ -20,17 +19,29 @@ namespace t32 {
 
 using namespace tc;
 
-constexpr int TBM = 128, TBN = 128, TBK = 32;          // fp32 elements
-constexpr int T_STAGES = 3;
-constexpr int TA_BYTES = TBM * TBK * 4, TB_BYTES = TBN * TBK * 4, T_STAGE_BYTES = TA_BYTES + TB_BYTES;   // 16 + 16 KB
+constexpr int TBM = 128, TBK = 32;                     // rows per CTA, fp32 elements per k-block (128-byte rows)
 constexpr int T_NUM_THREADS = 192;
 constexpr int T_TURN_LD = 36;                            // floats per staged row (144 B: 16-byte aligned, conflict-free)
 constexpr int T_BAR_BYTES = 128;
-constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_BAR_BYTES + 1024;   // + alignment slack
-static_assert(4 * 32 * T_TURN_LD * 4 <= T_STAGES * T_STAGE_BYTES, "the epilogue turns its chunks through the idle ring");
-// kind::tf32 instruction descriptor: D = f32 (bit 4), A = B = TF32 (format 2 at [7,10) and [10,13)), both K-major,
-// N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t T_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+
+// CG = 1: one CTA per 128 x 128 tile, 3 stages of 32 KB, two CTAs per SM (one's epilogue overlaps the other's mainloop) -- small
+//         problems.  Its operand traffic (4 KB + 4 KB per 64-cycle MMA, 32 FLOP per L2 byte) bounds it near 350 TF/s.
+// CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile, like the bf16 engine's pair kernels: each CTA stages
+//         its 128 A rows and HALF of the W tile (128 of the 256 N rows), the leader issues 256 x 256 x 8 MMAs that read both CTAs'
+//         shared memory, each CTA's TMEM holds its 128 rows x 256 columns.  4 stages of 32 KB, one CTA per SM.
+template <int CG> struct TCfg {
+  static constexpr int BN = CG == 2 ? 256 : 128;         // tile width
+  static constexpr int W_ROWS = BN / CG;                 // W rows staged by ONE CTA
+  static constexpr int STAGES = CG == 2 ? 4 : 3;
+  static constexpr int A_BYTES = TBM * TBK * 4, B_BYTES = W_ROWS * TBK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int VEC_BYTES = 2 * BN * 4;           // bias | csum of the tile's columns, staged once by the epilogue warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + T_BAR_BYTES + VEC_BYTES + 1024;   // + alignment slack
+  static constexpr int MIN_CTAS = CG == 2 ? 1 : 2;
+  static_assert(4 * 32 * T_TURN_LD * 4 <= STAGES * STAGE_BYTES, "the epilogue turns its chunks through the idle ring");
+  // kind::tf32 instruction descriptor: D = f32 (bit 4), A = B = TF32 (format 2 at [7,10) and [10,13)), both K-major,
+  // N >> 3 at [17,23), M >> 4 at [24,29)
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TBM * CG) >> 4) << 24);
+};
 
 #ifndef DSHEG_EMU
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -38,6 +49,13 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 #endif
@@ -52,68 +70,84 @@ struct T32Params {
   float* out; int ldo; float* out2;
 };
 
-__global__ void __launch_bounds__(T_NUM_THREADS, 2)
+template <int CG>
+__global__ void __launch_bounds__(T_NUM_THREADS, TCfg<CG>::MIN_CTAS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmW, const T32Params p) {
+  using C = TCfg<CG>;
+  constexpr int BN = C::BN, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_BYTES = C::A_BYTES;
   DSHEG_TC_DYN_SMEM(smem_raw);
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B alignment
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + T_STAGES * T_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (T_STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * T_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * T_STAGES + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - smem_base));
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m_blk = blockIdx.x / p.tiles_n, n_blk = blockIdx.x % p.tiles_n;   // n fastest: concurrent CTAs share the A panel in L2
+  const int tile = blockIdx.x / CG;                                    // one tile per CTA (pair)
+  const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;   // n fastest: concurrent CTAs share the A panel in L2
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < T_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull_bar, 1);
     fence_mbarrier_init();
     prefetch_tensormap(&tmA0);
     prefetch_tensormap(&tmW);
   }
-  if (warp == 1) tmem_alloc<1, TBN>(tmem_slot);
+  if (warp == 1) tmem_alloc<CG, BN>(tmem_slot);   // the same warp id in both CTAs of a pair
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (each CTA fills its own smem; a pair credits all bytes to the leader's barrier) =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, seg = 0;
+      const uint32_t leader_full0 = CG == 2 ? mapa_rank(full_bar(0), 0) : 0u;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         while (kb >= p.seg_kb_start[seg + 1]) ++seg;
         mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * T_STAGE_BYTES, sb = sa + TA_BYTES;
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
         const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
-        mbar_arrive_expect_tx(full_bar(stage), T_STAGE_BYTES);
-        tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
         // W's K axis lays every segment out padded to 64 = two k-blocks, so k-block kb of the walk IS W's k-block kb
-        tma_load_2d(&tmW, full_bar(stage), sb, kb * TBK, n_blk * TBN);
-        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+        if (CG == 2) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          const uint32_t lb = leader_full0 + 8u * stage;
+          tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
+          tma_load_2d_pair(&tmW, lb, sb, kb * TBK, n_blk * BN + (int)rank * (BN / 2));
+        } else {
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
+          tma_load_2d(&tmW, full_bar(stage), sb, kb * TBK, n_blk * BN);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * T_STAGE_BYTES, sb = sa + TA_BYTES;
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
-        for (int k = 0; k < TBK / 8; ++k)   // 8 TF32 = 32 bytes per k-step: +2 in 16-byte descriptor units
-          tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), T_IDESC, (kb | k) != 0);
-        tc_commit(empty_bar(stage));   // frees the smem slot when the MMAs retire
-        if (++stage == T_STAGES) { stage = 0; phase ^= 1; }
+        for (int k = 0; k < TBK / 8; ++k) {   // 8 TF32 = 32 bytes per k-step: +2 in 16-byte descriptor units
+          if (CG == 2) tc_mma_tf32_pair(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+          else tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+        }
+        if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));   // frees the smem slot(s) when the MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(tfull_bar);            // accumulator complete -> epilogue
+      if (CG == 2) tc_commit_pair(tfull_bar); else tc_commit(tfull_bar);   // accumulator complete -> epilogue(s)
     }
     __syncwarp();
   } else {
@@ -124,12 +158,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const float mu = (ln && m_row < p.M) ? __ldg(p.mu + m_row) : 0.f;
     const float rstd = (ln && m_row < p.M) ? __ldg(p.rstd + m_row) : 1.f;
     float* turn = reinterpret_cast<float*>(gen_base) + (warp - 2) * 32 * T_TURN_LD;   // this warp's 32 x 36 staging rows (idle ring)
+    float* vbias = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + T_BAR_BYTES);   // [BN] bias, [BN] csum (outside the ring:
+    float* vcsum = vbias + BN;                                                                 //  staged while the mainloop runs)
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      const int n = n_blk * BN + i;
+      vbias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+      vcsum[i] = (ln && n < p.N) ? __ldg(p.csum + n) : 0.f;
+    }
+    epi_bar_sync<128>();
     const int tr = lane >> 3, tcg = lane & 7;              // coalesced layout: row 4 it + tr of the chunk, columns 4 tcg .. + 3
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int ch = 0; ch < TBN / 32; ++ch) {
-      const int n0 = n_blk * TBN + ch * 32;
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      const int n0 = n_blk * BN + ch * 32;
       if (n0 >= p.N) break;                                 // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ch * 32), r);
@@ -141,9 +183,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int n = n0 + j + e;
           float x = __uint_as_float(r[j + e]);
           if (n < p.N) {
-            if (ln) x = rstd * (x - mu * __ldg(p.csum + n));
-            if (p.bias) x += __ldg(p.bias + n);
-            x = apply_act(x, p.act);
+            if (ln) x = rstd * (x - mu * vcsum[ch * 32 + j + e]);
+            x = apply_act(x + vbias[ch * 32 + j + e], p.act);
           }
           v[e] = x;
         }
@@ -151,7 +192,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       __syncwarp();
       const int n = n0 + 4 * tcg;
-      const bool vec_ok = n + 3 < p.N;
+      const bool vec_ok = n + 3 < p.N && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rl = 4 * it + tr;
@@ -159,21 +200,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (m >= p.M || n >= p.N) continue;
         float4 x = *reinterpret_cast<const float4*>(turn + rl * T_TURN_LD + 4 * tcg);
         const size_t o = (size_t)m * p.ldo + n;
-        if (vec_ok && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0)) {
+        const int mr = p.res_mod > 0 ? m % p.res_mod : m;
+        if (vec_ok) {
           if (p.res) {
-            const int mr = p.res_mod > 0 ? m % p.res_mod : m;
             const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)mr * p.ldr + n));
             x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
           }
           *reinterpret_cast<float4*>(p.out + o) = x;
           if (p.out2) *reinterpret_cast<float4*>(p.out2 + o) = x;
-        } else {
-          const float xs[4] = {x.x, x.y, x.z, x.w};
-          for (int e = 0; e < 4 && n + e < p.N; ++e) {
-            float y = xs[e];
-            if (p.res) { const int mr = p.res_mod > 0 ? m % p.res_mod : m; y += p.res[(size_t)mr * p.ldr + n + e]; }
-            p.out[o + e] = y;
-            if (p.out2) p.out2[o + e] = y;
+        } else {   // ragged N / unaligned rows: element by element
+          if (p.res) {
+            x.x += p.res[(size_t)mr * p.ldr + n];
+            if (n + 1 < p.N) x.y += p.res[(size_t)mr * p.ldr + n + 1];
+            if (n + 2 < p.N) x.z += p.res[(size_t)mr * p.ldr + n + 2];
+            if (n + 3 < p.N) x.w += p.res[(size_t)mr * p.ldr + n + 3];
+          }
+          p.out[o] = x.x;
+          if (n + 1 < p.N) p.out[o + 1] = x.y;
+          if (n + 2 < p.N) p.out[o + 2] = x.z;
+          if (n + 3 < p.N) p.out[o + 3] = x.w;
+          if (p.out2) {
+            p.out2[o] = x.x;
+            if (n + 1 < p.N) p.out2[o + 1] = x.y;
+            if (n + 2 < p.N) p.out2[o + 2] = x.z;
+            if (n + 3 < p.N) p.out2[o + 3] = x.w;
           }
         }
       }
@@ -182,9 +232,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's smem / signal its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<1, TBN>(tmem_base);
+    tmem_dealloc<CG, BN>(tmem_base);
   }
 }
 
@@ -224,13 +275,31 @@ inline bool tf32_eligible(const GemmDesc& d) {
 }
 
 // A, W, residual, out: fp32 (the "tf32" mode keeps every activation in fp32); residual / out may be fp32 by type or by flag
-inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::string* err) {
+template <int CG>
+inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params& p, int tiles, cudaStream_t st) {
+  auto kern = gemm_tf32_kernel<CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<CG>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles * CG); cfg.blockDim = dim3(T_NUM_THREADS); cfg.dynamicSmemBytes = TCfg<CG>::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+}
+
+// A, W, residual, out: fp32 (the "tf32" mode keeps every activation in fp32); residual / out may be fp32 by type or by flag.
+// cg_force: 0 = automatic (CTA pairs for M >= 2048 and N >= 256), 1 / 2 = force
+inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::string* err, int cg_force = 0) {
+  const int cg = cg_force ? cg_force : ((d.M >= 2048 && d.N >= 256) ? 2 : 1);
+  const int bn = cg == 2 ? 256 : 128;
   T32Params p{};
   p.M = d.M; p.N = d.N; p.nseg = d.nseg;
   CUtensorMap maps[5];
@@ -247,14 +316,13 @@ inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::str
   for (int s = d.nseg + 1; s < 5; ++s) p.seg_kb_start[s] = 1 << 30;
   p.num_kb = koff / TBK;
   for (int s = d.nseg; s < 4; ++s) maps[s] = maps[0];
-  if (!make_tmap_f32(&maps[4], d.w, d.N, d.Kp, d.Kp, TBN, err)) return cudaErrorInvalidValue;
-  p.tiles_n = (d.N + TBN - 1) / TBN;
-  const int tiles_m = (d.M + TBM - 1) / TBM;
+  if (!make_tmap_f32(&maps[4], d.w, d.N, d.Kp, d.Kp, bn / cg, err)) return cudaErrorInvalidValue;
+  p.tiles_n = (d.N + bn - 1) / bn;
+  const int tiles_m = (d.M + TBM * cg - 1) / (TBM * cg);
   p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd; p.act = d.act;
   p.res = reinterpret_cast<const float*>(d.res); p.ldr = d.ldr; p.res_mod = d.res_mod;
   p.out = reinterpret_cast<float*>(d.out); p.ldo = d.ldo; p.out2 = reinterpret_cast<float*>(d.out2);
-  gemm_tf32_kernel<<<tiles_m * p.tiles_n, T_NUM_THREADS, T_SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
-  return cudaGetLastError();
+  return cg == 2 ? launch_tf32_variant<2>(maps, p, tiles_m * p.tiles_n, st) : launch_tf32_variant<1>(maps, p, tiles_m * p.tiles_n, st);
 }
 #endif  // DSHEG_EMU
 

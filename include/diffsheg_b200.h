@@ -171,6 +171,11 @@ int dsheg_bench_gemm(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t bn, 
 int dsheg_op_attention(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
                        float* z, int32_t Bn, int32_t T, int32_t D, int32_t H, void* stream);
 
+/* Same op as the tf32 mode runs it (attn_tf32.cuh: fp32 arrays, heads of 64; the two products on mma.sync TF32, softmaxes, sums and
+ * LayerNorm exact fp32). */
+int dsheg_op_attention_tf32(const float* qkv, const float* ln_g, const float* ln_b, const float* scale_shift,
+                            float* z, int32_t Bn, int32_t T, int32_t D, int32_t H, void* stream);
+
 /* Same op on the bf16 fast path (D = 512, 8 heads, T <= 96): qkv and z are bf16 arrays.
  * numerators = 1: the engine's default kernel (attn_tma.cuh: persistent, TMA-staged); the Q and K columns of qkv already hold the
  *                 softmax NUMERATORS exp(value - shift) that the ACT_EXPO epilogue of the QKV GEMM writes (any per-(row, head)

@@ -176,6 +176,28 @@ def test_op_attention(L, Bn, T, D, H):
     assert relmax(z, want) < 2e-5
 
 
+@pytest.mark.parametrize("Bn,T,H", [(3, 88, 8), (2, 34, 8), (2, 84, 8), (1, 30, 8), (5, 96, 8), (2, 16, 8), (1, 7, 8), (2, 100, 8), (2, 40, 2), (300, 88, 8)])
+def test_op_attention_tf32_tensor_core(L, Bn, T, H):
+    """attn_tf32 (the tf32 mode's attention: fp32 activations, the two products on TF32 mma.sync) vs fp64."""
+    torch.manual_seed(T)
+    D = 64 * H
+    qkv = 1.5 * torch.randn(Bn, T, 3 * D, device="cuda")
+    g, b = 1 + 0.1 * torch.randn(D, device="cuda"), 0.1 * torch.randn(D, device="cuda")
+    ss = 0.5 * torch.randn(Bn, 2 * D, device="cuda")
+    z = torch.full((Bn, T, D), float("nan"), device="cuda")
+    assert L.dsheg_op_attention_tf32(P(qkv), P(g), P(b), P(ss), P(z), Bn, T, D, H, S()) == 0, L.dsheg_last_error(None)
+    q, k, v = qkv.double().split(D, dim=-1)
+    q = torch.softmax(q.view(Bn, T, H, -1), dim=-1)
+    k = torch.softmax(k.view(Bn, T, H, -1), dim=1)
+    att = torch.einsum("bnhd,bnhl->bhdl", k, v.view(Bn, T, H, -1))
+    y = torch.einsum("bnhd,bhdl->bnhl", q, att).reshape(Bn, T, D)
+    yn = torch.nn.functional.layer_norm(y, (D,), g.double(), b.double(), 1e-5)
+    want = torch.nn.functional.silu(yn * (1 + ss[:, None, :D].double()) + ss[:, None, D:].double())
+    err = relmax(z, want)
+    print(f"\n[parity] attention tf32 tensor-core Bn{Bn} T{T} H{H}: relmax={err:.3e}")
+    assert torch.isfinite(z).all() and err < 3e-3    # TF32 operands (2^-11 each) through two products and a LayerNorm
+
+
 @pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (2, 84), (1, 30), (5, 96), (2, 16), (1, 7)])
 def test_op_attention_bf16_tensor_core(L, Bn, T):
     """attn_v3 (plain q, k, v: the per-layer fallback) vs an fp64 evaluation of the same bf16 inputs (bf16 output rounding: 2^-8)."""
