@@ -351,17 +351,18 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 #ifndef DSHEG_EMU
 // (column, frame, sample) view of a bf16 tensor [n_samples * T, cols]; box = 64 columns x Tpad frames of one sample.
-inline bool make_frames_tmap(CUtensorMap* map, const void* base, int cols, int n_samples, int T, std::string* err) {
-  struct Key { const void* p; int c, n, t; bool operator==(const Key& o) const { return p == o.p && c == o.c && n == o.n && t == o.t; } };
-  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.t << 48) ^ ((size_t)k.c << 32); } };
+// box_frames: height of the box in frames (default: all Tpad frames of the sample; attn_ws.cuh loads Q' by row halves).
+inline bool make_frames_tmap(CUtensorMap* map, const void* base, int cols, int n_samples, int T, std::string* err, int box_frames = -1) {
+  struct Key { const void* p; int c, n, t, b; bool operator==(const Key& o) const { return p == o.p && c == o.c && n == o.n && t == o.t && b == o.b; } };
+  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.t << 48) ^ ((size_t)k.c << 32) ^ ((size_t)k.b << 56); } };
   static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
-  const Key k{base, cols, n_samples, T};
+  const Key k{base, cols, n_samples, T, box_frames};
   auto it = cache.find(k);
   if (it != cache.end()) { *map = it->second; return true; }
   tc::EncodeTiledFn fn = tc::get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (cols % 8)) { *err = "attention operand not 16-byte aligned"; return false; }
-  const int Tpad = (T + 15) / 16 * 16;
+  const int Tpad = box_frames > 0 ? box_frames : (T + 15) / 16 * 16;
   cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)n_samples};
   cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)T * cols * 2};
   cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)Tpad, 1};

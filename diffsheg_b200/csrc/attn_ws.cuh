@@ -1,0 +1,387 @@
+// Linear-attention core + StylizationBlock prologue, bf16 (D = 512, 8 heads of 64, T <= 96) -- PERSISTENT, TMA-STAGED, WARP-SPECIALISED.
+//
+// Mathematics (reference transformer.py:112-130 + :86-97), input contract = the ACT_EXPO epilogue of the QKV GEMM (gemm_tc.cuh):
+// the Q and K columns hold exp(value - static shift) (softmax is shift-invariant; pack.py:expo_shift proves the range), V is plain:
+//   A = K'^T V / colsum(K')  [64 x 64 per head]     Y = Q' A / rowsum(Q')     z = SiLU(LN_512(Y) * (1 + scale) + shift)
+//
+// Why this shape.  attn_tma.cuh (round 2's first TMA kernel) has all 16 compute warps of the one CTA an SM can hold walk through the
+// same phases together -- A^T, Y, a CTA-wide barrier, the LayerNorm pass -- so the tensor pipe idles during LayerNorm, the FP32 / MUFU
+// pipes idle during the products, and every dependency stall is exposed at 4 warps per scheduler (ncu: issue slots 34 % busy, 0.42 of
+// the copy peak in the sampling loop).  Two samples cannot be resident (Y of one sample is 96 KB of shared memory).  Here the phases
+// belong to DIFFERENT warps working on DIFFERENT samples, and Y never exists in shared memory:
+//   * 4 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep) into the normalised bf16 A^T of that
+//     head in one of 8 per-head slots (64 KB).  They run up to a whole sample ahead of the Y warps; a slot is rewritten as soon as
+//     its two readers have finished the head (mbarrier pair per head).
+//   * 16 "Y warps" = 8 heads x 2 row halves.  Warp (h, half) owns head h of up to three 16-frame tiles: its Q' box (48 frames x 64
+//     columns, 6 KB) arrives by a TMA load the warp issues ITSELF for the next sample the moment its last product has consumed the
+//     current one, so the reload has the whole LayerNorm part to land.  Per tile: Y = Q' A on mma.sync from ldmatrix fragments (A^T
+//     rows are stored permuted so that a thread's 16 output columns are two contiguous runs of 8), row sums on the tensor core, and
+//     the per-row LayerNorm partials (sum, sum of squares over the head's 64 columns) straight from the fp32 accumulators into a
+//     [row][head] table.  Finished tiles are PARKED IN TENSOR MEMORY (tcgen05.st, thread-private columns: TMEM as a 96 KB register
+//     spill space for mma.sync warps; micro-benchmark scripts/ubench), which frees the A^T slot after the last product instead of
+//     after the LayerNorm part.
+//   * one named barrier per row half and sample publishes the partials; then every warp normalises, modulates and applies SiLU to
+//     its own tiles IN REGISTERS (fp32 Y, never rounded to bf16 before the LayerNorm) and writes z with 16-byte stores: a store
+//     instruction covers 64 contiguous bytes of 8 rows.  No CTA-wide barrier, no LayerNorm pass over shared memory, no shuffles
+//     beyond one quad reduction per tile.
+// Issue slots per sample drop from 37 k to about 20 k warp-instructions and the three pipes (tensor: A warps + Y products; FP32 /
+// MUFU: LayerNorm parts; TMA) overlap because the warps drift apart instead of marching in step.
+// HBM traffic: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample (unchanged).
+#pragma once
+#include "attn_tma.cuh"
+
+namespace dsheg {
+namespace aws {
+
+using av3::TP; using av3::HD; using av3::D; using av3::TILE_BYTES;
+using av3::pack2; using av3::swz;
+using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::tanh_approx; using prims::rcp_approx;
+using prims::ffma2; using prims::fadd2; using prims::fmul2;
+using atm::BF2_ONES;
+
+constexpr int NH = 8;                          // heads
+constexpr int NYW = 2 * NH;                    // Y warps: head = warp & 7, row half = warp >> 3
+constexpr int NAW = 4;                         // A warps (the LAST warps of the CTA)
+constexpr int NTHREADS = 32 * (NYW + NAW);
+constexpr int MH = TP / 32;                    // 16-frame tiles per row half (3)
+constexpr int QBOX_BYTES = MH * 16 * 128;      // one Y warp's Q' box: 48 frames x 64 columns
+constexpr int A_BYTES = HD * 128;              // one head's A^T (64 x 64 bf16)
+constexpr int NST = 4;                         // K' / V ring slots = two heads
+constexpr int Q_OFF = 0;                                      // [NYW] Q' boxes
+constexpr int A_OFF = Q_OFF + NYW * QBOX_BYTES;               // [NH] A^T slots
+constexpr int RING_OFF = A_OFF + NH * A_BYTES;                // [NST] K' / V tiles
+constexpr int STAT_OFF = RING_OFF + NST * TILE_BYTES;         // [sample parity][half][tile][row 16][head 8] float2 (sum, sumsq)
+constexpr int STAT_BYTES = 2 * 2 * MH * 16 * NH * 8;
+constexpr int CSUM_OFF = STAT_OFF + STAT_BYTES;               // [head parity][64] column sums of K'
+constexpr int BAR_OFF = CSUM_OFF + 2 * HD * 4;                // kv_full[NST] a_full[NH] a_empty[NH] q_full[NYW]
+constexpr int NBAR = NST + 2 * NH + NYW;
+constexpr int TMEM_SLOT_OFF = BAR_OFF + NBAR * 8;
+constexpr int SMEM_BYTES = ((TMEM_SLOT_OFF + 4 + 127) / 128) * 128;
+constexpr int TMEM_COLS = 256;                 // 4 Y warps per lane quadrant x (MH - 1) parked tiles x 32 columns
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(Q_OFF % 1024 == 0 && QBOX_BYTES % 1024 == 0 && A_OFF % 1024 == 0 && A_BYTES % 1024 == 0 && RING_OFF % 1024 == 0 && TILE_BYTES % 1024 == 0,
+              "SWIZZLE_128B tiles start on 1024-byte boundaries");
+static_assert((NYW / 4) * (MH - 1) * 32 <= TMEM_COLS, "parking space");
+
+__device__ __forceinline__ void half_sync(int half) { prims::named_bar_sync<32 * NH>(1 + half); }     // ids 1, 2: the 8 Y warps of a row half
+__device__ __forceinline__ void agroup_sync() { prims::named_bar_sync<32 * NAW>(3); }                 // id 3: the A warps
+
+// shared-memory row of A^T that holds output column l of the head: n-tile nt = 4 (l >> 5) + ((l >> 1) & 3), row 2 ((l >> 3) & 3) + (l & 1)
+// of the tile -- thread q of an mma quad then owns l = 32 a + 8 q + {0 .. 7}, a = 0, 1: two 16-byte runs of the output row.
+__device__ __forceinline__ int a_row(int l) { return 8 * (4 * (l >> 5) + ((l >> 1) & 3)) + 2 * ((l >> 3) & 3) + (l & 1); }
+
+// Self-attention: tmQ and tmKV both view the fused qkv tensor [rows, 1536] (boxes of 16 mh and 16 n_kt frames), kcol = 512, vcol = 1024.
+// Cross-attention (transformer.py:133-166): tmQ views q' [n_samples * T, 512], tmKV views [n_samples * Tkv, 1024] (k' | v), kcol = 0, vcol = 512.
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int kcol, int vcol,
+               bf16* __restrict__ z, int n_samples, int T, int Tkv, int B,
+               const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+  DSHEG_PDL_ENTER();
+  DSHEG_TC_DYN_SMEM(sm);
+  const uint32_t sbase = tc::smem_u32(sm);
+  if (sbase & 1023u) tc::trap();   // SWIZZLE_128B tiles: the dynamic smem base must be 1024-byte aligned
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_mt = (T + 15) >> 4;            // 16-frame tiles of Q' / Y that contain valid frames
+  const int n_kt = (Tkv + 15) >> 4;          // ... of K' / V
+  const int mh = (n_mt + 1) >> 1;            // tiles of the first row half = height of a Q' box in tiles
+  const uint32_t q_tx = (uint32_t)mh * 16u * 128u;      // bytes one TMA box delivers (frames beyond T arrive as zeros)
+  const uint32_t kv_tx = (uint32_t)n_kt * 16u * 128u;
+  auto kv_full = [&](int s) { return sbase + BAR_OFF + 8u * s; };
+  auto a_full = [&](int h) { return sbase + BAR_OFF + 8u * (NST + h); };
+  auto a_empty = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NH + h); };
+  auto q_full = [&](int w) { return sbase + BAR_OFF + 8u * (NST + 2 * NH + w); };
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) tc::mbar_init(kv_full(s), 1);
+    for (int h = 0; h < NH; ++h) { tc::mbar_init(a_full(h), NAW); tc::mbar_init(a_empty(h), 2); }
+    for (int w = 0; w < NYW; ++w) tc::mbar_init(q_full(w), 1);
+    tc::fence_mbarrier_init();
+  }
+  if (warp == NYW) tc::tmem_alloc<1, TMEM_COLS>(sbase + TMEM_SLOT_OFF);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(sm + TMEM_SLOT_OFF);
+  const int n_iter = ((int)blockIdx.x < n_samples) ? (n_samples - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // samples of this CTA
+  const int g = lane >> 2, q = lane & 3;           // mma fragment coordinates
+  const int mat = lane >> 3, rr = lane & 7;        // ldmatrix: matrix index / row inside the matrix
+
+  if (warp < NYW) {
+    // ========================================================== Y warps ==========================================================
+    const int h = warp & 7, half = warp >> 3;
+    const int mt0 = half * mh;                                   // first tile of this warp
+    const int nu = n_mt - mt0 < mh ? (n_mt - mt0 > 0 ? n_mt - mt0 : 0) : mh;   // tiles of this warp (0 .. 3; the same for the 8 warps of a half)
+    const uint32_t qb_addr = sbase + Q_OFF + warp * QBOX_BYTES, as_addr = sbase + A_OFF + h * A_BYTES;
+    const uint32_t park = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * (MH - 1) * 32);
+    if (nu > 0 && lane == 0 && n_iter > 0) {
+      tc::prefetch_tensormap(&tmQ);
+      tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
+      tc::tma_load_3d(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, (int)blockIdx.x);
+    }
+    const int colA = h * HD + 8 * q;     // this thread's output columns: [colA, colA + 8) and [colA + 32, colA + 40)
+    for (int i = 0; i < n_iter; ++i) {
+      const int smp = (int)blockIdx.x + i * (int)gridDim.x;
+      const uint32_t par = (uint32_t)(i & 1);
+      float2* const stat = reinterpret_cast<float2*>(sm + STAT_OFF) + (size_t)((par * 2 + half) * MH) * 16 * NH;
+      if (nu > 0) tc::mbar_wait(q_full(warp), par);
+      tc::mbar_wait(a_full(h), par);
+      float y[8][4];
+#pragma unroll 1
+      for (int u = 0; u < nu; ++u) {
+        // ---- Y[t][l] = Q'[t][:] . A: the 16 x 64 tile of (tile u, head h); row sums of Q' on the tensor core (Q' . ones)
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int kd = 0; kd < 4; ++kd)   // A fragments: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15) of the 16 x 16 block
+          ldsm_x4(qb_addr + swz(u * 16 + rr + ((mat & 1) << 3), 2 * kd + (mat >> 1)), pa[kd][0], pa[kd][1], pa[kd][2], pa[kd][3]);
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};   // rs: rows g, g + 8 in [0], [2]
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f; }
+#pragma unroll
+        for (int kd = 0; kd < 4; ++kd) {
+          mma_bf16(rs, pa[kd], BF2_ONES, BF2_ONES);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {   // B fragments of two n-tiles per ldmatrix.x4 from the (row-permuted) A^T[l][d]
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(as_addr + swz(16 * np + rr + ((mat >> 1) << 3), 2 * kd + (mat & 1)), b0, b1, b2, b3);
+            mma_bf16(y[2 * np], pa[kd], b0, b1);
+            mma_bf16(y[2 * np + 1], pa[kd], b2, b3);
+          }
+        }
+        if (u == nu - 1) {
+          // the last product of this sample has consumed every Q' and A^T fragment (the mma results depend on them): hand the A^T
+          // slot back to the A warps and fetch the next sample's Q' box into this warp's own (now dead, only ever read) box
+          __syncwarp();
+          if (lane == 0) {
+            tc::mbar_arrive(a_empty(h));
+            if (i + 1 < n_iter) {
+              tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
+              tc::tma_load_3d(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp + (int)gridDim.x);
+            }
+          }
+        }
+        const int ra = (mt0 + u) * 16 + g, rb = ra + 8;
+        // zero-filled Q' rows beyond T have zero sums: keep their Y rows at 0
+        const float r0 = ra >= T ? 0.f : rcp_approx(rs[0]), r1 = rb >= T ? 0.f : rcp_approx(rs[2]);
+        const float2 r02 = make_float2(r0, r0), r12 = make_float2(r1, r1);
+        float2 sa = make_float2(0.f, 0.f), sb = sa, qa = sa, qb = sa;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float2 ya = fmul2(make_float2(y[nt][0], y[nt][1]), r02), yb = fmul2(make_float2(y[nt][2], y[nt][3]), r12);
+          y[nt][0] = ya.x; y[nt][1] = ya.y; y[nt][2] = yb.x; y[nt][3] = yb.y;
+          sa = fadd2(sa, ya); qa = ffma2(ya, ya, qa);
+          sb = fadd2(sb, yb); qb = ffma2(yb, yb, qb);
+        }
+        float s0 = sa.x + sa.y, q0 = qa.x + qa.y, s1 = sb.x + sb.y, q1 = qb.x + qb.y;
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {   // the 4 lanes of a quad hold the 64 columns of rows g / g + 8
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        }
+        if (q == 0) {
+          stat[(u * 16 + g) * NH + h] = make_float2(s0, q0);
+          stat[(u * 16 + g + 8) * NH + h] = make_float2(s1, q1);
+        }
+        if (u < nu - 1) {   // park the tile in tensor memory until the LayerNorm part
+          uint32_t pk[32];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            pk[4 * nt] = __float_as_uint(y[nt][0]); pk[4 * nt + 1] = __float_as_uint(y[nt][1]);
+            pk[4 * nt + 2] = __float_as_uint(y[nt][2]); pk[4 * nt + 3] = __float_as_uint(y[nt][3]);
+          }
+          tc::tmem_st32(park + (uint32_t)(u * 32), pk);
+        }
+      }
+      if (nu == 0) {   // a row half without frames (T <= 16 ...): keep the A^T hand-shake in step
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_empty(h));
+        continue;
+      }
+      // ---- this thread's LayerNorm / modulation constants for the sample:  t = ((v - mean) rstd g + b)(1 + scale) + shift = 2 ((v - mean) rstd G + Bc),
+      //      SiLU(t) = h + h tanh(h) with h = t / 2.  Loaded before the barrier so that the L2 round trip overlaps the wait.
+      float2 G[8], Bc[8];
+      {
+        const float* sc = ss + (size_t)(smp % B) * ss_ld;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int col = colA + 32 * a;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + col + 4 * e)), t4 = __ldg(reinterpret_cast<const float4*>(sc + D + col + 4 * e));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + col + 4 * e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col + 4 * e));
+            const float sx = 1.f + s4.x, sy = 1.f + s4.y, sz = 1.f + s4.z, sw = 1.f + s4.w;
+            G[4 * a + 2 * e] = make_float2(0.5f * g4.x * sx, 0.5f * g4.y * sy);
+            G[4 * a + 2 * e + 1] = make_float2(0.5f * g4.z * sz, 0.5f * g4.w * sw);
+            Bc[4 * a + 2 * e] = make_float2(0.5f * fmaf(b4.x, sx, t4.x), 0.5f * fmaf(b4.y, sy, t4.y));
+            Bc[4 * a + 2 * e + 1] = make_float2(0.5f * fmaf(b4.z, sz, t4.z), 0.5f * fmaf(b4.w, sw, t4.w));
+          }
+        }
+      }
+      half_sync(half);   // the partials of all 8 heads of this half's rows are in the table
+      const size_t row0 = (size_t)smp * T;
+#pragma unroll 1
+      for (int u = nu - 1; u >= 0; --u) {   // the last tile is still in registers; the others come back from tensor memory
+        if (u < nu - 1) {
+          uint32_t pk[32];
+          tc::tmem_ld32(park + (uint32_t)(u * 32), pk);
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            y[nt][0] = __uint_as_float(pk[4 * nt]); y[nt][1] = __uint_as_float(pk[4 * nt + 1]);
+            y[nt][2] = __uint_as_float(pk[4 * nt + 2]); y[nt][3] = __uint_as_float(pk[4 * nt + 3]);
+          }
+        }
+        float2 rsd[2], nmr[2];   // per row: (rstd, rstd), (-mean rstd, -mean rstd)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float4* sp = reinterpret_cast<const float4*>(stat + (u * 16 + g + 8 * r) * NH);
+          const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];   // heads (0,1) (2,3) (4,5) (6,7): (sum, sumsq) pairs
+          const float s = ((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z));
+          const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
+          const float mean = s * (1.f / D);
+          // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
+          const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+          rsd[r] = make_float2(rstd, rstd); nmr[r] = make_float2(-mean * rstd, -mean * rstd);
+        }
+        const int ra = (mt0 + u) * 16 + g;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          uint32_t o[8];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const float2 hv = ffma2(ffma2(make_float2(y[nt][2 * r], y[nt][2 * r + 1]), rsd[r], nmr[r]), G[nt], Bc[nt]);
+            const float2 v = ffma2(hv, make_float2(tanh_approx(hv.x), tanh_approx(hv.y)), hv);
+            o[nt] = pack2(v.x, v.y);
+          }
+          const int t = ra + 8 * r;
+          if (t < T) {
+            bf16* dst = z + (row0 + t) * (size_t)D + colA;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dst + 32) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+    }
+  } else {
+    // ========================================================== A warps ==========================================================
+    const int wq = warp - NYW;
+    const int lq = wq & 1, dq = wq >> 1;      // this warp's 32 x 32 quadrant of A^T[l][d]: l-half lq, d-half dq
+    const int n_heads = n_iter * NH;          // (sample, head) units of this CTA, in order
+    auto issue = [&](int hc) {                // lane 0 of the first A warp: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
+      const int smp = (int)blockIdx.x + (hc >> 3) * (int)gridDim.x, hh = hc & 7, s0 = 2 * (hc & 1);
+      tc::mbar_arrive_expect_tx(kv_full(s0), kv_tx);
+      tc::tma_load_3d(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp);
+      tc::mbar_arrive_expect_tx(kv_full(s0 + 1), kv_tx);
+      tc::tma_load_3d(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp);
+      // pull the same head of the NEXT sample from HBM into L2 (the ring itself is only two heads deep: it then covers L2 latency, not HBM latency)
+      if (smp + (int)gridDim.x < n_samples) {
+        tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, 0, smp + (int)gridDim.x);
+        tc::tma_prefetch_l2_3d(&tmKV, vcol + hh * HD, 0, smp + (int)gridDim.x);
+      }
+    };
+    if (wq == 0 && lane == 0) {
+      tc::prefetch_tensormap(&tmKV);
+      for (int hc = 0; hc < 2 && hc < n_heads; ++hc) issue(hc);
+    }
+    const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
+#pragma unroll 1
+    for (int hc = 0; hc < n_heads; ++hc) {
+      const int hh = hc & 7, s0 = 2 * (hc & 1);
+      const uint32_t par = (uint32_t)((hc >> 1) & 1);
+      const uint32_t ks_addr = sbase + RING_OFF + s0 * TILE_BYTES, vs_addr = ks_addr + TILE_BYTES;
+      float* const colsum = reinterpret_cast<float*>(sm + CSUM_OFF) + (hc & 1) * HD;
+      tc::mbar_wait(kv_full(s0), par);
+      tc::mbar_wait(kv_full(s0 + 1), par);
+      // ---- A^T[l][d] = sum_t V[t][l] K'[t][d]; on the same K' fragments the column sums of K' for d = 32 dq + 16 lq .. + 15 (ones . K')
+      float acc[2][4][4], cs[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
+      cs[0][0] = cs[0][1] = cs[0][2] = cs[0][3] = cs[1][0] = cs[1][1] = cs[1][2] = cs[1][3] = 0.f;
+#pragma unroll 2
+      for (int kt = 0; kt < n_kt; ++kt) {   // 16 frames per k-step
+        uint32_t a0[4], a1[4];
+        {
+          const int r = kt * 16 + rr + ((mat >> 1) << 3);
+          ldsm_x4_trans(vs_addr + swz(r, 4 * lq + (mat & 1)), a0[0], a0[1], a0[2], a0[3]);
+          ldsm_x4_trans(vs_addr + swz(r, 4 * lq + 2 + (mat & 1)), a1[0], a1[1], a1[2], a1[3]);
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {    // two d n-tiles per ldmatrix.x4
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(ks_addr + swz(kt * 16 + rr + ((mat & 1) << 3), 4 * dq + 2 * np + (mat >> 1)), b0, b1, b2, b3);
+          mma_bf16(acc[0][2 * np], a0, b0, b1);
+          mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
+          mma_bf16(acc[1][2 * np], a1, b0, b1);
+          mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
+          if (np == lq) {   // warp-uniform: the two warps of a d-half share its column sums
+            mma_bf16(cs[0], ones, b0, b1);
+            mma_bf16(cs[1], ones, b2, b3);
+          }
+        }
+      }
+      if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
+        *reinterpret_cast<float2*>(colsum + 32 * dq + 16 * lq + 2 * q) = make_float2(cs[0][0], cs[0][1]);
+        *reinterpret_cast<float2*>(colsum + 32 * dq + 16 * lq + 8 + 2 * q) = make_float2(cs[1][0], cs[1][1]);
+      }
+      agroup_sync();   // column sums published; all four warps are done reading this unit's K' and V tiles
+      if (wq == 0 && lane == 0 && hc + 2 < n_heads) issue(hc + 2);   // refill the two slots (only ever read: no proxy fence needed)
+      tc::mbar_wait(a_empty(hh), (uint32_t)(((hc >> 3) & 1) ^ 1));   // both readers of the previous sample's A^T of this head are done
+      uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
+      const float* csum = colsum + 32 * dq;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 s2 = *reinterpret_cast<const float2*>(csum + 8 * nt + 2 * q);
+        const float2 inv = make_float2(rcp_approx(s2.x), rcp_approx(s2.y));
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const int l = 32 * lq + 16 * mi + g;
+          const float2 lo = fmul2(make_float2(acc[mi][nt][0], acc[mi][nt][1]), inv), hi = fmul2(make_float2(acc[mi][nt][2], acc[mi][nt][3]), inv);
+          *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l), 4 * dq + nt) + q * 4) = pack2(lo.x, lo.y);
+          *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l + 8), 4 * dq + nt) + q * 4) = pack2(hi.x, hi.y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's quadrant of A^T is written
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == NYW) tc::tmem_dealloc<1, TMEM_COLS>(tmem_base);
+}
+
+#ifndef DSHEG_EMU
+inline cudaError_t launch_attn_ws_qkv(const CUtensorMap& mq, const CUtensorMap& mkv, int kcol, int vcol, bf16* z, int n_samples, int T, int Tkv,
+                                      int ssB, const float* ln_g, const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = n_samples < num_sms ? n_samples : num_sms;
+  DSHEG_LAUNCH(attn_ws_kernel, grid, NTHREADS, SMEM_BYTES, st, mq, mkv, kcol, vcol, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld);
+  return cudaGetLastError();
+}
+
+inline int q_box_frames(int T) { return 16 * ((((T + 15) >> 4) + 1) >> 1); }
+
+// self-attention on the fused projection qkv [n_samples * T, 1536] (q' | k' | v)
+inline cudaError_t launch_attn_ws(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
+                                  const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+  CUtensorMap mq, mkv;
+  if (!atm::make_frames_tmap(&mq, qkv, 3 * D, n_samples, T, err, q_box_frames(T)) || !atm::make_frames_tmap(&mkv, qkv, 3 * D, n_samples, T, err))
+    return cudaErrorInvalidValue;
+  return launch_attn_ws_qkv(mq, mkv, D, 2 * D, z, n_samples, T, T, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
+}
+
+// cross-attention (transformer.py:133-166): q' [n_samples * T, 512] from the motion stream, kv [n_samples * Tkv, 1024] (k' | v) from the conditioning
+inline cudaError_t launch_cross_attn_ws(const bf16* q, const bf16* kv, bf16* z, int n_samples, int T, int Tkv, int ssB, const float* ln_g,
+                                        const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+  CUtensorMap mq, mkv;
+  if (!atm::make_frames_tmap(&mq, q, D, n_samples, T, err, q_box_frames(T)) || !atm::make_frames_tmap(&mkv, kv, 2 * D, n_samples, Tkv, err))
+    return cudaErrorInvalidValue;
+  return launch_attn_ws_qkv(mq, mkv, 0, D, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
+}
+#endif  // DSHEG_EMU
+
+}  // namespace aws
+}  // namespace dsheg

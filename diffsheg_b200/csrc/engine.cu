@@ -15,6 +15,7 @@
 #include "attn_v3.cuh"
 #include "attn_small.cuh"
 #include "attn_tma.cuh"
+#include "attn_ws.cuh"
 #include "attn_tf32.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -357,7 +358,7 @@ struct Runner {
     // Softmax numerators from the epilogue (tr:122-123): Q and K leave the QKV GEMM as exp(v - static shift) for the layers whose
     // packed weights carry provably safe shifts (pack.py:expo_shift); attn_tma consumes them.  Other layers: plain epilogue + attn_v3.
     const bool tc_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP;
-    const bool kpre = tc_attn && h->attn_mode == 2 && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
+    const bool kpre = tc_attn && h->attn_mode >= 2 && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
     if (kpre) { gq.act = ACT_EXPO; gq.eshift = L.qkv_eshift; gq.expo_cols = 2 * D; }
     if (gemm(gq, L.qkv, "qkv")) return 1;
     // K9 + K10 prologue: linear attention, then LN * (1+scale) + shift, SiLU
@@ -367,8 +368,10 @@ struct Runner {
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
     if (kpre) {
       std::string terr;
-      const cudaError_t le = atm::launch_attn_tma((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr);
-      if (le != cudaSuccess) return fail(h, std::string("attn_tma launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
+      const cudaError_t le = h->attn_mode == 3
+          ? aws::launch_attn_ws((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr)
+          : atm::launch_attn_tma((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr);
+      if (le != cudaSuccess) return fail(h, std::string("attn_tma / attn_ws launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
     } else if (tc_attn && h->attn_mode >= 1) {   // no provably safe shifts for this layer (or DSHEG_ATTN=v3 / DSHEG_EXPO=0): softmaxes in the kernel
       DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, float>::value && HD == 64 && h->cfg.precision == DSHEG_PREC_TF32 && h->gemm_engine == 1) {
@@ -603,6 +606,7 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   const char* att = getenv("DSHEG_ATTN");
   if (att && !strcmp(att, "v1")) h->attn_mode = 0;
   if (att && !strcmp(att, "v3")) h->attn_mode = 1;
+  if (att && !strcmp(att, "ws")) h->attn_mode = 3;
   const char* aa = getenv("DSHEG_ATTN_AUD");
   if (aa && !strcmp(aa, "0")) h->attn_aud = 0;
   const char* fl = getenv("DSHEG_FUSE_LNMS");
@@ -1146,7 +1150,10 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t le = atm::launch_attn_tma((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr);
+    const char* att = getenv("DSHEG_ATTN");
+    cudaError_t le = (att && !strcmp(att, "ws"))
+        ? aws::launch_attn_ws((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr)
+        : atm::launch_attn_tma((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr);
     if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (tma): ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
   } else {            // plain q, k, v: softmaxes inside the kernel (the per-layer fallback)
     cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
@@ -1167,8 +1174,11 @@ int dsheg_op_cross_attention_bf16(const void* q, const void* kv, const float* ln
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t le = atm::launch_cross_attn_tma((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms,
-                                              (cudaStream_t)stream, &terr);
+  const char* att = getenv("DSHEG_ATTN");
+  cudaError_t le = (att && !strcmp(att, "ws"))
+      ? aws::launch_cross_attn_ws((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr)
+      : atm::launch_cross_attn_tma((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms,
+                                   (cudaStream_t)stream, &terr);
   if (le != cudaSuccess) { g_create_error = std::string("op_cross_attention_bf16: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
   return step_done("dsheg_op_cross_attention_bf16");
 }

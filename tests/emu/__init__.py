@@ -52,3 +52,11 @@ def gemm_lib(*defines):
     L = _load("emu_gemm", defines)
     L.emu_gemm_last_error.restype = ctypes.c_char_p
     return L
+
+
+def attn_ws_lib():
+    """attn_ws.cuh (warp-specialised TMA attention: mbarriers, 3-D TMA boxes, mma.sync, tensor-memory parking) on the models of
+    emu_prims.h + emu_tc_prims.h."""
+    L = _load("emu_attn_ws")
+    L.emu_attn_ws_last_error.restype = ctypes.c_char_p
+    return L

@@ -23,6 +23,7 @@ struct CUtensorMap {   // emulated tensor map: row-major bf16 [rows, cols], lead
   uint64_t cols = 0, rows = 0, ld_bytes = 0;
   uint32_t box_cols = 0, box_rows = 0;
   int swizzle_bytes = 128;
+  uint64_t n2 = 1, ld2_bytes = 0;   // 3-D maps (column, frame, sample): number of samples and their stride; `rows` = frames per sample
 };
 
 #define DSHEG_TC_DYN_SMEM(name) uint8_t* name = emu::self().cta->smem
@@ -138,6 +139,16 @@ inline void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int 
   emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
 }
 inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
+// 3-D (column, frame, sample): the box covers one sample; frames beyond the sample's `rows` (and samples beyond n2) arrive as zeros
+inline void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  emu::delay("EMU_DELAY_TMA");
+  CUtensorMap m2 = *map;
+  if (c2 < 0 || (uint64_t)c2 >= map->n2) m2.rows = 0;   // everything out of bounds
+  else m2.base = static_cast<const uint8_t*>(map->base) + (size_t)c2 * map->ld2_bytes;
+  tma_copy(&m2, emu::self().cta, dst, c0, c1, true);
+  emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
+}
+inline void tma_prefetch_l2_3d(const CUtensorMap*, int, int, int) {}
 inline void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
   emu::delay("EMU_DELAY_TMA");
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
@@ -242,6 +253,14 @@ inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   const float* src = emu::tc_state(t.cta).tmem.data() + (size_t)(lane_base + t.lane) * 512 + col;
   memcpy(r, src, 32 * 4);
   __syncwarp();   // .sync.aligned: the warp executes it together
+}
+inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  emu::Thread& t = emu::self();
+  const uint32_t lane_base = taddr >> 16, col = taddr & 0xFFFFu;
+  if (lane_base != (uint32_t)(t.warp & 3) * 32u) emu::rt().error = "tcgen05.st: a warp may only touch the TMEM lane quadrant (warp id % 4)";
+  if (lane_base + 32 > 128 || col + 32 > 512) { emu::rt().error = "tcgen05.st: TMEM address out of range"; return; }
+  memcpy(emu::tc_state(t.cta).tmem.data() + (size_t)(lane_base + t.lane) * 512 + col, r, 32 * 4);
+  __syncwarp();   // .sync.aligned
 }
 template <int CG, int COLS> inline void tmem_alloc(uint32_t slot) {
   static_assert(COLS == 32 || COLS == 64 || COLS == 128 || COLS == 256 || COLS == 512, "TMEM allocations are powers of two >= 32 columns");
