@@ -9,9 +9,13 @@
 // pipes idle during the products, and every dependency stall is exposed at 4 warps per scheduler (ncu: issue slots 34 % busy, 0.42 of
 // the copy peak in the sampling loop).  Two samples cannot be resident (Y of one sample is 96 KB of shared memory).  Here the phases
 // belong to DIFFERENT warps working on DIFFERENT samples, and Y never exists in shared memory:
-//   * 4 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep) into the normalised bf16 A^T of that
-//     head in one of 8 per-head slots (64 KB).  They run up to a whole sample ahead of the Y warps; a slot is rewritten as soon as
-//     its two readers have finished the head (mbarrier pair per head).
+//   * 4 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep, refilled by the A warps in turn) into the
+//     normalised bf16 A^T of that head (a 32 x 32 quadrant per warp; the column sums of K' come out of the same fragments, ones . K',
+//     in exactly the accumulator layout, so nothing is exchanged between the warps) and PARK it in tensor memory (16 words per
+//     thread and head).  That is phase 1 of a sample and needs nothing from the Y warps, so it runs a whole sample ahead.  Phase 2
+//     copies the 8 parked heads into the per-head shared-memory slots (64 KB) as their readers release them (mbarrier pair per
+//     head).  The first hardware version accumulated at most ONE head ahead of the release and was serial with the Y warps:
+//     8 heads x (accumulate + epilogue) after every release, 2.36 TB/s (profiles/r02/call10).
 //   * 16 "Y warps" = 8 heads x 2 row halves.  Warp (h, half) owns head h of up to three 16-frame tiles: its Q' box (48 frames x 64
 //     columns, 6 KB) arrives by a TMA load the warp issues ITSELF for the next sample the moment its last product has consumed the
 //     current one, so the reload has the whole LayerNorm part to land.  Per tile: Y = Q' A on mma.sync from ldmatrix fragments (A^T
@@ -41,8 +45,8 @@ using atm::BF2_ONES;
 
 constexpr int NH = 8;                          // heads
 constexpr int NYW = 2 * NH;                    // Y warps: head = warp & 7, row half = warp >> 3
-constexpr int NAW = 4;                         // A warps (the LAST warps of the CTA)
-constexpr int NTHREADS = 32 * (NYW + NAW);
+constexpr int NAW = 4;                         // A warps
+constexpr int NTHREADS = 32 * (NYW + NAW);     // 5 warps per SM sub-partition: 96 registers each (a 21st warp would cut everyone to 80)
 constexpr int MH = TP / 32;                    // 16-frame tiles per row half (3)
 constexpr int QBOX_BYTES = MH * 16 * 128;      // one Y warp's Q' box: 48 frames x 64 columns
 constexpr int A_BYTES = HD * 128;              // one head's A^T (64 x 64 bf16)
@@ -52,19 +56,18 @@ constexpr int A_OFF = Q_OFF + NYW * QBOX_BYTES;               // [NH] A^T slots
 constexpr int RING_OFF = A_OFF + NH * A_BYTES;                // [NST] K' / V tiles
 constexpr int STAT_OFF = RING_OFF + NST * TILE_BYTES;         // [sample parity][half][tile][row 16][head 8] float2 (sum, sumsq)
 constexpr int STAT_BYTES = 2 * 2 * MH * 16 * NH * 8;
-constexpr int CSUM_OFF = STAT_OFF + STAT_BYTES;               // [head parity][64] column sums of K'
-constexpr int BAR_OFF = CSUM_OFF + 2 * HD * 4;                // kv_full[NST] a_full[NH] a_empty[NH] q_full[NYW]
-constexpr int NBAR = NST + 2 * NH + NYW;
+constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;                // kv_full[NST] kv_empty[NST / 2] a_full[NH] a_empty[NH] q_full[NYW]
+constexpr int NBAR = NST + NST / 2 + 2 * NH + NYW;
 constexpr int TMEM_SLOT_OFF = BAR_OFF + NBAR * 8;
 constexpr int SMEM_BYTES = ((TMEM_SLOT_OFF + 4 + 127) / 128) * 128;
-constexpr int TMEM_COLS = 256;                 // 4 Y warps per lane quadrant x (MH - 1) parked tiles x 32 columns
+constexpr int TMEM_COLS = 512;                 // columns [0, 256): 4 Y warps per lane quadrant x (MH - 1) parked tiles x 32; [256, 384): 8 heads x 16 of the A warp
+constexpr int APARK_COL = (NYW / 4) * (MH - 1) * 32;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 static_assert(Q_OFF % 1024 == 0 && QBOX_BYTES % 1024 == 0 && A_OFF % 1024 == 0 && A_BYTES % 1024 == 0 && RING_OFF % 1024 == 0 && TILE_BYTES % 1024 == 0,
               "SWIZZLE_128B tiles start on 1024-byte boundaries");
-static_assert((NYW / 4) * (MH - 1) * 32 <= TMEM_COLS, "parking space");
+static_assert(APARK_COL + NH * 16 <= TMEM_COLS, "parking space");
 
 __device__ __forceinline__ void half_sync(int half) { prims::named_bar_sync<32 * NH>(1 + half); }     // ids 1, 2: the 8 Y warps of a row half
-__device__ __forceinline__ void agroup_sync() { prims::named_bar_sync<32 * NAW>(3); }                 // id 3: the A warps
 
 // shared-memory row of A^T that holds output column l of the head: n-tile nt = 4 (l >> 5) + ((l >> 1) & 3), row 2 ((l >> 3) & 3) + (l & 1)
 // of the tile -- thread q of an mma quad then owns l = 32 a + 8 q + {0 .. 7}, a = 0, 1: two 16-byte runs of the output row.
@@ -87,11 +90,13 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t q_tx = (uint32_t)mh * 16u * 128u;      // bytes one TMA box delivers (frames beyond T arrive as zeros)
   const uint32_t kv_tx = (uint32_t)n_kt * 16u * 128u;
   auto kv_full = [&](int s) { return sbase + BAR_OFF + 8u * s; };
-  auto a_full = [&](int h) { return sbase + BAR_OFF + 8u * (NST + h); };
-  auto a_empty = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NH + h); };
-  auto q_full = [&](int w) { return sbase + BAR_OFF + 8u * (NST + 2 * NH + w); };
+  auto kv_empty = [&](int p) { return sbase + BAR_OFF + 8u * (NST + p); };
+  auto a_full = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NST / 2 + h); };
+  auto a_empty = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NST / 2 + NH + h); };
+  auto q_full = [&](int w) { return sbase + BAR_OFF + 8u * (NST + NST / 2 + 2 * NH + w); };
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) tc::mbar_init(kv_full(s), 1);
+    for (int p2 = 0; p2 < NST / 2; ++p2) tc::mbar_init(kv_empty(p2), NAW);
     for (int h = 0; h < NH; ++h) { tc::mbar_init(a_full(h), NAW); tc::mbar_init(a_empty(h), 2); }
     for (int w = 0; w < NYW; ++w) tc::mbar_init(q_full(w), 1);
     tc::fence_mbarrier_init();
@@ -122,7 +127,12 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int smp = (int)blockIdx.x + i * (int)gridDim.x;
       const uint32_t par = (uint32_t)(i & 1);
       float2* const stat = reinterpret_cast<float2*>(sm + STAT_OFF) + (size_t)((par * 2 + half) * MH) * 16 * NH;
-      if (nu > 0) tc::mbar_wait(q_full(warp), par);
+      if (nu > 0) {
+        // the sample's modulation row (scale | shift) of this thread's columns -> L1 now; it is read after the products
+        const float* sc = ss + (size_t)(smp % B) * ss_ld + colA;
+        prims::prefetch_l1(sc); prims::prefetch_l1(sc + 32); prims::prefetch_l1(sc + D); prims::prefetch_l1(sc + D + 32);
+        tc::mbar_wait(q_full(warp), par);
+      }
       tc::mbar_wait(a_full(h), par);
       float y[8][4];
 #pragma unroll 1
@@ -263,14 +273,20 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ========================================================== A warps ==========================================================
     const int wq = warp - NYW;
     const int lq = wq & 1, dq = wq >> 1;      // this warp's 32 x 32 quadrant of A^T[l][d]: l-half lq, d-half dq
+    const uint32_t apark = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)APARK_COL;
+    const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
+    // fragment addresses of k-step 0 (row kt * 16 adds kt * 2048 bytes: 16 rows of 128 bytes, the XOR pattern repeats every 8 rows)
+    const int vr = rr + ((mat >> 1) << 3), kr = rr + ((mat & 1) << 3);
+    const uint32_t v_off0 = swz(vr, 4 * lq + (mat & 1)), v_off1 = swz(vr, 4 * lq + 2 + (mat & 1));
+    const uint32_t k_off0 = swz(kr, 4 * dq + (mat >> 1)), k_off1 = swz(kr, 4 * dq + 2 + (mat >> 1));
     const int n_heads = n_iter * NH;          // (sample, head) units of this CTA, in order
-    auto issue = [&](int hc) {                // lane 0 of the first A warp: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
+    auto issue = [&](int hc) {                // one lane: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
       const int smp = (int)blockIdx.x + (hc >> 3) * (int)gridDim.x, hh = hc & 7, s0 = 2 * (hc & 1);
       tc::mbar_arrive_expect_tx(kv_full(s0), kv_tx);
       tc::tma_load_3d(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp);
       tc::mbar_arrive_expect_tx(kv_full(s0 + 1), kv_tx);
       tc::tma_load_3d(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp);
-      // pull the same head of the NEXT sample from HBM into L2 (the ring itself is only two heads deep: it then covers L2 latency, not HBM latency)
+      // pull the same head of the NEXT sample from HBM into L2 (the ring is only two units deep: it then covers L2 latency, not HBM latency)
       if (smp + (int)gridDim.x < n_samples) {
         tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, 0, smp + (int)gridDim.x);
         tc::tma_prefetch_l2_3d(&tmKV, vcol + hh * HD, 0, smp + (int)gridDim.x);
@@ -280,67 +296,93 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::prefetch_tensormap(&tmKV);
       for (int hc = 0; hc < 2 && hc < n_heads; ++hc) issue(hc);
     }
-    const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
 #pragma unroll 1
-    for (int hc = 0; hc < n_heads; ++hc) {
-      const int hh = hc & 7, s0 = 2 * (hc & 1);
-      const uint32_t par = (uint32_t)((hc >> 1) & 1);
-      const uint32_t ks_addr = sbase + RING_OFF + s0 * TILE_BYTES, vs_addr = ks_addr + TILE_BYTES;
-      float* const colsum = reinterpret_cast<float*>(sm + CSUM_OFF) + (hc & 1) * HD;
-      tc::mbar_wait(kv_full(s0), par);
-      tc::mbar_wait(kv_full(s0 + 1), par);
-      // ---- A^T[l][d] = sum_t V[t][l] K'[t][d]; on the same K' fragments the column sums of K' for d = 32 dq + 16 lq .. + 15 (ones . K')
-      float acc[2][4][4], cs[2][4];
+    for (int i = 0; i < n_iter; ++i) {
+      // ---- phase 1: A^T of the sample's 8 heads, normalised, packed to bf16 and parked in tensor memory (independent of the Y warps)
+#pragma unroll 1
+      for (int hh = 0; hh < NH; ++hh) {
+        const int hc = i * NH + hh, s0 = 2 * (hc & 1);
+        const uint32_t par = (uint32_t)((hc >> 1) & 1);
+        const uint32_t ks_addr = sbase + RING_OFF + s0 * TILE_BYTES, vs_addr = ks_addr + TILE_BYTES;
+        tc::mbar_wait(kv_full(s0), par);
+        tc::mbar_wait(kv_full(s0 + 1), par);
+        // A^T[l][d] = sum_t V[t][l] K'[t][d]; cs = ones . K' = the column sums of K' in the layout of the accumulator columns
+        float acc[2][4][4], cs[4][4];
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
+        for (int nt = 0; nt < 4; ++nt) {
+          cs[nt][0] = cs[nt][1] = cs[nt][2] = cs[nt][3] = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
-      cs[0][0] = cs[0][1] = cs[0][2] = cs[0][3] = cs[1][0] = cs[1][1] = cs[1][2] = cs[1][3] = 0.f;
-#pragma unroll 2
-      for (int kt = 0; kt < n_kt; ++kt) {   // 16 frames per k-step
-        uint32_t a0[4], a1[4];
-        {
-          const int r = kt * 16 + rr + ((mat >> 1) << 3);
-          ldsm_x4_trans(vs_addr + swz(r, 4 * lq + (mat & 1)), a0[0], a0[1], a0[2], a0[3]);
-          ldsm_x4_trans(vs_addr + swz(r, 4 * lq + 2 + (mat & 1)), a1[0], a1[1], a1[2], a1[3]);
+          for (int mi = 0; mi < 2; ++mi) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
         }
+        uint32_t fa[2][4], fb[2][4];   // fragments of the current k-step; the next step's are loaded under its products
+        ldsm_x4_trans(vs_addr + v_off0, fa[0][0], fa[0][1], fa[0][2], fa[0][3]);
+        ldsm_x4_trans(vs_addr + v_off1, fa[1][0], fa[1][1], fa[1][2], fa[1][3]);
+        ldsm_x4_trans(ks_addr + k_off0, fb[0][0], fb[0][1], fb[0][2], fb[0][3]);
+        ldsm_x4_trans(ks_addr + k_off1, fb[1][0], fb[1][1], fb[1][2], fb[1][3]);
+#pragma unroll 2
+        for (int kt = 0; kt < n_kt; ++kt) {   // 16 frames per k-step
+          uint32_t na[2][4], nb[2][4];
+          if (kt + 1 < n_kt) {
+            const uint32_t o = (uint32_t)(kt + 1) * 2048u;
+            ldsm_x4_trans(vs_addr + v_off0 + o, na[0][0], na[0][1], na[0][2], na[0][3]);
+            ldsm_x4_trans(vs_addr + v_off1 + o, na[1][0], na[1][1], na[1][2], na[1][3]);
+            ldsm_x4_trans(ks_addr + k_off0 + o, nb[0][0], nb[0][1], nb[0][2], nb[0][3]);
+            ldsm_x4_trans(ks_addr + k_off1 + o, nb[1][0], nb[1][1], nb[1][2], nb[1][3]);
+          }
 #pragma unroll
-        for (int np = 0; np < 2; ++np) {    // two d n-tiles per ldmatrix.x4
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4_trans(ks_addr + swz(kt * 16 + rr + ((mat & 1) << 3), 4 * dq + 2 * np + (mat >> 1)), b0, b1, b2, b3);
-          mma_bf16(acc[0][2 * np], a0, b0, b1);
-          mma_bf16(acc[0][2 * np + 1], a0, b2, b3);
-          mma_bf16(acc[1][2 * np], a1, b0, b1);
-          mma_bf16(acc[1][2 * np + 1], a1, b2, b3);
-          if (np == lq) {   // warp-uniform: the two warps of a d-half share its column sums
-            mma_bf16(cs[0], ones, b0, b1);
-            mma_bf16(cs[1], ones, b2, b3);
+          for (int np = 0; np < 2; ++np) {    // two d n-tiles per ldmatrix.x4
+            mma_bf16(acc[0][2 * np], fa[0], fb[np][0], fb[np][1]);
+            mma_bf16(acc[0][2 * np + 1], fa[0], fb[np][2], fb[np][3]);
+            mma_bf16(acc[1][2 * np], fa[1], fb[np][0], fb[np][1]);
+            mma_bf16(acc[1][2 * np + 1], fa[1], fb[np][2], fb[np][3]);
+            mma_bf16(cs[2 * np], ones, fb[np][0], fb[np][1]);
+            mma_bf16(cs[2 * np + 1], ones, fb[np][2], fb[np][3]);
+          }
+          if (kt + 1 < n_kt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { fa[0][e] = na[0][e]; fa[1][e] = na[1][e]; fb[0][e] = nb[0][e]; fb[1][e] = nb[1][e]; }
           }
         }
-      }
-      if (g == 0) {   // every accumulator row holds the same sums; row 0 publishes them
-        *reinterpret_cast<float2*>(colsum + 32 * dq + 16 * lq + 2 * q) = make_float2(cs[0][0], cs[0][1]);
-        *reinterpret_cast<float2*>(colsum + 32 * dq + 16 * lq + 8 + 2 * q) = make_float2(cs[1][0], cs[1][1]);
-      }
-      agroup_sync();   // column sums published; all four warps are done reading this unit's K' and V tiles
-      if (wq == 0 && lane == 0 && hc + 2 < n_heads) issue(hc + 2);   // refill the two slots (only ever read: no proxy fence needed)
-      tc::mbar_wait(a_empty(hh), (uint32_t)(((hc >> 3) & 1) ^ 1));   // both readers of the previous sample's A^T of this head are done
-      uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
-      const float* csum = colsum + 32 * dq;
+        // every fragment of this unit's K' / V tiles has been consumed by a product: the two ring slots go back to the producer
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(kv_empty(hc & 1));
+        uint32_t pk[16];   // [nt][mi][rows g | g + 8]: bf16 pairs of columns d = 32 dq + 8 nt + 2 q, + 1
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const float2 s2 = *reinterpret_cast<const float2*>(csum + 8 * nt + 2 * q);
-        const float2 inv = make_float2(rcp_approx(s2.x), rcp_approx(s2.y));
+        for (int nt = 0; nt < 4; ++nt) {
+          const float2 inv = make_float2(rcp_approx(cs[nt][0]), rcp_approx(cs[nt][1]));
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) {
-          const int l = 32 * lq + 16 * mi + g;
-          const float2 lo = fmul2(make_float2(acc[mi][nt][0], acc[mi][nt][1]), inv), hi = fmul2(make_float2(acc[mi][nt][2], acc[mi][nt][3]), inv);
-          *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l), 4 * dq + nt) + q * 4) = pack2(lo.x, lo.y);
-          *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l + 8), 4 * dq + nt) + q * 4) = pack2(hi.x, hi.y);
+          for (int mi = 0; mi < 2; ++mi) {
+            const float2 lo = fmul2(make_float2(acc[mi][nt][0], acc[mi][nt][1]), inv), hi = fmul2(make_float2(acc[mi][nt][2], acc[mi][nt][3]), inv);
+            pk[4 * nt + 2 * mi] = pack2(lo.x, lo.y);
+            pk[4 * nt + 2 * mi + 1] = pack2(hi.x, hi.y);
+          }
         }
+        tc::tmem_st16(apark + (uint32_t)(hh * 16), pk);
+        // refill duty rotates over the A warps: by now (after the pack / park) the other three have normally arrived, so the wait is short
+        if (wq == (hc & 3) && lane == 0 && hc + 2 < n_heads) {
+          tc::mbar_wait(kv_empty(hc & 1), par);
+          issue(hc + 2);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's quadrant of A^T is written
+      // ---- phase 2: parked heads -> the per-head A^T slots, each as soon as both readers of the previous sample have released it
+#pragma unroll 1
+      for (int hh = 0; hh < NH; ++hh) {
+        uint32_t pk[16];
+        tc::tmem_ld16(apark + (uint32_t)(hh * 16), pk);
+        tc::mbar_wait(a_empty(hh), (uint32_t)((i & 1) ^ 1));
+        uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const int l = 32 * lq + 16 * mi + g;
+            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l), 4 * dq + nt) + q * 4) = pk[4 * nt + 2 * mi];
+            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l + 8), 4 * dq + nt) + q * 4) = pk[4 * nt + 2 * mi + 1];
+          }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's quadrant of A^T is written
+      }
     }
   }
   tc::tc_fence_before();

@@ -7,8 +7,12 @@
 // fp32 in TMEM.  out[M, N] = epilogue(A[M, K] . W[N, K]^T), A = virtual concat of up to 4 fp32 segments.
 //
 // Shape: one output tile per CTA or CTA pair (not persistent; see TCfg), K in blocks of 32 fp32 (128-byte rows, SWIZZLE_128B --
-// byte-for-byte the operand geometry of the bf16 kernel: 8 TF32 elements = 32 bytes per MMA k-step), 3 / 4-stage TMA ring.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (one TMEM lane quadrant each).  The epilogue does its per-row / per-column math in the TMEM layout
+// byte-for-byte the operand geometry of the bf16 kernel: 8 TF32 elements = 32 bytes per MMA k-step), 3-stage TMA ring, TWO CTAs per SM
+// (96 KB of ring + 256 TMEM columns each): the fp32 epilogue (exact erf GELU, fp32 residual / output rows of 1 - 6 KB) costs several
+// times the mainloop, so one CTA's epilogue runs under the other's mainloop -- or, most of the time, under its epilogue: 16 epilogue
+// warps per SM.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue (TMEM lane quadrant = warp id % 4,
+// column half = (warp - 2) / 4).  Round 2's first pair version had 4 epilogue warps and one CTA per SM: tensor pipe 5 - 12 % busy
+// (profiles/r02/call9).  The epilogue does its per-row / per-column math in the TMEM layout
 // (thread = row), then turns each 32-column chunk through shared memory (the mainloop's ring is free by then) so that the
 // residual loads and the stores are 128-byte coalesced: 8 lanes x 16 bytes per row, 4 rows per instruction.
 #pragma once
@@ -20,7 +24,8 @@ namespace t32 {
 using namespace tc;
 
 constexpr int TBM = 128, TBK = 32;                     // rows per CTA, fp32 elements per k-block (128-byte rows)
-constexpr int T_NUM_THREADS = 192;
+constexpr int T_NUM_EPI_WARPS = 8;
+constexpr int T_NUM_THREADS = 64 + 32 * T_NUM_EPI_WARPS;
 constexpr int T_TURN_LD = 36;                            // floats per staged row (144 B: 16-byte aligned, conflict-free)
 constexpr int T_BAR_BYTES = 128;
 
@@ -28,16 +33,16 @@ constexpr int T_BAR_BYTES = 128;
 //         problems.  Its operand traffic (4 KB + 4 KB per 64-cycle MMA, 32 FLOP per L2 byte) bounds it near 350 TF/s.
 // CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile, like the bf16 engine's pair kernels: each CTA stages
 //         its 128 A rows and HALF of the W tile (128 of the 256 N rows), the leader issues 256 x 256 x 8 MMAs that read both CTAs'
-//         shared memory, each CTA's TMEM holds its 128 rows x 256 columns.  4 stages of 32 KB, one CTA per SM.
+//         shared memory, each CTA's TMEM holds its 128 rows x 256 columns.  3 stages of 32 KB, two CTAs (of different pairs) per SM.
 template <int CG> struct TCfg {
   static constexpr int BN = CG == 2 ? 256 : 128;         // tile width
   static constexpr int W_ROWS = BN / CG;                 // W rows staged by ONE CTA
-  static constexpr int STAGES = CG == 2 ? 4 : 3;
+  static constexpr int STAGES = 3;
   static constexpr int A_BYTES = TBM * TBK * 4, B_BYTES = W_ROWS * TBK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int VEC_BYTES = 2 * BN * 4;           // bias | csum of the tile's columns, staged once by the epilogue warps
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + T_BAR_BYTES + VEC_BYTES + 1024;   // + alignment slack
-  static constexpr int MIN_CTAS = CG == 2 ? 1 : 2;
-  static_assert(4 * 32 * T_TURN_LD * 4 <= STAGES * STAGE_BYTES, "the epilogue turns its chunks through the idle ring");
+  static constexpr int MIN_CTAS = 2;
+  static_assert(T_NUM_EPI_WARPS * 32 * T_TURN_LD * 4 <= STAGES * STAGE_BYTES, "the epilogue turns its chunks through the idle ring");
   // kind::tf32 instruction descriptor: D = f32 (bit 4), A = B = TF32 (format 2 at [7,10) and [10,13)), both K-major,
   // N >> 3 at [17,23), M >> 4 at [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TBM * CG) >> 4) << 24);
@@ -151,8 +156,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ================= epilogue: warps 2..5, TMEM lane quadrant = warp id % 4 =================
-    const int qd = warp & 3;
+    // ================= epilogue: warps 2..9, TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4 =================
+    const int qd = warp & 3, chalf = (warp - 2) >> 2;
+    constexpr int CH_PER_WARP = BN / 32 / (T_NUM_EPI_WARPS / 4);
     const int m_row = m_blk * TBM + qd * 32 + lane;        // the row this thread holds in the TMEM layout
     const bool ln = p.csum != nullptr;
     const float mu = (ln && m_row < p.M) ? __ldg(p.mu + m_row) : 0.f;
@@ -160,17 +166,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     float* turn = reinterpret_cast<float*>(gen_base) + (warp - 2) * 32 * T_TURN_LD;   // this warp's 32 x 36 staging rows (idle ring)
     float* vbias = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + T_BAR_BYTES);   // [BN] bias, [BN] csum (outside the ring:
     float* vcsum = vbias + BN;                                                                 //  staged while the mainloop runs)
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+    for (int i = threadIdx.x - 64; i < BN; i += 32 * T_NUM_EPI_WARPS) {
       const int n = n_blk * BN + i;
       vbias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
       vcsum[i] = (ln && n < p.N) ? __ldg(p.csum + n) : 0.f;
     }
-    epi_bar_sync<128>();
+    epi_bar_sync<32 * T_NUM_EPI_WARPS>();
     const int tr = lane >> 3, tcg = lane & 7;              // coalesced layout: row 4 it + tr of the chunk, columns 4 tcg .. + 3
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
+    for (int ch = chalf * CH_PER_WARP; ch < (chalf + 1) * CH_PER_WARP; ++ch) {
       const int n0 = n_blk * BN + ch * 32;
       if (n0 >= p.N) break;                                 // warp-uniform
       uint32_t r[32];

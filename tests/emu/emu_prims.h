@@ -133,6 +133,7 @@ template <int NTHREADS> inline void named_bar_sync(int id) {
   emu::rendezvous(emu::self().cta->named[id], NTHREADS, "bar.sync (named)");
 }
 inline float ex2f(float x) { ++op_counters().ex2; return exp2f(x); }
+inline void prefetch_l1(const void*) {}
 inline float rcp_approx(float x) { ++op_counters().rcp; return 1.0f / x; }
 inline float tanh_approx(float x) { ++op_counters().tanh; return tanhf(x); }
 inline float2 ffma2(float2 a, float2 b, float2 c) { ++op_counters().packed_fp32; return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }

@@ -262,6 +262,22 @@ inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   memcpy(emu::tc_state(t.cta).tmem.data() + (size_t)(lane_base + t.lane) * 512 + col, r, 32 * 4);
   __syncwarp();   // .sync.aligned
 }
+template <int N> inline float* emu_tmem_row(uint32_t taddr, const char* what) {
+  emu::Thread& t = emu::self();
+  const uint32_t lane_base = taddr >> 16, col = taddr & 0xFFFFu;
+  if (lane_base != (uint32_t)(t.warp & 3) * 32u) emu::rt().error = std::string(what) + ": a warp may only touch the TMEM lane quadrant (warp id % 4)";
+  if (lane_base + 32 > 128 || col + N > 512) { emu::rt().error = std::string(what) + ": TMEM address out of range"; return nullptr; }
+  return emu::tc_state(t.cta).tmem.data() + (size_t)(lane_base + t.lane) * 512 + col;
+}
+inline void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  if (float* p = emu_tmem_row<16>(taddr, "tcgen05.st")) memcpy(p, r, 16 * 4);
+  __syncwarp();
+}
+inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  emu::delay("EMU_DELAY_TMEM_LD");
+  if (const float* p = emu_tmem_row<16>(taddr, "tcgen05.ld")) memcpy(r, p, 16 * 4);
+  __syncwarp();
+}
 template <int CG, int COLS> inline void tmem_alloc(uint32_t slot) {
   static_assert(COLS == 32 || COLS == 64 || COLS == 128 || COLS == 256 || COLS == 512, "TMEM allocations are powers of two >= 32 columns");
   emu::Cta* c = emu::self().cta;

@@ -243,3 +243,74 @@ def test_postprocess_kernel_sources_on_emulator_match_reference_goldens(golden_d
     assert np.abs(euler - g["euler_deg"]).max() < 2e-3         # degrees; the tolerance of tests/test_postprocess.py
     assert np.abs(outn - g["out_motions"]).max() < 2e-3
     assert np.isfinite(euler).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# attn_ws.cuh: the warp-specialised TMA attention kernel (mbarriers, 3-D TMA boxes, mma.sync, tensor-memory parking).  Input
+# contract = softmax NUMERATORS (Q' and K' hold exp(value - shift), the ACT_EXPO epilogue of the QKV GEMM), V plain.
+# ------------------------------------------------------------------------------------------------------------------------------
+def reference_numerators(qn, kn, v, g, b, ss, H=8):
+    """tr:122-128 + :92-96 on numerators: softmax_d(q) = q' / rowsum(q'), softmax_t(k) = k' / colsum(k') (shift invariance)."""
+    Bn, T, D = qn.shape
+    Tk = kn.shape[1]
+    q = qn.bfloat16().double().view(Bn, T, H, -1)
+    k = kn.bfloat16().double().view(Bn, Tk, H, -1)
+    vv = v.bfloat16().double().view(Bn, Tk, H, -1)
+    q = q / q.sum(-1, keepdim=True)
+    k = k / k.sum(1, keepdim=True)
+    att = torch.einsum("bnhd,bnhl->bhdl", k, vv)
+    y = torch.einsum("bnhd,bhdl->bnhl", q, att).reshape(Bn, T, D)
+    yn = torch.nn.functional.layer_norm(y, (D,), g.double(), b.double(), 1e-5)
+    idx = torch.arange(Bn) % ss.shape[0]
+    return torch.nn.functional.silu(yn * (1 + ss[idx, None, :D].double()) + ss[idx, None, D:].double())
+
+
+def _ws_case(Bn, T, Tk=None, nb=None, seed=0):
+    torch.manual_seed(seed + T)
+    D, Tk = 512, Tk or T
+    qn, kn, v = torch.exp(1.5 * torch.randn(Bn, T, D)), torch.exp(1.5 * torch.randn(Bn, Tk, D)), 1.5 * torch.randn(Bn, Tk, D)
+    g, b = 1 + 0.1 * torch.randn(D), 0.1 * torch.randn(D)
+    ss = 0.5 * torch.randn(nb or Bn, 2 * D)
+    return qn, kn, v, g, b, ss
+
+
+def run_attention_ws(qn, kn, v, g, b, ss, grid=2):
+    Bn, T, D = qn.shape
+    Tk = kn.shape[1]
+    L = emu.attn_ws_lib()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    z = np.zeros((Bn, T, D), dtype=np.int16)
+    gg, bb, s = (x.float().numpy().copy() for x in (g, b, ss))
+    if Tk == T:      # self-attention: one fused tensor [q' | k' | v], like the engine
+        qkv = _bf16_bits(torch.cat([qn, kn, v], -1))
+        rc = L.emu_attention_ws(P(qkv), 3 * D, P(qkv), 3 * D, D, 2 * D, P(z), Bn, T, T, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], grid)
+    else:            # cross-attention (tr:133-166): separate q' and (k' | v) sources and lengths
+        q, kv = _bf16_bits(qn), _bf16_bits(torch.cat([kn, v], -1))
+        rc = L.emu_attention_ws(P(q), D, P(kv), 2 * D, 0, D, P(z), Bn, T, Tk, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], grid)
+    assert rc == 0, L.emu_attn_ws_last_error().decode()
+    return z
+
+
+@pytest.mark.parametrize("Bn,T,Tk,nb,grid", [(3, 88, None, None, 2), (2, 34, None, 1, 1), (1, 96, None, None, 1), (2, 16, None, None, 2), (1, 7, None, None, 1),
+                                             (1, 84, None, None, 1), (5, 30, None, 2, 2), (2, 88, 40, None, 1), (2, 20, 96, None, 2)])
+def test_attn_ws_kernel_source_on_emulator(Bn, T, Tk, nb, grid):
+    """Every role of the kernel (A warps, Y warps of both row halves incl. empty halves, TMEM parking of 0 / 1 / 2 tiles, several
+    samples per persistent CTA, ragged last tiles, cross-attention lengths) against the fp64 reference."""
+    qn, kn, v, g, b, ss = _ws_case(Bn, T, Tk, nb)
+    got = _from_bits(run_attention_ws(qn, kn, v, g, b, ss, grid))
+    want = reference_numerators(qn, kn, v, g, b, ss)
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max() / want.abs().max()) < 8e-3     # bf16 operands and output; LayerNorm on fp32 Y
+
+
+@pytest.mark.parametrize("env", [{"EMU_SCHED": "reverse"}, {"EMU_SCHED": "shuffle"}, {"EMU_SCHED": "shuffle", "EMU_SCHED_SEED": "5", "EMU_DELAY_TMA": "25"},
+                                 {"EMU_DELAY_TMA": "40"}, {"EMU_DELAY_TMEM_LD": "40"}])
+def test_attn_ws_is_independent_of_the_thread_schedule(env, monkeypatch):
+    """Stand-in for racecheck: reversed / shuffled thread orders, late TMA arrivals and slow TMEM loads must reproduce the default
+    schedule's output bit for bit (4 samples on ONE persistent CTA: every ring slot, A^T slot, Q' box and parity wraps)."""
+    qn, kn, v, g, b, ss = _ws_case(4, 40, seed=3)
+    base = run_attention_ws(qn, kn, v, g, b, ss, grid=1)
+    assert np.array_equal(base, run_attention_ws(qn, kn, v, g, b, ss, grid=3))    # and of the sample -> CTA assignment
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)
+    assert np.array_equal(base, run_attention_ws(qn, kn, v, g, b, ss, grid=1))
