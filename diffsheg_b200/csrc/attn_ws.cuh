@@ -9,29 +9,32 @@
 // pipes idle during the products, and every dependency stall is exposed at 4 warps per scheduler (ncu: issue slots 34 % busy, 0.42 of
 // the copy peak in the sampling loop).  Two samples cannot be resident (Y of one sample is 96 KB of shared memory).  Here the phases
 // belong to DIFFERENT warps working on DIFFERENT samples, and Y never exists in shared memory:
-//   * 4 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep, refilled by the A warps in turn) into the
-//     normalised bf16 A^T of that head (a 32 x 32 quadrant per warp; the column sums of K' come out of the same fragments, ones . K',
-//     in exactly the accumulator layout, so nothing is exchanged between the warps) and PARK it in tensor memory (16 words per
+//   * 8 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep, refilled by the A warps in turn) into the
+//     normalised bf16 A^T of that head (a 32 x 16 tile per warp; the column sums of K' come out of the same fragments, ones . K',
+//     in exactly the accumulator layout, so nothing is exchanged between the warps) and PARK it in tensor memory (8 words per
 //     thread and head).  That is phase 1 of a sample and needs nothing from the Y warps, so it runs a whole sample ahead.  Phase 2
 //     copies the 8 parked heads into the per-head shared-memory slots (64 KB) as their readers release them (mbarrier pair per
 //     head).  The first hardware version accumulated at most ONE head ahead of the release and was serial with the Y warps:
-//     8 heads x (accumulate + epilogue) after every release, 2.36 TB/s (profiles/r02/call10).
+//     8 heads x (accumulate + epilogue) after every release, 2.36 TB/s (profiles/r02/call10); the second had 4 A warps with 32 x 32
+//     quadrants: one warp per SM sub-partition issuing 620 instructions per head at 0.17 IPC was the critical path (call11).
 //   * 16 "Y warps" = 8 heads x 2 row halves.  Warp (h, half) owns head h of up to three 16-frame tiles: its Q' box (48 frames x 64
 //     columns, 6 KB) arrives by a TMA load the warp issues ITSELF for the next sample the moment its last product has consumed the
 //     current one, so the reload has the whole LayerNorm part to land.  Per tile: Y = Q' A on mma.sync from ldmatrix fragments (A^T
 //     rows are stored permuted so that a thread's 16 output columns are two contiguous runs of 8), row sums on the tensor core, and
 //     the per-row LayerNorm partials (sum, sum of squares over the head's 64 columns) straight from the fp32 accumulators into a
-//     [row][head] table.  Finished tiles are PARKED IN TENSOR MEMORY (tcgen05.st, thread-private columns: TMEM as a 96 KB register
+//     [row][head] table.  Finished tiles are PARKED IN TENSOR MEMORY (tcgen05.st, thread-private columns: TMEM as a 192 KB register
 //     spill space for mma.sync warps; micro-benchmark scripts/ubench), which frees the A^T slot after the last product instead of
-//     after the LayerNorm part.
+//     after the LayerNorm part and keeps every warp within 80 registers (24 warps per SM).
 //   * one named barrier per row half and sample publishes the partials; then every warp normalises, modulates and applies SiLU to
-//     its own tiles IN REGISTERS (fp32 Y, never rounded to bf16 before the LayerNorm) and writes z with 16-byte stores: a store
-//     instruction covers 64 contiguous bytes of 8 rows.  No CTA-wide barrier, no LayerNorm pass over shared memory, no shuffles
+//     its own tiles (fp32 Y back from tensor memory, 16 columns at a time, never rounded to bf16 before the LayerNorm) and writes z
+//     with 16-byte stores: a store instruction covers 64 contiguous bytes of 8 rows.  No CTA-wide barrier, no LayerNorm pass over shared memory, no shuffles
 //     beyond one quad reduction per tile.
 // Issue slots per sample drop from 37 k to about 20 k warp-instructions and the three pipes (tensor: A warps + Y products; FP32 /
 // MUFU: LayerNorm parts; TMA) overlap because the warps drift apart instead of marching in step.
 // HBM traffic: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample (unchanged).
 #pragma once
+#include <type_traits>
+
 #include "attn_tma.cuh"
 
 namespace dsheg {
@@ -45,8 +48,8 @@ using atm::BF2_ONES;
 
 constexpr int NH = 8;                          // heads
 constexpr int NYW = 2 * NH;                    // Y warps: head = warp & 7, row half = warp >> 3
-constexpr int NAW = 4;                         // A warps
-constexpr int NTHREADS = 32 * (NYW + NAW);     // 5 warps per SM sub-partition: 96 registers each (a 21st warp would cut everyone to 80)
+constexpr int NAW = 8;                         // A warps (the LAST warps of the CTA): l-half = wq & 1, 16-column d-slice = wq >> 1
+constexpr int NTHREADS = 32 * (NYW + NAW);     // 6 warps per SM sub-partition: 80 registers each
 constexpr int MH = TP / 32;                    // 16-frame tiles per row half (3)
 constexpr int QBOX_BYTES = MH * 16 * 128;      // one Y warp's Q' box: 48 frames x 64 columns
 constexpr int A_BYTES = HD * 128;              // one head's A^T (64 x 64 bf16)
@@ -60,12 +63,13 @@ constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;                // kv_full[NST] kv
 constexpr int NBAR = NST + NST / 2 + 2 * NH + NYW;
 constexpr int TMEM_SLOT_OFF = BAR_OFF + NBAR * 8;
 constexpr int SMEM_BYTES = ((TMEM_SLOT_OFF + 4 + 127) / 128) * 128;
-constexpr int TMEM_COLS = 512;                 // columns [0, 256): 4 Y warps per lane quadrant x (MH - 1) parked tiles x 32; [256, 384): 8 heads x 16 of the A warp
-constexpr int APARK_COL = (NYW / 4) * (MH - 1) * 32;
+constexpr int TMEM_COLS = 512;                 // per lane quadrant: 4 Y warps x MH parked tiles x 32 columns, then 2 A warps x 8 heads x 8 columns
+constexpr int YPARK_COLS = MH * 32;
+constexpr int APARK_COL = (NYW / 4) * YPARK_COLS;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 static_assert(Q_OFF % 1024 == 0 && QBOX_BYTES % 1024 == 0 && A_OFF % 1024 == 0 && A_BYTES % 1024 == 0 && RING_OFF % 1024 == 0 && TILE_BYTES % 1024 == 0,
               "SWIZZLE_128B tiles start on 1024-byte boundaries");
-static_assert(APARK_COL + NH * 16 <= TMEM_COLS, "parking space");
+static_assert(APARK_COL + (NAW / 4) * NH * 8 <= TMEM_COLS, "parking space");
 
 __device__ __forceinline__ void half_sync(int half) { prims::named_bar_sync<32 * NH>(1 + half); }     // ids 1, 2: the 8 Y warps of a row half
 
@@ -116,25 +120,24 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int mt0 = half * mh;                                   // first tile of this warp
     const int nu = n_mt - mt0 < mh ? (n_mt - mt0 > 0 ? n_mt - mt0 : 0) : mh;   // tiles of this warp (0 .. 3; the same for the 8 warps of a half)
     const uint32_t qb_addr = sbase + Q_OFF + warp * QBOX_BYTES, as_addr = sbase + A_OFF + h * A_BYTES;
-    const uint32_t park = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * (MH - 1) * 32);
+    const uint32_t park = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * YPARK_COLS);
     if (nu > 0 && lane == 0 && n_iter > 0) {
       tc::prefetch_tensormap(&tmQ);
       tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
       tc::tma_load_3d(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, (int)blockIdx.x);
     }
     const int colA = h * HD + 8 * q;     // this thread's output columns: [colA, colA + 8) and [colA + 32, colA + 40)
+#pragma unroll 1
     for (int i = 0; i < n_iter; ++i) {
       const int smp = (int)blockIdx.x + i * (int)gridDim.x;
       const uint32_t par = (uint32_t)(i & 1);
       float2* const stat = reinterpret_cast<float2*>(sm + STAT_OFF) + (size_t)((par * 2 + half) * MH) * 16 * NH;
+      const float* const sc = ss + (size_t)(smp % B) * ss_ld + colA;   // the sample's modulation row (scale | shift) at this thread's columns
       if (nu > 0) {
-        // the sample's modulation row (scale | shift) of this thread's columns -> L1 now; it is read after the products
-        const float* sc = ss + (size_t)(smp % B) * ss_ld + colA;
-        prims::prefetch_l1(sc); prims::prefetch_l1(sc + 32); prims::prefetch_l1(sc + D); prims::prefetch_l1(sc + D + 32);
+        prims::prefetch_l1(sc); prims::prefetch_l1(sc + 32); prims::prefetch_l1(sc + D); prims::prefetch_l1(sc + D + 32);   // read after the products
         tc::mbar_wait(q_full(warp), par);
       }
       tc::mbar_wait(a_full(h), par);
-      float y[8][4];
 #pragma unroll 1
       for (int u = 0; u < nu; ++u) {
         // ---- Y[t][l] = Q'[t][:] . A: the 16 x 64 tile of (tile u, head h); row sums of Q' on the tensor core (Q' . ones)
@@ -142,7 +145,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int kd = 0; kd < 4; ++kd)   // A fragments: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15) of the 16 x 16 block
           ldsm_x4(qb_addr + swz(u * 16 + rr + ((mat & 1) << 3), 2 * kd + (mat >> 1)), pa[kd][0], pa[kd][1], pa[kd][2], pa[kd][3]);
-        float rs[4] = {0.f, 0.f, 0.f, 0.f};   // rs: rows g, g + 8 in [0], [2]
+        float y[8][4], rs[4] = {0.f, 0.f, 0.f, 0.f};   // rs: rows g, g + 8 in [0], [2]
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) { y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f; }
 #pragma unroll
@@ -167,19 +170,23 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               tc::tma_load_3d(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp + (int)gridDim.x);
             }
           }
+          __syncwarp();
         }
         const int ra = (mt0 + u) * 16 + g, rb = ra + 8;
         // zero-filled Q' rows beyond T have zero sums: keep their Y rows at 0
         const float r0 = ra >= T ? 0.f : rcp_approx(rs[0]), r1 = rb >= T ? 0.f : rcp_approx(rs[2]);
         const float2 r02 = make_float2(r0, r0), r12 = make_float2(r1, r1);
         float2 sa = make_float2(0.f, 0.f), sb = sa, qa = sa, qb = sa;
+        uint32_t pk[32];   // the tile as it is parked: column 4 nt + j of the warp's parking row = y[nt][j]
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           const float2 ya = fmul2(make_float2(y[nt][0], y[nt][1]), r02), yb = fmul2(make_float2(y[nt][2], y[nt][3]), r12);
-          y[nt][0] = ya.x; y[nt][1] = ya.y; y[nt][2] = yb.x; y[nt][3] = yb.y;
+          pk[4 * nt] = __float_as_uint(ya.x); pk[4 * nt + 1] = __float_as_uint(ya.y);
+          pk[4 * nt + 2] = __float_as_uint(yb.x); pk[4 * nt + 3] = __float_as_uint(yb.y);
           sa = fadd2(sa, ya); qa = ffma2(ya, ya, qa);
           sb = fadd2(sb, yb); qb = ffma2(yb, yb, qb);
         }
+        tc::tmem_st32(park + (uint32_t)(u * 32), pk);   // parked in tensor memory until the LayerNorm part
         float s0 = sa.x + sa.y, q0 = qa.x + qa.y, s1 = sb.x + sb.y, q1 = qb.x + qb.y;
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {   // the 4 lanes of a quad hold the 64 columns of rows g / g + 8
@@ -190,95 +197,92 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           stat[(u * 16 + g) * NH + h] = make_float2(s0, q0);
           stat[(u * 16 + g + 8) * NH + h] = make_float2(s1, q1);
         }
-        if (u < nu - 1) {   // park the tile in tensor memory until the LayerNorm part
-          uint32_t pk[32];
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            pk[4 * nt] = __float_as_uint(y[nt][0]); pk[4 * nt + 1] = __float_as_uint(y[nt][1]);
-            pk[4 * nt + 2] = __float_as_uint(y[nt][2]); pk[4 * nt + 3] = __float_as_uint(y[nt][3]);
-          }
-          tc::tmem_st32(park + (uint32_t)(u * 32), pk);
-        }
       }
       if (nu == 0) {   // a row half without frames (T <= 16 ...): keep the A^T hand-shake in step
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(a_empty(h));
+        __syncwarp();
         continue;
       }
-      // ---- this thread's LayerNorm / modulation constants for the sample:  t = ((v - mean) rstd g + b)(1 + scale) + shift = 2 ((v - mean) rstd G + Bc),
-      //      SiLU(t) = h + h tanh(h) with h = t / 2.  Loaded before the barrier so that the L2 round trip overlaps the wait.
-      float2 G[8], Bc[8];
-      {
-        const float* sc = ss + (size_t)(smp % B) * ss_ld;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const int col = colA + 32 * a;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + col + 4 * e)), t4 = __ldg(reinterpret_cast<const float4*>(sc + D + col + 4 * e));
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + col + 4 * e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + col + 4 * e));
-            const float sx = 1.f + s4.x, sy = 1.f + s4.y, sz = 1.f + s4.z, sw = 1.f + s4.w;
-            G[4 * a + 2 * e] = make_float2(0.5f * g4.x * sx, 0.5f * g4.y * sy);
-            G[4 * a + 2 * e + 1] = make_float2(0.5f * g4.z * sz, 0.5f * g4.w * sw);
-            Bc[4 * a + 2 * e] = make_float2(0.5f * fmaf(b4.x, sx, t4.x), 0.5f * fmaf(b4.y, sy, t4.y));
-            Bc[4 * a + 2 * e + 1] = make_float2(0.5f * fmaf(b4.z, sz, t4.z), 0.5f * fmaf(b4.w, sw, t4.w));
-          }
-        }
-      }
       half_sync(half);   // the partials of all 8 heads of this half's rows are in the table
+      // ---- LayerNorm + modulation + SiLU:  t = ((v - mean) rstd g + b)(1 + scale) + shift = 2 ((v - mean) rstd G + Bc),  SiLU(t) = h + h tanh(h), h = t / 2
+      float2 rn[MH][2];   // per tile and row (g, g + 8): (rstd, -mean rstd)
+#pragma unroll
+      for (int u = 0; u < MH; ++u)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          rn[u][r] = make_float2(0.f, 0.f);
+          if (u < nu) {
+            const float4* sp = reinterpret_cast<const float4*>(stat + (u * 16 + g + 8 * r) * NH);
+            const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];   // heads (0,1) (2,3) (4,5) (6,7): (sum, sumsq) pairs
+            const float s = ((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z));
+            const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
+            const float mean = s * (1.f / D);
+            // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
+            const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+            rn[u][r] = make_float2(rstd, -mean * rstd);
+          }
+        }
       const size_t row0 = (size_t)smp * T;
-#pragma unroll 1
-      for (int u = nu - 1; u >= 0; --u) {   // the last tile is still in registers; the others come back from tensor memory
-        if (u < nu - 1) {
-          uint32_t pk[32];
-          tc::tmem_ld32(park + (uint32_t)(u * 32), pk);
+      // steps st = 0 .. 2 nu - 1: (run a, tile u) = (st / nu, st % nu), the thread's run a = columns [colA + 32 a, + 8) = n-tiles 4 a .. 4 a + 3 of
+      // tile u = 16 parked columns; a step's load is in flight while the previous step is processed.
+      float2 G[4], Bc[4];
+      auto load_consts = [&](int a) {
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            y[nt][0] = __uint_as_float(pk[4 * nt]); y[nt][1] = __uint_as_float(pk[4 * nt + 1]);
-            y[nt][2] = __uint_as_float(pk[4 * nt + 2]); y[nt][3] = __uint_as_float(pk[4 * nt + 3]);
+        for (int e = 0; e < 2; ++e) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + 32 * a + 4 * e)), t4 = __ldg(reinterpret_cast<const float4*>(sc + D + 32 * a + 4 * e));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + colA + 32 * a + 4 * e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + colA + 32 * a + 4 * e));
+          const float sx = 1.f + s4.x, sy = 1.f + s4.y, sz = 1.f + s4.z, sw = 1.f + s4.w;
+          G[2 * e] = make_float2(0.5f * g4.x * sx, 0.5f * g4.y * sy);
+          G[2 * e + 1] = make_float2(0.5f * g4.z * sz, 0.5f * g4.w * sw);
+          Bc[2 * e] = make_float2(0.5f * fmaf(b4.x, sx, t4.x), 0.5f * fmaf(b4.y, sy, t4.y));
+          Bc[2 * e + 1] = make_float2(0.5f * fmaf(b4.z, sz, t4.z), 0.5f * fmaf(b4.w, sw, t4.w));
+        }
+      };
+      // steps st = 0 .. 2 NU - 1, fully unrolled for the warp's tile count NU (so every register index is a compile-time constant)
+      auto ln_part = [&](auto nu_c) {
+        constexpr int NU = decltype(nu_c)::value;
+        uint32_t w[2][16];
+        load_consts(0);
+        tc::tmem_ld16_issue(park, w[0]);
+#pragma unroll
+        for (int st = 0; st < 2 * NU; ++st) {
+          const int a = st / NU, u = st % NU;
+          tc::tmem_wait_ld();                                    // w[st & 1] = step st
+          if (st + 1 < 2 * NU) tc::tmem_ld16_issue(park + (uint32_t)(((st + 1) % NU) * 32 + ((st + 1) / NU) * 16), w[(st + 1) & 1]);
+          if (st == NU) load_consts(1);
+          const int ra = (mt0 + u) * 16 + g;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float2 rs2 = make_float2(rn[u][r].x, rn[u][r].x), nm2 = make_float2(rn[u][r].y, rn[u][r].y);
+            uint32_t o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float2 v = make_float2(__uint_as_float(w[st & 1][4 * c + 2 * r]), __uint_as_float(w[st & 1][4 * c + 2 * r + 1]));
+              const float2 hv = ffma2(ffma2(v, rs2, nm2), G[c], Bc[c]);
+              const float2 sv = ffma2(hv, make_float2(tanh_approx(hv.x), tanh_approx(hv.y)), hv);
+              o[c] = pack2(sv.x, sv.y);
+            }
+            const int t = ra + 8 * r;
+            if (t < T) *reinterpret_cast<uint4*>(z + (row0 + t) * (size_t)D + colA + 32 * a) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
-        float2 rsd[2], nmr[2];   // per row: (rstd, rstd), (-mean rstd, -mean rstd)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const float4* sp = reinterpret_cast<const float4*>(stat + (u * 16 + g + 8 * r) * NH);
-          const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];   // heads (0,1) (2,3) (4,5) (6,7): (sum, sumsq) pairs
-          const float s = ((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z));
-          const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
-          const float mean = s * (1.f / D);
-          // y is O(1) (a convex combination of V rows), so E[x^2] - mean^2 is safe in fp32
-          const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
-          rsd[r] = make_float2(rstd, rstd); nmr[r] = make_float2(-mean * rstd, -mean * rstd);
-        }
-        const int ra = (mt0 + u) * 16 + g;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          uint32_t o[8];
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            const float2 hv = ffma2(ffma2(make_float2(y[nt][2 * r], y[nt][2 * r + 1]), rsd[r], nmr[r]), G[nt], Bc[nt]);
-            const float2 v = ffma2(hv, make_float2(tanh_approx(hv.x), tanh_approx(hv.y)), hv);
-            o[nt] = pack2(v.x, v.y);
-          }
-          const int t = ra + 8 * r;
-          if (t < T) {
-            bf16* dst = z + (row0 + t) * (size_t)D + colA;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(dst + 32) = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-        }
-      }
+      };
+      static_assert(MH == 3, "the dispatch below spells out 1 .. 3 tiles");
+      if (nu == 3) ln_part(std::integral_constant<int, 3>{});
+      else if (nu == 2) ln_part(std::integral_constant<int, 2>{});
+      else ln_part(std::integral_constant<int, 1>{});
     }
   } else {
     // ========================================================== A warps ==========================================================
     const int wq = warp - NYW;
-    const int lq = wq & 1, dq = wq >> 1;      // this warp's 32 x 32 quadrant of A^T[l][d]: l-half lq, d-half dq
-    const uint32_t apark = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)APARK_COL;
+    const int lq = wq & 1, d8 = wq >> 1;      // this warp's 32 x 16 tile of A^T[l][d]: l-half lq, d = 16 d8 .. + 15
+    const uint32_t apark = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(APARK_COL + (wq >> 2) * NH * 8);
     const uint32_t ones[4] = {BF2_ONES, BF2_ONES, BF2_ONES, BF2_ONES};
-    // fragment addresses of k-step 0 (row kt * 16 adds kt * 2048 bytes: 16 rows of 128 bytes, the XOR pattern repeats every 8 rows)
+    // fragment addresses of k-step 0 (k-step kt adds kt * 2048 bytes: 16 rows of 128 bytes, the XOR pattern repeats every 8 rows)
     const int vr = rr + ((mat >> 1) << 3), kr = rr + ((mat & 1) << 3);
     const uint32_t v_off0 = swz(vr, 4 * lq + (mat & 1)), v_off1 = swz(vr, 4 * lq + 2 + (mat & 1));
-    const uint32_t k_off0 = swz(kr, 4 * dq + (mat >> 1)), k_off1 = swz(kr, 4 * dq + 2 + (mat >> 1));
+    const uint32_t k_off = swz(kr, 2 * d8 + (mat >> 1));
     const int n_heads = n_iter * NH;          // (sample, head) units of this CTA, in order
     auto issue = [&](int hc) {                // one lane: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
       const int smp = (int)blockIdx.x + (hc >> 3) * (int)gridDim.x, hh = hc & 7, s0 = 2 * (hc & 1);
@@ -307,48 +311,43 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::mbar_wait(kv_full(s0), par);
         tc::mbar_wait(kv_full(s0 + 1), par);
         // A^T[l][d] = sum_t V[t][l] K'[t][d]; cs = ones . K' = the column sums of K' in the layout of the accumulator columns
-        float acc[2][4][4], cs[4][4];
+        float acc[2][2][4], cs[2][4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < 2; ++nt) {
           cs[nt][0] = cs[nt][1] = cs[nt][2] = cs[nt][3] = 0.f;
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
         }
-        uint32_t fa[2][4], fb[2][4];   // fragments of the current k-step; the next step's are loaded under its products
+        uint32_t fa[2][4], fb[4];   // fragments of the current k-step; the next step's are loaded under its products
         ldsm_x4_trans(vs_addr + v_off0, fa[0][0], fa[0][1], fa[0][2], fa[0][3]);
         ldsm_x4_trans(vs_addr + v_off1, fa[1][0], fa[1][1], fa[1][2], fa[1][3]);
-        ldsm_x4_trans(ks_addr + k_off0, fb[0][0], fb[0][1], fb[0][2], fb[0][3]);
-        ldsm_x4_trans(ks_addr + k_off1, fb[1][0], fb[1][1], fb[1][2], fb[1][3]);
+        ldsm_x4_trans(ks_addr + k_off, fb[0], fb[1], fb[2], fb[3]);
 #pragma unroll 2
         for (int kt = 0; kt < n_kt; ++kt) {   // 16 frames per k-step
-          uint32_t na[2][4], nb[2][4];
+          uint32_t na[2][4], nb[4];
           if (kt + 1 < n_kt) {
             const uint32_t o = (uint32_t)(kt + 1) * 2048u;
             ldsm_x4_trans(vs_addr + v_off0 + o, na[0][0], na[0][1], na[0][2], na[0][3]);
             ldsm_x4_trans(vs_addr + v_off1 + o, na[1][0], na[1][1], na[1][2], na[1][3]);
-            ldsm_x4_trans(ks_addr + k_off0 + o, nb[0][0], nb[0][1], nb[0][2], nb[0][3]);
-            ldsm_x4_trans(ks_addr + k_off1 + o, nb[1][0], nb[1][1], nb[1][2], nb[1][3]);
+            ldsm_x4_trans(ks_addr + k_off + o, nb[0], nb[1], nb[2], nb[3]);
           }
-#pragma unroll
-          for (int np = 0; np < 2; ++np) {    // two d n-tiles per ldmatrix.x4
-            mma_bf16(acc[0][2 * np], fa[0], fb[np][0], fb[np][1]);
-            mma_bf16(acc[0][2 * np + 1], fa[0], fb[np][2], fb[np][3]);
-            mma_bf16(acc[1][2 * np], fa[1], fb[np][0], fb[np][1]);
-            mma_bf16(acc[1][2 * np + 1], fa[1], fb[np][2], fb[np][3]);
-            mma_bf16(cs[2 * np], ones, fb[np][0], fb[np][1]);
-            mma_bf16(cs[2 * np + 1], ones, fb[np][2], fb[np][3]);
-          }
+          mma_bf16(acc[0][0], fa[0], fb[0], fb[1]);
+          mma_bf16(acc[0][1], fa[0], fb[2], fb[3]);
+          mma_bf16(acc[1][0], fa[1], fb[0], fb[1]);
+          mma_bf16(acc[1][1], fa[1], fb[2], fb[3]);
+          mma_bf16(cs[0], ones, fb[0], fb[1]);
+          mma_bf16(cs[1], ones, fb[2], fb[3]);
           if (kt + 1 < n_kt) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { fa[0][e] = na[0][e]; fa[1][e] = na[1][e]; fb[0][e] = nb[0][e]; fb[1][e] = nb[1][e]; }
+            for (int e = 0; e < 4; ++e) { fa[0][e] = na[0][e]; fa[1][e] = na[1][e]; fb[e] = nb[e]; }
           }
         }
-        // every fragment of this unit's K' / V tiles has been consumed by a product: the two ring slots go back to the producer
+        // every fragment of this unit's K' / V tiles has been consumed by a product: the two ring slots go back to the refill duty
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(kv_empty(hc & 1));
-        uint32_t pk[16];   // [nt][mi][rows g | g + 8]: bf16 pairs of columns d = 32 dq + 8 nt + 2 q, + 1
+        uint32_t pk[8];   // [nt][mi][rows g | g + 8]: bf16 pairs of columns d = 16 d8 + 8 nt + 2 q, + 1
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < 2; ++nt) {
           const float2 inv = make_float2(rcp_approx(cs[nt][0]), rcp_approx(cs[nt][1]));
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
@@ -357,9 +356,9 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             pk[4 * nt + 2 * mi + 1] = pack2(hi.x, hi.y);
           }
         }
-        tc::tmem_st16(apark + (uint32_t)(hh * 16), pk);
-        // refill duty rotates over the A warps: by now (after the pack / park) the other three have normally arrived, so the wait is short
-        if (wq == (hc & 3) && lane == 0 && hc + 2 < n_heads) {
+        tc::tmem_st8(apark + (uint32_t)(hh * 8), pk);
+        // refill duty rotates over the A warps: by now (after the pack / park) the others have normally arrived, so the wait is short
+        if (wq == (hc & 7) && lane == 0 && hc + 2 < n_heads) {
           tc::mbar_wait(kv_empty(hc & 1), par);
           issue(hc + 2);
         }
@@ -368,20 +367,20 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- phase 2: parked heads -> the per-head A^T slots, each as soon as both readers of the previous sample have released it
 #pragma unroll 1
       for (int hh = 0; hh < NH; ++hh) {
-        uint32_t pk[16];
-        tc::tmem_ld16(apark + (uint32_t)(hh * 16), pk);
+        uint32_t pk[8];
+        tc::tmem_ld8(apark + (uint32_t)(hh * 8), pk);
         tc::mbar_wait(a_empty(hh), (uint32_t)((i & 1) ^ 1));
         uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
             const int l = 32 * lq + 16 * mi + g;
-            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l), 4 * dq + nt) + q * 4) = pk[4 * nt + 2 * mi];
-            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l + 8), 4 * dq + nt) + q * 4) = pk[4 * nt + 2 * mi + 1];
+            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l), 2 * d8 + nt) + q * 4) = pk[4 * nt + 2 * mi];
+            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l + 8), 2 * d8 + nt) + q * 4) = pk[4 * nt + 2 * mi + 1];
           }
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's quadrant of A^T is written
+        if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's tile of A^T is written
       }
     }
   }

@@ -278,6 +278,35 @@ inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   if (const float* p = emu_tmem_row<16>(taddr, "tcgen05.ld")) memcpy(r, p, 16 * 4);
   __syncwarp();
 }
+inline void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  if (float* p = emu_tmem_row<8>(taddr, "tcgen05.st")) memcpy(p, r, 8 * 4);
+  __syncwarp();
+}
+inline void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  emu::delay("EMU_DELAY_TMEM_LD");
+  if (const float* p = emu_tmem_row<8>(taddr, "tcgen05.ld")) memcpy(r, p, 8 * 4);
+  __syncwarp();
+}
+// split load: the destination registers hold poison until the thread's tcgen05.wait::ld (a use before the wait fails parity)
+struct PendingTmemLd { uint32_t* dst; const float* src; int n; };
+inline std::unordered_map<emu::Thread*, std::vector<PendingTmemLd>>& pending_tmem_lds() {
+  static std::unordered_map<emu::Thread*, std::vector<PendingTmemLd>> p;
+  return p;
+}
+inline void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  emu::delay("EMU_DELAY_TMEM_LD");
+  for (int i = 0; i < 16; ++i) r[i] = 0x7FC0DEADu;   // NaN poison
+  if (const float* p = emu_tmem_row<16>(taddr, "tcgen05.ld")) pending_tmem_lds()[&emu::self()].push_back(PendingTmemLd{r, p, 16});
+  __syncwarp();
+}
+inline void tmem_wait_ld() {
+  auto it = pending_tmem_lds().find(&emu::self());
+  if (it != pending_tmem_lds().end()) {
+    for (const PendingTmemLd& l : it->second) memcpy(l.dst, l.src, (size_t)l.n * 4);
+    pending_tmem_lds().erase(it);
+  }
+  __syncwarp();
+}
 template <int CG, int COLS> inline void tmem_alloc(uint32_t slot) {
   static_assert(COLS == 32 || COLS == 64 || COLS == 128 || COLS == 256 || COLS == 512, "TMEM allocations are powers of two >= 32 columns");
   emu::Cta* c = emu::self().cta;
