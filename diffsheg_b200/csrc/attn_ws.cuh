@@ -71,6 +71,18 @@ static_assert(Q_OFF % 1024 == 0 && QBOX_BYTES % 1024 == 0 && A_OFF % 1024 == 0 &
               "SWIZZLE_128B tiles start on 1024-byte boundaries");
 static_assert(APARK_COL + (NAW / 4) * NH * 8 <= TMEM_COLS, "parking space");
 
+// mbarrier wait that SLEEPS (suspend-time hint) instead of spinning: a waiting warp must not take issue slots from the working ones.
+// Watchdog like tc::mbar_wait: a lost arrive becomes a launch error after 4 s, not a hung GPU.
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  if (tc::mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  while (!tc::mbar_try_wait_hint(bar, parity, 20000u)) {
+    const uint64_t now = tc::globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) tc::trap();
+  }
+}
+
 __device__ __forceinline__ void half_sync(int half) { prims::named_bar_sync<32 * NH>(1 + half); }     // ids 1, 2: the 8 Y warps of a row half
 
 // shared-memory row of A^T that holds output column l of the head: n-tile nt = 4 (l >> 5) + ((l >> 1) & 3), row 2 ((l >> 3) & 3) + (l & 1)
@@ -135,9 +147,9 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float* const sc = ss + (size_t)(smp % B) * ss_ld + colA;   // the sample's modulation row (scale | shift) at this thread's columns
       if (nu > 0) {
         prims::prefetch_l1(sc); prims::prefetch_l1(sc + 32); prims::prefetch_l1(sc + D); prims::prefetch_l1(sc + D + 32);   // read after the products
-        tc::mbar_wait(q_full(warp), par);
+        wait_bar(q_full(warp), par);
       }
-      tc::mbar_wait(a_full(h), par);
+      wait_bar(a_full(h), par);
 #pragma unroll 1
       for (int u = 0; u < nu; ++u) {
         // ---- Y[t][l] = Q'[t][:] . A: the 16 x 64 tile of (tile u, head h); row sums of Q' on the tensor core (Q' . ones)
@@ -308,8 +320,8 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int hc = i * NH + hh, s0 = 2 * (hc & 1);
         const uint32_t par = (uint32_t)((hc >> 1) & 1);
         const uint32_t ks_addr = sbase + RING_OFF + s0 * TILE_BYTES, vs_addr = ks_addr + TILE_BYTES;
-        tc::mbar_wait(kv_full(s0), par);
-        tc::mbar_wait(kv_full(s0 + 1), par);
+        wait_bar(kv_full(s0), par);
+        wait_bar(kv_full(s0 + 1), par);
         // A^T[l][d] = sum_t V[t][l] K'[t][d]; cs = ones . K' = the column sums of K' in the layout of the accumulator columns
         float acc[2][2][4], cs[2][4];
 #pragma unroll
@@ -318,28 +330,31 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) { acc[mi][nt][0] = acc[mi][nt][1] = acc[mi][nt][2] = acc[mi][nt][3] = 0.f; }
         }
-        uint32_t fa[2][4], fb[4];   // fragments of the current k-step; the next step's are loaded under its products
-        ldsm_x4_trans(vs_addr + v_off0, fa[0][0], fa[0][1], fa[0][2], fa[0][3]);
-        ldsm_x4_trans(vs_addr + v_off1, fa[1][0], fa[1][1], fa[1][2], fa[1][3]);
-        ldsm_x4_trans(ks_addr + k_off, fb[0], fb[1], fb[2], fb[3]);
-#pragma unroll 2
-        for (int kt = 0; kt < n_kt; ++kt) {   // 16 frames per k-step
-          uint32_t na[2][4], nb[4];
-          if (kt + 1 < n_kt) {
-            const uint32_t o = (uint32_t)(kt + 1) * 2048u;
-            ldsm_x4_trans(vs_addr + v_off0 + o, na[0][0], na[0][1], na[0][2], na[0][3]);
-            ldsm_x4_trans(vs_addr + v_off1 + o, na[1][0], na[1][1], na[1][2], na[1][3]);
-            ldsm_x4_trans(ks_addr + k_off + o, nb[0], nb[1], nb[2], nb[3]);
-          }
+        // two fragment sets in ping-pong (no register copies): a k-step's fragments are loaded under the products of the step before
+        uint32_t fa0[2][4], fb0[4], fa1[2][4], fb1[4];
+        auto load_frags = [&](uint32_t (&fa)[2][4], uint32_t (&fb)[4], int kt) {
+          const uint32_t o = (uint32_t)kt * 2048u;
+          ldsm_x4_trans(vs_addr + v_off0 + o, fa[0][0], fa[0][1], fa[0][2], fa[0][3]);
+          ldsm_x4_trans(vs_addr + v_off1 + o, fa[1][0], fa[1][1], fa[1][2], fa[1][3]);
+          ldsm_x4_trans(ks_addr + k_off + o, fb[0], fb[1], fb[2], fb[3]);
+        };
+        auto products = [&](const uint32_t (&fa)[2][4], const uint32_t (&fb)[4]) {
           mma_bf16(acc[0][0], fa[0], fb[0], fb[1]);
           mma_bf16(acc[0][1], fa[0], fb[2], fb[3]);
           mma_bf16(acc[1][0], fa[1], fb[0], fb[1]);
           mma_bf16(acc[1][1], fa[1], fb[2], fb[3]);
           mma_bf16(cs[0], ones, fb[0], fb[1]);
           mma_bf16(cs[1], ones, fb[2], fb[3]);
-          if (kt + 1 < n_kt) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { fa[0][e] = na[0][e]; fa[1][e] = na[1][e]; fb[e] = nb[e]; }
+        };
+        load_frags(fa0, fb0, 0);
+#pragma unroll 1
+        for (int kt = 0; kt < n_kt; kt += 2) {   // 16 frames per k-step, two k-steps per iteration
+          const bool two = kt + 1 < n_kt;        // warp-uniform
+          if (two) load_frags(fa1, fb1, kt + 1);
+          products(fa0, fb0);
+          if (two) {
+            if (kt + 2 < n_kt) load_frags(fa0, fb0, kt + 2);
+            products(fa1, fb1);
           }
         }
         // every fragment of this unit's K' / V tiles has been consumed by a product: the two ring slots go back to the refill duty
@@ -359,7 +374,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::tmem_st8(apark + (uint32_t)(hh * 8), pk);
         // refill duty rotates over the A warps: by now (after the pack / park) the others have normally arrived, so the wait is short
         if (wq == (hc & 7) && lane == 0 && hc + 2 < n_heads) {
-          tc::mbar_wait(kv_empty(hc & 1), par);
+          wait_bar(kv_empty(hc & 1), par);
           issue(hc + 2);
         }
         __syncwarp();
@@ -369,7 +384,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int hh = 0; hh < NH; ++hh) {
         uint32_t pk[8];
         tc::tmem_ld8(apark + (uint32_t)(hh * 8), pk);
-        tc::mbar_wait(a_empty(hh), (uint32_t)((i & 1) ^ 1));
+        wait_bar(a_empty(hh), (uint32_t)((i & 1) ^ 1));
         uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)

@@ -98,7 +98,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   uint64_t t0 = 0;
   while (true) {
+#if defined(DSHEG_MBAR_SLEEP) && DSHEG_MBAR_SLEEP
+    done = spins ? mbar_try_wait_hint(bar, parity, 20000u) : mbar_try_wait(bar, parity);   // experiment: sleep instead of spinning
+#else
     done = mbar_try_wait(bar, parity);
+#endif
     if (done) break;
     // watchdog: a lost arrive / wrong descriptor becomes a launch error after 4 s, not a hung GPU
     if ((++spins & 0x3FFu) == 0) {

@@ -42,6 +42,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done;
 }
+// the same with a suspend-time hint (ns): the thread may sleep in hardware until the phase completes or the time is up, instead of
+// spinning through the issue slots of the warps that do have work (attn_ws.cuh: 4 waiting warps per scheduler stole ~0.7 IPC)
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return done;
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -115,6 +115,7 @@ inline uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   emu::self().waiting_on = "";
   return 0;
 }
+inline uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t) { return mbar_try_wait(bar, parity); }
 
 // ---- TMA ------------------------------------------------------------------------------------------------------------------
 inline void tma_copy(const CUtensorMap* m, emu::Cta* cta, uint32_t smem_off, int c0, int c1, bool load) {
