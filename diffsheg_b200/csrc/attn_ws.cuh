@@ -216,6 +216,25 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         __syncwarp();
         continue;
       }
+      float2 G[4], Bc[4];
+      float4 raw[4];   // the sample's (scale | shift) values of one run: in flight well before they are folded
+      auto load_raw = [&](int a) {
+        raw[0] = __ldg(reinterpret_cast<const float4*>(sc + 32 * a)); raw[1] = __ldg(reinterpret_cast<const float4*>(sc + 32 * a + 4));
+        raw[2] = __ldg(reinterpret_cast<const float4*>(sc + D + 32 * a)); raw[3] = __ldg(reinterpret_cast<const float4*>(sc + D + 32 * a + 4));
+      };
+      auto load_consts = [&](int a) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float4 s4 = raw[e], t4 = raw[2 + e];
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + colA + 32 * a + 4 * e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + colA + 32 * a + 4 * e));
+          const float sx = 1.f + s4.x, sy = 1.f + s4.y, sz = 1.f + s4.z, sw = 1.f + s4.w;
+          G[2 * e] = make_float2(0.5f * g4.x * sx, 0.5f * g4.y * sy);
+          G[2 * e + 1] = make_float2(0.5f * g4.z * sz, 0.5f * g4.w * sw);
+          Bc[2 * e] = make_float2(0.5f * fmaf(b4.x, sx, t4.x), 0.5f * fmaf(b4.y, sy, t4.y));
+          Bc[2 * e + 1] = make_float2(0.5f * fmaf(b4.z, sz, t4.z), 0.5f * fmaf(b4.w, sw, t4.w));
+        }
+      };
+      load_raw(0);       // L2 round trip under the barrier wait
       half_sync(half);   // the partials of all 8 heads of this half's rows are in the table
       // ---- LayerNorm + modulation + SiLU:  t = ((v - mean) rstd g + b)(1 + scale) + shift = 2 ((v - mean) rstd G + Bc),  SiLU(t) = h + h tanh(h), h = t / 2
       float2 rn[MH][2];   // per tile and row (g, g + 8): (rstd, -mean rstd)
@@ -238,19 +257,6 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const size_t row0 = (size_t)smp * T;
       // steps st = 0 .. 2 nu - 1: (run a, tile u) = (st / nu, st % nu), the thread's run a = columns [colA + 32 a, + 8) = n-tiles 4 a .. 4 a + 3 of
       // tile u = 16 parked columns; a step's load is in flight while the previous step is processed.
-      float2 G[4], Bc[4];
-      auto load_consts = [&](int a) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + 32 * a + 4 * e)), t4 = __ldg(reinterpret_cast<const float4*>(sc + D + 32 * a + 4 * e));
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + colA + 32 * a + 4 * e)), b4 = __ldg(reinterpret_cast<const float4*>(ln_b + colA + 32 * a + 4 * e));
-          const float sx = 1.f + s4.x, sy = 1.f + s4.y, sz = 1.f + s4.z, sw = 1.f + s4.w;
-          G[2 * e] = make_float2(0.5f * g4.x * sx, 0.5f * g4.y * sy);
-          G[2 * e + 1] = make_float2(0.5f * g4.z * sz, 0.5f * g4.w * sw);
-          Bc[2 * e] = make_float2(0.5f * fmaf(b4.x, sx, t4.x), 0.5f * fmaf(b4.y, sy, t4.y));
-          Bc[2 * e + 1] = make_float2(0.5f * fmaf(b4.z, sz, t4.z), 0.5f * fmaf(b4.w, sw, t4.w));
-        }
-      };
       // steps st = 0 .. 2 NU - 1, fully unrolled for the warp's tile count NU (so every register index is a compile-time constant)
       auto ln_part = [&](auto nu_c) {
         constexpr int NU = decltype(nu_c)::value;
@@ -262,7 +268,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int a = st / NU, u = st % NU;
           tc::tmem_wait_ld();                                    // w[st & 1] = step st
           if (st + 1 < 2 * NU) tc::tmem_ld16_issue(park + (uint32_t)(((st + 1) % NU) * 32 + ((st + 1) / NU) * 16), w[(st + 1) & 1]);
-          if (st == NU) load_consts(1);
+          if (st == NU) { load_raw(1); load_consts(1); }   // (loading run 1's values a step early costs 360 bytes of spills at 80 registers)
           const int ra = (mt0 + u) * 16 + g;
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
@@ -295,6 +301,16 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int vr = rr + ((mat >> 1) << 3), kr = rr + ((mat & 1) << 3);
     const uint32_t v_off0 = swz(vr, 4 * lq + (mat & 1)), v_off1 = swz(vr, 4 * lq + 2 + (mat & 1));
     const uint32_t k_off = swz(kr, 2 * d8 + (mat >> 1));
+    // byte offsets of this thread's 8 words inside a head's A^T slot: [nt][mi][rows g | g + 8] (row-permuted, swizzled)
+    uint32_t a_off[8];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int l = 32 * lq + 16 * mi + g;
+        a_off[4 * nt + 2 * mi] = swz(a_row(l), 2 * d8 + nt) + q * 4;
+        a_off[4 * nt + 2 * mi + 1] = swz(a_row(l + 8), 2 * d8 + nt) + q * 4;
+      }
     const int n_heads = n_iter * NH;          // (sample, head) units of this CTA, in order
     auto issue = [&](int hc) {                // one lane: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
       const int smp = (int)blockIdx.x + (hc >> 3) * (int)gridDim.x, hh = hc & 7, s0 = 2 * (hc & 1);
@@ -314,7 +330,8 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 #pragma unroll 1
     for (int i = 0; i < n_iter; ++i) {
-      // ---- phase 1: A^T of the sample's 8 heads, normalised, packed to bf16 and parked in tensor memory (independent of the Y warps)
+      // ---- phase 1: A^T of the sample's 8 heads, normalised and packed to bf16 (independent of the Y warps)
+      uint32_t parked = 0;   // heads of this sample that wait in tensor memory for their slot
 #pragma unroll 1
       for (int hh = 0; hh < NH; ++hh) {
         const int hc = i * NH + hh, s0 = 2 * (hc & 1);
@@ -347,14 +364,24 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mma_bf16(cs[1], ones, fb[2], fb[3]);
         };
         load_frags(fa0, fb0, 0);
-#pragma unroll 1
-        for (int kt = 0; kt < n_kt; kt += 2) {   // 16 frames per k-step, two k-steps per iteration
-          const bool two = kt + 1 < n_kt;        // warp-uniform
-          if (two) load_frags(fa1, fb1, kt + 1);
-          products(fa0, fb0);
-          if (two) {
-            if (kt + 2 < n_kt) load_frags(fa0, fb0, kt + 2);
+        if (n_kt == TP / 16) {   // the full-length window (T = 81 .. 96): six k-steps, fully unrolled
+#pragma unroll
+          for (int kt = 0; kt < TP / 16; kt += 2) {
+            load_frags(fa1, fb1, kt + 1);
+            products(fa0, fb0);
+            if (kt + 2 < TP / 16) load_frags(fa0, fb0, kt + 2);
             products(fa1, fb1);
+          }
+        } else {
+#pragma unroll 1
+          for (int kt = 0; kt < n_kt; kt += 2) {   // 16 frames per k-step, two k-steps per iteration
+            const bool two = kt + 1 < n_kt;        // warp-uniform
+            if (two) load_frags(fa1, fb1, kt + 1);
+            products(fa0, fb0);
+            if (two) {
+              if (kt + 2 < n_kt) load_frags(fa0, fb0, kt + 2);
+              products(fa1, fb1);
+            }
           }
         }
         // every fragment of this unit's K' / V tiles has been consumed by a product: the two ring slots go back to the refill duty
@@ -371,31 +398,37 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             pk[4 * nt + 2 * mi + 1] = pack2(hi.x, hi.y);
           }
         }
-        tc::tmem_st8(apark + (uint32_t)(hh * 8), pk);
-        // refill duty rotates over the A warps: by now (after the pack / park) the others have normally arrived, so the wait is short
+        // the head's slot is normally free by now (both readers of the previous sample are done with it): write it directly.  Only a
+        // head that finishes EARLY (the A warps running ahead of the Y warps) is parked in tensor memory and copied in phase 2.
+        uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
+        if (tc::mbar_try_wait(a_empty(hh), (uint32_t)((i & 1) ^ 1))) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) *reinterpret_cast<uint32_t*>(as_ptr + a_off[e]) = pk[e];
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's tile of A^T is written
+        } else {
+          tc::tmem_st8(apark + (uint32_t)(hh * 8), pk);
+          parked |= 1u << hh;
+        }
+        // refill duty rotates over the A warps: by now the others have normally arrived, so the wait is short
         if (wq == (hc & 7) && lane == 0 && hc + 2 < n_heads) {
           wait_bar(kv_empty(hc & 1), par);
           issue(hc + 2);
         }
         __syncwarp();
       }
-      // ---- phase 2: parked heads -> the per-head A^T slots, each as soon as both readers of the previous sample have released it
+      // ---- phase 2: parked heads -> their A^T slots, each as soon as both readers of the previous sample have released it
 #pragma unroll 1
       for (int hh = 0; hh < NH; ++hh) {
+        if (!((parked >> hh) & 1u)) continue;   // warp-uniform
         uint32_t pk[8];
         tc::tmem_ld8(apark + (uint32_t)(hh * 8), pk);
         wait_bar(a_empty(hh), (uint32_t)((i & 1) ^ 1));
         uint8_t* const as_ptr = sm + A_OFF + hh * A_BYTES;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            const int l = 32 * lq + 16 * mi + g;
-            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l), 2 * d8 + nt) + q * 4) = pk[4 * nt + 2 * mi];
-            *reinterpret_cast<uint32_t*>(as_ptr + swz(a_row(l + 8), 2 * d8 + nt) + q * 4) = pk[4 * nt + 2 * mi + 1];
-          }
+        for (int e = 0; e < 8; ++e) *reinterpret_cast<uint32_t*>(as_ptr + a_off[e]) = pk[e];
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's tile of A^T is written
+        if (lane == 0) tc::mbar_arrive(a_full(hh));
       }
     }
   }
