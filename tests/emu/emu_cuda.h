@@ -293,6 +293,14 @@ template <class T> static inline T __shfl_sync(uint32_t, T v, int src_lane) {
   memcpy(&r, slots[src_lane & 31], sizeof(T));
   return r;
 }
+static inline int __all_sync(uint32_t, int pred) {
+  uint8_t(*slots)[64] = emu::warp_exchange(&pred, sizeof(int), "__all_sync");
+  int all = 1;
+  for (int l = 0; l < 32; ++l) { int v; memcpy(&v, slots[l], sizeof(int)); all &= (v != 0); }
+  return all;
+}
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t old = *p; *p = old + v; ++emu::rt().progress; return old; }   // fibers never preempt
+static inline void __threadfence_block() {}
 static inline size_t __cvta_generic_to_shared(const void* p) {
   emu::Cta* c = emu::self().cta;
   const uint8_t* b = static_cast<const uint8_t*>(p);

@@ -303,12 +303,15 @@ def test_attn_ws_kernel_source_on_emulator(Bn, T, Tk, nb, grid):
     assert float((got - want).abs().max() / want.abs().max()) < 8e-3     # bf16 operands and output; LayerNorm on fp32 Y
 
 
+@pytest.mark.parametrize("T", [40, 88])
 @pytest.mark.parametrize("env", [{"EMU_SCHED": "reverse"}, {"EMU_SCHED": "shuffle"}, {"EMU_SCHED": "shuffle", "EMU_SCHED_SEED": "5", "EMU_DELAY_TMA": "25"},
-                                 {"EMU_DELAY_TMA": "40"}, {"EMU_DELAY_TMEM_LD": "40"}])
-def test_attn_ws_is_independent_of_the_thread_schedule(env, monkeypatch):
+                                 {"EMU_SCHED": "shuffle", "EMU_SCHED_SEED": "11"}, {"EMU_DELAY_TMA": "40"}, {"EMU_DELAY_TMEM_LD": "40"}])
+def test_attn_ws_is_independent_of_the_thread_schedule(env, T, monkeypatch):
     """Stand-in for racecheck: reversed / shuffled thread orders, late TMA arrivals and slow TMEM loads must reproduce the default
-    schedule's output bit for bit (4 samples on ONE persistent CTA: every ring slot, A^T slot, Q' box and parity wraps)."""
-    qn, kn, v, g, b, ss = _ws_case(4, 40, seed=3)
+    schedule's output bit for bit (4 samples on ONE persistent CTA: every ring slot, A^T slot, Q' box and parity wraps; T = 88 runs the
+    unrolled k-loop, T = 40 the generic one).  A lane-divergent choice between two branches that hold warp collectives (found here
+    before it ever misbehaved on hardware) shows up as garbage operands under the shuffled schedules."""
+    qn, kn, v, g, b, ss = _ws_case(4, T, seed=3)
     base = run_attention_ws(qn, kn, v, g, b, ss, grid=1)
     assert np.array_equal(base, run_attention_ws(qn, kn, v, g, b, ss, grid=3))    # and of the sample -> CTA assignment
     for k, val in env.items():
