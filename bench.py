@@ -347,7 +347,7 @@ def run_ours(args):
             "peak_source": pk["source"] + ", sustained" + (" bf16 / 2 (dense TF32 rate is half the bf16 rate)" if args.precision == "tf32" else ""),
             "launches_per_step": g["count"], "ms_per_step": g["ms"], "share_of_step": g["ms"] / ms if world == 1 else None,
             "executed_flops_per_step": g["work"]}
-    attn_kernel = ("attn_tma_kernel (persistent, TMA-staged linear attention + LN/modulate/SiLU; attn_small for the audio layer)"
+    attn_kernel = ("attn_ws_kernel (persistent, TMA-staged, warp-specialised linear attention + LN/modulate/SiLU; attn_small for the audio layer)"
                    if args.precision == "bf16" else "attn_kernel (generic fp32 SIMT linear attention)")
     roof_attn = {"kernel": attn_kernel, "bound": "hbm", "achieved": attn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                  "frac": attn_gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "launches_per_step": at["count"],
@@ -359,7 +359,7 @@ def run_ours(args):
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")))
         if args.precision == "bf16" and args.config in ("2", "5") and not any(k.startswith("DSHEG_") and v for k, v in os.environ.items()):
-            ge, ae = tr.get("gemm_tc_kernel"), tr.get("attn_tma_kernel")
+            ge, ae = tr.get("gemm_tc_kernel"), tr.get("attn_ws_kernel")
             if ge:
                 roof["traffic"] = ge["dram_bytes_per_launch"]
                 roof["traffic_note"] = ge["note"] + f"; algorithmic operand+output bytes of the same launches: {ALGO_GEMM_BYTES_PER_LAYER / 7 / 1e6:.0f} MB per launch"

@@ -4,12 +4,12 @@
 // the Q and K columns hold exp(value - static shift) (softmax is shift-invariant; pack.py:expo_shift proves the range), V is plain:
 //   A = K'^T V / colsum(K')  [64 x 64 per head]     Y = Q' A / rowsum(Q')     z = SiLU(LN_512(Y) * (1 + scale) + shift)
 //
-// Why this shape.  attn_tma.cuh (round 2's first TMA kernel) has all 16 compute warps of the one CTA an SM can hold walk through the
+// Why this shape.  Round 2's first TMA kernel (attn_tma, deleted; profiles/r02/ci1, call9) had all 16 compute warps of the one CTA an SM can hold walk through the
 // same phases together -- A^T, Y, a CTA-wide barrier, the LayerNorm pass -- so the tensor pipe idles during LayerNorm, the FP32 / MUFU
 // pipes idle during the products, and every dependency stall is exposed at 4 warps per scheduler (ncu: issue slots 34 % busy, 0.42 of
 // the copy peak in the sampling loop).  Two samples cannot be resident (Y of one sample is 96 KB of shared memory).  Here the phases
 // belong to DIFFERENT warps working on DIFFERENT samples, and Y never exists in shared memory:
-//   * 8 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep, refilled by the A warps in turn) into the
+//   * 8 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep, refilled by the A warps in turn; half-tile granularity with a last-arriver refill was tried and lost: profiles/r02/call15) into the
 //     normalised bf16 A^T of that head (a 32 x 16 tile per warp; the column sums of K' come out of the same fragments, ones . K',
 //     in exactly the accumulator layout, so nothing is exchanged between the warps) and PARK it in tensor memory (8 words per
 //     thread and head).  That is phase 1 of a sample and needs nothing from the Y warps, so it runs a whole sample ahead.  Phase 2
@@ -35,7 +35,8 @@
 #pragma once
 #include <type_traits>
 
-#include "attn_tma.cuh"
+#include "attn_v3.cuh"
+#include "gemm_tc.cuh"   // tc:: mbarrier / TMA primitives, tensor-map encoder entry point
 
 namespace dsheg {
 namespace aws {
@@ -44,7 +45,7 @@ using av3::TP; using av3::HD; using av3::D; using av3::TILE_BYTES;
 using av3::pack2; using av3::swz;
 using prims::ldsm_x4; using prims::ldsm_x4_trans; using prims::mma_bf16; using prims::tanh_approx; using prims::rcp_approx;
 using prims::ffma2; using prims::fadd2; using prims::fmul2;
-using atm::BF2_ONES;
+constexpr uint32_t BF2_ONES = 0x3F803F80u;      // bf16x2 (1.0, 1.0)
 
 constexpr int NH = 8;                          // heads
 constexpr int NYW = 2 * NH;                    // Y warps: head = warp & 7, row half = warp >> 3
@@ -59,11 +60,10 @@ constexpr int A_OFF = Q_OFF + NYW * QBOX_BYTES;               // [NH] A^T slots
 constexpr int RING_OFF = A_OFF + NH * A_BYTES;                // [NST] K' / V tiles
 constexpr int STAT_OFF = RING_OFF + NST * TILE_BYTES;         // [sample parity][half][tile][row 16][head 8] float2 (sum, sumsq)
 constexpr int STAT_BYTES = 2 * 2 * MH * 16 * NH * 8;
-constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;                // kv_full[NST] (pair, half-tile) a_full[NH] a_empty[NH] q_full[NYW]
-constexpr int NBAR = NST + 2 * NH + NYW;
+constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;                // kv_full[NST] kv_empty[NST / 2] a_full[NH] a_empty[NH] q_full[NYW]
+constexpr int NBAR = NST + NST / 2 + 2 * NH + NYW;
 constexpr int TMEM_SLOT_OFF = BAR_OFF + NBAR * 8;
-constexpr int CNT_OFF = TMEM_SLOT_OFF + 16;                   // [NST] arrival counters of the A warps per (pair, half-tile)
-constexpr int SMEM_BYTES = ((CNT_OFF + NST * 4 + 127) / 128) * 128;
+constexpr int SMEM_BYTES = ((TMEM_SLOT_OFF + 4 + 127) / 128) * 128;
 constexpr int TMEM_COLS = 512;                 // per lane quadrant: 4 Y warps x MH parked tiles x 32 columns, then 2 A warps x 8 heads x 8 columns
 constexpr int YPARK_COLS = MH * 32;
 constexpr int APARK_COL = (NYW / 4) * YPARK_COLS;
@@ -105,15 +105,15 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int n_kt = (Tkv + 15) >> 4;          // ... of K' / V
   const int mh = (n_mt + 1) >> 1;            // tiles of the first row half = height of a Q' box in tiles
   const uint32_t q_tx = (uint32_t)mh * 16u * 128u;      // bytes one TMA box delivers (frames beyond T arrive as zeros)
-  const int kh = (n_kt + 1) >> 1;            // k-steps of the first half of a K' / V tile = height of a K' / V box in 16-frame tiles
-  const uint32_t kv_tx = 2u * (uint32_t)kh * 16u * 128u;   // one (pair, half) barrier: the K' half and the V half
+  const uint32_t kv_tx = (uint32_t)n_kt * 16u * 128u;
   auto kv_full = [&](int s) { return sbase + BAR_OFF + 8u * s; };
-  auto a_full = [&](int h) { return sbase + BAR_OFF + 8u * (NST + h); };
-  auto a_empty = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NH + h); };
-  auto q_full = [&](int w) { return sbase + BAR_OFF + 8u * (NST + 2 * NH + w); };
+  auto kv_empty = [&](int p) { return sbase + BAR_OFF + 8u * (NST + p); };
+  auto a_full = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NST / 2 + h); };
+  auto a_empty = [&](int h) { return sbase + BAR_OFF + 8u * (NST + NST / 2 + NH + h); };
+  auto q_full = [&](int w) { return sbase + BAR_OFF + 8u * (NST + NST / 2 + 2 * NH + w); };
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) tc::mbar_init(kv_full(s), 1);
-    for (int c = 0; c < NST; ++c) reinterpret_cast<uint32_t*>(sm + CNT_OFF)[c] = 0u;
+    for (int p2 = 0; p2 < NST / 2; ++p2) tc::mbar_init(kv_empty(p2), NAW);
     for (int h = 0; h < NH; ++h) { tc::mbar_init(a_full(h), NAW); tc::mbar_init(a_empty(h), 2); }
     for (int w = 0; w < NYW; ++w) tc::mbar_init(q_full(w), 1);
     tc::fence_mbarrier_init();
@@ -313,24 +313,21 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         a_off[4 * nt + 2 * mi + 1] = swz(a_row(l + 8), 2 * d8 + nt) + q * 4;
       }
     const int n_heads = n_iter * NH;          // (sample, head) units of this CTA, in order
-    // The K' / V tiles travel as HALF tiles (frames [0, 16 kh) and [16 kh, 32 kh)): a half goes back into flight as soon as the last A
-    // warp has used it -- half a head earlier than whole tiles would -- which is what the two-unit ring needs to cover the TMA latency.
-    uint32_t* const cnt = reinterpret_cast<uint32_t*>(sm + CNT_OFF);
-    auto issue_half = [&](int hc, int hf) {   // one lane: half hf of the K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
+    auto issue = [&](int hc) {                // one lane: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
       const int smp = (int)blockIdx.x + (hc >> 3) * (int)gridDim.x, hh = hc & 7, s0 = 2 * (hc & 1);
-      const uint32_t bar = kv_full(s0 + hf), dst = sbase + RING_OFF + s0 * TILE_BYTES + (uint32_t)(hf * kh) * 2048u;
-      tc::mbar_arrive_expect_tx(bar, kv_tx);
-      tc::tma_load_3d(&tmKV, bar, dst, kcol + hh * HD, hf * kh * 16, smp);
-      tc::tma_load_3d(&tmKV, bar, dst + TILE_BYTES, vcol + hh * HD, hf * kh * 16, smp);
-      // pull the same half of the NEXT sample from HBM into L2: the ring then covers L2 latency, not HBM latency
+      tc::mbar_arrive_expect_tx(kv_full(s0), kv_tx);
+      tc::tma_load_3d(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp);
+      tc::mbar_arrive_expect_tx(kv_full(s0 + 1), kv_tx);
+      tc::tma_load_3d(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp);
+      // pull the same head of the NEXT sample from HBM into L2 (the ring is only two units deep: it then covers L2 latency, not HBM latency)
       if (smp + (int)gridDim.x < n_samples) {
-        tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, hf * kh * 16, smp + (int)gridDim.x);
-        tc::tma_prefetch_l2_3d(&tmKV, vcol + hh * HD, hf * kh * 16, smp + (int)gridDim.x);
+        tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, 0, smp + (int)gridDim.x);
+        tc::tma_prefetch_l2_3d(&tmKV, vcol + hh * HD, 0, smp + (int)gridDim.x);
       }
     };
     if (wq == 0 && lane == 0) {
       tc::prefetch_tensormap(&tmKV);
-      for (int hc = 0; hc < 2 && hc < n_heads; ++hc) { issue_half(hc, 0); issue_half(hc, 1); }
+      for (int hc = 0; hc < 2 && hc < n_heads; ++hc) issue(hc);
     }
 #pragma unroll 1
     for (int i = 0; i < n_iter; ++i) {
@@ -341,7 +338,8 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int hc = i * NH + hh, s0 = 2 * (hc & 1);
         const uint32_t par = (uint32_t)((hc >> 1) & 1);
         const uint32_t ks_addr = sbase + RING_OFF + s0 * TILE_BYTES, vs_addr = ks_addr + TILE_BYTES;
-        wait_bar(kv_full(s0), par);   // first half of the K' and V tiles
+        wait_bar(kv_full(s0), par);
+        wait_bar(kv_full(s0 + 1), par);
         // A^T[l][d] = sum_t V[t][l] K'[t][d]; cs = ones . K' = the column sums of K' in the layout of the accumulator columns
         float acc[2][2][4], cs[2][4];
 #pragma unroll
@@ -366,49 +364,30 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mma_bf16(cs[0], ones, fb[0], fb[1]);
           mma_bf16(cs[1], ones, fb[2], fb[3]);
         };
-        // every fragment of half hf has been consumed by a product of this warp; the LAST of the A warps to get here puts the half
-        // of unit hc + 2 into flight (arrival counter in shared memory: nobody waits for anybody)
-        auto release_half = [&](int hf) {
-          __syncwarp();
-          if (lane == 0) {
-            __threadfence_block();
-            if (atomicAdd(cnt + s0 + hf, 1u) == (uint32_t)(NAW - 1)) {
-              cnt[s0 + hf] = 0u;
-              if (hc + 2 < n_heads) issue_half(hc + 2, hf);
-            }
-          }
-          __syncwarp();
-        };
         load_frags(fa0, fb0, 0);
-        if (n_kt == TP / 16) {   // the full-length window (T = 81 .. 96): six k-steps (three per half), fully unrolled
-          load_frags(fa1, fb1, 1); products(fa0, fb0);
-          load_frags(fa0, fb0, 2); products(fa1, fb1);
-          wait_bar(kv_full(s0 + 1), par);   // second half
-          load_frags(fa1, fb1, 3); products(fa0, fb0);
-          release_half(0);
-          load_frags(fa0, fb0, 4); products(fa1, fb1);
-          load_frags(fa1, fb1, 5); products(fa0, fb0);
-          products(fa1, fb1);
+        if (n_kt == TP / 16) {   // the full-length window (T = 81 .. 96): six k-steps, fully unrolled
+#pragma unroll
+          for (int kt = 0; kt < TP / 16; kt += 2) {
+            load_frags(fa1, fb1, kt + 1);
+            products(fa0, fb0);
+            if (kt + 2 < TP / 16) load_frags(fa0, fb0, kt + 2);
+            products(fa1, fb1);
+          }
         } else {
-          auto ldk = [&](uint32_t (&fa)[2][4], uint32_t (&fb)[4], int kt) {
-            if (kt == kh) wait_bar(kv_full(s0 + 1), par);   // first k-step of the second half
-            load_frags(fa, fb, kt);
-          };
 #pragma unroll 1
           for (int kt = 0; kt < n_kt; kt += 2) {   // 16 frames per k-step, two k-steps per iteration
             const bool two = kt + 1 < n_kt;        // warp-uniform
-            if (two) ldk(fa1, fb1, kt + 1);
+            if (two) load_frags(fa1, fb1, kt + 1);
             products(fa0, fb0);
-            if (kt == kh - 1) release_half(0);
             if (two) {
-              if (kt + 2 < n_kt) ldk(fa0, fb0, kt + 2);
+              if (kt + 2 < n_kt) load_frags(fa0, fb0, kt + 2);
               products(fa1, fb1);
-              if (kt + 1 == kh - 1) release_half(0);
             }
           }
-          if (n_kt == kh) wait_bar(kv_full(s0 + 1), par);   // a second half without frames (n_kt = 1) still arrives (as zeros)
         }
-        release_half(1);
+        // every fragment of this unit's K' / V tiles has been consumed by a product: the two ring slots go back to the refill duty
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(kv_empty(hc & 1));
         uint32_t pk[8];   // [nt][mi][rows g | g + 8]: bf16 pairs of columns d = 16 d8 + 8 nt + 2 q, + 1
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
@@ -432,6 +411,12 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc::tmem_st8(apark + (uint32_t)(hh * 8), pk);
           parked |= 1u << hh;
         }
+        // refill duty rotates over the A warps: by now the others have normally arrived, so the wait is short
+        if (wq == (hc & 7) && lane == 0 && hc + 2 < n_heads) {
+          wait_bar(kv_empty(hc & 1), par);
+          issue(hc + 2);
+        }
+        __syncwarp();
       }
       // ---- phase 2: parked heads -> their A^T slots, each as soon as both readers of the previous sample have released it
 #pragma unroll 1
@@ -454,6 +439,31 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 #ifndef DSHEG_EMU
+// (column, frame, sample) view of a bf16 tensor [n_samples * T, cols]; box = 64 columns x Tpad frames of one sample.
+// box_frames: height of the box in frames (default: all Tpad frames of the sample; Q' is loaded by row halves).
+inline bool make_frames_tmap(CUtensorMap* map, const void* base, int cols, int n_samples, int T, std::string* err, int box_frames = -1) {
+  struct Key { const void* p; int c, n, t, b; bool operator==(const Key& o) const { return p == o.p && c == o.c && n == o.n && t == o.t && b == o.b; } };
+  struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.t << 48) ^ ((size_t)k.c << 32) ^ ((size_t)k.b << 56); } };
+  static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+  const Key k{base, cols, n_samples, T, box_frames};
+  auto it = cache.find(k);
+  if (it != cache.end()) { *map = it->second; return true; }
+  tc::EncodeTiledFn fn = tc::get_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (cols % 8)) { *err = "attention operand not 16-byte aligned"; return false; }
+  const int Tpad = box_frames > 0 ? box_frames : (T + 15) / 16 * 16;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)n_samples};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)T * cols * 2};
+  cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)Tpad, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (3-D frames view) failed, CUresult " + std::to_string((int)r); return false; }
+  if (cache.size() > 1024) cache.clear();
+  cache.emplace(k, *map);
+  return true;
+}
+
 inline cudaError_t launch_attn_ws_qkv(const CUtensorMap& mq, const CUtensorMap& mkv, int kcol, int vcol, bf16* z, int n_samples, int T, int Tkv,
                                       int ssB, const float* ln_g, const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st) {
   static bool attr_set = false;
@@ -467,13 +477,13 @@ inline cudaError_t launch_attn_ws_qkv(const CUtensorMap& mq, const CUtensorMap& 
   return cudaGetLastError();
 }
 
-inline int q_box_frames(int T) { return 16 * ((((T + 15) >> 4) + 1) >> 1); }    // Q' boxes: a row half; K' / V boxes: a half tile (same rule on Tkv)
+inline int q_box_frames(int T) { return 16 * ((((T + 15) >> 4) + 1) >> 1); }
 
 // self-attention on the fused projection qkv [n_samples * T, 1536] (q' | k' | v)
 inline cudaError_t launch_attn_ws(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
                                   const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
   CUtensorMap mq, mkv;
-  if (!atm::make_frames_tmap(&mq, qkv, 3 * D, n_samples, T, err, q_box_frames(T)) || !atm::make_frames_tmap(&mkv, qkv, 3 * D, n_samples, T, err, q_box_frames(T)))
+  if (!make_frames_tmap(&mq, qkv, 3 * D, n_samples, T, err, q_box_frames(T)) || !make_frames_tmap(&mkv, qkv, 3 * D, n_samples, T, err))
     return cudaErrorInvalidValue;
   return launch_attn_ws_qkv(mq, mkv, D, 2 * D, z, n_samples, T, T, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
 }
@@ -482,7 +492,7 @@ inline cudaError_t launch_attn_ws(const bf16* qkv, bf16* z, int n_samples, int T
 inline cudaError_t launch_cross_attn_ws(const bf16* q, const bf16* kv, bf16* z, int n_samples, int T, int Tkv, int ssB, const float* ln_g,
                                         const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
   CUtensorMap mq, mkv;
-  if (!atm::make_frames_tmap(&mq, q, D, n_samples, T, err, q_box_frames(T)) || !atm::make_frames_tmap(&mkv, kv, 2 * D, n_samples, Tkv, err, q_box_frames(Tkv)))
+  if (!make_frames_tmap(&mq, q, D, n_samples, T, err, q_box_frames(T)) || !make_frames_tmap(&mkv, kv, 2 * D, n_samples, Tkv, err))
     return cudaErrorInvalidValue;
   return launch_attn_ws_qkv(mq, mkv, 0, D, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
 }

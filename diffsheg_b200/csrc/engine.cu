@@ -14,7 +14,6 @@
 #include "../../include/diffsheg_b200.h"
 #include "attn_v3.cuh"
 #include "attn_small.cuh"
-#include "attn_tma.cuh"
 #include "attn_ws.cuh"
 #include "attn_tf32.cuh"
 #include "common.cuh"
@@ -85,7 +84,7 @@ struct dsheg_handle {
   std::unordered_map<std::string, DevTensor> tensors;
   bool finalized = false;
   int gemm_engine = 1;  // 1 = tcgen05 (bf16 mode default), 0 = SIMT
-  // bf16 mode attention: 2 = persistent TMA-staged kernel on the ACT_EXPO numerators (attn_tma.cuh; default), falling back per
+  // bf16 mode attention: 2 = persistent warp-specialised TMA kernel on the ACT_EXPO numerators (attn_ws.cuh; default), falling back per
   // layer to 1 = attn_v3 (in-kernel softmaxes) when the packer found no provably safe static shifts (DSHEG_ATTN=v3 forces it),
   // 0 = generic SIMT kernel (DSHEG_ATTN=v1; also what T > 96 and the fp32 / tf32 modes use)
   int attn_mode = 2;
@@ -110,7 +109,7 @@ struct dsheg_handle {
   // bisecting switches (all on by default; hardware-validated in round 2, profiles/r02):
   int attn_aud = 1;            // DSHEG_ATTN_AUD=0: generic kernel instead of attn_small.cuh for the audio encoder layer (D = 128, 8 heads of 16)
   int fuse_lnms = 1;           // DSHEG_FUSE_LNMS=0: separate ln_mod_silu pass instead of the ACT_LNMS epilogue of ffn.linear2 (rows >= 4096)
-  int expo = 1;                // DSHEG_EXPO=0: plain QKV epilogue + attn_v3 instead of ACT_EXPO numerators + attn_tma
+  int expo = 1;                // DSHEG_EXPO=0: plain QKV epilogue + attn_v3 instead of ACT_EXPO numerators + attn_ws
   int use_graphs = 1;          // DSHEG_GRAPHS=0 disables
   int graph_max_rows = 4096;   // B*T above which launches are no longer the bottleneck
   float2 *PS, *CS;      // fused LayerNorm statistics: per-row / per-64-column partials, conditioning partials
@@ -356,7 +355,7 @@ struct Runner {
     gq.csum = L.qkv.csum;
     gq.out = h->QKV; gq.ldo = 3 * D;
     // Softmax numerators from the epilogue (tr:122-123): Q and K leave the QKV GEMM as exp(v - static shift) for the layers whose
-    // packed weights carry provably safe shifts (pack.py:expo_shift); attn_tma consumes them.  Other layers: plain epilogue + attn_v3.
+    // packed weights carry provably safe shifts (pack.py:expo_shift); attn_ws consumes them.  Other layers: plain epilogue + attn_v3.
     const bool tc_attn = std::is_same<TA, bf16>::value && D / H == 64 && D == av3::D && H == av3::NH && T <= av3::TP;
     const bool kpre = tc_attn && h->attn_mode >= 2 && h->expo && h->gemm_engine == 1 && L.qkv_eshift != nullptr;
     if (kpre) { gq.act = ACT_EXPO; gq.eshift = L.qkv_eshift; gq.expo_cols = 2 * D; }
@@ -368,10 +367,8 @@ struct Runner {
     prof_begin(h, st, PROF_ATTN, 4.0 * rows * (double)D * sizeof(TA));
     if (kpre) {
       std::string terr;
-      const cudaError_t le = h->attn_mode == 3
-          ? aws::launch_attn_ws((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr)
-          : atm::launch_attn_tma((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr);
-      if (le != cudaSuccess) return fail(h, std::string("attn_tma / attn_ws launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
+      const cudaError_t le = aws::launch_attn_ws((const bf16*)h->QKV, (bf16*)h->Z, n_samples, T, ssB, L.sa_g, L.sa_b, ss, ss_ld, h->num_sms, st, &terr);
+      if (le != cudaSuccess) return fail(h, std::string("attn_ws launch: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()));
     } else if (tc_attn && h->attn_mode >= 1) {   // no provably safe shifts for this layer (or DSHEG_ATTN=v3 / DSHEG_EXPO=0): softmaxes in the kernel
       DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, float>::value && HD == 64 && h->cfg.precision == DSHEG_PREC_TF32 && h->gemm_engine == 1) {
@@ -606,7 +603,6 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   const char* att = getenv("DSHEG_ATTN");
   if (att && !strcmp(att, "v1")) h->attn_mode = 0;
   if (att && !strcmp(att, "v3")) h->attn_mode = 1;
-  if (att && !strcmp(att, "ws")) h->attn_mode = 3;
   const char* aa = getenv("DSHEG_ATTN_AUD");
   if (aa && !strcmp(aa, "0")) h->attn_aud = 0;
   const char* fl = getenv("DSHEG_FUSE_LNMS");
@@ -1150,11 +1146,8 @@ int dsheg_op_attention_bf16(const void* qkv, const float* ln_g, const float* ln_
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* att = getenv("DSHEG_ATTN");
-    cudaError_t le = (att && !strcmp(att, "ws"))
-        ? aws::launch_attn_ws((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr)
-        : atm::launch_attn_tma((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr);
-    if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (tma): ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
+    cudaError_t le = aws::launch_attn_ws((const bf16*)qkv, (bf16*)z, Bn, T, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr);
+    if (le != cudaSuccess) { g_create_error = std::string("op_attention_bf16 (ws): ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
   } else {            // plain q, k, v: softmaxes inside the kernel (the per-layer fallback)
     cudaFuncSetAttribute(av3::attn_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av3::SMEM_BYTES);
     DSHEG_LAUNCH(av3::attn_v3_kernel, Bn, av3::NTHREADS, av3::SMEM_BYTES, (cudaStream_t)stream, (const bf16*)qkv, (bf16*)z, T, Bn, ln_g, ln_b,
@@ -1174,11 +1167,8 @@ int dsheg_op_cross_attention_bf16(const void* q, const void* kv, const float* ln
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const char* att = getenv("DSHEG_ATTN");
-  cudaError_t le = (att && !strcmp(att, "ws"))
-      ? aws::launch_cross_attn_ws((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms, (cudaStream_t)stream, &terr)
-      : atm::launch_cross_attn_tma((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms,
-                                   (cudaStream_t)stream, &terr);
+  cudaError_t le = aws::launch_cross_attn_ws((const bf16*)q, (const bf16*)kv, (bf16*)z, Bn, T, N, Bn, ln_g, ln_b, scale_shift, 2 * av3::D, sms,
+                                             (cudaStream_t)stream, &terr);
   if (le != cudaSuccess) { g_create_error = std::string("op_cross_attention_bf16: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
   return step_done("dsheg_op_cross_attention_bf16");
 }

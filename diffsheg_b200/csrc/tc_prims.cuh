@@ -58,7 +58,7 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-// 3-D variant (attn_tma.cuh): coordinates (column, frame, sample); elements outside the tensor in ANY dimension arrive as zeros
+// 3-D variant (attn_ws.cuh): coordinates (column, frame, sample); elements outside the tensor in ANY dimension arrive as zeros
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

@@ -12,7 +12,7 @@ exact up to floating-point reassociation:
 * ``*.nullc``: under classifier-free guidance the whole feat_proj input row of the uncond half is the
   learned ``null_cond_emb`` (tr:326-332), so feat_proj(null) is one constant vector per layer.
 * ``*.qkv.eshift`` (optional): static softmax shifts for the Q | K columns when ``expo_shift`` can prove the exponent range
-  for every possible input (enables the ACT_EXPO epilogue of the QKV GEMM + attn_tma; layers without it keep attn_v3).
+  for every possible input (enables the ACT_EXPO epilogue of the QKV GEMM + attn_ws; layers without it keep attn_v3).
 * ``*.hub``: BatchNorm1d (eval) folded into the first Conv1d of hubert_encoder (tr:436-442).
 * K axes of GEMM weights are laid out per A-segment, each padded to a multiple of 64
   (h | audio_proj | hubert | expr for feat1).

@@ -177,7 +177,7 @@ int dsheg_op_attention_tf32(const float* qkv, const float* ln_g, const float* ln
                             float* z, int32_t Bn, int32_t T, int32_t D, int32_t H, void* stream);
 
 /* Same op on the bf16 fast path (D = 512, 8 heads, T <= 96): qkv and z are bf16 arrays.
- * numerators = 1: the engine's default kernel (attn_tma.cuh: persistent, TMA-staged); the Q and K columns of qkv already hold the
+ * numerators = 1: the engine's default kernel (attn_ws.cuh: persistent, TMA-staged, warp-specialised); the Q and K columns of qkv already hold the
  *                 softmax NUMERATORS exp(value - shift) that the ACT_EXPO epilogue of the QKV GEMM writes (any per-(row, head)
  *                 shift for Q, any per-(sample, column) shift for K: softmax is shift-invariant);
  * numerators = 0: plain q, k, v; both softmaxes run inside the kernel (attn_v3.cuh, the per-layer fallback). */

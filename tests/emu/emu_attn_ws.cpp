@@ -21,7 +21,7 @@ extern "C" int emu_attention_ws(const uint16_t* q, int q_cols, const uint16_t* k
                                 int T, int Tkv, int ssB, const float* ln_g, const float* ln_b, const float* ss, int ss_ld, int grid) {
   g_err.clear();
   const int n_mt = (T + 15) >> 4, mh = (n_mt + 1) >> 1, n_kt = (Tkv + 15) >> 4;
-  const CUtensorMap mq = frames_map(q, q_cols, n_samples, T, 16 * mh), mkv = frames_map(kv, kv_cols, n_samples, Tkv, 16 * ((n_kt + 1) >> 1));
+  const CUtensorMap mq = frames_map(q, q_cols, n_samples, T, 16 * mh), mkv = frames_map(kv, kv_cols, n_samples, Tkv, 16 * n_kt);
   bf16* zo = reinterpret_cast<bf16*>(z);
   if (grid > n_samples) grid = n_samples;
   const bool ok = emu::run_grid(grid, aws::NTHREADS, 1, aws::SMEM_BYTES,

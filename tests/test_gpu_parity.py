@@ -274,7 +274,7 @@ def test_op_linear_layernorm_modulate_silu_epilogue(L, M, K, T, B):
 
 @pytest.mark.parametrize("Bn,T", [(3, 88), (2, 34), (1, 96), (2, 16), (1, 7), (301, 88), (150, 33), (1900, 88)])
 def test_op_attention_with_static_shift_numerators(L, Bn, T):
-    """attn_tma (the default kernel): the Q and K columns hold exp(value - shift) with shifts that are NOT the maxima (per (row, head)
+    """attn_ws (the default kernel): the Q and K columns hold exp(value - shift) with shifts that are NOT the maxima (per (row, head)
     for Q, per (sample, column) for K); the result must equal the attention of the original q, k.  Bn > 148: several samples per
     persistent CTA (ring wrap-around, Q' / Y region hand-over); Bn = 1900: the headline launch."""
     torch.manual_seed(T)
@@ -640,7 +640,7 @@ def test_same_overlap_noisy_chain_on_the_step_kernels_matches_oracle_same_seed()
 @pytest.mark.parametrize("Bn,T,N", [(3, 88, 88), (2, 34, 60), (2, 88, 17), (200, 40, 96), (1, 7, 3)])
 def test_op_cross_attention_with_static_shift_numerators(L, Bn, T, N):
     """LinearTemporalCrossAttention (tr:133-166) + Stylization prologue at op level: Q from the motion stream (T frames), K / V from a
-    conditioning sequence of N != T frames; attn_tma with separate sources.  Inputs are the numerators exp(. - shift) (ACT_EXPO
+    conditioning sequence of N != T frames; attn_ws with separate sources.  Inputs are the numerators exp(. - shift) (ACT_EXPO
     contract); the result must equal the cross-attention of the original q, k (softmax is shift-invariant)."""
     torch.manual_seed(T + N)
     D, H = 512, 8
