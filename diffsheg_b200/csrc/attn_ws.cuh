@@ -95,7 +95,7 @@ __device__ __forceinline__ int a_row(int l) { return 8 * (4 * (l >> 5) + ((l >> 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int kcol, int vcol,
                bf16* __restrict__ z, int n_samples, int T, int Tkv, int B,
-               const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld) {
+               const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ ss, int ss_ld, int rev) {
   DSHEG_PDL_ENTER();
   DSHEG_TC_DYN_SMEM(sm);
   const uint32_t sbase = tc::smem_u32(sm);
@@ -124,6 +124,8 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(sm + TMEM_SLOT_OFF);
   const int n_iter = ((int)blockIdx.x < n_samples) ? (n_samples - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // samples of this CTA
+  // j-th sample of this CTA; rev: last samples first (start where the producer of q' / k' / v finished: those rows are still in L2)
+  auto smp_at = [&](int j) { const int s = (int)blockIdx.x + j * (int)gridDim.x; return rev ? n_samples - 1 - s : s; };
   const int g = lane >> 2, q = lane & 3;           // mma fragment coordinates
   const int mat = lane >> 3, rr = lane & 7;        // ldmatrix: matrix index / row inside the matrix
 
@@ -137,12 +139,12 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (nu > 0 && lane == 0 && n_iter > 0) {
       tc::prefetch_tensormap(&tmQ);
       tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
-      tc::tma_load_3d(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, (int)blockIdx.x);
+      tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(0), tc::HINT_STREAM);
     }
     const int colA = h * HD + 8 * q;     // this thread's output columns: [colA, colA + 8) and [colA + 32, colA + 40)
 #pragma unroll 1
     for (int i = 0; i < n_iter; ++i) {
-      const int smp = (int)blockIdx.x + i * (int)gridDim.x;
+      const int smp = smp_at(i);
       const uint32_t par = (uint32_t)(i & 1);
       float2* const stat = reinterpret_cast<float2*>(sm + STAT_OFF) + (size_t)((par * 2 + half) * MH) * 16 * NH;
       const float* const sc = ss + (size_t)(smp % B) * ss_ld + colA;   // the sample's modulation row (scale | shift) at this thread's columns
@@ -180,7 +182,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc::mbar_arrive(a_empty(h));
             if (i + 1 < n_iter) {
               tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
-              tc::tma_load_3d(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp + (int)gridDim.x);
+              tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(i + 1), tc::HINT_STREAM);
             }
           }
           __syncwarp();
@@ -314,15 +316,15 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     const int n_heads = n_iter * NH;          // (sample, head) units of this CTA, in order
     auto issue = [&](int hc) {                // one lane: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
-      const int smp = (int)blockIdx.x + (hc >> 3) * (int)gridDim.x, hh = hc & 7, s0 = 2 * (hc & 1);
+      const int smp = smp_at(hc >> 3), hh = hc & 7, s0 = 2 * (hc & 1);
       tc::mbar_arrive_expect_tx(kv_full(s0), kv_tx);
-      tc::tma_load_3d(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp);
+      tc::tma_load_3d_hint(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp, tc::HINT_STREAM);
       tc::mbar_arrive_expect_tx(kv_full(s0 + 1), kv_tx);
-      tc::tma_load_3d(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp);
+      tc::tma_load_3d_hint(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp, tc::HINT_STREAM);
       // pull the same head of the NEXT sample from HBM into L2 (the ring is only two units deep: it then covers L2 latency, not HBM latency)
-      if (smp + (int)gridDim.x < n_samples) {
-        tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, 0, smp + (int)gridDim.x);
-        tc::tma_prefetch_l2_3d(&tmKV, vcol + hh * HD, 0, smp + (int)gridDim.x);
+      if ((hc >> 3) + 1 < n_iter) {
+        tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, 0, smp_at((hc >> 3) + 1));
+        tc::tma_prefetch_l2_3d(&tmKV, vcol + hh * HD, 0, smp_at((hc >> 3) + 1));
       }
     };
     if (wq == 0 && lane == 0) {
@@ -465,7 +467,7 @@ inline bool make_frames_tmap(CUtensorMap* map, const void* base, int cols, int n
 }
 
 inline cudaError_t launch_attn_ws_qkv(const CUtensorMap& mq, const CUtensorMap& mkv, int kcol, int vcol, bf16* z, int n_samples, int T, int Tkv,
-                                      int ssB, const float* ln_g, const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st) {
+                                      int ssB, const float* ln_g, const float* ln_b, const float* ss, int ss_ld, int num_sms, cudaStream_t st, int rev = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -473,7 +475,7 @@ inline cudaError_t launch_attn_ws_qkv(const CUtensorMap& mq, const CUtensorMap& 
     attr_set = true;
   }
   const int grid = n_samples < num_sms ? n_samples : num_sms;
-  DSHEG_LAUNCH(attn_ws_kernel, grid, NTHREADS, SMEM_BYTES, st, mq, mkv, kcol, vcol, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld);
+  DSHEG_LAUNCH(attn_ws_kernel, grid, NTHREADS, SMEM_BYTES, st, mq, mkv, kcol, vcol, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld, rev);
   return cudaGetLastError();
 }
 
@@ -481,11 +483,11 @@ inline int q_box_frames(int T) { return 16 * ((((T + 15) >> 4) + 1) >> 1); }
 
 // self-attention on the fused projection qkv [n_samples * T, 1536] (q' | k' | v)
 inline cudaError_t launch_attn_ws(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
-                                  const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err) {
+                                  const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err, int rev = 0) {
   CUtensorMap mq, mkv;
   if (!make_frames_tmap(&mq, qkv, 3 * D, n_samples, T, err, q_box_frames(T)) || !make_frames_tmap(&mkv, qkv, 3 * D, n_samples, T, err))
     return cudaErrorInvalidValue;
-  return launch_attn_ws_qkv(mq, mkv, D, 2 * D, z, n_samples, T, T, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
+  return launch_attn_ws_qkv(mq, mkv, D, 2 * D, z, n_samples, T, T, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st, rev);
 }
 
 // cross-attention (transformer.py:133-166): q' [n_samples * T, 512] from the motion stream, kv [n_samples * Tkv, 1024] (k' | v) from the conditioning

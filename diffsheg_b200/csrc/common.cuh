@@ -121,6 +121,7 @@ struct GemmDesc {
   void* out = nullptr;
   int ldo = 0;
   int out_f32 = 0;   // store fp32 instead of the activation type
+  int rev = 0;       // tcgen05 engine: walk the row panels last-to-first (start where the producer of A finished: its last rows are still in L2)
   void* out2 = nullptr;  // optional duplicate store (same ld / type as out)
   // ---- fused LayerNorm statistics (tcgen05 engine only; N == 512 residual-stream GEMMs) -------------------
   // producer side (residual variants): per row and 64-column group, (sum, sum of squares) of the stored output

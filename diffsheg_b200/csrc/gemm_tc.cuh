@@ -83,7 +83,7 @@ enum { RES_NONE = 0, RES_BF16 = 1, RES_F32_MOD = 2 };
 struct Params {
   int M, N, num_kb, nseg;
   int seg_kb_start[5];
-  int tiles_m, tiles_n;
+  int tiles_m, tiles_n, rev;
   const float* bias; const float* csum; const float* mu; const float* rstd;
   const void* res; int ldr, res_mod;
   void* out; int ldo; void* out2;
@@ -92,6 +92,14 @@ struct Params {
   const float* eshift; int expo_cols;   // ACT_EXPO (appended likewise)
   const float* lnms_g; const float* lnms_b; const float* lnms_ss; int lnms_ld, lnms_B, lnms_T;   // ACT_LNMS (appended likewise)
 };
+
+// L2 eviction priorities of the TMA loads (-DDSHEG_L2_HINTS=1 experiment: activations / residuals are read once -> evict first,
+// weights are re-read by every row panel -> evict last; default: normal priority everywhere)
+#if defined(DSHEG_L2_HINTS) && DSHEG_L2_HINTS
+constexpr uint64_t HINT_STREAM = L2_EVICT_FIRST, HINT_KEEP = L2_EVICT_LAST;
+#else
+constexpr uint64_t HINT_STREAM = L2_EVICT_NORMAL, HINT_KEEP = L2_EVICT_NORMAL;
+#endif
 
 // ---- spin on an mbarrier phase (PTX primitives: tc_prims.cuh) ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -221,7 +229,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       const uint32_t leader_full0 = CG == 2 ? mapa_rank(full_bar(0), 0) : 0u;
       for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
-        const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
+        const int m_pan = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int m_blk = (p.rev ? p.tiles_m - 1 - m_pan : m_pan) * CG + (int)rank;
         int seg = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           while (kb >= p.seg_kb_start[seg + 1]) ++seg;
@@ -232,12 +241,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // both CTAs fill their own smem; all bytes are credited to the leader's full barrier
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             const uint32_t lb = leader_full0 + 8u * stage;
-            tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
-            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+            tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM, HINT_STREAM);
+            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2), HINT_KEEP);
           } else {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
-            tma_load_2d(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN);
+            tma_load_2d_hint(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM, HINT_STREAM);
+            tma_load_2d_hint(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN, HINT_KEEP);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -300,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       epi_bar_sync<NE * 32>();
       int pbuf = 0;
       for (int unit = cta_first; unit < p.tiles_m; unit += cta_stride) {
-        const int m0 = (unit * CG + (int)rank) * BM + q * 32;
+        const int m0 = ((p.rev ? p.tiles_m - 1 - unit : unit) * CG + (int)rank) * BM + q * 32;
         const int m = m0 + lane;
         const bool row_ok = m < p.M;
         // ---- pass 1: statistics of this thread's 2 x 64 columns; stage 0 is read while the MMAs still fill stage 1
@@ -393,7 +402,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     } else
     for (int tile = tile_first; tile < num_tiles; tile = tile_next(tile)) {
-      const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
+      const int m_pan = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int m_blk = (p.rev ? p.tiles_m - 1 - m_pan : m_pan) * CG + (int)rank;
       const int n_tile0 = n_blk * BN;
       // ---- stage per-column vectors for this tile (double-buffered with the accumulator stage)
       float* vb = vecs + (C::NVEC == 1 ? 0 : acc) * 2 * BN;
@@ -417,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
         if (RES == RES_BF16 && lane == 0) {   // residual box by TMA, in flight while the mainloop runs
           mbar_arrive_expect_tx(res_bar(e), STG_BYTES);
-          tma_load_2d(&tmRes, res_bar(e), stg, nc0, m0);
+          tma_load_2d_hint(&tmRes, res_bar(e), stg, nc0, m0, HINT_STREAM);
         }
       }
       // ---- per-row operands, fetched before the accumulator is ready
@@ -784,6 +794,7 @@ inline cudaError_t launch_gemm_tc(const GemmDesc& d, int num_sms, cudaStream_t s
     if (d.res && !d.res_f32 && !make_tmap(&maps[7], d.res, d.M, d.N, d.ldr, 32, err)) return cudaErrorInvalidValue;
   }
   p.tiles_m = (d.M + BM * cg - 1) / (BM * cg); p.tiles_n = (d.N + bn - 1) / bn;   // tiles per CTA (pair)
+  p.rev = d.rev;
   p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd;
   p.res = d.res; p.ldr = d.ldr; p.res_mod = d.res_mod;
   p.out = d.out; p.ldo = d.ldo; p.out2 = d.out2;

@@ -28,6 +28,7 @@ struct EmuGemmArgs {
   int32_t expo_cols;
   const float *lnms_g, *lnms_b, *lnms_ss;
   int32_t lnms_ld, lnms_B, lnms_T;
+  int32_t rev;
 };
 
 static std::string g_err;
@@ -46,6 +47,7 @@ extern "C" int emu_gemm_tc(const EmuGemmArgs* a) {
   d.ps_slots = a->ps_slots; d.ps_P = a->ps_P;
   d.eshift = a->eshift; d.expo_cols = a->expo_cols;
   d.lnms_g = a->lnms_g; d.lnms_b = a->lnms_b; d.lnms_ss = a->lnms_ss; d.lnms_ld = a->lnms_ld; d.lnms_B = a->lnms_B; d.lnms_T = a->lnms_T;
+  d.rev = a->rev;
   std::string terr;
   const cudaError_t e = tc::launch_gemm_tc(d, a->num_sms, nullptr, &terr, a->bn_force, a->cg_force);
   if (e != cudaSuccess) { g_err = terr + " " + tc::g_emu_error(); return 1; }

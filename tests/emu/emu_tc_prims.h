@@ -139,6 +139,7 @@ inline void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int 
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
   emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
 }
+inline void tma_load_2d_hint(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t) { tma_load_2d(map, bar, dst, c0, c1); }
 inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
 // 3-D (column, frame, sample): the box covers one sample; frames beyond the sample's `rows` (and samples beyond n2) arrive as zeros
 inline void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -149,8 +150,10 @@ inline void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int 
   tma_copy(&m2, emu::self().cta, dst, c0, c1, true);
   emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
 }
+inline void tma_load_3d_hint(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t) { tma_load_3d(map, bar, dst, c0, c1, c2); }
 inline void tma_prefetch_l2_3d(const CUtensorMap*, int, int, int) {}
-inline void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+constexpr uint64_t L2_EVICT_NORMAL = 0, L2_EVICT_FIRST = 1, L2_EVICT_LAST = 2;   // cache hints are not modelled
+inline void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1, uint64_t = 0) {
   emu::delay("EMU_DELAY_TMA");
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
   emu::bar_complete_tx(leader_bar, (long long)map->box_cols * 2 * map->box_rows);

@@ -27,7 +27,7 @@ class Args(ctypes.Structure):
                 ("num_sms", ctypes.c_int32), ("bn_force", ctypes.c_int32), ("cg_force", ctypes.c_int32),
                 ("eshift", ctypes.c_void_p), ("expo_cols", ctypes.c_int32),
                 ("lnms_g", ctypes.c_void_p), ("lnms_b", ctypes.c_void_p), ("lnms_ss", ctypes.c_void_p),
-                ("lnms_ld", ctypes.c_int32), ("lnms_B", ctypes.c_int32), ("lnms_T", ctypes.c_int32)]
+                ("lnms_ld", ctypes.c_int32), ("lnms_B", ctypes.c_int32), ("lnms_T", ctypes.c_int32), ("rev", ctypes.c_int32)]
 
 
 def bf16_bits(t):
@@ -47,7 +47,7 @@ def r64(k):
 
 
 def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, dup=False, stats_out=False, n_uncond=0,
-             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, expo_cols=0, expo_q_cols=0, lnms_T=0, lnms_B=0):
+             ps_in=False, num_sms=4, bn=0, cg=0, seed=0, lib=None, expo_cols=0, expo_q_cols=0, lnms_T=0, lnms_B=0, rev=0):
     """Builds operands like the engine does (K laid out per segment padded to 64), runs the emulated kernel, returns
     (got, want, extras)."""
     g = torch.Generator().manual_seed(seed)
@@ -76,6 +76,7 @@ def run_gemm(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, out_f32=False, d
     bias = rnd(N).float().numpy()
     a = Args()
     a.M, a.N, a.nseg, a.Kp = M, N, len(seg_ks), Kp
+    a.rev = rev
     for i, (ab, ld, k) in enumerate(segs):
         a.seg_k[i], a.seg_ld[i], a.seg_ptr[i] = k, ld, ptr(ab)
     a.w, a.bias, a.act = ptr(Wb), ptr(bias), act
@@ -293,3 +294,18 @@ def test_gemm_is_independent_of_the_thread_schedule(kw, sched, monkeypatch):
     monkeypatch.setenv("EMU_SCHED", sched)
     _, _, ex1 = run_gemm(M, N, ks, seed=31, **k)
     assert np.array_equal(base, ex1["out_bits"])
+
+
+@pytest.mark.parametrize("kw", [dict(M=520, N=512, ks=[512], cg=2, num_sms=2, res="bf16", stats_out=True),
+                                dict(M=700, N=1536, ks=[512], cg=2, num_sms=4, ln=True, ps_in=True),
+                                dict(M=520, N=512, ks=[1024], act=ACT_LNMS, lnms_T=88, lnms_B=3, cg=2, num_sms=2),
+                                dict(M=300, N=512, ks=[768], cg=1, num_sms=2, res="bf16")])
+def test_reverse_row_panel_walk_gives_the_same_result(kw):
+    """GemmDesc::rev (DSHEG_ZIGZAG experiment): the persistent tile walk takes the row panels last-to-first; every row still gets
+    exactly its own tile (ragged last panel included), so the output is bit-identical to the forward walk."""
+    kw = dict(kw)
+    M, N, ks = kw.pop("M"), kw.pop("N"), kw.pop("ks")
+    fwd, want, _ = run_gemm(M, N, ks, seed=21, **kw)
+    rev, _, _ = run_gemm(M, N, ks, seed=21, rev=1, **kw)
+    assert torch.equal(fwd, rev)
+    assert float((fwd - want).abs().max() / want.abs().max()) < 2e-2

@@ -274,7 +274,7 @@ def _ws_case(Bn, T, Tk=None, nb=None, seed=0):
     return qn, kn, v, g, b, ss
 
 
-def run_attention_ws(qn, kn, v, g, b, ss, grid=2):
+def run_attention_ws(qn, kn, v, g, b, ss, grid=2, rev=0):
     Bn, T, D = qn.shape
     Tk = kn.shape[1]
     L = emu.attn_ws_lib()
@@ -283,10 +283,10 @@ def run_attention_ws(qn, kn, v, g, b, ss, grid=2):
     gg, bb, s = (x.float().numpy().copy() for x in (g, b, ss))
     if Tk == T:      # self-attention: one fused tensor [q' | k' | v], like the engine
         qkv = _bf16_bits(torch.cat([qn, kn, v], -1))
-        rc = L.emu_attention_ws(P(qkv), 3 * D, P(qkv), 3 * D, D, 2 * D, P(z), Bn, T, T, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], grid)
+        rc = L.emu_attention_ws(P(qkv), 3 * D, P(qkv), 3 * D, D, 2 * D, P(z), Bn, T, T, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], grid, rev)
     else:            # cross-attention (tr:133-166): separate q' and (k' | v) sources and lengths
         q, kv = _bf16_bits(qn), _bf16_bits(torch.cat([kn, v], -1))
-        rc = L.emu_attention_ws(P(q), D, P(kv), 2 * D, 0, D, P(z), Bn, T, Tk, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], grid)
+        rc = L.emu_attention_ws(P(q), D, P(kv), 2 * D, 0, D, P(z), Bn, T, Tk, ss.shape[0], P(gg), P(bb), P(s), ss.shape[1], grid, rev)
     assert rc == 0, L.emu_attn_ws_last_error().decode()
     return z
 
@@ -314,6 +314,7 @@ def test_attn_ws_is_independent_of_the_thread_schedule(env, T, monkeypatch):
     qn, kn, v, g, b, ss = _ws_case(4, T, seed=3)
     base = run_attention_ws(qn, kn, v, g, b, ss, grid=1)
     assert np.array_equal(base, run_attention_ws(qn, kn, v, g, b, ss, grid=3))    # and of the sample -> CTA assignment
+    assert np.array_equal(base, run_attention_ws(qn, kn, v, g, b, ss, grid=2, rev=1))   # ... and of the walk direction
     for k, val in env.items():
         monkeypatch.setenv(k, val)
     assert np.array_equal(base, run_attention_ws(qn, kn, v, g, b, ss, grid=1))

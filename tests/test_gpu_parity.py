@@ -345,7 +345,7 @@ def test_denoise_matches_oracle_variants(prec):
     gate(got, want, prec, "call", "denoise show nocfg T40 vs fp64 oracle")
 
 
-@pytest.mark.parametrize("switch", ["DSHEG_EXPO=0", "DSHEG_ATTN=v3", "DSHEG_ATTN=v1", "DSHEG_FUSE_LNMS=0", "DSHEG_ATTN_AUD=0", "DSHEG_FUSE_STATS=0"])
+@pytest.mark.parametrize("switch", ["DSHEG_EXPO=0", "DSHEG_ATTN=v3", "DSHEG_ATTN=v1", "DSHEG_FUSE_LNMS=0", "DSHEG_ATTN_AUD=0", "DSHEG_FUSE_STATS=0", "DSHEG_ZIGZAG=0"])
 def test_denoise_bisecting_switches_keep_parity(golden_dir, switch, monkeypatch):
     """Every default-on fusion has an off switch (read at dsheg_create) that routes through the kernel it replaced: plain QKV epilogue +
     attn_v3 (also the per-layer fallback when the packer finds no provably safe softmax shifts), the generic attention kernel, the
