@@ -139,7 +139,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (nu > 0 && lane == 0 && n_iter > 0) {
       tc::prefetch_tensormap(&tmQ);
       tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
-      tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(0), tc::HINT_STREAM);
+      tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(0), tc::L2_EVICT_FIRST);
     }
     const int colA = h * HD + 8 * q;     // this thread's output columns: [colA, colA + 8) and [colA + 32, colA + 40)
 #pragma unroll 1
@@ -182,7 +182,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc::mbar_arrive(a_empty(h));
             if (i + 1 < n_iter) {
               tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
-              tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(i + 1), tc::HINT_STREAM);
+              tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(i + 1), tc::L2_EVICT_FIRST);
             }
           }
           __syncwarp();
@@ -318,9 +318,9 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto issue = [&](int hc) {                // one lane: K' and V tiles of unit hc -> ring slots 2 (hc & 1), + 1
       const int smp = smp_at(hc >> 3), hh = hc & 7, s0 = 2 * (hc & 1);
       tc::mbar_arrive_expect_tx(kv_full(s0), kv_tx);
-      tc::tma_load_3d_hint(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp, tc::HINT_STREAM);
+      tc::tma_load_3d_hint(&tmKV, kv_full(s0), sbase + RING_OFF + s0 * TILE_BYTES, kcol + hh * HD, 0, smp, tc::L2_EVICT_FIRST);
       tc::mbar_arrive_expect_tx(kv_full(s0 + 1), kv_tx);
-      tc::tma_load_3d_hint(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp, tc::HINT_STREAM);
+      tc::tma_load_3d_hint(&tmKV, kv_full(s0 + 1), sbase + RING_OFF + (s0 + 1) * TILE_BYTES, vcol + hh * HD, 0, smp, tc::L2_EVICT_FIRST);
       // pull the same head of the NEXT sample from HBM into L2 (the ring is only two units deep: it then covers L2 latency, not HBM latency)
       if ((hc >> 3) + 1 < n_iter) {
         tc::tma_prefetch_l2_3d(&tmKV, kcol + hh * HD, 0, smp_at((hc >> 3) + 1));

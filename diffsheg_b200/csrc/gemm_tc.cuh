@@ -93,24 +93,15 @@ struct Params {
   const float* lnms_g; const float* lnms_b; const float* lnms_ss; int lnms_ld, lnms_B, lnms_T;   // ACT_LNMS (appended likewise)
 };
 
-// L2 eviction priorities of the TMA loads (-DDSHEG_L2_HINTS=1 experiment: activations / residuals are read once -> evict first,
-// weights are re-read by every row panel -> evict last; default: normal priority everywhere)
-#if defined(DSHEG_L2_HINTS) && DSHEG_L2_HINTS
-constexpr uint64_t HINT_STREAM = L2_EVICT_FIRST, HINT_KEEP = L2_EVICT_LAST;
-#else
-constexpr uint64_t HINT_STREAM = L2_EVICT_NORMAL, HINT_KEEP = L2_EVICT_NORMAL;
-#endif
+// (L2 eviction hints on the operand loads -- activations / residuals evict-first, weights evict-last -- LOST on hardware: the A panel
+//  is re-read by the n-tiles of its row panel and evict-first throws it out in between; 830 -> 787 TF/s, profiles/r02/call17.)
 
 // ---- spin on an mbarrier phase (PTX primitives: tc_prims.cuh) ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   uint64_t t0 = 0;
   while (true) {
-#if defined(DSHEG_MBAR_SLEEP) && DSHEG_MBAR_SLEEP
-    done = spins ? mbar_try_wait_hint(bar, parity, 20000u) : mbar_try_wait(bar, parity);   // experiment: sleep instead of spinning
-#else
-    done = mbar_try_wait(bar, parity);
-#endif
+    done = mbar_try_wait(bar, parity);   // (try_wait with a suspend-time hint -- sleeping instead of spinning -- measured no difference here: call13)
     if (done) break;
     // watchdog: a lost arrive / wrong descriptor becomes a launch error after 4 s, not a hung GPU
     if ((++spins & 0x3FFu) == 0) {
@@ -241,12 +232,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // both CTAs fill their own smem; all bytes are credited to the leader's full barrier
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             const uint32_t lb = leader_full0 + 8u * stage;
-            tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM, HINT_STREAM);
-            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2), HINT_KEEP);
+            tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
+            tma_load_2d_pair(&tmW, lb, sb, kb * BK, n_blk * BN + (int)rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d_hint(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM, HINT_STREAM);
-            tma_load_2d_hint(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN, HINT_KEEP);
+            tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * BK, m_blk * BM);
+            tma_load_2d(&tmW, full_bar(stage), sb, kb * BK, n_blk * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -427,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
         if (RES == RES_BF16 && lane == 0) {   // residual box by TMA, in flight while the mainloop runs
           mbar_arrive_expect_tx(res_bar(e), STG_BYTES);
-          tma_load_2d_hint(&tmRes, res_bar(e), stg, nc0, m0, HINT_STREAM);
+          tma_load_2d(&tmRes, res_bar(e), stg, nc0, m0);
         }
       }
       // ---- per-row operands, fetched before the accumulator is ready

@@ -64,14 +64,9 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// The same loads with an explicit L2 eviction-priority hint (createpolicy encodings): operands that are read exactly once should not
-// push the activations the NEXT kernel starts with (engine.cu: alternating row walk) out of L2.
+// 3-D load with an explicit L2 eviction-priority hint (createpolicy encodings): the attention kernel reads q' / k' / v exactly once; they
+// should not push the activations the NEXT kernel starts with (engine.cu: alternating row walk) out of L2 (+2 % on hardware, call17).
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
-}
 __device__ __forceinline__ void tma_load_3d_hint(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t hint) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"

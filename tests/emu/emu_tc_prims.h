@@ -139,7 +139,6 @@ inline void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int 
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
   emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
 }
-inline void tma_load_2d_hint(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t) { tma_load_2d(map, bar, dst, c0, c1); }
 inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
 // 3-D (column, frame, sample): the box covers one sample; frames beyond the sample's `rows` (and samples beyond n2) arrive as zeros
 inline void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
