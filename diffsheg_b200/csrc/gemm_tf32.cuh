@@ -179,6 +179,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int ch = chalf * CH_PER_WARP; ch < (chalf + 1) * CH_PER_WARP; ++ch) {
       const int n0 = n_blk * BN + ch * 32;
       if (n0 >= p.N) break;                                 // warp-uniform
+      const int n = n0 + 4 * tcg;
+      const bool vec_ok = n + 3 < p.N && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0);
+      // the chunk's residual values first: 8 independent 16-byte loads per thread in flight under the TMEM load, the epilogue math and
+      // the turn through shared memory (inside the store loop below they were 8 SERIAL L2 / HBM round trips per chunk -- the compiler
+      // cannot hoist a load above the previous iteration's store to a possibly aliasing pointer: 30 % of all stall samples, call9)
+      float4 rv[8];
+      if (p.res && vec_ok) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m_blk * TBM + qd * 32 + 4 * it + tr;
+          const int mr = p.res_mod > 0 ? m % p.res_mod : m;
+          rv[it] = (m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)mr * p.ldr + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ch * 32), r);
 #pragma unroll
@@ -197,8 +211,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         *reinterpret_cast<float4*>(turn + lane * T_TURN_LD + j) = make_float4(v[0], v[1], v[2], v[3]);
       }
       __syncwarp();
-      const int n = n0 + 4 * tcg;
-      const bool vec_ok = n + 3 < p.N && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rl = 4 * it + tr;
@@ -208,10 +220,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const size_t o = (size_t)m * p.ldo + n;
         const int mr = p.res_mod > 0 ? m % p.res_mod : m;
         if (vec_ok) {
-          if (p.res) {
-            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)mr * p.ldr + n));
-            x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
-          }
+          if (p.res) { x.x += rv[it].x; x.y += rv[it].y; x.z += rv[it].z; x.w += rv[it].w; }
           *reinterpret_cast<float4*>(p.out + o) = x;
           if (p.out2) *reinterpret_cast<float4*>(p.out2 + o) = x;
         } else {   // ragged N / unaligned rows: element by element
