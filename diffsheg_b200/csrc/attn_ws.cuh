@@ -4,19 +4,21 @@
 // the Q and K columns hold exp(value - static shift) (softmax is shift-invariant; pack.py:expo_shift proves the range), V is plain:
 //   A = K'^T V / colsum(K')  [64 x 64 per head]     Y = Q' A / rowsum(Q')     z = SiLU(LN_512(Y) * (1 + scale) + shift)
 //
-// Why this shape.  Round 2's first TMA kernel (attn_tma, deleted; profiles/r02/ci1, call9) had all 16 compute warps of the one CTA an SM can hold walk through the
-// same phases together -- A^T, Y, a CTA-wide barrier, the LayerNorm pass -- so the tensor pipe idles during LayerNorm, the FP32 / MUFU
-// pipes idle during the products, and every dependency stall is exposed at 4 warps per scheduler (ncu: issue slots 34 % busy, 0.42 of
-// the copy peak in the sampling loop).  Two samples cannot be resident (Y of one sample is 96 KB of shared memory).  Here the phases
-// belong to DIFFERENT warps working on DIFFERENT samples, and Y never exists in shared memory:
-//   * 8 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep, refilled by the A warps in turn; half-tile granularity with a last-arriver refill was tried and lost: profiles/r02/call15) into the
-//     normalised bf16 A^T of that head (a 32 x 16 tile per warp; the column sums of K' come out of the same fragments, ones . K',
-//     in exactly the accumulator layout, so nothing is exchanged between the warps) and PARK it in tensor memory (8 words per
-//     thread and head).  That is phase 1 of a sample and needs nothing from the Y warps, so it runs a whole sample ahead.  Phase 2
-//     copies the 8 parked heads into the per-head shared-memory slots (64 KB) as their readers release them (mbarrier pair per
-//     head).  The first hardware version accumulated at most ONE head ahead of the release and was serial with the Y warps:
-//     8 heads x (accumulate + epilogue) after every release, 2.36 TB/s (profiles/r02/call10); the second had 4 A warps with 32 x 32
-//     quadrants: one warp per SM sub-partition issuing 620 instructions per head at 0.17 IPC was the critical path (call11).
+// Why this shape.  Round 2's first TMA kernel (attn_tma, deleted; profiles/r02/ci1, call9) had all 16 compute warps of the one CTA an SM
+// can hold walk through the same phases together -- A^T, Y, a CTA-wide barrier, the LayerNorm pass -- so the tensor pipe idled during
+// LayerNorm, the FP32 / MUFU pipes idled during the products, and every dependency stall was exposed at 4 warps per scheduler (ncu:
+// issue slots 34 % busy, 0.42 of the copy peak in the sampling loop).  Two samples cannot be resident (Y of one sample is 96 KB of
+// shared memory).  Here the phases belong to DIFFERENT warps working on DIFFERENT samples, and Y never exists in shared memory:
+//   * 8 "A warps" turn the K' / V tiles of one head after the other (TMA ring, two heads deep; the refill duty rotates over the A
+//     warps; the same head of the next sample is prefetched into L2) into the normalised bf16 A^T of that head -- a 32 x 16 tile per
+//     warp; the column sums of K' come out of the same fragments (ones . K') in exactly the accumulator layout, so nothing is
+//     exchanged between the warps.  The tile goes straight into the head's shared-memory slot (8 x 8 KB) when both readers of the
+//     previous sample have released it (mbarrier pair per head; the test is a warp vote: both branches hold warp collectives), and
+//     is otherwise PARKED in tensor memory (8 words per thread) and copied in a second phase: nothing in phase 1 waits for the Y
+//     warps, so the A warps can run a whole sample ahead.
+//     (History, profiles/r02/call10 .. call15: v1 accumulated at most ONE head ahead of the release and was serial with the Y warps,
+//     2.36 TB/s; v2 had 4 A warps with 32 x 32 quadrants -- one warp per SM sub-partition issuing 620 instructions per head at 0.17
+//     IPC was the critical path; half tiles refilled by the last-arriving warp through a shared-memory atomic lost to this version.)
 //   * 16 "Y warps" = 8 heads x 2 row halves.  Warp (h, half) owns head h of up to three 16-frame tiles: its Q' box (48 frames x 64
 //     columns, 6 KB) arrives by a TMA load the warp issues ITSELF for the next sample the moment its last product has consumed the
 //     current one, so the reload has the whole LayerNorm part to land.  Per tile: Y = Q' A on mma.sync from ldmatrix fragments (A^T
@@ -27,11 +29,12 @@
 //     after the LayerNorm part and keeps every warp within 80 registers (24 warps per SM).
 //   * one named barrier per row half and sample publishes the partials; then every warp normalises, modulates and applies SiLU to
 //     its own tiles (fp32 Y back from tensor memory, 16 columns at a time, never rounded to bf16 before the LayerNorm) and writes z
-//     with 16-byte stores: a store instruction covers 64 contiguous bytes of 8 rows.  No CTA-wide barrier, no LayerNorm pass over shared memory, no shuffles
-//     beyond one quad reduction per tile.
-// Issue slots per sample drop from 37 k to about 20 k warp-instructions and the three pipes (tensor: A warps + Y products; FP32 /
-// MUFU: LayerNorm parts; TMA) overlap because the warps drift apart instead of marching in step.
-// HBM traffic: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample (unchanged).
+//     with 16-byte stores: a store instruction covers 64 contiguous bytes of 8 rows.  No CTA-wide barrier, no LayerNorm pass over
+//     shared memory, no shuffles beyond one quad reduction per tile.
+// Measured (profiles/r02/ci3): 3.23 TB/s in the sampling loop at 1 492 MHz = 0.49 of the copy peak, 168 - 174 us = 0.60 - 0.62 alone
+// under ncu (attn_tma: 2.7 / 207 us); 35 k warp-instructions per sample, issue slots 40 % busy; the A warps (223 instructions and
+// 2.9 k cycles per head, 19 % of it waiting for K' / V tiles) are the critical path.  `rev` walks the CTA's samples last-to-first
+// (engine.cu: alternating row walk).  HBM traffic: read q', k', v + write z = 4 * T * 512 * 2 bytes per sample.
 #pragma once
 #include <type_traits>
 
@@ -60,7 +63,7 @@ constexpr int A_OFF = Q_OFF + NYW * QBOX_BYTES;               // [NH] A^T slots
 constexpr int RING_OFF = A_OFF + NH * A_BYTES;                // [NST] K' / V tiles
 constexpr int STAT_OFF = RING_OFF + NST * TILE_BYTES;         // [sample parity][half][tile][row 16][head 8] float2 (sum, sumsq)
 constexpr int STAT_BYTES = 2 * 2 * MH * 16 * NH * 8;
-constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;                // kv_full[NST] kv_empty[NST / 2] a_full[NH] a_empty[NH] q_full[NYW]
+constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;                // kv_full[NST] kv_empty[NST / 2] a_full[NH] a_empty[NH] q_full[NYW] (mbarriers)
 constexpr int NBAR = NST + NST / 2 + 2 * NH + NYW;
 constexpr int TMEM_SLOT_OFF = BAR_OFF + NBAR * 8;
 constexpr int SMEM_BYTES = ((TMEM_SLOT_OFF + 4 + 127) / 128) * 128;
