@@ -87,6 +87,17 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Who arrives on the A^T hand-over barriers.  Default: lane 0 after __syncwarp (release is cumulative over the warp's stores).
+// -DDSHEG_AWS_ALL_LANES_ARRIVE=1 (diagnostic build, not shipped): every lane arrives itself, so that a tool which tracks happens-before
+// per thread (compute-sanitizer racecheck) sees an edge from each storing / loading lane to the barrier.
+#if defined(DSHEG_AWS_ALL_LANES_ARRIVE) && DSHEG_AWS_ALL_LANES_ARRIVE
+constexpr int ARRIVALS_PER_WARP = 32;
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int) { tc::mbar_arrive(bar); }
+#else
+constexpr int ARRIVALS_PER_WARP = 1;
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) { if (lane == 0) tc::mbar_arrive(bar); }
+#endif
+
 __device__ __forceinline__ void half_sync(int half) { prims::named_bar_sync<32 * NH>(1 + half); }     // ids 1, 2: the 8 Y warps of a row half
 
 // shared-memory row of A^T that holds output column l of the head: n-tile nt = 4 (l >> 5) + ((l >> 1) & 3), row 2 ((l >> 3) & 3) + (l & 1)
@@ -117,7 +128,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) tc::mbar_init(kv_full(s), 1);
     for (int p2 = 0; p2 < NST / 2; ++p2) tc::mbar_init(kv_empty(p2), NAW);
-    for (int h = 0; h < NH; ++h) { tc::mbar_init(a_full(h), NAW); tc::mbar_init(a_empty(h), 2); }
+    for (int h = 0; h < NH; ++h) { tc::mbar_init(a_full(h), NAW * ARRIVALS_PER_WARP); tc::mbar_init(a_empty(h), 2 * ARRIVALS_PER_WARP); }
     for (int w = 0; w < NYW; ++w) tc::mbar_init(q_full(w), 1);
     tc::fence_mbarrier_init();
   }
@@ -181,8 +192,8 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           // the last product of this sample has consumed every Q' and A^T fragment (the mma results depend on them): hand the A^T
           // slot back to the A warps and fetch the next sample's Q' box into this warp's own (now dead, only ever read) box
           __syncwarp();
+          warp_arrive(a_empty(h), lane);
           if (lane == 0) {
-            tc::mbar_arrive(a_empty(h));
             if (i + 1 < n_iter) {
               tc::mbar_arrive_expect_tx(q_full(warp), q_tx);
               tc::tma_load_3d_hint(&tmQ, q_full(warp), qb_addr, h * HD, mt0 * 16, smp_at(i + 1), tc::L2_EVICT_FIRST);
@@ -218,7 +229,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       if (nu == 0) {   // a row half without frames (T <= 16 ...): keep the A^T hand-shake in step
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(a_empty(h));
+        warp_arrive(a_empty(h), lane);
         __syncwarp();
         continue;
       }
@@ -411,7 +422,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 8; ++e) *reinterpret_cast<uint32_t*>(as_ptr + a_off[e]) = pk[e];
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(a_full(hh));   // release: this warp's tile of A^T is written
+          warp_arrive(a_full(hh), lane);   // release: this warp's tile of A^T is written
         } else {
           tc::tmem_st8(apark + (uint32_t)(hh * 8), pk);
           parked |= 1u << hh;
@@ -434,7 +445,7 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int e = 0; e < 8; ++e) *reinterpret_cast<uint32_t*>(as_ptr + a_off[e]) = pk[e];
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(a_full(hh));
+        warp_arrive(a_full(hh), lane);
       }
     }
   }
