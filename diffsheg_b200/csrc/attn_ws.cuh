@@ -87,10 +87,12 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Who arrives on the A^T hand-over barriers.  Default: lane 0 after __syncwarp (release is cumulative over the warp's stores).
-// -DDSHEG_AWS_ALL_LANES_ARRIVE=1 (diagnostic build, not shipped): every lane arrives itself, so that a tool which tracks happens-before
-// per thread (compute-sanitizer racecheck) sees an edge from each storing / loading lane to the barrier.
-#if defined(DSHEG_AWS_ALL_LANES_ARRIVE) && DSHEG_AWS_ALL_LANES_ARRIVE
+// Who arrives on the A^T hand-over barriers: EVERY lane (default).  One arrive by lane 0 after __syncwarp is sufficient under the PTX
+// memory model (release is cumulative over the stores the warp barrier ordered before it) and was the shipped form until the last
+// hardware session, but compute-sanitizer racecheck tracks happens-before per thread and reported the A^T hand-over as a RAW hazard
+// (profiles/r02/ci3); with every storing / loading lane arriving itself the same run reports 0 hazards (profiles/r02/diag).
+// -DDSHEG_AWS_ALL_LANES_ARRIVE=0 restores the single arrive.
+#if !defined(DSHEG_AWS_ALL_LANES_ARRIVE) || DSHEG_AWS_ALL_LANES_ARRIVE
 constexpr int ARRIVALS_PER_WARP = 32;
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int) { tc::mbar_arrive(bar); }
 #else
