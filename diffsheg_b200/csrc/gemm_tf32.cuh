@@ -63,6 +63,9 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+#else   // tests/emu: host model of kind::tf32 (emu_tc_prims.h)
+inline void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { tc_mma_tf32_emu(1, tmem_d, da, db, idesc, acc); }
+inline void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { tc_mma_tf32_emu(2, tmem_d, da, db, idesc, acc); }
 #endif
 
 struct T32Params {
@@ -254,10 +257,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
-#ifndef DSHEG_EMU
 // fp32 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 32 columns] (128-byte rows,
 // SWIZZLE_128B); elements are rounded to TF32 by the load; out-of-bounds elements read as zero.
 inline bool make_tmap_f32(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, std::string* err) {
+#ifdef DSHEG_EMU   // tests/emu: the emulated tensor map records the same geometry (emu_tc_prims.h)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 4)) { *err = "TMA operand not 16-byte aligned"; return false; }
+  map->base = ptr; map->cols = (uint64_t)cols; map->rows = (uint64_t)rows; map->ld_bytes = (uint64_t)ld * 4;
+  map->box_cols = (uint32_t)TBK; map->box_rows = (uint32_t)box_rows; map->swizzle_bytes = 128; map->elem_bytes = 4;
+  return true;
+#else
   struct Key { const void* p; int r, c, l, b; bool operator==(const Key& o) const { return p == o.p && r == o.r && c == o.c && l == o.l && b == o.b; } };
   struct Hash { size_t operator()(const Key& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.r * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.c * 0xC2B2AE3D27D4EB4Full) ^ ((size_t)k.l << 20) ^ ((size_t)k.b << 7); } };
   static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
@@ -276,6 +284,7 @@ inline bool make_tmap_f32(CUtensorMap* map, const void* ptr, int rows, int cols,
   if (cache.size() > 8192) cache.clear();
   cache.emplace(k, *map);
   return true;
+#endif
 }
 
 // true when the TMA path can take this GEMM (16-byte aligned bases and row strides, fp32 in / fp32 out); the caller falls
@@ -290,9 +299,23 @@ inline bool tf32_eligible(const GemmDesc& d) {
 }
 
 // A, W, residual, out: fp32 (the "tf32" mode keeps every activation in fp32); residual / out may be fp32 by type or by flag
+#ifdef DSHEG_EMU
+inline std::string& g_emu_error_tf32() { static std::string e; return e; }
+#endif
+
 template <int CG>
 inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params& p, int tiles, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<CG>;
+#ifdef DSHEG_EMU   // tests/emu: run the grid on the thread-level emulator (clusters of CG CTAs)
+  (void)st;
+  const CUtensorMap m0 = maps[0], m1 = maps[1], m2 = maps[2], m3 = maps[3], m4 = maps[4];
+  static std::string emu_err;
+  if (!emu::run_grid(tiles * CG, T_NUM_THREADS, CG, TCfg<CG>::SMEM_BYTES, [=] { kern(m0, m1, m2, m3, m4, p); }, &emu_err)) {
+    g_emu_error_tf32() = emu_err;
+    return cudaErrorLaunchFailure;
+  }
+  return cudaSuccess;
+#else
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<CG>::SMEM_BYTES);
@@ -308,6 +331,7 @@ inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params&
     cfg.attrs = attr; cfg.numAttrs = 1;
   }
   return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+#endif
 }
 
 // A, W, residual, out: fp32 (the "tf32" mode keeps every activation in fp32); residual / out may be fp32 by type or by flag.
@@ -339,7 +363,6 @@ inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::str
   p.out = reinterpret_cast<float*>(d.out); p.ldo = d.ldo; p.out2 = reinterpret_cast<float*>(d.out2);
   return cg == 2 ? launch_tf32_variant<2>(maps, p, tiles_m * p.tiles_n, st) : launch_tf32_variant<1>(maps, p, tiles_m * p.tiles_n, st);
 }
-#endif  // DSHEG_EMU
 
 }  // namespace t32
 }  // namespace dsheg

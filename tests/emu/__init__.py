@@ -60,3 +60,10 @@ def attn_ws_lib():
     L = _load("emu_attn_ws")
     L.emu_attn_ws_last_error.restype = ctypes.c_char_p
     return L
+
+
+def gemm_tf32_lib():
+    """gemm_tf32.cuh (tcgen05 kind::tf32, TFLOAT32 tensor maps, CTA pairs, two CTAs per SM) on the models of emu_tc_prims.h."""
+    L = _load("emu_gemm_tf32")
+    L.emu_gemm_tf32_last_error.restype = ctypes.c_char_p
+    return L

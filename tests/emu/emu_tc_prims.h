@@ -10,6 +10,7 @@
 //                   XOR); cta_group::2: M = 256 -- rows 0..127 from the leader's smem / TMEM, 128..255 from the peer's;
 //                   each CTA supplies HALF of the N rows of B.  Executed synchronously at issue, so tcgen05.commit
 //                   arrives immediately (the real ordering guarantees are a superset).
+//   kind::tf32    : the same with fp32 operands read as TF32 (19 bits), K = 8 per instruction; TFLOAT32 tensor maps round on load
 //   tcgen05.ld    : 32x32b.x32 -- thread `lane` of the warp reads 32 consecutive columns of TMEM lane (base + lane)
 //   TMEM          : 128 lanes x 512 fp32 columns per CTA; alloc returns base 0
 // Not modelled: async-proxy / generic-proxy ordering (fence.proxy.async), TMEM allocation contention, timing.
@@ -24,6 +25,7 @@ struct CUtensorMap {   // emulated tensor map: row-major bf16 [rows, cols], lead
   uint32_t box_cols = 0, box_rows = 0;
   int swizzle_bytes = 128;
   uint64_t n2 = 1, ld2_bytes = 0;   // 3-D maps (column, frame, sample): number of samples and their stride; `rows` = frames per sample
+  int elem_bytes = 2;               // 2: bf16; 4: fp32 loaded as TF32 (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32: gemm_tf32.cuh)
 };
 
 #define DSHEG_TC_DYN_SMEM(name) uint8_t* name = emu::self().cta->smem
@@ -121,23 +123,35 @@ inline uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t) { re
 inline void tma_copy(const CUtensorMap* m, emu::Cta* cta, uint32_t smem_off, int c0, int c1, bool load) {
   if (smem_off % (m->swizzle_bytes == 128 ? 1024 : (m->swizzle_bytes == 64 ? 512 : 16)))
     emu::rt().error = "TMA: shared-memory box not aligned to its swizzle atom";
-  const uint32_t row_bytes = m->box_cols * 2;
+  const uint32_t eb = (uint32_t)m->elem_bytes, row_bytes = m->box_cols * eb;
   if ((size_t)smem_off + (size_t)row_bytes * m->box_rows > cta->smem_bytes) { emu::rt().error = "TMA: box outside shared memory"; return; }
   for (uint32_t r = 0; r < m->box_rows; ++r) {
     for (uint32_t c = 0; c < m->box_cols; ++c) {
       const long long gr = (long long)c1 + r, gc = (long long)c0 + c;
       const bool inb = gr >= 0 && gc >= 0 && (uint64_t)gr < m->rows && (uint64_t)gc < m->cols;
-      uint8_t* sp = cta->smem + emu::swizzle_addr(smem_off + r * row_bytes + c * 2, m->swizzle_bytes);
-      uint8_t* gp = const_cast<uint8_t*>(static_cast<const uint8_t*>(m->base)) + (size_t)gr * m->ld_bytes + (size_t)gc * 2;
-      if (load) { if (inb) memcpy(sp, gp, 2); else memset(sp, 0, 2); }
-      else if (inb) memcpy(gp, sp, 2);
+      uint8_t* sp = cta->smem + emu::swizzle_addr(smem_off + r * row_bytes + c * eb, m->swizzle_bytes);
+      uint8_t* gp = const_cast<uint8_t*>(static_cast<const uint8_t*>(m->base)) + (size_t)gr * m->ld_bytes + (size_t)gc * eb;
+      if (load) {
+        if (!inb) { memset(sp, 0, eb); continue; }
+        if (eb == 4) {   // TFLOAT32 load: the 13 low mantissa bits are rounded away (nearest even); Inf / NaN pass through
+          uint32_t u;
+          memcpy(&u, gp, 4);
+          if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x0FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+          memcpy(sp, &u, 4);
+        } else {
+          memcpy(sp, gp, eb);
+        }
+      } else if (inb) {
+        memcpy(gp, sp, eb);
+      }
     }
   }
 }
+inline long long tma_box_bytes(const CUtensorMap* m) { return (long long)m->box_cols * m->elem_bytes * m->box_rows; }
 inline void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
   emu::delay("EMU_DELAY_TMA");
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
-  emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
+  emu::bar_complete_tx(bar, tma_box_bytes(map));
 }
 inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
 // 3-D (column, frame, sample): the box covers one sample; frames beyond the sample's `rows` (and samples beyond n2) arrive as zeros
@@ -147,7 +161,7 @@ inline void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int 
   if (c2 < 0 || (uint64_t)c2 >= map->n2) m2.rows = 0;   // everything out of bounds
   else m2.base = static_cast<const uint8_t*>(map->base) + (size_t)c2 * map->ld2_bytes;
   tma_copy(&m2, emu::self().cta, dst, c0, c1, true);
-  emu::bar_complete_tx(bar, (long long)map->box_cols * 2 * map->box_rows);
+  emu::bar_complete_tx(bar, tma_box_bytes(map));
 }
 inline void tma_load_3d_hint(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t) { tma_load_3d(map, bar, dst, c0, c1, c2); }
 inline void tma_prefetch_l2_3d(const CUtensorMap*, int, int, int) {}
@@ -155,7 +169,7 @@ constexpr uint64_t L2_EVICT_NORMAL = 0, L2_EVICT_FIRST = 1, L2_EVICT_LAST = 2;  
 inline void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1, uint64_t = 0) {
   emu::delay("EMU_DELAY_TMA");
   tma_copy(map, emu::self().cta, dst, c0, c1, true);
-  emu::bar_complete_tx(leader_bar, (long long)map->box_cols * 2 * map->box_rows);
+  emu::bar_complete_tx(leader_bar, tma_box_bytes(map));
 }
 // TMA stores are ASYNCHRONOUS: the engine may read the shared-memory box at any time until the issuing thread's
 // cp.async.bulk.wait_group(.read) returns.  The model reads it at the LATEST legal moment -- at that wait -- so a kernel that reuses
@@ -203,17 +217,30 @@ inline float emu_bf16_at(const emu::Cta* c, uint32_t addr) {
   memcpy(&f, &u, 4);
   return f;
 }
-// element (row, k) of a K-major SWIZZLE_128B operand described by `desc` (k < 16: one UMMA_K slice)
-inline float emu_operand(const emu::Cta* c, uint64_t desc, int row, int k) {
+inline float emu_f32_at(const emu::Cta* c, uint32_t addr) {
+  if ((size_t)addr + 4 > c->smem_bytes) { emu::rt().error = "tcgen05.mma: operand read outside shared memory"; return 0.f; }
+  uint32_t u;
+  memcpy(&u, c->smem + addr, 4);
+  u &= 0xFFFFE000u;   // kind::tf32 reads 19 bits (the TMA load already rounded them)
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// element (row, k) of a K-major SWIZZLE_128B operand described by `desc`; eb = 2: bf16, k < 16; eb = 4: tf32, k < 8 (one UMMA_K slice = 32 bytes)
+inline float emu_operand(const emu::Cta* c, uint64_t desc, int row, int k, int eb = 2) {
   const uint32_t start = (uint32_t)(desc & 0x3FFFu) << 4;
   const uint32_t sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
   const uint32_t layout = (uint32_t)(desc >> 61) & 7u;
   if (layout != 2 || sbo != 1024) emu::rt().error = "tcgen05.mma: the emulator models K-major SWIZZLE_128B descriptors with SBO = 1024 only";
-  const uint32_t lin = start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
-  return emu_bf16_at(c, emu::swizzle_addr(lin, 128));
+  const uint32_t lin = start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)(k * eb);
+  return eb == 4 ? emu_f32_at(c, emu::swizzle_addr(lin, 128)) : emu_bf16_at(c, emu::swizzle_addr(lin, 128));
 }
-inline void emu_mma(int cg, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// kind: 0 = kind::f16 with bf16 operands (K = 16 per instruction), 1 = kind::tf32 (K = 8)
+inline void emu_mma(int cg, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, int kind = 0) {
   const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
+  const int K = kind == 1 ? 8 : 16, eb = kind == 1 ? 4 : 2;
+  const uint32_t fmt_a = (idesc >> 7) & 7u, fmt_b = (idesc >> 10) & 7u;
+  if (kind == 1 && (fmt_a != 2 || fmt_b != 2)) emu::rt().error = "tcgen05.mma.kind::tf32: the instruction descriptor does not say TF32 operands";
   emu::delay("EMU_DELAY_MMA");
   emu::Cta* me = emu::self().cta;
   if (cg == 2 && me->rank != 0) { emu::rt().error = "tcgen05.mma.cta_group::2 issued by the non-leader CTA"; return; }
@@ -222,24 +249,24 @@ inline void emu_mma(int cg, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, u
     return;
   }
   const int col0 = (int)(tmem_d & 0xFFFFu);
-  std::vector<float> a((size_t)M * 16), b((size_t)N * 16);
+  std::vector<float> a((size_t)M * K), b((size_t)N * K);
   for (int m = 0; m < M; ++m) {
     const emu::Cta* c = cg == 2 ? &me->cluster->ctas[m / 128] : me;
-    for (int k = 0; k < 16; ++k) a[(size_t)m * 16 + k] = emu_operand(c, desc_a, m % 128, k);
+    for (int k = 0; k < K; ++k) a[(size_t)m * K + k] = emu_operand(c, desc_a, m % 128, k, eb);
   }
   const int n_per_cta = N / cg;
   for (int n = 0; n < N; ++n) {
     const emu::Cta* c = cg == 2 ? &me->cluster->ctas[n / n_per_cta] : me;
-    for (int k = 0; k < 16; ++k) b[(size_t)n * 16 + k] = emu_operand(c, desc_b, n % n_per_cta, k);
+    for (int k = 0; k < K; ++k) b[(size_t)n * K + k] = emu_operand(c, desc_b, n % n_per_cta, k, eb);
   }
   for (int m = 0; m < M; ++m) {
     emu::Cta* c = cg == 2 ? &me->cluster->ctas[m / 128] : me;
     float* d = emu::tc_state(c).tmem.data() + (size_t)(m % 128) * 512 + col0;
-    const float* am = &a[(size_t)m * 16];
+    const float* am = &a[(size_t)m * K];
     for (int n = 0; n < N; ++n) {
-      const float* bn = &b[(size_t)n * 16];
+      const float* bn = &b[(size_t)n * K];
       float s = 0.f;
-      for (int k = 0; k < 16; ++k) s += am[k] * bn[k];
+      for (int k = 0; k < K; ++k) s += am[k] * bn[k];
       d[n] = accumulate ? d[n] + s : s;
     }
   }
@@ -247,6 +274,7 @@ inline void emu_mma(int cg, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, u
 }
 inline void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { emu_mma(1, tmem_d, da, db, idesc, acc); }
 inline void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { emu_mma(2, tmem_d, da, db, idesc, acc); }
+inline void tc_mma_tf32_emu(int cg, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) { emu_mma(cg, tmem_d, da, db, idesc, acc, 1); }
 inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   emu::delay("EMU_DELAY_TMEM_LD");
   emu::Thread& t = emu::self();

@@ -309,3 +309,110 @@ def test_reverse_row_panel_walk_gives_the_same_result(kw):
     rev, _, _ = run_gemm(M, N, ks, seed=21, rev=1, **kw)
     assert torch.equal(fwd, rev)
     assert float((fwd - want).abs().max() / want.abs().max()) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# gemm_tf32.cuh: the GEMM engine of the tf32 precision mode (fp32 activations, TF32 operands, fp32 accumulate / epilogue / output)
+# ------------------------------------------------------------------------------------------------------------------------------
+class Tf32Args(ctypes.Structure):
+    _fields_ = [("M", ctypes.c_int32), ("N", ctypes.c_int32), ("nseg", ctypes.c_int32),
+                ("seg_k", ctypes.c_int32 * 4), ("seg_ld", ctypes.c_int32 * 4), ("seg_ptr", ctypes.c_void_p * 4),
+                ("w", ctypes.c_void_p), ("Kp", ctypes.c_int32),
+                ("bias", ctypes.c_void_p), ("csum", ctypes.c_void_p), ("mu", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+                ("act", ctypes.c_int32), ("res", ctypes.c_void_p), ("ldr", ctypes.c_int32), ("res_mod", ctypes.c_int32),
+                ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("out2", ctypes.c_void_p), ("cg_force", ctypes.c_int32)]
+
+
+def _to_tf32(t):
+    """fp32 -> TF32 (10-bit mantissa, round to nearest even) as the TFLOAT32 tensor map delivers it; returned as float64."""
+    u = t.float().contiguous().view(torch.int32)
+    u = (u + 0x0FFF + ((u >> 13) & 1)) & ~0x1FFF
+    return u.view(torch.float32).double()
+
+
+def run_gemm_tf32(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, dup=False, cg=0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    Kp = sum(r64(k) for k in seg_ks)
+    W = torch.zeros(N, Kp)
+    keep, A_cat, off = [], [], 0
+    a = Tf32Args()
+    a.M, a.N, a.nseg, a.Kp, a.cg_force, a.act = M, N, len(seg_ks), Kp, cg, act
+    for i, k in enumerate(seg_ks):
+        ld = r64(k) + 12                                   # a wider buffer: exercises the leading dimension (multiple of 4)
+        seg = torch.full((M, ld), 7.0)                     # garbage beyond the segment width must never reach the product
+        seg[:, :k] = rnd(M, k)
+        W[:, off:off + k] = rnd(N, k) / np.sqrt(sum(seg_ks))
+        buf = np.ascontiguousarray(seg.numpy())
+        keep.append(buf)
+        a.seg_k[i], a.seg_ld[i], a.seg_ptr[i] = k, ld, buf.ctypes.data
+        A_cat.append((_to_tf32(seg[:, :k]), _to_tf32(W[:, off:off + k])))
+        off += r64(k)
+    acc = sum(x @ w.T for x, w in A_cat)
+    Wb = np.ascontiguousarray(W.numpy())
+    bias = rnd(N).numpy().copy()
+    a.w, a.bias = Wb.ctypes.data, bias.ctypes.data
+    want = acc.clone()
+    if ln:                                                 # LayerNorm fold: out = rstd * (acc - mu * csum) + bias
+        csum, mu, rstd = rnd(N).numpy().copy(), rnd(M).numpy().copy(), (0.5 + torch.rand(M, generator=g)).numpy().copy()
+        keep += [csum, mu, rstd]
+        a.csum, a.mu, a.rstd = csum.ctypes.data, mu.ctypes.data, rstd.ctypes.data
+        want = torch.from_numpy(rstd).double()[:, None] * (acc - torch.from_numpy(mu).double()[:, None] * torch.from_numpy(csum).double()[None, :])
+    want = want + torch.from_numpy(bias).double()[None, :]
+    if act == ACT_GELU:
+        want = torch.nn.functional.gelu(want)
+    elif act == ACT_SILU:
+        want = torch.nn.functional.silu(want)
+    if res == "f32":
+        ldr = N + 4
+        r = np.ascontiguousarray(rnd(M, ldr).numpy())
+        keep.append(r)
+        a.res, a.ldr, a.res_mod = r.ctypes.data, ldr, 0
+        want = want + torch.from_numpy(r[:, :N]).double()
+    elif res == "f32mod":
+        rows = 34
+        r = np.ascontiguousarray(rnd(rows, N).numpy())
+        keep.append(r)
+        a.res, a.ldr, a.res_mod = r.ctypes.data, N, rows
+        want = want + torch.from_numpy(r).double()[torch.arange(M) % rows]
+    ldo = N + 8
+    out = np.full((M, ldo), np.float32(-777.0))
+    out2 = np.full((M, ldo), np.float32(-777.0)) if dup else None
+    a.out, a.ldo = out.ctypes.data, ldo
+    a.out2 = out2.ctypes.data if dup else None
+    L = emu.gemm_tf32_lib()
+    rc = L.emu_gemm_tf32(ctypes.byref(a))
+    assert rc == 0, L.emu_gemm_tf32_last_error().decode()
+    assert (out[:, N:] == -777.0).all(), "wrote beyond the N columns of a row"
+    got = torch.from_numpy(out[:, :N]).double()
+    if dup:
+        assert np.array_equal(out, out2)
+    return got, want
+
+
+@pytest.mark.parametrize("kw", [
+    dict(M=300, N=512, ks=[512], cg=2),                                   # CTA pair, ragged last pair of row panels
+    dict(M=700, N=1536, ks=[512], cg=2, ln=True),                         # qkv: LayerNorm fold
+    dict(M=260, N=1024, ks=[512], cg=2, act=ACT_GELU),                    # ffn1: exact-erf GELU
+    dict(M=260, N=512, ks=[1024], cg=2, res="f32"),                       # ffn_out / sa_out: fp32 residual (prefetched per chunk)
+    dict(M=140, N=512, ks=[232], cg=1, res="f32mod", dup=True),           # joint_embed + PE, dual store, single CTAs, ragged K
+    dict(M=200, N=512, ks=[512, 256, 128, 103], cg=2, ln=True, act=ACT_SILU),   # feat_proj: 4-segment virtual concat, ragged last segment
+    dict(M=129, N=200, ks=[96], cg=1),                                    # ragged N (element-wise store path), one k-block of padding
+])
+def test_gemm_tf32_kernel_source_on_emulator(kw):
+    """The tf32 engine's kernel AND host launch code on the emulator (it had hardware coverage only): TFLOAT32 tensor maps, kind::tf32
+    MMAs with K = 8, CTA pairs, the 8-warp epilogue with its turn through shared memory, every epilogue family the tf32 mode uses."""
+    kw = dict(kw)
+    M, N, ks = kw.pop("M"), kw.pop("N"), kw.pop("ks")
+    got, want = run_gemm_tf32(M, N, ks, seed=5, **kw)
+    assert torch.isfinite(got).all()
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 2e-5, err        # operands are exactly the TF32 values the reference uses; only fp32 accumulation order differs
+
+
+@pytest.mark.parametrize("sched", ["reverse", "shuffle"])
+def test_gemm_tf32_is_independent_of_the_thread_schedule(sched, monkeypatch):
+    base, _ = run_gemm_tf32(260, 512, [512], cg=2, res="f32", seed=6)
+    monkeypatch.setenv("EMU_SCHED", sched)
+    got, _ = run_gemm_tf32(260, 512, [512], cg=2, res="f32", seed=6)
+    assert torch.equal(base, got)
