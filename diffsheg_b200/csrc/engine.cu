@@ -267,7 +267,7 @@ struct Runner {
       if (e != cudaSuccess && !terr.empty()) return fail(h, std::string("gemm ") + name + ": " + terr);
     } else if (std::is_same<TA, float>::value && h->cfg.precision == DSHEG_PREC_TF32 && h->gemm_engine == 1 && d.M >= 16 && t32::tf32_eligible(d)) {
       std::string terr;   // tf32 mode: tensor cores for every GEMM the TMA path can take; tiny / odd-shaped ones stay on the fp32 SIMT kernel
-      e = t32::launch_gemm_tf32(d, st, &terr);
+      e = t32::launch_gemm_tf32(d, h->num_sms, st, &terr);
       if (e != cudaSuccess && !terr.empty()) return fail(h, std::string("gemm ") + name + " (tf32): " + terr);
     } else {
       e = launch_gemm_simt<TA, TW>(d, st);
@@ -972,7 +972,10 @@ int dsheg_op_linear(int32_t precision, const float* A, const float* W, const flo
     std::string terr;
     if (precision == DSHEG_PREC_TF32) {
       if (!t32::tf32_eligible(d)) { if (Wp) cudaFree(Wp); g_create_error = "op_linear tf32: operands must be 16-byte aligned with K % 4 == 0"; return 1; }
-      e = t32::launch_gemm_tf32(d, st, &terr);
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      e = t32::launch_gemm_tf32(d, sms, st, &terr);
     } else {
       e = launch_gemm_simt<float, float>(d, st);
     }

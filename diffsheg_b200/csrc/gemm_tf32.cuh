@@ -6,15 +6,16 @@
 // are rounded to TF32 (10-bit mantissa, round-to-nearest by the TMA load: CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), accumulation is
 // fp32 in TMEM.  out[M, N] = epilogue(A[M, K] . W[N, K]^T), A = virtual concat of up to 4 fp32 segments.
 //
-// Shape: one output tile per CTA or CTA pair (not persistent; see TCfg), K in blocks of 32 fp32 (128-byte rows, SWIZZLE_128B --
-// byte-for-byte the operand geometry of the bf16 kernel: 8 TF32 elements = 32 bytes per MMA k-step), 3-stage TMA ring, TWO CTAs per SM
-// (96 KB of ring + 256 TMEM columns each): the fp32 epilogue (exact erf GELU, fp32 residual / output rows of 1 - 6 KB) costs several
-// times the mainloop, so one CTA's epilogue runs under the other's mainloop -- or, most of the time, under its epilogue: 16 epilogue
-// warps per SM.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue (TMEM lane quadrant = warp id % 4,
-// column half = (warp - 2) / 4).  Round 2's first pair version had 4 epilogue warps and one CTA per SM: tensor pipe 5 - 12 % busy
-// (profiles/r02/call9).  The epilogue does its per-row / per-column math in the TMEM layout
-// (thread = row), then turns each 32-column chunk through shared memory (the mainloop's ring is free by then) so that the
-// residual loads and the stores are 128-byte coalesced: 8 lanes x 16 bytes per row, 4 rows per instruction.
+// Shape: PERSISTENT like the bf16 engine (one CTA or CTA pair per SM walks the output tiles, n fastest), K in blocks of 32 fp32
+// (128-byte rows, SWIZZLE_128B -- byte-for-byte the operand geometry of the bf16 kernel: 8 TF32 elements = 32 bytes per MMA k-step),
+// 4-stage TMA ring, TWO accumulator stages in TMEM (2 x 256 columns): the fp32 epilogue of tile i -- exact erf GELU, fp32 residual /
+// output rows of 1 - 6 KB, several times the mainloop when it ran alone -- runs on 16 warps under the mainloop of tile i + 1.
+// Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..19 = epilogue (TMEM lane quadrant = warp id % 4, column group =
+// (warp - 4) / 4; a warp hands its accumulator stage back right after its last tcgen05.ld).  The epilogue does its per-row /
+// per-column math in the TMEM layout (thread = row), then turns each 32-column chunk through a private 4.5 KB staging buffer so that
+// the residual loads and the stores are 128-byte coalesced: 8 lanes x 16 bytes per row, 4 rows per instruction.
+// History (profiles/r02): 4 epilogue warps, one tile per CTA, one CTA per SM: tensor pipe 5 - 12 % busy (call9) -> 8 epilogue warps,
+// two CTAs per SM (call11: 2 x) -> residual values of a chunk loaded up front (t32: + 6 %) -> this persistent form.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -24,25 +25,28 @@ namespace t32 {
 using namespace tc;
 
 constexpr int TBM = 128, TBK = 32;                     // rows per CTA, fp32 elements per k-block (128-byte rows)
-constexpr int T_NUM_EPI_WARPS = 8;
-constexpr int T_NUM_THREADS = 64 + 32 * T_NUM_EPI_WARPS;
+constexpr int T_NE = 16;                                 // epilogue warps (warps 4 .. 19)
+constexpr int T_NUM_THREADS = 128 + 32 * T_NE;
+constexpr int T_NUM_ACC = 2;                             // accumulator stages in TMEM
 constexpr int T_TURN_LD = 36;                            // floats per staged row (144 B: 16-byte aligned, conflict-free)
+constexpr int T_TURN_BYTES = 32 * T_TURN_LD * 4;         // one warp's staging rows
 constexpr int T_BAR_BYTES = 128;
 
-// CG = 1: one CTA per 128 x 128 tile, 3 stages of 32 KB, two CTAs per SM (one's epilogue overlaps the other's mainloop) -- small
-//         problems.  Its operand traffic (4 KB + 4 KB per 64-cycle MMA, 32 FLOP per L2 byte) bounds it near 350 TF/s.
-// CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile, like the bf16 engine's pair kernels: each CTA stages
-//         its 128 A rows and HALF of the W tile (128 of the 256 N rows), the leader issues 256 x 256 x 8 MMAs that read both CTAs'
-//         shared memory, each CTA's TMEM holds its 128 rows x 256 columns.  3 stages of 32 KB, two CTAs (of different pairs) per SM.
+// CG = 1: a CTA per 128 x 128 tile (small problems).  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile, like
+//         the bf16 engine's pair kernels: each CTA stages its 128 A rows and HALF of the W tile (128 of the 256 N rows), the leader
+//         issues 256 x 256 x 8 MMAs that read both CTAs' shared memory, each CTA's TMEM holds its 128 rows x 2 x 256 columns.
 template <int CG> struct TCfg {
   static constexpr int BN = CG == 2 ? 256 : 128;         // tile width
+  static constexpr int CPW = BN / (T_NE / 4);            // columns per epilogue warp (64 / 32)
   static constexpr int W_ROWS = BN / CG;                 // W rows staged by ONE CTA
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 4;
   static constexpr int A_BYTES = TBM * TBK * 4, B_BYTES = W_ROWS * TBK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int VEC_BYTES = 2 * BN * 4;           // bias | csum of the tile's columns, staged once by the epilogue warps
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + T_BAR_BYTES + VEC_BYTES + 1024;   // + alignment slack
-  static constexpr int MIN_CTAS = 2;
-  static_assert(T_NUM_EPI_WARPS * 32 * T_TURN_LD * 4 <= STAGES * STAGE_BYTES, "the epilogue turns its chunks through the idle ring");
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int VEC_BYTES = T_NUM_ACC * 2 * BN * 4;   // bias | csum of a tile's columns, double-buffered with the accumulator stage
+  static constexpr int SMEM_BYTES = PIPE_BYTES + T_NE * T_TURN_BYTES + T_BAR_BYTES + VEC_BYTES + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = T_NUM_ACC * BN;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+  static_assert((2 * STAGES + 2 * T_NUM_ACC + 1) * 8 <= T_BAR_BYTES, "barrier area");
   // kind::tf32 instruction descriptor: D = f32 (bit 4), A = B = TF32 (format 2 at [7,10) and [10,13)), both K-major,
   // N >> 3 at [17,23), M >> 4 at [24,29)
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TBM * CG) >> 4) << 24);
@@ -71,7 +75,7 @@ inline void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t
 struct T32Params {
   int M, N, num_kb, nseg;
   int seg_kb_start[5];
-  int tiles_n;
+  int tiles_m, tiles_n;
   const float* bias; const float* csum; const float* mu; const float* rstd;
   int act;
   const float* res; int ldr, res_mod;
@@ -79,34 +83,36 @@ struct T32Params {
 };
 
 template <int CG>
-__global__ void __launch_bounds__(T_NUM_THREADS, TCfg<CG>::MIN_CTAS)
+__global__ void __launch_bounds__(T_NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmW, const T32Params p) {
   using C = TCfg<CG>;
-  constexpr int BN = C::BN, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_BYTES = C::A_BYTES;
+  constexpr int BN = C::BN, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_BYTES = C::A_BYTES, CPW = C::CPW;
   DSHEG_TC_DYN_SMEM(smem_raw);
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair = leader (issues the MMAs)
+  const int cta_stride = gridDim.x / CG, cta_first = blockIdx.x / CG;   // tiles are walked per CTA (pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-B alignment
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + C::PIPE_BYTES + T_NE * T_TURN_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + T_NUM_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * T_NUM_ACC);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + (tmem_slot - smem_base));
+  float* vecs = reinterpret_cast<float*>(gen_base + (bar_base - smem_base) + T_BAR_BYTES);   // [T_NUM_ACC][2][BN]: bias | csum
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int tile = blockIdx.x / CG;                                    // one tile per CTA (pair)
-  const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;   // n fastest: concurrent CTAs share the A panel in L2
+  const int num_tiles = p.tiles_m * p.tiles_n;   // tiles per CTA (pair), numbered n fastest: concurrent CTAs share the A panel in L2
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull_bar, 1);
+    for (int a = 0; a < T_NUM_ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), T_NE * CG); }
     fence_mbarrier_init();
     prefetch_tensormap(&tmA0);
     prefetch_tensormap(&tmW);
   }
-  if (warp == 1) tmem_alloc<CG, BN>(tmem_slot);   // the same warp id in both CTAs of a pair
+  if (warp == 1) tmem_alloc<CG, C::TMEM_COLS>(tmem_slot);   // the same warp id in both CTAs of a pair
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
@@ -116,25 +122,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // ================= TMA producer (each CTA fills its own smem; a pair credits all bytes to the leader's barrier) =================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, seg = 0;
+      int stage = 0; uint32_t phase = 0;
       const uint32_t leader_full0 = CG == 2 ? mapa_rank(full_bar(0), 0) : 0u;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        while (kb >= p.seg_kb_start[seg + 1]) ++seg;
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
-        // W's K axis lays every segment out padded to 64 = two k-blocks, so k-block kb of the walk IS W's k-block kb
-        if (CG == 2) {
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-          const uint32_t lb = leader_full0 + 8u * stage;
-          tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
-          tma_load_2d_pair(&tmW, lb, sb, kb * TBK, n_blk * BN + (int)rank * (BN / 2));
-        } else {
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
-          tma_load_2d(&tmW, full_bar(stage), sb, kb * TBK, n_blk * BN);
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+        const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
+        int seg = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          while (kb >= p.seg_kb_start[seg + 1]) ++seg;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const CUtensorMap* ma = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : (seg == 2 ? &tmA2 : &tmA3));
+          // W's K axis lays every segment out padded to 64 = two k-blocks, so k-block kb of the walk IS W's k-block kb
+          if (CG == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            const uint32_t lb = leader_full0 + 8u * stage;
+            tma_load_2d_pair(ma, lb, sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
+            tma_load_2d_pair(&tmW, lb, sb, kb * TBK, n_blk * BN + (int)rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(ma, full_bar(stage), sa, (kb - p.seg_kb_start[seg]) * TBK, m_blk * TBM);
+            tma_load_2d(&tmW, full_bar(stage), sb, kb * TBK, n_blk * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -142,110 +152,133 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // the epilogue warps (of both CTAs) have drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
-        for (int k = 0; k < TBK / 8; ++k) {   // 8 TF32 = 32 bytes per k-step: +2 in 16-byte descriptor units
-          if (CG == 2) tc_mma_tf32_pair(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
-          else tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+          for (int k = 0; k < TBK / 8; ++k) {   // 8 TF32 = 32 bytes per k-step: +2 in 16-byte descriptor units
+            if (CG == 2) tc_mma_tf32_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+            else tc_mma_tf32(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::IDESC, (kb | k) != 0);
+          }
+          if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));   // frees the smem slot(s) when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));   // frees the smem slot(s) when the MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (CG == 2) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue(s)
+        if (++acc == T_NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
-      if (CG == 2) tc_commit_pair(tfull_bar); else tc_commit(tfull_bar);   // accumulator complete -> epilogue(s)
     }
     __syncwarp();
-  } else {
-    // ================= epilogue: warps 2..9, TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4 =================
-    const int qd = warp & 3, chalf = (warp - 2) >> 2;
-    constexpr int CH_PER_WARP = BN / 32 / (T_NUM_EPI_WARPS / 4);
-    const int m_row = m_blk * TBM + qd * 32 + lane;        // the row this thread holds in the TMEM layout
+  } else if (warp >= 4) {
+    // ================= epilogue: warps 4..19, TMEM lane quadrant = warp id % 4, column group = (warp - 4) / 4 =================
+    const int e = warp - 4, qd = warp & 3, cgp = e >> 2;
+    const int etid = threadIdx.x - 128;
     const bool ln = p.csum != nullptr;
-    const float mu = (ln && m_row < p.M) ? __ldg(p.mu + m_row) : 0.f;
-    const float rstd = (ln && m_row < p.M) ? __ldg(p.rstd + m_row) : 1.f;
-    float* turn = reinterpret_cast<float*>(gen_base) + (warp - 2) * 32 * T_TURN_LD;   // this warp's 32 x 36 staging rows (idle ring)
-    float* vbias = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + T_BAR_BYTES);   // [BN] bias, [BN] csum (outside the ring:
-    float* vcsum = vbias + BN;                                                                 //  staged while the mainloop runs)
-    for (int i = threadIdx.x - 64; i < BN; i += 32 * T_NUM_EPI_WARPS) {
-      const int n = n_blk * BN + i;
-      vbias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
-      vcsum[i] = (ln && n < p.N) ? __ldg(p.csum + n) : 0.f;
-    }
-    epi_bar_sync<32 * T_NUM_EPI_WARPS>();
+    float* turn = reinterpret_cast<float*>(gen_base + C::PIPE_BYTES) + e * 32 * T_TURN_LD;   // this warp's 32 x 36 staging rows
     const int tr = lane >> 3, tcg = lane & 7;              // coalesced layout: row 4 it + tr of the chunk, columns 4 tcg .. + 3
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
+    const uint32_t leader_tempty0 = CG == 2 ? mapa_rank(tempty_bar(0), 0) : 0u;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      const int m_blk = (tile / p.tiles_n) * CG + (int)rank, n_blk = tile % p.tiles_n;
+      // ---- per-column vectors of this tile, double-buffered with the accumulator stage (a warp can be at most one tile ahead of another)
+      float* vbias = vecs + acc * 2 * BN;
+      float* vcsum = vbias + BN;
+      for (int i = etid; i < BN; i += 32 * T_NE) {
+        const int n = n_blk * BN + i;
+        vbias[i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        vcsum[i] = (ln && n < p.N) ? __ldg(p.csum + n) : 0.f;
+      }
+      epi_bar_sync<32 * T_NE>();
+      const int m_row = m_blk * TBM + qd * 32 + lane;        // the row this thread holds in the TMEM layout
+      const float mu = (ln && m_row < p.M) ? __ldg(p.mu + m_row) : 0.f;
+      const float rstd = (ln && m_row < p.M) ? __ldg(p.rstd + m_row) : 1.f;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-    for (int ch = chalf * CH_PER_WARP; ch < (chalf + 1) * CH_PER_WARP; ++ch) {
-      const int n0 = n_blk * BN + ch * 32;
-      if (n0 >= p.N) break;                                 // warp-uniform
-      const int n = n0 + 4 * tcg;
-      const bool vec_ok = n + 3 < p.N && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0);
-      // the chunk's residual values first: 8 independent 16-byte loads per thread in flight under the TMEM load, the epilogue math and
-      // the turn through shared memory (inside the store loop below they were 8 SERIAL L2 / HBM round trips per chunk -- the compiler
-      // cannot hoist a load above the previous iteration's store to a possibly aliasing pointer: 30 % of all stall samples, call9)
-      float4 rv[8];
-      if (p.res && vec_ok) {
+      for (int ch = 0; ch < CPW / 32; ++ch) {
+        const int c0 = cgp * CPW + ch * 32;                  // first column of the chunk inside the tile
+        const int n0 = n_blk * BN + c0;
+        const bool chunk_ok = n0 < p.N;                      // warp-uniform
+        const int n = n0 + 4 * tcg;
+        const bool vec_ok = n + 3 < p.N && (p.ldo & 3) == 0 && (!p.res || (p.ldr & 3) == 0);
+        // the chunk's residual values first: 8 independent 16-byte loads per thread in flight under the TMEM load, the epilogue math
+        // and the turn through shared memory (inside the store loop they would be 8 SERIAL round trips: the compiler cannot hoist a
+        // load above the previous iteration's store to a possibly aliasing pointer)
+        float4 rv[8];
+        if (p.res && vec_ok && chunk_ok) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int m = m_blk * TBM + qd * 32 + 4 * it + tr;
+            const int mr = p.res_mod > 0 ? m % p.res_mod : m;
+            rv[it] = (m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)mr * p.ldr + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        if (ch == CPW / 32 - 1) {   // this warp's last TMEM read of the tile is complete: hand the accumulator stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(leader_tempty0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+          }
+        }
+        if (!chunk_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float v[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int nn = n0 + j + q4;
+            float x = __uint_as_float(r[j + q4]);
+            if (nn < p.N) {
+              if (ln) x = rstd * (x - mu * vcsum[c0 + j + q4]);
+              x = apply_act(x + vbias[c0 + j + q4], p.act);
+            }
+            v[q4] = x;
+          }
+          *reinterpret_cast<float4*>(turn + lane * T_TURN_LD + j) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncwarp();
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int m = m_blk * TBM + qd * 32 + 4 * it + tr;
+          const int rl = 4 * it + tr;
+          const int m = m_blk * TBM + qd * 32 + rl;
+          if (m >= p.M || n >= p.N) continue;
+          float4 x = *reinterpret_cast<const float4*>(turn + rl * T_TURN_LD + 4 * tcg);
+          const size_t o = (size_t)m * p.ldo + n;
           const int mr = p.res_mod > 0 ? m % p.res_mod : m;
-          rv[it] = (m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)mr * p.ldr + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ch * 32), r);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int n = n0 + j + e;
-          float x = __uint_as_float(r[j + e]);
-          if (n < p.N) {
-            if (ln) x = rstd * (x - mu * vcsum[ch * 32 + j + e]);
-            x = apply_act(x + vbias[ch * 32 + j + e], p.act);
-          }
-          v[e] = x;
-        }
-        *reinterpret_cast<float4*>(turn + lane * T_TURN_LD + j) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rl = 4 * it + tr;
-        const int m = m_blk * TBM + qd * 32 + rl;
-        if (m >= p.M || n >= p.N) continue;
-        float4 x = *reinterpret_cast<const float4*>(turn + rl * T_TURN_LD + 4 * tcg);
-        const size_t o = (size_t)m * p.ldo + n;
-        const int mr = p.res_mod > 0 ? m % p.res_mod : m;
-        if (vec_ok) {
-          if (p.res) { x.x += rv[it].x; x.y += rv[it].y; x.z += rv[it].z; x.w += rv[it].w; }
-          *reinterpret_cast<float4*>(p.out + o) = x;
-          if (p.out2) *reinterpret_cast<float4*>(p.out2 + o) = x;
-        } else {   // ragged N / unaligned rows: element by element
-          if (p.res) {
-            x.x += p.res[(size_t)mr * p.ldr + n];
-            if (n + 1 < p.N) x.y += p.res[(size_t)mr * p.ldr + n + 1];
-            if (n + 2 < p.N) x.z += p.res[(size_t)mr * p.ldr + n + 2];
-            if (n + 3 < p.N) x.w += p.res[(size_t)mr * p.ldr + n + 3];
-          }
-          p.out[o] = x.x;
-          if (n + 1 < p.N) p.out[o + 1] = x.y;
-          if (n + 2 < p.N) p.out[o + 2] = x.z;
-          if (n + 3 < p.N) p.out[o + 3] = x.w;
-          if (p.out2) {
-            p.out2[o] = x.x;
-            if (n + 1 < p.N) p.out2[o + 1] = x.y;
-            if (n + 2 < p.N) p.out2[o + 2] = x.z;
-            if (n + 3 < p.N) p.out2[o + 3] = x.w;
+          if (vec_ok) {
+            if (p.res) { x.x += rv[it].x; x.y += rv[it].y; x.z += rv[it].z; x.w += rv[it].w; }
+            *reinterpret_cast<float4*>(p.out + o) = x;
+            if (p.out2) *reinterpret_cast<float4*>(p.out2 + o) = x;
+          } else {   // ragged N / unaligned rows: element by element
+            if (p.res) {
+              x.x += p.res[(size_t)mr * p.ldr + n];
+              if (n + 1 < p.N) x.y += p.res[(size_t)mr * p.ldr + n + 1];
+              if (n + 2 < p.N) x.z += p.res[(size_t)mr * p.ldr + n + 2];
+              if (n + 3 < p.N) x.w += p.res[(size_t)mr * p.ldr + n + 3];
+            }
+            p.out[o] = x.x;
+            if (n + 1 < p.N) p.out[o + 1] = x.y;
+            if (n + 2 < p.N) p.out[o + 2] = x.z;
+            if (n + 3 < p.N) p.out[o + 3] = x.w;
+            if (p.out2) {
+              p.out2[o] = x.x;
+              if (n + 1 < p.N) p.out2[o + 1] = x.y;
+              if (n + 2 < p.N) p.out2[o + 2] = x.z;
+              if (n + 3 < p.N) p.out2[o + 3] = x.w;
+            }
           }
         }
+        __syncwarp();   // the staging rows are rewritten by the next chunk
       }
-      __syncwarp();   // the staging rows are rewritten by the next chunk
+      if (++acc == T_NUM_ACC) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -253,7 +286,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's smem / signal its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<CG, BN>(tmem_base);
+    tmem_dealloc<CG, C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -304,13 +337,15 @@ inline std::string& g_emu_error_tf32() { static std::string e; return e; }
 #endif
 
 template <int CG>
-inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params& p, int tiles, cudaStream_t st) {
+inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params& p, int tiles, int num_sms, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<CG>;
+  const int slots = num_sms / CG > 0 ? num_sms / CG : 1;          // persistent: one CTA (pair) per SM (pair) walks the tiles
+  const int units = tiles < slots ? tiles : slots;
 #ifdef DSHEG_EMU   // tests/emu: run the grid on the thread-level emulator (clusters of CG CTAs)
   (void)st;
   const CUtensorMap m0 = maps[0], m1 = maps[1], m2 = maps[2], m3 = maps[3], m4 = maps[4];
   static std::string emu_err;
-  if (!emu::run_grid(tiles * CG, T_NUM_THREADS, CG, TCfg<CG>::SMEM_BYTES, [=] { kern(m0, m1, m2, m3, m4, p); }, &emu_err)) {
+  if (!emu::run_grid(units * CG, T_NUM_THREADS, CG, TCfg<CG>::SMEM_BYTES, [=] { kern(m0, m1, m2, m3, m4, p); }, &emu_err)) {
     g_emu_error_tf32() = emu_err;
     return cudaErrorLaunchFailure;
   }
@@ -323,7 +358,7 @@ inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params&
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tiles * CG); cfg.blockDim = dim3(T_NUM_THREADS); cfg.dynamicSmemBytes = TCfg<CG>::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(units * CG); cfg.blockDim = dim3(T_NUM_THREADS); cfg.dynamicSmemBytes = TCfg<CG>::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   if (CG == 2) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -336,7 +371,7 @@ inline cudaError_t launch_tf32_variant(const CUtensorMap* maps, const T32Params&
 
 // A, W, residual, out: fp32 (the "tf32" mode keeps every activation in fp32); residual / out may be fp32 by type or by flag.
 // cg_force: 0 = automatic (CTA pairs for M >= 2048 and N >= 256), 1 / 2 = force
-inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::string* err, int cg_force = 0) {
+inline cudaError_t launch_gemm_tf32(const GemmDesc& d, int num_sms, cudaStream_t st, std::string* err, int cg_force = 0) {
   const int cg = cg_force ? cg_force : ((d.M >= 2048 && d.N >= 256) ? 2 : 1);
   const int bn = cg == 2 ? 256 : 128;
   T32Params p{};
@@ -358,10 +393,11 @@ inline cudaError_t launch_gemm_tf32(const GemmDesc& d, cudaStream_t st, std::str
   if (!make_tmap_f32(&maps[4], d.w, d.N, d.Kp, d.Kp, bn / cg, err)) return cudaErrorInvalidValue;
   p.tiles_n = (d.N + bn - 1) / bn;
   const int tiles_m = (d.M + TBM * cg - 1) / (TBM * cg);
+  p.tiles_m = tiles_m;
   p.bias = d.bias; p.csum = d.csum; p.mu = d.mu; p.rstd = d.rstd; p.act = d.act;
   p.res = reinterpret_cast<const float*>(d.res); p.ldr = d.ldr; p.res_mod = d.res_mod;
   p.out = reinterpret_cast<float*>(d.out); p.ldo = d.ldo; p.out2 = reinterpret_cast<float*>(d.out2);
-  return cg == 2 ? launch_tf32_variant<2>(maps, p, tiles_m * p.tiles_n, st) : launch_tf32_variant<1>(maps, p, tiles_m * p.tiles_n, st);
+  return cg == 2 ? launch_tf32_variant<2>(maps, p, tiles_m * p.tiles_n, num_sms, st) : launch_tf32_variant<1>(maps, p, tiles_m * p.tiles_n, num_sms, st);
 }
 
 }  // namespace t32

@@ -17,7 +17,7 @@ struct EmuGemmTf32Args {
   float* out;
   int32_t ldo;
   float* out2;
-  int32_t cg_force;
+  int32_t cg_force, num_sms;
 };
 
 static std::string g_err;
@@ -33,7 +33,7 @@ extern "C" int emu_gemm_tf32(const EmuGemmTf32Args* a) {
   d.out = a->out; d.ldo = a->ldo; d.out_f32 = 1; d.out2 = a->out2;
   if (!t32::tf32_eligible(d)) { g_err = "not eligible for the tf32 TMA path"; return 2; }
   std::string terr;
-  const cudaError_t e = t32::launch_gemm_tf32(d, nullptr, &terr, a->cg_force);
+  const cudaError_t e = t32::launch_gemm_tf32(d, a->num_sms, nullptr, &terr, a->cg_force);
   if (e != cudaSuccess) { g_err = terr + " " + t32::g_emu_error_tf32(); return 1; }
   g_err.clear();
   return 0;

@@ -320,7 +320,7 @@ class Tf32Args(ctypes.Structure):
                 ("w", ctypes.c_void_p), ("Kp", ctypes.c_int32),
                 ("bias", ctypes.c_void_p), ("csum", ctypes.c_void_p), ("mu", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
                 ("act", ctypes.c_int32), ("res", ctypes.c_void_p), ("ldr", ctypes.c_int32), ("res_mod", ctypes.c_int32),
-                ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("out2", ctypes.c_void_p), ("cg_force", ctypes.c_int32)]
+                ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("out2", ctypes.c_void_p), ("cg_force", ctypes.c_int32), ("num_sms", ctypes.c_int32)]
 
 
 def _to_tf32(t):
@@ -330,14 +330,14 @@ def _to_tf32(t):
     return u.view(torch.float32).double()
 
 
-def run_gemm_tf32(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, dup=False, cg=0, seed=0):
+def run_gemm_tf32(M, N, seg_ks, *, ln=False, act=ACT_NONE, res=None, dup=False, cg=0, seed=0, num_sms=2):
     g = torch.Generator().manual_seed(seed)
     rnd = lambda *s: torch.randn(*s, generator=g)
     Kp = sum(r64(k) for k in seg_ks)
     W = torch.zeros(N, Kp)
     keep, A_cat, off = [], [], 0
     a = Tf32Args()
-    a.M, a.N, a.nseg, a.Kp, a.cg_force, a.act = M, N, len(seg_ks), Kp, cg, act
+    a.M, a.N, a.nseg, a.Kp, a.cg_force, a.act, a.num_sms = M, N, len(seg_ks), Kp, cg, act, num_sms
     for i, k in enumerate(seg_ks):
         ld = r64(k) + 12                                   # a wider buffer: exercises the leading dimension (multiple of 4)
         seg = torch.full((M, ld), 7.0)                     # garbage beyond the segment width must never reach the product
@@ -415,4 +415,20 @@ def test_gemm_tf32_is_independent_of_the_thread_schedule(sched, monkeypatch):
     base, _ = run_gemm_tf32(260, 512, [512], cg=2, res="f32", seed=6)
     monkeypatch.setenv("EMU_SCHED", sched)
     got, _ = run_gemm_tf32(260, 512, [512], cg=2, res="f32", seed=6)
+    assert torch.equal(base, got)
+
+
+@pytest.mark.parametrize("env", [{"EMU_DELAY_TMEM_LD": "40"}, {"EMU_DELAY_MMA": "40"}, {"EMU_DELAY_TMA": "40"},
+                                 {"EMU_SCHED": "shuffle", "EMU_SCHED_SEED": "7", "EMU_DELAY_TMEM_LD": "15"}])
+@pytest.mark.parametrize("cg,num_sms", [(2, 2), (1, 1)])
+def test_gemm_tf32_persistent_pipeline_under_adversarial_timing(env, cg, num_sms, monkeypatch):
+    """The persistent form: ONE CTA (pair) walks 12 / 24 tiles, so ring slots and both accumulator stages wrap many times.  A slow
+    epilogue (late tcgen05.ld), a slow MMA issuer or late TMA arrivals must not change a bit: an accumulator stage overwritten before
+    its last read, a ring slot refilled under a pending MMA or per-column vectors restaged too early would."""
+    kw = dict(ln=True, act=ACT_GELU, cg=cg, num_sms=num_sms, seed=9)
+    base, want = run_gemm_tf32(390, 1024, [256], **kw)
+    assert float((base - want).abs().max() / want.abs().max()) < 2e-5
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, _ = run_gemm_tf32(390, 1024, [256], **kw)
     assert torch.equal(base, got)
