@@ -17,6 +17,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 PREC = {"fp32": 0, "bf16": 1, "tf32": 2}   # tf32: fp32 activations + tcgen05 kind::tf32 GEMMs
+COND_PROJECTION = {"mlp_includeX": 0, "linear_includeX": 1, "mlp_excludeX": 2, "linear_excludeX": 3}   # DSHEG_COND_*
+ABI_VERSION = 2
 
 
 def _sources():
@@ -53,7 +55,7 @@ class Config(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "abi_version", "dim_pose", "expression_dim", "audio_dim", "hubert_dim", "aud_latent_dim",
         "latent_dim", "num_layers", "num_heads", "ff_size", "style_dim", "classifier_free",
-        "precision", "max_batch", "max_frames")]
+        "precision", "max_batch", "max_frames", "cond_projection", "no_cond_residual")]
 
 
 _lib = None

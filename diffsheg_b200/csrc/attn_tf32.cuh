@@ -23,6 +23,33 @@ inline size_t smem_bytes(int T) {
   return (size_t)(Tp * LDQ + 2 * Tp * LDK + HD * LDK + 4 * HD) * sizeof(float);
 }
 
+#ifdef DSHEG_EMU
+// tests/emu models of the two PTX instructions (test infrastructure; the product build takes the #else branch):
+//   cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 mantissa bits kept
+//   mma.m16n8k8.row.col tf32 (g = lane / 4, q = lane % 4): A regs {(g, q), (g + 8, q), (g, q + 4), (g + 8, q + 4)},
+//   B regs {(k = q, n = g), (k = q + 4, n = g)}, C/D {(g, 2q), (g, 2q + 1), (g + 8, 2q), (g + 8, 2q + 1)}; fp32 accumulation
+inline float to_tf32(float x) {
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+  return __uint_as_float(u);
+}
+inline void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  struct Frag { uint32_t a[4], b[2]; } mine{{a[0], a[1], a[2], a[3]}, {b0, b1}};
+  const int lane = emu::self().lane, g = lane >> 2, q = lane & 3;
+  uint8_t(*slots)[64] = emu::warp_exchange(&mine, sizeof(Frag), "mma.sync tf32");
+  auto frag = [&](int l) { Frag f; memcpy(&f, slots[l], sizeof(Frag)); return f; };
+  for (int e = 0; e < 4; ++e) {
+    const int row = g + 8 * (e >> 1), n = 2 * q + (e & 1);
+    float acc = c[e];
+    for (int k = 0; k < 8; ++k) {
+      const Frag fa = frag(row % 8 * 4 + (k & 3)), fb = frag(n * 4 + (k & 3));
+      const float av = __uint_as_float(fa.a[(row >> 3) + 2 * (k >> 2)] & 0xffffe000u), bv = __uint_as_float(fb.b[k >> 2] & 0xffffe000u);
+      acc += av * bv;
+    }
+    c[e] = acc;
+  }
+}
+#else
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -33,12 +60,17 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+#endif
 
 // qkv: [n_samples * T, 3 D] fp32 (q | k | v), y32: [n_samples * T, D] fp32 scratch, z: [n_samples * T, D] fp32.
 __global__ void __launch_bounds__(NTHREADS) attn_tf32_kernel(const float* __restrict__ qkv, float* __restrict__ y32, float* __restrict__ z, int T, int D,
                                                              int H, int B, const float* __restrict__ g, const float* __restrict__ b,
                                                              const float* __restrict__ ss, int ss_ld) {
+#ifdef DSHEG_EMU
+  float* sm = reinterpret_cast<float*>(emu::self().cta->smem);
+#else
   extern __shared__ float sm[];
+#endif
   const int Tp = (T + 15) / 16 * 16;          // frames padded to whole m-tiles (rows T .. Tp-1 are zero)
   float* Qs = sm;                              // [Tp][LDQ]
   float* Ks = Qs + Tp * LDQ;                   // [Tp][LDK]

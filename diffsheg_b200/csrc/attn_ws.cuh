@@ -514,6 +514,24 @@ inline cudaError_t launch_cross_attn_ws(const bf16* q, const bf16* kv, bf16* z, 
     return cudaErrorInvalidValue;
   return launch_attn_ws_qkv(mq, mkv, 0, D, z, n_samples, T, Tkv, ssB, ln_g, ln_b, ss, ss_ld, num_sms, st);
 }
+#elif defined(DSHEG_EMU_RUNTIME)
+// tests/emu whole-engine build: the same self-attention launch on the emulated 3-D tensor maps (emu_tc_prims.h)
+inline cudaError_t launch_attn_ws(const bf16* qkv, bf16* z, int n_samples, int T, int ssB, const float* ln_g, const float* ln_b,
+                                  const float* ss, int ss_ld, int num_sms, cudaStream_t st, std::string* err, int rev = 0) {
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15)) { *err = "attention operand not 16-byte aligned"; return cudaErrorInvalidValue; }
+  auto frames_map = [&](int box_frames) {
+    CUtensorMap m;
+    m.base = qkv; m.cols = (uint64_t)(3 * D); m.rows = (uint64_t)T; m.ld_bytes = (uint64_t)(3 * D) * 2;
+    m.box_cols = HD; m.box_rows = (uint32_t)box_frames; m.swizzle_bytes = 128;
+    m.n2 = (uint64_t)n_samples; m.ld2_bytes = (uint64_t)T * (3 * D) * 2;
+    return m;
+  };
+  const int n_mt = (T + 15) >> 4, mh = (n_mt + 1) >> 1;
+  const CUtensorMap mq = frames_map(16 * mh), mkv = frames_map(16 * n_mt);
+  const int grid = n_samples < num_sms ? n_samples : num_sms;
+  DSHEG_LAUNCH(attn_ws_kernel, grid, NTHREADS, SMEM_BYTES, st, mq, mkv, D, 2 * D, z, n_samples, T, T, ssB, ln_g, ln_b, ss, ss_ld, rev);
+  return cudaGetLastError();
+}
 #endif  // DSHEG_EMU
 
 }  // namespace aws

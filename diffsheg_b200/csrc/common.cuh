@@ -2,6 +2,9 @@
 #pragma once
 #ifdef DSHEG_EMU
 #include "emu_cuda.h"   // tests/emu: host emulation of the CUDA subset the SIMT kernels use (test infrastructure only)
+#ifdef DSHEG_EMU_RUNTIME
+#include "emu_runtime.h"   // ... and of the runtime API the engine's host code uses (whole-engine emulation)
+#endif
 #else
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -46,9 +49,18 @@ inline cudaError_t pdl_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t
 }  // namespace dsheg
 #define DSHEG_LAUNCH(kern, grid, block, smem, st, ...) dsheg::pdl_launch(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
 #define DSHEG_PDL_ATTRS 1
+#elif defined(DSHEG_EMU) && defined(DSHEG_EMU_RUNTIME)   // tests/emu/emu_engine.cpp: every launch runs on the thread-level emulator
+#define DSHEG_LAUNCH(kern, grid, block, smem, st, ...) emu_rt::launch(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#define DSHEG_PDL_ATTRS 0
 #else
 #define DSHEG_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
 #define DSHEG_PDL_ATTRS 0
+#endif
+// DSHEG_LAUNCH_PLAIN: always the classic stream-ordered launch (kernels that do not execute DSHEG_PDL_WAIT)
+#if defined(DSHEG_EMU) && defined(DSHEG_EMU_RUNTIME)
+#define DSHEG_LAUNCH_PLAIN(kern, grid, block, smem, st, ...) emu_rt::launch(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#else
+#define DSHEG_LAUNCH_PLAIN(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
 #endif
 
 namespace dsheg {

@@ -1,7 +1,9 @@
 // diffsheg_b200 engine: handle, packed weights, workspace and the per-step launch graph of the
 // UniDiffuser denoiser (reference models/transformer.py:728-770) behind the C ABI of
 // include/diffsheg_b200.h.  All device work is enqueued on the caller's stream; no host syncs.
+#ifndef DSHEG_EMU   // tests/emu/emu_engine.cpp compiles this file for the host emulator (emu_runtime.h stands in for the runtime API)
 #include <cuda_runtime.h>
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,6 +62,7 @@ struct LinW {
 };
 struct LayerW {
   LinW feat1, feat2, qkv, sa_out, ffn1, ffn2, ffn_out;
+  LinW featl;                          // linear_* cond_projection: the single Linear that replaces feat1 / feat2 (tr:281-282)
   const float* nullc = nullptr;
   const float* qkv_eshift = nullptr;   // optional: static softmax shifts of the Q | K columns (pack.py:expo_shift), [2 D]
   const float *sa_g = nullptr, *sa_b = nullptr, *ffn_g = nullptr, *ffn_b = nullptr;
@@ -83,6 +86,13 @@ struct dsheg_handle {
   std::string err;
   std::unordered_map<std::string, DevTensor> tensors;
   bool finalized = false;
+  // opt.cond_projection / opt.cond_residual (tr:262-263,281-289,302-338), resolved once in dsheg_create:
+  //   include_x     feat_proj consumes cat(x, conditioning) (else the conditioning only)
+  //   mlp_proj      LayerNorm -> Linear -> SiLU -> Linear (else one Linear)
+  //   feat_residual feat_proj's result is ADDED to the layer input (cond_residual, and always for *_excludeX; tr:302,337);
+  //                 the same condition doubles the input of the xf = None audio layer (tr:337-338)
+  //   variant       anything but the shipped mlp_includeX + cond_residual: takes the generic (unfused-statistics) layer path
+  bool include_x = true, mlp_proj = true, feat_residual = true, variant = false;
   int gemm_engine = 1;  // 1 = tcgen05 (bf16 mode default), 0 = SIMT
   // bf16 mode attention: 2 = persistent warp-specialised TMA kernel on the ACT_EXPO numerators (attn_ws.cuh; default), falling back per
   // layer to 1 = attn_v3 (in-kernel softmaxes) when the packer found no provably safe static shifts (DSHEG_ATTN=v3 forces it),
@@ -226,8 +236,12 @@ struct Resolver {
     LayerW L;
     L.has_feat = featKp > 0;
     if (L.has_feat) {
-      L.feat1 = lin(p + ".feat1", 2 * D, featKp, true);
-      L.feat2 = lin(p + ".feat2", D, 2 * D, false);
+      if (h->mlp_proj) {
+        L.feat1 = lin(p + ".feat1", 2 * D, featKp, true);
+        L.feat2 = lin(p + ".feat2", D, 2 * D, false);
+      } else {
+        L.featl = lin(p + ".featl", D, featKp, false);
+      }
       if (has_null) L.nullc = f32(p + ".nullc", {D});
     }
     L.qkv = lin(p + ".qkv", 3 * D, round_up(D, 64), true);
@@ -280,6 +294,71 @@ struct Runner {
 
   static Seg seg(const void* p, int ld, int k) { Seg s; s.ptr = p; s.ld = ld; s.k = k; return s; }
 
+  // feat_prep launch (row statistics of the virtual concat for the cond rows + null-row constant for the CFG-null rows; kernels.cuh)
+  int feat_prep(TA* hin, int ld_hin, int D, int n_uncond, int rows, const float* nullc, const Seg* extra, int n_extra) {
+    const int warps_per_block = 8;
+    Seg e3[3] = {seg(nullptr, 0, 0), seg(nullptr, 0, 0), seg(nullptr, 0, 0)};
+    for (int i = 0; i < n_extra; ++i) e3[i] = extra[i];
+    double fb = (double)n_uncond * D * 2 + (double)(rows - n_uncond) * D;
+    for (int i = 0; i < n_extra; ++i) fb += (double)(rows - n_uncond) * extra[i].k;
+    prof_begin(h, st, PROF_ROW, fb * sizeof(TA));
+    if (std::is_same<TA, bf16>::value)
+      DSHEG_LAUNCH(feat_prep_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st,
+          (bf16*)hin, ld_hin, D, n_uncond, rows, nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
+    else
+      DSHEG_LAUNCH_PLAIN(feat_prep_kernel<TA>, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st,
+          hin, ld_hin, D, n_uncond, rows, nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
+    prof_end(h, st);
+    LAUNCH_CHECK("feat_prep");
+    return 0;
+  }
+
+  // K7 for every cond_projection / cond_residual combination other than the shipped one (tr:300-338), on the
+  // kernels of the shipped path:
+  //   CFG-null rows   their whole feat_proj input is the learned null row (tr:326-332), so feat_proj(null) is the packed per-layer
+  //                   constant `nullc`: h = nullc + (feat_residual ? h : 0) -- the rows are zeroed first when nothing is added back
+  //   mlp_*           LayerNorm statistics over the virtual concat (feat_prep with D = 0 leaves x out for *_excludeX), folded into
+  //                   the first Linear; SiLU; second Linear (+ residual), in place
+  //   linear_includeX one Linear over cat(x, cond): its A operand contains the rows it would overwrite, so the result is staged
+  //                   in F1 and copied back
+  //   linear_excludeX one Linear over the conditioning, residual always, in place
+  int feat_proj_variant(const LayerW& L, TA* hin, int ld_hin, int rows, int n_uncond, int D, const Seg* extra, int n_extra) {
+    const int n_cond = rows - n_uncond;
+    TA* hc = hin + (size_t)n_uncond * ld_hin;
+    const bool incl = h->include_x, resid = h->feat_residual;
+    if (n_uncond > 0 && !resid) CK(cudaMemset2DAsync(hin, (size_t)ld_hin * sizeof(TA), 0, (size_t)D * sizeof(TA), n_uncond, st));
+    if (h->mlp_proj && incl) {
+      if (feat_prep(hin, ld_hin, D, n_uncond, rows, L.nullc, extra, n_extra)) return 1;
+    } else {
+      if (n_uncond > 0 && feat_prep(hin, ld_hin, D, n_uncond, n_uncond, L.nullc, nullptr, 0)) return 1;   // CFG-null rows only
+      if (h->mlp_proj && feat_prep(hin, ld_hin, 0, n_uncond, rows, nullptr, extra, n_extra)) return 1;     // statistics without x
+    }
+    GemmDesc g1;
+    int ns = 0;
+    if (incl) g1.a[ns++] = seg(hc, ld_hin, D);
+    for (int i = 0; i < n_extra; ++i) g1.a[ns++] = extra[i];
+    g1.nseg = ns; g1.M = n_cond;
+    if (h->mlp_proj) {
+      g1.csum = L.feat1.csum; g1.mu = h->MU; g1.rstd = h->RSTD; g1.act = ACT_SILU;
+      g1.out = h->F1; g1.ldo = 2 * D;
+      if (gemm(g1, L.feat1, "feat1")) return 1;
+      GemmDesc g2;
+      g2.a[0] = seg(h->F1, 2 * D, 2 * D); g2.nseg = 1; g2.M = n_cond;
+      if (resid) { g2.res = hc; g2.ldr = ld_hin; }
+      g2.out = hc; g2.ldo = ld_hin;
+      return gemm(g2, L.feat2, "feat2");
+    }
+    if (incl) {
+      if (resid) { g1.res = hc; g1.ldr = ld_hin; }
+      g1.out = h->F1; g1.ldo = D;
+      if (gemm(g1, L.featl, "feat_lin")) return 1;
+      CK(cudaMemcpy2DAsync(hc, (size_t)ld_hin * sizeof(TA), h->F1, (size_t)D * sizeof(TA), (size_t)D * sizeof(TA), n_cond, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
+    g1.res = hc; g1.ldr = ld_hin; g1.out = hc; g1.ldo = ld_hin;
+    return gemm(g1, L.featl, "feat_lin");
+  }
+
   // One LinearTemporalDiffusionTransformerLayer (tr:300-346) on `rows` hidden rows of width D.
   //   hin/hout: residual stream in / out (may alias);  n_uncond: leading CFG-null rows
   //   stats_in:   the LayerNorm partials PS of hin are valid (written by the previous layer's ffn_out epilogue,
@@ -311,6 +390,8 @@ struct Runner {
       g2.res = hc; g2.ldr = ld_hin; g2.out = hc; g2.ldo = ld_hin;
       g2.ps_out = h->PS + (size_t)n_uncond * slots;  // refreshed partials of the cond rows for the QKV LayerNorm
       if (gemm(g2, L.feat2, "feat2")) return 1;
+    } else if (L.has_feat && h->variant) {
+      if (feat_proj_variant(L, hin, ld_hin, rows, n_uncond, D, extra, n_extra)) return 1;
     } else if (L.has_feat) {
       // K7: LayerNorm(P) stats over the virtual concat + null-row constant for the uncond half
       const int n_cond = rows - n_uncond;
@@ -325,7 +406,7 @@ struct Runner {
         DSHEG_LAUNCH(feat_prep_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, 
             (bf16*)hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
       else
-        feat_prep_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+        DSHEG_LAUNCH_PLAIN(feat_prep_kernel<TA>, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st,
             hin, ld_hin, D, n_uncond, rows, L.nullc, e3[0], e3[1], e3[2], n_extra, h->MU, h->RSTD);
       prof_end(h, st);
       LAUNCH_CHECK("feat_prep");
@@ -351,7 +432,7 @@ struct Runner {
     if (std::is_same<TA, bf16>::value)
       DSHEG_LAUNCH(rowstats_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, (const bf16*)hcur, ldc, D, rows, h->MU2, h->RSTD2);
     else
-      rowstats_kernel<TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(hcur, ldc, D, rows, h->MU2, h->RSTD2);
+      DSHEG_LAUNCH_PLAIN(rowstats_kernel<TA>, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, (const TA*)hcur, ldc, D, rows, h->MU2, h->RSTD2);
     prof_end(h, st);
     LAUNCH_CHECK("rowstats");
     gq.mu = h->MU2; gq.rstd = h->RSTD2;
@@ -380,18 +461,20 @@ struct Runner {
       DSHEG_LAUNCH(av3::attn_v3_kernel, n_samples, av3::NTHREADS, av3::SMEM_BYTES, st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB, L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, float>::value && HD == 64 && h->cfg.precision == DSHEG_PREC_TF32 && h->gemm_engine == 1) {
       // tf32 mode: the two products of a head on mma.sync TF32, softmaxes / sums / LayerNorm exact fp32 (attn_tf32.cuh)
-      at32::attn_tf32_kernel<<<n_samples, at32::NTHREADS, at32::smem_bytes(T), st>>>((const float*)h->QKV, h->Y32, (float*)h->Z, T, D, H, ssB,
-                                                                                       L.sa_g, L.sa_b, ss, ss_ld);
+      DSHEG_LAUNCH_PLAIN(at32::attn_tf32_kernel, n_samples, at32::NTHREADS, at32::smem_bytes(T), st, (const float*)h->QKV, h->Y32, (float*)h->Z, T, D, H, ssB,
+                         L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 64) {
-      attn_kernel<TA, 64><<<n_samples, 256, attn_smem_bytes<64>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
-                                                                          L.sa_g, L.sa_b, ss, ss_ld);
+      const auto k64 = attn_kernel<TA, 64>;
+      DSHEG_LAUNCH_PLAIN(k64, n_samples, 256, attn_smem_bytes<64>(T), st, (const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
+                         L.sa_g, L.sa_b, ss, ss_ld);
     } else if (std::is_same<TA, bf16>::value && HD == 16 && D == asmall::D && H == asmall::NH && T <= asmall::TP && h->attn_aud) {
       // the audio encoder's attention with all 8 heads processed at once (attn_small.cuh; DSHEG_ATTN_AUD=0: generic kernel below)
       DSHEG_LAUNCH(asmall::attn_d128_kernel, n_samples, asmall::NTHREADS, asmall::smem_bytes(T), st, (const bf16*)h->QKV, (bf16*)h->Z, T, ssB,
                    L.sa_g, L.sa_b, ss, ss_ld);
     } else if (HD == 16) {
-      attn_kernel<TA, 16><<<n_samples, 256, attn_smem_bytes<16>(T), st>>>((const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
-                                                                          L.sa_g, L.sa_b, ss, ss_ld);
+      const auto k16 = attn_kernel<TA, 16>;
+      DSHEG_LAUNCH_PLAIN(k16, n_samples, 256, attn_smem_bytes<16>(T), st, (const TA*)h->QKV, h->Y32, (TA*)h->Z, T, D, H, ssB,
+                         L.sa_g, L.sa_b, ss, ss_ld);
     } else {
       return fail(h, "unsupported head dim");
     }
@@ -425,8 +508,11 @@ struct Runner {
       DSHEG_LAUNCH(ln_mod_silu_bf16_kernel, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st, 
           (const bf16*)h->Y, D, (bf16*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
     else
-      ln_mod_silu_kernel<TA, TA><<<(rows + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+    {
+      const auto klms = ln_mod_silu_kernel<TA, TA>;
+      DSHEG_LAUNCH_PLAIN(klms, (rows + warps_per_block - 1) / warps_per_block, 256, 0, st,
           (const TA*)h->Y, D, (TA*)h->Z, D, D, rows, T, ssB, L.ffn_g, L.ffn_b, ss + 2 * D, ss_ld);
+    }
     prof_end(h, st);
     LAUNCH_CHECK("ln_mod_silu");
     }
@@ -443,18 +529,18 @@ struct Runner {
     const int R1 = B * T, E = 4 * c.latent_dim, A = c.audio_dim;
     {
       const size_t n = (size_t)R1 * A;
-      mel_stage_kernel<TA><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mel, A, (TA*)h->AUD256, 2 * A, (TA*)h->A0, R1);
+      DSHEG_LAUNCH_PLAIN(mel_stage_kernel<TA>, (unsigned)((n + 255) / 256), 256, 0, st, mel, A, (TA*)h->AUD256, 2 * A, (TA*)h->A0, R1);
       LAUNCH_CHECK("mel_stage");
     }
     const int tiles = (T + HC_TR - 1) / HC_TR;
     for (int n = 0; n < 2; ++n) {
       const NetW& nw = h->net[n];
       // K4: hubert_encoder (BN folded into conv 0)
-      hubconv_kernel<float><<<B * tiles, HC_CO, (HC_TR + 2) * c.hubert_dim * sizeof(float), st>>>(
+      DSHEG_LAUNCH_PLAIN(hubconv_kernel<float>, B * tiles, HC_CO, (HC_TR + 2) * c.hubert_dim * sizeof(float), st,
           hubert, c.hubert_dim, nw.hub_w0, nw.hub_b0, ACT_GELU, h->MID, HC_CO, T, tiles);
       LAUNCH_CHECK("hubconv0");
-      hubconv_kernel<TA><<<B * tiles, HC_CO, (HC_TR + 2) * HC_CO * sizeof(float), st>>>(
-          h->MID, HC_CO, nw.hub_w3, nullptr, ACT_NONE, (TA*)h->HUB[n], HC_CO, T, tiles);
+      DSHEG_LAUNCH_PLAIN(hubconv_kernel<TA>, B * tiles, HC_CO, (HC_TR + 2) * HC_CO * sizeof(float), st,
+          (const float*)h->MID, HC_CO, nw.hub_w3, (const float*)nullptr, ACT_NONE, (TA*)h->HUB[n], HC_CO, T, tiles);
       LAUNCH_CHECK("hubconv3");
       // K2: pid_embed MLP (fp32 SIMT GEMMs, once per window)
       GemmDesc p0;
@@ -509,8 +595,14 @@ struct Runner {
       if (gemm(g, h->net[n].ss, "ss")) return 1;
     }
     // ---- K5: encoder_aud (D=128, 8 heads of 16) on 2*mel, result into AUD256[:, A:2A]
-    if (layer(h->aud, (TA*)h->A0, A, (TA*)h->A1, (TA*)h->AUD256 + A, 2 * A, R1, 0, A, F, c.num_heads, nullptr, 0, h->SSA, 4 * A, 1, T))
+    //      (2 * mel: the layer adds its input back although xf is None, tr:337-338; without cond_residual -- and with a projection
+    //      that includes x -- nothing is added and the layer reads mel itself, columns [0, A) of AUD256)
+    if (h->feat_residual) {
+      if (layer(h->aud, (TA*)h->A0, A, (TA*)h->A1, (TA*)h->AUD256 + A, 2 * A, R1, 0, A, F, c.num_heads, nullptr, 0, h->SSA, 4 * A, 1, T))
+        return 1;
+    } else if (layer(h->aud, (TA*)h->AUD256, 2 * A, (TA*)h->A1, (TA*)h->AUD256 + A, 2 * A, R1, 0, A, F, c.num_heads, nullptr, 0, h->SSA, 4 * A, 1, T)) {
       return 1;
+    }
     // ---- the two MotionTransformers, expression first (tr:741-763)
     for (int n = 0; n < 2; ++n) {
       const NetW& nw = h->net[n];
@@ -534,7 +626,7 @@ struct Runner {
       extra[n_extra++] = seg(h->XF, c.aud_latent_dim, c.aud_latent_dim);
       extra[n_extra++] = seg(h->HUB[n], HC_CO, HC_CO);
       if (n == 1) extra[n_extra++] = seg(h->EXPR, h->ldE, c.expression_dim);  // tr:506-507,533-535
-      const bool fused = std::is_same<TA, bf16>::value && h->gemm_engine == 1 && h->fuse_stats && D == 512;
+      const bool fused = std::is_same<TA, bf16>::value && h->gemm_engine == 1 && h->fuse_stats && D == 512 && !h->variant;
       if (fused) {
         DSHEG_LAUNCH(cond_stats_bf16_kernel, (R1 + 7) / 8, 256, 0, st, extra[0], extra[1], n_extra > 2 ? extra[2] : extra[0], n_extra, R1, h->CS);
         LAUNCH_CHECK("cond_stats");
@@ -582,7 +674,15 @@ const char* dsheg_last_error(const dsheg_handle* h) { return h ? h->err.c_str() 
 
 int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return 1; }
-  if (cfg->abi_version != DSHEG_ABI_VERSION) { g_create_error = "ABI version mismatch"; return 1; }
+  if (cfg->abi_version != DSHEG_ABI_VERSION && cfg->abi_version != 1) { g_create_error = "ABI version mismatch"; return 1; }
+  dsheg_config cfg_v{};   // a version-1 caller passes the 15-field struct: the version-2 fields keep their zero defaults
+  memcpy(&cfg_v, cfg, cfg->abi_version == 1 ? offsetof(dsheg_config, cond_projection) : sizeof(dsheg_config));
+  cfg = &cfg_v;
+  if (cfg->cond_projection < DSHEG_COND_MLP_INCLUDEX || cfg->cond_projection > DSHEG_COND_LINEAR_EXCLUDEX ||
+      (cfg->no_cond_residual != 0 && cfg->no_cond_residual != 1)) {
+    g_create_error = "unsupported cond_projection / no_cond_residual (DSHEG_COND_* of include/diffsheg_b200.h; 0 or 1)";
+    return 1;
+  }
   if (cfg->latent_dim % 64 || cfg->audio_dim % 64 || cfg->latent_dim / cfg->num_heads != 64 ||
       cfg->audio_dim / cfg->num_heads != 16 || cfg->latent_dim > 32 * LMS_MAXV || cfg->ff_size % 64 ||
       cfg->aud_latent_dim != 2 * cfg->audio_dim || cfg->max_batch < 1 || cfg->max_frames < 2) {
@@ -602,6 +702,10 @@ int dsheg_create(const dsheg_config* cfg, int device, dsheg_handle** out) {
   }
   dsheg_handle* h = new dsheg_handle();
   h->cfg = *cfg;
+  h->include_x = cfg->cond_projection == DSHEG_COND_MLP_INCLUDEX || cfg->cond_projection == DSHEG_COND_LINEAR_INCLUDEX;
+  h->mlp_proj = cfg->cond_projection == DSHEG_COND_MLP_INCLUDEX || cfg->cond_projection == DSHEG_COND_MLP_EXCLUDEX;
+  h->feat_residual = !cfg->no_cond_residual || !h->include_x;
+  h->variant = !(h->include_x && h->mlp_proj && h->feat_residual);
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->gemm_engine = 1;
@@ -744,7 +848,7 @@ int dsheg_finalize_weights(dsheg_handle* h) {
     nw.joint = r.lin(p + ".joint", D, round_up(nw.feats, 64), false);
     nw.audproj = r.lin(p + ".audproj", c.aud_latent_dim, 2 * A, false);
     nw.out = r.lin(p + ".out", nw.feats, D, false);
-    const int featKp = D + c.aud_latent_dim + HC_CO + (n == 1 ? round_up(c.expression_dim, 64) : 0);
+    const int featKp = (h->include_x ? D : 0) + c.aud_latent_dim + HC_CO + (n == 1 ? round_up(c.expression_dim, 64) : 0);
     nw.layers.clear();
     for (int l = 0; l < L; ++l) nw.layers.push_back(r.layer(p + ".l" + std::to_string(l), D, F, featKp, c.classifier_free != 0));
   }
@@ -807,6 +911,9 @@ int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, floa
 }
 
 int64_t dsheg_launch_count(const dsheg_handle* h) { return h ? h->launches : 0; }
+
+#ifndef DSHEG_EMU   // the whole-engine emulator build (tests/emu/emu_engine.cpp) ends here: profiling, the stateless step kernels and
+                    // the op-level / bench entry points have their own emulator coverage (tests/emu/emu_kernels.cpp, emu_gemm*.cpp)
 
 int dsheg_profile_begin(dsheg_handle* h) {
   if (!h) return 1;
@@ -1184,5 +1291,6 @@ int dsheg_op_cross_attention_bf16(const void* q, const void* kv, const float* ln
   if (le != cudaSuccess) { g_create_error = std::string("op_cross_attention_bf16: ") + (terr.empty() ? cudaGetErrorString(le) : terr.c_str()); return 1; }
   return step_done("dsheg_op_cross_attention_bf16");
 }
+#endif  // DSHEG_EMU
 
 }  // extern "C"

@@ -13,8 +13,13 @@ constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
 
 template <typename TA, typename TW>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
+#ifdef DSHEG_EMU   // tests/emu: the two static tiles live in the emulated CTA's shared-memory window (launch_gemm_simt passes their size)
+  float (*As)[SG_BM + 4] = reinterpret_cast<float (*)[SG_BM + 4]>(emu::self().cta->smem);
+  float (*Ws)[SG_BN + 4] = reinterpret_cast<float (*)[SG_BN + 4]>(emu::self().cta->smem + sizeof(float) * SG_BK * (SG_BM + 4));
+#else
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Ws[SG_BK][SG_BN + 4];
+#endif
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
@@ -89,7 +94,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
 template <typename TA, typename TW>
 inline cudaError_t launch_gemm_simt(const GemmDesc& d, cudaStream_t st) {
   dim3 grid((d.N + SG_BN - 1) / SG_BN, (d.M + SG_BM - 1) / SG_BM);
-  gemm_simt_kernel<TA, TW><<<grid, 256, 0, st>>>(d);
+  const auto kern = gemm_simt_kernel<TA, TW>;
+#ifdef DSHEG_EMU
+  DSHEG_LAUNCH_PLAIN(kern, grid, 256, sizeof(float) * SG_BK * (SG_BM + 4 + SG_BN + 4), st, d);
+#else
+  DSHEG_LAUNCH_PLAIN(kern, grid, 256, 0, st, d);
+#endif
   return cudaGetLastError();
 }
 

@@ -376,7 +376,11 @@ __global__ void __launch_bounds__(256) ln_mod_silu_sample_bf16_kernel(const bf16
       for (int e = 0; e < 16; ++e) {
         const float hh = 0.5f * fmaf(fmaf(v[e], rstd, nmr), G[e], Bc[e]);
         float th;
+#ifdef DSHEG_EMU
+        th = tanhf(hh);
+#else
         asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+#endif
         o[e] = fmaf(hh, th, hh);
       }
       bf16* zr = z + (row0 + (rr == 0 ? t : t2)) * D;
@@ -397,7 +401,11 @@ __global__ void __launch_bounds__(256) ln_mod_silu_sample_bf16_kernel(const bf16
 template <typename TA, int HD>
 __global__ void __launch_bounds__(256) attn_kernel(const TA* qkv, float* y32, TA* z, int T, int D, int H, int B,
                                                    const float* g, const float* b, const float* ss, int ss_ld) {
+#ifdef DSHEG_EMU
+  float* sm = reinterpret_cast<float*>(emu::self().cta->smem);
+#else
   extern __shared__ float sm[];
+#endif
   constexpr int LD = HD + 1;
   constexpr int NPART = 256 / HD;
   float* Qs = sm;
@@ -587,7 +595,11 @@ constexpr int HC_TR = 8, HC_CO = 128;
 template <typename TOUT>
 __global__ void __launch_bounds__(HC_CO) hubconv_kernel(const float* in, int Cin, const float* w, const float* bias,
                                                         int act, TOUT* out, int ldo, int T, int tiles_per_sample) {
+#ifdef DSHEG_EMU
+  float* xs = reinterpret_cast<float*>(emu::self().cta->smem);
+#else
   extern __shared__ float xs[];  // [(HC_TR+2)][Cin]
+#endif
   const int smp = blockIdx.x / tiles_per_sample, t0 = (blockIdx.x % tiles_per_sample) * HC_TR;
   const int co = threadIdx.x;
   for (int e = threadIdx.x; e < (HC_TR + 2) * Cin; e += HC_CO) {

@@ -17,8 +17,7 @@ from .pack import pack_state_dict
 _CFG_KEYS = ("dim_pose", "expression_dim", "audio_dim", "hubert_dim", "aud_latent_dim", "latent_dim",
              "num_layers", "num_heads", "ff_size", "style_dim")
 
-_SUPPORTED = dict(unidiffuser=True, model_base="transformer_encoder", cond_projection="mlp_includeX",
-                  cond_residual=True, addHubert=True, encode_hubert=True, expAddHubert=False,
+_SUPPORTED = dict(unidiffuser=True, model_base="transformer_encoder", addHubert=True, encode_hubert=True, expAddHubert=False,
                   addWav2Vec2=False, addTextCond=False, addEmoCond=False, no_style=False, ExprID_off=False,
                   ExprID_off_uncond=False, fix_head_var=False, separate=None)
 
@@ -31,16 +30,29 @@ def cfg_from_opt(opt, **over):
             raise NotImplementedError(f"diffsheg_b200 supports only opt.{k}={v!r} (got {getattr(opt, k)!r})")
     if getattr(opt, "model_mean_type", "epsilon") != "epsilon":
         raise NotImplementedError("only epsilon prediction is supported")
+    cond_projection = getattr(opt, "cond_projection", "mlp_includeX")
+    if cond_projection not in _lib.COND_PROJECTION:   # 'none': the reference's own layers raise for it (tr:323-324)
+        raise NotImplementedError(f"diffsheg_b200 supports opt.cond_projection in {sorted(_lib.COND_PROJECTION)} (got {cond_projection!r})")
     cfg = dict(dim_pose=opt.dim_pose, expression_dim=opt.expression_dim,
                audio_dim=getattr(opt, "audio_dim", 128), hubert_dim=1024,
                aud_latent_dim=getattr(opt, "audio_latent_dim", 256), latent_dim=getattr(opt, "latent_dim", 512),
                num_layers=getattr(opt, "num_layers", 8), num_heads=8, ff_size=1024,
                style_dim=getattr(opt, "style_dim", 4), hubert_enc_dim=128,
                classifier_free=bool(getattr(opt, "classifier_free", False)),
-               cond_scale=float(getattr(opt, "cond_scale", 1.0)), n_poses=getattr(opt, "n_poses", 88))
+               cond_scale=float(getattr(opt, "cond_scale", 1.0)), n_poses=getattr(opt, "n_poses", 88),
+               cond_projection=cond_projection, cond_residual=bool(getattr(opt, "cond_residual", True)))
     cfg.update(over)
     cfg["net_dim_pose"] = cfg["dim_pose"] + cfg["expression_dim"]
     return cfg
+
+
+def engine_config(cfg, precision, max_batch, max_frames):
+    """The ``dsheg_config`` struct of include/diffsheg_b200.h for a configuration dict (``synth.make_cfg`` / ``cfg_from_opt``)."""
+    return _lib.Config(abi_version=_lib.ABI_VERSION, classifier_free=int(bool(cfg["classifier_free"])),
+                       precision=_lib.PREC[precision], max_batch=int(max_batch), max_frames=int(max_frames),
+                       cond_projection=_lib.COND_PROJECTION[cfg.get("cond_projection", "mlp_includeX")],
+                       no_cond_residual=int(not cfg.get("cond_residual", True)),
+                       **{k: int(cfg[k]) for k in _CFG_KEYS})
 
 
 def _ptr(t):
@@ -67,9 +79,7 @@ class FusedUniDiffuser:
         self.max_frames = int(max_frames or cfg["n_poses"])
         self.cond_scale = float(cfg.get("cond_scale", 1.0))
         L = _lib.lib()
-        c = _lib.Config(abi_version=1, classifier_free=int(bool(cfg["classifier_free"])),
-                        precision=_lib.PREC[precision], max_batch=self.max_batch, max_frames=self.max_frames,
-                        **{k: int(cfg[k]) for k in _CFG_KEYS})
+        c = engine_config(cfg, precision, self.max_batch, self.max_frames)
         h = ctypes.c_void_p()
         _lib.check(L.dsheg_create(ctypes.byref(c), self.device.index, ctypes.byref(h)), None, "dsheg_create")
         self._h = h

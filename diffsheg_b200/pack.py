@@ -16,6 +16,9 @@ exact up to floating-point reassociation:
 * ``*.hub``: BatchNorm1d (eval) folded into the first Conv1d of hubert_encoder (tr:436-442).
 * K axes of GEMM weights are laid out per A-segment, each padded to a multiple of 64
   (h | audio_proj | hubert | expr for feat1).
+* ``cfg['cond_projection']`` (tr:262-263,281-289,304-324; default ``mlp_includeX``): the ``*_excludeX`` projections drop the ``h``
+  segment; the ``linear_*`` ones have a single Linear, packed as ``*.featl`` (no LayerNorm, so no csum), and their ``*.nullc`` is
+  ``W null + b``.
 
 Packed names (n in aud/exp/ges, i = layer): see ``pack_state_dict``; shapes are validated by
 ``dsheg_finalize_weights``.
@@ -121,7 +124,13 @@ class Packer:
 
     def layer(self, name, key, seg_widths, null_row):
         g = self.g
-        if seg_widths:
+        if seg_widths and self.cfg.get("cond_projection", "mlp_includeX").startswith("linear"):
+            W, b = g(key + ".feat_proj.weight"), g(key + ".feat_proj.bias")   # tr:281-282: one Linear(pre_proj_dim, latent_dim)
+            self.put_w(name + ".featl.w", W, seg_widths)
+            self.put_f32(name + ".featl.b", b)
+            if null_row is not None:
+                self.put_f32(name + ".nullc", W @ null_row + b)
+        elif seg_widths:
             fp = key + ".feat_proj"
             gam, bet = g(fp + ".0.weight"), g(fp + ".0.bias")
             W1, b1 = g(fp + ".1.weight"), g(fp + ".1.bias")
@@ -188,7 +197,8 @@ class Packer:
             self.lin(name + ".joint", key + ".joint_embed")
             self.lin(name + ".audproj", key + ".audio_proj")
             self.lin(name + ".out", key + ".out")
-            widths = [D, cfg["aud_latent_dim"], cfg["hubert_enc_dim"]] + ([extra] if extra else [])
+            include_x = cfg.get("cond_projection", "mlp_includeX").endswith("includeX")   # tr:262-263: *_excludeX projects the conditioning only
+            widths = ([D] if include_x else []) + [cfg["aud_latent_dim"], cfg["hubert_enc_dim"]] + ([extra] if extra else [])
             null = g(key + ".null_cond_emb")[0] if cfg["classifier_free"] else None
             for i, b in enumerate(blocks):
                 self.layer(f"{name}.l{i}", b, widths, null)

@@ -57,8 +57,12 @@ def state_dict_shapes(cfg):
         ln(prefix + ".norm", d)
         lin(prefix + ".out_layers.2", d, d)
 
+    cond_projection = cfg.get("cond_projection", "mlp_includeX")
+
     def layer(prefix, d, pre_proj):
-        if pre_proj:
+        if pre_proj and cond_projection.startswith("linear"):   # tr:281-282
+            lin(prefix + ".feat_proj", d, pre_proj)
+        elif pre_proj:
             ln(prefix + ".feat_proj.0", pre_proj)
             lin(prefix + ".feat_proj.1", 2 * d, pre_proj)
             lin(prefix + ".feat_proj.3", d, 2 * d)
@@ -75,7 +79,7 @@ def state_dict_shapes(cfg):
     layer("encoder_aud", A, 0)
     for net, feats, extra in (("encoder_exp", cfg["expression_dim"], 0),
                               ("encoder_ges", cfg["dim_pose"], cfg["expression_dim"])):
-        P = D + AL + extra + HE
+        P = (D if cond_projection.endswith("includeX") else 0) + AL + extra + HE   # tr:260-276
         if cfg["classifier_free"]:
             shapes[net + ".null_cond_emb"] = (1, P)
         shapes[net + ".PE.pe"] = (1, 1200, D)

@@ -21,13 +21,20 @@
 extern "C" {
 #endif
 
-#define DSHEG_ABI_VERSION 1
+/* Version 2 appends cond_projection / no_cond_residual to dsheg_config; a version-1 caller (abi_version = 1, the 15-field struct)
+ * is still accepted and gets the shipped defaults. */
+#define DSHEG_ABI_VERSION 2
 
 /* FP32: strict parity mode (SIMT fp32 GEMMs).  BF16: performance mode (tcgen05 bf16 GEMMs, bf16 activations).
  * TF32: fp32 activations / residual stream / statistics / epilogues with tcgen05 kind::tf32 GEMMs (operands rounded to
  *       TF32 by the TMA load, fp32 accumulation) -- the precise-and-fast middle mode. */
 enum { DSHEG_PREC_FP32 = 0, DSHEG_PREC_BF16 = 1, DSHEG_PREC_TF32 = 2 };
 enum { DSHEG_DTYPE_F32 = 0, DSHEG_DTYPE_BF16 = 1 };
+/* opt.cond_projection (options/base_options.py:21; models/transformer.py:262-263,281-289,304-324): what feat_proj of every
+ * MotionTransformer layer consumes and computes.  *_INCLUDEX: cat(x, audio, hubert[, expression]); *_EXCLUDEX: the conditioning
+ * only (the input is then always added back, transformer.py:302,337).  MLP: LayerNorm -> Linear -> SiLU -> Linear; LINEAR: one
+ * Linear.  'none' is not offered: the reference's own layers raise NotImplementedError for it (transformer.py:323-324). */
+enum { DSHEG_COND_MLP_INCLUDEX = 0, DSHEG_COND_LINEAR_INCLUDEX = 1, DSHEG_COND_MLP_EXCLUDEX = 2, DSHEG_COND_LINEAR_EXCLUDEX = 3 };
 
 /* Frozen subset of the reference `opt` Namespace + build_models() arguments
  * (runner.py:32-45, runner.py:124-222, options/base_options.py:16-128). */
@@ -47,6 +54,10 @@ typedef struct dsheg_config {
   int32_t precision;       /* DSHEG_PREC_* : arithmetic of the per-step GEMMs/activations */
   int32_t max_batch;       /* workspace is sized for max_batch x max_frames (x2 under CFG) */
   int32_t max_frames;
+  /* ---- ABI version 2 (zero = the shipped configuration) ---- */
+  int32_t cond_projection;  /* DSHEG_COND_*; 0 = mlp_includeX (the default of options/base_options.py:21) */
+  int32_t no_cond_residual; /* 1 = opt.cond_residual False: feat_proj's result replaces x instead of being added to it
+                               (transformer.py:302,337; ignored by the *_EXCLUDEX projections, which always add) */
 } dsheg_config;
 
 typedef struct dsheg_handle dsheg_handle;

@@ -5,14 +5,18 @@ layout) and plain tensors; dtype/device follow the inputs, so
 same code gives the fp32 CPU baseline, an fp64 "truth" run and (on a GPU box) an
 eager torch-cuda run of the reference op stream.
 
-Only the shipped configuration is restated (SURVEY 8b "supported set"):
-unidiffuser=True, model_base=transformer_encoder, cond_projection=mlp_includeX,
-cond_residual=True, addHubert=encode_hubert=True, PE=pe_sinu, eps prediction.
+Restated: unidiffuser=True, model_base=transformer_encoder, addHubert=encode_hubert=True,
+PE=pe_sinu, eps prediction, with every cond_projection the reference's UniDiffuser can
+run (mlp_includeX -- the shipped one --, linear_includeX, mlp_excludeX, linear_excludeX;
+tr:262-263,281-289,302-338) and cond_residual on or off.  'none' builds
+(tr:641-650) but raises NotImplementedError in every MotionTransformer layer (tr:323-324).
 """
 import math
 
 import torch
 import torch.nn.functional as F
+
+COND_PROJECTIONS = ("mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX")
 
 
 def timestep_embedding(timesteps, dim, max_period=10000):
@@ -87,22 +91,33 @@ def ffn(p, x, emb):
     return x + stylization(p.sub("proj_out."), y, emb)
 
 
-def transformer_layer(p, x, xf, emb, add_cond, null_cond_emb, num_head, cfg_double):
-    """LinearTemporalDiffusionTransformerLayer.forward tr:300-346 for
-    cond_projection=mlp_includeX, cond_residual=True, eval mode."""
+def transformer_layer(p, x, xf, emb, add_cond, null_cond_emb, num_head, cfg_double,
+                      cond_projection="mlp_includeX", cond_residual=True):
+    """LinearTemporalDiffusionTransformerLayer.forward tr:300-346, eval mode.
+
+    cond_projection (tr:304-324): *_includeX projects cat(x, xf, add_cond), *_excludeX projects cat(xf, add_cond) only;
+    mlp_* = LayerNorm -> Linear -> SiLU -> Linear, linear_* = one Linear (tr:281-289).
+    The input is added back when cond_residual is set OR the projection excludes x (tr:302-303,337-338)."""
+    assert cond_projection in COND_PROJECTIONS, cond_projection
+    residual = cond_residual or cond_projection.endswith("excludeX")
     x_ori = x
     if xf is not None:
-        x = torch.cat((x, xf), -1) if add_cond is None else torch.cat((x, xf, add_cond), -1)
+        parts = ([x] if cond_projection.endswith("includeX") else []) + [xf] + ([] if add_cond is None else [add_cond])
+        x = torch.cat(parts, -1)
         if cfg_double:
-            # tr:330-332: rows [0, B'/2) take the learned null row for the WHOLE concat.
+            # tr:330-332: rows [0, B'/2) take the learned null row for the WHOLE feat_proj input.
             n = x.shape[0]
             mask = (torch.linspace(0, 1, n) < 0.5).to(x.device)
             null = null_cond_emb.repeat(x.shape[1], 1).unsqueeze(0)
             x = torch.where(mask.unsqueeze(1).unsqueeze(2), null, x)
-        fp = p.sub("feat_proj.")
-        x = _layer_norm(fp, "0", x)
-        x = _linear(fp, "3", F.silu(_linear(fp, "1", x)))
-    x = x + x_ori  # cond_residual; NB with xf=None (encoder_aud) this doubles x (tr:337-338)
+        if cond_projection.startswith("mlp"):
+            fp = p.sub("feat_proj.")
+            x = _layer_norm(fp, "0", x)
+            x = _linear(fp, "3", F.silu(_linear(fp, "1", x)))
+        else:
+            x = _linear(p, "feat_proj", x)
+    if residual:
+        x = x + x_ori  # NB with xf=None (encoder_aud) this doubles x (tr:337-338)
     x = linear_self_attention(p.sub("sa_block."), x, emb, num_head)
     return ffn(p.sub("ffn."), x, emb)
 
@@ -119,7 +134,8 @@ def hubert_encoder(p, feat):
 
 
 def motion_transformer(p, x, timesteps, audio_emb, person_id, hubert, exp_cond,
-                       num_layers, num_head, latent_dim, cond_scale, classifier_free):
+                       num_layers, num_head, latent_dim, cond_scale, classifier_free,
+                       cond_projection="mlp_includeX", cond_residual=True):
     """MotionTransformer.forward tr:496-587.
 
     audio_emb: [B,T,256] (mel | audio_feat); hubert: raw [B,T,1024];
@@ -145,7 +161,7 @@ def motion_transformer(p, x, timesteps, audio_emb, person_id, hubert, exp_cond,
     null = p("null_cond_emb") if classifier_free else None
     for i in range(num_layers):
         h = transformer_layer(p.sub(f"temporal_decoder_blocks.{i}."), h, xf, emb, add_cond,
-                              null, num_head, cfg_double)
+                              null, num_head, cfg_double, cond_projection, cond_residual)
     out = _linear(p, "out", h).view(B, T, -1)
     if cfg_double:  # tr:585-586
         half = out.shape[0] // 2
@@ -162,8 +178,10 @@ def unidiffuser_forward(sd, cfg, x, timesteps, sqrt_alphas, audio_emb, person_id
     sqrt_recipm1_alphas_cumprod_t) broadcastable to the expression block (gd:527-532),
     audio_emb = mel [B,T,128], person_id [B,style_dim], hubert [B,T,1024].
     cfg: dict with dim_pose, expression_dim, num_layers, num_heads, latent_dim,
-    classifier_free, cond_scale.
+    classifier_free, cond_scale and optionally cond_projection / cond_residual
+    (defaults: the shipped mlp_includeX / True).
     """
+    cp, cr = cfg.get("cond_projection", "mlp_includeX"), bool(cfg.get("cond_residual", True))
     device = x.device
     p = _SD(sd, "", dtype, device)
     x = x.to(dtype)
@@ -172,13 +190,13 @@ def unidiffuser_forward(sd, cfg, x, timesteps, sqrt_alphas, audio_emb, person_id
     L, H, D = cfg["num_layers"], cfg["num_heads"], cfg["latent_dim"]
     temb = timestep_embedding(timesteps, D).to(dtype)
     emb = _linear(p, "time_embed.2", F.silu(_linear(p, "time_embed.0", temb)))
-    audio_feat = transformer_layer(p.sub("encoder_aud."), audio_emb, None, emb, None, None, H, False)
+    audio_feat = transformer_layer(p.sub("encoder_aud."), audio_emb, None, emb, None, None, H, False, cp, cr)
     audio_emb = torch.cat((audio_emb, audio_feat), dim=-1)
     gesture, expression = torch.split(x, [cfg["dim_pose"], cfg["expression_dim"]], dim=-1)
     exp_noise = motion_transformer(p.sub("encoder_exp."), expression, timesteps, audio_emb, person_id,
-                                   hubert, None, L, H, D, cfg["cond_scale"], cfg["classifier_free"])
+                                   hubert, None, L, H, D, cfg["cond_scale"], cfg["classifier_free"], cp, cr)
     a, b = sqrt_alphas
     expr_cond = a * expression - b * exp_noise  # tr:717-725, tr:749
     ges_noise = motion_transformer(p.sub("encoder_ges."), gesture, timesteps, audio_emb, person_id,
-                                   hubert, expr_cond, L, H, D, cfg["cond_scale"], cfg["classifier_free"])
+                                   hubert, expr_cond, L, H, D, cfg["cond_scale"], cfg["classifier_free"], cp, cr)
     return torch.cat((ges_noise, exp_noise), dim=-1)

@@ -67,3 +67,70 @@ def gemm_tf32_lib():
     L = _load("emu_gemm_tf32")
     L.emu_gemm_tf32_last_error.restype = ctypes.c_char_p
     return L
+
+
+def engine_lib():
+    """The WHOLE engine (diffsheg_b200/csrc/engine.cu and every kernel it launches) on the emulator: the library exports the C ABI of
+    include/diffsheg_b200.h itself; "device" pointers are host pointers (emu_runtime.h)."""
+    from diffsheg_b200 import _lib as product
+    L = _load("emu_engine", ("DSHEG_EMU_RUNTIME",))
+    for name in ("dsheg_last_error", "dsheg_create", "dsheg_destroy", "dsheg_load_tensor", "dsheg_finalize_weights",
+                 "dsheg_prepare_window", "dsheg_denoise", "dsheg_launch_count"):
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = product.SIGNATURES[name]
+    L.emu_engine_last_launch_error.restype = ctypes.c_char_p
+    return L
+
+
+class EmuEngine:
+    """FusedUniDiffuser's create / load / finalize / prepare_window / denoise sequence (diffsheg_b200/engine.py) against the emulated
+    engine, with CPU tensors.  The packer (diffsheg_b200/pack.py) is the product's own."""
+
+    def __init__(self, state_dict, cfg, precision="fp32", max_batch=1, max_frames=None, sms=8):
+        import torch
+        from diffsheg_b200 import _lib as product
+        from diffsheg_b200.engine import engine_config
+        from diffsheg_b200.pack import pack_state_dict
+        self.torch, self.cfg = torch, dict(cfg)
+        self.L = L = engine_lib()
+        L.emu_engine_set_sms(int(sms))
+        self.max_frames = int(max_frames or cfg["n_poses"])
+        c = engine_config(cfg, precision, int(max_batch), self.max_frames)
+        h = ctypes.c_void_p()
+        self._check(L.dsheg_create(ctypes.byref(c), 0, ctypes.byref(h)), None, "dsheg_create")
+        self.h = h
+        self._packed = pack_state_dict(state_dict, self.cfg, precision, self.max_frames)
+        for name, (t, dt) in self._packed.items():
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            self._check(L.dsheg_load_tensor(h, name.encode(), ctypes.c_void_p(t.data_ptr()), dt, shape, t.dim()), h, name)
+        self._check(L.dsheg_finalize_weights(h), h, "dsheg_finalize_weights")
+        self._keep = None
+
+    def _check(self, rc, h, what):
+        if rc != 0:
+            msg = self.L.dsheg_last_error(h)
+            raise RuntimeError(f"emulated engine: {what} failed: {msg.decode() if msg else ''} "
+                               f"[{self.L.emu_engine_last_launch_error().decode()}]")
+
+    def prepare_window(self, mel, hubert, person_id):
+        f = lambda t: t.to(self.torch.float32).contiguous()   # noqa: E731
+        mel, hubert, person_id = f(mel), f(hubert), f(person_id)
+        self._keep = (mel, hubert, person_id)
+        self.B, self.T = mel.shape[0], mel.shape[1]
+        self._check(self.L.dsheg_prepare_window(self.h, mel.data_ptr(), hubert.data_ptr(), person_id.data_ptr(), self.B, self.T, None),
+                    self.h, "dsheg_prepare_window")
+
+    def denoise(self, x, t_orig, a, b, cond_scale=None):
+        x = x.to(self.torch.float32).contiguous()
+        out = self.torch.empty_like(x)
+        s = float(self.cfg.get("cond_scale", 1.0)) if cond_scale is None else float(cond_scale)
+        self._check(self.L.dsheg_denoise(self.h, x.data_ptr(), int(t_orig), float(a), float(b), s, out.data_ptr(), None), self.h, "dsheg_denoise")
+        return out
+
+    def launch_count(self):
+        return int(self.L.dsheg_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.dsheg_destroy(self.h)
+            self.h = None

@@ -8,7 +8,26 @@
 // (fp32 with bf16 roundings where the kernel rounds).  What it cannot check: memory-model / async-proxy ordering, bank
 // conflicts, performance.  Nothing here is linked into libdiffsheg_b200.so.
 #pragma once
+#if !defined(__x86_64__) || defined(EMU_USE_UCONTEXT)
 #include <ucontext.h>
+#define EMU_UCONTEXT 1
+#else
+#define EMU_UCONTEXT 0
+// Fiber switch without the two rt_sigprocmask system calls of glibc's swapcontext (a third of the emulator's run time): push the
+// callee-saved registers, swap stack pointers, pop, return.  The fibers never touch the signal mask or the FP control words.
+extern "C" void emu_ctx_switch(void** save_sp, void* load_sp);
+asm(".text\n"
+    ".hidden emu_ctx_switch\n"
+    ".globl emu_ctx_switch\n"
+    ".type emu_ctx_switch,@function\n"
+    "emu_ctx_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size emu_ctx_switch, .-emu_ctx_switch\n");
+#endif
 
 #include <cmath>
 #include <cstdint>
@@ -114,7 +133,11 @@ struct Cluster {
   uint64_t arrive_gen_seen = 0;
 };
 struct Thread {
+#if EMU_UCONTEXT
   ucontext_t ctx;
+#else
+  void* sp = nullptr;
+#endif
   std::vector<uint8_t> stack;
   Cta* cta = nullptr;
   uint3 tid{0, 0, 0};
@@ -130,7 +153,11 @@ struct Launch {
 };
 
 struct Runtime {
+#if EMU_UCONTEXT
   ucontext_t sched;
+#else
+  void* sched_sp = nullptr;
+#endif
   Thread* cur = nullptr;
   Launch launch;
   uint64_t progress = 0;
@@ -139,7 +166,11 @@ struct Runtime {
 };
 inline Runtime& rt() { static Runtime r; return r; }
 inline Thread& self() { return *rt().cur; }
+#if EMU_UCONTEXT
 inline void yield() { Thread* t = rt().cur; swapcontext(&t->ctx, &rt().sched); }
+#else
+inline void yield() { Thread* t = rt().cur; emu_ctx_switch(&t->sp, rt().sched_sp); }
+#endif
 
 inline void rendezvous(Rendezvous& r, int expected, const char* what) {
   if (r.arrived == 0) r.expected = expected;
@@ -175,19 +206,22 @@ inline void trampoline() {
 }
 
 // Run `body` (a call of the kernel with its arguments) for every thread of a grid; clusters execute one after another.
+// A 2-D grid (grid_y > 1; clusters of one CTA only) is walked x-fastest: blockIdx = {i % grid_x, i / grid_x, 0}.
 inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, size_t smem_bytes, std::function<void()> body,
-                     std::string* err) {
+                     std::string* err, uint32_t grid_y = 1) {
   Runtime& R = rt();
   R.body = body;
   R.error.clear();
-  R.launch.grid = {grid_x, 1, 1};
+  R.launch.grid = {grid_x, grid_y, 1};
   R.launch.block = {block_x, 1, 1};
   R.launch.cluster_size = cluster_size;
   if (grid_x % cluster_size || block_x % 32) { *err = "grid / block not a multiple of the cluster size / warp size"; return false; }
+  if (grid_y > 1 && cluster_size != 1) { *err = "2-D grids are emulated for clusters of one CTA only"; return false; }
+  const uint32_t grid_total = grid_x * grid_y;
   const size_t nthr = (size_t)cluster_size * block_x;
   std::vector<std::unique_ptr<Thread>> threads(nthr);
   for (auto& t : threads) { t.reset(new Thread); t->stack.resize(192 * 1024); }
-  for (uint32_t c0 = 0; c0 < grid_x; c0 += cluster_size) {
+  for (uint32_t c0 = 0; c0 < grid_total; c0 += cluster_size) {
     Cluster cl;
     cl.ctas.resize(cluster_size);
     for (uint32_t r = 0; r < cluster_size; ++r) {
@@ -196,7 +230,7 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
       c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(c.smem_store.data()) + 1023) & ~(uintptr_t)1023);
       c.smem_bytes = smem_bytes;
       c.nthreads = (int)block_x;
-      c.bid = {c0 + r, 0, 0};
+      c.bid = {(c0 + r) % grid_x, (c0 + r) / grid_x, 0};
       c.rank = r;
       c.cluster = &cl;
       c.warps.resize(block_x / 32);
@@ -209,11 +243,22 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
         t.parity = 0;
         t.cluster_wait_gen = 0;
         t.done = false;
+#if EMU_UCONTEXT
         getcontext(&t.ctx);
         t.ctx.uc_stack.ss_sp = t.stack.data();
         t.ctx.uc_stack.ss_size = t.stack.size();
         t.ctx.uc_link = &R.sched;
         makecontext(&t.ctx, (void (*)())trampoline, 0);
+#else
+        {   // initial frame: six zeroed callee-saved registers, the entry point as the return address, then a null return slot at an
+            // address = 8 mod 16 (what a function sees right after being called); trampoline() never returns
+          uintptr_t top = (reinterpret_cast<uintptr_t>(t.stack.data()) + t.stack.size()) & ~(uintptr_t)15;
+          void** frame = reinterpret_cast<void**>(top - 64);
+          for (int q = 0; q < 8; ++q) frame[q] = nullptr;
+          frame[6] = reinterpret_cast<void*>(&trampoline);
+          t.sp = frame;
+        }
+#endif
       }
     }
     // Scheduling order of a pass.  Any order is a legal execution (threads only rendezvous at synchronising operations), so code
@@ -248,7 +293,11 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
         if (tp->done) continue;
         if (sched_mode == 2 && sit_out[order[oi] / 32]) { skipped = true; ++remaining; continue; }
         R.cur = tp.get();
+#if EMU_UCONTEXT
         swapcontext(&R.sched, &tp->ctx);
+#else
+        emu_ctx_switch(&R.sched_sp, tp->sp);
+#endif
         if (!tp->done) ++remaining;
       }
       if (skipped && R.progress == before) continue;   // nobody who ran made progress, but some warps sat out: not a deadlock

@@ -1,0 +1,103 @@
+"""The WHOLE engine on the CPU: diffsheg_b200/csrc/engine.cu -- handle, packed-weight resolution, workspace carving, the launch
+sequence of Runner::prepare_window / Runner::denoise and every kernel it launches (SIMT, mma.sync, tcgen05 / TMA / TMEM) -- compiled
+for the thread-level emulator (tests/emu/emu_engine.cpp + emu_runtime.h) and driven through the C ABI of include/diffsheg_b200.h with
+the product's own packer, against the fp64 oracle.
+
+What this pins without a GPU: the host-side orchestration (pointers, leading dimensions, CFG row split, segment order of the virtual
+concat, which epilogue family each GEMM takes, the packed-tensor contract between pack.py and dsheg_finalize_weights) for the shipped
+configuration in all three precision modes, and for every cond_projection / cond_residual combination of the reference
+(models/transformer.py:262-263,281-289,300-338).  What it cannot pin: memory-model ordering and performance -- the
+-m gpu tests (tests/test_gpu_parity.py, tests/test_gpu_variants.py) and compute-sanitizer runs on hardware do that.
+Sizes are tiny (B <= 2, T <= 20, 1-2 layers per net): a launch costs the emulator ~0.1 s.
+"""
+import pytest
+import torch
+
+import emu
+from diffsheg_b200 import synth
+from oracle.denoiser import COND_PROJECTIONS, unidiffuser_forward
+
+# relmax against the fp64 oracle, one denoiser call; gates ~ 3x the measured emulator values (they match the hardware figures of the
+# same modes: tests/test_gpu_parity.py)
+TOL = {"fp32": 5e-6, "tf32": 2e-3, "bf16": 2.5e-2}
+A_RECIP, B_RECIPM1, T_ORIG = 1.8, 1.5, 480
+
+
+def _run(name, precision, B, T, **over):
+    cfg = synth.make_cfg(name, **over)
+    sd = synth.make_state_dict(cfg, seed=1)
+    inp = synth.make_inputs(cfg, B, T, seed=2)
+    eng = emu.EmuEngine(sd, cfg, precision=precision, max_batch=B, max_frames=T)
+    try:
+        eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+        got = eng.denoise(inp["x_T"], T_ORIG, A_RECIP, B_RECIPM1)
+        launches = eng.launch_count()
+    finally:
+        eng.close()
+    ts = torch.full((B,), T_ORIG, dtype=torch.long)
+    with torch.no_grad():
+        want = unidiffuser_forward(sd, cfg, inp["x_T"], ts, (torch.tensor(A_RECIP), torch.tensor(B_RECIPM1)), inp["mel"],
+                                   inp["person_id"], inp["hubert"], dtype=torch.float64)
+    assert torch.isfinite(got).all()
+    return float((got.double() - want).abs().max() / want.abs().max()), launches
+
+
+@pytest.mark.parametrize("name,precision,B,T", [("show", "fp32", 1, 8), ("beat", "fp32", 2, 5), ("show", "bf16", 1, 8),
+                                                ("beat", "bf16", 2, 20), ("show", "tf32", 1, 8)])
+def test_shipped_configuration_on_the_emulated_engine(name, precision, B, T):
+    """mlp_includeX + cond_residual (the configuration every benchmark runs): CFG pair (show) and single pass (beat); the bf16 runs
+    take the fused-statistics layer path, ACT_EXPO + attn_ws, tcgen05 GEMMs; tf32 the kind::tf32 GEMMs + TF32 mma.sync attention."""
+    err, launches = _run(name, precision, B, T, num_layers=2 if precision == "bf16" else 1)
+    assert err < TOL[precision], (name, precision, err)
+    assert launches > 40
+
+
+_VARIANTS = [(cp, cr) for cp in COND_PROJECTIONS for cr in (True, False) if not (cp == "mlp_includeX" and cr)]
+
+
+@pytest.mark.parametrize("cond_projection,cond_residual", _VARIANTS)
+def test_cond_projection_variants_fp32_cfg(cond_projection, cond_residual):
+    """Every other cond_projection / cond_residual combination under classifier-free guidance (the CFG-null rows take the packed
+    feat_proj(null_cond_emb) constant, tr:326-338), strict-fp32 engine."""
+    err, _ = _run("show", "fp32", 1, 6, num_layers=1, cond_projection=cond_projection, cond_residual=cond_residual)
+    assert err < TOL["fp32"], (cond_projection, cond_residual, err)
+
+
+@pytest.mark.parametrize("cond_projection,cond_residual,name,precision", [
+    ("linear_includeX", False, "show", "bf16"), ("mlp_excludeX", True, "show", "bf16"), ("linear_excludeX", True, "beat", "bf16"),
+    ("mlp_includeX", False, "beat", "bf16"), ("linear_includeX", True, "beat", "tf32"), ("mlp_excludeX", False, "show", "tf32")])
+def test_cond_projection_variants_tensor_core_modes(cond_projection, cond_residual, name, precision):
+    """The variants on the tcgen05 engines (bf16: multi-segment TMA operands without the hidden-state segment, the no-LayerNorm
+    multi-segment GEMM, staging + copy-back of linear_includeX; two layers so that the second layer consumes the first one's output)."""
+    err, _ = _run(name, precision, 2, 12, num_layers=2 if precision == "bf16" else 1, cond_projection=cond_projection,
+                  cond_residual=cond_residual)
+    assert err < TOL[precision], (cond_projection, cond_residual, name, precision, err)
+
+
+def test_abi_version_1_struct_is_still_accepted_and_unknown_projection_is_rejected():
+    """dsheg_create (include/diffsheg_b200.h): a version-1 caller passes the 15-field struct and gets the shipped defaults; values
+    outside DSHEG_COND_* fail with a message instead of being misread."""
+    import ctypes
+
+    from diffsheg_b200 import _lib
+    from diffsheg_b200.engine import engine_config
+    L = emu.engine_lib()
+    cfg = synth.make_cfg("beat", num_layers=1)
+    c = engine_config(cfg, "fp32", 1, 4)
+    c.abi_version, c.cond_projection, c.no_cond_residual = 1, 99, 99     # garbage beyond the version-1 prefix must be ignored
+    h = ctypes.c_void_p()
+    assert L.dsheg_create(ctypes.byref(c), 0, ctypes.byref(h)) == 0
+    L.dsheg_destroy(h)
+    c.abi_version = _lib.ABI_VERSION
+    assert L.dsheg_create(ctypes.byref(c), 0, ctypes.byref(h)) != 0
+    assert b"cond_projection" in L.dsheg_last_error(None)
+    c.cond_projection, c.no_cond_residual = _lib.COND_PROJECTION["linear_excludeX"], 1
+    assert L.dsheg_create(ctypes.byref(c), 0, ctypes.byref(h)) == 0
+    # the packed contract follows the projection: the shipped feat1 / feat2 tensors are not what a linear_* engine resolves
+    for name, (t, dt) in __import__("diffsheg_b200.pack", fromlist=["pack_state_dict"]).pack_state_dict(
+            synth.make_state_dict(cfg, seed=1), cfg, "fp32", 4).items():
+        shape = (ctypes.c_int64 * t.dim())(*t.shape)
+        assert L.dsheg_load_tensor(h, name.encode(), ctypes.c_void_p(t.data_ptr()), dt, shape, t.dim()) == 0
+    assert L.dsheg_finalize_weights(h) != 0
+    assert b"featl" in L.dsheg_last_error(h)
+    L.dsheg_destroy(h)
