@@ -7,7 +7,7 @@ What this pins without a GPU: the host-side orchestration (pointers, leading dim
 concat, which epilogue family each GEMM takes, the packed-tensor contract between pack.py and dsheg_finalize_weights) for the shipped
 configuration in all three precision modes, and for every cond_projection / cond_residual combination of the reference
 (models/transformer.py:262-263,281-289,300-338).  What it cannot pin: memory-model ordering and performance -- the
--m gpu tests (tests/test_gpu_parity.py, tests/test_gpu_variants.py) and compute-sanitizer runs on hardware do that.
+-m gpu tests (tests/test_gpu_parity.py, tests/test_variants_gpu.py) and compute-sanitizer runs on hardware do that.
 Sizes are tiny (B <= 2, T <= 20, 1-2 layers per net): a launch costs the emulator ~0.1 s.
 """
 import pytest

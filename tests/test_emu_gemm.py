@@ -203,6 +203,15 @@ CASES = [
     dict(M=300, N=512, ks=[1024], cg=2, num_sms=2, res="bf16", stats_out=True, n_uncond=100),   # feat2: 5 stages, wide boxes
     dict(M=270, N=1024, ks=[512, 128, 128, 103], cg=2, num_sms=4, ln=True, act=ACT_SILU),        # feat1: virtual concat, 999 -> 1024
     dict(M=256, N=256, ks=[768], cg=2, num_sms=2, dup=True),
+    # the feat_proj GEMMs of the other cond_projection variants (engine.cu: feat_proj_variant; tr:262-263,281-289): operand lists
+    # without the 512-wide hidden-state segment, the no-LayerNorm multi-segment Linear with and without the bf16 residual
+    dict(M=270, N=1024, ks=[256, 128, 103], cg=2, num_sms=4, ln=True, act=ACT_SILU),    # mlp_excludeX feat1, gesture net: K = 512 class pairs
+    dict(M=300, N=1024, ks=[256, 128], cg=1, num_sms=3, ln=True, act=ACT_SILU),         # mlp_excludeX feat1, expression net: K = 384, single CTAs
+    dict(M=300, N=512, ks=[512, 256, 128, 103], cg=2, num_sms=2, res="bf16"),           # linear_includeX + cond_residual, gesture net (long K, wide boxes)
+    dict(M=300, N=512, ks=[512, 256, 128], cg=2, num_sms=2),                            # linear_includeX without residual, expression net (narrow boxes)
+    dict(M=300, N=512, ks=[256, 128, 103], cg=2, num_sms=2, res="bf16"),                # linear_excludeX, gesture net (in place in the engine)
+    dict(M=200, N=512, ks=[256, 128], cg=1, num_sms=2, res="bf16"),                     # linear_excludeX, expression net
+    dict(M=40, N=512, ks=[256, 128], cg=1, bn=128, num_sms=8, res="bf16"),              # ... in the single-clip regime (128-wide tiles)
 ]
 
 

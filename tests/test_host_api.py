@@ -22,12 +22,35 @@ def test_cfg_from_opt_accepts_the_shipped_configs_and_rejects_the_rest():
         for k in ("dim_pose", "expression_dim", "style_dim", "classifier_free", "cond_scale", "net_dim_pose"):
             assert cfg[k] == cfg0[k], k
     opt = synth.make_opt(synth.make_cfg("show"))
-    for field, bad in (("model_base", "transformer_decoder"), ("cond_projection", "linear_includeX"), ("unidiffuser", False),
+    for field, bad in (("model_base", "transformer_decoder"), ("cond_projection", "none"), ("unidiffuser", False),
                        ("encode_hubert", False), ("model_mean_type", "start_x")):
         o = argparse.Namespace(**vars(opt))
         setattr(o, field, bad)
         with pytest.raises(NotImplementedError):
             cfg_from_opt(o)
+
+
+def test_cfg_from_opt_carries_the_cond_projection_variants_into_the_engine_config():
+    """options/base_options.py:21,95: every projection the reference's UniDiffuser can run, cond_residual on or off."""
+    from diffsheg_b200 import _lib
+    from diffsheg_b200.engine import engine_config
+    opt = synth.make_opt(synth.make_cfg("show"))
+    c = engine_config(cfg_from_opt(opt), "bf16", 4, 88)     # an opt without the two fields = the shipped configuration
+    assert (c.abi_version, c.cond_projection, c.no_cond_residual) == (_lib.ABI_VERSION, 0, 0)
+    for code, cp in enumerate(("mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX")):
+        for cr in (True, False):
+            o = argparse.Namespace(**vars(opt), cond_projection=cp, cond_residual=cr)
+            cfg = cfg_from_opt(o)
+            assert (cfg["cond_projection"], cfg["cond_residual"]) == (cp, cr)
+            c = engine_config(cfg, "fp32", 1, 8)
+            assert (c.cond_projection, c.no_cond_residual) == (code, int(not cr))
+            # the synthetic state_dict follows the projection: P = [512 +] 256 + 128 [+ expression_dim] (tr:260-276)
+            shapes = synth.state_dict_shapes(dict(synth.make_cfg("show"), cond_projection=cp))
+            P = (512 if cp.endswith("includeX") else 0) + 256 + 128
+            assert shapes["encoder_exp.null_cond_emb"] == (1, P)
+            assert shapes["encoder_ges.null_cond_emb"] == (1, P + 103)
+            key = "encoder_exp.temporal_decoder_blocks.0.feat_proj" + (".weight" if cp.startswith("linear") else ".1.weight")
+            assert shapes[key] == ((512 if cp.startswith("linear") else 1024), P)
 
 
 def test_unsupported_sampler_options_fail_loudly():

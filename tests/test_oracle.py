@@ -61,6 +61,49 @@ def test_denoiser_matches_golden(golden_dir, name, B, T, t_resp):
     assert relmax(eps.numpy(), g["eps"]) < 2e-5
 
 
+_VARIANTS = [(cp, cr) for cp in ("mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX") for cr in (True, False)
+             if not (cp == "mlp_includeX" and cr)]
+
+
+@pytest.mark.parametrize("name", ["show", "beat"])
+def test_denoiser_variants_match_golden(golden_dir, name):
+    """cond_projection / cond_residual variants (tr:262-263,281-289,300-338) against outputs of the REAL reference
+    (tests/golden/make_golden_variants.py)."""
+    g = np.load(os.path.join(golden_dir, "denoise_variants.npz"))
+    B, T, _, t_orig, a, b = g[name + "_consts"]
+    B, T = int(B), int(T)
+    for cp, cr in _VARIANTS:
+        cfg = synth.make_cfg(name, cond_projection=cp, cond_residual=cr)
+        sd = synth.make_state_dict(cfg, seed=1)
+        inp = synth.make_inputs(cfg, B, T, seed=2)
+        np.testing.assert_allclose(_fp(inp["x_T"], inp["mel"], inp["hubert"]), g[name + "_fp"], rtol=1e-9)
+        ts = torch.full((B,), int(t_orig), dtype=torch.long)
+        with torch.no_grad():
+            eps = unidiffuser_forward(sd, cfg, inp["x_T"], ts, (torch.tensor(float(a)), torch.tensor(float(b))), inp["mel"],
+                                      inp["person_id"], inp["hubert"])
+        assert relmax(eps.numpy(), g[f"{name}_{cp}_{'res' if cr else 'nores'}"]) < 2e-5, (name, cp, cr)
+
+
+@have_ref
+@pytest.mark.parametrize("cond_projection,cond_residual", _VARIANTS)
+def test_denoiser_variants_match_live_reference(cond_projection, cond_residual):
+    """Same op stream as the reference module itself (strict state_dict load: the synthetic key layout of every variant IS the
+    reference's), two layers per net, CFG pair."""
+    cfg = synth.make_cfg("show", cond_projection=cond_projection, cond_residual=cond_residual, num_layers=2)
+    sd = synth.make_state_dict(cfg, seed=3)
+    opt = refshim.make_opt(cfg, cond_projection=cond_projection, cond_residual=cond_residual)
+    model, _ = refshim.build_reference(cfg, sd, opt)
+    B, T = 2, 11
+    inp = synth.make_inputs(cfg, B, T, seed=4)
+    ts = torch.full((B,), 360, dtype=torch.long)
+    sa = (torch.tensor(1.7), torch.tensor(1.4))
+    with torch.no_grad():
+        want = model(inp["x_T"], ts, sqrt_alphas=sa, audio_emb=inp["mel"], length=torch.LongTensor([T] * B),
+                     person_id=inp["person_id"], add_cond={"pretrain_aud_feat": inp["hubert"]}, pe_type="pe_sinu", y={})
+        got = unidiffuser_forward(sd, cfg, inp["x_T"], ts, sa, inp["mel"], inp["person_id"], inp["hubert"])
+    assert relmax(got.numpy(), want.numpy()) < 1e-6
+
+
 @pytest.mark.parametrize("fn,name,B,T,ov,kw", [
     ("loop_show_B1_T88_ov0_ddim25.npz", "show", 1, 88, 0, {}),
     ("loop_beat_B2_T34_ov0_ddim25.npz", "beat", 2, 34, 0, {}),

@@ -1,0 +1,134 @@
+"""GPU parity of the cond_projection / cond_residual variants of the reference's transformer layer (models/transformer.py:
+262-263,281-289,300-338; options/base_options.py:21,95) through the C ABI: linear_includeX, mlp_excludeX,
+linear_excludeX and cond_residual off, on the kernels of the shipped mlp_includeX path (csrc/engine.cu: feat_proj_variant).
+
+Checked against outputs of the REAL reference (tests/golden/denoise_variants.npz, made by tests/golden/make_golden_variants.py),
+against the oracle at a CTA-pair row count, and through a whole ddim25 loop.  The same launch sequences run on the CPU in
+tests/test_emu_engine.py (whole-engine emulation).
+
+Gates: these paths were written after the round's GPU budget was spent, so there is no B200 measurement to set them at 2x of.
+They are the gates of the shipped configuration (tests/test_gpu_parity.py: TOL) widened by 1.5x (mlp_*) / 2x (linear_*, whose
+residual stream grows ~2x per layer with the unit-gain synthetic weights: |eps| up to 3e3).  Whole-engine emulator values at full
+depth (8 layers, B = 2, T = 20; relmax / per_channel / rel_rms vs the fp32 oracle): bf16 worst 1.4e-2 / 3.3e-2 / 1.3e-2 (the shipped
+configuration measures 1.1e-2 / 2.9e-2 / 1.0e-2 on the same emulator run, 1.15e-2 / 2.4e-2 / 1.0e-2 on B200), fp32 2.2e-6 / 3.6e-6 /
+1.8e-6, tf32 8.7e-4 / 2.1e-3 / 8.3e-4.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffsheg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+from parity_util import check as parity_check, fmt as parity_fmt, parity_metrics
+from test_gpu_parity import TOL
+
+COND_PROJECTIONS = ("mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX")
+VARIANTS = [(cp, cr) for cp in COND_PROJECTIONS for cr in (True, False) if not (cp == "mlp_includeX" and cr)]
+WIDEN = {"mlp": 1.5, "linear": 2.0}
+
+
+def _gate(got, want, prec, kind, what, widen=1.0):
+    m = parity_metrics(got, want)
+    print(f"\n[parity] {what} {prec}: {parity_fmt(m)}")
+    parity_check(m, {k: v * widen for k, v in TOL[prec][kind].items()}, f"{what} {prec}")
+
+
+def _engine(name, prec, B, T, cp, cr, **over):
+    from diffsheg_b200 import FusedUniDiffuser
+    cfg = synth.make_cfg(name, cond_projection=cp, cond_residual=cr, **over)
+    sd = synth.make_state_dict(cfg, seed=1)
+    return cfg, sd, FusedUniDiffuser(sd, cfg, precision=prec, max_batch=B, max_frames=T)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
+@pytest.mark.parametrize("cp,cr", VARIANTS)
+@pytest.mark.parametrize("name", ["show", "beat"])
+def test_variant_denoise_matches_reference_golden(golden_dir, name, cp, cr, prec):
+    g = np.load(os.path.join(golden_dir, "denoise_variants.npz"))
+    B, T, _, t_orig, a, b = g[name + "_consts"]
+    B, T = int(B), int(T)
+    cfg, sd, eng = _engine(name, prec, B, T, cp, cr)
+    inp = synth.make_inputs(cfg, B, T, seed=2)
+    eng.prepare_window(inp["mel"].cuda(), inp["hubert"].cuda(), inp["person_id"].cuda())
+    eps = eng.denoise(inp["x_T"].cuda(), int(t_orig), float(a), float(b))
+    torch.cuda.synchronize()
+    assert torch.isfinite(eps).all()
+    want = torch.from_numpy(g[f"{name}_{cp}_{'res' if cr else 'nores'}"])
+    _gate(eps, want, prec, "call", f"denoise {name} {cp} cond_residual={cr} vs reference golden", WIDEN[cp.split("_")[0]])
+
+
+@pytest.mark.parametrize("cp,cr", [("linear_includeX", True), ("mlp_excludeX", True), ("linear_excludeX", False), ("mlp_includeX", False)])
+def test_variant_denoise_at_a_cta_pair_row_count_matches_oracle(cp, cr):
+    """B = 50, T = 88 under CFG: 8800 rows -- the tcgen05 GEMMs take their CTA-pair (cta_group::2) forms, the multi-segment operand
+    without the hidden-state segment included; bf16 engine vs the fp32 oracle on the same GPU."""
+    from oracle.denoiser import unidiffuser_forward
+    B, T = 50, 88
+    cfg, sd, eng = _engine("show", "bf16", B, T, cp, cr)
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=5).items()}
+    eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+    a, b = 1.8, 1.5
+    got = eng.denoise(inp["x_T"], 480, a, b)
+    ts = torch.full((B,), 480, dtype=torch.long, device="cuda")
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        want = unidiffuser_forward(sd_c, cfg, inp["x_T"], ts, (torch.tensor(a, device="cuda"), torch.tensor(b, device="cuda")),
+                                   inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float32)
+    assert torch.isfinite(got).all()
+    _gate(got, want, "bf16", "call", f"denoise show B{B} {cp} cond_residual={cr} vs fp32 oracle", WIDEN[cp.split("_")[0]])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,cp,cr", [("show", "mlp_excludeX", True), ("beat", "linear_excludeX", True), ("show", "linear_includeX", False)])
+def test_variant_ddim25_loop_matches_oracle(name, cp, cr, prec):
+    """The whole sampling loop (25 denoiser calls + step kernels, CUDA-graph replay from the third call on) on a variant engine,
+    driven through the reference's calling protocol, vs the oracle loop on the same x_T.  linear_includeX without cond_residual
+    is the case whose captured graph holds a memset node (CFG-null rows) and a 2-D copy node (staged projection)."""
+    from diffsheg_b200 import FusedSpacedDiffusion, get_named_beta_schedule, space_timesteps
+    from oracle import diffusion as odiff
+    B = 2
+    cfg, sd, eng = _engine(name, prec, B, None, cp, cr)
+    T = cfg["n_poses"]
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=2).items()}
+    opt = synth.make_opt(cfg, ddim=True)
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim25"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    kw = dict(audio_emb=inp["mel"], length=None, person_id=inp["person_id"], add_cond={"pretrain_aud_feat": inp["hubert"]}, y={},
+              pe_type="pe_sinu")
+    out = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), noise=inp["x_T"], clip_denoised=False, model_kwargs=kw)
+    assert diff.last_stats["denoise_calls"] == 25
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        den = odiff.make_denoise(sd_c, cfg, inp["mel"], inp["person_id"], inp["hubert"])
+        want = odiff.OracleDiffusion(1000, "ddim25").ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"])
+    assert torch.isfinite(out).all()
+    _gate(out, want, prec, "loop", f"ddim25 loop {name} {cp} cond_residual={cr} vs oracle", WIDEN[cp.split("_")[0]])
+
+
+def test_from_module_protocol_picks_the_variant_up_from_opt():
+    """SEAM #1 with a variant `opt` (what FusedUniDiffuser.from_module / patch_trainer see): cfg_from_opt carries cond_projection and
+    cond_residual into the engine, the packer follows the state_dict layout of that variant."""
+    import argparse
+
+    from diffsheg_b200 import FusedUniDiffuser, cfg_from_opt
+    from oracle.denoiser import unidiffuser_forward
+    cp, cr, B, T = "linear_includeX", False, 3, 34
+    cfg0 = synth.make_cfg("beat", cond_projection=cp, cond_residual=cr)
+    opt = argparse.Namespace(**vars(synth.make_opt(cfg0)), cond_projection=cp, cond_residual=cr)
+    cfg = cfg_from_opt(opt, n_poses=T)
+    assert (cfg["cond_projection"], cfg["cond_residual"]) == (cp, cr)
+    sd = synth.make_state_dict(cfg0, seed=1)
+    eng = FusedUniDiffuser(sd, cfg, precision="fp32", max_batch=B, max_frames=T)
+    inp = {k: v.cuda() for k, v in synth.make_inputs(cfg0, B, T, seed=6).items()}
+    ts = torch.full((B,), 200, dtype=torch.long, device="cuda")
+    shp = (B, T, cfg["expression_dim"])
+    got = eng(inp["x_T"], ts, sqrt_alphas=[torch.full(shp, 1.3, device="cuda"), torch.full(shp, 0.9, device="cuda")],
+              audio_emb=inp["mel"], length=None, person_id=inp["person_id"], add_cond={"pretrain_aud_feat": inp["hubert"]},
+              pe_type="pe_sinu", y={})
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        want = unidiffuser_forward(sd_c, cfg0, inp["x_T"], ts, (torch.tensor(1.3, device="cuda"), torch.tensor(0.9, device="cuda")),
+                                   inp["mel"], inp["person_id"], inp["hubert"], dtype=torch.float64)
+    _gate(got, want, "fp32", "call", "from-opt linear_includeX cond_residual=False vs fp64 oracle", WIDEN["linear"])
