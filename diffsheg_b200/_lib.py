@@ -82,6 +82,7 @@ SIGNATURES = {
     "dsheg_inv_standardize": (ctypes.c_int, [_P, _I32, _P, _P, _P, _I32, _I64, _I32, _P]),
     "dsheg_beat_axis_angle_to_euler": (ctypes.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "dsheg_resample_linear": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
+    "dsheg_mel_spectrogram": (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P]),
     "dsheg_op_linear": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "dsheg_op_linear_fused": (ctypes.c_int, [_I32, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "dsheg_bench_gemm": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(ctypes.c_float)]),

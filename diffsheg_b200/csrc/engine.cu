@@ -19,6 +19,7 @@
 #include "attn_ws.cuh"
 #include "attn_tf32.cuh"
 #include "common.cuh"
+#include "frontend.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tf32.cuh"
@@ -1043,6 +1044,20 @@ int dsheg_resample_linear(const float* in, float* out, int32_t B, int32_t n_in, 
   const long long total4 = (long long)B * n_out * (C / 4);
   resample_linear_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(in, out, n_in, n_out, C, total4);
   return step_done("dsheg_resample_linear");
+}
+
+int dsheg_mel_spectrogram(const float* audio, int64_t n_samples, int32_t n_fft, int32_t hop, int32_t pad_mode, const float* window,
+                          const float* mel_basis, const int32_t* mel_range, int32_t n_mels, float* out, int32_t n_frames, void* stream) {
+  if (!audio || !window || !mel_basis || !mel_range || !out || n_samples < 1 || hop < 1 || n_mels < 1 || n_frames < 1 ||
+      n_fft != fe::NFFT || (pad_mode != fe::PAD_CONSTANT && pad_mode != fe::PAD_REFLECT) ||
+      (pad_mode == fe::PAD_REFLECT && n_samples <= fe::NFFT / 2) || (int64_t)(n_frames - 1) * hop > n_samples) {
+    g_create_error = "dsheg_mel_spectrogram: bad arguments (n_fft must be 2048; frames 0 .. n_samples / hop; reflect padding needs more than 1024 samples)";
+    return 1;
+  }
+  DeviceGuard dg(device_of(audio));
+  DSHEG_LAUNCH_PLAIN(fe::mel_power_kernel, n_frames, fe::NTHREADS, fe::SMEM_BYTES, (cudaStream_t)stream, audio, (long long)n_samples, hop, pad_mode,
+                     window, mel_basis, (const int*)mel_range, n_mels, out);
+  return step_done("dsheg_mel_spectrogram");
 }
 
 // ---- op-level test entry points --------------------------------------------------------------

@@ -151,6 +151,15 @@ int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mea
  * (trainers/ddpm_show_trainer.py:1082, datasets/show.py:98, datasets/beat.py:445).  fp32, C % 4 == 0. */
 int dsheg_resample_linear(const float* in, float* out, int32_t B, int32_t n_in, int32_t n_out, int32_t C, void* stream);
 
+/* Audio front-end, mel half: librosa.feature.melspectrogram(y=aud, sr=18000, hop_length=1200, n_mels=128) as the
+ * trainers call it (trainers/ddpm_show_trainer.py:1063, trainers/ddpm_beat_trainer.py:1244, datasets/beat.py:371): centred frames of
+ * n_fft = 2048 samples every `hop`, times `window` [n_fft], |rfft|^2, times the filterbank mel_basis [n_mels, n_fft/2 + 1] whose band m
+ * is non-zero on bins mel_range[2m] .. mel_range[2m+1]-1.  pad_mode: 0 = zeros ('constant'), 1 = 'reflect' (np.pad modes of
+ * librosa.stft).  audio fp32 [n_samples]; out fp32 [n_frames, n_mels], frame-major (the layout after np.swapaxes, show:1066),
+ * n_frames <= 1 + n_samples / hop.  Window and filterbank are the caller's (diffsheg_b200/frontend.py builds librosa's). */
+int dsheg_mel_spectrogram(const float* audio, int64_t n_samples, int32_t n_fft, int32_t hop, int32_t pad_mode, const float* window,
+                          const float* mel_basis, const int32_t* mel_range, int32_t n_mels, float* out, int32_t n_frames, void* stream);
+
 /* ---- op-level entry points used by the parity tests -------------------------------------- */
 
 /* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); precision selects the SIMT fp32, the

@@ -4,6 +4,7 @@
 
 #include "attn_v3.cuh"
 #include "attn_small.cuh"
+#include "frontend.cuh"
 #include "postprocess.cuh"
 #include "sampler.cuh"
 
@@ -79,4 +80,12 @@ extern "C" int emu_ddpm_step(const float* x, const float* eps, const float* nois
 extern "C" int emu_repaint_merge(const float* x, const float* gt, const unsigned char* mask, const float* noise, float* out, long long n,
                                  float c1, float c2) {
   return ew(n, [=] { repaint_merge_kernel(x, gt, mask, noise, out, n, c1, c2); });
+}
+
+// mel power spectrogram (csrc/frontend.cuh): one CTA per frame
+extern "C" int emu_mel_spectrogram(const float* audio, long long n_samples, int hop, int pad_mode, const float* window, const float* basis,
+                                   const int* range, int n_mels, float* out, int n_frames) {
+  g_err.clear();
+  return emu::run_grid(n_frames, fe::NTHREADS, 1, fe::SMEM_BYTES,
+                       [=] { fe::mel_power_kernel(audio, n_samples, hop, pad_mode, window, basis, range, n_mels, out); }, &g_err) ? 0 : 1;
 }
