@@ -52,6 +52,29 @@ def test_shipped_configuration_on_the_emulated_engine(name, precision, B, T):
     assert launches > 40
 
 
+def test_emulated_bf16_engine_reproduces_an_output_of_the_real_reference(golden_dir):
+    """Full depth (8 layers per net) against tests/golden/denoise_beat_B1_T30_t3.npz -- an output of the REAL reference module
+    (tests/golden/make_golden.py) -- in the benchmarked precision mode: the comparison test_gpu_parity.py makes on the B200, here
+    without one.  The full golden set runs offline (scripts/emu_golden_sweep.py -> profiles/r02/emu/): the emulator's figures match the
+    hardware's (show B2 T88 bf16: 1.19e-2 / 2.8e-2 / 1.0e-2 emulated vs 1.15e-2 / 2.4e-2 / 1.0e-2 on B200)."""
+    import os
+
+    import numpy as np
+
+    from parity_util import check, parity_metrics
+    g = np.load(os.path.join(golden_dir, "denoise_beat_B1_T30_t3.npz"))
+    cfg = synth.make_cfg("beat")
+    sd = synth.make_state_dict(cfg, seed=1)
+    inp = synth.make_inputs(cfg, 1, 30, seed=2)
+    eng = emu.EmuEngine(sd, cfg, precision="bf16", max_batch=1, max_frames=30)
+    try:
+        eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+        got = eng.denoise(inp["x_T"], int(g["t_orig"]), float(g["a"]), float(g["b"]))
+    finally:
+        eng.close()
+    check(parity_metrics(got, torch.from_numpy(g["eps"])), dict(relmax=2.5e-2, rel_rms=2.2e-2), "emulated bf16 engine vs reference golden")
+
+
 _VARIANTS = [(cp, cr) for cp in COND_PROJECTIONS for cr in (True, False) if not (cp == "mlp_includeX" and cr)]
 
 
