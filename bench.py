@@ -239,7 +239,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     C = CONFIGS[args.config]
-    cfg = synth.make_cfg(C["net"])
+    variant = {}
+    if args.cond_projection != "mlp_includeX" or args.no_cond_residual:    # DESIGN 3.5; the defaults are the shipped model
+        variant = dict(cond_projection=args.cond_projection, cond_residual=not args.no_cond_residual)
+    cfg = synth.make_cfg(C["net"], **variant)
     T, Dm = cfg["n_poses"], cfg["net_dim_pose"]
     scaling = C.get("scaling", "weak")
     ddim, overlap, long_frames = C.get("ddim", True), C.get("overlap", 0), C.get("long_frames", 0)
@@ -380,7 +383,7 @@ def run_ours(args):
                        "inputs": "pre-drawn with one global seed and sliced by rank (result independent of the GPU count)" if scaling == "strong"
                                  else "per-rank seed",
                        # experiment switches in effect (empty = the shipped defaults), so variant runs describe themselves
-                       "switches": {k: v for k, v in os.environ.items() if k.startswith("DSHEG_") and v}},
+                       "switches": {k: v for k, v in os.environ.items() if k.startswith("DSHEG_") and v}, **({"model_variant": variant} if variant else {})},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world,
@@ -417,6 +420,9 @@ def main():
     ap.add_argument("--config", default="2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: 2, the one the metric is quoted on)")
     ap.add_argument("--batch", type=int, default=0, help="override the config's batch (per GPU for weak, global for strong scaling)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--cond-projection", default="mlp_includeX", choices=["mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX"],
+                    help="opt.cond_projection of the synthetic model (default: the shipped one; BASELINE numbers are quoted on the default)")
+    ap.add_argument("--no-cond-residual", action="store_true", help="opt.cond_residual False")
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample of the workload (about 10 s of CPU work per loop)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference op stream eagerly on the GPU (about 20 s)")

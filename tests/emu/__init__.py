@@ -79,6 +79,7 @@ def engine_lib():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = product.SIGNATURES[name]
     L.emu_engine_last_launch_error.restype = ctypes.c_char_p
+    L.emu_engine_launches.restype = ctypes.c_longlong
     return L
 
 
@@ -129,6 +130,10 @@ class EmuEngine:
 
     def launch_count(self):
         return int(self.L.dsheg_launch_count(self.h))
+
+    def emulated_launches(self):
+        """Kernel launches the emulator has actually executed in this process (all engines)."""
+        return int(self.L.emu_engine_launches())
 
     def close(self):
         if self.h:

@@ -161,6 +161,7 @@ struct Runtime {
   Thread* cur = nullptr;
   Launch launch;
   uint64_t progress = 0;
+  uint64_t grids_run = 0;   // number of run_grid calls = kernel launches the emulator has executed
   std::string error;
   std::function<void()> body;
 };
@@ -212,6 +213,7 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
   Runtime& R = rt();
   R.body = body;
   R.error.clear();
+  ++R.grids_run;
   R.launch.grid = {grid_x, grid_y, 1};
   R.launch.block = {block_x, 1, 1};
   R.launch.cluster_size = cluster_size;
