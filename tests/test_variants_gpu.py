@@ -29,12 +29,26 @@ from test_gpu_parity import TOL
 COND_PROJECTIONS = ("mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX")
 VARIANTS = [(cp, cr) for cp in COND_PROJECTIONS for cr in (True, False) if not (cp == "mlp_includeX" and cr)]
 WIDEN = {"mlp": 1.5, "linear": 2.0}
+PAIR_B, PAIR_T = 50, 88     # 2 * 50 * 88 = 8800 rows under CFG: >= 4096 cond rows, the CTA-pair regime of the tcgen05 GEMMs
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32_oracle():
+    """The reference runs strict fp32: no TF32 in the oracle's matmuls / convolutions on the GPU."""
+    tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
 
 
 def _gate(got, want, prec, kind, what, widen=1.0):
     m = parity_metrics(got, want)
     print(f"\n[parity] {what} {prec}: {parity_fmt(m)}")
-    parity_check(m, {k: v * widen for k, v in TOL[prec][kind].items()}, f"{what} {prec}")
+    tol = {k: v * widen for k, v in TOL[prec][kind].items()}
+    if want.numel() // want.shape[-1] < 32:
+        tol.pop("per_channel")   # a channel's own scale is not defined by a handful of frames (as in tests/test_gpu_parity.py: gate)
+    parity_check(m, tol, f"{what} {prec}")
 
 
 def _engine(name, prec, B, T, cp, cr, **over):
@@ -66,7 +80,7 @@ def test_variant_denoise_at_a_cta_pair_row_count_matches_oracle(cp, cr):
     """B = 50, T = 88 under CFG: 8800 rows -- the tcgen05 GEMMs take their CTA-pair (cta_group::2) forms, the multi-segment operand
     without the hidden-state segment included; bf16 engine vs the fp32 oracle on the same GPU."""
     from oracle.denoiser import unidiffuser_forward
-    B, T = 50, 88
+    B, T = PAIR_B, PAIR_T
     cfg, sd, eng = _engine("show", "bf16", B, T, cp, cr)
     inp = {k: v.cuda() for k, v in synth.make_inputs(cfg, B, T, seed=5).items()}
     eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
@@ -102,7 +116,7 @@ def test_variant_ddim25_loop_matches_oracle(name, cp, cr, prec):
     sd_c = {k: v.cuda() for k, v in sd.items()}
     with torch.no_grad():
         den = odiff.make_denoise(sd_c, cfg, inp["mel"], inp["person_id"], inp["hubert"])
-        want = odiff.OracleDiffusion(1000, "ddim25").ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"])
+        want = odiff.OracleDiffusion(1000, "ddim25").ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"], device="cuda")
     assert torch.isfinite(out).all()
     _gate(out, want, prec, "loop", f"ddim25 loop {name} {cp} cond_residual={cr} vs oracle", WIDEN[cp.split("_")[0]])
 
