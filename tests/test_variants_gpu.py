@@ -7,11 +7,15 @@ against the oracle at a CTA-pair row count, and through a whole ddim25 loop.  Th
 tests/test_emu_engine.py (whole-engine emulation).
 
 Gates: these paths were written after the round's GPU budget was spent, so there is no B200 measurement to set them at 2x of.
-They are the gates of the shipped configuration (tests/test_gpu_parity.py: TOL) widened by 1.5x (mlp_*) / 2x (linear_*, whose
-residual stream grows ~2x per layer with the unit-gain synthetic weights: |eps| up to 3e3).  Whole-engine emulator values at full
-depth (8 layers, B = 2, T = 20; relmax / per_channel / rel_rms vs the fp32 oracle): bf16 worst 1.4e-2 / 3.3e-2 / 1.3e-2 (the shipped
-configuration measures 1.1e-2 / 2.9e-2 / 1.0e-2 on the same emulator run, 1.15e-2 / 2.4e-2 / 1.0e-2 on B200), fp32 2.2e-6 / 3.6e-6 /
-1.8e-6, tf32 8.7e-4 / 2.1e-3 / 8.3e-4.
+They are the gates of the shipped configuration (tests/test_gpu_parity.py: TOL) widened by 1.5x, which is 2x - 3.7x the worst value
+of the SAME comparison (these goldens, full depth and size) on the whole-engine emulator -- scripts/emu_golden_sweep.py ->
+profiles/r02/emu/golden_variants_emulated_engine.txt, relmax / per_channel / rel_rms:
+  bf16  linear_* 1.33e-2 / 2.53e-2 / 1.26e-2   mlp_* 1.03e-2 / 3.05e-2 / 1.00e-2
+  tf32  linear_* 9.5e-4 / 1.96e-3 / 9.4e-4     mlp_* 1.21e-3 / 3.08e-3 / 1.05e-3
+  fp32  linear_* 2.2e-6 / 3.5e-6 / 1.9e-6      mlp_* 1.9e-6 / 4.2e-6 / 1.5e-6
+The emulator's figures track the hardware's: for the shipped configuration the same sweep gives 1.19e-2 / 2.8e-2 / 1.0e-2 (bf16),
+8.1e-4 / 2.0e-3 / 7.4e-4 (tf32), 2.0e-6 / 3.8e-6 / 1.4e-6 (fp32) against 1.15e-2 / 2.4e-2 / 1.0e-2, 8.7e-4 / 1.7e-3 / 7.4e-4 and
+1.8e-6 / 3.0e-6 / 1.5e-6 measured on B200 (profiles/r02/emu/golden_shipped_emulated_engine.txt, profiles/r02/parity_report.json).
 """
 import os
 
@@ -28,7 +32,7 @@ from test_gpu_parity import TOL
 
 COND_PROJECTIONS = ("mlp_includeX", "linear_includeX", "mlp_excludeX", "linear_excludeX")
 VARIANTS = [(cp, cr) for cp in COND_PROJECTIONS for cr in (True, False) if not (cp == "mlp_includeX" and cr)]
-WIDEN = {"mlp": 1.5, "linear": 2.0}
+WIDEN = {"mlp": 1.5, "linear": 1.5}
 PAIR_B, PAIR_T = 50, 88     # 2 * 50 * 88 = 8800 rows under CFG: >= 4096 cond rows, the CTA-pair regime of the tcgen05 GEMMs
 
 
