@@ -30,14 +30,12 @@ namespace emu_rt {
 inline cudaError_t& sticky() { static cudaError_t e = cudaSuccess; return e; }
 inline std::string& last_launch_error() { static std::string s; return s; }
 inline int& num_sms() { static int n = 8; return n; }   // a small "device": persistent kernels walk several tiles per CTA
-inline long long& launches() { static long long n = 0; return n; }
 
 // kernel<<<grid, block, smem, stream>>>(args...) on the emulator; a kernel with STATIC shared memory passes its size as `smem`
 template <typename... KA, typename... A>
 inline void launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t, A... a) {
   std::tuple<typename std::decay<KA>::type...> args(static_cast<typename std::decay<KA>::type>(a)...);
   std::string err;
-  ++launches();
   if (grid.z != 1 || block.y != 1 || block.z != 1) { sticky() = cudaErrorInvalidValue; last_launch_error() = "emulated launches are 2-D grids of 1-D blocks"; return; }
   const bool ok = emu::run_grid(grid.x, block.x, 1, smem, [&] { std::apply(kern, args); }, &err, grid.y);
   if (!ok) { sticky() = cudaErrorLaunchFailure; last_launch_error() = err; }
