@@ -80,6 +80,7 @@ def engine_lib():
         fn.restype, fn.argtypes = product.SIGNATURES[name]
     L.emu_engine_last_launch_error.restype = ctypes.c_char_p
     L.emu_engine_launches.restype = ctypes.c_longlong
+    L.emu_engine_graph_launches.restype = ctypes.c_longlong
     return L
 
 
@@ -134,6 +135,10 @@ class EmuEngine:
     def emulated_launches(self):
         """Kernel launches the emulator has actually executed in this process (all engines)."""
         return int(self.L.emu_engine_launches())
+
+    def graph_launches(self):
+        """cudaGraphLaunch calls so far in this process: replays of a captured denoiser call (the small-batch regime of dsheg_denoise)."""
+        return int(self.L.emu_engine_graph_launches())
 
     def close(self):
         if self.h:

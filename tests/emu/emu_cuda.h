@@ -199,6 +199,13 @@ inline uint8_t (*warp_exchange(const void* mine, int bytes, const char* what))[6
   return w.slot[p];
 }
 
+// Stream capture (emu_runtime.h: cudaStreamBeginCapture ... cudaGraphLaunch): while a capture is active, run_grid RECORDS the launch --
+// grid shape and the body with its by-value kernel arguments, exactly what a CUDA graph kernel node bakes in -- instead of running it;
+// replaying the recorded list re-executes it.  A host value that changes from step to step and was passed by value to a captured launch
+// is therefore stale on replay, as on the device.
+struct Capture { std::vector<std::function<bool(std::string*)>> ops; };
+inline Capture*& active_capture() { static Capture* c = nullptr; return c; }
+
 inline void trampoline() {
   rt().body();
   self().done = true;
@@ -210,6 +217,10 @@ inline void trampoline() {
 // A 2-D grid (grid_y > 1; clusters of one CTA only) is walked x-fastest: blockIdx = {i % grid_x, i / grid_x, 0}.
 inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, size_t smem_bytes, std::function<void()> body,
                      std::string* err, uint32_t grid_y = 1) {
+  if (Capture* cap = active_capture()) {
+    cap->ops.push_back([=](std::string* e) { return run_grid(grid_x, block_x, cluster_size, smem_bytes, body, e, grid_y); });
+    return true;
+  }
   Runtime& R = rt();
   R.body = body;
   R.error.clear();

@@ -9,3 +9,4 @@
 extern "C" void emu_engine_set_sms(int n) { emu_rt::num_sms() = n; }
 extern "C" long long emu_engine_launches() { return (long long)emu::rt().grids_run; }   // every kernel launch the emulator executed
 extern "C" const char* emu_engine_last_launch_error() { return emu_rt::last_launch_error().c_str(); }
+extern "C" long long emu_engine_graph_launches() { return emu_rt::graph_launches(); }

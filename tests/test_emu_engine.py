@@ -105,6 +105,40 @@ def test_cond_projection_variants_tensor_core_modes(cond_projection, cond_residu
     assert err < TOL[precision], (cond_projection, cond_residual, name, precision, err)
 
 
+@pytest.mark.parametrize("name,precision,over", [
+    ("show", "fp32", {}), ("show", "bf16", {}),
+    # the variants whose call holds stream-ordered host operations between the kernels: a memset of the CFG-null rows (nothing is added
+    # back) and the 2-D copy of the staged single-Linear projection -- memset / memcpy nodes of the captured graph
+    ("show", "fp32", dict(cond_projection="linear_includeX", cond_residual=False)),
+    ("show", "bf16", dict(cond_projection="mlp_includeX", cond_residual=False))])
+def test_graph_replay_path_of_dsheg_denoise(name, precision, over):
+    """Small batches replay a captured graph of the call from the third call of a window shape on (engine.cu: dsheg_denoise; on the
+    device every test of this size takes that path inside a sampling loop).  The emulated capture records each launch with its by-value
+    arguments like a CUDA graph node, so a step-dependent host value baked into the capture would be stale on replay: three calls
+    with different timesteps, step scalars and inputs must each match the oracle, the launch accounting must hold on replays too."""
+    B, T = 1, 6
+    cfg = synth.make_cfg(name, num_layers=1, **over)
+    sd = synth.make_state_dict(cfg, seed=1)
+    inp = synth.make_inputs(cfg, B, T, seed=2)
+    eng = emu.EmuEngine(sd, cfg, precision=precision, max_batch=B, max_frames=T)
+    try:
+        eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+        x, replays0 = inp["x_T"], eng.graph_launches()
+        for i, (t, a, b) in enumerate([(960, 7.1, 7.0), (480, 1.8, 1.5), (40, 1.02, 0.2)]):
+            n0, e0 = eng.launch_count(), eng.emulated_launches()
+            got = eng.denoise(x, t, a, b)
+            assert eng.launch_count() - n0 == eng.emulated_launches() - e0
+            assert eng.graph_launches() - replays0 == max(0, i)          # call 0 runs eagerly, call 1 captures and replays, 2.. replay
+            with torch.no_grad():
+                want = unidiffuser_forward(sd, cfg, x, torch.full((B,), t, dtype=torch.long), (torch.tensor(a), torch.tensor(b)), inp["mel"],
+                                           inp["person_id"], inp["hubert"], dtype=torch.float64)
+            err = float((got.double() - want).abs().max() / want.abs().max())
+            assert err < TOL[precision], (i, t, err)
+            x = a * x - b * got          # the next call sees a different input, like the next step of a sampler
+    finally:
+        eng.close()
+
+
 def test_abi_version_1_struct_is_still_accepted_and_unknown_projection_is_rejected():
     """dsheg_create (include/diffsheg_b200.h): a version-1 caller passes the 15-field struct and gets the shipped defaults; values
     outside DSHEG_COND_* fail with a message instead of being misread."""
