@@ -913,8 +913,6 @@ int dsheg_denoise(dsheg_handle* h, const float* x, int32_t t_orig, float a, floa
 
 int64_t dsheg_launch_count(const dsheg_handle* h) { return h ? h->launches : 0; }
 
-#ifndef DSHEG_EMU   // the whole-engine emulator build (tests/emu/emu_engine.cpp) ends here: profiling, the stateless step kernels and
-                    // the op-level / bench entry points have their own emulator coverage (tests/emu/emu_kernels.cpp, emu_gemm*.cpp)
 
 int dsheg_profile_begin(dsheg_handle* h) {
   if (!h) return 1;
@@ -1002,8 +1000,8 @@ int dsheg_ddpm_step(const float* x, const float* eps, const float* noise, float*
                     float sqrt_recipm1_ac, float coef1, float coef2, float sigma, float* pred_xstart_out, void* stream) {
   if (!x || !eps || !noise || !x_out || n <= 0) { g_create_error = "dsheg_ddpm_step: bad arguments"; return 1; }
   DeviceGuard dg(device_of(x));
-  ddpm_step_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, x_out, pred_xstart_out, n, sqrt_recip_ac,
-                                                                 sqrt_recipm1_ac, coef1, coef2, sigma);
+  DSHEG_LAUNCH_PLAIN(ddpm_step_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, x, eps, noise, x_out, pred_xstart_out, (long long)n, sqrt_recip_ac,
+                     sqrt_recipm1_ac, coef1, coef2, sigma);
   return step_done("dsheg_ddpm_step");
 }
 
@@ -1011,7 +1009,7 @@ int dsheg_repaint_merge(const float* x, const float* gt, const uint8_t* mask, co
                         float sqrt_ac, float sqrt_one_minus_ac, void* stream) {
   if (!x || !gt || !mask || !noise || !x_out || n <= 0) { g_create_error = "dsheg_repaint_merge: bad arguments"; return 1; }
   DeviceGuard dg(device_of(x));
-  repaint_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, gt, mask, noise, x_out, n, sqrt_ac, sqrt_one_minus_ac);
+  DSHEG_LAUNCH_PLAIN(repaint_merge_kernel, ew_grid(n), 256, 0, (cudaStream_t)stream, x, gt, mask, noise, x_out, (long long)n, sqrt_ac, sqrt_one_minus_ac);
   return step_done("dsheg_repaint_merge");
 }
 
@@ -1020,7 +1018,7 @@ int dsheg_inv_standardize(const float* x, int32_t ldx, const float* mean, const 
                           int64_t rows, int32_t D, void* stream) {
   if (!x || !mean || !stdv || !out || rows <= 0 || D <= 0 || ldx < D || ldo < D) { g_create_error = "dsheg_inv_standardize: bad arguments"; return 1; }
   DeviceGuard dg(device_of(x));
-  inv_standardize_kernel<<<ew_grid(rows * D), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean, stdv, out, ldo, rows, D);
+  DSHEG_LAUNCH_PLAIN(inv_standardize_kernel, ew_grid(rows * D), 256, 0, (cudaStream_t)stream, x, ldx, mean, stdv, out, ldo, (long long)rows, D);
   return step_done("dsheg_inv_standardize");
 }
 
@@ -1031,8 +1029,8 @@ int dsheg_beat_axis_angle_to_euler(const float* x, int32_t ldx, const float* mea
     g_create_error = "dsheg_beat_axis_angle_to_euler: bad arguments (C must be 3 * joints)"; return 1;
   }
   DeviceGuard dg(device_of(x));
-  beat_axis_angle_kernel<<<ew_grid(rows * (C / 3)), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean_aa, std_aa, mean_pose, std_pose,
-                                                                                   euler_deg, out_norm, rows, C / 3);
+  DSHEG_LAUNCH_PLAIN(beat_axis_angle_kernel, ew_grid(rows * (C / 3)), 256, 0, (cudaStream_t)stream, x, ldx, mean_aa, std_aa, mean_pose, std_pose,
+                     euler_deg, out_norm, (long long)rows, C / 3);
   return step_done("dsheg_beat_axis_angle_to_euler");
 }
 
@@ -1042,7 +1040,7 @@ int dsheg_resample_linear(const float* in, float* out, int32_t B, int32_t n_in, 
   }
   DeviceGuard dg(device_of(in));
   const long long total4 = (long long)B * n_out * (C / 4);
-  resample_linear_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(in, out, n_in, n_out, C, total4);
+  DSHEG_LAUNCH_PLAIN(resample_linear_kernel, ew_grid(total4), 256, 0, (cudaStream_t)stream, in, out, n_in, n_out, C, total4);
   return step_done("dsheg_resample_linear");
 }
 
@@ -1060,6 +1058,8 @@ int dsheg_mel_spectrogram(const float* audio, int64_t n_samples, int32_t n_fft, 
   return step_done("dsheg_mel_spectrogram");
 }
 
+#ifndef DSHEG_EMU   // the whole-engine emulator build (tests/emu/emu_engine.cpp) ends here: the op-level / bench entry points below
+                    // have their own emulator coverage (tests/emu/emu_kernels.cpp, emu_gemm*.cpp, emu_attn_ws.cpp)
 // ---- op-level test entry points --------------------------------------------------------------
 namespace {
 __global__ void bf16_to_f32_kernel(const bf16* in, float* out, size_t n) {

@@ -74,10 +74,11 @@ def engine_lib():
     include/diffsheg_b200.h itself; "device" pointers are host pointers (emu_runtime.h)."""
     from diffsheg_b200 import _lib as product
     L = _load("emu_engine", ("DSHEG_EMU_RUNTIME",))
-    for name in ("dsheg_last_error", "dsheg_create", "dsheg_destroy", "dsheg_load_tensor", "dsheg_finalize_weights",
-                 "dsheg_prepare_window", "dsheg_denoise", "dsheg_launch_count"):
+    for name, sig in product.SIGNATURES.items():     # everything but the op-level test / bench entry points is in the emulated build
+        if name.startswith(("dsheg_op_", "dsheg_bench_")):
+            continue
         fn = getattr(L, name)
-        fn.restype, fn.argtypes = product.SIGNATURES[name]
+        fn.restype, fn.argtypes = sig
     L.emu_engine_last_launch_error.restype = ctypes.c_char_p
     L.emu_engine_launches.restype = ctypes.c_longlong
     L.emu_engine_graph_launches.restype = ctypes.c_longlong

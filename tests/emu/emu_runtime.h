@@ -27,6 +27,8 @@ typedef void* cudaEvent_t;
 typedef void* cudaGraph_t;
 typedef void* cudaGraphExec_t;
 struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 148; };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type = cudaMemoryTypeDevice; int device = 0; };
 
 namespace emu_rt {
 inline cudaError_t& sticky() { static cudaError_t e = cudaSuccess; return e; }
@@ -78,6 +80,7 @@ inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyK
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
   return emu_rt::stream_op([=] { for (size_t r = 0; r < height; ++r) memmove(static_cast<char*>(d) + r * dpitch, static_cast<const char*>(s) + r * spitch, width); });
 }
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* at, const void*) { *at = cudaPointerAttributes(); return cudaSuccess; }   // every pointer is "device 0" memory
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
