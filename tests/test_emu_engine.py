@@ -139,6 +139,30 @@ def test_graph_replay_path_of_dsheg_denoise(name, precision, over):
         eng.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_whole_call_is_bit_identical_under_a_shuffled_thread_schedule(precision, monkeypatch):
+    """The emulator's stand-in for compute-sanitizer racecheck, at the level of the whole call: any order in which the emulator runs
+    its fibers is a legal execution (EMU_SCHED=shuffle draws a new order every scheduler pass and lets random warps sit passes out), so
+    every kernel of the call -- the row-wise / glue kernels of kernels.cuh, the SIMT GEMM, the generic and TF32 attention, the hubert
+    convolutions, next to the tcgen05 GEMMs and attn_ws that have kernel-level versions of this test -- must produce the same BITS."""
+    cfg = synth.make_cfg("show", num_layers=1)
+    sd = synth.make_state_dict(cfg, seed=1)
+    inp = synth.make_inputs(cfg, 1, 6, seed=2)
+    outs = []
+    for sched in (None, "shuffle"):
+        if sched:
+            monkeypatch.setenv("EMU_SCHED", sched)       # read by the emulator at every launch
+        else:
+            monkeypatch.delenv("EMU_SCHED", raising=False)
+        eng = emu.EmuEngine(sd, cfg, precision=precision, max_batch=1, max_frames=6)
+        try:
+            eng.prepare_window(inp["mel"], inp["hubert"], inp["person_id"])
+            outs.append(eng.denoise(inp["x_T"], T_ORIG, A_RECIP, B_RECIPM1))
+        finally:
+            eng.close()
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+
+
 def test_c_host_loop_of_the_integration_guide_on_the_emulated_library():
     """a non-Python host drives dsheg_prepare_window once, then dsheg_denoise + dsheg_ddim_step (in place)
     per step with the tables of SpacedDiffusion -- here through ctypes on the emulated library, a 5-step DDIM schedule ('ddim5':

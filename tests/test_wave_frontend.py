@@ -5,6 +5,7 @@ librosa is absent (no network), so the oracle (oracle/frontend.py) is a restatem
 against librosa itself.  It is anchored here on an independent STFT (torch.stft in float64), on Parseval's identity and on the closed
 form of the Slaney filterbank; the CUDA kernel is then held to the oracle."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -89,6 +90,15 @@ def test_mel_kernel_source_on_emulator(n, pad_mode):
     want = ofe.melspectrogram(y, SR, 2048, HOP, N_MELS, pad_mode).T
     assert np.isfinite(out).all()
     assert _relmax(out, want) < 1e-5
+    # schedule independence (the emulator's racecheck stand-in): a shuffled thread order must give the same bits -- a missing
+    # __syncthreads between two butterfly stages would not
+    out2 = np.full_like(out, np.nan)
+    os.environ["EMU_SCHED"] = "shuffle"
+    try:
+        assert L.emu_mel_spectrogram(P(y), ctypes.c_longlong(n), HOP, fe.PAD_MODES[pad_mode], P(win), P(basis), P(rng), N_MELS, P(out2), n_frames) == 0
+    finally:
+        del os.environ["EMU_SCHED"]
+    assert np.array_equal(out, out2)
 
 
 # ---- the product on a GPU ---------------------------------------------------------------------------------------------------------
