@@ -9,8 +9,10 @@ reference makes -- ``librosa.feature.melspectrogram(y=aud, sr=18000, hop_length=
   ``np.fft.rfft(window * frames)`` in float64, stored as complex64;
 * ``_spectrogram``: ``np.abs(S) ** 2`` (float32);
 * ``librosa.filters.mel``: Slaney scale, ``norm='slaney'`` triangles (float32), ``np.dot(mel_basis, S)``.
-It is anchored on properties instead (tests/test_wave_frontend.py): Parseval per frame, a pure tone lands in the band that contains it,
-the filterbank's closed form (unit-area triangles, band edges), and agreement with scipy.signal.stft / torch.stft.
+It is anchored instead (tests/test_wave_frontend.py) on two independent implementations -- torch.stft in float64 for framing /
+padding / FFT, and transformers.audio_utils (Hugging Face's librosa-compatible window, Slaney filterbank and mel spectrogram:
+1.7e-7 on the whole spectrogram, 2e-9 on the filterbank) -- and on properties: Parseval per frame, a pure tone lands in the band that
+contains it, the filterbank's closed form (unit-area triangles, band edges).
 """
 import numpy as np
 

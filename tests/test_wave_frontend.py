@@ -42,6 +42,23 @@ def test_oracle_agrees_with_an_independent_stft(pad_mode):
     assert _relmax(want, got) < 2e-6
 
 
+def test_oracle_agrees_with_the_librosa_compatible_implementation_of_transformers():
+    """transformers.audio_utils restates librosa too (its Slaney filterbank and STFT are the ones HF's feature extractors were
+    validated against librosa with) -- a third-party implementation of the same published algorithm, present in this image:
+    window, filterbank and the whole mel spectrogram must agree with the oracle and with the product's host tables."""
+    au = pytest.importorskip("transformers.audio_utils")
+    fb = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=N_MELS, min_frequency=0.0, max_frequency=SR / 2,
+                            sampling_rate=SR, norm="slaney", mel_scale="slaney")
+    assert np.abs(fb.T - fe.mel_filterbank(SR, 2048, N_MELS)).max() < 1e-8
+    win = au.window_function(2048, "hann", periodic=True)
+    assert np.abs(win - fe.hann_periodic(2048)).max() < 1e-12
+    y = _audio(SR * 2 + 123, seed=7)
+    got = au.spectrogram(y.astype(np.float64), win, frame_length=2048, hop_length=HOP, fft_length=2048, power=2.0, center=True,
+                         pad_mode="constant", mel_filters=fb)
+    want = ofe.melspectrogram(y, SR, 2048, HOP, N_MELS, "constant")
+    assert got.shape == want.shape and _relmax(want, got) < 2e-6
+
+
 def test_oracle_frames_satisfy_parseval_and_a_tone_lands_in_its_band():
     y = _audio(HOP * 6, seed=2)
     yp = np.pad(y, 1024)
