@@ -48,7 +48,7 @@ def lib():
 
 def gemm_lib(*defines):
     """The tcgen05 GEMM (gemm_tc.cuh) on the mbarrier / TMA / tcgen05 models of emu_tc_prims.h; `defines` selects an
-    experiment build (e.g. "DSHEG_K512_DEEP=1")."""
+    experiment build (a -D macro of gemm_tc.cuh)."""
     L = _load("emu_gemm", defines)
     L.emu_gemm_last_error.restype = ctypes.c_char_p
     return L
