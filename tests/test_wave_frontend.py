@@ -118,6 +118,27 @@ def test_mel_kernel_source_on_emulator(n, pad_mode):
     assert np.array_equal(out, out2)
 
 
+def test_mel_entry_point_of_the_c_abi_on_the_emulated_library():
+    """dsheg_mel_spectrogram itself (argument checks + launch code of csrc/engine.cu) through ctypes on the emulated library."""
+    import emu
+    L = emu.engine_lib()
+    n = HOP * 2 + 300
+    y = _audio(n, seed=6)
+    win = fe.hann_periodic(2048).astype(np.float32)
+    basis = fe.mel_filterbank(SR, 2048, N_MELS)
+    rng = fe.band_ranges(basis)
+    n_frames = 1 + n // HOP
+    out = np.full((n_frames, N_MELS), np.nan, np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    call = lambda n_fft, pad, frames, samples=n: L.dsheg_mel_spectrogram(P(y), samples, n_fft, HOP, pad, P(win), P(basis), P(rng), N_MELS, P(out), frames, None)   # noqa: E731
+    assert call(2048, 0, n_frames) == 0, L.dsheg_last_error(None)
+    assert _relmax(out, ofe.melspectrogram(y, SR, 2048, HOP, N_MELS).T) < 1e-5
+    assert call(1024, 0, n_frames) != 0 and b"n_fft must be 2048" in L.dsheg_last_error(None)
+    assert call(2048, 2, n_frames) != 0                      # unknown pad mode
+    assert call(2048, 0, n_frames + 1) != 0                  # more frames than 1 + n_samples / hop
+    assert call(2048, 1, 1, samples=900) != 0                # reflect padding needs more than n_fft / 2 samples
+
+
 # ---- the product on a GPU ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("seconds,pad_mode", [(60.0, "constant"), (7.3, "reflect"), (0.2, "constant")])
