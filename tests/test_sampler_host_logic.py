@@ -5,6 +5,7 @@ The CUDA pieces are stubbed: the C-ABI step kernels by torch expressions with th
 (include/diffsheg_b200.h), the engine by the oracle denoiser.  Nothing of the product is modified -- the stubs are
 monkeypatched in -- so this pins everything ABOVE the C ABI on a machine without a GPU.
 """
+import ctypes
 import os
 
 import numpy as np
@@ -88,11 +89,109 @@ class OracleEngine(FusedUniDiffuser):
         return out
 
 
-@pytest.fixture
-def cpu_sampler(monkeypatch):
-    monkeypatch.setattr(D, "_lib", FakeLibModule)
+class EmulatedStepLib:
+    """The REAL sampler-step entry points -- csrc/engine.cu's argument checks and launches, csrc/sampler.cuh's kernels -- compiled for
+    the CPU emulator (tests/emu/emu_engine.cpp).  Tensors arrive in place of device pointers; their host addresses ARE the emulated
+    device addresses."""
+
+    def __init__(self):
+        import emu
+        self.L = emu.engine_lib()
+
+    @staticmethod
+    def _p(t, dtype=torch.float32):
+        if t is None:
+            return None
+        assert t.dtype == dtype and t.is_contiguous() and t.device.type == "cpu", (t.dtype, t.is_contiguous())
+        return ctypes.c_void_p(t.data_ptr())
+
+    def dsheg_ddim_step(self, x, eps, out, n, T, Dm, a, b, sacp, s1m, gt, mask, noise2, blend, ov, pred, stream):
+        p = self._p
+        return self.L.dsheg_ddim_step(p(x), p(eps), p(out), n, T, Dm, a, b, sacp, s1m, p(gt), p(mask, torch.uint8), p(noise2), blend, ov, p(pred), None)
+
+    def dsheg_undo_step(self, x, noise, out, n, c1, c2, stream):
+        p = self._p
+        return self.L.dsheg_undo_step(p(x), p(noise), p(out), n, c1, c2, None)
+
+    def dsheg_ddpm_step(self, x, eps, noise, out, n, a, b, k1, k2, sigma, pred, stream):
+        p = self._p
+        return self.L.dsheg_ddpm_step(p(x), p(eps), p(noise), p(out), n, a, b, k1, k2, sigma, p(pred), None)
+
+    def dsheg_repaint_merge(self, x, gt, mask, noise, out, n, c1, c2, stream):
+        p = self._p
+        return self.L.dsheg_repaint_merge(p(x), p(gt), p(mask, torch.uint8), p(noise), p(out), n, c1, c2, None)
+
+
+class EmulatedLibModule(FakeLibModule):
+    _L = None
+
+    @classmethod
+    def lib(cls):
+        if cls._L is None:
+            cls._L = EmulatedStepLib()
+        return cls._L
+
+
+@pytest.fixture(params=["torch-stubs", "emulated-kernels"])
+def cpu_sampler(monkeypatch, request):
+    """torch-stubs: the step kernels restated in torch (pins the orchestration alone).  emulated-kernels: the product's loops drive the
+    real C entry points and kernel sources on the CPU emulator -- everything of the sampler path but the hardware."""
+    monkeypatch.setattr(D, "_lib", FakeLibModule if request.param == "torch-stubs" else EmulatedLibModule)
     monkeypatch.setattr(D, "_ptr", lambda t: t)
     monkeypatch.setattr(D, "_stream", lambda device=None: None)
+
+
+class EmulatedEngine(FusedUniDiffuser):
+    """The sampler's view of the engine, served by the WHOLE emulated engine (tests/emu: csrc/engine.cu + every kernel on the CPU,
+    behind the production C ABI).  The product's own __call__ / window-cache logic (diffsheg_b200/engine.py) runs unmodified on top."""
+
+    def __init__(self, sd, cfg, precision, max_batch, max_frames):  # no super().__init__: no CUDA library / device
+        import emu
+        self.e = emu.EmuEngine(sd, cfg, precision=precision, max_batch=max_batch, max_frames=max_frames)
+        self.cfg, self.device, self.cond_scale = dict(cfg), torch.device("cpu"), float(cfg["cond_scale"])
+        self.max_batch, self.max_frames, self._window = max_batch, max_frames, None
+
+    def __del__(self):
+        pass
+
+    def prepare_window(self, mel, hubert, person_id):
+        self.e.prepare_window(mel, hubert, person_id)
+        self._window, self._window_key = (mel.shape[0], mel.shape[1]), None
+
+    def denoise(self, x, t_orig, a, b, cond_scale=None, out=None):
+        res = self.e.denoise(x, t_orig, a, b, self.cond_scale if cond_scale is None else cond_scale)
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
+
+
+def test_product_sampling_loop_over_the_emulated_engine_and_step_kernels(monkeypatch):
+    """Everything of the hot path but the hardware: the product's FusedSpacedDiffusion.ddim_sample_loop (Python step loop, host
+    scalars, model(x, ts, **kwargs) protocol and window cache of FusedUniDiffuser.__call__) drives the emulated engine (graph replay
+    from the third call on) and the emulated step kernels, against the oracle's loop on the same x_T.  SHOW under CFG, one layer per
+    net, a 6-step DDIM schedule."""
+    from oracle import diffusion as odiff
+    monkeypatch.setattr(D, "_lib", EmulatedLibModule)
+    monkeypatch.setattr(D, "_ptr", lambda t: t)
+    monkeypatch.setattr(D, "_stream", lambda device=None: None)
+    B, T = 1, 6
+    cfg = synth.make_cfg("show", num_layers=1)
+    sd = synth.make_state_dict(cfg, seed=1)
+    inp = synth.make_inputs(cfg, B, T, seed=2)
+    eng = EmulatedEngine(sd, cfg, "fp32", B, T)
+    replays0 = eng.e.graph_launches()
+    opt = synth.make_opt(cfg, timestep_respacing="ddim6")
+    diff = FusedSpacedDiffusion(space_timesteps(1000, "ddim6"), opt=opt, betas=get_named_beta_schedule("linear", 1000))
+    kw = dict(audio_emb=inp["mel"], length=None, person_id=inp["person_id"], add_cond={"pretrain_aud_feat": inp["hubert"]}, y={}, pe_type="pe_sinu")
+    out = diff.ddim_sample_loop(eng, (B, T, cfg["net_dim_pose"]), noise=inp["x_T"].clone(), clip_denoised=False, model_kwargs=kw)
+    assert diff.last_stats == {"denoise_calls": 6, "undo_steps": 0}
+    assert eng.e.graph_launches() - replays0 == 5          # the first call runs eagerly, the second captures, calls 2 .. 6 replay
+    eng.e.close()
+    with torch.no_grad():
+        den = odiff.make_denoise(sd, cfg, inp["mel"], inp["person_id"], inp["hubert"])
+        want = odiff.OracleDiffusion(1000, "ddim6").ddim_sample_loop(den, (B, T, cfg["net_dim_pose"]), y={}, noise=inp["x_T"].clone())
+    assert relmax(out.numpy(), want.numpy()) < 2e-5
 
 
 def relmax(a, b):
