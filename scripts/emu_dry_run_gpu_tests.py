@@ -3,7 +3,7 @@ kernel behind the production C ABI, graph replay included) stands in for FusedUn
 emulated step-kernel entry points, `.cuda()` is the identity.  Test infrastructure, offline (the pair and loop cases take 8 - 10
 minutes each): it executes the TEST code -- names, keyword arguments, fixtures, gates -- at the GPU sizes before its first hardware run.
 
-    python scripts/emu_dry_run_gpu_tests.py [golden|protocol|pair|loop ...] > profiles/r02/emu/gpu_test_bodies_dry_run.txt
+    python scripts/emu_dry_run_gpu_tests.py [golden|protocol|pair|loop|mel ...] > profiles/r02/emu/gpu_test_bodies_dry_run.txt
 """
 import os
 import sys
@@ -35,6 +35,37 @@ torch.tensor = lambda *a, **k: _tensor(*a, **{kk: v for kk, v in k.items() if kk
 
 import test_variants_gpu as t  # noqa: E402
 
+
+def _mel_cases():
+    """tests/test_wave_frontend.py's GPU tests: diffsheg_b200/frontend.py itself over the emulated dsheg_mel_spectrogram (a Tensor
+    subclass answers is_cuda, torch.cuda.device is a null context)."""
+    import contextlib
+
+    import emu
+    import test_wave_frontend as w
+    from diffsheg_b200 import frontend as fe
+
+    class FakeCuda(torch.Tensor):
+        is_cuda = property(lambda self: True)
+
+    L = emu.engine_lib()
+
+    class LibMod:
+        lib = staticmethod(lambda: L)
+
+        @staticmethod
+        def check(rc, handle=None, what=""):
+            if rc != 0:
+                raise RuntimeError(what + ": " + L.dsheg_last_error(None).decode())
+
+    fe._lib, fe._stream = LibMod, (lambda device=None: None)
+    torch.cuda.device = lambda d: contextlib.nullcontext()
+    torch.Tensor.cuda = lambda self, *a, **k: self.as_subclass(FakeCuda)
+    torch.Tensor.cpu = lambda self, *a, **k: self.as_subclass(torch.Tensor)
+    return [(w.test_mel_spectrogram_matches_oracle, a) for a in ((60.0, "constant"), (7.3, "reflect"), (0.2, "constant"))] + \
+        [(w.test_audio_embedding_is_the_trainers_tensor_and_bad_calls_fail_loudly, ())]
+
+
 CASES = {
     "golden": [(t.test_variant_denoise_matches_reference_golden, (os.path.join(ROOT, "tests", "golden"),) + a) for a in (
         ("beat", "linear_excludeX", False, "bf16"), ("beat", "mlp_includeX", False, "fp32"), ("show", "mlp_excludeX", True, "tf32"))],
@@ -45,7 +76,7 @@ CASES = {
 
 if __name__ == "__main__":
     for kind in (sys.argv[1:] or ["golden", "protocol"]):
-        for fn, args in CASES[kind]:
+        for fn, args in (_mel_cases() if kind == "mel" else CASES[kind]):
             t0 = time.time()
             fn(*args)
             print(f"PASSED on the emulated stack: {fn.__name__}{args[1:] if kind == 'golden' else args}  ({time.time() - t0:.0f} s)", flush=True)
