@@ -132,13 +132,14 @@ struct Cluster {
   Rendezvous rv;          // barrier.cluster (arrive + wait as one rendezvous, or split: see cluster_arrive / cluster_wait)
   uint64_t arrive_gen_seen = 0;
 };
+constexpr size_t kStackBytes = 192 * 1024;
 struct Thread {
 #if EMU_UCONTEXT
   ucontext_t ctx;
 #else
   void* sp = nullptr;
 #endif
-  std::vector<uint8_t> stack;
+  std::unique_ptr<uint8_t[]> stack;   // kStackBytes, uninitialised
   Cta* cta = nullptr;
   uint3 tid{0, 0, 0};
   int lane = 0, warp = 0;
@@ -232,8 +233,11 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
   if (grid_y > 1 && cluster_size != 1) { *err = "2-D grids are emulated for clusters of one CTA only"; return false; }
   const uint32_t grid_total = grid_x * grid_y;
   const size_t nthr = (size_t)cluster_size * block_x;
-  std::vector<std::unique_ptr<Thread>> threads(nthr);
-  for (auto& t : threads) { t.reset(new Thread); t->stack.resize(192 * 1024); }
+  // fiber objects and their 192 KB stacks are pooled across launches (a 768-thread kernel would otherwise allocate and zero 144 MB
+  // per launch); every field a launch reads is re-initialised below, the stacks need no clearing
+  static std::vector<std::unique_ptr<Thread>> pool;
+  while (pool.size() < nthr) { pool.emplace_back(new Thread); pool.back()->stack.reset(new uint8_t[kStackBytes]); }
+  std::vector<std::unique_ptr<Thread>>& threads = pool;
   for (uint32_t c0 = 0; c0 < grid_total; c0 += cluster_size) {
     Cluster cl;
     cl.ctas.resize(cluster_size);
@@ -256,16 +260,17 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
         t.parity = 0;
         t.cluster_wait_gen = 0;
         t.done = false;
+        t.waiting_on = "";
 #if EMU_UCONTEXT
         getcontext(&t.ctx);
-        t.ctx.uc_stack.ss_sp = t.stack.data();
-        t.ctx.uc_stack.ss_size = t.stack.size();
+        t.ctx.uc_stack.ss_sp = t.stack.get();
+        t.ctx.uc_stack.ss_size = kStackBytes;
         t.ctx.uc_link = &R.sched;
         makecontext(&t.ctx, (void (*)())trampoline, 0);
 #else
         {   // initial frame: six zeroed callee-saved registers, the entry point as the return address, then a null return slot at an
             // address = 8 mod 16 (what a function sees right after being called); trampoline() never returns
-          uintptr_t top = (reinterpret_cast<uintptr_t>(t.stack.data()) + t.stack.size()) & ~(uintptr_t)15;
+          uintptr_t top = (reinterpret_cast<uintptr_t>(t.stack.get()) + kStackBytes) & ~(uintptr_t)15;
           void** frame = reinterpret_cast<void**>(top - 64);
           for (int q = 0; q < 8; ++q) frame[q] = nullptr;
           frame[6] = reinterpret_cast<void*>(&trampoline);
@@ -318,9 +323,11 @@ inline bool run_grid(uint32_t grid_x, uint32_t block_x, uint32_t cluster_size, s
       if (remaining && R.progress == before) {
         std::string msg = "deadlock: ";
         int shown = 0;
-        for (auto& tp : threads)
+        for (size_t ti = 0; ti < nthr; ++ti) {
+          auto& tp = threads[ti];
           if (!tp->done && shown++ < 6)
             msg += "[cta " + std::to_string(tp->cta->bid.x) + " thread " + std::to_string(tp->tid.x) + " waits on " + tp->waiting_on + "] ";
+        }
         *err = msg;
         return false;
       }
